@@ -1,0 +1,142 @@
+"""ctypes binding of libscasml_b200.so (include/scasml_b200.h) + device-buffer helpers.
+
+PyTorch is used only to own device memory, pinned host staging buffers and the current stream.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscasml_b200.so")
+
+MAX_LEVEL = 8
+MAX_Q = 8
+EVAL_U, EVAL_TERMINAL, EVAL_UG, EVAL_PDE = 0, 1, 2, 3
+ROUTE_F64, ROUTE_TC = 0, 1
+ERR_NUMERIC = 3
+
+
+class PicardParams(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int), ("scasml", C.c_int), ("n", C.c_int), ("d", C.c_int), ("M", C.c_int), ("qmax", C.c_int),
+        ("Qrow", C.c_int * MAX_LEVEL), ("Mfrow", C.c_int * MAX_LEVEL), ("Mgrow", C.c_int * (MAX_LEVEL + 1)),
+        ("c", C.c_double * (MAX_Q * MAX_Q)), ("w", C.c_double * (MAX_Q * MAX_Q)),
+        ("T", C.c_double), ("mu", C.c_double), ("sigma", C.c_double), ("clip", C.c_double),
+        ("stale_delta", C.c_int), ("cast_levels", C.c_int), ("seed", C.c_uint), ("key_counter", C.c_uint),
+        ("rank", C.c_int), ("world", C.c_int), ("gid0", C.c_longlong),
+    ]
+
+
+class PicardStats(C.Structure):
+    _fields_ = [(n, C.c_longlong) for n in ("keys_used", "eval_counter", "sample_points", "executed_points",
+                                            "n_calls", "launches", "eval_points_total")]
+
+
+_SIGNATURES = {
+    "scasml_last_error": (C.c_char_p, []),
+    "scasml_abi_version": (C.c_int, []),
+    "scasml_set_normal_table": (C.c_int, [C.c_void_p]),
+    "scasml_debug_draw": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "scasml_equation_g": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "scasml_equation_f": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "scasml_gp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double, C.POINTER(C.c_void_p)]),
+    "scasml_gp_destroy": (C.c_int, [C.c_void_p]),
+    "scasml_gp_clone": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "scasml_gp_set_centres": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scasml_gp_set_alpha": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scasml_gp_get_alpha": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scasml_gp_gram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "scasml_gp_fit_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "scasml_gp_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                C.c_size_t, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]),
+    "scasml_gp_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scasml_gp_gradient_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_longlong]),
+    "scasml_gp_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scasml_picard_plan": (C.c_int, [C.POINTER(PicardParams), C.c_longlong, C.POINTER(C.c_size_t), C.POINTER(PicardStats)]),
+    "scasml_uz_solve": (C.c_int, [C.c_void_p, C.POINTER(PicardParams), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.POINTER(PicardStats), C.c_void_p]),
+    "scasml_clip": (C.c_int, [C.c_void_p, C.c_longlong, C.c_double, C.c_void_p]),
+    "scasml_debug_spd_inverse": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scasml_debug_lu_solve": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+_table_devices = set()
+
+
+class ScasmlError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the compiled library; raises if it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScasmlError(
+            f"{LIB_PATH} is missing: build it with `python -m scasml_gp_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().scasml_last_error()
+    msg = msg.decode() if msg else "unknown error"
+    if rc == ERR_NUMERIC:
+        raise ValueError(msg)                      # mirrors models/GP.py:264-265
+    raise ScasmlError(f"libscasml_b200 status {rc}: {msg}")
+
+
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise ScasmlError("a CUDA device (B200, sm_100a) is required: this path has no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    torch = torch_cuda()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def normal_half_table():
+    """T[i] = float16(ndtri(0.5 + (i + 0.5)/65536)): the sampler's inverse-CDF table (see csrc/common.cuh)."""
+    from scipy.special import ndtri
+    i = np.arange(32768, dtype=np.float64)
+    return ndtri(0.5 + (i + 0.5) / 65536.0).astype(np.float16)
+
+
+def ensure_normal_table():
+    torch = torch_cuda()
+    dev = torch.cuda.current_device()
+    if dev in _table_devices:
+        return
+    tab = np.ascontiguousarray(normal_half_table().view(np.uint16))
+    check(load().scasml_set_normal_table(tab.ctypes.data_as(C.c_void_p)))
+    _table_devices.add(dev)
+
+
+def to_device(a, pinned=True):
+    """NumPy (any float dtype) -> contiguous float64 CUDA tensor, staged through pinned memory."""
+    torch = torch_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=torch.float64).contiguous()
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    t = torch.from_numpy(a)
+    if pinned and a.size:
+        t = t.pin_memory()
+    return t.to("cuda", non_blocking=True)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)

@@ -1,0 +1,340 @@
+// extern "C" entry points of libscasml_b200.so (declared in include/scasml_b200.h).
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+#include "../../include/scasml_b200.h"
+#include "common.cuh"
+#include "gp.cuh"
+#include "gp_fit.cuh"
+#include "picard.cuh"
+
+static_assert(sizeof(scasml_picard_params) == sizeof(scasml::PicardParams), "ABI struct mismatch");
+static_assert(sizeof(scasml_picard_stats) == sizeof(scasml::PicardStats), "ABI struct mismatch");
+static_assert(SCASML_MAX_LEVEL == scasml::MAX_LEVEL && SCASML_MAX_Q == scasml::MAX_Q, "ABI constants");
+static_assert(sizeof(scasml::LevelDev) <= 4000, "LevelDev must fit the kernel parameter space");
+
+namespace scasml {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+static __half* g_ntab[64] = {nullptr};
+
+static const __half* normal_table_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return g_ntab[dev];
+}
+
+namespace {
+
+__global__ void debug_draw_kernel(PhiloxKey key, unsigned long long start, long long count, int uniform,
+                                  const __half* __restrict__ tab, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t c = chunk16(start + (unsigned long long)i, key);
+    out[i] = uniform ? chunk_to_uniform(c) : chunk_to_normal(tab, c);
+}
+
+__global__ void equation_g_kernel(const double* __restrict__ x, long long R, int d, double* __restrict__ out) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const double* p = x + r * (d + 1);
+    double acc = 0.0;
+    for (int j = lane; j <= d; j += 32) acc += p[j];
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = 1.0 - 1.0 / (1.0 + exp(acc));
+}
+
+__global__ void equation_f_kernel(const double* __restrict__ u, const double* __restrict__ z, long long R, int d,
+                                  double sigma, double* __restrict__ out) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const double* p = z + r * d;
+    double acc = 0.0;
+    for (int j = lane; j < d; j += 32) acc += p[j];
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = sigma * u[r] * acc;
+}
+
+__global__ void clip_kernel(double* __restrict__ x, long long n, double c) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    x[i] = (v < -c) ? -c : ((v > c) ? c : v);
+}
+
+__global__ void add_diag_kernel(double* K, long n, double v) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) K[i * n + i] += v;
+}
+
+}  // namespace
+}  // namespace scasml
+
+using namespace scasml;
+
+struct scasml_gp {
+    GpView v{};
+    double nugget = 1e-2;
+    double sigma_eq = 0.25;
+    double* C = nullptr;      // [NdPad + NbPad][D]
+    double* feat = nullptr;   // [NdPad + NbPad][CF_STRIDE]
+    double* alpha = nullptr;  // [4 Nd + Nb]
+    bool has_centres = false, has_alpha = false;
+    long phi() const { return 4L * v.Nd + v.Nb; }
+    long ncpad() const { return (long)v.NdPad + v.NbPad; }
+};
+
+static int gp_alloc(scasml_gp* g) {
+    const long nc = g->ncpad();
+    SC_CUDA(cudaMalloc(&g->C, (size_t)nc * g->v.D * sizeof(double)));
+    SC_CUDA(cudaMalloc(&g->feat, (size_t)nc * CF_STRIDE * sizeof(double)));
+    SC_CUDA(cudaMalloc(&g->alpha, (size_t)g->phi() * sizeof(double)));
+    SC_CUDA(cudaMemset(g->C, 0, (size_t)nc * g->v.D * sizeof(double)));
+    SC_CUDA(cudaMemset(g->feat, 0, (size_t)nc * CF_STRIDE * sizeof(double)));
+    SC_CUDA(cudaMemset(g->alpha, 0, (size_t)g->phi() * sizeof(double)));
+    g->v.C = g->C; g->v.feat = g->feat;
+    return OK;
+}
+
+extern "C" {
+
+const char* scasml_last_error(void) { return last_error_cstr(); }
+int scasml_abi_version(void) { return SCASML_ABI_VERSION; }
+
+int scasml_set_normal_table(const uint16_t* half_bits_host) {
+    SC_REQUIRE(half_bits_host != nullptr, "normal table is null");
+    int dev = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_REQUIRE(dev >= 0 && dev < 64, "device index");
+    if (!g_ntab[dev]) SC_CUDA(cudaMalloc(&g_ntab[dev], 32768 * sizeof(__half)));
+    SC_CUDA(cudaMemcpy(g_ntab[dev], half_bits_host, 32768 * sizeof(__half), cudaMemcpyHostToDevice));
+    return OK;
+}
+
+int scasml_debug_draw(unsigned stream_id, unsigned domain, unsigned seed, long long start, long long count,
+                      int uniform, double* out_dev, void* stream) {
+    const __half* tab = normal_table_for_current_device();
+    SC_REQUIRE(tab != nullptr, "normal table not set");
+    if (count <= 0) return OK;
+    debug_draw_kernel<<<(unsigned)cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(
+        make_key(stream_id, domain, seed), (unsigned long long)start, count, uniform, tab, out_dev);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int scasml_equation_g(const double* x_t_dev, long long R, int d, double* out_dev, void* stream) {
+    if (R <= 0) return OK;
+    equation_g_kernel<<<(unsigned)cdiv(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(x_t_dev, R, d, out_dev);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int scasml_equation_f(const double* u_dev, const double* z_dev, long long R, int d, double sigma, double* out_dev,
+                      void* stream) {
+    if (R <= 0) return OK;
+    equation_f_kernel<<<(unsigned)cdiv(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(u_dev, z_dev, R, d, sigma, out_dev);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int scasml_gp_create(int d, int n_dom, int n_bdy, const int* idx_set5, double kernel_a, double sigma_eq,
+                     double nugget, scasml_gp** out) {
+    SC_REQUIRE(out != nullptr, "gp_create: out is null");
+    SC_REQUIRE(d >= 2 && n_dom >= 1 && n_bdy >= 0, "gp_create: sizes");
+    SC_REQUIRE(idx_set5 != nullptr, "gp_create: idx_set is null");
+    for (int m = 0; m < MC_IDX; ++m) SC_REQUIRE(idx_set5[m] >= 0 && idx_set5[m] < d, "gp_create: idx_set out of range");
+    scasml_gp* g = new (std::nothrow) scasml_gp();
+    SC_REQUIRE(g != nullptr, "gp_create: out of host memory");
+    g->v.d = d; g->v.D = d + 1; g->v.Nd = n_dom; g->v.Nb = n_bdy;
+    g->v.NdPad = (int)(cdiv(n_dom, CENTRE_PAD) * CENTRE_PAD);
+    g->v.NbPad = (int)(cdiv(n_bdy, CENTRE_PAD) * CENTRE_PAD);
+    g->v.a = kernel_a; g->v.sig2 = sigma_eq * sigma_eq;
+    for (int m = 0; m < MC_IDX; ++m) g->v.I[m] = idx_set5[m];
+    g->nugget = nugget; g->sigma_eq = sigma_eq;
+    const int rc = gp_alloc(g);
+    if (rc != OK) { scasml_gp_destroy(g); return rc; }
+    *out = g;
+    return OK;
+}
+
+int scasml_gp_destroy(scasml_gp* g) {
+    if (!g) return OK;
+    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha);
+    delete g;
+    return OK;
+}
+
+int scasml_gp_clone(const scasml_gp* src, scasml_gp** out) {
+    SC_REQUIRE(src && out, "gp_clone: null");
+    scasml_gp* g = new (std::nothrow) scasml_gp();
+    SC_REQUIRE(g != nullptr, "gp_clone: out of host memory");
+    g->v = src->v; g->nugget = src->nugget; g->sigma_eq = src->sigma_eq;
+    g->has_centres = src->has_centres; g->has_alpha = src->has_alpha;
+    g->C = nullptr; g->feat = nullptr; g->alpha = nullptr;
+    int rc = gp_alloc(g);
+    if (rc != OK) { scasml_gp_destroy(g); return rc; }
+    const long nc = g->ncpad();
+    SC_CUDA(cudaMemcpy(g->C, src->C, (size_t)nc * g->v.D * sizeof(double), cudaMemcpyDeviceToDevice));
+    SC_CUDA(cudaMemcpy(g->feat, src->feat, (size_t)nc * CF_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice));
+    SC_CUDA(cudaMemcpy(g->alpha, src->alpha, (size_t)g->phi() * sizeof(double), cudaMemcpyDeviceToDevice));
+    *out = g;
+    return OK;
+}
+
+int scasml_gp_set_centres(scasml_gp* g, const double* x_dom_dev, const double* x_bdy_dev, void* stream) {
+    SC_REQUIRE(g && x_dom_dev && (x_bdy_dev || g->v.Nb == 0), "gp_set_centres: null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = g->v.D;
+    SC_CUDA(cudaMemsetAsync(g->C, 0, (size_t)g->ncpad() * D * sizeof(double), st));
+    SC_CUDA(cudaMemcpyAsync(g->C, x_dom_dev, (size_t)g->v.Nd * D * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (g->v.Nb > 0)
+        SC_CUDA(cudaMemcpyAsync(g->C + (size_t)g->v.NdPad * D, x_bdy_dev, (size_t)g->v.Nb * D * sizeof(double),
+                                cudaMemcpyDeviceToDevice, st));
+    g->has_centres = true; g->has_alpha = false;
+    return build_centre_features(g->v, nullptr, g->feat, st);
+}
+
+int scasml_gp_set_alpha(scasml_gp* g, const double* alpha_dev, void* stream) {
+    SC_REQUIRE(g && alpha_dev, "gp_set_alpha: null");
+    SC_REQUIRE(g->has_centres, "gp_set_alpha: centres not set");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (alpha_dev != g->alpha)
+        SC_CUDA(cudaMemcpyAsync(g->alpha, alpha_dev, (size_t)g->phi() * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    g->has_alpha = true;
+    return build_centre_features(g->v, g->alpha, g->feat, st);
+}
+
+int scasml_gp_get_alpha(const scasml_gp* g, double* alpha_dev, void* stream) {
+    SC_REQUIRE(g && alpha_dev, "gp_get_alpha: null");
+    SC_CUDA(cudaMemcpyAsync(alpha_dev, g->alpha, (size_t)g->phi() * sizeof(double), cudaMemcpyDeviceToDevice,
+                            (cudaStream_t)stream));
+    return OK;
+}
+
+int scasml_gp_gram(const scasml_gp* g, double* K_dev, int f16_entries, int add_nugget, void* stream) {
+    SC_REQUIRE(g && K_dev, "gp_gram: null");
+    SC_REQUIRE(g->has_centres, "gp_gram: centres not set");
+    return gram_assemble(g->v, K_dev, add_nugget ? g->nugget : 0.0, f16_entries, (cudaStream_t)stream);
+}
+
+size_t scasml_gp_fit_workspace_bytes(const scasml_gp* g) { return g ? fit_workspace_bytes(g->v.Nd, g->v.Nb) : 0; }
+
+int scasml_gp_fit(scasml_gp* g, const double* g_bdy_dev, const double* sol0_dev, int gn_steps, double damping,
+                  double tol, int f16_gram, void* ws_dev, size_t ws_bytes, double* sol_out_dev,
+                  double* loss_hist_host, int* steps_done, void* stream) {
+    SC_REQUIRE(g && sol0_dev && ws_dev && loss_hist_host && steps_done, "gp_fit: null");
+    SC_REQUIRE(g_bdy_dev || g->v.Nb == 0, "gp_fit: g_bdy is null");
+    SC_REQUIRE(g->has_centres, "gp_fit: centres not set");
+    SC_REQUIRE(gn_steps >= 0, "gp_fit: gn_steps");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = gp_fit_device(g->v, g_bdy_dev, sol0_dev, gn_steps, damping, tol, g->nugget, f16_gram, ws_dev, ws_bytes,
+                           g->alpha, sol_out_dev, loss_hist_host, steps_done, st);
+    if (rc != OK) return rc;
+    return scasml_gp_set_alpha(g, g->alpha, stream);
+}
+
+int scasml_gp_eval(const scasml_gp* g, const double* X_dev, long long R, int mode, int route, double* out0_dev,
+                   double* out1_dev, double* out2_dev, double* out3_dev, void* stream) {
+    SC_REQUIRE(g != nullptr, "gp_eval: null handle");
+    SC_REQUIRE(g->has_alpha, "gp_eval: GP is not fitted (call GPsolver first)");
+    if (route == SCASML_ROUTE_TC)
+        return launch_eval_tc(g->v, nullptr, X_dev, (long)R, mode, out0_dev, out1_dev, out2_dev, out3_dev, (cudaStream_t)stream);
+    SC_REQUIRE(route == SCASML_ROUTE_F64, "gp_eval: unknown route");
+    return launch_eval_f64(g->v, X_dev, (long)R, mode, out0_dev, out1_dev, out2_dev, out3_dev, (cudaStream_t)stream);
+}
+
+size_t scasml_gp_gradient_workspace_bytes(const scasml_gp* g, long long R) {
+    return g ? gradient_scratch_bytes(g->v, (long)R) : 0;
+}
+
+int scasml_gp_gradient(const scasml_gp* g, const double* X_dev, long long R, double* grad_dev, void* ws_dev,
+                       size_t ws_bytes, void* stream) {
+    SC_REQUIRE(g && X_dev && grad_dev && ws_dev, "gp_gradient: null");
+    SC_REQUIRE(g->has_alpha, "gp_gradient: GP is not fitted");
+    return launch_gradient_f64(g->v, X_dev, (long)R, grad_dev, (double*)ws_dev, ws_bytes, (cudaStream_t)stream);
+}
+
+int scasml_picard_plan(const scasml_picard_params* p, long long B, size_t* ws_bytes, scasml_picard_stats* stats) {
+    SC_REQUIRE(p != nullptr, "picard_plan: null params");
+    PicardParams pp;
+    std::memcpy(&pp, p, sizeof(pp));
+    PicardPlan plan;
+    const int rc = plan.build(pp, (long)B);
+    if (rc != OK) return rc;
+    if (ws_bytes) *ws_bytes = plan.workspace_bytes();
+    if (stats) std::memcpy(stats, &plan.stats(), sizeof(PicardStats));
+    return OK;
+}
+
+int scasml_uz_solve(const scasml_gp* g, const scasml_picard_params* p, int route, const double* x_t_dev, long long B,
+                    double* out_uz_dev, void* ws_dev, size_t ws_bytes, scasml_picard_stats* stats, void* stream) {
+    SC_REQUIRE(p && x_t_dev && out_uz_dev && ws_dev, "uz_solve: null");
+    PicardParams pp;
+    std::memcpy(&pp, p, sizeof(pp));
+    SC_REQUIRE(!pp.scasml || (g && g->has_alpha), "uz_solve: ScaSML needs a fitted GP");
+    SC_REQUIRE(!pp.scasml || g->v.d == pp.d, "uz_solve: dimension mismatch between GP and params");
+    PicardPlan plan;
+    int rc = plan.build(pp, (long)B);
+    if (rc != OK) return rc;
+    PicardStats st;
+    rc = plan.run(g ? &g->v : nullptr, route, x_t_dev, out_uz_dev, ws_dev, ws_bytes, normal_table_for_current_device(),
+                  (cudaStream_t)stream, &st);
+    if (rc != OK) return rc;
+    if (stats) std::memcpy(stats, &st, sizeof(st));
+    return OK;
+}
+
+int scasml_clip(double* x_dev, long long count, double c, void* stream) {
+    if (count <= 0) return OK;
+    clip_kernel<<<(unsigned)cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, count, c);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int scasml_debug_spd_inverse(double* A_dev, long long n, double* P_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const long nblk = cdiv(n, 64);
+    const size_t need = ((size_t)n * n + (size_t)nblk * 64 * 64 + 64 * (size_t)n) * 8 + 1024;
+    SC_REQUIRE(ws_bytes >= need, "debug_spd_inverse: workspace too small");
+    double* X = (double*)ws_dev;
+    double* invd = X + (size_t)n * n;
+    double* tmp = invd + (size_t)nblk * 64 * 64;
+    int* d_fail = (int*)(tmp + 64 * (size_t)n);
+    SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+    int rc = cholesky_lower(A_dev, (long)n, invd, d_fail, st);
+    if (rc != OK) return rc;
+    rc = tri_inverse_lower(A_dev, (long)n, invd, X, tmp, st);
+    if (rc != OK) return rc;
+    rc = dgemm((int)n, (int)n, (int)n, 1.0, X, 1, n, X, n, 1, 0.0, P_dev, n, 0, st);
+    if (rc != OK) return rc;
+    int h_fail = 0;
+    SC_CUDA(cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SC_CUDA(cudaStreamSynchronize(st));
+    if (h_fail) { set_error("matrix is not positive definite"); return ERR_NUMERIC; }
+    return OK;
+}
+
+int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_fail = nullptr;
+    SC_CUDA(cudaMalloc(&d_fail, sizeof(int)));
+    SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+    int rc = lu_solve_inplace(A_dev, (long)n, rhs_dev, d_fail, st);
+    int h_fail = 0;
+    if (rc == OK) {
+        cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    cudaFree(d_fail);
+    if (rc != OK) return rc;
+    if (h_fail) { set_error("singular matrix in LU"); return ERR_NUMERIC; }
+    return OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,583 @@
+// Flattened multilevel-Picard recursion on the device (sm_100a).
+//
+// The reference walks the Picard tree depth-first in Python, one batch of XLA ops per uz_solve call
+// (solvers/ScaSML.py:149-305; 473 calls at n = rho = 4).  Here the tree is enumerated once on the host
+// (PicardPlan::build), every call of one level is packed into a single level-wise batch, and a level costs
+//   sampler kernels  : Philox increments + path/terminal points (sample_terminal_kernel, sample_paths_kernel)
+//   evaluation       : fused surrogate kernels over the level's whole point buffer (gp_eval*.cu)
+//   one reduction    : warp-per-row Monte-Carlo means, weights, clip (reduce_kernel)
+// Levels are sampled top-down (children's rows are the parents' sample points) and reduced bottom-up.
+#include <algorithm>
+#include <cstring>
+#include "picard.cuh"
+
+namespace scasml {
+
+// ------------------------------------------------------------------ plan (host) --------------------------
+
+int PicardPlan::q_of(int L, int l) const { return p_.variant == 0 ? p_.Qrow[L - l - 1] : 1; }
+int PicardPlan::mcf_of(int L, int l) const {
+    if (p_.variant == 0) return p_.Mfrow[L - l - 1];
+    long long v = 1;
+    for (int i = 0; i < L - l; ++i) v *= p_.M;
+    return (int)v;
+}
+int PicardPlan::mcg_of(int L) const {
+    if (p_.variant == 0) return p_.Mgrow[L];
+    long long v = 1;
+    for (int i = 0; i < L; ++i) v *= p_.M;
+    return (int)v;
+}
+long long PicardPlan::owned(long long units, bool strided) const {
+    if (!strided) return units;
+    return units > p_.rank ? (units - p_.rank + p_.world - 1) / p_.world : 0;
+}
+
+namespace {
+struct Mult { long long v; };
+}
+
+// mult = rows per test point in the unsharded tree (for the reference-equivalent sample-point count)
+static void level0_counters(const PicardParams& p, PicardStats& st, long long mult, int mcg0) {
+    st.eval_counter += (p.scasml ? 1 : 0) + mcg0;          // g() call + "+= MC_g" (solvers/ScaSML.py:59,205)
+    st.sample_points += mult * mcg0;                        // drawn and discarded by the reference (:190-219)
+}
+
+int PicardPlan::add_call(int level, long long nrows, int parent, int pl, int pk) {
+    const int idx = (int)calls_.size();
+    calls_.emplace_back();
+    {
+        CallRec& r = calls_[idx];
+        std::memset(&r, 0, sizeof(r));
+        r.level = level; r.nrows = nrows; r.parent = parent; r.pl = pl; r.pk = pk;
+        r.rowbase = levels_[level].NR;
+        for (int i = 0; i < MAXLK; ++i) { r.child[i][0] = -1; r.child[i][1] = -1; }
+    }
+    levels_[level].NR += nrows;
+    levels_[level].calls.push_back(idx);
+    return idx;
+}
+
+int PicardPlan::build(const PicardParams& p, long B) {
+    p_ = p; B_ = B;
+    SC_REQUIRE(p.n >= 0 && p.n <= MAX_LEVEL, "picard: level n out of range");
+    SC_REQUIRE(p.d >= 1, "picard: d");
+    SC_REQUIRE(p.world >= 1 && p.rank >= 0 && p.rank < p.world, "picard: rank/world");
+    SC_REQUIRE(B >= 0, "picard: B");
+    if (p.variant == 0) {
+        SC_REQUIRE(p.qmax >= 1 && p.qmax <= MAX_Q, "picard: qmax out of range");
+        for (int i = 0; i < p.n; ++i) {
+            SC_REQUIRE(p.Qrow[i] >= 1 && p.Qrow[i] <= p.qmax, "picard: Q entry out of range");
+            SC_REQUIRE(p.Mfrow[i] >= 1, "picard: Mf entry");
+        }
+        for (int i = 0; i <= p.n; ++i) SC_REQUIRE(p.Mgrow[i] >= 1, "picard: Mg entry");
+    } else {
+        SC_REQUIRE(p.M >= 1, "picard: M");
+    }
+    calls_.clear();
+    levels_.assign(MAX_LEVEL + 1, LevelRec());
+    stats_ = PicardStats();
+    keyctr_ = p.key_counter;
+    if (p.n == 0) {                       // uz_solve(0, ...) returns zeros after the discarded terminal work
+        level0_counters(p_, stats_, 1, mcg_of(0));
+        ws_bytes_ = 256;
+        return OK;
+    }
+
+    // depth-first enumeration in the reference's execution order (key assignment = order of random.split)
+    struct Frame { int call; long long mult; };
+    // recursion via explicit lambda
+    struct Rec {
+        PicardPlan* self;
+        void go(int idx, long long mult) {
+            PicardPlan& P = *self;
+            const PicardParams& p = P.p_;
+            const int L = P.calls_[idx].level;
+            const long long nrows = P.calls_[idx].nrows;
+            const int mcg = P.mcg_of(L);
+            const bool strided = (L == p.n) && p.world > 1;
+            P.stats_.eval_counter += (p.scasml ? 1 : 0) + mcg;
+            P.stats_.sample_points += mult * mcg;
+            P.stats_.n_calls += 1;
+            for (int l = 0; l < L; ++l) {
+                const int q = P.q_of(L, l), mcf = P.mcf_of(L, l);
+                const long long npts = P.owned(nrows * mcf, strided);
+                for (int k = 0; k < q; ++k) {
+                    const int lk = l * MAX_Q + k;
+                    if (p.variant == 0) P.calls_[idx].key[lk] = P.keyctr_++;
+                    P.stats_.sample_points += mult * mcf;
+                    const long long fcount = (p.variant == 0) ? mcf : (p.scasml ? mcg : mcf);  // quirk A.3-7
+                    for (int role = 0; role < 2; ++role) {
+                        const int cl = l - role;                 // child level: l, then l-1
+                        if (role == 1 && l == 0) break;
+                        if (cl >= 1) {
+                            const int ci = P.add_call(cl, npts, idx, l, k);
+                            P.calls_[idx].child[lk][role] = ci;
+                            go(ci, mult * mcf);
+                        } else {
+                            level0_counters(p, P.stats_, mult * mcf, P.mcg_of(0));
+                        }
+                        P.stats_.eval_counter += (p.scasml ? 1 : 0) + fcount;   // f() call + "+= MC_f"
+                    }
+                }
+            }
+        }
+    } rec{this};
+    const int top = add_call(p.n, B, -1, 0, 0);
+    rec.go(top, 1);
+    stats_.keys_used = (long long)(keyctr_ - p.key_counter);
+
+    // layout
+    const int D = p.d + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    long long executed = 0;
+    for (int L = 1; L <= p.n; ++L) {
+        LevelRec& lv = levels_[L];
+        const bool strided = (L == p.n) && p.world > 1;
+        lv.NT = owned(lv.NR * mcg_of(L), strided);
+        long long pt = 0;
+        lv.term_off = pt; pt += lv.NT;
+        lv.ug_off = pt;
+        for (int l = 1; l < L; ++l) {
+            lv.NP[l] = owned(lv.NR * mcf_of(L, l), strided);
+            for (int k = 0; k < q_of(L, l); ++k) { lv.set_off[l * MAX_Q + k] = pt; pt += lv.NP[l]; }
+        }
+        lv.n_ug = pt - lv.ug_off;
+        lv.pde_off = pt;
+        // MLP never reads its level-0 step points (f(x,0,0) = 0 and the level-0 children return zeros)
+        lv.NP[0] = p.scasml ? owned(lv.NR * mcf_of(L, 0), strided) : 0;
+        for (int k = 0; k < q_of(L, 0); ++k) { lv.set_off[k] = pt; pt += lv.NP[0]; }
+        lv.n_pde = pt - lv.pde_off;
+        lv.npoints = pt;
+        executed += pt;
+        lv.off_P = take((size_t)pt * D * sizeof(double));
+        lv.off_gid = take((size_t)pt * sizeof(long long));
+        lv.off_ev0 = take((size_t)pt * sizeof(double));
+        lv.off_ev1 = take((size_t)pt * sizeof(double));
+        lv.off_us = take((size_t)lv.NR * 2 * sizeof(double));
+        lv.off_calls = take(lv.calls.size() * sizeof(CallDev));
+    }
+    stats_.executed_points = executed;
+    ws_bytes_ = off + 256;
+    return OK;
+}
+
+// ------------------------------------------------------------------ kernels -------------------------------
+
+namespace {
+
+__device__ __forceinline__ int find_call(const LevelDev& lv, long long R) {
+    int lo = 0, hi = lv.ncalls - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (lv.calls[mid].rowbase <= R) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ long long ceil_div_pos(long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; }
+
+// terminal points X_T = x + mu (T-t) + sigma sqrt(T-t) N   (solvers/ScaSML.py:190-198)
+__global__ void __launch_bounds__(256) sample_terminal_kernel(LevelDev lv) {
+    const int d = lv.d, D = lv.D;
+    const int nslot = (d + 14) / 8;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = tid / nslot;
+    const int b = (int)(tid % nslot);
+    if (s >= lv.NT) return;
+    const long long u = lv.rank + (long long)lv.world * s;
+    const long long R = u / lv.MCg;
+    const int m = (int)(u - R * lv.MCg);
+    const CallDev& c = lv.calls[find_call(lv, R)];
+    const long long i = R - c.rowbase;
+    const double* x = c.xsrc + i * D;
+    const long long gidrow = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
+    const double t = x[d];
+    const double Tt = lv.T - t, sq = sqrt(Tt), drift = lv.mu * Tt;
+    const unsigned long long f0 = (unsigned long long)(gidrow * lv.MCg + m) * (unsigned long long)d;
+    const unsigned long long blk = (f0 >> 3) + (unsigned long long)b;
+    const uint4 w = philox4x32_10(blk, make_key(0u, 0u, lv.seed));
+    double* dst = lv.P + (lv.term_off + s) * D;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const long long j = (long long)(blk * 8ull + e) - (long long)f0;
+        if (j >= 0 && j < d) {
+            const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
+            dst[j] = (x[j] + drift) + lv.sigma * (sq * N);
+        }
+    }
+    if (b == 0) dst[d] = lv.T;
+}
+
+// interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
+__global__ void __launch_bounds__(256) sample_paths_kernel(LevelDev lv, int l) {
+    const int d = lv.d, D = lv.D;
+    const int nslot = (d + 14) / 8;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = tid / nslot;
+    const int b = (int)(tid % nslot);
+    if (s >= lv.NP[l]) return;
+    const int MCf = lv.MCf[l];
+    const long long u = lv.rank + (long long)lv.world * s;
+    const long long R = u / MCf;
+    const int m = (int)(u - R * MCf);
+    const CallDev& c = lv.calls[find_call(lv, R)];
+    const long long i = R - c.rowbase;
+    const double* x = c.xsrc + i * D;
+    const long long gidrow = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
+    const double t = x[d];
+    const long long pgid = gidrow * MCf + m;
+    const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
+    const unsigned long long blk = (f0 >> 3) + (unsigned long long)b;
+    double Xr[8];
+    bool ok[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const long long j = (long long)(blk * 8ull + e) - (long long)f0;
+        ok[e] = (j >= 0 && j < d);
+        Xr[e] = ok[e] ? x[j] : 0.0;
+    }
+    const long long jbase = (long long)(blk * 8ull) - (long long)f0;
+    if (lv.variant == 0) {
+        double tprev = t;
+        const int q = lv.q[l];
+        for (int k = 0; k < q; ++k) {
+            const int lk = l * MAX_Q + k;
+            const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
+            const double dk = __dsub_rn(tk, tprev);
+            const double sq = sqrt(dk), drift = lv.mu * dk;
+            const uint4 w = philox4x32_10(blk, make_key(c.key[lk], 1u, lv.seed));
+            double* dst = lv.P + (lv.set_off[lk] + s) * D;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (ok[e]) {
+                    const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
+                    Xr[e] = Xr[e] + (drift + lv.sigma * (sq * N));
+                    dst[jbase + e] = Xr[e];
+                }
+            }
+            if (b == 0) { dst[d] = tk; lv.gid[lv.set_off[lk] + s] = pgid; }
+            tprev = tk;
+        }
+    } else {
+        const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+        const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
+        const double steps = tau * (lv.T - t);
+        const double sq = sqrt(steps), drift = lv.mu * steps;
+        const uint4 w = philox4x32_10(blk, kT);
+        double* dst = lv.P + (lv.set_off[l * MAX_Q] + s) * D;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (ok[e]) {
+                const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
+                dst[jbase + e] = Xr[e] + (drift + lv.sigma * (sq * N));
+            }
+        }
+        if (b == 0) { dst[d] = t + steps; lv.gid[lv.set_off[l * MAX_Q] + s] = pgid; }
+    }
+}
+
+// MLP terminal values g(X_T) (solvers/MLP.py:42-55): one warp per terminal point
+__global__ void __launch_bounds__(256) mlp_terminal_kernel(LevelDev lv) {
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= lv.NT) return;
+    const double* x = lv.P + (lv.term_off + s) * lv.D;
+    double acc = 0.0;
+    for (int j = lane; j < lv.D; j += 32) acc += x[j];           // t + sum_i x_i
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) lv.ev0[lv.term_off + s] = 1.0 - 1.0 / (1.0 + exp(acc));
+}
+
+__device__ __forceinline__ double clip_keep_nan(double v, double c) { return (v < -c) ? -c : ((v > c) ? c : v); }
+
+// Monte-Carlo means of one level: terminal part + all step sets + clip (solvers/ScaSML.py:211-215,252-284)
+template <int JCH>
+__global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
+    const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (R >= lv.NR) return;
+    const int d = lv.d, D = lv.D, L = lv.L;
+    const CallDev& c = lv.calls[find_call(lv, R)];
+    const long long irow = R - c.rowbase;
+    const double* x = c.xsrc + irow * D;
+    const long long gidrow = c.gidsrc ? c.gidsrc[irow] : lv.gid0 + irow;
+    const double t = x[d], T = lv.T, Tt = T - t;
+    const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+    const long long world = lv.world, rank = lv.rank;
+
+    double zs = 0.0, uacc = 0.0;
+    const bool top = (lv.out_uz != nullptr);
+    // coordinates are processed in passes of 32*JCH so the per-lane accumulators stay in registers
+    for (int jpass = 0; jpass < d; jpass += 32 * JCH) {
+    double zacc[JCH];
+#pragma unroll
+    for (int i = 0; i < JCH; ++i) zacc[i] = 0.0;
+    uacc = 0.0;
+
+    {   // terminal condition
+        const int MCg = lv.MCg;
+        const long long s_lo = ceil_div_pos(R * MCg - rank, world), s_hi = ceil_div_pos((R + 1) * MCg - rank, world);
+        for (long long s = s_lo; s < s_hi; ++s) {
+            const int m = (int)(rank + world * s - R * MCg);
+            const double gt = lv.ev0[lv.term_off + s];
+            const unsigned long long f0 = (unsigned long long)(gidrow * MCg + m) * (unsigned long long)d;
+#pragma unroll
+            for (int i = 0; i < JCH; ++i) {
+                const int j = jpass + lane + 32 * i;
+                if (j < d) zacc[i] = fma(gt, chunk_to_normal(lv.ntab, chunk16(f0 + j, kT)), zacc[i]);
+            }
+            uacc += gt;
+        }
+        const double delta0 = (lv.variant == 0) ? (Tt + 1e-6) : Tt;    // ScaSML.py:213 vs ScaSML_full_history.py:133
+        uacc = uacc / MCg;
+#pragma unroll
+        for (int i = 0; i < JCH; ++i) zacc[i] = zacc[i] / MCg / delta0;
+    }
+
+    double delta = Tt + 1e-6;                  // running delta_t of solvers/MLP.py (stale-delta quirk)
+    const double sig = lv.sigma;
+    for (int l = 0; l < L; ++l) {
+        const int q = lv.q[l], MCf = lv.MCf[l];
+        double sqk[MAX_Q], cu[MAX_Q], ca[MAX_Q], cs[MAX_Q];
+        if (lv.variant == 0) {
+            double tprev = t;
+            for (int k = 0; k < q; ++k) {
+                const int lk = l * MAX_Q + k;
+                const double tk = cloc_of(T, t, lv.cnode[lk]);
+                sqk[k] = sqrt(__dsub_rn(tk, tprev));
+                tprev = tk;
+                const double wk = wloc_of(T, t, lv.wnode[lk]);
+                const double dnew = (tk - t) + 1e-6;
+                const double dadd = lv.stale_delta ? delta : dnew;
+                if (!lv.stale_delta || l >= 1) delta = dnew;
+                cu[k] = wk / MCf;
+                ca[k] = wk / (MCf * dadd);
+                cs[k] = wk / (MCf * delta);
+            }
+        }
+        if (!lv.scasml && l == 0) continue;       // MLP: f(x, 0, 0) = 0 at level 0, nothing to add (solvers/MLP.py:243)
+        const long long s_lo = ceil_div_pos(R * MCf - rank, world), s_hi = ceil_div_pos((R + 1) * MCf - rank, world);
+        for (long long s = s_lo; s < s_hi; ++s) {
+            const int m = (int)(rank + world * s - R * MCf);
+            const long long pgid = gidrow * MCf + m;
+            const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
+            const long long crow = s - c.rowbase * MCf;            // row of this sample inside the child calls
+            double W[JCH];
+#pragma unroll
+            for (int i = 0; i < JCH; ++i) W[i] = 0.0;
+            double dsq = 1.0;
+            if (lv.variant == 1) {
+                const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
+                dsq = sqrt(tau * Tt + 1e-6);                       // ScaSML_full_history.py:169
+            }
+            for (int k = 0; k < q; ++k) {
+                const int lk = l * MAX_Q + k;
+                const long long pt = lv.set_off[lk] + s;
+                double y1 = 0.0, y2 = 0.0;
+                if (l >= 1) {
+                    double uh = 0.0, sG = 0.0;
+                    if (lv.scasml) { uh = lv.ev0[pt]; sG = sig * lv.ev1[pt]; }
+                    const double* r1 = lv.us[l] + 2 * (c.childbase[lk][0] + crow);
+                    y1 = lv.scasml ? sig * ((r1[0] + uh) * (sG + r1[1]) - uh * sG) : sig * r1[0] * r1[1];
+                    if (l >= 2) {
+                        const double* r2 = lv.us[l - 1] + 2 * (c.childbase[lk][1] + crow);
+                        y2 = lv.scasml ? sig * ((r2[0] + uh) * (sG + r2[1]) - uh * sG) : sig * r2[0] * r2[1];
+                    }
+                } else if (lv.scasml) {
+                    y1 = lv.ev0[pt];                                 // PDE residual of the surrogate (ScaSML.py:275)
+                }
+                if (lv.variant == 0) {
+                    uacc += cu[k] * (y1 - y2);
+                    const double yc = y1 * ca[k] - y2 * cs[k];
+                    const PhiloxKey key = make_key(c.key[lk], 1u, lv.seed);
+#pragma unroll
+                    for (int i = 0; i < JCH; ++i) {
+                        const int j = jpass + lane + 32 * i;
+                        if (j < d) {
+                            W[i] = fma(sqk[k], chunk_to_normal(lv.ntab, chunk16(f0 + j, key)), W[i]);
+                            zacc[i] = fma(yc, W[i], zacc[i]);
+                        }
+                    }
+                } else {
+                    const double yc = Tt * (y1 - y2) / MCf;
+                    uacc += yc;
+                    const double yz = yc / dsq;
+#pragma unroll
+                    for (int i = 0; i < JCH; ++i) {
+                        const int j = jpass + lane + 32 * i;
+                        if (j < d) zacc[i] = fma(yz, chunk_to_normal(lv.ntab, chunk16(f0 + j, kT)), zacc[i]);
+                    }
+                }
+            }
+        }
+    }
+
+    // clip / cast / row sum (solvers/ScaSML.py:281-284)
+#pragma unroll
+    for (int i = 0; i < JCH; ++i) {
+        const int j = jpass + lane + 32 * i;
+        if (j < d) {
+            double z = zacc[i];
+            if (!lv.partial) {
+                z = clip_keep_nan(z, lv.clip);
+                if (lv.cast_levels && !top) z = round_f16(z);
+            }
+            zs += z;
+            if (top) lv.out_uz[R * (d + 1) + 1 + j] = z;
+        }
+    }
+    }   // jpass
+    if (!lv.partial) {
+        uacc = clip_keep_nan(uacc, lv.clip);
+        if (lv.cast_levels && !top) uacc = round_f16(uacc);
+    }
+    for (int o = 16; o >= 1; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
+    if (lane == 0) {
+        lv.us[L][2 * R] = uacc;
+        lv.us[L][2 * R + 1] = zs;
+        if (top) lv.out_uz[R * (d + 1)] = uacc;
+    }
+}
+
+template <int JCH>
+int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
+    const long long threads = lv.NR * 32;
+    reduce_kernel<JCH><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ run -----------------------------------
+
+int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_uz, void* workspace, size_t ws_bytes,
+                    const __half* normal_table, cudaStream_t stream, PicardStats* stats_out) {
+    SC_REQUIRE(ws_bytes >= ws_bytes_, "picard: workspace too small");
+    SC_REQUIRE(normal_table != nullptr, "picard: normal table not set (scasml_set_normal_table)");
+    SC_REQUIRE(!p_.scasml || gp != nullptr, "picard: ScaSML variant needs a fitted GP");
+    const int d = p_.d, D = d + 1, n = p_.n;
+    long long launches = 0, eval_points = 0;
+    if (B_ == 0) { if (stats_out) *stats_out = stats_; return OK; }
+    if (n == 0) {
+        SC_CUDA(cudaMemsetAsync(out_uz, 0, (size_t)B_ * D * sizeof(double), stream));
+        if (stats_out) *stats_out = stats_;
+        return OK;
+    }
+    char* ws = (char*)workspace;
+    std::vector<LevelDev> lvs(n + 1);
+    std::vector<std::vector<CallDev>> host_calls(n + 1);
+    for (int L = 1; L <= n; ++L) {
+        const LevelRec& lr = levels_[L];
+        LevelDev& lv = lvs[L];
+        std::memset(&lv, 0, sizeof(lv));
+        lv.L = L; lv.ncalls = (int)lr.calls.size();
+        lv.calls = (const CallDev*)(ws + lr.off_calls);
+        lv.NR = lr.NR;
+        const bool strided = (L == n) && p_.world > 1;
+        lv.world = strided ? p_.world : 1; lv.rank = strided ? p_.rank : 0;
+        lv.MCg = mcg_of(L); lv.NT = lr.NT; lv.term_off = lr.term_off;
+        for (int l = 0; l < L; ++l) {
+            lv.q[l] = q_of(L, l); lv.MCf[l] = mcf_of(L, l); lv.NP[l] = lr.NP[l];
+            for (int k = 0; k < lv.q[l]; ++k) {
+                const int lk = l * MAX_Q + k;
+                lv.set_off[lk] = lr.set_off[lk];
+                if (p_.variant == 0) {
+                    lv.cnode[lk] = p_.c[k * p_.qmax + (lv.q[l] - 1)];
+                    lv.wnode[lk] = p_.w[k * p_.qmax + (lv.q[l] - 1)];
+                }
+            }
+        }
+        lv.P = (double*)(ws + lr.off_P);
+        lv.gid = (long long*)(ws + lr.off_gid);
+        lv.ev0 = (double*)(ws + lr.off_ev0);
+        lv.ev1 = (double*)(ws + lr.off_ev1);
+        for (int q = 1; q <= n; ++q) lv.us[q] = (double*)(ws + levels_[q].off_us);
+        lv.out_uz = (L == n) ? out_uz : nullptr;
+        lv.d = d; lv.D = D; lv.variant = p_.variant; lv.scasml = p_.scasml;
+        lv.stale_delta = p_.stale_delta; lv.cast_levels = p_.cast_levels;
+        lv.partial = (L == n && p_.world > 1) ? 1 : 0;
+        lv.T = p_.T; lv.mu = p_.mu; lv.sigma = p_.sigma; lv.clip = p_.clip;
+        lv.seed = p_.seed; lv.gid0 = p_.gid0; lv.ntab = normal_table;
+    }
+    // per-call device records (sources resolve to slices of the parents' point buffers)
+    for (int L = 1; L <= n; ++L) {
+        const LevelRec& lr = levels_[L];
+        std::vector<CallDev>& hc = host_calls[L];
+        hc.resize(lr.calls.size());
+        for (size_t ci = 0; ci < lr.calls.size(); ++ci) {
+            const CallRec& r = calls_[lr.calls[ci]];
+            CallDev& cd = hc[ci];
+            std::memset(&cd, 0, sizeof(cd));
+            cd.rowbase = r.rowbase; cd.nrows = r.nrows;
+            if (r.parent < 0) {
+                cd.xsrc = x_t; cd.gidsrc = nullptr;
+            } else {
+                const CallRec& pr = calls_[r.parent];
+                const LevelDev& plv = lvs[pr.level];
+                const long long poff = plv.set_off[r.pl * MAX_Q + r.pk] + pr.rowbase * plv.MCf[r.pl];
+                cd.xsrc = plv.P + poff * D;
+                cd.gidsrc = plv.gid + poff;
+            }
+            for (int lk = 0; lk < MAXLK; ++lk) {
+                cd.key[lk] = r.key[lk];
+                for (int role = 0; role < 2; ++role)
+                    cd.childbase[lk][role] = r.child[lk][role] >= 0 ? calls_[r.child[lk][role]].rowbase : -1;
+            }
+        }
+        SC_CUDA(cudaMemcpyAsync(ws + lr.off_calls, hc.data(), hc.size() * sizeof(CallDev), cudaMemcpyHostToDevice, stream));
+    }
+    const int nslot = (d + 14) / 8;
+    // top-down: sample + evaluate
+    for (int L = n; L >= 1; --L) {
+        const LevelDev& lv = lvs[L];
+        const LevelRec& lr = levels_[L];
+        if (lv.NT > 0) {
+            sample_terminal_kernel<<<(unsigned)cdiv(lv.NT * nslot, 256), 256, 0, stream>>>(lv);
+            SC_LAUNCH_CHECK(); ++launches;
+        }
+        for (int l = 0; l < L; ++l) {
+            if (lv.NP[l] == 0) continue;
+            sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l] * nslot, 256), 256, 0, stream>>>(lv, l);
+            SC_LAUNCH_CHECK(); ++launches;
+        }
+        if (p_.scasml) {
+            struct Sec { long long off, cnt; int mode; } secs[3] = {
+                {lr.term_off, lr.NT, EVAL_TERMINAL}, {lr.ug_off, lr.n_ug, EVAL_UG}, {lr.pde_off, lr.n_pde, EVAL_PDE}};
+            for (const Sec& s : secs) {
+                if (s.cnt == 0) continue;
+                int rc;
+                if (route == 1)
+                    rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
+                                        nullptr, nullptr, stream);
+                else
+                    rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
+                                         nullptr, nullptr, stream);
+                if (rc != OK) return rc;
+                ++launches; eval_points += s.cnt;
+            }
+        } else if (lv.NT > 0) {
+            mlp_terminal_kernel<<<(unsigned)cdiv(lv.NT * 32, 256), 256, 0, stream>>>(lv);
+            SC_LAUNCH_CHECK(); ++launches;
+        }
+    }
+    // bottom-up: reduce
+    for (int L = 1; L <= n; ++L) {
+        const LevelDev& lv = lvs[L];
+        int rc;
+        if (d <= 32) rc = launch_reduce<1>(lv, stream);
+        else if (d <= 64) rc = launch_reduce<2>(lv, stream);
+        else if (d <= 128) rc = launch_reduce<4>(lv, stream);
+        else rc = launch_reduce<8>(lv, stream);
+        if (rc != OK) return rc;
+        ++launches;
+    }
+    stats_.launches = launches;
+    stats_.eval_points_total = eval_points;
+    if (stats_out) *stats_out = stats_;
+    return OK;
+}
+
+}  // namespace scasml

@@ -1,0 +1,205 @@
+"""PDE-constrained Gaussian-process surrogate -- host mirror of the reference's ``models/GP.py``.
+
+Same class names, constructor, method signatures and state attributes as the reference
+(models/GP.py:8-26, 487-604, 653-769); all arithmetic happens in ``libscasml_b200.so``:
+  GPsolver            -> scasml_gp_set_centres + scasml_gp_fit  (Gram tiles, blocked Cholesky, Newton/LU)
+  predict             -> scasml_gp_eval(EVAL_U)
+  compute_gradient    -> scasml_gp_gradient
+  compute_PDE_loss    -> scasml_gp_eval(EVAL_PDE)
+Public results are float16 NumPy arrays (the reference's ``.astype(jnp.float16)``); ``*_raw`` variants
+return the float64 device results for parity checks.  Inputs the reference draws from JAX's threefry
+stream and that cannot be reproduced (the Hutchinson index set, models/GP.py:35, and the Newton start,
+:501) are constructor / method parameters with NumPy defaults.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+
+MC = 5  # models/GP.py:30
+
+
+class GP(object):
+    '''Gaussian Kernel Solver for high dimensional PDE'''
+
+    route = _lib.ROUTE_F64            # arithmetic route of predict / PDE residual (ROUTE_TC = tcgen05)
+
+    def __init__(self, equation, idx_set=None):
+        self.equation = equation
+        equation.geometry()
+        self.T = equation.T
+        self.t0 = equation.t0
+        self.n_input = equation.n_input
+        self.n_output = equation.n_output
+        self.d = self.n_input - 1
+        self.sigma = equation.sigma() * np.sqrt(self.d)      # models/GP.py:25
+        self.nugget = 1e-2                                    # models/GP.py:26
+        if idx_set is None:
+            # reference: random.choice(PRNGKey(0), d, (5,), replace=False) (models/GP.py:35) -- threefry stream
+            # is not reproducible here; any 5 distinct indices are statistically equivalent
+            idx_set = np.random.default_rng(0).choice(self.d, MC, replace=False)
+        self.idx_set = np.asarray(idx_set, dtype=np.int32)
+        self._handle = None
+        self.loss_history = []
+        self.f16_gram = True          # Gram entries rounded to float16 once (models/GP.py:258 semantics)
+
+    # ---- handle management ----
+    def _kernel_a(self):
+        return 1.0 / (self.sigma ** 2)
+
+    def _release(self):
+        if getattr(self, "_handle", None):
+            try:
+                _lib.load().scasml_gp_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_handle":
+                continue
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._handle = None
+        if self._handle:
+            h = C.c_void_p()
+            _lib.check(_lib.load().scasml_gp_clone(self._handle, C.byref(h)))
+            new._handle = h
+        return new
+
+    def _make_handle(self, n_dom, n_bdy):
+        self._release()
+        lib = _lib.load()
+        _lib.torch_cuda()
+        h = C.c_void_p()
+        idx = (C.c_int * MC)(*[int(i) for i in self.idx_set])
+        _lib.check(lib.scasml_gp_create(self.d, n_dom, n_bdy, idx, self._kernel_a(), self.equation.sigma(),
+                                        self.nugget, C.byref(h)))
+        self._handle = h
+
+    def _require_fit(self):
+        if not self._handle or not hasattr(self, "right_vector"):
+            raise AttributeError("GP is not fitted: call GPsolver(x_t_domain, x_t_boundary) first")
+
+    # ---- reference API ----
+    def kernel_phi_phi(self, x_t_domain, x_t_boundary):
+        '''K(phi, phi) + nugget*I as float16 (models/GP.py:182-268); also (re)binds the collocation sets.'''
+        self._bind(x_t_domain, x_t_boundary)
+        torch = _lib.torch_cuda()
+        K = torch.empty((self.phi_dim, self.phi_dim), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().scasml_gp_gram(self._handle, _lib.ptr(K), int(self.f16_gram), 1, _lib.stream_ptr()))
+        return K.cpu().numpy().astype(np.float16)
+
+    def _bind(self, x_t_domain, x_t_boundary):
+        x_t_domain = np.asarray(x_t_domain)
+        x_t_boundary = np.asarray(x_t_boundary)
+        self.N_domain = x_t_domain.shape[0]
+        self.N_boundary = x_t_boundary.shape[0]
+        self.phi_dim = 4 * self.N_domain + self.N_boundary
+        self.x_t_domain = x_t_domain
+        self.x_t_boundary = x_t_boundary
+        self._make_handle(self.N_domain, self.N_boundary)
+        xd = _lib.to_device(x_t_domain)
+        xb = _lib.to_device(x_t_boundary)
+        _lib.check(_lib.load().scasml_gp_set_centres(self._handle, _lib.ptr(xd), _lib.ptr(xb), _lib.stream_ptr()))
+        return xd, xb
+
+    def bdy_g(self, x_t_boundary):
+        return self.equation.g(x_t_boundary)[:, 0]
+
+    def GPsolver(self, x_t_domain, x_t_boundary, GN_steps=20, sol0=None):
+        '''Damped Newton fit (models/GP.py:487-604). Returns predict(x_t_domain) like the reference.'''
+        lib = _lib.load()
+        torch = _lib.torch_cuda()
+        self._bind(x_t_domain, x_t_boundary)
+        N = self.N_domain
+        g_bdy = _lib.to_device(np.asarray(self.bdy_g(self.x_t_boundary), dtype=np.float64))
+        if sol0 is None:
+            sol0 = np.random.default_rng(0).standard_normal(3 * N) * 1e-3       # models/GP.py:501
+        sol0_d = _lib.to_device(np.asarray(sol0, dtype=np.float64))
+        ws_bytes = lib.scasml_gp_fit_workspace_bytes(self._handle)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        sol_out = torch.empty(3 * N, dtype=torch.float64, device="cuda")
+        hist = (C.c_double * (GN_steps + 1))()
+        steps = C.c_int(0)
+        _lib.check(lib.scasml_gp_fit(self._handle, _lib.ptr(g_bdy), _lib.ptr(sol0_d), int(GN_steps), 1e-4, 1e-5,
+                                     int(self.f16_gram), _lib.ptr(ws), ws_bytes, _lib.ptr(sol_out), hist,
+                                     C.byref(steps), _lib.stream_ptr()))
+        del ws
+        self.newton_steps = int(steps.value)
+        self.loss_history = [h for h in list(hist) if not np.isnan(h)]
+        self.sol = sol_out.cpu().numpy()
+        alpha = torch.empty(self.phi_dim, dtype=torch.float64, device="cuda")
+        _lib.check(lib.scasml_gp_get_alpha(self._handle, _lib.ptr(alpha), _lib.stream_ptr()))
+        self.right_vector = alpha.cpu().numpy()[:, np.newaxis]                  # models/GP.py:599-600
+        return self.predict(x_t_domain)
+
+    def set_right_vector(self, right_vector):
+        '''Install externally computed GP weights (test hook; the reference assigns self.right_vector directly).'''
+        rv = np.asarray(right_vector, dtype=np.float64).reshape(-1)
+        a = _lib.to_device(rv)
+        _lib.check(_lib.load().scasml_gp_set_alpha(self._handle, _lib.ptr(a), _lib.stream_ptr()))
+        self.right_vector = rv[:, np.newaxis]
+
+    def _eval(self, x, mode, nout=1):
+        self._require_fit()
+        torch = _lib.torch_cuda()
+        xd = _lib.to_device(x)
+        R = xd.shape[0]
+        outs = [torch.empty(R, dtype=torch.float64, device="cuda") for _ in range(nout)]
+        ptrs = [_lib.ptr(o) for o in outs] + [C.c_void_p(0)] * (4 - nout)
+        _lib.check(_lib.load().scasml_gp_eval(self._handle, _lib.ptr(xd), R, mode, int(self.route), *ptrs,
+                                              _lib.stream_ptr()))
+        return outs
+
+    def predict_raw(self, x_t_infer):
+        return self._eval(x_t_infer, _lib.EVAL_U)[0].cpu().numpy()
+
+    def predict(self, x_t_infer):
+        '''u_hat(x), shape (N, 1), float16 (models/GP.py:653-671).'''
+        return self.predict_raw(x_t_infer)[:, np.newaxis].astype(np.float16)
+
+    def gradient_raw(self, x_t_infer):
+        self._require_fit()
+        lib = _lib.load()
+        torch = _lib.torch_cuda()
+        xd = _lib.to_device(x_t_infer)
+        R = xd.shape[0]
+        out = torch.empty((R, self.n_input), dtype=torch.float64, device="cuda")
+        ws_bytes = lib.scasml_gp_gradient_workspace_bytes(self._handle, R)
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device="cuda")
+        _lib.check(lib.scasml_gp_gradient(self._handle, _lib.ptr(xd), R, _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                                          _lib.stream_ptr()))
+        return out.cpu().numpy()
+
+    def compute_gradient(self, x_t_infer, sol_infer=None):
+        '''grad_x u_hat, shape (N, n_input), float16 (models/GP.py:673-687).'''
+        return self.gradient_raw(x_t_infer).astype(np.float16)
+
+    def pde_terms_raw(self, x_t_infer):
+        '''(eps, div_x u, lap_x u, dt_x u) in float64 -- parity hook.'''
+        return [o.cpu().numpy() for o in self._eval(x_t_infer, _lib.EVAL_PDE, nout=4)]
+
+    def compute_PDE_loss(self, x_t_infer):
+        raise NotImplementedError
+
+
+class GP_Grad_Dependent_Nonlinear(GP):
+    '''Gaussian Kernel Solver for the Grad_Dependent_Nonlinear (models/GP.py:693-769)'''
+
+    def __init__(self, equation, idx_set=None):
+        super(GP_Grad_Dependent_Nonlinear, self).__init__(equation, idx_set=idx_set)
+
+    def rhs_f(self, x_t):
+        return np.zeros((np.asarray(x_t).shape[0]), dtype=np.asarray(x_t).dtype)     # models/GP.py:700-702
+
+    def compute_PDE_loss(self, x_t_infer):
+        '''PDE residual of the surrogate, shape (N, 1), float16 (models/GP.py:746-769).'''
+        return self._eval(x_t_infer, _lib.EVAL_PDE)[0].cpu().numpy()[:, np.newaxis].astype(np.float16)
