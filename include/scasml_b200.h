@@ -70,6 +70,8 @@ typedef struct scasml_picard_params {
     unsigned key_counter;            /* random.split count at entry, solvers/ScaSML.py:27,228 */
     int rank, world;                 /* top-level sample sharding (unit u owned iff u % world == rank) */
     long long gid0;                  /* global index of the first row of x_t (RNG addressing) */
+    int timing;                      /* 1: bracket kernel groups with CUDA events (adds a stream sync at the end) */
+    int reserved;
 } scasml_picard_params;
 
 typedef struct scasml_picard_stats {
@@ -80,6 +82,11 @@ typedef struct scasml_picard_stats {
     long long n_calls;           /* uz_solve calls of level >= 1 in the tree */
     long long launches;          /* kernel launches issued */
     long long eval_points_total; /* surrogate evaluations launched on this rank */
+    long long eval_launches;     /* surrogate-evaluation kernel launches */
+    long long eval_time_ns;      /* device time of the evaluation launches (timing = 1) */
+    long long sample_time_ns;    /* device time of the sampler launches (timing = 1) */
+    long long reduce_time_ns;    /* device time of the reduction launches (timing = 1) */
+    long long eval_flops;        /* algorithmic distance-contraction flops of the evaluation launches */
 } scasml_picard_stats;
 
 SCASML_API const char* scasml_last_error(void);

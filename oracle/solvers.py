@@ -52,6 +52,7 @@ class _Base:
         self.key_counter = 0          # number of random.split calls so far (solvers/ScaSML.py:27,228)
         self._tables = {}
         self.sample_points = 0        # diagnostic: normal vectors drawn over all rows (SURVEY.md 8d work unit)
+        self.sample_points_executed = 0   # same, without the level-0 terminals the reference draws and discards
 
     # -- generator / terminal (solvers/ScaSML.py:29-63 vs solvers/MLP.py:27-55) --
     def f(self, x_t, u, z):
@@ -127,6 +128,7 @@ class _Quadrature(_Base):
             gv = self.g(term_in).reshape(B, MC_g, 1)
             self.evaluation_counter += MC_g
             self.sample_points += B * MC_g
+            self.sample_points_executed += B * MC_g
             if own is not None:
                 gv = gv * own[:, :, None]
             u = gv.sum(axis=1) / MC_g
@@ -147,6 +149,7 @@ class _Quadrature(_Base):
                     W = W + dW
                     X = X + (mu * d[:, k][:, None, None] + sigma * dW)
                     self.sample_points += B * MC_f
+                    self.sample_points_executed += B * MC_f
                     tk = cloc[:, k, q - 1]
                     pts = np.concatenate([X, np.repeat(tk[:, None, None], MC_f, axis=1)], axis=2).reshape(-1, self.n_input)
                     sim = self.uz_solve(l, rho, pts, gid0 * MC_f, None, _top=False).reshape(B, MC_f, -1)
@@ -245,6 +248,7 @@ class _FullHistory(_Base):
             gv = self.g(term_in).reshape(B, MC_g, 1)
             self.evaluation_counter += MC_g
             self.sample_points += B * MC_g
+            self.sample_points_executed += B * MC_g
             if own is not None:
                 gv = gv * own[:, :, None]
             u = gv.sum(axis=1) / MC_g
@@ -259,6 +263,7 @@ class _FullHistory(_Base):
                 dW = np.sqrt(steps) * std_normal
                 X = x[:, None, :] + (mu * steps + sigma * dW)
                 self.sample_points += B * MC_f
+                self.sample_points_executed += B * MC_f
                 pts = np.concatenate([X, t[:, None, None] + steps], axis=2).reshape(-1, self.n_input)
                 sim = self.uz_solve(l, None, pts, M, gid0 * MC_f, None, _top=False).reshape(B, MC_f, dim + 1)
                 y = self.f(pts, sim[:, :, 0].reshape(-1, 1), sim[:, :, 1:].reshape(-1, dim)).reshape(B, MC_f, 1)

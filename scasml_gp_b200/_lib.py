@@ -24,13 +24,14 @@ class PicardParams(C.Structure):
         ("c", C.c_double * (MAX_Q * MAX_Q)), ("w", C.c_double * (MAX_Q * MAX_Q)),
         ("T", C.c_double), ("mu", C.c_double), ("sigma", C.c_double), ("clip", C.c_double),
         ("stale_delta", C.c_int), ("cast_levels", C.c_int), ("seed", C.c_uint), ("key_counter", C.c_uint),
-        ("rank", C.c_int), ("world", C.c_int), ("gid0", C.c_longlong),
+        ("rank", C.c_int), ("world", C.c_int), ("gid0", C.c_longlong), ("timing", C.c_int), ("reserved", C.c_int),
     ]
 
 
 class PicardStats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("keys_used", "eval_counter", "sample_points", "executed_points",
-                                            "n_calls", "launches", "eval_points_total")]
+                                            "n_calls", "launches", "eval_points_total", "eval_launches",
+                                            "eval_time_ns", "sample_time_ns", "reduce_time_ns", "eval_flops")]
 
 
 _SIGNATURES = {

@@ -530,10 +530,24 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         SC_CUDA(cudaMemcpyAsync(ws + lr.off_calls, hc.data(), hc.size() * sizeof(CallDev), cudaMemcpyHostToDevice, stream));
     }
     const int nslot = (d + 14) / 8;
+    // optional CUDA-event timing of the three kernel groups (sampler / evaluation / reduction)
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    const bool timing = p_.timing != 0;
+    auto begin_span = [&](int kind) {
+        if (!timing) return;
+        Span sp; sp.kind = kind;
+        cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+        cudaEventRecord(sp.a, stream);
+        spans.push_back(sp);
+    };
+    auto end_span = [&]() { if (timing) cudaEventRecord(spans.back().b, stream); };
+    long long eval_launches = 0, eval_flops = 0;
     // top-down: sample + evaluate
     for (int L = n; L >= 1; --L) {
         const LevelDev& lv = lvs[L];
         const LevelRec& lr = levels_[L];
+        begin_span(0);
         if (lv.NT > 0) {
             sample_terminal_kernel<<<(unsigned)cdiv(lv.NT * nslot, 256), 256, 0, stream>>>(lv);
             SC_LAUNCH_CHECK(); ++launches;
@@ -543,12 +557,15 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
             sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l] * nslot, 256), 256, 0, stream>>>(lv, l);
             SC_LAUNCH_CHECK(); ++launches;
         }
+        end_span();
         if (p_.scasml) {
             struct Sec { long long off, cnt; int mode; } secs[3] = {
                 {lr.term_off, lr.NT, EVAL_TERMINAL}, {lr.ug_off, lr.n_ug, EVAL_UG}, {lr.pde_off, lr.n_pde, EVAL_PDE}};
+            const long long fu = 2LL * D * (2LL * gp->Nd + gp->Nb), fp = 2LL * D * ((long long)gp->Nd + gp->Nb);
             for (const Sec& s : secs) {
                 if (s.cnt == 0) continue;
                 int rc;
+                begin_span(1);
                 if (route == 1)
                     rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                         nullptr, nullptr, stream);
@@ -556,7 +573,9 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
                     rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                          nullptr, nullptr, stream);
                 if (rc != OK) return rc;
-                ++launches; eval_points += s.cnt;
+                end_span();
+                ++launches; ++eval_launches; eval_points += s.cnt;
+                eval_flops += s.cnt * (fu + (s.mode == EVAL_PDE ? fp : 0));
             }
         } else if (lv.NT > 0) {
             mlp_terminal_kernel<<<(unsigned)cdiv(lv.NT * 32, 256), 256, 0, stream>>>(lv);
@@ -567,15 +586,30 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
     for (int L = 1; L <= n; ++L) {
         const LevelDev& lv = lvs[L];
         int rc;
+        begin_span(2);
         if (d <= 32) rc = launch_reduce<1>(lv, stream);
         else if (d <= 64) rc = launch_reduce<2>(lv, stream);
         else if (d <= 128) rc = launch_reduce<4>(lv, stream);
         else rc = launch_reduce<8>(lv, stream);
         if (rc != OK) return rc;
+        end_span();
         ++launches;
+    }
+    stats_.eval_time_ns = stats_.sample_time_ns = stats_.reduce_time_ns = 0;
+    if (timing) {
+        SC_CUDA(cudaStreamSynchronize(stream));
+        for (Span& sp : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, sp.a, sp.b);
+            const long long ns = (long long)(ms * 1e6);
+            if (sp.kind == 0) stats_.sample_time_ns += ns; else if (sp.kind == 1) stats_.eval_time_ns += ns; else stats_.reduce_time_ns += ns;
+            cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+        }
     }
     stats_.launches = launches;
     stats_.eval_points_total = eval_points;
+    stats_.eval_launches = eval_launches;
+    stats_.eval_flops = eval_flops;
     if (stats_out) *stats_out = stats_;
     return OK;
 }

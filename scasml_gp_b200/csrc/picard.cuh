@@ -29,6 +29,8 @@ struct PicardParams {
     unsigned key_counter;     // running random.split count at entry (solvers/ScaSML.py:27,228)
     int rank, world;          // top-level sample sharding: unit u owned iff u % world == rank
     long long gid0;           // global index of the first test point of this batch
+    int timing;               // 1: CUDA-event timing of kernel groups (adds a stream sync)
+    int reserved;
 };
 
 struct PicardStats {
@@ -39,6 +41,9 @@ struct PicardStats {
     long long n_calls;            // uz_solve calls of level >= 1 in the tree
     long long launches;           // kernel launches issued by run()
     long long eval_points_total;  // surrogate evaluations launched (all rows, this rank)
+    long long eval_launches;
+    long long eval_time_ns, sample_time_ns, reduce_time_ns;
+    long long eval_flops;         // 2 (d+1) x centres per distance contraction, summed over evaluation launches
 };
 
 constexpr int MAXLK = MAX_LEVEL * MAX_Q;

@@ -92,6 +92,7 @@ class PicardSolverBase(object):
     seed = 0
     workspace_budget_bytes = int(os.environ.get("SCASML_WORKSPACE_BYTES", 24 << 30))
     distributed = False         # shard top-level samples over torch.distributed ranks + one all_reduce
+    timing = False              # CUDA-event timing of the sampler / evaluation / reduction groups (last_stats)
 
     def _init_common(self, equation):
         self.equation = equation
@@ -152,6 +153,7 @@ class PicardSolverBase(object):
         p.stale_delta, p.cast_levels = int(self.stale_delta), int(self.cast_levels)
         p.seed, p.key_counter = int(self.seed), int(self.key) & 0xFFFFFFFF
         p.rank, p.world, p.gid0 = int(rank), int(world), 0
+        p.timing = int(self.timing)
         return p
 
     def plan(self, n, rho, B, M=None, rank=0, world=1):
@@ -208,7 +210,8 @@ class PicardSolverBase(object):
             if agg is None:
                 agg = {f: getattr(stats, f) for f, _ in _lib.PicardStats._fields_}
             else:
-                for f in ("executed_points", "launches", "eval_points_total"):
+                for f in ("executed_points", "launches", "eval_points_total", "eval_launches", "eval_time_ns",
+                          "sample_time_ns", "reduce_time_ns", "eval_flops"):
                     agg[f] += getattr(stats, f)
         if B == 0:
             _, st = self.plan(n, rho, 0, M)

@@ -31,9 +31,9 @@ def test_header_symbols_are_exported(lib):
 
 def test_struct_layout_matches_header(lib):
     # sizes are static_assert'ed against the C++ structs in csrc/abi.cu; here: the Python mirror vs the header
-    assert C.sizeof(lib.PicardStats) == 7 * 8
+    assert C.sizeof(lib.PicardStats) == 12 * 8
     ints = 6 + 8 + 8 + 9
-    assert C.sizeof(lib.PicardParams) == ((ints * 4 + 7) // 8) * 8 + 2 * 64 * 8 + 4 * 8 + 6 * 4 + 8
+    assert C.sizeof(lib.PicardParams) == ((ints * 4 + 7) // 8) * 8 + 2 * 64 * 8 + 4 * 8 + 6 * 4 + 8 + 8
 
 
 class _Eq:
