@@ -144,6 +144,12 @@ SCASML_API int scasml_clip(double* x_dev, long long count, double c, void* strea
 SCASML_API int scasml_debug_spd_inverse(double* A_dev /*in: SPD, out: L*/, long long n, double* P_dev, void* ws_dev,
                              size_t ws_bytes, void* stream); /* ws >= (n*n + 64*64*ceil(n/64) + 64*n)*8 */
 SCASML_API int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream);
+/* tcgen05 plumbing self-test: D[128][N] (f32) = A[128][K] (f16) x B[N][K]^T (f16) through the same shared-memory
+ * layout, descriptors, tcgen05.mma and tcgen05.ld helpers as the evaluation kernel (descriptor fields at run time) */
+SCASML_API int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* D_dev, int K, int N, unsigned lbo16,
+                         unsigned sbo16, unsigned layout, unsigned kstep_bytes, void* stream);
+/* 1 if this handle can use SCASML_ROUTE_TC (d + 1 <= 128) */
+SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 
 #ifdef __cplusplus
 }

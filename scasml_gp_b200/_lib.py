@@ -60,6 +60,8 @@ _SIGNATURES = {
     "scasml_clip": (C.c_int, [C.c_void_p, C.c_longlong, C.c_double, C.c_void_p]),
     "scasml_debug_spd_inverse": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scasml_debug_lu_solve": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "scasml_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]),
+    "scasml_gp_tc_supported": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 #include "gp.cuh"
 #include "gp_fit.cuh"
 #include "picard.cuh"
+#include "gp_tc.cuh"
 
 static_assert(sizeof(scasml_picard_params) == sizeof(scasml::PicardParams), "ABI struct mismatch");
 static_assert(sizeof(scasml_picard_stats) == sizeof(scasml::PicardStats), "ABI struct mismatch");
@@ -85,6 +86,7 @@ struct scasml_gp {
     double* C = nullptr;      // [NdPad + NbPad][D]
     double* feat = nullptr;   // [NdPad + NbPad][CF_STRIDE]
     double* alpha = nullptr;  // [4 Nd + Nb]
+    TcState tc{};             // tcgen05 route: operand images (rebuilt with every set_alpha)
     bool has_centres = false, has_alpha = false;
     long phi() const { return 4L * v.Nd + v.Nb; }
     long ncpad() const { return (long)v.NdPad + v.NbPad; }
@@ -99,6 +101,14 @@ static int gp_alloc(scasml_gp* g) {
     SC_CUDA(cudaMemset(g->feat, 0, (size_t)nc * CF_STRIDE * sizeof(double)));
     SC_CUDA(cudaMemset(g->alpha, 0, (size_t)g->phi() * sizeof(double)));
     g->v.C = g->C; g->v.feat = g->feat;
+    g->tc = TcState();
+    g->v.tc = nullptr;
+    if (tc_supported(g->v)) {
+        const size_t bytes = tc_image_bytes(g->v, &g->tc);
+        SC_CUDA(cudaMalloc(&g->tc.images, bytes));
+        SC_CUDA(cudaMemset(g->tc.images, 0, bytes));
+        g->v.tc = &g->tc;
+    }
     return OK;
 }
 
@@ -165,7 +175,7 @@ int scasml_gp_create(int d, int n_dom, int n_bdy, const int* idx_set5, double ke
 
 int scasml_gp_destroy(scasml_gp* g) {
     if (!g) return OK;
-    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha);
+    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha); cudaFree(g->tc.images);
     delete g;
     return OK;
 }
@@ -183,6 +193,9 @@ int scasml_gp_clone(const scasml_gp* src, scasml_gp** out) {
     SC_CUDA(cudaMemcpy(g->C, src->C, (size_t)nc * g->v.D * sizeof(double), cudaMemcpyDeviceToDevice));
     SC_CUDA(cudaMemcpy(g->feat, src->feat, (size_t)nc * CF_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice));
     SC_CUDA(cudaMemcpy(g->alpha, src->alpha, (size_t)g->phi() * sizeof(double), cudaMemcpyDeviceToDevice));
+    if (g->tc.images && src->tc.images)
+        SC_CUDA(cudaMemcpy(g->tc.images, src->tc.images, (size_t)(g->tc.ntile_dom + g->tc.ntile_bdy) * g->tc.tile_bytes,
+                           cudaMemcpyDeviceToDevice));
     *out = g;
     return OK;
 }
@@ -207,7 +220,10 @@ int scasml_gp_set_alpha(scasml_gp* g, const double* alpha_dev, void* stream) {
     if (alpha_dev != g->alpha)
         SC_CUDA(cudaMemcpyAsync(g->alpha, alpha_dev, (size_t)g->phi() * sizeof(double), cudaMemcpyDeviceToDevice, st));
     g->has_alpha = true;
-    return build_centre_features(g->v, g->alpha, g->feat, st);
+    int rc = build_centre_features(g->v, g->alpha, g->feat, st);
+    if (rc != OK) return rc;
+    if (g->tc.images) rc = tc_build_images(g->v, g->tc, st);
+    return rc;
 }
 
 int scasml_gp_get_alpha(const scasml_gp* g, double* alpha_dev, void* stream) {
@@ -319,6 +335,14 @@ int scasml_debug_spd_inverse(double* A_dev, long long n, double* P_dev, void* ws
     if (h_fail) { set_error("matrix is not positive definite"); return ERR_NUMERIC; }
     return OK;
 }
+
+int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* D_dev, int K, int N, unsigned lbo16,
+                         unsigned sbo16, unsigned layout, unsigned kstep_bytes, void* stream) {
+    SC_REQUIRE(A_half_dev && B_half_dev && D_dev, "debug_tc_gemm: null");
+    return tc_selftest(A_half_dev, B_half_dev, D_dev, K, N, lbo16, sbo16, layout, kstep_bytes, (cudaStream_t)stream);
+}
+
+int scasml_gp_tc_supported(const scasml_gp* g) { return (g && g->tc.images) ? 1 : 0; }
 
 int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -33,6 +33,7 @@ struct GpView {
     int I[MC_IDX];            // Hutchinson index set (models/GP.py:35)
     const double* C;          // [NdPad + NbPad][D] centres, float64 (float16-valued)
     const double* feat;       // [NdPad + NbPad][CF_STRIDE]
+    const void* tc;           // host pointer to the TcState of the tcgen05 route (never dereferenced on the device)
 };
 
 // evaluation modes of the fused surrogate kernel

@@ -1,8 +1,534 @@
-// tcgen05 route of the surrogate evaluation -- placeholder until the TMEM kernel lands.
+// tcgen05 route of the fused surrogate evaluation (sm_100a).
+//
+// Same contract as gp_eval.cu (reference models/GP.py:630-687, 326-411, 746-769), different arithmetic:
+//   * the three distance contractions x.y, x.roll(y), roll(x).y run on the 5th-gen tensor cores:
+//     tcgen05.mma kind::f16, M = 128 points x N = 64 centres per instruction, FP32 accumulators in TMEM;
+//   * centres are float16-valued (DeepXDE float16 collocation points), so the B operand is EXACT in f16;
+//     sampled points are split  a' x = hi + lo  (two f16 terms, |error| <= 2^-22 |a' x|) and both halves are
+//     accumulated into the same TMEM tile: 2 MMA passes instead of 3xTF32, at twice the TF32 rate;
+//   * the Gaussian factorises, k(x,y) = K_i K_j exp(a x.y) with K = exp(-a |.|^2 / 2): K_j is folded into the GP
+//     weights once per fit, K_i is applied once per point, so the epilogue does one ex2 per pair-distance
+//     directly on the accumulator (the scale a log2 e is folded into the A operand);
+//   * centre tiles (operand images in the 128B-swizzled K-major layout + FP32 feature records) are built once
+//     per fit and streamed with cp.async.bulk into a 2-stage ring; MMA of tile t+1 overlaps the epilogue of t;
+//   * epilogue: 8 warps, thread <-> (point row, half of the tile's centres), tcgen05.ld 32x32b, FP32 per-tile
+//     partial sums flushed into FP64 accumulators.
+// Accuracy: ~1e-7 absolute on u_hat (FP32 exponent); parity with the FP64 route is tested under the "nocast" policy.
+#include <cstring>
 #include "picard.cuh"
+#include "gp_tc.cuh"
+
 namespace scasml {
-int launch_eval_tc(const GpView&, const void*, const double*, long, int, double*, double*, double*, double*, cudaStream_t) {
-    set_error("tcgen05 evaluation route is not available in this build");
-    return ERR_INVALID;
+
+namespace tc {
+
+constexpr int TM = 128;              // points per CTA (UMMA M)
+constexpr int TN = 64;               // centres per tile (UMMA N)
+constexpr int KBLK = 64;             // f16 elements per 128-byte swizzle row
+constexpr int A_BLK = TM * 128;      // bytes of one [128 x 64] f16 block
+constexpr int B_BLK = TN * 128;      // bytes of one [64 x 64] f16 block
+constexpr int NF = TC_NF;            // floats per centre feature record
+constexpr int NTHREADS = 320;        // 8 epilogue warps + producer warp + MMA warp
+constexpr uint32_t SPIN_LIMIT = 1u << 27;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// K-major, 128-byte swizzle: [rows][64 f16], 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(lbo16 & 0x3FFF) << 16;
+    d |= (uint64_t)(sbo16 & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): f16 x f16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of element (row r, col c) inside one [rows x 64] f16 block, Swizzle<3,4,3>
+__host__ __device__ inline uint32_t sw128_off(int r, int c) {
+    return (uint32_t)(r * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
+}
+
+// ---- self test: D[128 x N] = A[128 x K] B[N x K]^T with runtime descriptor fields -------------------------------
+__global__ void __launch_bounds__(128, 1)
+selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ Dout, int K, int N,
+                uint32_t lbo16, uint32_t sbo16, uint32_t layout, uint32_t kstep_bytes) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int KB = K / KBLK;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)KB * A_BLK;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < TM * K; idx += 128) {
+        const int r = idx / K, c = idx % K;
+        *(__half*)(sA + (size_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK)) = A[(size_t)r * K + c];
+    }
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int r = idx / K, c = idx % K;
+        *(__half*)(sB + (size_t)(c / KBLK) * (N * 128) + sw128_off(r, c % KBLK)) = B[(size_t)r * K + c];
+    }
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 64);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(TM, N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb)
+            for (int ks = 0; ks < KBLK / 16; ++ks) {
+                const uint64_t ad = make_desc(smem_u32(sA + (size_t)kb * A_BLK) + ks * kstep_bytes, lbo16, sbo16, layout);
+                const uint64_t bd = make_desc(smem_u32(sB + (size_t)kb * (N * 128)) + ks * kstep_bytes, lbo16, sbo16, layout);
+                umma_f16(tmem_base, ad, bd, idesc, acc);
+                acc = 1;
+            }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) Dout[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// ---- operand images of the centres (built once per fit) ---------------------------------------------------
+// images: per tile t: [C image: KB blocks of [64 x 64] f16, swizzled][Croll image (domain tiles)][features 64 x NF f32]
+__global__ void build_images_kernel(GpView gp, TcState st) {
+    const int tile = blockIdx.x;
+    const bool dom = tile < st.ntile_dom;
+    const int c0 = tile * TN;                          // padded centre index of the tile's first centre
+    uint8_t* base = st.images + (size_t)tile * st.tile_bytes;
+    const int D = gp.D, d = gp.d, KB = st.KB;
+    const double a = gp.a;
+    for (int idx = threadIdx.x; idx < TN * KB * KBLK; idx += blockDim.x) {
+        const int r = idx / (KB * KBLK), c = idx % (KB * KBLK);
+        const double* y = gp.C + (size_t)(c0 + r) * D;
+        const double v = (c < D) ? y[c] : 0.0;
+        const double vr = (c < D) ? y[(c + 1 == D) ? 0 : c + 1] : 0.0;
+        const uint32_t off = (uint32_t)(c / KBLK) * B_BLK + sw128_off(r, c % KBLK);
+        *(__half*)(base + off) = __double2half(v);
+        *(__half*)(base + (size_t)KB * B_BLK + off) = __double2half(dom ? vr : 0.0);
+    }
+    float* feat = (float*)(base + 2 * (size_t)KB * B_BLK);
+    for (int r = threadIdx.x; r < TN; r += blockDim.x) {
+        const double* f = gp.feat + (size_t)(c0 + r) * CF_STRIDE;
+        const double Kj = exp(-0.5 * a * f[CF_NY]);
+        float* o = feat + r * NF;
+        o[TF_SY] = (float)f[CF_SY]; o[TF_YT] = (float)f[CF_YT]; o[TF_Y0] = (float)f[CF_Y0]; o[TF_SYROLL] = (float)f[CF_SYROLL];
+        for (int m = 0; m < MC_IDX; ++m) { o[TF_YI + m] = (float)f[CF_YI + m]; o[TF_YIR + m] = (float)f[CF_YIR + m]; }
+        o[TF_A1] = (float)(f[CF_A1] * Kj);
+        o[TF_A3D] = (float)(f[CF_A3] * Kj * (double)d);
+        o[TF_A4] = (float)(f[CF_A4] * Kj);
+        o[TF_A5] = (float)(f[CF_A5] * Kj);
+        for (int i = TF_A5 + 1; i < NF; ++i) o[i] = 0.f;
+    }
+}
+
+// ---- the fused evaluation kernel ---------------------------------------------------------------------------
+// CLASS 0: u (EVAL_U / EVAL_TERMINAL), 1: u + div_x u, 2: PDE residual.  KB: 64-wide K blocks (1 or 2).
+struct XF { float sx, xt, x0, sxroll, xi[MC_IDX], xir[MC_IDX]; };
+
+template <int CLASS, int KB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int mode,
+               double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
+    constexpr bool PDE = (CLASS == 2);
+    constexpr int NA = PDE ? 4 : 2;                                   // A images: hi, lo (, roll hi, roll lo)
+    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK + TN * NF * 4;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                               // NA * KB * A_BLK
+    uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // 2 stages
+    uint8_t* sMisc = sStage + 2 * (size_t)STAGE_BYTES;
+    XF* xfeat = (XF*)sMisc;                                           // [128]
+    double* Ki = (double*)(sMisc + TM * sizeof(XF));                  // [128]
+    double* xchg = Ki + TM;                                           // [128][4]
+    uint64_t* bars = (uint64_t*)(xchg + TM * 4);                      // full[2], accfull[2], free[2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = gp.D, d = gp.d;
+    const long row0 = (long)blockIdx.x * TM;
+    const uint32_t bar_full[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+    const uint32_t bar_acc[2] = {smem_u32(&bars[2]), smem_u32(&bars[3])};
+    const uint32_t bar_free[2] = {smem_u32(&bars[4]), smem_u32(&bars[5])};
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_full[s], 1); mbar_init(bar_acc[s], 1); mbar_init(bar_free[s], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+
+    // ---- build the A operand: a' x = hi + lo, swizzled f16 (and the rolled copy for the PDE rows) ----
+    const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
+    if (warp < 8) {
+        for (int r = warp; r < TM; r += 8) {
+            const long row = row0 + r;
+            const double* xr = X + row * (long)D;
+            double nx = 0.0, sxs = 0.0;
+            for (int c = lane; c < KB * KBLK; c += 32) {
+                double v = 0.0, vr = 0.0;
+                if (row < R && c < D) {
+                    v = xr[c];
+                    if (PDE) vr = xr[(c + 1 == D) ? 0 : c + 1];
+                    nx = fma(v, v, nx);
+                    if (c < d) sxs += v;
+                }
+                const uint32_t off = (uint32_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK);
+                const double sv = ascale * v;
+                const __half h = __double2half(sv);
+                *(__half*)(sA + off) = h;
+                *(__half*)(sA + (size_t)KB * A_BLK + off) = __double2half(sv - (double)__half2float(h));
+                if (PDE) {
+                    const double svr = ascale * vr;
+                    const __half hr = __double2half(svr);
+                    *(__half*)(sA + 2 * (size_t)KB * A_BLK + off) = hr;
+                    *(__half*)(sA + 3 * (size_t)KB * A_BLK + off) = __double2half(svr - (double)__half2float(hr));
+                }
+            }
+            for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
+            if (lane == 0) {
+                XF f;
+                const bool ok = row < R;
+                const double xt = ok ? xr[d] : 0.0, x0 = ok ? xr[0] : 0.0;
+                f.sx = (float)sxs; f.xt = (float)xt; f.x0 = (float)x0; f.sxroll = (float)(sxs - x0 + xt);
+                for (int m = 0; m < MC_IDX; ++m) {
+                    f.xi[m] = ok ? (float)xr[gp.I[m]] : 0.f;
+                    f.xir[m] = ok ? (float)xr[gp.I[m] + 1] : 0.f;
+                }
+                xfeat[r] = f;
+                Ki[r] = exp(-0.5 * gp.a * nx);
+            }
+        }
+        fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ntile = st.ntile_dom + st.ntile_bdy;
+    constexpr uint32_t ACC_STRIDE = 256;                              // TMEM columns per stage: d1 | d2 | d3 at +0/+64/+128
+
+    if (warp == 8) {
+        // ===== producer: stream centre tiles (operand images + feature records) =====
+        if (lane == 0) {
+            for (int t = 0; t < ntile; ++t) {
+                const int s = t & 1;
+                if (t >= 2) mbar_wait(bar_free[s], ((t >> 1) - 1) & 1);
+                const bool dom = t < st.ntile_dom;
+                const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
+                uint8_t* dst = sStage + (size_t)s * STAGE_BYTES;
+                const uint32_t bytes_c = KB * B_BLK, bytes_f = TN * NF * 4;
+                mbar_expect_tx(bar_full[s], bytes_c + (dom ? bytes_c : 0) + bytes_f);
+                bulk_g2s(smem_u32(dst), src, bytes_c, bar_full[s]);
+                if (dom) bulk_g2s(smem_u32(dst + bytes_c), src + bytes_c, bytes_c, bar_full[s]);
+                bulk_g2s(smem_u32(dst + 2 * bytes_c), src + 2 * bytes_c, bytes_f, bar_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TM, TN);
+            for (int t = 0; t < ntile; ++t) {
+                const int s = t & 1;
+                const bool dom = t < st.ntile_dom;
+                mbar_wait(bar_full[s], (t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t sB = smem_u32(sStage + (size_t)s * STAGE_BYTES);
+                const uint32_t sBr = sB + KB * B_BLK;
+                const uint32_t acc = tmem_base + s * ACC_STRIDE;
+                // low halves first (tiny terms), then the high halves
+#pragma unroll
+                for (int half = 1; half >= 0; --half) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                        for (int ks = 0; ks < KBLK / 16; ++ks) {
+                            const uint32_t first = (half == 1 && kb == 0 && ks == 0) ? 0u : 1u;
+                            const uint32_t aoff = (uint32_t)(half * KB + kb) * A_BLK + ks * 32;
+                            const uint64_t ad = make_desc(smem_u32(sA) + aoff, 1, 64, 2);
+                            const uint64_t bd = make_desc(sB + kb * B_BLK + ks * 32, 1, 64, 2);
+                            umma_f16(acc, ad, bd, idesc, first);
+                            if (dom) {
+                                const uint64_t brd = make_desc(sBr + kb * B_BLK + ks * 32, 1, 64, 2);
+                                umma_f16(acc + 64, ad, brd, idesc, first);
+                            }
+                            if (PDE) {
+                                const uint64_t ard = make_desc(smem_u32(sA) + (uint32_t)(2 * KB) * A_BLK + aoff, 1, 64, 2);
+                                umma_f16(acc + 128, ard, bd, idesc, first);
+                            }
+                        }
+                    }
+                }
+                umma_commit(bar_acc[s]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: thread <-> (point row, half of the tile's centres) =====
+        const int r = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;                                  // centres [32*half, 32*half + 32) of each tile
+        const XF xf = xfeat[r];
+        const float a = (float)gp.a, a2 = a * a, a3 = a2 * a, dd = (float)d, inv5 = 1.f / MC_IDX;
+        double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        for (int t = 0; t < ntile; ++t) {
+            const int s = t & 1;
+            const bool dom = t < st.ntile_dom;
+            mbar_wait(bar_full[s], (t >> 1) & 1);                     // feature records landed (async proxy -> this thread)
+            mbar_wait(bar_acc[s], (t >> 1) & 1);
+            tc_fence_after();
+            const float* feat = (const float*)(sStage + (size_t)s * STAGE_BYTES + 2 * KB * B_BLK) + (half * 32) * NF;
+            const uint32_t acc = tmem_base + s * ACC_STRIDE + lane_addr + half * 32;
+            float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                float v1[16], v2[16], v3[PDE ? 16 : 1];
+                tmem_ld16(acc + c0, v1);
+                if (dom) tmem_ld16(acc + 64 + c0, v2);
+                if (PDE) tmem_ld16(acc + 128 + c0, v3);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float* c = feat + (c0 + i) * NF;
+                    const float4 f0 = *(const float4*)(c);            // sy, yt, y0, syroll
+                    const float4 fa = *(const float4*)(c + TF_A1);    // A1, A3d, A4, A5
+                    const float sy = f0.x, yt = f0.y;
+                    const float A1 = fa.x, A3d = fa.y, A4 = fa.z, A5 = fa.w;
+                    const float S = xf.sx - sy, rt = xf.xt - yt;
+                    const float k = ex2f(v1[i]);
+                    pu = fmaf(k, A1 + a * (A4 * rt + A5 * S), pu);
+                    if (CLASS >= 1) pg = fmaf(k, -a * S * A1 - a2 * rt * S * A4 + (a * dd - a2 * S * S) * A5, pg);
+                    if (PDE) pt = fmaf(k, -a * rt * A1 + (a - a2 * rt * rt) * A4 - a2 * rt * S * A5, pt);
+                    if (dom) {
+                        const float ky = ex2f(v2[i]);
+                        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+                        for (int m = 0; m < MC_IDX; ++m) {
+                            const float ry = xf.xi[m] - c[TF_YIR + m];
+                            m1 += ry; m2 = fmaf(ry, ry, m2);
+                        }
+                        const float MH = a2 * m2 * inv5 - a;
+                        const float w3 = ky * A3d;
+                        pu = fmaf(w3, MH, pu);
+                        if (CLASS >= 1) {
+                            const float Sy = xf.sx - f0.w;
+                            pg = fmaf(w3, 2.f * a2 * m1 * inv5 + a2 * Sy - a3 * Sy * m2 * inv5, pg);
+                        }
+                        if (PDE) pt = fmaf(w3 * MH, -a * (xf.xt - f0.z), pt);
+                    }
+                    if (PDE) {
+                        const float kx = ex2f(v3[i]);
+                        float n1 = 0.f, n2 = 0.f, q2 = 0.f;
+#pragma unroll
+                        for (int m = 0; m < MC_IDX; ++m) {
+                            const float rx = xf.xir[m] - c[TF_YI + m];
+                            n1 += rx; n2 = fmaf(rx, rx, n2);
+                            const float q = xf.xir[m] - c[TF_YIR + m];
+                            q2 = fmaf(q, q, q2);
+                        }
+                        const float MHx = a2 * n2 * inv5 - a;
+                        const float Sx = xf.sxroll - sy, rxd = xf.x0 - yt;
+                        pl = fmaf(kx * dd, MHx * (A1 + A4 * a * rxd) + A5 * (-2.f * a2 * n1 * inv5 - a2 * Sx + a3 * Sx * n2 * inv5), pl);
+                        if (dom) {
+                            const float Aq = a2 * q2 - MC_IDX * a;
+                            pl = fmaf(A3d * (dd / (MC_IDX * MC_IDX)) * k, Aq * Aq + 2.f * MC_IDX * a2 - 4.f * a3 * q2, pl);
+                        }
+                    }
+                }
+            }
+            U += (double)pu;
+            if (CLASS >= 1) G += (double)pg;
+            if (PDE) { L += (double)pl; T += (double)pt; }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free[s]);
+        }
+        // combine the two centre halves of each point, apply K_i, write
+        if (half == 1) { xchg[r * 4 + 0] = U; xchg[r * 4 + 1] = G; xchg[r * 4 + 2] = L; xchg[r * 4 + 3] = T; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+            const long row = row0 + r;
+            if (row < R) {
+                const double ki = Ki[r];
+                const double u = ki * (U + xchg[r * 4 + 0]);
+                if (CLASS == 0) {
+                    if (mode == EVAL_TERMINAL) {
+                        const double* xr = X + row * (long)D;
+                        double sx = 0.0;
+                        for (int c = 0; c <= d; ++c) sx += xr[c];
+                        out0[row] = (1.0 - 1.0 / (1.0 + exp(sx))) - u;       // equations.py:259 minus u_hat
+                    } else out0[row] = u;
+                } else if (CLASS == 1) {
+                    out0[row] = u;
+                    out1[row] = ki * (G + xchg[r * 4 + 1]);
+                } else {
+                    const double g = ki * (G + xchg[r * 4 + 1]), l = ki * (L + xchg[r * 4 + 2]), tt = ki * (T + xchg[r * 4 + 3]);
+                    const double s2 = gp.sig2;
+                    out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;
+                    if (out1) out1[row] = g;
+                    if (out2) out2[row] = l;
+                    if (out3) out3[row] = tt;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+template <int CLASS, int KB>
+static size_t smem_bytes() {
+    constexpr int NA = (CLASS == 2) ? 4 : 2;
+    return 1024 + (size_t)NA * KB * A_BLK + 2 * (size_t)(2 * KB * B_BLK + TN * NF * 4) + TM * sizeof(XF) + TM * 8 + TM * 4 * 8 + 64;
+}
+
+template <int CLASS, int KB>
+static int launch(const GpView& gp, const TcState& st, const double* X, long R, int mode,
+                  double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
+    static bool configured = false;
+    const size_t smem = smem_bytes<CLASS, KB>();
+    if (!configured) {
+        SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    eval_tc_kernel<CLASS, KB><<<(unsigned)cdiv(R, TM), NTHREADS, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+}  // namespace tc
+
+// ---- host API --------------------------------------------------------------------------------------------------
+
+int tc_supported(const GpView& gp) { return gp.D <= 2 * tc::KBLK; }
+
+size_t tc_image_bytes(const GpView& gp, TcState* st) {
+    st->KB = (gp.D + tc::KBLK - 1) / tc::KBLK;
+    st->ntile_dom = gp.NdPad / tc::TN;
+    st->ntile_bdy = gp.NbPad / tc::TN;
+    st->tile_bytes = 2 * (size_t)st->KB * tc::B_BLK + (size_t)tc::TN * tc::NF * 4;
+    return (size_t)(st->ntile_dom + st->ntile_bdy) * st->tile_bytes;
+}
+
+int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d + 1 <= 128 (larger d: FP64 route)");
+    SC_REQUIRE(st.images != nullptr, "tc: image buffer is null");
+    tc::build_images_kernel<<<st.ntile_dom + st.ntile_bdy, 256, 0, stream>>>(gp, st);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
+                   double* out0, double* out1, double* out2, double* out3, cudaStream_t stream) {
+    if (R <= 0) return OK;
+    const TcState* st = (const TcState*)tc_state;
+    if (st == nullptr) st = (const TcState*)gp.tc;
+    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route: operand images not built (GP not fitted?)");
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d + 1 <= 128 (larger d: FP64 route)");
+    SC_REQUIRE(X && out0, "eval: null pointer");
+    const int KB = st->KB;
+    const int cls = (mode == EVAL_PDE) ? 2 : (mode == EVAL_UG ? 1 : 0);
+    if (cls == 1) SC_REQUIRE(out1 != nullptr, "eval UG: out1 is null");
+    if (KB == 1) {
+        if (cls == 0) return tc::launch<0, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+        if (cls == 1) return tc::launch<1, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+        return tc::launch<2, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+    }
+    if (cls == 0) return tc::launch<0, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+    if (cls == 1) return tc::launch<1, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+    return tc::launch<2, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+}
+
+int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
+                unsigned layout, unsigned kstep_bytes, cudaStream_t stream) {
+    SC_REQUIRE(K % tc::KBLK == 0 && K >= 64 && K <= 256, "selftest: K must be a multiple of 64");
+    SC_REQUIRE(N % 16 == 0 && N >= 16 && N <= 64, "selftest: N in [16, 64], multiple of 16");
+    const size_t smem = 1024 + (size_t)(K / tc::KBLK) * (tc::A_BLK + (size_t)N * 128);
+    SC_CUDA(cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::selftest_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N, lbo16, sbo16,
+                                                  layout, kstep_bytes);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
 }  // namespace scasml
