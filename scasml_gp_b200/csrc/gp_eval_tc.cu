@@ -9,10 +9,16 @@
 //   * the Gaussian factorises, k(x,y) = K_i K_j exp(a x.y) with K = exp(-a |.|^2 / 2): K_j is folded into the GP
 //     weights once per fit, K_i is applied once per point, so the epilogue does one ex2 per pair-distance
 //     directly on the accumulator (the scale a log2 e is folded into the A operand);
-//   * centre tiles (operand images in the 128B-swizzled K-major layout + FP32 feature records) are built once
-//     per fit and streamed with cp.async.bulk into a 2-stage ring; MMA of tile t+1 overlaps the epilogue of t;
-//   * epilogue: 8 warps, thread <-> (point row, half of the tile's centres), tcgen05.ld 32x32b, FP32 per-tile
-//     partial sums flushed into FP64 accumulators.
+//   * every functional is (polynomial in separable pair quantities) x Gaussian, so it is expanded once per fit into
+//     per-centre coefficient records against per-point monomials (sx, xt, sx^2, ...): the epilogue is a handful
+//     of FMAs per pair instead of the closed forms of SURVEY App. B evaluated pair by pair;
+//   * the 5-index sums of the rotated "Laplacian" (sum_m x_{I_m} y_{I_m+1} etc.) are partial sums of the same
+//     contractions: the K axis is permuted so the index-set columns sit in k-step 0 and their successors in an
+//     extra k-step 1, and three small MMAs (A[step a] x B[step b]) deliver them as extra TMEM accumulators;
+//   * centre tiles (operand images in the 128B-swizzled K-major layout + FP32 coefficient records) are built once
+//     per fit and streamed with cp.async.bulk into a 2-stage ring; MMA of item t+1 overlaps the epilogue of t;
+//   * epilogue: 16 warps, thread <-> (point row, quarter of the tile's centres), tcgen05.ld 32x32b.x16, FP32
+//     per-tile partial sums flushed into FP64 accumulators.
 // Accuracy: ~1e-7 absolute on u_hat (FP32 exponent); parity with the FP64 route is tested under the "nocast" policy.
 #include <cstring>
 #include "picard.cuh"
@@ -27,8 +33,10 @@ constexpr int TN = 64;               // centres per tile (UMMA N)
 constexpr int KBLK = 64;             // f16 elements per 128-byte swizzle row
 constexpr int A_BLK = TM * 128;      // bytes of one [128 x 64] f16 block
 constexpr int B_BLK = TN * 128;      // bytes of one [64 x 64] f16 block
-constexpr int NF = TC_NF;            // floats per centre feature record
-constexpr int NTHREADS = 320;        // 8 epilogue warps + producer warp + MMA warp
+constexpr int NFA = TC_NFA;          // floats per centre record, k / ky classes
+constexpr int NFB = TC_NFB;          // floats per centre record, kx class
+constexpr int NEPI = 16;             // epilogue warps
+constexpr int NTHREADS = (NEPI + 2) * 32;   // + producer warp + MMA warp
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -88,6 +96,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
                  : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -168,42 +184,88 @@ selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, floa
     if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
-// ---- operand images of the centres (built once per fit) ---------------------------------------------------
-// images: per tile t: [C image: KB blocks of [64 x 64] f16, swizzled][Croll image (domain tiles)][features 64 x NF f32]
+
+// ---- operand images + coefficient records of the centres (built once per fit) ------------------------------------
+// per tile t: [C image: KB blocks of [64 x 64] f16][Croll image (zeros for boundary tiles)][recA 64 x NFA f32][recB 64 x NFB f32]
+// K axis permuted by st.perm: k-step 0 = index-set columns I_m, k-step 1 = I_m + 1, k-steps >= 2 = all other columns.
 __global__ void build_images_kernel(GpView gp, TcState st) {
     const int tile = blockIdx.x;
     const bool dom = tile < st.ntile_dom;
     const int c0 = tile * TN;                          // padded centre index of the tile's first centre
     uint8_t* base = st.images + (size_t)tile * st.tile_bytes;
     const int D = gp.D, d = gp.d, KB = st.KB;
-    const double a = gp.a;
+    const double a = gp.a, a2 = a * a, a3 = a2 * a;
     for (int idx = threadIdx.x; idx < TN * KB * KBLK; idx += blockDim.x) {
         const int r = idx / (KB * KBLK), c = idx % (KB * KBLK);
+        const int src = st.perm[c];
         const double* y = gp.C + (size_t)(c0 + r) * D;
-        const double v = (c < D) ? y[c] : 0.0;
-        const double vr = (c < D) ? y[(c + 1 == D) ? 0 : c + 1] : 0.0;
+        const double v = (src >= 0) ? y[src] : 0.0;
+        const bool step1 = (c >= 16 && c < 32);
+        const double vr = (src >= 0 && !step1 && dom) ? y[(src + 1 == D) ? 0 : src + 1] : 0.0;
         const uint32_t off = (uint32_t)(c / KBLK) * B_BLK + sw128_off(r, c % KBLK);
         *(__half*)(base + off) = __double2half(v);
-        *(__half*)(base + (size_t)KB * B_BLK + off) = __double2half(dom ? vr : 0.0);
+        *(__half*)(base + (size_t)KB * B_BLK + off) = __double2half(vr);
     }
-    float* feat = (float*)(base + 2 * (size_t)KB * B_BLK);
+    float* recA = (float*)(base + 2 * (size_t)KB * B_BLK);
+    float* recB = recA + TN * NFA;
+    const double inv = st.inv_ascale;                  // accumulators carry a log2(e) x (dot product)
     for (int r = threadIdx.x; r < TN; r += blockDim.x) {
         const double* f = gp.feat + (size_t)(c0 + r) * CF_STRIDE;
         const double Kj = exp(-0.5 * a * f[CF_NY]);
-        float* o = feat + r * NF;
-        o[TF_SY] = (float)f[CF_SY]; o[TF_YT] = (float)f[CF_YT]; o[TF_Y0] = (float)f[CF_Y0]; o[TF_SYROLL] = (float)f[CF_SYROLL];
-        for (int m = 0; m < MC_IDX; ++m) { o[TF_YI + m] = (float)f[CF_YI + m]; o[TF_YIR + m] = (float)f[CF_YIR + m]; }
-        o[TF_A1] = (float)(f[CF_A1] * Kj);
-        o[TF_A3D] = (float)(f[CF_A3] * Kj * (double)d);
-        o[TF_A4] = (float)(f[CF_A4] * Kj);
-        o[TF_A5] = (float)(f[CF_A5] * Kj);
-        for (int i = TF_A5 + 1; i < NF; ++i) o[i] = 0.f;
+        const double A1 = f[CF_A1] * Kj, A3 = f[CF_A3] * Kj, A4 = f[CF_A4] * Kj, A5 = f[CF_A5] * Kj;
+        const double sy = f[CF_SY], yt = f[CF_YT], y0 = f[CF_Y0], syr = f[CF_SYROLL], dd = (double)d;
+        double Q1 = 0, Q2 = 0, T1 = 0, T2 = 0;
+        for (int m = 0; m < MC_IDX; ++m) {
+            Q1 += f[CF_YI + m]; Q2 += f[CF_YI + m] * f[CF_YI + m];
+            T1 += f[CF_YIR + m]; T2 += f[CF_YIR + m] * f[CF_YIR + m];
+        }
+        float* o = recA + r * NFA;
+        // k class, u:  A1 + a A4 (xt - yt) + a A5 (sx - sy)
+        o[RA_U0] = (float)(A1 - a * A4 * yt - a * A5 * sy);
+        o[RA_U1] = (float)(a * A4);
+        o[RA_U2] = (float)(a * A5);
+        // ky class, h = w3 (a^2/5 m2 - a), m2 = P2 + T2 - 2 e_y ; w3 = A3 d
+        const double w3 = A3 * dd;
+        o[RA_Y0] = (float)(w3 * (a2 / MC_IDX * T2 - a));
+        o[RA_Y1] = (float)(w3 * a2 / MC_IDX);
+        o[RA_Y2] = (float)(-2.0 * w3 * a2 / MC_IDX * inv);
+        // ky class, div_x:  w3 (2a^2/5 (P1 - T1)) - a Sy h
+        o[RA_Y3] = (float)(-w3 * 2.0 * a2 / MC_IDX * T1);
+        o[RA_Y4] = (float)(w3 * 2.0 * a2 / MC_IDX);
+        // k class, div_x:  -a S A1 - a^2 rt S A4 + (a d - a^2 S^2) A5
+        o[RA_G0] = (float)(a * A1 * sy - a2 * A4 * yt * sy + a * dd * A5 - a2 * A5 * sy * sy);
+        o[RA_GSX] = (float)(-a * A1 + a2 * A4 * yt + 2.0 * a2 * A5 * sy);
+        o[RA_GXT] = (float)(a2 * A4 * sy);
+        o[RA_GSXXT] = (float)(-a2 * A4);
+        o[RA_GSX2] = (float)(-a2 * A5);
+        o[RA_SYR] = (float)syr;
+        o[RA_Y0T] = (float)y0;
+        o[RA_T2] = (float)T2;
+        // k class, dt_x:  -a rt A1 + (a - a^2 rt^2) A4 - a^2 rt S A5
+        o[RA_T0] = (float)(a * A1 * yt + a * A4 - a2 * A4 * yt * yt - a2 * A5 * yt * sy);
+        o[RA_TXT] = (float)(-a * A1 + 2.0 * a2 * A4 * yt + a2 * A5 * sy);
+        o[RA_TSX] = (float)(a2 * A5 * yt);
+        o[RA_TXT2] = (float)(-a2 * A4);
+        o[RA_TSXXT] = (float)(-a2 * A5);
+        // k class, lap_x lap_y:  A3 d^2/25 (a^4 q2^2 - 14 a^3 q2 + 35 a^2)
+        o[RA_LW] = (float)(A3 * dd * dd / (MC_IDX * MC_IDX));
+        o[22] = 0.f; o[23] = 0.f;
+        // kx class:  d [ MHx (A1 + a A4 (x0 - yt) + a A5 (sxr - sy)) - 2a^2/5 A5 (R1 - Q1) ]
+        float* p = recB + r * NFB;
+        p[RB_X0] = (float)(dd * (A1 - a * A4 * yt - a * A5 * sy));
+        p[RB_X1] = (float)(dd * a * A4);
+        p[RB_X2] = (float)(dd * a * A5);
+        p[RB_X3] = (float)(dd * 2.0 * a2 / MC_IDX * A5 * Q1);
+        p[RB_X4] = (float)(-dd * 2.0 * a2 / MC_IDX * A5);
+        p[RB_Q2] = (float)Q2;
+        p[6] = 0.f; p[7] = 0.f;
+        (void)a3;
     }
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
 // CLASS 0: u (EVAL_U / EVAL_TERMINAL), 1: u + div_x u, 2: PDE residual.  KB: 64-wide K blocks (1 or 2).
-struct XF { float sx, xt, x0, sxroll, xi[MC_IDX], xir[MC_IDX]; };
+struct XF { float sx, xt, sx2, sxxt, xt2, P1, P2, R1, R2, x0, sxr, pad; };
 
 template <int CLASS, int KB>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -211,16 +273,17 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
     constexpr bool PDE = (CLASS == 2);
     constexpr int NA = PDE ? 4 : 2;                                   // A images: hi, lo (, roll hi, roll lo)
-    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK + TN * NF * 4;
+    constexpr int NSTEP = 4 * KB;                                     // k-steps of 16
+    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK + TN * NFA * 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;                                               // NA * KB * A_BLK
+    uint8_t* sA = smem;                                               // NA * KB * A_BLK (re-used as exchange buffer at the end)
     uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // 2 stages
     uint8_t* sMisc = sStage + 2 * (size_t)STAGE_BYTES;
     XF* xfeat = (XF*)sMisc;                                           // [128]
     double* Ki = (double*)(sMisc + TM * sizeof(XF));                  // [128]
-    double* xchg = Ki + TM;                                           // [128][4]
-    uint64_t* bars = (uint64_t*)(xchg + TM * 4);                      // full[2], accfull[2], free[2]
+    double* gterm = Ki + TM;                                          // [128]
+    uint64_t* bars = (uint64_t*)(gterm + TM);                         // full[2], acc[2], free[2]
     uint32_t* tmem_slot = (uint32_t*)(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -231,25 +294,26 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     const uint32_t bar_free[2] = {smem_u32(&bars[4]), smem_u32(&bars[5])};
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_full[s], 1); mbar_init(bar_acc[s], 1); mbar_init(bar_free[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_full[s], 1); mbar_init(bar_acc[s], 1); mbar_init(bar_free[s], NEPI); }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
 
-    // ---- build the A operand: a' x = hi + lo, swizzled f16 (and the rolled copy for the PDE rows) ----
+    // ---- build the A operand: a' x = hi + lo, permuted + swizzled f16 (and the rolled copy for the PDE rows) ----
     const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
-    if (warp < 8) {
-        for (int r = warp; r < TM; r += 8) {
+    if (warp < NEPI) {
+        for (int r = warp; r < TM; r += NEPI) {
             const long row = row0 + r;
+            const bool ok = row < R;
             const double* xr = X + row * (long)D;
             double nx = 0.0, sxs = 0.0;
+            if (ok) for (int c = lane; c < D; c += 32) { const double v = xr[c]; nx = fma(v, v, nx); if (c < d) sxs += v; }
             for (int c = lane; c < KB * KBLK; c += 32) {
+                const int src = st.perm[c];
                 double v = 0.0, vr = 0.0;
-                if (row < R && c < D) {
-                    v = xr[c];
-                    if (PDE) vr = xr[(c + 1 == D) ? 0 : c + 1];
-                    nx = fma(v, v, nx);
-                    if (c < d) sxs += v;
+                if (ok && src >= 0) {
+                    v = xr[src];
+                    if (PDE && !(c >= 16 && c < 32)) vr = xr[(src + 1 == D) ? 0 : src + 1];
                 }
                 const uint32_t off = (uint32_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK);
                 const double sv = ascale * v;
@@ -266,15 +330,18 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
             if (lane == 0) {
                 XF f;
-                const bool ok = row < R;
                 const double xt = ok ? xr[d] : 0.0, x0 = ok ? xr[0] : 0.0;
-                f.sx = (float)sxs; f.xt = (float)xt; f.x0 = (float)x0; f.sxroll = (float)(sxs - x0 + xt);
+                double P1 = 0, P2 = 0, R1 = 0, R2 = 0;
                 for (int m = 0; m < MC_IDX; ++m) {
-                    f.xi[m] = ok ? (float)xr[gp.I[m]] : 0.f;
-                    f.xir[m] = ok ? (float)xr[gp.I[m] + 1] : 0.f;
+                    const double xi = ok ? xr[gp.I[m]] : 0.0, xir = ok ? xr[gp.I[m] + 1] : 0.0;
+                    P1 += xi; P2 = fma(xi, xi, P2); R1 += xir; R2 = fma(xir, xir, R2);
                 }
+                f.sx = (float)sxs; f.xt = (float)xt; f.sx2 = (float)(sxs * sxs); f.sxxt = (float)(sxs * xt); f.xt2 = (float)(xt * xt);
+                f.P1 = (float)P1; f.P2 = (float)P2; f.R1 = (float)R1; f.R2 = (float)R2;
+                f.x0 = (float)x0; f.sxr = (float)(sxs - x0 + xt); f.pad = 0.f;
                 xfeat[r] = f;
                 Ki[r] = exp(-0.5 * gp.a * nx);
+                gterm[r] = 1.0 - 1.0 / (1.0 + exp(sxs + xt));                 // equations.py:259
             }
         }
         fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
@@ -284,135 +351,182 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int ntile = st.ntile_dom + st.ntile_bdy;
-    constexpr uint32_t ACC_STRIDE = 256;                              // TMEM columns per stage: d1 | d2 | d3 at +0/+64/+128
+    const int nitem = PDE ? 2 * ntile : ntile;
+    // TMEM columns.  CLASS 0/1: stage s at 192 s: d1 | d2 | e_y.  PDE: kind a at 0: d1 | d2 | e_y | e_q ; kind b at 256: d3 | e_x.
+    constexpr uint32_t ACC_STRIDE = PDE ? 256 : 192;
 
-    if (warp == 8) {
-        // ===== producer: stream centre tiles (operand images + feature records) =====
+    if (warp == NEPI) {
+        // ===== producer: stream centre tiles (operand images + coefficient records) =====
         if (lane == 0) {
-            for (int t = 0; t < ntile; ++t) {
-                const int s = t & 1;
-                if (t >= 2) mbar_wait(bar_free[s], ((t >> 1) - 1) & 1);
+            for (int w = 0; w < nitem; ++w) {
+                const int s = w & 1;
+                if (w >= 2) mbar_wait(bar_free[s], ((w >> 1) - 1) & 1);
+                const int t = PDE ? (w >> 1) : w;
+                const bool kindb = PDE && (w & 1);
                 const bool dom = t < st.ntile_dom;
                 const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
                 uint8_t* dst = sStage + (size_t)s * STAGE_BYTES;
-                const uint32_t bytes_c = KB * B_BLK, bytes_f = TN * NF * 4;
-                mbar_expect_tx(bar_full[s], bytes_c + (dom ? bytes_c : 0) + bytes_f);
-                bulk_g2s(smem_u32(dst), src, bytes_c, bar_full[s]);
-                if (dom) bulk_g2s(smem_u32(dst + bytes_c), src + bytes_c, bytes_c, bar_full[s]);
-                bulk_g2s(smem_u32(dst + 2 * bytes_c), src + 2 * bytes_c, bytes_f, bar_full[s]);
+                const uint32_t bytes_c = KB * B_BLK;
+                if (!kindb) {
+                    mbar_expect_tx(bar_full[s], bytes_c + (dom ? bytes_c : 0) + TN * NFA * 4);
+                    bulk_g2s(smem_u32(dst), src, bytes_c, bar_full[s]);
+                    if (dom) bulk_g2s(smem_u32(dst + bytes_c), src + bytes_c, bytes_c, bar_full[s]);
+                    bulk_g2s(smem_u32(dst + 2 * bytes_c), src + 2 * bytes_c, TN * NFA * 4, bar_full[s]);
+                } else {
+                    mbar_expect_tx(bar_full[s], bytes_c + TN * NFB * 4);
+                    bulk_g2s(smem_u32(dst), src, bytes_c, bar_full[s]);
+                    bulk_g2s(smem_u32(dst + 2 * bytes_c), src + 2 * bytes_c + TN * NFA * 4, TN * NFB * 4, bar_full[s]);
+                }
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == NEPI + 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TM, TN);
-            for (int t = 0; t < ntile; ++t) {
-                const int s = t & 1;
+            const uint32_t aBase = smem_u32(sA);
+            auto adesc = [&](int img, int step) {        // img: 0 hi, 1 lo, 2 roll hi, 3 roll lo
+                return make_desc(aBase + (uint32_t)(img * KB + (step >> 2)) * A_BLK + (step & 3) * 32, 1, 64, 2);
+            };
+            for (int w = 0; w < nitem; ++w) {
+                const int s = w & 1;
+                const int t = PDE ? (w >> 1) : w;
+                const bool kindb = PDE && (w & 1);
                 const bool dom = t < st.ntile_dom;
-                mbar_wait(bar_full[s], (t >> 1) & 1);
+                mbar_wait(bar_full[s], (w >> 1) & 1);
                 tc_fence_after();
                 const uint32_t sB = smem_u32(sStage + (size_t)s * STAGE_BYTES);
                 const uint32_t sBr = sB + KB * B_BLK;
-                const uint32_t acc = tmem_base + s * ACC_STRIDE;
-                // low halves first (tiny terms), then the high halves
+                auto bdesc = [&](uint32_t basep, int step) { return make_desc(basep + (uint32_t)(step >> 2) * B_BLK + (step & 3) * 32, 1, 64, 2); };
+                const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)s * ACC_STRIDE);
+                if (!kindb) {
+                    // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves
+                    uint32_t f1 = 0, f2 = 0;
 #pragma unroll
-                for (int half = 1; half >= 0; --half) {
+                    for (int half = 1; half >= 0; --half) {
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-                        for (int ks = 0; ks < KBLK / 16; ++ks) {
-                            const uint32_t first = (half == 1 && kb == 0 && ks == 0) ? 0u : 1u;
-                            const uint32_t aoff = (uint32_t)(half * KB + kb) * A_BLK + ks * 32;
-                            const uint64_t ad = make_desc(smem_u32(sA) + aoff, 1, 64, 2);
-                            const uint64_t bd = make_desc(sB + kb * B_BLK + ks * 32, 1, 64, 2);
-                            umma_f16(acc, ad, bd, idesc, first);
-                            if (dom) {
-                                const uint64_t brd = make_desc(sBr + kb * B_BLK + ks * 32, 1, 64, 2);
-                                umma_f16(acc + 64, ad, brd, idesc, first);
-                            }
-                            if (PDE) {
-                                const uint64_t ard = make_desc(smem_u32(sA) + (uint32_t)(2 * KB) * A_BLK + aoff, 1, 64, 2);
-                                umma_f16(acc + 128, ard, bd, idesc, first);
-                            }
+                        for (int step = 0; step < NSTEP; ++step) {
+                            if (step == 1) continue;
+                            const uint64_t ad = adesc(half, step);
+                            umma_f16(acc, ad, bdesc(sB, step), idesc, f1); f1 = 1;
+                            if (dom) { umma_f16(acc + 64, ad, bdesc(sBr, step), idesc, f2); f2 = 1; }
                         }
                     }
+                    if (dom) {
+                        // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x B[step 1]
+                        umma_f16(acc + 128, adesc(1, 0), bdesc(sB, 1), idesc, 0);
+                        umma_f16(acc + 128, adesc(0, 0), bdesc(sB, 1), idesc, 1);
+                        if (PDE) {   // e_q = sum_m x_{I_m+1} y_{I_m+1}: A[step 1] x B[step 1]
+                            umma_f16(acc + 192, adesc(1, 1), bdesc(sB, 1), idesc, 0);
+                            umma_f16(acc + 192, adesc(0, 1), bdesc(sB, 1), idesc, 1);
+                        }
+                    }
+                } else {
+                    uint32_t f3 = 0;
+#pragma unroll
+                    for (int half = 1; half >= 0; --half) {
+#pragma unroll
+                        for (int step = 0; step < NSTEP; ++step) {
+                            if (step == 1) continue;
+                            umma_f16(acc, adesc(2 + half, step), bdesc(sB, step), idesc, f3); f3 = 1;
+                        }
+                    }
+                    // e_x = sum_m x_{I_m+1} y_{I_m}: A[step 1] x B[step 0]
+                    umma_f16(acc + 64, adesc(1, 1), bdesc(sB, 0), idesc, 0);
+                    umma_f16(acc + 64, adesc(0, 1), bdesc(sB, 0), idesc, 1);
                 }
                 umma_commit(bar_acc[s]);
             }
         }
         __syncwarp();
     } else {
-        // ===== epilogue: thread <-> (point row, half of the tile's centres) =====
+        // ===== epilogue: thread <-> (point row, 16 of the tile's 64 centres) =====
         const int r = (warp & 3) * 32 + lane;
-        const int half = warp >> 2;                                  // centres [32*half, 32*half + 32) of each tile
+        const int cg = warp >> 2;                                    // centres [16 cg, 16 cg + 16) of each tile
         const XF xf = xfeat[r];
-        const float a = (float)gp.a, a2 = a * a, a3 = a2 * a, dd = (float)d, inv5 = 1.f / MC_IDX;
+        const float a = (float)gp.a, a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
+        const float m2inv = (float)(-2.0 * st.inv_ascale);
+        const float a2_5 = a2 / MC_IDX;
         double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        for (int t = 0; t < ntile; ++t) {
-            const int s = t & 1;
+        for (int w = 0; w < nitem; ++w) {
+            const int s = w & 1;
+            const int t = PDE ? (w >> 1) : w;
+            const bool kindb = PDE && (w & 1);
             const bool dom = t < st.ntile_dom;
-            mbar_wait(bar_full[s], (t >> 1) & 1);                     // feature records landed (async proxy -> this thread)
-            mbar_wait(bar_acc[s], (t >> 1) & 1);
+            mbar_wait(bar_full[s], (w >> 1) & 1);                     // coefficient records landed (async proxy -> this thread)
+            mbar_wait(bar_acc[s], (w >> 1) & 1);
             tc_fence_after();
-            const float* feat = (const float*)(sStage + (size_t)s * STAGE_BYTES + 2 * KB * B_BLK) + (half * 32) * NF;
-            const uint32_t acc = tmem_base + s * ACC_STRIDE + lane_addr + half * 32;
+            const uint8_t* stage = sStage + (size_t)s * STAGE_BYTES + 2 * KB * B_BLK;
+            const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)s * ACC_STRIDE) + lane_addr + cg * 16;
             float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
+            if (!kindb) {
+                constexpr int CH = PDE ? 8 : 16;                      // centres per TMEM load batch (register budget)
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                float v1[16], v2[16], v3[PDE ? 16 : 1];
-                tmem_ld16(acc + c0, v1);
-                if (dom) tmem_ld16(acc + 64 + c0, v2);
-                if (PDE) tmem_ld16(acc + 128 + c0, v3);
+                for (int cb = 0; cb < 16; cb += CH) {
+                float v1[CH], v2[CH], ve[CH], vq[PDE ? CH : 1];
+                if (PDE) {
+                    tmem_ld8(acc + cb, v1);
+                    if (dom) { tmem_ld8(acc + 64 + cb, v2); tmem_ld8(acc + 128 + cb, ve); tmem_ld8(acc + 192 + cb, vq); }
+                } else {
+                    tmem_ld16(acc, v1);
+                    if (dom) { tmem_ld16(acc + 64, v2); tmem_ld16(acc + 128, ve); }
+                }
                 tmem_ld_wait();
+                const float* rec = (const float*)stage + (cg * 16 + cb) * NFA;
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const float* c = rec + i * NFA;
+                    const float4 f0 = *(const float4*)(c);            // U0 U1 U2 Y0
+                    const float k = ex2f(v1[i]);
+                    pu = fmaf(k, fmaf(f0.z, xf.sx, fmaf(f0.y, xf.xt, f0.x)), pu);
+                    float ky = 0.f, h = 0.f;
+                    float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dom) {
+                        f1 = *(const float4*)(c + 4);                 // Y1 Y2 Y3 Y4
+                        ky = ex2f(v2[i]);
+                        h = fmaf(f1.y, ve[i], fmaf(f1.x, xf.P2, f0.w));
+                        pu = fmaf(ky, h, pu);
+                    }
+                    if (CLASS >= 1) {
+                        const float4 f2 = *(const float4*)(c + 8);    // G0 Gsx Gxt Gsxxt
+                        const float4 f3 = *(const float4*)(c + 12);   // Gsx2 syr y0 T2
+                        const float g = fmaf(f3.x, xf.sx2, fmaf(f2.w, xf.sxxt, fmaf(f2.z, xf.xt, fmaf(f2.y, xf.sx, f2.x))));
+                        pg = fmaf(k, g, pg);
+                        if (dom) {
+                            const float Sy = xf.sx - f3.y;
+                            pg = fmaf(ky, fmaf(-a * Sy, h, fmaf(f1.w, xf.P1, f1.z)), pg);
+                        }
+                        if (PDE) {
+                            const float4 f4 = *(const float4*)(c + 16);   // T0 Txt Tsx Txt2
+                            const float2 f5 = *(const float2*)(c + 20);   // Tsxxt Lw
+                            const float tt = fmaf(f5.x, xf.sxxt, fmaf(f4.w, xf.xt2, fmaf(f4.z, xf.sx, fmaf(f4.y, xf.xt, f4.x))));
+                            pt = fmaf(k, tt, pt);
+                            if (dom) {
+                                pt = fmaf(ky * h, -a * (xf.xt - f3.z), pt);
+                                const float q2 = fmaf(m2inv, vq[i], xf.R2 + f3.w);
+                                pl = fmaf(k * f5.y, fmaf(fmaf(a4, q2, -14.f * a3), q2, 35.f * a2), pl);
+                            }
+                        }
+                    }
+                }
+                }
+            } else {
+                float v3[16], vx[16];
+                tmem_ld16(acc, v3);
+                tmem_ld16(acc + 64, vx);
+                tmem_ld_wait();
+                const float* rec = (const float*)stage + (cg * 16) * NFB;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float* c = feat + (c0 + i) * NF;
-                    const float4 f0 = *(const float4*)(c);            // sy, yt, y0, syroll
-                    const float4 fa = *(const float4*)(c + TF_A1);    // A1, A3d, A4, A5
-                    const float sy = f0.x, yt = f0.y;
-                    const float A1 = fa.x, A3d = fa.y, A4 = fa.z, A5 = fa.w;
-                    const float S = xf.sx - sy, rt = xf.xt - yt;
-                    const float k = ex2f(v1[i]);
-                    pu = fmaf(k, A1 + a * (A4 * rt + A5 * S), pu);
-                    if (CLASS >= 1) pg = fmaf(k, -a * S * A1 - a2 * rt * S * A4 + (a * dd - a2 * S * S) * A5, pg);
-                    if (PDE) pt = fmaf(k, -a * rt * A1 + (a - a2 * rt * rt) * A4 - a2 * rt * S * A5, pt);
-                    if (dom) {
-                        const float ky = ex2f(v2[i]);
-                        float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-                        for (int m = 0; m < MC_IDX; ++m) {
-                            const float ry = xf.xi[m] - c[TF_YIR + m];
-                            m1 += ry; m2 = fmaf(ry, ry, m2);
-                        }
-                        const float MH = a2 * m2 * inv5 - a;
-                        const float w3 = ky * A3d;
-                        pu = fmaf(w3, MH, pu);
-                        if (CLASS >= 1) {
-                            const float Sy = xf.sx - f0.w;
-                            pg = fmaf(w3, 2.f * a2 * m1 * inv5 + a2 * Sy - a3 * Sy * m2 * inv5, pg);
-                        }
-                        if (PDE) pt = fmaf(w3 * MH, -a * (xf.xt - f0.z), pt);
-                    }
-                    if (PDE) {
-                        const float kx = ex2f(v3[i]);
-                        float n1 = 0.f, n2 = 0.f, q2 = 0.f;
-#pragma unroll
-                        for (int m = 0; m < MC_IDX; ++m) {
-                            const float rx = xf.xir[m] - c[TF_YI + m];
-                            n1 += rx; n2 = fmaf(rx, rx, n2);
-                            const float q = xf.xir[m] - c[TF_YIR + m];
-                            q2 = fmaf(q, q, q2);
-                        }
-                        const float MHx = a2 * n2 * inv5 - a;
-                        const float Sx = xf.sxroll - sy, rxd = xf.x0 - yt;
-                        pl = fmaf(kx * dd, MHx * (A1 + A4 * a * rxd) + A5 * (-2.f * a2 * n1 * inv5 - a2 * Sx + a3 * Sx * n2 * inv5), pl);
-                        if (dom) {
-                            const float Aq = a2 * q2 - MC_IDX * a;
-                            pl = fmaf(A3d * (dd / (MC_IDX * MC_IDX)) * k, Aq * Aq + 2.f * MC_IDX * a2 - 4.f * a3 * q2, pl);
-                        }
-                    }
+                    const float* c = rec + i * NFB;
+                    const float4 f0 = *(const float4*)(c);            // X0 X1 X2 X3
+                    const float2 f1 = *(const float2*)(c + 4);        // X4 Q2
+                    const float kx = ex2f(v3[i]);
+                    const float n2 = fmaf(m2inv, vx[i], xf.R2 + f1.y);
+                    const float MHx = fmaf(a2_5, n2, -a);
+                    const float p1 = fmaf(f0.z, xf.sxr, fmaf(f0.y, xf.x0, f0.x));
+                    pl = fmaf(kx, fmaf(MHx, p1, fmaf(f1.x, xf.R1, f0.w)), pl);
                 }
             }
             U += (double)pu;
@@ -422,28 +536,29 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_free[s]);
         }
-        // combine the two centre halves of each point, apply K_i, write
-        if (half == 1) { xchg[r * 4 + 0] = U; xchg[r * 4 + 1] = G; xchg[r * 4 + 2] = L; xchg[r * 4 + 3] = T; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (half == 0) {
+        // combine the four centre groups of each point (the A images are dead now: reuse them), apply K_i, write
+        double* xchg = (double*)sA;                                   // [4 groups][128 rows][4]
+        if (cg > 0) { double* p = xchg + ((size_t)cg * TM + r) * 4; p[0] = U; p[1] = G; p[2] = L; p[3] = T; }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (cg == 0) {
             const long row = row0 + r;
             if (row < R) {
+#pragma unroll
+                for (int g2 = 1; g2 < 4; ++g2) {
+                    const double* p = xchg + ((size_t)g2 * TM + r) * 4;
+                    U += p[0]; G += p[1]; L += p[2]; T += p[3];
+                }
                 const double ki = Ki[r];
-                const double u = ki * (U + xchg[r * 4 + 0]);
+                const double u = ki * U;
                 if (CLASS == 0) {
-                    if (mode == EVAL_TERMINAL) {
-                        const double* xr = X + row * (long)D;
-                        double sx = 0.0;
-                        for (int c = 0; c <= d; ++c) sx += xr[c];
-                        out0[row] = (1.0 - 1.0 / (1.0 + exp(sx))) - u;       // equations.py:259 minus u_hat
-                    } else out0[row] = u;
+                    out0[row] = (mode == EVAL_TERMINAL) ? gterm[r] - u : u;
                 } else if (CLASS == 1) {
                     out0[row] = u;
-                    out1[row] = ki * (G + xchg[r * 4 + 1]);
+                    out1[row] = ki * G;
                 } else {
-                    const double g = ki * (G + xchg[r * 4 + 1]), l = ki * (L + xchg[r * 4 + 2]), tt = ki * (T + xchg[r * 4 + 3]);
+                    const double g = ki * G, l = ki * L, tt = ki * T;
                     const double s2 = gp.sig2;
-                    out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;
+                    out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;   // GP.py:767-768
                     if (out1) out1[row] = g;
                     if (out2) out2[row] = l;
                     if (out3) out3[row] = tt;
@@ -453,13 +568,13 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
 }
 
 template <int CLASS, int KB>
 static size_t smem_bytes() {
     constexpr int NA = (CLASS == 2) ? 4 : 2;
-    return 1024 + (size_t)NA * KB * A_BLK + 2 * (size_t)(2 * KB * B_BLK + TN * NF * 4) + TM * sizeof(XF) + TM * 8 + TM * 4 * 8 + 64;
+    return 1024 + (size_t)NA * KB * A_BLK + 2 * (size_t)(2 * KB * B_BLK + TN * NFA * 4) + TM * sizeof(XF) + 2 * TM * 8 + 128;
 }
 
 template <int CLASS, int KB>
@@ -480,18 +595,26 @@ static int launch(const GpView& gp, const TcState& st, const double* X, long R, 
 
 // ---- host API --------------------------------------------------------------------------------------------------
 
-int tc_supported(const GpView& gp) { return gp.D <= 2 * tc::KBLK; }
+// k-steps 0 and 1 hold the index-set columns and their successors; the other d + 1 - 5 columns need <= 96 slots
+int tc_supported(const GpView& gp) { return gp.D - MC_IDX <= 2 * tc::KBLK - 32; }
 
 size_t tc_image_bytes(const GpView& gp, TcState* st) {
-    st->KB = (gp.D + tc::KBLK - 1) / tc::KBLK;
+    const int rest = gp.D - MC_IDX;
+    st->KB = (32 + rest + tc::KBLK - 1) / tc::KBLK;
     st->ntile_dom = gp.NdPad / tc::TN;
     st->ntile_bdy = gp.NbPad / tc::TN;
-    st->tile_bytes = 2 * (size_t)st->KB * tc::B_BLK + (size_t)tc::TN * tc::NF * 4;
+    st->tile_bytes = 2 * (size_t)st->KB * tc::B_BLK + (size_t)tc::TN * (tc::NFA + tc::NFB) * 4;
+    st->inv_ascale = 1.0 / (gp.a * 1.4426950408889634);
+    for (int c = 0; c < 128; ++c) st->perm[c] = -1;
+    bool in_set[1024] = {false};
+    for (int m = 0; m < MC_IDX; ++m) { st->perm[m] = (short)gp.I[m]; st->perm[16 + m] = (short)(gp.I[m] + 1); in_set[gp.I[m]] = true; }
+    int slot = 32;
+    for (int c = 0; c < gp.D && slot < 128; ++c) if (!in_set[c]) st->perm[slot++] = (short)c;
     return (size_t)(st->ntile_dom + st->ntile_bdy) * st->tile_bytes;
 }
 
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
-    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d + 1 <= 128 (larger d: FP64 route)");
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 100 (larger d: FP64 route)");
     SC_REQUIRE(st.images != nullptr, "tc: image buffer is null");
     tc::build_images_kernel<<<st.ntile_dom + st.ntile_bdy, 256, 0, stream>>>(gp, st);
     SC_LAUNCH_CHECK();
@@ -503,8 +626,8 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
-    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route: operand images not built (GP not fitted?)");
-    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d + 1 <= 128 (larger d: FP64 route)");
+    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route unavailable for this GP (d > 100 or not fitted): use the FP64 route");
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 100 (larger d: FP64 route)");
     SC_REQUIRE(X && out0, "eval: null pointer");
     const int KB = st->KB;
     const int cls = (mode == EVAL_PDE) ? 2 : (mode == EVAL_UG ? 1 : 0);

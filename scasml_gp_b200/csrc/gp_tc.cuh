@@ -1,27 +1,35 @@
-// tcgen05 route: per-fit operand images and feature records (gp_eval_tc.cu).
+// tcgen05 route: per-fit operand images and coefficient records (gp_eval_tc.cu).
 #pragma once
 #include "gp.cuh"
 
 namespace scasml {
 
-// FP32 centre feature record of the tcgen05 epilogue (weights pre-multiplied by K_j = exp(-a |y_j|^2 / 2))
-enum TcFeat : int {
-    TF_SY = 0, TF_YT = 1, TF_Y0 = 2, TF_SYROLL = 3,
-    TF_YI = 4,       // 5 values
-    TF_YIR = 9,      // 5 values
-    TF_A1 = 16, TF_A3D = 17, TF_A4 = 18, TF_A5 = 19,
+// FP32 coefficient records of the tcgen05 epilogue.  Every GP weight is pre-multiplied by K_j = exp(-a |y_j|^2 / 2);
+// the closed-form functionals are expanded against the per-point monomials
+// 1, sx, xt, sx^2, sx xt, xt^2 (sx = sum_i x_i, xt = time) and the 5-index sums P1, P2, R1, R2.
+enum TcRecA : int {          // k class (distance x - y) and ky class (x - roll y)
+    RA_U0 = 0, RA_U1 = 1, RA_U2 = 2, RA_Y0 = 3,
+    RA_Y1 = 4, RA_Y2 = 5, RA_Y3 = 6, RA_Y4 = 7,
+    RA_G0 = 8, RA_GSX = 9, RA_GXT = 10, RA_GSXXT = 11,
+    RA_GSX2 = 12, RA_SYR = 13, RA_Y0T = 14, RA_T2 = 15,
+    RA_T0 = 16, RA_TXT = 17, RA_TSX = 18, RA_TXT2 = 19,
+    RA_TSXXT = 20, RA_LW = 21,
 };
-constexpr int TC_NF = 20;
+enum TcRecB : int { RB_X0 = 0, RB_X1 = 1, RB_X2 = 2, RB_X3 = 3, RB_X4 = 4, RB_Q2 = 5 };   // kx class (roll x - y)
+constexpr int TC_NFA = 24;
+constexpr int TC_NFB = 8;
 
 struct TcState {
-    uint8_t* images = nullptr;   // per centre tile: [C image][Croll image][feature records]
+    uint8_t* images = nullptr;   // per centre tile: [C image][Croll image][records A][records B]
     size_t tile_bytes = 0;
-    int KB = 0;                  // 64-wide K blocks of the contraction (d + 1 <= 64 KB)
+    int KB = 0;                  // 64-wide K blocks of the permuted contraction axis
     int ntile_dom = 0, ntile_bdy = 0;
+    double inv_ascale = 0.0;     // 1 / (a log2 e): un-scales the 5-index accumulators
+    short perm[128];             // permuted K slot -> source coordinate (-1: zero padding)
 };
 
 int tc_supported(const GpView& gp);
-size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills KB / tile counts / tile_bytes
+size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills KB / tile counts / tile_bytes / perm
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
 int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
                 unsigned layout, unsigned kstep_bytes, cudaStream_t stream);
