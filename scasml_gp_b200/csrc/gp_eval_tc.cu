@@ -274,27 +274,36 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     constexpr bool PDE = (CLASS == 2);
     constexpr int NA = PDE ? 4 : 2;                                   // A images: hi, lo (, roll hi, roll lo)
     constexpr int NSTEP = 4 * KB;                                     // k-steps of 16
-    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK + TN * NFA * 4;
+    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK;                  // operand stage: C image | Croll image
+    constexpr uint32_t REC_BYTES = TN * NFA * 4;                      // coefficient-record slot
+    constexpr int NREC = 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                               // NA * KB * A_BLK (re-used as exchange buffer at the end)
-    uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // 2 stages
-    uint8_t* sMisc = sStage + 2 * (size_t)STAGE_BYTES;
+    uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // 2 operand stages, freed by the MMA commit
+    uint8_t* sRec = sStage + 2 * (size_t)STAGE_BYTES;                 // 4 record slots, freed by the epilogue
+    uint8_t* sMisc = sRec + NREC * (size_t)REC_BYTES;
     XF* xfeat = (XF*)sMisc;                                           // [128]
     double* Ki = (double*)(sMisc + TM * sizeof(XF));                  // [128]
     double* gterm = Ki + TM;                                          // [128]
-    uint64_t* bars = (uint64_t*)(gterm + TM);                         // full[2], acc[2], free[2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+    uint64_t* bars = (uint64_t*)(gterm + TM);                         // op_full[2] op_empty[2] acc_full[2] acc_free[2] rec_full[4] rec_free[4]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 16);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
     const long row0 = (long)blockIdx.x * TM;
-    const uint32_t bar_full[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
-    const uint32_t bar_acc[2] = {smem_u32(&bars[2]), smem_u32(&bars[3])};
-    const uint32_t bar_free[2] = {smem_u32(&bars[4]), smem_u32(&bars[5])};
+    const uint32_t op_full[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+    const uint32_t op_empty[2] = {smem_u32(&bars[2]), smem_u32(&bars[3])};
+    const uint32_t acc_full[2] = {smem_u32(&bars[4]), smem_u32(&bars[5])};
+    const uint32_t acc_free[2] = {smem_u32(&bars[6]), smem_u32(&bars[7])};
+    const uint32_t rec_full[4] = {smem_u32(&bars[8]), smem_u32(&bars[9]), smem_u32(&bars[10]), smem_u32(&bars[11])};
+    const uint32_t rec_free[4] = {smem_u32(&bars[12]), smem_u32(&bars[13]), smem_u32(&bars[14]), smem_u32(&bars[15])};
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_full[s], 1); mbar_init(bar_acc[s], 1); mbar_init(bar_free[s], NEPI); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(op_full[s], 1); mbar_init(op_empty[s], 1); mbar_init(acc_full[s], 1); mbar_init(acc_free[s], NEPI);
+        }
+        for (int q = 0; q < NREC; ++q) { mbar_init(rec_full[q], 1); mbar_init(rec_free[q], NEPI); }
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -356,26 +365,29 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     constexpr uint32_t ACC_STRIDE = PDE ? 256 : 192;
 
     if (warp == NEPI) {
-        // ===== producer: stream centre tiles (operand images + coefficient records) =====
+        // ===== producer: stream centre tiles (operand images) and coefficient records =====
         if (lane == 0) {
             for (int w = 0; w < nitem; ++w) {
-                const int s = w & 1;
-                if (w >= 2) mbar_wait(bar_free[s], ((w >> 1) - 1) & 1);
+                const int s = w & 1, q = w & 3;
+                if (w >= 2) mbar_wait(op_empty[s], ((w >> 1) - 1) & 1);       // MMAs of item w-2 have read the stage
+                if (w >= 4) mbar_wait(rec_free[q], ((w >> 2) - 1) & 1);       // epilogue of item w-4 is done with the slot
                 const int t = PDE ? (w >> 1) : w;
                 const bool kindb = PDE && (w & 1);
                 const bool dom = t < st.ntile_dom;
                 const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
                 uint8_t* dst = sStage + (size_t)s * STAGE_BYTES;
+                uint8_t* rdst = sRec + (size_t)q * REC_BYTES;
                 const uint32_t bytes_c = KB * B_BLK;
+                const bool need_roll = dom && !kindb;
+                mbar_expect_tx(op_full[s], bytes_c + (need_roll ? bytes_c : 0));
+                bulk_g2s(smem_u32(dst), src, bytes_c, op_full[s]);
+                if (need_roll) bulk_g2s(smem_u32(dst + bytes_c), src + bytes_c, bytes_c, op_full[s]);
                 if (!kindb) {
-                    mbar_expect_tx(bar_full[s], bytes_c + (dom ? bytes_c : 0) + TN * NFA * 4);
-                    bulk_g2s(smem_u32(dst), src, bytes_c, bar_full[s]);
-                    if (dom) bulk_g2s(smem_u32(dst + bytes_c), src + bytes_c, bytes_c, bar_full[s]);
-                    bulk_g2s(smem_u32(dst + 2 * bytes_c), src + 2 * bytes_c, TN * NFA * 4, bar_full[s]);
+                    mbar_expect_tx(rec_full[q], TN * NFA * 4);
+                    bulk_g2s(smem_u32(rdst), src + 2 * bytes_c, TN * NFA * 4, rec_full[q]);
                 } else {
-                    mbar_expect_tx(bar_full[s], bytes_c + TN * NFB * 4);
-                    bulk_g2s(smem_u32(dst), src, bytes_c, bar_full[s]);
-                    bulk_g2s(smem_u32(dst + 2 * bytes_c), src + 2 * bytes_c + TN * NFA * 4, TN * NFB * 4, bar_full[s]);
+                    mbar_expect_tx(rec_full[q], TN * NFB * 4);
+                    bulk_g2s(smem_u32(rdst), src + 2 * bytes_c + TN * NFA * 4, TN * NFB * 4, rec_full[q]);
                 }
             }
         }
@@ -393,7 +405,8 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 const int t = PDE ? (w >> 1) : w;
                 const bool kindb = PDE && (w & 1);
                 const bool dom = t < st.ntile_dom;
-                mbar_wait(bar_full[s], (w >> 1) & 1);
+                mbar_wait(op_full[s], (w >> 1) & 1);
+                if (w >= 2) mbar_wait(acc_free[s], ((w >> 1) - 1) & 1);       // epilogue of item w-2 drained the TMEM stage
                 tc_fence_after();
                 const uint32_t sB = smem_u32(sStage + (size_t)s * STAGE_BYTES);
                 const uint32_t sBr = sB + KB * B_BLK;
@@ -435,7 +448,8 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                     umma_f16(acc + 64, adesc(1, 1), bdesc(sB, 0), idesc, 0);
                     umma_f16(acc + 64, adesc(0, 1), bdesc(sB, 0), idesc, 1);
                 }
-                umma_commit(bar_acc[s]);
+                umma_commit(op_empty[s]);                                     // operand stage reusable
+                umma_commit(acc_full[s]);                                     // accumulators ready
             }
         }
         __syncwarp();
@@ -454,10 +468,11 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             const int t = PDE ? (w >> 1) : w;
             const bool kindb = PDE && (w & 1);
             const bool dom = t < st.ntile_dom;
-            mbar_wait(bar_full[s], (w >> 1) & 1);                     // coefficient records landed (async proxy -> this thread)
-            mbar_wait(bar_acc[s], (w >> 1) & 1);
+            const int q = w & 3;
+            mbar_wait(rec_full[q], (w >> 2) & 1);                     // coefficient records landed
+            mbar_wait(acc_full[s], (w >> 1) & 1);
             tc_fence_after();
-            const uint8_t* stage = sStage + (size_t)s * STAGE_BYTES + 2 * KB * B_BLK;
+            const uint8_t* stage = sRec + (size_t)q * REC_BYTES;
             const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)s * ACC_STRIDE) + lane_addr + cg * 16;
             float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
             if (!kindb) {
@@ -534,7 +549,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             if (PDE) { L += (double)pl; T += (double)pt; }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_free[s]);
+            if (lane == 0) { mbar_arrive(acc_free[s]); mbar_arrive(rec_free[q]); }
         }
         // combine the four centre groups of each point (the A images are dead now: reuse them), apply K_i, write
         double* xchg = (double*)sA;                                   // [4 groups][128 rows][4]
@@ -574,7 +589,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
 template <int CLASS, int KB>
 static size_t smem_bytes() {
     constexpr int NA = (CLASS == 2) ? 4 : 2;
-    return 1024 + (size_t)NA * KB * A_BLK + 2 * (size_t)(2 * KB * B_BLK + TN * NFA * 4) + TM * sizeof(XF) + 2 * TM * 8 + 128;
+    return 1024 + (size_t)NA * KB * A_BLK + 2 * (size_t)(2 * KB * B_BLK) + 4 * (size_t)(TN * NFA * 4) + TM * sizeof(XF) + 2 * TM * 8 + 256;
 }
 
 template <int CLASS, int KB>

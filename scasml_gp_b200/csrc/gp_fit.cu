@@ -427,6 +427,55 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(const double* __restrict
     }
 }
 
+// solve (L L^T) x = rhs for the blocked Cholesky factor (row-major, lower) using the stored inverses of the
+// 64x64 diagonal blocks; single CTA, x overwrites rhs.  Used for the SPD Newton systems.
+__global__ void __launch_bounds__(256) chol_solve_kernel(const double* __restrict__ Lm, long n,
+                                                          const double* __restrict__ invdiag, double* __restrict__ x) {
+    __shared__ double tvec[CB];
+    __shared__ double part[4][CB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long nblk = (n + CB - 1) / CB;
+    // forward: L y = rhs
+    for (long b = 0; b < nblk; ++b) {
+        const long b0 = b * CB;
+        const int nb = (int)((n - b0 < CB) ? (n - b0) : CB);
+        for (int r = wid; r < nb; r += 8) {
+            const double* row = Lm + (b0 + r) * n;
+            double acc = 0.0;
+            for (long j = lane; j < b0; j += 32) acc = fma(row[j], x[j], acc);
+            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) tvec[r] = x[b0 + r] - acc;
+        }
+        __syncthreads();
+        const double* inv = invdiag + b * CB * CB;
+        if (tid < nb) {
+            double acc = 0.0;
+            for (int c = 0; c <= tid; ++c) acc = fma(inv[tid * CB + c], tvec[c], acc);
+            x[b0 + tid] = acc;
+        }
+        __syncthreads();
+    }
+    // backward: L^T x = y
+    for (long b = nblk - 1; b >= 0; --b) {
+        const long b0 = b * CB;
+        const int nb = (int)((n - b0 < CB) ? (n - b0) : CB);
+        const int g = tid >> 6, c = tid & 63;
+        double acc = 0.0;
+        if (c < nb) for (long i = b0 + CB + g; i < n; i += 4) acc = fma(Lm[i * n + b0 + c], x[i], acc);
+        part[g][c] = acc;
+        __syncthreads();
+        if (tid < nb) tvec[tid] = x[b0 + tid] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
+        __syncthreads();
+        const double* inv = invdiag + b * CB * CB;
+        if (tid < nb) {
+            double a2 = 0.0;
+            for (int r = tid; r < nb; ++r) a2 = fma(inv[r * CB + tid], tvec[r], a2);   // (inv L_bb)^T
+            x[b0 + tid] = a2;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ host drivers --------------------------
@@ -521,7 +570,8 @@ size_t fit_workspace_bytes(int Nd, int Nb) {
     bytes += nblk * CB * CB * 8;       // diagonal-block inverses
     bytes += CB * phi * 8;             // tmp
     bytes += (4 * phi + 4 * n3 + 64) * 8;
-    return bytes + 4096;
+    bytes += ((n3 + CB - 1) / CB) * CB * CB * 8;   // diagonal-block inverses of the Newton system
+    return bytes + 8192;
 }
 
 // The whole fit.  Returns alpha (device, [phi]) and the loss history (host).
@@ -546,6 +596,8 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
     double* rhs = take(n3 * 8);
     double* scal = take(64);
     int* d_fail = (int*)take(64);
+    int* d_fail2 = (int*)take(64);
+    double* invh = take((size_t)cdiv(n3, CB) * CB * CB * 8);
     double* H = X;                                  // reuse after P is formed
     SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
 
@@ -592,8 +644,23 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
         if (std::sqrt(g2) < tol) break;                                  // models/GP.py:521
         hessian_kernel<<<(unsigned)cdiv(n3 * n3, 256), 256, 0, st>>>(f, sol, w, P, damping, H);
         SC_LAUNCH_CHECK();
-        rc = lu_solve_inplace(H, n3, rhs, d_fail, st);
+        // The damped Hessian is symmetric and, near the solution, positive definite: blocked Cholesky first.
+        // A non-positive pivot falls back to LU with partial pivoting (what the reference's jnp.linalg.solve does).
+        SC_CUDA(cudaMemsetAsync(d_fail2, 0, sizeof(int), st));
+        rc = cholesky_lower(H, n3, invh, d_fail2, st);
         if (rc != OK) return rc;
+        int h_fail2 = 0;
+        SC_CUDA(cudaMemcpyAsync(&h_fail2, d_fail2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SC_CUDA(cudaStreamSynchronize(st));
+        if (!h_fail2) {
+            chol_solve_kernel<<<1, 256, 0, st>>>(H, n3, invh, rhs);
+            SC_LAUNCH_CHECK();
+        } else {
+            hessian_kernel<<<(unsigned)cdiv(n3 * n3, 256), 256, 0, st>>>(f, sol, w, P, damping, H);
+            SC_LAUNCH_CHECK();
+            rc = lu_solve_inplace(H, n3, rhs, d_fail, st);
+            if (rc != OK) return rc;
+        }
         axpy_kernel<<<(unsigned)cdiv(n3, 256), 256, 0, st>>>(n3, 1.0, rhs, sol);
         SC_LAUNCH_CHECK();
         rc = loss_now(&loss_hist_host[nh++]);
