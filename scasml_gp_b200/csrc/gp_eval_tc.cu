@@ -277,8 +277,9 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK;                  // operand stage: C image | Croll image
     constexpr uint32_t REC_BYTES = TN * NFA * 4;                      // coefficient-record slot
     constexpr int NREC = 4;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];             // no static smem in this kernel: window offset 0
+    uint8_t* smem = smem_raw;                                         // (plain pointer arithmetic keeps LDS/STS codegen)
+    if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
     uint8_t* sA = smem;                                               // NA * KB * A_BLK (re-used as exchange buffer at the end)
     uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // 2 operand stages, freed by the MMA commit
     uint8_t* sRec = sStage + 2 * (size_t)STAGE_BYTES;                 // 4 record slots, freed by the epilogue
@@ -309,51 +310,98 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
 
     // ---- build the A operand: a' x = hi + lo, permuted + swizzled f16 (and the rolled copy for the PDE rows) ----
+    // All global loads of a warp's 8 rows are issued before the first use (the prologue is latency-bound otherwise).
     const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
     if (warp < NEPI) {
+        constexpr int RPW = TM / NEPI;                                // rows per warp
+        int slot_m[4], slot_1[4], slot_r[4];                          // this lane's columns -> permuted slots
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            slot_m[q] = (c < D) ? st.iperm[c] : 0;
+            slot_1[q] = (c < D) ? st.iperm1[c] : -1;
+            slot_r[q] = (c < D) ? st.iperm[(c == 0) ? D - 1 : c - 1] : 0;
+        }
+        double v[RPW][4];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const long row = row0 + warp + NEPI * i;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                v[i][q] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
+            }
+        }
+        // zero padding slots (k-step padding and, for the rolled images, the whole k-step 1)
         for (int r = warp; r < TM; r += NEPI) {
-            const long row = row0 + r;
-            const bool ok = row < R;
-            const double* xr = X + row * (long)D;
-            double nx = 0.0, sxs = 0.0;
-            if (ok) for (int c = lane; c < D; c += 32) { const double v = xr[c]; nx = fma(v, v, nx); if (c < d) sxs += v; }
             for (int c = lane; c < KB * KBLK; c += 32) {
-                const int src = st.perm[c];
-                double v = 0.0, vr = 0.0;
-                if (ok && src >= 0) {
-                    v = xr[src];
-                    if (PDE && !(c >= 16 && c < 32)) vr = xr[(src + 1 == D) ? 0 : src + 1];
-                }
                 const uint32_t off = (uint32_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK);
-                const double sv = ascale * v;
-                const __half h = __double2half(sv);
-                *(__half*)(sA + off) = h;
-                *(__half*)(sA + (size_t)KB * A_BLK + off) = __double2half(sv - (double)__half2float(h));
-                if (PDE) {
-                    const double svr = ascale * vr;
-                    const __half hr = __double2half(svr);
-                    *(__half*)(sA + 2 * (size_t)KB * A_BLK + off) = hr;
-                    *(__half*)(sA + 3 * (size_t)KB * A_BLK + off) = __double2half(svr - (double)__half2float(hr));
+                const bool pad = st.perm[c] < 0;
+                if (pad) { *(__half*)(sA + off) = __half(); *(__half*)(sA + (size_t)KB * A_BLK + off) = __half(); }
+                if (PDE && (pad || (c >= 16 && c < 32))) {
+                    *(__half*)(sA + 2 * (size_t)KB * A_BLK + off) = __half();
+                    *(__half*)(sA + 3 * (size_t)KB * A_BLK + off) = __half();
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int r = warp + NEPI * i;
+            double nx = 0.0, sxs = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                if (c < D) {
+                    const double val = v[i][q];
+                    nx = fma(val, val, nx);
+                    if (c < d) sxs += val;
+                    const double sv = ascale * val;
+                    const __half h = __double2half(sv);
+                    const __half lo = __double2half(sv - (double)__half2float(h));
+                    const int slot = slot_m[q];
+                    const uint32_t off = (uint32_t)(slot / KBLK) * A_BLK + sw128_off(r, slot % KBLK);
+                    *(__half*)(sA + off) = h;
+                    *(__half*)(sA + (size_t)KB * A_BLK + off) = lo;
+                    const int s1 = slot_1[q];
+                    if (s1 >= 0) {
+                        const uint32_t off1 = (uint32_t)(s1 / KBLK) * A_BLK + sw128_off(r, s1 % KBLK);
+                        *(__half*)(sA + off1) = h;
+                        *(__half*)(sA + (size_t)KB * A_BLK + off1) = lo;
+                    }
+                    if (PDE) {                                        // roll(x)_{c-1} = x_c
+                        const int sr = slot_r[q];
+                        const uint32_t offr = (uint32_t)(sr / KBLK) * A_BLK + sw128_off(r, sr % KBLK);
+                        *(__half*)(sA + 2 * (size_t)KB * A_BLK + offr) = h;
+                        *(__half*)(sA + 3 * (size_t)KB * A_BLK + offr) = lo;
+                    }
                 }
             }
             for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
-            if (lane == 0) {
-                XF f;
-                const double xt = ok ? xr[d] : 0.0, x0 = ok ? xr[0] : 0.0;
-                double P1 = 0, P2 = 0, R1 = 0, R2 = 0;
-                for (int m = 0; m < MC_IDX; ++m) {
-                    const double xi = ok ? xr[gp.I[m]] : 0.0, xir = ok ? xr[gp.I[m] + 1] : 0.0;
-                    P1 += xi; P2 = fma(xi, xi, P2); R1 += xir; R2 = fma(xir, xir, R2);
-                }
-                f.sx = (float)sxs; f.xt = (float)xt; f.sx2 = (float)(sxs * sxs); f.sxxt = (float)(sxs * xt); f.xt2 = (float)(xt * xt);
-                f.P1 = (float)P1; f.P2 = (float)P2; f.R1 = (float)R1; f.R2 = (float)R2;
-                f.x0 = (float)x0; f.sxr = (float)(sxs - x0 + xt); f.pad = 0.f;
-                xfeat[r] = f;
-                Ki[r] = exp(-0.5 * gp.a * nx);
-                gterm[r] = 1.0 - 1.0 / (1.0 + exp(sxs + xt));                 // equations.py:259
-            }
+            if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
         }
         fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid < TM) {
+            const int r = tid;
+            const long row = row0 + r;
+            const bool ok = row < R;
+            const double* xr = X + row * (long)D;
+            const double nx = Ki[r], sxs = gterm[r];
+            const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+            double P1 = 0, P2 = 0, R1 = 0, R2 = 0;
+#pragma unroll
+            for (int m = 0; m < MC_IDX; ++m) {
+                const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                P1 += xi; P2 = fma(xi, xi, P2); R1 += xir; R2 = fma(xir, xir, R2);
+            }
+            XF f;
+            f.sx = (float)sxs; f.xt = (float)xt; f.sx2 = (float)(sxs * sxs); f.sxxt = (float)(sxs * xt); f.xt2 = (float)(xt * xt);
+            f.P1 = (float)P1; f.P2 = (float)P2; f.R1 = (float)R1; f.R2 = (float)R2;
+            f.x0 = (float)x0; f.sxr = (float)(sxs - x0 + xt); f.pad = 0.f;
+            xfeat[r] = f;
+            Ki[r] = exp(-0.5 * gp.a * nx);
+            gterm[r] = 1.0 - 1.0 / (1.0 + exp(sxs + xt));                     // equations.py:259
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -625,6 +673,12 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
     for (int m = 0; m < MC_IDX; ++m) { st->perm[m] = (short)gp.I[m]; st->perm[16 + m] = (short)(gp.I[m] + 1); in_set[gp.I[m]] = true; }
     int slot = 32;
     for (int c = 0; c < gp.D && slot < 128; ++c) if (!in_set[c]) st->perm[slot++] = (short)c;
+    for (int c = 0; c < 128; ++c) { st->iperm[c] = 0; st->iperm1[c] = -1; }
+    for (int k = 0; k < 128; ++k) {
+        const int c = st->perm[k];
+        if (c < 0) continue;
+        if (k >= 16 && k < 32) st->iperm1[c] = (short)k; else st->iperm[c] = (short)k;
+    }
     return (size_t)(st->ntile_dom + st->ntile_bdy) * st->tile_bytes;
 }
 

@@ -26,6 +26,8 @@ struct TcState {
     int ntile_dom = 0, ntile_bdy = 0;
     double inv_ascale = 0.0;     // 1 / (a log2 e): un-scales the 5-index accumulators
     short perm[128];             // permuted K slot -> source coordinate (-1: zero padding)
+    short iperm[128];            // source coordinate -> slot in k-steps {0, 2, 3, ...}
+    short iperm1[128];           // source coordinate -> slot in k-step 1 (successors of the index set), else -1
 };
 
 int tc_supported(const GpView& gp);
