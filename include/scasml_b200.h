@@ -148,7 +148,12 @@ SCASML_API int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev
  * layout, descriptors, tcgen05.mma and tcgen05.ld helpers as the evaluation kernel (descriptor fields at run time) */
 SCASML_API int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* D_dev, int K, int N, unsigned lbo16,
                          unsigned sbo16, unsigned layout, unsigned kstep_bytes, void* stream);
-/* 1 if this handle can use SCASML_ROUTE_TC (d + 1 <= 128) */
+/* test hook: SM-clock timeline of CTA `block` of one tcgen05 evaluation launch (stamps_dev: 256 int64; scratch_dev: 4 R doubles).
+ * [0] entry [1] operand scatter done [2] prologue done [3] exit; item w: [4+4w] MMA issue start, [5+4w] MMA issue end,
+ * [6+4w] epilogue start, [7+4w] epilogue end */
+SCASML_API int scasml_debug_tc_timeline(const scasml_gp* gp, const double* X_dev, long long R, int mode, int block,
+                             long long* stamps_dev, double* scratch_dev, void* stream);
+/* 1 if this handle can use SCASML_ROUTE_TC (d <= 100) */
 SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 
 #ifdef __cplusplus

@@ -342,6 +342,12 @@ int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* 
     return tc_selftest(A_half_dev, B_half_dev, D_dev, K, N, lbo16, sbo16, layout, kstep_bytes, (cudaStream_t)stream);
 }
 
+int scasml_debug_tc_timeline(const scasml_gp* g, const double* X_dev, long long R, int mode, int block,
+                             long long* stamps_dev, double* scratch_dev, void* stream) {
+    SC_REQUIRE(g && g->has_alpha && g->tc.images, "debug_tc_timeline: tcgen05 route unavailable");
+    return tc_timeline(g->v, g->tc, X_dev, (long)R, mode, block, stamps_dev, scratch_dev, (cudaStream_t)stream);
+}
+
 int scasml_gp_tc_supported(const scasml_gp* g) { return (g && g->tc.images) ? 1 : 0; }
 
 int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream) {

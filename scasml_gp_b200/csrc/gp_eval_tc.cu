@@ -293,6 +293,9 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
     const long row0 = (long)blockIdx.x * TM;
+    long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
+#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
+    if (tid == 0) TC_STAMP(0);
     const uint32_t op_full[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
     const uint32_t op_empty[2] = {smem_u32(&bars[2]), smem_u32(&bars[3])};
     const uint32_t acc_full[2] = {smem_u32(&bars[4]), smem_u32(&bars[5])};
@@ -380,6 +383,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
         }
         fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
+        if (tid == 0) TC_STAMP(1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (tid < TM) {
             const int r = tid;
@@ -406,6 +410,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) TC_STAMP(2);
     const uint32_t tmem_base = *tmem_slot;
     const int ntile = st.ntile_dom + st.ntile_bdy;
     const int nitem = PDE ? 2 * ntile : ntile;
@@ -456,6 +461,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 mbar_wait(op_full[s], (w >> 1) & 1);
                 if (w >= 2) mbar_wait(acc_free[s], ((w >> 1) - 1) & 1);       // epilogue of item w-2 drained the TMEM stage
                 tc_fence_after();
+                TC_STAMP(4 + 4 * w);
                 const uint32_t sB = smem_u32(sStage + (size_t)s * STAGE_BYTES);
                 const uint32_t sBr = sB + KB * B_BLK;
                 auto bdesc = [&](uint32_t basep, int step) { return make_desc(basep + (uint32_t)(step >> 2) * B_BLK + (step & 3) * 32, 1, 64, 2); };
@@ -498,6 +504,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 }
                 umma_commit(op_empty[s]);                                     // operand stage reusable
                 umma_commit(acc_full[s]);                                     // accumulators ready
+                TC_STAMP(5 + 4 * w);
             }
         }
         __syncwarp();
@@ -520,6 +527,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             mbar_wait(rec_full[q], (w >> 2) & 1);                     // coefficient records landed
             mbar_wait(acc_full[s], (w >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) TC_STAMP(6 + 4 * w);
             const uint8_t* stage = sRec + (size_t)q * REC_BYTES;
             const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)s * ACC_STRIDE) + lane_addr + cg * 16;
             float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
@@ -597,6 +605,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
             if (PDE) { L += (double)pl; T += (double)pt; }
             tc_fence_before();
             __syncwarp();
+            if (tid == 0) TC_STAMP(7 + 4 * w);
             if (lane == 0) { mbar_arrive(acc_free[s]); mbar_arrive(rec_free[q]); }
         }
         // combine the four centre groups of each point (the A images are dead now: reuse them), apply K_i, write
@@ -631,7 +640,9 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) TC_STAMP(3);
     if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
+#undef TC_STAMP
 }
 
 template <int CLASS, int KB>
@@ -709,6 +720,16 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     if (cls == 0) return tc::launch<0, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
     if (cls == 1) return tc::launch<1, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
     return tc::launch<2, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+}
+
+// timeline of one CTA: stamps[0] entry, [1] operand scatter done, [2] prologue done, [3] exit,
+// item w: [4+4w] MMA issue start, [5+4w] MMA issue end, [6+4w] epilogue start, [7+4w] epilogue end   (SM clock cycles)
+int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
+                double* scratch_out, cudaStream_t stream) {
+    TcState dbgst = st;
+    dbgst.dbg = stamps_dev;
+    dbgst.dbg_block = block;
+    return launch_eval_tc(gp, &dbgst, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream);
 }
 
 int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,

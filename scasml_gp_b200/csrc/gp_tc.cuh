@@ -28,11 +28,15 @@ struct TcState {
     short perm[128];             // permuted K slot -> source coordinate (-1: zero padding)
     short iperm[128];            // source coordinate -> slot in k-steps {0, 2, 3, ...}
     short iperm1[128];           // source coordinate -> slot in k-step 1 (successors of the index set), else -1
+    long long* dbg = nullptr;    // optional timeline buffer (clock64 stamps of CTA dbg_block), see scasml_debug_tc_timeline
+    int dbg_block = 0;
 };
 
 int tc_supported(const GpView& gp);
 size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills KB / tile counts / tile_bytes / perm
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
+int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
+                double* scratch_out, cudaStream_t stream);
 int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
                 unsigned layout, unsigned kstep_bytes, cudaStream_t stream);
 

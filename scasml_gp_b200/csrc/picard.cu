@@ -178,103 +178,133 @@ __device__ __forceinline__ int find_call(const LevelDev& lv, long long R) {
 
 __device__ __forceinline__ long long ceil_div_pos(long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; }
 
+// Sampler kernels.  A thread owns one Philox block (8 consecutive flat indices) of one point; the CTA stages its
+// points in shared memory and writes them out as one contiguous, fully coalesced range of the level's point buffer.
+constexpr int SAMPLE_THREADS = 256;
+constexpr int SAMPLE_TILE = 2304;      // doubles; (256 / nslot) * (d + 1) < 2048 for every d with nslot <= 256
+
 // terminal points X_T = x + mu (T-t) + sigma sqrt(T-t) N   (solvers/ScaSML.py:190-198)
-__global__ void __launch_bounds__(256) sample_terminal_kernel(LevelDev lv) {
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_terminal_kernel(LevelDev lv, int ppb) {
+    __shared__ double tile[SAMPLE_TILE];
     const int d = lv.d, D = lv.D;
     const int nslot = (d + 14) / 8;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long s = tid / nslot;
-    const int b = (int)(tid % nslot);
-    if (s >= lv.NT) return;
-    const long long u = lv.rank + (long long)lv.world * s;
-    const long long R = u / lv.MCg;
-    const int m = (int)(u - R * lv.MCg);
-    const CallDev& c = lv.calls[find_call(lv, R)];
-    const long long i = R - c.rowbase;
-    const double* x = c.xsrc + i * D;
-    const long long gidrow = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
-    const double t = x[d];
-    const double Tt = lv.T - t, sq = sqrt(Tt), drift = lv.mu * Tt;
-    const unsigned long long f0 = (unsigned long long)(gidrow * lv.MCg + m) * (unsigned long long)d;
-    const unsigned long long blk = (f0 >> 3) + (unsigned long long)b;
-    const uint4 w = philox4x32_10(blk, make_key(0u, 0u, lv.seed));
-    double* dst = lv.P + (lv.term_off + s) * D;
+    const int p = threadIdx.x / nslot, b = threadIdx.x % nslot;
+    const long long s0 = (long long)blockIdx.x * ppb;
+    const long long s = s0 + p;
+    const bool active = (p < ppb) && (s < lv.NT);
+    if (active) {
+        const long long u = lv.rank + (long long)lv.world * s;
+        const long long R = u / lv.MCg;
+        const int m = (int)(u - R * lv.MCg);
+        const CallDev& c = lv.calls[find_call(lv, R)];
+        const long long i = R - c.rowbase;
+        const double* x = c.xsrc + i * D;
+        const long long gidrow = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
+        const double t = x[d];
+        const double Tt = lv.T - t, sq = sqrt(Tt), drift = lv.mu * Tt;
+        const unsigned long long f0 = (unsigned long long)(gidrow * lv.MCg + m) * (unsigned long long)d;
+        const unsigned long long blk = (f0 >> 3) + (unsigned long long)b;
+        const uint4 w = philox4x32_10(blk, make_key(0u, 0u, lv.seed));
+        double* dst = tile + p * D;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const long long j = (long long)(blk * 8ull + e) - (long long)f0;
-        if (j >= 0 && j < d) {
-            const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
-            dst[j] = (x[j] + drift) + lv.sigma * (sq * N);
+        for (int e = 0; e < 8; ++e) {
+            const long long j = (long long)(blk * 8ull + e) - (long long)f0;
+            if (j >= 0 && j < d) {
+                const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
+                dst[j] = (x[j] + drift) + lv.sigma * (sq * N);
+            }
         }
+        if (b == 0) dst[d] = lv.T;
     }
-    if (b == 0) dst[d] = lv.T;
+    __syncthreads();
+    const long long npt = (lv.NT - s0 < ppb) ? (lv.NT - s0) : ppb;
+    double* out = lv.P + (lv.term_off + s0) * D;
+    for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
 }
 
 // interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
-__global__ void __launch_bounds__(256) sample_paths_kernel(LevelDev lv, int l) {
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_paths_kernel(LevelDev lv, int l, int ppb) {
+    __shared__ double tile[SAMPLE_TILE];
     const int d = lv.d, D = lv.D;
     const int nslot = (d + 14) / 8;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long s = tid / nslot;
-    const int b = (int)(tid % nslot);
-    if (s >= lv.NP[l]) return;
+    const int p = threadIdx.x / nslot, b = threadIdx.x % nslot;
+    const long long s0 = (long long)blockIdx.x * ppb;
+    const long long s = s0 + p;
+    const bool active = (p < ppb) && (s < lv.NP[l]);
+    const long long npt = (lv.NP[l] - s0 < ppb) ? (lv.NP[l] - s0) : ppb;
     const int MCf = lv.MCf[l];
-    const long long u = lv.rank + (long long)lv.world * s;
-    const long long R = u / MCf;
-    const int m = (int)(u - R * MCf);
-    const CallDev& c = lv.calls[find_call(lv, R)];
-    const long long i = R - c.rowbase;
-    const double* x = c.xsrc + i * D;
-    const long long gidrow = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
-    const double t = x[d];
-    const long long pgid = gidrow * MCf + m;
-    const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
-    const unsigned long long blk = (f0 >> 3) + (unsigned long long)b;
     double Xr[8];
     bool ok[8];
+    const CallDev* cp = nullptr;
+    double t = 0.0;
+    long long pgid = 0, jbase = 0;
+    unsigned long long blk = 0;
+    if (active) {
+        const long long u = lv.rank + (long long)lv.world * s;
+        const long long R = u / MCf;
+        const int m = (int)(u - R * MCf);
+        cp = &lv.calls[find_call(lv, R)];
+        const long long i = R - cp->rowbase;
+        const double* x = cp->xsrc + i * D;
+        const long long gidrow = cp->gidsrc ? cp->gidsrc[i] : lv.gid0 + i;
+        t = x[d];
+        pgid = gidrow * MCf + m;
+        const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
+        blk = (f0 >> 3) + (unsigned long long)b;
+        jbase = (long long)(blk * 8ull) - (long long)f0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const long long j = (long long)(blk * 8ull + e) - (long long)f0;
-        ok[e] = (j >= 0 && j < d);
-        Xr[e] = ok[e] ? x[j] : 0.0;
+        for (int e = 0; e < 8; ++e) {
+            const long long j = jbase + e;
+            ok[e] = (j >= 0 && j < d);
+            Xr[e] = ok[e] ? x[j] : 0.0;
+        }
     }
-    const long long jbase = (long long)(blk * 8ull) - (long long)f0;
+    double* dstt = tile + p * D;
     if (lv.variant == 0) {
         double tprev = t;
         const int q = lv.q[l];
         for (int k = 0; k < q; ++k) {
             const int lk = l * MAX_Q + k;
-            const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
-            const double dk = __dsub_rn(tk, tprev);
-            const double sq = sqrt(dk), drift = lv.mu * dk;
-            const uint4 w = philox4x32_10(blk, make_key(c.key[lk], 1u, lv.seed));
-            double* dst = lv.P + (lv.set_off[lk] + s) * D;
+            if (active) {
+                const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
+                const double dk = __dsub_rn(tk, tprev);
+                const double sq = sqrt(dk), drift = lv.mu * dk;
+                const uint4 w = philox4x32_10(blk, make_key(cp->key[lk], 1u, lv.seed));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (ok[e]) {
+                        const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
+                        Xr[e] = Xr[e] + (drift + lv.sigma * (sq * N));
+                        dstt[jbase + e] = Xr[e];
+                    }
+                }
+                if (b == 0) { dstt[d] = tk; lv.gid[lv.set_off[lk] + s] = pgid; }
+                tprev = tk;
+            }
+            __syncthreads();
+            double* out = lv.P + (lv.set_off[lk] + s0) * D;
+            for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
+            __syncthreads();
+        }
+    } else {
+        if (active) {
+            const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+            const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
+            const double steps = tau * (lv.T - t);
+            const double sq = sqrt(steps), drift = lv.mu * steps;
+            const uint4 w = philox4x32_10(blk, kT);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 if (ok[e]) {
                     const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
-                    Xr[e] = Xr[e] + (drift + lv.sigma * (sq * N));
-                    dst[jbase + e] = Xr[e];
+                    dstt[jbase + e] = Xr[e] + (drift + lv.sigma * (sq * N));
                 }
             }
-            if (b == 0) { dst[d] = tk; lv.gid[lv.set_off[lk] + s] = pgid; }
-            tprev = tk;
+            if (b == 0) { dstt[d] = t + steps; lv.gid[lv.set_off[l * MAX_Q] + s] = pgid; }
         }
-    } else {
-        const PhiloxKey kT = make_key(0u, 0u, lv.seed);
-        const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
-        const double steps = tau * (lv.T - t);
-        const double sq = sqrt(steps), drift = lv.mu * steps;
-        const uint4 w = philox4x32_10(blk, kT);
-        double* dst = lv.P + (lv.set_off[l * MAX_Q] + s) * D;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (ok[e]) {
-                const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
-                dst[jbase + e] = Xr[e] + (drift + lv.sigma * (sq * N));
-            }
-        }
-        if (b == 0) { dst[d] = t + steps; lv.gid[lv.set_off[l * MAX_Q] + s] = pgid; }
+        __syncthreads();
+        double* out = lv.P + (lv.set_off[l * MAX_Q] + s0) * D;
+        for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
     }
 }
 
@@ -292,9 +322,24 @@ __global__ void __launch_bounds__(256) mlp_terminal_kernel(LevelDev lv) {
 
 __device__ __forceinline__ double clip_keep_nan(double v, double c) { return (v < -c) ? -c : ((v > c) ? c : v); }
 
+// One Philox block serves 8 consecutive flat indices: the lanes of a warp generate the blocks covering
+// [fstart, fstart + count) once, park them in shared memory, and every lane picks its 16-bit chunk from there.
+__device__ __forceinline__ void fill_chunks(uint4* buf, unsigned long long fstart, int count, PhiloxKey key, int lane) {
+    const unsigned long long blk0 = fstart >> 3;
+    const int nblk = (int)(((fstart + (unsigned long long)count - 1ull) >> 3) - blk0) + 1;
+    __syncwarp();
+    for (int b = lane; b < nblk; b += 32) buf[b] = philox4x32_10(blk0 + (unsigned long long)b, key);
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t read_chunk(const uint4* buf, unsigned long long fstart, unsigned long long f) {
+    return (uint32_t)((const unsigned short*)buf)[(int)(f - ((fstart >> 3) << 3))];
+}
+
 // Monte-Carlo means of one level: terminal part + all step sets + clip (solvers/ScaSML.py:211-215,252-284)
 template <int JCH>
 __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
+    __shared__ uint4 wbuf_all[4][4 * JCH + 3];
+    uint4* wbuf = wbuf_all[threadIdx.x >> 5];
     const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (R >= lv.NR) return;
@@ -323,10 +368,13 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
             const int m = (int)(rank + world * s - R * MCg);
             const double gt = lv.ev0[lv.term_off + s];
             const unsigned long long f0 = (unsigned long long)(gidrow * MCg + m) * (unsigned long long)d;
+            const unsigned long long fs = f0 + (unsigned long long)jpass;
+            const int cnt = (d - jpass < 32 * JCH) ? (d - jpass) : 32 * JCH;
+            fill_chunks(wbuf, fs, cnt, kT, lane);
 #pragma unroll
             for (int i = 0; i < JCH; ++i) {
                 const int j = jpass + lane + 32 * i;
-                if (j < d) zacc[i] = fma(gt, chunk_to_normal(lv.ntab, chunk16(f0 + j, kT)), zacc[i]);
+                if (j < d) zacc[i] = fma(gt, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
             }
             uacc += gt;
         }
@@ -363,6 +411,8 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
             const int m = (int)(rank + world * s - R * MCf);
             const long long pgid = gidrow * MCf + m;
             const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
+            const unsigned long long fs = f0 + (unsigned long long)jpass;
+            const int cnt = (d - jpass < 32 * JCH) ? (d - jpass) : 32 * JCH;
             const long long crow = s - c.rowbase * MCf;            // row of this sample inside the child calls
             double W[JCH];
 #pragma unroll
@@ -392,11 +442,12 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
                     uacc += cu[k] * (y1 - y2);
                     const double yc = y1 * ca[k] - y2 * cs[k];
                     const PhiloxKey key = make_key(c.key[lk], 1u, lv.seed);
+                    fill_chunks(wbuf, fs, cnt, key, lane);
 #pragma unroll
                     for (int i = 0; i < JCH; ++i) {
                         const int j = jpass + lane + 32 * i;
                         if (j < d) {
-                            W[i] = fma(sqk[k], chunk_to_normal(lv.ntab, chunk16(f0 + j, key)), W[i]);
+                            W[i] = fma(sqk[k], chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), W[i]);
                             zacc[i] = fma(yc, W[i], zacc[i]);
                         }
                     }
@@ -404,10 +455,11 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
                     const double yc = Tt * (y1 - y2) / MCf;
                     uacc += yc;
                     const double yz = yc / dsq;
+                    fill_chunks(wbuf, fs, cnt, kT, lane);
 #pragma unroll
                     for (int i = 0; i < JCH; ++i) {
                         const int j = jpass + lane + 32 * i;
-                        if (j < d) zacc[i] = fma(yz, chunk_to_normal(lv.ntab, chunk16(f0 + j, kT)), zacc[i]);
+                        if (j < d) zacc[i] = fma(yz, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
                     }
                 }
             }
@@ -530,6 +582,8 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         SC_CUDA(cudaMemcpyAsync(ws + lr.off_calls, hc.data(), hc.size() * sizeof(CallDev), cudaMemcpyHostToDevice, stream));
     }
     const int nslot = (d + 14) / 8;
+    SC_REQUIRE(nslot <= SAMPLE_THREADS, "picard: d > 2034 is not supported by the sampler");
+    const int ppb = SAMPLE_THREADS / nslot;            // points per sampler CTA
     // optional CUDA-event timing of the three kernel groups (sampler / evaluation / reduction)
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
@@ -549,12 +603,12 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         const LevelRec& lr = levels_[L];
         begin_span(0);
         if (lv.NT > 0) {
-            sample_terminal_kernel<<<(unsigned)cdiv(lv.NT * nslot, 256), 256, 0, stream>>>(lv);
+            sample_terminal_kernel<<<(unsigned)cdiv(lv.NT, ppb), SAMPLE_THREADS, 0, stream>>>(lv, ppb);
             SC_LAUNCH_CHECK(); ++launches;
         }
         for (int l = 0; l < L; ++l) {
             if (lv.NP[l] == 0) continue;
-            sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l] * nslot, 256), 256, 0, stream>>>(lv, l);
+            sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l], ppb), SAMPLE_THREADS, 0, stream>>>(lv, l, ppb);
             SC_LAUNCH_CHECK(); ++launches;
         }
         end_span();

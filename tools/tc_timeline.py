@@ -1,0 +1,32 @@
+"""Print the SM-clock timeline of one CTA of the tcgen05 evaluation kernel (debug aid; needs a GPU)."""
+import sys
+import numpy as np
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bench import gen_points
+from scasml_gp_b200 import _lib
+from scasml_gp_b200.equations.equations import Grad_Dependent_Nonlinear
+from scasml_gp_b200.models.GP import GP_Grad_Dependent_Nonlinear
+
+d, nd, nb = 100, 1000, 200
+dom, bdy, X = gen_points(d, nd, nb, 148 * 128 * 4)
+eq = Grad_Dependent_Nonlinear(d + 1)
+gp = GP_Grad_Dependent_Nonlinear(eq)
+gp._bind(dom, bdy)
+gp.set_right_vector(np.random.default_rng(0).standard_normal(4 * nd + nb) * 0.1)
+xd = _lib.to_device(X)
+R = xd.shape[0]
+lib = _lib.load()
+for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PDE")):
+    stamps = torch.zeros(256, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(4 * R, dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        _lib.check(lib.scasml_debug_tc_timeline(gp._handle, _lib.ptr(xd), R, mode, 300, _lib.ptr(stamps), _lib.ptr(scratch), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    t = stamps.cpu().numpy().astype(np.int64)
+    t0 = t[0]
+    nitem = int(((t[4:] > 0).sum()) // 4)
+    print(f"== {name}: entry 0, scatter {t[1]-t0}, prologue {t[2]-t0}, exit {t[3]-t0} cycles; items {nitem}")
+    for w in range(min(nitem, 44)):
+        a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
+        print(f"  item {w:2d}: mma issue {a:7d}..{b:7d} ({b-a:5d})   epilogue {c:7d}..{e:7d} ({e-c:5d})")
