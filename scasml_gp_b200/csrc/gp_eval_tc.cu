@@ -202,9 +202,10 @@ __global__ void build_images_kernel(GpView gp, TcState st) {
         const double v = (src >= 0) ? y[src] : 0.0;
         const bool step1 = (c >= 16 && c < 32);
         const double vr = (src >= 0 && !step1 && dom) ? y[(src + 1 == D) ? 0 : src + 1] : 0.0;
-        const uint32_t off = (uint32_t)(c / KBLK) * B_BLK + sw128_off(r, c % KBLK);
+        // K block kb holds [C rows 0..63 | Croll rows 0..63]: one 128-row operand for the merged d1|d2 MMA
+        const uint32_t off = (uint32_t)(c / KBLK) * (2 * B_BLK) + sw128_off(r, c % KBLK);
         *(__half*)(base + off) = __double2half(v);
-        *(__half*)(base + (size_t)KB * B_BLK + off) = __double2half(vr);
+        *(__half*)(base + B_BLK + off) = __double2half(vr);
     }
     float* recA = (float*)(base + 2 * (size_t)KB * B_BLK);
     float* recB = recA + TN * NFA;
@@ -274,21 +275,22 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     constexpr bool PDE = (CLASS == 2);
     constexpr int NA = PDE ? 4 : 2;                                   // A images: hi, lo (, roll hi, roll lo)
     constexpr int NSTEP = 4 * KB;                                     // k-steps of 16
-    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK;                  // operand stage: C image | Croll image
+    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK;                  // operand stage: per K block [C rows | Croll rows]
     constexpr uint32_t REC_BYTES = TN * NFA * 4;                      // coefficient-record slot
     constexpr int NREC = 4;
+    constexpr int NOPS = PDE ? 2 : 3;                                 // operand stages (shared-memory budget)
     extern __shared__ __align__(1024) uint8_t smem_raw[];             // no static smem in this kernel: window offset 0
     uint8_t* smem = smem_raw;                                         // (plain pointer arithmetic keeps LDS/STS codegen)
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
     uint8_t* sA = smem;                                               // NA * KB * A_BLK (re-used as exchange buffer at the end)
-    uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // 2 operand stages, freed by the MMA commit
-    uint8_t* sRec = sStage + 2 * (size_t)STAGE_BYTES;                 // 4 record slots, freed by the epilogue
+    uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // NOPS operand stages, freed by the MMA commit
+    uint8_t* sRec = sStage + NOPS * (size_t)STAGE_BYTES;              // 4 record slots, freed by the epilogue
     uint8_t* sMisc = sRec + NREC * (size_t)REC_BYTES;
     XF* xfeat = (XF*)sMisc;                                           // [128]
     double* Ki = (double*)(sMisc + TM * sizeof(XF));                  // [128]
     double* gterm = Ki + TM;                                          // [128]
-    uint64_t* bars = (uint64_t*)(gterm + TM);                         // op_full[2] op_empty[2] acc_full[2] acc_free[2] rec_full[4] rec_free[4]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+    uint64_t* bars = (uint64_t*)(gterm + TM);                         // op_full[3] op_empty[3] acc_full[2] acc_free[2] rec_full[4] rec_free[4]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 18);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
@@ -296,17 +298,16 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
 #define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
-    const uint32_t op_full[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
-    const uint32_t op_empty[2] = {smem_u32(&bars[2]), smem_u32(&bars[3])};
-    const uint32_t acc_full[2] = {smem_u32(&bars[4]), smem_u32(&bars[5])};
-    const uint32_t acc_free[2] = {smem_u32(&bars[6]), smem_u32(&bars[7])};
-    const uint32_t rec_full[4] = {smem_u32(&bars[8]), smem_u32(&bars[9]), smem_u32(&bars[10]), smem_u32(&bars[11])};
-    const uint32_t rec_free[4] = {smem_u32(&bars[12]), smem_u32(&bars[13]), smem_u32(&bars[14]), smem_u32(&bars[15])};
+    const uint32_t op_full[3] = {smem_u32(&bars[0]), smem_u32(&bars[1]), smem_u32(&bars[2])};
+    const uint32_t op_empty[3] = {smem_u32(&bars[3]), smem_u32(&bars[4]), smem_u32(&bars[5])};
+    const uint32_t acc_full[2] = {smem_u32(&bars[6]), smem_u32(&bars[7])};
+    const uint32_t acc_free[2] = {smem_u32(&bars[8]), smem_u32(&bars[9])};
+    const uint32_t rec_full[4] = {smem_u32(&bars[10]), smem_u32(&bars[11]), smem_u32(&bars[12]), smem_u32(&bars[13])};
+    const uint32_t rec_free[4] = {smem_u32(&bars[14]), smem_u32(&bars[15]), smem_u32(&bars[16]), smem_u32(&bars[17])};
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(op_full[s], 1); mbar_init(op_empty[s], 1); mbar_init(acc_full[s], 1); mbar_init(acc_free[s], NEPI);
-        }
+        for (int s = 0; s < 3; ++s) { mbar_init(op_full[s], 1); mbar_init(op_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full[s], 1); mbar_init(acc_free[s], NEPI); }
         for (int q = 0; q < NREC; ++q) { mbar_init(rec_full[q], 1); mbar_init(rec_free[q], NEPI); }
         fence_barrier_init();
     }
@@ -321,10 +322,13 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = lane + 32 * q;
-            slot_m[q] = (c < D) ? st.iperm[c] : 0;
-            slot_1[q] = (c < D) ? st.iperm1[c] : -1;
-            slot_r[q] = (c < D) ? st.iperm[(c == 0) ? D - 1 : c - 1] : 0;
+            slot_m[q] = (c < D) ? __ldg(st.tabs + 128 + c) : 0;
+            slot_1[q] = (c < D) ? __ldg(st.tabs + 256 + c) : -1;
+            slot_r[q] = (c < D) ? __ldg(st.tabs + 128 + ((c == 0) ? D - 1 : c - 1)) : 0;
         }
+        bool padslot[KB * 2];                                         // this lane's slots c = lane + 32 i: zero padding?
+#pragma unroll
+        for (int i = 0; i < KB * 2; ++i) padslot[i] = __ldg(st.tabs + lane + 32 * i) < 0;
         double v[RPW][4];
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
@@ -337,9 +341,11 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         }
         // zero padding slots (k-step padding and, for the rolled images, the whole k-step 1)
         for (int r = warp; r < TM; r += NEPI) {
-            for (int c = lane; c < KB * KBLK; c += 32) {
+#pragma unroll
+            for (int i = 0; i < KB * 2; ++i) {
+                const int c = lane + 32 * i;
                 const uint32_t off = (uint32_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK);
-                const bool pad = st.perm[c] < 0;
+                const bool pad = padslot[i];
                 if (pad) { *(__half*)(sA + off) = __half(); *(__half*)(sA + (size_t)KB * A_BLK + off) = __half(); }
                 if (PDE && (pad || (c >= 16 && c < 32))) {
                     *(__half*)(sA + 2 * (size_t)KB * A_BLK + off) = __half();
@@ -421,8 +427,8 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         // ===== producer: stream centre tiles (operand images) and coefficient records =====
         if (lane == 0) {
             for (int w = 0; w < nitem; ++w) {
-                const int s = w & 1, q = w & 3;
-                if (w >= 2) mbar_wait(op_empty[s], ((w >> 1) - 1) & 1);       // MMAs of item w-2 have read the stage
+                const int s = w % NOPS, q = w & 3;
+                if (w >= NOPS) mbar_wait(op_empty[s], ((w / NOPS) - 1) & 1);  // MMAs of item w-NOPS have read the stage
                 if (w >= 4) mbar_wait(rec_free[q], ((w >> 2) - 1) & 1);       // epilogue of item w-4 is done with the slot
                 const int t = PDE ? (w >> 1) : w;
                 const bool kindb = PDE && (w & 1);
@@ -430,17 +436,21 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
                 uint8_t* dst = sStage + (size_t)s * STAGE_BYTES;
                 uint8_t* rdst = sRec + (size_t)q * REC_BYTES;
-                const uint32_t bytes_c = KB * B_BLK;
-                const bool need_roll = dom && !kindb;
-                mbar_expect_tx(op_full[s], bytes_c + (need_roll ? bytes_c : 0));
-                bulk_g2s(smem_u32(dst), src, bytes_c, op_full[s]);
-                if (need_roll) bulk_g2s(smem_u32(dst + bytes_c), src + bytes_c, bytes_c, op_full[s]);
+                if (dom && !kindb) {                                  // C and Croll rows of every K block
+                    mbar_expect_tx(op_full[s], STAGE_BYTES);
+                    bulk_g2s(smem_u32(dst), src, STAGE_BYTES, op_full[s]);
+                } else {                                              // C rows only
+                    mbar_expect_tx(op_full[s], KB * B_BLK);
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+                        bulk_g2s(smem_u32(dst + kb * 2 * B_BLK), src + (size_t)kb * 2 * B_BLK, B_BLK, op_full[s]);
+                }
                 if (!kindb) {
                     mbar_expect_tx(rec_full[q], TN * NFA * 4);
-                    bulk_g2s(smem_u32(rdst), src + 2 * bytes_c, TN * NFA * 4, rec_full[q]);
+                    bulk_g2s(smem_u32(rdst), src + STAGE_BYTES, TN * NFA * 4, rec_full[q]);
                 } else {
                     mbar_expect_tx(rec_full[q], TN * NFB * 4);
-                    bulk_g2s(smem_u32(rdst), src + 2 * bytes_c + TN * NFA * 4, TN * NFB * 4, rec_full[q]);
+                    bulk_g2s(smem_u32(rdst), src + STAGE_BYTES + TN * NFA * 4, TN * NFB * 4, rec_full[q]);
                 }
             }
         }
@@ -448,44 +458,43 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     } else if (warp == NEPI + 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(TM, TN);
+            const uint32_t idesc = make_idesc(TM, TN), idesc2 = make_idesc(TM, 2 * TN);
             const uint32_t aBase = smem_u32(sA);
             auto adesc = [&](int img, int step) {        // img: 0 hi, 1 lo, 2 roll hi, 3 roll lo
                 return make_desc(aBase + (uint32_t)(img * KB + (step >> 2)) * A_BLK + (step & 3) * 32, 1, 64, 2);
             };
             for (int w = 0; w < nitem; ++w) {
-                const int s = w & 1;
+                const int s = w % NOPS, sa = w & 1;
                 const int t = PDE ? (w >> 1) : w;
                 const bool kindb = PDE && (w & 1);
                 const bool dom = t < st.ntile_dom;
-                mbar_wait(op_full[s], (w >> 1) & 1);
-                if (w >= 2) mbar_wait(acc_free[s], ((w >> 1) - 1) & 1);       // epilogue of item w-2 drained the TMEM stage
+                mbar_wait(op_full[s], (w / NOPS) & 1);
+                if (w >= 2) mbar_wait(acc_free[sa], ((w >> 1) - 1) & 1);      // epilogue of item w-2 drained the TMEM stage
                 tc_fence_after();
                 TC_STAMP(4 + 4 * w);
                 const uint32_t sB = smem_u32(sStage + (size_t)s * STAGE_BYTES);
-                const uint32_t sBr = sB + KB * B_BLK;
-                auto bdesc = [&](uint32_t basep, int step) { return make_desc(basep + (uint32_t)(step >> 2) * B_BLK + (step & 3) * 32, 1, 64, 2); };
-                const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)s * ACC_STRIDE);
+                // K block kb of the stage: [C rows 0..63 | Croll rows 64..127], 128-byte rows
+                auto bdesc = [&](int step) { return make_desc(sB + (uint32_t)(step >> 2) * (2 * B_BLK) + (step & 3) * 32, 1, 64, 2); };
+                const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)sa * ACC_STRIDE);
                 if (!kindb) {
-                    // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves
-                    uint32_t f1 = 0, f2 = 0;
+                    // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves.
+                    // Domain tiles: one N = 128 MMA per step writes d1 | d2 (the A slice is read once for both).
+                    uint32_t f1 = 0;
 #pragma unroll
                     for (int half = 1; half >= 0; --half) {
 #pragma unroll
                         for (int step = 0; step < NSTEP; ++step) {
                             if (step == 1) continue;
-                            const uint64_t ad = adesc(half, step);
-                            umma_f16(acc, ad, bdesc(sB, step), idesc, f1); f1 = 1;
-                            if (dom) { umma_f16(acc + 64, ad, bdesc(sBr, step), idesc, f2); f2 = 1; }
+                            umma_f16(acc, adesc(half, step), bdesc(step), dom ? idesc2 : idesc, f1); f1 = 1;
                         }
                     }
                     if (dom) {
-                        // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x B[step 1]
-                        umma_f16(acc + 128, adesc(1, 0), bdesc(sB, 1), idesc, 0);
-                        umma_f16(acc + 128, adesc(0, 0), bdesc(sB, 1), idesc, 1);
-                        if (PDE) {   // e_q = sum_m x_{I_m+1} y_{I_m+1}: A[step 1] x B[step 1]
-                            umma_f16(acc + 192, adesc(1, 1), bdesc(sB, 1), idesc, 0);
-                            umma_f16(acc + 192, adesc(0, 1), bdesc(sB, 1), idesc, 1);
+                        // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x C[step 1]
+                        umma_f16(acc + 128, adesc(1, 0), bdesc(1), idesc, 0);
+                        umma_f16(acc + 128, adesc(0, 0), bdesc(1), idesc, 1);
+                        if (PDE) {   // e_q = sum_m x_{I_m+1} y_{I_m+1}: A[step 1] x C[step 1]
+                            umma_f16(acc + 192, adesc(1, 1), bdesc(1), idesc, 0);
+                            umma_f16(acc + 192, adesc(0, 1), bdesc(1), idesc, 1);
                         }
                     }
                 } else {
@@ -495,15 +504,15 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
 #pragma unroll
                         for (int step = 0; step < NSTEP; ++step) {
                             if (step == 1) continue;
-                            umma_f16(acc, adesc(2 + half, step), bdesc(sB, step), idesc, f3); f3 = 1;
+                            umma_f16(acc, adesc(2 + half, step), bdesc(step), idesc, f3); f3 = 1;
                         }
                     }
-                    // e_x = sum_m x_{I_m+1} y_{I_m}: A[step 1] x B[step 0]
-                    umma_f16(acc + 64, adesc(1, 1), bdesc(sB, 0), idesc, 0);
-                    umma_f16(acc + 64, adesc(0, 1), bdesc(sB, 0), idesc, 1);
+                    // e_x = sum_m x_{I_m+1} y_{I_m}: A[step 1] x C[step 0]
+                    umma_f16(acc + 64, adesc(1, 1), bdesc(0), idesc, 0);
+                    umma_f16(acc + 64, adesc(0, 1), bdesc(0), idesc, 1);
                 }
                 umma_commit(op_empty[s]);                                     // operand stage reusable
-                umma_commit(acc_full[s]);                                     // accumulators ready
+                umma_commit(acc_full[sa]);                                    // accumulators ready
                 TC_STAMP(5 + 4 * w);
             }
         }
@@ -648,7 +657,8 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
 template <int CLASS, int KB>
 static size_t smem_bytes() {
     constexpr int NA = (CLASS == 2) ? 4 : 2;
-    return 1024 + (size_t)NA * KB * A_BLK + 2 * (size_t)(2 * KB * B_BLK) + 4 * (size_t)(TN * NFA * 4) + TM * sizeof(XF) + 2 * TM * 8 + 256;
+    constexpr int NOPS = (CLASS == 2) ? 2 : 3;
+    return 1024 + (size_t)NA * KB * A_BLK + NOPS * (size_t)(2 * KB * B_BLK) + 4 * (size_t)(TN * NFA * 4) + TM * sizeof(XF) + 2 * TM * 8 + 256;
 }
 
 template <int CLASS, int KB>
@@ -690,12 +700,16 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
         if (c < 0) continue;
         if (k >= 16 && k < 32) st->iperm1[c] = (short)k; else st->iperm[c] = (short)k;
     }
-    return (size_t)(st->ntile_dom + st->ntile_bdy) * st->tile_bytes;
+    return (size_t)(st->ntile_dom + st->ntile_bdy) * st->tile_bytes + 1024;    // + device copy of the permutation tables
 }
 
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
     SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 100 (larger d: FP64 route)");
-    SC_REQUIRE(st.images != nullptr, "tc: image buffer is null");
+    SC_REQUIRE(st.images != nullptr && st.tabs != nullptr, "tc: image buffer is null");
+    short host_tabs[384];
+    for (int i = 0; i < 128; ++i) { host_tabs[i] = st.perm[i]; host_tabs[128 + i] = st.iperm[i]; host_tabs[256 + i] = st.iperm1[i]; }
+    SC_CUDA(cudaMemcpyAsync((void*)st.tabs, host_tabs, sizeof(host_tabs), cudaMemcpyHostToDevice, stream));
+    SC_CUDA(cudaStreamSynchronize(stream));                       // host_tabs is a stack buffer
     tc::build_images_kernel<<<st.ntile_dom + st.ntile_bdy, 256, 0, stream>>>(gp, st);
     SC_LAUNCH_CHECK();
     return OK;

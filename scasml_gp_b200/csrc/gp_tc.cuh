@@ -28,6 +28,7 @@ struct TcState {
     short perm[128];             // permuted K slot -> source coordinate (-1: zero padding)
     short iperm[128];            // source coordinate -> slot in k-steps {0, 2, 3, ...}
     short iperm1[128];           // source coordinate -> slot in k-step 1 (successors of the index set), else -1
+    const short* tabs = nullptr; // device copy of [perm | iperm | iperm1] (constant-bank lookups with divergent indices serialise)
     long long* dbg = nullptr;    // optional timeline buffer (clock64 stamps of CTA dbg_block), see scasml_debug_tc_timeline
     int dbg_block = 0;
 };
