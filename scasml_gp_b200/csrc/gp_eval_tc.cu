@@ -364,9 +364,10 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                     const double val = v[i][q];
                     nx = fma(val, val, nx);
                     if (c < d) sxs += val;
-                    const double sv = ascale * val;
-                    const __half h = __double2half(sv);
-                    const __half lo = __double2half(sv - (double)__half2float(h));
+                    // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
+                    const float sv = (float)(ascale * val);
+                    const __half h = __float2half_rn(sv);
+                    const __half lo = __float2half_rn(sv - __half2float(h));
                     const int slot = slot_m[q];
                     const uint32_t off = (uint32_t)(slot / KBLK) * A_BLK + sw128_off(r, slot % KBLK);
                     *(__half*)(sA + off) = h;
