@@ -81,20 +81,6 @@ __device__ __forceinline__ double chunk_to_normal(const __half* __restrict__ tab
     return (double)(neg ? -v : v);
 }
 
-// same, table resident in shared memory (random 2-byte gathers: ~4 bank-conflict cycles instead of ~32 L1 tag cycles)
-__device__ __forceinline__ double chunk_to_normal_s(const __half* stab, uint32_t c) {
-    const bool neg = c < 32768u;
-    const uint32_t idx = neg ? (32767u - c) : (c - 32768u);
-    const float v = __half2float(stab[idx]);
-    return (double)(neg ? -v : v);
-}
-__device__ __forceinline__ void load_normal_table(__half* stab, const __half* __restrict__ gtab) {
-    const uint4* src = (const uint4*)gtab;
-    uint4* dst = (uint4*)stab;
-    for (int i = threadIdx.x; i < 32768 * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    __syncthreads();
-}
-
 __device__ __forceinline__ double chunk_to_uniform(uint32_t c) {
     return (double)(c >> 5) * (1.0 / 2048.0);
 }

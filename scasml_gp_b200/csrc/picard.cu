@@ -185,16 +185,11 @@ constexpr int SAMPLE_TILE = 2304;      // doubles; (256 / nslot) * (d + 1) < 204
 
 // terminal points X_T = x + mu (T-t) + sigma sqrt(T-t) N   (solvers/ScaSML.py:190-198)
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_terminal_kernel(LevelDev lv, int ppb) {
-    extern __shared__ __align__(16) uint8_t sample_smem[];
-    __half* stab = (__half*)sample_smem;                       // 64 KB inverse-CDF table
-    double* tile = (double*)(sample_smem + 65536);
-    load_normal_table(stab, lv.ntab);
+    __shared__ double tile[SAMPLE_TILE];
     const int d = lv.d, D = lv.D;
     const int nslot = (d + 14) / 8;
     const int p = threadIdx.x / nslot, b = threadIdx.x % nslot;
-    const long long ngroup = (lv.NT + ppb - 1) / ppb;
-    for (long long grp = blockIdx.x; grp < ngroup; grp += gridDim.x) {
-    const long long s0 = grp * ppb;
+    const long long s0 = (long long)blockIdx.x * ppb;
     const long long s = s0 + p;
     const bool active = (p < ppb) && (s < lv.NT);
     if (active) {
@@ -215,7 +210,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_terminal_kernel(LevelDe
         for (int e = 0; e < 8; ++e) {
             const long long j = (long long)(blk * 8ull + e) - (long long)f0;
             if (j >= 0 && j < d) {
-                const double N = chunk_to_normal_s(stab, chunk_of(w, e));
+                const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
                 dst[j] = (x[j] + drift) + lv.sigma * (sq * N);
             }
         }
@@ -225,22 +220,15 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_terminal_kernel(LevelDe
     const long long npt = (lv.NT - s0 < ppb) ? (lv.NT - s0) : ppb;
     double* out = lv.P + (lv.term_off + s0) * D;
     for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
-    __syncthreads();
-    }
 }
 
 // interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_paths_kernel(LevelDev lv, int l, int ppb) {
-    extern __shared__ __align__(16) uint8_t sample_smem[];
-    __half* stab = (__half*)sample_smem;
-    double* tile = (double*)(sample_smem + 65536);
-    load_normal_table(stab, lv.ntab);
+    __shared__ double tile[SAMPLE_TILE];
     const int d = lv.d, D = lv.D;
     const int nslot = (d + 14) / 8;
     const int p = threadIdx.x / nslot, b = threadIdx.x % nslot;
-    const long long ngroup = (lv.NP[l] + ppb - 1) / ppb;
-    for (long long grp = blockIdx.x; grp < ngroup; grp += gridDim.x) {
-    const long long s0 = grp * ppb;
+    const long long s0 = (long long)blockIdx.x * ppb;
     const long long s = s0 + p;
     const bool active = (p < ppb) && (s < lv.NP[l]);
     const long long npt = (lv.NP[l] - s0 < ppb) ? (lv.NP[l] - s0) : ppb;
@@ -285,7 +273,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_paths_kernel(LevelDev l
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     if (ok[e]) {
-                        const double N = chunk_to_normal_s(stab, chunk_of(w, e));
+                        const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
                         Xr[e] = Xr[e] + (drift + lv.sigma * (sq * N));
                         dstt[jbase + e] = Xr[e];
                     }
@@ -308,7 +296,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_paths_kernel(LevelDev l
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 if (ok[e]) {
-                    const double N = chunk_to_normal_s(stab, chunk_of(w, e));
+                    const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
                     dstt[jbase + e] = Xr[e] + (drift + lv.sigma * (sq * N));
                 }
             }
@@ -317,8 +305,6 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_paths_kernel(LevelDev l
         __syncthreads();
         double* out = lv.P + (lv.set_off[l * MAX_Q] + s0) * D;
         for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
-        __syncthreads();
-    }
     }
 }
 
@@ -350,17 +336,14 @@ __device__ __forceinline__ uint32_t read_chunk(const uint4* buf, unsigned long l
 }
 
 // Monte-Carlo means of one level: terminal part + all step sets + clip (solvers/ScaSML.py:211-215,252-284)
-constexpr int REDUCE_WARPS = 8;
-
 template <int JCH>
-__global__ void __launch_bounds__(REDUCE_WARPS * 32) reduce_kernel(LevelDev lv) {
-    extern __shared__ __align__(16) uint8_t reduce_smem[];
-    __half* stab = (__half*)reduce_smem;                       // 64 KB inverse-CDF table
-    uint4* wbuf = (uint4*)(reduce_smem + 65536) + (threadIdx.x >> 5) * (4 * JCH + 3);
-    load_normal_table(stab, lv.ntab);
+__global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
+    __shared__ uint4 wbuf_all[4][4 * JCH + 3];
+    uint4* wbuf = wbuf_all[threadIdx.x >> 5];
+    const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    if (R >= lv.NR) return;
     const int d = lv.d, D = lv.D, L = lv.L;
-    for (long long R = (long long)blockIdx.x * REDUCE_WARPS + (threadIdx.x >> 5); R < lv.NR; R += (long long)gridDim.x * REDUCE_WARPS) {
     const CallDev& c = lv.calls[find_call(lv, R)];
     const long long irow = R - c.rowbase;
     const double* x = c.xsrc + irow * D;
@@ -391,7 +374,7 @@ __global__ void __launch_bounds__(REDUCE_WARPS * 32) reduce_kernel(LevelDev lv) 
 #pragma unroll
             for (int i = 0; i < JCH; ++i) {
                 const int j = jpass + lane + 32 * i;
-                if (j < d) zacc[i] = fma(gt, chunk_to_normal_s(stab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
+                if (j < d) zacc[i] = fma(gt, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
             }
             uacc += gt;
         }
@@ -464,7 +447,7 @@ __global__ void __launch_bounds__(REDUCE_WARPS * 32) reduce_kernel(LevelDev lv) 
                     for (int i = 0; i < JCH; ++i) {
                         const int j = jpass + lane + 32 * i;
                         if (j < d) {
-                            W[i] = fma(sqk[k], chunk_to_normal_s(stab, read_chunk(wbuf, fs, f0 + j)), W[i]);
+                            W[i] = fma(sqk[k], chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), W[i]);
                             zacc[i] = fma(yc, W[i], zacc[i]);
                         }
                     }
@@ -476,7 +459,7 @@ __global__ void __launch_bounds__(REDUCE_WARPS * 32) reduce_kernel(LevelDev lv) 
 #pragma unroll
                     for (int i = 0; i < JCH; ++i) {
                         const int j = jpass + lane + 32 * i;
-                        if (j < d) zacc[i] = fma(yz, chunk_to_normal_s(stab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
+                        if (j < d) zacc[i] = fma(yz, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
                     }
                 }
             }
@@ -508,20 +491,12 @@ __global__ void __launch_bounds__(REDUCE_WARPS * 32) reduce_kernel(LevelDev lv) 
         lv.us[L][2 * R + 1] = zs;
         if (top) lv.out_uz[R * (d + 1)] = uacc;
     }
-    }   // row loop
 }
 
 template <int JCH>
-int launch_reduce(const LevelDev& lv, int nsm, cudaStream_t stream) {
-    static bool configured = false;
-    const size_t smem = 65536 + (size_t)REDUCE_WARPS * (4 * JCH + 3) * sizeof(uint4);
-    if (!configured) {
-        SC_CUDA(cudaFuncSetAttribute(reduce_kernel<JCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const long long want = cdiv(lv.NR, REDUCE_WARPS);
-    const unsigned grid = (unsigned)std::min<long long>(want, 3LL * nsm);      // persistent: 3 CTAs per SM
-    reduce_kernel<JCH><<<grid, REDUCE_WARPS * 32, smem, stream>>>(lv);
+int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
+    const long long threads = lv.NR * 32;
+    reduce_kernel<JCH><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -608,18 +583,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
     }
     const int nslot = (d + 14) / 8;
     SC_REQUIRE(nslot <= SAMPLE_THREADS, "picard: d > 2034 is not supported by the sampler");
-    const int ppb = SAMPLE_THREADS / nslot;            // points per sampler CTA iteration
-    int dev = 0, nsm = 148;
-    SC_CUDA(cudaGetDevice(&dev));
-    SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    const size_t sample_smem = 65536 + SAMPLE_TILE * sizeof(double);
-    static bool sampler_configured = false;
-    if (!sampler_configured) {
-        SC_CUDA(cudaFuncSetAttribute(sample_terminal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem));
-        SC_CUDA(cudaFuncSetAttribute(sample_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem));
-        sampler_configured = true;
-    }
-    auto sampler_grid = [&](long long npts) { return (unsigned)std::min<long long>(cdiv(npts, ppb), 2LL * nsm); };
+    const int ppb = SAMPLE_THREADS / nslot;            // points per sampler CTA
     // optional CUDA-event timing of the three kernel groups (sampler / evaluation / reduction)
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
@@ -639,12 +603,12 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         const LevelRec& lr = levels_[L];
         begin_span(0);
         if (lv.NT > 0) {
-            sample_terminal_kernel<<<sampler_grid(lv.NT), SAMPLE_THREADS, sample_smem, stream>>>(lv, ppb);
+            sample_terminal_kernel<<<(unsigned)cdiv(lv.NT, ppb), SAMPLE_THREADS, 0, stream>>>(lv, ppb);
             SC_LAUNCH_CHECK(); ++launches;
         }
         for (int l = 0; l < L; ++l) {
             if (lv.NP[l] == 0) continue;
-            sample_paths_kernel<<<sampler_grid(lv.NP[l]), SAMPLE_THREADS, sample_smem, stream>>>(lv, l, ppb);
+            sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l], ppb), SAMPLE_THREADS, 0, stream>>>(lv, l, ppb);
             SC_LAUNCH_CHECK(); ++launches;
         }
         end_span();
@@ -677,10 +641,10 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         const LevelDev& lv = lvs[L];
         int rc;
         begin_span(2);
-        if (d <= 32) rc = launch_reduce<1>(lv, nsm, stream);
-        else if (d <= 64) rc = launch_reduce<2>(lv, nsm, stream);
-        else if (d <= 128) rc = launch_reduce<4>(lv, nsm, stream);
-        else rc = launch_reduce<8>(lv, nsm, stream);
+        if (d <= 32) rc = launch_reduce<1>(lv, stream);
+        else if (d <= 64) rc = launch_reduce<2>(lv, stream);
+        else if (d <= 128) rc = launch_reduce<4>(lv, stream);
+        else rc = launch_reduce<8>(lv, stream);
         if (rc != OK) return rc;
         end_span();
         ++launches;
