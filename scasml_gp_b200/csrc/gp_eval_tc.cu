@@ -261,12 +261,138 @@ __global__ void build_images_kernel(GpView gp, TcState st) {
         p[RB_Q2] = (float)Q2;
         p[6] = 0.f; p[7] = 0.f;
         (void)a3;
+        // PDE kernel: the same coefficients regrouped per item kind
+        float* r0 = recB + TN * NFB + r * TC_NF0;
+        r0[0] = o[RA_U0]; r0[1] = o[RA_U1]; r0[2] = o[RA_U2]; r0[3] = o[RA_GSX2];
+        r0[4] = o[RA_G0]; r0[5] = o[RA_GSX]; r0[6] = o[RA_GXT]; r0[7] = o[RA_GSXXT];
+        r0[8] = o[RA_T0]; r0[9] = o[RA_TXT]; r0[10] = o[RA_TSX]; r0[11] = o[RA_TXT2];
+        r0[12] = o[RA_TSXXT]; r0[13] = o[RA_T2]; r0[14] = o[RA_LW]; r0[15] = 0.f;
+        float* r1 = recB + TN * NFB + TN * TC_NF0 + r * TC_NF1;
+        r1[0] = o[RA_Y0]; r1[1] = o[RA_Y1]; r1[2] = o[RA_Y2]; r1[3] = o[RA_Y3];
+        r1[4] = o[RA_Y4]; r1[5] = o[RA_SYR]; r1[6] = o[RA_Y0T]; r1[7] = 0.f;
     }
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
 // CLASS 0: u (EVAL_U / EVAL_TERMINAL), 1: u + div_x u, 2: PDE residual.  KB: 64-wide K blocks (1 or 2).
 struct XF { float sx, xt, sx2, sxxt, xt2, P1, P2, R1, R2, x0, sxr, pad; };
+
+// ---- A operand builder: a' x = hi + lo, permuted + swizzled f16 (and the rolled copy for the PDE rows) ----
+// All global loads of a warp's 8 rows are issued before the first use (the prologue is latency-bound otherwise).
+// Row r of warp `warp` is r = warp + 16 i, so the swizzle term (r & 7) is a per-warp constant.
+template <bool PDE, int KB>
+__device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState& st, const double* __restrict__ X, long R,
+                                                long row0, uint8_t* sA, XF* xfeat, double* Ki, double* gterm,
+                                                int tid, int warp, int lane, long long* dbg) {
+    const int D = gp.D, d = gp.d;
+    const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
+#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
+        constexpr int RPW = TM / NEPI;                                // rows per warp
+        int slot_m[4], slot_1[4], slot_r[4];                          // this lane's columns -> permuted slots
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = lane + 32 * q;
+            slot_m[q] = (c < D) ? __ldg(st.tabs + 128 + c) : 0;
+            slot_1[q] = (c < D) ? __ldg(st.tabs + 256 + c) : -1;
+            slot_r[q] = (c < D) ? __ldg(st.tabs + 128 + ((c == 0) ? D - 1 : c - 1)) : 0;
+        }
+        bool padslot[KB * 2];                                         // this lane's slots c = lane + 32 i: zero padding?
+#pragma unroll
+        for (int i = 0; i < KB * 2; ++i) padslot[i] = __ldg(st.tabs + lane + 32 * i) < 0;
+        // byte offset of (row r, slot) = base(slot) + 128 r, where base folds the per-warp-constant swizzle (r & 7 == warp & 7)
+        const int x7 = warp & 7;
+        auto slot_base = [&](int slot) {
+            return (uint32_t)(slot / KBLK) * A_BLK + (uint32_t)(((((slot % KBLK) >> 3) ^ x7) & 7) << 4) + (uint32_t)(slot & 7) * 2u;
+        };
+        uint32_t base_m[4], base_1[4], base_r[4], base_p[KB * 2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { base_m[q] = slot_base(slot_m[q]); base_1[q] = slot_base(slot_1[q] < 0 ? 0 : slot_1[q]); base_r[q] = slot_base(slot_r[q]); }
+#pragma unroll
+        for (int i = 0; i < KB * 2; ++i) base_p[i] = slot_base(lane + 32 * i);
+        constexpr uint32_t IMG = (uint32_t)KB * A_BLK;                // bytes per A image
+        double v[RPW][4];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const long row = row0 + warp + NEPI * i;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                v[i][q] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
+            }
+        }
+        // zero padding slots (k-step padding and, for the rolled images, the whole k-step 1)
+        const __half hz = __float2half_rn(0.f);
+#pragma unroll
+        for (int ri = 0; ri < RPW; ++ri) {
+            uint8_t* rowp = sA + (uint32_t)(warp + NEPI * ri) * 128u;
+#pragma unroll
+            for (int i = 0; i < KB * 2; ++i) {
+                const int c = lane + 32 * i;
+                if (padslot[i]) { *(__half*)(rowp + base_p[i]) = hz; *(__half*)(rowp + IMG + base_p[i]) = hz; }
+                if (PDE && (padslot[i] || (c >= 16 && c < 32))) {
+                    *(__half*)(rowp + 2 * IMG + base_p[i]) = hz;
+                    *(__half*)(rowp + 3 * IMG + base_p[i]) = hz;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int r = warp + NEPI * i;
+            uint8_t* rowp = sA + (uint32_t)r * 128u;
+            double nx = 0.0, sxs = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = lane + 32 * q;
+                if (c < D) {
+                    const double val = v[i][q];
+                    nx = fma(val, val, nx);
+                    if (c < d) sxs += val;
+                    // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
+                    const float sv = (float)(ascale * val);
+                    const __half h = __float2half_rn(sv);
+                    const __half lo = __float2half_rn(sv - __half2float(h));
+                    *(__half*)(rowp + base_m[q]) = h;
+                    *(__half*)(rowp + IMG + base_m[q]) = lo;
+                    if (slot_1[q] >= 0) {
+                        *(__half*)(rowp + base_1[q]) = h;
+                        *(__half*)(rowp + IMG + base_1[q]) = lo;
+                    }
+                    if (PDE) {                                        // roll(x)_{c-1} = x_c
+                        *(__half*)(rowp + 2 * IMG + base_r[q]) = h;
+                        *(__half*)(rowp + 3 * IMG + base_r[q]) = lo;
+                    }
+                }
+            }
+            for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
+            if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
+        }
+        fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
+        if (tid == 0) TC_STAMP(1);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid < TM) {
+            const int r = tid;
+            const long row = row0 + r;
+            const bool ok = row < R;
+            const double* xr = X + row * (long)D;
+            const double nx = Ki[r], sxs = gterm[r];
+            const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+            double P1 = 0, P2 = 0, R1 = 0, R2 = 0;
+#pragma unroll
+            for (int m = 0; m < MC_IDX; ++m) {
+                const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                P1 += xi; P2 = fma(xi, xi, P2); R1 += xir; R2 = fma(xir, xir, R2);
+            }
+            XF f;
+            f.sx = (float)sxs; f.xt = (float)xt; f.sx2 = (float)(sxs * sxs); f.sxxt = (float)(sxs * xt); f.xt2 = (float)(xt * xt);
+            f.P1 = (float)P1; f.P2 = (float)P2; f.R1 = (float)R1; f.R2 = (float)R2;
+            f.x0 = (float)x0; f.sxr = (float)(sxs - x0 + xt); f.pad = 0.f;
+            xfeat[r] = f;
+            Ki[r] = exp(-0.5 * gp.a * nx);
+            gterm[r] = 1.0 - 1.0 / (1.0 + exp(sxs + xt));                     // equations.py:259
+        }
+#undef TC_STAMP
+}
+
 
 template <int CLASS, int KB>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -313,107 +439,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
 
-    // ---- build the A operand: a' x = hi + lo, permuted + swizzled f16 (and the rolled copy for the PDE rows) ----
-    // All global loads of a warp's 8 rows are issued before the first use (the prologue is latency-bound otherwise).
-    const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
-    if (warp < NEPI) {
-        constexpr int RPW = TM / NEPI;                                // rows per warp
-        int slot_m[4], slot_1[4], slot_r[4];                          // this lane's columns -> permuted slots
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = lane + 32 * q;
-            slot_m[q] = (c < D) ? __ldg(st.tabs + 128 + c) : 0;
-            slot_1[q] = (c < D) ? __ldg(st.tabs + 256 + c) : -1;
-            slot_r[q] = (c < D) ? __ldg(st.tabs + 128 + ((c == 0) ? D - 1 : c - 1)) : 0;
-        }
-        bool padslot[KB * 2];                                         // this lane's slots c = lane + 32 i: zero padding?
-#pragma unroll
-        for (int i = 0; i < KB * 2; ++i) padslot[i] = __ldg(st.tabs + lane + 32 * i) < 0;
-        double v[RPW][4];
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const long row = row0 + warp + NEPI * i;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = lane + 32 * q;
-                v[i][q] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
-            }
-        }
-        // zero padding slots (k-step padding and, for the rolled images, the whole k-step 1)
-        for (int r = warp; r < TM; r += NEPI) {
-#pragma unroll
-            for (int i = 0; i < KB * 2; ++i) {
-                const int c = lane + 32 * i;
-                const uint32_t off = (uint32_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK);
-                const bool pad = padslot[i];
-                if (pad) { *(__half*)(sA + off) = __half(); *(__half*)(sA + (size_t)KB * A_BLK + off) = __half(); }
-                if (PDE && (pad || (c >= 16 && c < 32))) {
-                    *(__half*)(sA + 2 * (size_t)KB * A_BLK + off) = __half();
-                    *(__half*)(sA + 3 * (size_t)KB * A_BLK + off) = __half();
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const int r = warp + NEPI * i;
-            double nx = 0.0, sxs = 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = lane + 32 * q;
-                if (c < D) {
-                    const double val = v[i][q];
-                    nx = fma(val, val, nx);
-                    if (c < d) sxs += val;
-                    // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
-                    const float sv = (float)(ascale * val);
-                    const __half h = __float2half_rn(sv);
-                    const __half lo = __float2half_rn(sv - __half2float(h));
-                    const int slot = slot_m[q];
-                    const uint32_t off = (uint32_t)(slot / KBLK) * A_BLK + sw128_off(r, slot % KBLK);
-                    *(__half*)(sA + off) = h;
-                    *(__half*)(sA + (size_t)KB * A_BLK + off) = lo;
-                    const int s1 = slot_1[q];
-                    if (s1 >= 0) {
-                        const uint32_t off1 = (uint32_t)(s1 / KBLK) * A_BLK + sw128_off(r, s1 % KBLK);
-                        *(__half*)(sA + off1) = h;
-                        *(__half*)(sA + (size_t)KB * A_BLK + off1) = lo;
-                    }
-                    if (PDE) {                                        // roll(x)_{c-1} = x_c
-                        const int sr = slot_r[q];
-                        const uint32_t offr = (uint32_t)(sr / KBLK) * A_BLK + sw128_off(r, sr % KBLK);
-                        *(__half*)(sA + 2 * (size_t)KB * A_BLK + offr) = h;
-                        *(__half*)(sA + 3 * (size_t)KB * A_BLK + offr) = lo;
-                    }
-                }
-            }
-            for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
-            if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
-        }
-        fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
-        if (tid == 0) TC_STAMP(1);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid < TM) {
-            const int r = tid;
-            const long row = row0 + r;
-            const bool ok = row < R;
-            const double* xr = X + row * (long)D;
-            const double nx = Ki[r], sxs = gterm[r];
-            const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
-            double P1 = 0, P2 = 0, R1 = 0, R2 = 0;
-#pragma unroll
-            for (int m = 0; m < MC_IDX; ++m) {
-                const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                P1 += xi; P2 = fma(xi, xi, P2); R1 += xir; R2 = fma(xir, xir, R2);
-            }
-            XF f;
-            f.sx = (float)sxs; f.xt = (float)xt; f.sx2 = (float)(sxs * sxs); f.sxxt = (float)(sxs * xt); f.xt2 = (float)(xt * xt);
-            f.P1 = (float)P1; f.P2 = (float)P2; f.R1 = (float)R1; f.R2 = (float)R2;
-            f.x0 = (float)x0; f.sxr = (float)(sxs - x0 + xt); f.pad = 0.f;
-            xfeat[r] = f;
-            Ki[r] = exp(-0.5 * gp.a * nx);
-            gterm[r] = 1.0 - 1.0 / (1.0 + exp(sxs + xt));                     // equations.py:259
-        }
-    }
+    if (warp < NEPI) build_operand_A<PDE, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tid, warp, lane, dbg);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -655,6 +681,239 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
 #undef TC_STAMP
 }
 
+
+// ---- PDE-residual kernel: three 128-column item kinds on a 4-slot ring ------------------------------------------------
+// kind 0 (k class,  x - y):       d1 = A x C        (+ e_q = A[step 1] x C[step 1] on domain tiles)
+// kind 1 (ky class, x - roll y):  d2 = A x Croll     + e_y = A[step 0] x Croll[step 0]        (domain tiles only)
+// kind 2 (kx class, roll x - y):  d3 = Aroll x C     + e_x = A[step 1] x C[step 0]
+// Every kind needs 128 TMEM columns, so operands, records and accumulators share one 4-slot ring (slot = item & 3):
+// the MMA warp runs up to three items ahead of the epilogue, which is the binding stage of this mode.
+template <int KB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
+                   double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
+    constexpr int NSTEP = 4 * KB;
+    constexpr uint32_t STAGE_BYTES = KB * B_BLK;                      // one operand image (C or Croll)
+    constexpr uint32_t REC_BYTES = TN * TC_NF0 * 4;
+    constexpr int NSLOT = 4;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
+    uint8_t* sA = smem;                                               // hi | lo | roll hi | roll lo
+    uint8_t* sStage = sA + 4 * (size_t)KB * A_BLK;
+    uint8_t* sRec = sStage + NSLOT * (size_t)STAGE_BYTES;
+    uint8_t* sMisc = sRec + NSLOT * (size_t)REC_BYTES;
+    XF* xfeat = (XF*)sMisc;
+    double* Ki = (double*)(sMisc + TM * sizeof(XF));
+    double* gterm = Ki + TM;
+    uint64_t* bars = (uint64_t*)(gterm + TM);                         // full[4] acc[4] free[4]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = gp.d;
+    const long row0 = (long)blockIdx.x * TM;
+    long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
+#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
+    if (tid == 0) TC_STAMP(0);
+    uint32_t b_full[NSLOT], b_acc[NSLOT], b_free[NSLOT];
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q) { b_full[q] = smem_u32(&bars[q]); b_acc[q] = smem_u32(&bars[4 + q]); b_free[q] = smem_u32(&bars[8 + q]); }
+    if (tid == 0) {
+        for (int q = 0; q < NSLOT; ++q) { mbar_init(b_full[q], 1); mbar_init(b_acc[q], 1); mbar_init(b_free[q], NEPI); }
+        fence_barrier_init();
+    }
+    if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp < NEPI) build_operand_A<true, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tid, warp, lane, dbg);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) TC_STAMP(2);
+    const uint32_t tmem_base = *tmem_slot;
+    const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
+    const int nitem = 3 * ndom + 2 * nbdy;
+    // item w -> (tile, kind): domain tiles run kinds 0,1,2; boundary tiles kinds 0,2
+    auto item_of = [&](int w, int& t, int& kind) {
+        if (w < 3 * ndom) { t = w / 3; kind = w - 3 * t; }
+        else { const int v = w - 3 * ndom; t = ndom + (v >> 1); kind = (v & 1) * 2; }
+    };
+    const size_t rec_base = 2 * (size_t)KB * B_BLK + (size_t)TN * (NFA + NFB) * 4;   // rec0 | rec1 after recA | recB
+
+    if (warp == NEPI) {
+        if (lane == 0) {
+            for (int w = 0; w < nitem; ++w) {
+                const int q = w & 3;
+                if (w >= NSLOT) mbar_wait(b_free[q], ((w >> 2) - 1) & 1);     // epilogue of item w-4 released the slot
+                int t, kind; item_of(w, t, kind);
+                const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
+                uint8_t* dst = sStage + (size_t)q * STAGE_BYTES;
+                const uint32_t recbytes = (kind == 0) ? TN * TC_NF0 * 4 : TN * TC_NF1 * 4;
+                mbar_expect_tx(b_full[q], STAGE_BYTES + recbytes);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)     // global image: per K block [C rows | Croll rows]
+                    bulk_g2s(smem_u32(dst + kb * B_BLK), src + (size_t)kb * 2 * B_BLK + (kind == 1 ? B_BLK : 0), B_BLK, b_full[q]);
+                const uint8_t* rsrc = (kind == 0) ? src + rec_base
+                                    : (kind == 1) ? src + rec_base + TN * TC_NF0 * 4
+                                                  : src + 2 * (size_t)KB * B_BLK + TN * NFA * 4;      // recB
+                bulk_g2s(smem_u32(sRec + (size_t)q * REC_BYTES), rsrc, recbytes, b_full[q]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == NEPI + 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TM, TN);
+            const uint32_t aBase = smem_u32(sA);
+            auto adesc = [&](int img, int step) {
+                return make_desc(aBase + (uint32_t)(img * KB + (step >> 2)) * A_BLK + (step & 3) * 32, 1, 64, 2);
+            };
+            for (int w = 0; w < nitem; ++w) {
+                const int q = w & 3;
+                int t, kind; item_of(w, t, kind);
+                const bool dom = t < ndom;
+                mbar_wait(b_full[q], (w >> 2) & 1);
+                tc_fence_after();
+                if (w < 60) TC_STAMP(4 + 4 * w);
+                const uint32_t sB = smem_u32(sStage + (size_t)q * STAGE_BYTES);
+                auto bdesc = [&](int step) { return make_desc(sB + (uint32_t)(step >> 2) * B_BLK + (step & 3) * 32, 1, 64, 2); };
+                const uint32_t acc = tmem_base + (uint32_t)q * 128u;
+                const int aimg = (kind == 2) ? 2 : 0;                  // rolled A images for the kx class
+                uint32_t f = 0;
+#pragma unroll
+                for (int half = 1; half >= 0; --half) {
+#pragma unroll
+                    for (int step = 0; step < NSTEP; ++step) {
+                        if (step == 1) continue;
+                        umma_f16(acc, adesc(aimg + half, step), bdesc(step), idesc, f); f = 1;
+                    }
+                }
+                if (kind == 0) {
+                    if (dom) { umma_f16(acc + 64, adesc(1, 1), bdesc(1), idesc, 0); umma_f16(acc + 64, adesc(0, 1), bdesc(1), idesc, 1); }
+                } else if (kind == 1) {
+                    umma_f16(acc + 64, adesc(1, 0), bdesc(0), idesc, 0); umma_f16(acc + 64, adesc(0, 0), bdesc(0), idesc, 1);
+                } else {
+                    umma_f16(acc + 64, adesc(1, 1), bdesc(0), idesc, 0); umma_f16(acc + 64, adesc(0, 1), bdesc(0), idesc, 1);
+                }
+                umma_commit(b_acc[q]);
+                if (w < 60) TC_STAMP(5 + 4 * w);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int r = (warp & 3) * 32 + lane;
+        const int cg = warp >> 2;
+        const XF xf = xfeat[r];
+        const float a = (float)gp.a, a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
+        const float m2inv = (float)(-2.0 * st.inv_ascale);
+        const float a2_5 = a2 / MC_IDX;
+        double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        for (int w = 0; w < nitem; ++w) {
+            const int q = w & 3;
+            int t, kind; item_of(w, t, kind);
+            const bool dom = t < ndom;
+            mbar_wait(b_full[q], (w >> 2) & 1);                       // records landed (slot is refilled only after our release)
+            mbar_wait(b_acc[q], (w >> 2) & 1);
+            tc_fence_after();
+            if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
+            const uint32_t acc = tmem_base + (uint32_t)q * 128u + lane_addr + cg * 16;
+            float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
+            float v1[16], ve[16];
+            tmem_ld16(acc, v1);
+            if (kind != 0 || dom) tmem_ld16(acc + 64, ve);
+            tmem_ld_wait();
+            if (kind == 0) {
+                const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * TC_NF0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float* c = rec + i * TC_NF0;
+                    const float4 f0 = *(const float4*)(c);            // U0 U1 U2 Gsx2
+                    const float4 f1 = *(const float4*)(c + 4);        // G0 Gsx Gxt Gsxxt
+                    const float4 f2 = *(const float4*)(c + 8);        // T0 Txt Tsx Txt2
+                    const float4 f3 = *(const float4*)(c + 12);       // Tsxxt T2 Lw -
+                    const float k = ex2f(v1[i]);
+                    pu = fmaf(k, fmaf(f0.z, xf.sx, fmaf(f0.y, xf.xt, f0.x)), pu);
+                    pg = fmaf(k, fmaf(f0.w, xf.sx2, fmaf(f1.w, xf.sxxt, fmaf(f1.z, xf.xt, fmaf(f1.y, xf.sx, f1.x)))), pg);
+                    pt = fmaf(k, fmaf(f3.x, xf.sxxt, fmaf(f2.w, xf.xt2, fmaf(f2.z, xf.sx, fmaf(f2.y, xf.xt, f2.x)))), pt);
+                    if (dom) {
+                        const float q2 = fmaf(m2inv, ve[i], xf.R2 + f3.y);
+                        pl = fmaf(k * f3.z, fmaf(fmaf(a4, q2, -14.f * a3), q2, 35.f * a2), pl);
+                    }
+                }
+            } else if (kind == 1) {
+                const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * TC_NF1;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float* c = rec + i * TC_NF1;
+                    const float4 f0 = *(const float4*)(c);            // Y0 Y1 Y2 Y3
+                    const float4 f1 = *(const float4*)(c + 4);        // Y4 syr y0 -
+                    const float ky = ex2f(v1[i]);
+                    const float h = fmaf(f0.z, ve[i], fmaf(f0.y, xf.P2, f0.x));
+                    pu = fmaf(ky, h, pu);
+                    pg = fmaf(ky, fmaf(-a * (xf.sx - f1.y), h, fmaf(f1.x, xf.P1, f0.w)), pg);
+                    pt = fmaf(ky * h, -a * (xf.xt - f1.z), pt);
+                }
+            } else {
+                const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * NFB;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float* c = rec + i * NFB;
+                    const float4 f0 = *(const float4*)(c);            // X0 X1 X2 X3
+                    const float2 f1 = *(const float2*)(c + 4);        // X4 Q2
+                    const float kx = ex2f(v1[i]);
+                    const float n2 = fmaf(m2inv, ve[i], xf.R2 + f1.y);
+                    const float MHx = fmaf(a2_5, n2, -a);
+                    const float p1 = fmaf(f0.z, xf.sxr, fmaf(f0.y, xf.x0, f0.x));
+                    pl = fmaf(kx, fmaf(MHx, p1, fmaf(f1.x, xf.R1, f0.w)), pl);
+                }
+            }
+            U += (double)pu; G += (double)pg; L += (double)pl; T += (double)pt;
+            tc_fence_before();
+            __syncwarp();
+            if (tid == 0 && w < 60) TC_STAMP(7 + 4 * w);
+            if (lane == 0) mbar_arrive(b_free[q]);
+        }
+        double* xchg = (double*)sA;                                   // the A images are dead now
+        if (cg > 0) { double* p = xchg + ((size_t)cg * TM + r) * 4; p[0] = U; p[1] = G; p[2] = L; p[3] = T; }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (cg == 0) {
+            const long row = row0 + r;
+            if (row < R) {
+#pragma unroll
+                for (int g2 = 1; g2 < 4; ++g2) {
+                    const double* p = xchg + ((size_t)g2 * TM + r) * 4;
+                    U += p[0]; G += p[1]; L += p[2]; T += p[3];
+                }
+                const double ki = Ki[r];
+                const double u = ki * U, g = ki * G, l = ki * L, tt = ki * T;
+                const double s2 = gp.sig2;
+                out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;       // GP.py:767-768
+                if (out1) out1[row] = g;
+                if (out2) out2[row] = l;
+                if (out3) out3[row] = tt;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) TC_STAMP(3);
+    if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
+#undef TC_STAMP
+}
+
+template <int KB>
+static int launch_pde(const GpView& gp, const TcState& st, const double* X, long R,
+                      double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
+    static bool configured = false;
+    const size_t smem = 1024 + 4 * (size_t)KB * A_BLK + 4 * (size_t)(KB * B_BLK) + 4 * (size_t)(TN * TC_NF0 * 4)
+                        + TM * sizeof(XF) + 2 * TM * 8 + 256;
+    if (!configured) {
+        SC_CUDA(cudaFuncSetAttribute(eval_tc_pde_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    eval_tc_pde_kernel<KB><<<(unsigned)cdiv(R, TM), NTHREADS, smem, stream>>>(gp, st, X, R, o0, o1, o2, o3);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
 template <int CLASS, int KB>
 static size_t smem_bytes() {
     constexpr int NA = (CLASS == 2) ? 4 : 2;
@@ -688,7 +947,7 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
     st->KB = (32 + rest + tc::KBLK - 1) / tc::KBLK;
     st->ntile_dom = gp.NdPad / tc::TN;
     st->ntile_bdy = gp.NbPad / tc::TN;
-    st->tile_bytes = 2 * (size_t)st->KB * tc::B_BLK + (size_t)tc::TN * (tc::NFA + tc::NFB) * 4;
+    st->tile_bytes = 2 * (size_t)st->KB * tc::B_BLK + (size_t)tc::TN * (tc::NFA + tc::NFB + TC_NF0 + TC_NF1) * 4;
     st->inv_ascale = 1.0 / (gp.a * 1.4426950408889634);
     for (int c = 0; c < 128; ++c) st->perm[c] = -1;
     bool in_set[1024] = {false};
@@ -730,11 +989,11 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     if (KB == 1) {
         if (cls == 0) return tc::launch<0, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
         if (cls == 1) return tc::launch<1, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
-        return tc::launch<2, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+        return tc::launch_pde<1>(gp, *st, X, R, out0, out1, out2, out3, stream);
     }
     if (cls == 0) return tc::launch<0, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
     if (cls == 1) return tc::launch<1, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
-    return tc::launch<2, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
+    return tc::launch_pde<2>(gp, *st, X, R, out0, out1, out2, out3, stream);
 }
 
 // timeline of one CTA: stamps[0] entry, [1] operand scatter done, [2] prologue done, [3] exit,

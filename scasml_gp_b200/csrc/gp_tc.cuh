@@ -18,6 +18,10 @@ enum TcRecA : int {          // k class (distance x - y) and ky class (x - roll 
 enum TcRecB : int { RB_X0 = 0, RB_X1 = 1, RB_X2 = 2, RB_X3 = 3, RB_X4 = 4, RB_Q2 = 5 };   // kx class (roll x - y)
 constexpr int TC_NFA = 24;
 constexpr int TC_NFB = 8;
+// PDE kernel records (three item kinds): kind 0 = k class [U0 U1 U2 Gsx2 | G0 Gsx Gxt Gsxxt | T0 Txt Tsx Txt2 | Tsxxt T2 Lw 0],
+// kind 1 = ky class [Y0 Y1 Y2 Y3 | Y4 syr y0 0], kind 2 = kx class (= TcRecB)
+constexpr int TC_NF0 = 16;
+constexpr int TC_NF1 = 8;
 
 struct TcState {
     uint8_t* images = nullptr;   // per centre tile: [C image][Croll image][records A][records B]
