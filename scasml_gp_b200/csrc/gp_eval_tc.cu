@@ -85,6 +85,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, 32-bit column c = K elements 2c, 2c+1), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -185,6 +197,68 @@ selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, floa
 }
 
 
+
+// ---- self test, A operand in tensor memory: D[128 x N] = A[128 x K] B[N x K]^T -------------------------------------
+__global__ void __launch_bounds__(128, 1)
+selftest_ts_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ Dout, int K, int N) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int KB = K / KBLK;
+    uint8_t* sB = smem;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int r = idx / K, c = idx % K;
+        *(__half*)(sB + (size_t)(c / KBLK) * (N * 128) + sw128_off(r, c % KBLK)) = B[(size_t)r * K + c];
+    }
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t colA = 64;                                   // A image at columns [64, 64 + K/2)
+    {   // thread = row: pack two consecutive K elements per 32-bit column
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        for (int c0 = 0; c0 < K / 2; c0 += 16) {
+            uint32_t w[16];
+            for (int i = 0; i < 16; ++i) {
+                const __half lo = A[(size_t)tid * K + 2 * (c0 + i)], hi = A[(size_t)tid * K + 2 * (c0 + i) + 1];
+                w[i] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+            }
+            tmem_st16(tmem_base + lane_addr + colA + c0, w);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(TM, N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb)
+            for (int ks = 0; ks < KBLK / 16; ++ks) {
+                const uint64_t bd = make_desc(smem_u32(sB + (size_t)kb * (N * 128)) + ks * 32, 1, 64, 2);
+                umma_f16_ts(tmem_base, tmem_base + colA + (uint32_t)(kb * 4 + ks) * 8u, bd, idesc, acc);
+                acc = 1;
+            }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) Dout[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 // ---- operand images + coefficient records of the centres (built once per fit) ------------------------------------
 // per tile t: [C image: KB blocks of [64 x 64] f16][Croll image (zeros for boundary tiles)][recA 64 x NFA f32][recB 64 x NFB f32]
 // K axis permuted by st.perm: k-step 0 = index-set columns I_m, k-step 1 = I_m + 1, k-steps >= 2 = all other columns.
@@ -283,7 +357,7 @@ struct XF { float sx, xt, sx2, sxxt, xt2, P1, P2, R1, R2, x0, sxr, pad; };
 template <bool PDE, int KB>
 __device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState& st, const double* __restrict__ X, long R,
                                                 long row0, uint8_t* sA, XF* xfeat, double* Ki, double* gterm,
-                                                int tid, int warp, int lane, long long* dbg) {
+                                                uint32_t tmemA, int tid, int warp, int lane, long long* dbg) {
     const int D = gp.D, d = gp.d;
     const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
 #define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
@@ -366,9 +440,30 @@ __device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState&
             for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
             if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
         }
-        fence_proxy_async();                                          // generic-proxy smem writes -> visible to UMMA
         if (tid == 0) TC_STAMP(1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
+        // stage the images into tensor memory: the MMAs take the A operand from TMEM (lane = row, 32-bit column c =
+        // K slots 2c, 2c+1), so the 128-row A strip is not re-read from shared memory by every instruction
+        if (warp < 4 * (PDE ? 4 : 2)) {
+            const int img = warp >> 2;
+            const int r = (warp & 3) * 32 + lane;
+            const uint32_t taddr = tmemA + (uint32_t)img * 64u + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                const uint8_t* rowp = sA + (size_t)img * IMG + (size_t)kb * A_BLK + (uint32_t)r * 128u;
+#pragma unroll
+                for (int j0 = 0; j0 < 8; j0 += 4) {
+                    uint32_t wv[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 ch = *(const uint4*)(rowp + ((((j0 + j) ^ (r & 7)) & 7) << 4));
+                        wv[4 * j] = ch.x; wv[4 * j + 1] = ch.y; wv[4 * j + 2] = ch.z; wv[4 * j + 3] = ch.w;
+                    }
+                    tmem_st16(taddr + (uint32_t)(kb * 32 + j0 * 4), wv);
+                }
+            }
+            tmem_st_wait();
+        }
         if (tid < TM) {
             const int r = tid;
             const long row = row0 + r;
@@ -394,6 +489,7 @@ __device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState&
 }
 
 
+// CLASS 0 / 1 only (the PDE residual has its own kernel below)
 template <int CLASS, int KB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int mode,
@@ -438,13 +534,17 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();                                                  // TMEM base address + barriers visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t COL_A = 384;                                   // A images (hi | lo) behind the two accumulator stages
 
-    if (warp < NEPI) build_operand_A<PDE, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tid, warp, lane, dbg);
+    if (warp < NEPI) build_operand_A<PDE, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (tid == 0) TC_STAMP(2);
-    const uint32_t tmem_base = *tmem_slot;
     const int ntile = st.ntile_dom + st.ntile_bdy;
     const int nitem = PDE ? 2 * ntile : ntile;
     // TMEM columns.  CLASS 0/1: stage s at 192 s: d1 | d2 | e_y.  PDE: kind a at 0: d1 | d2 | e_y | e_q ; kind b at 256: d3 | e_x.
@@ -486,10 +586,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TM, TN), idesc2 = make_idesc(TM, 2 * TN);
-            const uint32_t aBase = smem_u32(sA);
-            auto adesc = [&](int img, int step) {        // img: 0 hi, 1 lo, 2 roll hi, 3 roll lo
-                return make_desc(aBase + (uint32_t)(img * KB + (step >> 2)) * A_BLK + (step & 3) * 32, 1, 64, 2);
-            };
+            auto atmem = [&](int img, int step) { return tmem_base + COL_A + (uint32_t)img * 64u + (uint32_t)step * 8u; };
             for (int w = 0; w < nitem; ++w) {
                 const int s = w % NOPS, sa = w & 1;
                 const int t = PDE ? (w >> 1) : w;
@@ -512,31 +609,14 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
 #pragma unroll
                         for (int step = 0; step < NSTEP; ++step) {
                             if (step == 1) continue;
-                            umma_f16(acc, adesc(half, step), bdesc(step), dom ? idesc2 : idesc, f1); f1 = 1;
+                            umma_f16_ts(acc, atmem(half, step), bdesc(step), dom ? idesc2 : idesc, f1); f1 = 1;
                         }
                     }
                     if (dom) {
                         // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x C[step 1]
-                        umma_f16(acc + 128, adesc(1, 0), bdesc(1), idesc, 0);
-                        umma_f16(acc + 128, adesc(0, 0), bdesc(1), idesc, 1);
-                        if (PDE) {   // e_q = sum_m x_{I_m+1} y_{I_m+1}: A[step 1] x C[step 1]
-                            umma_f16(acc + 192, adesc(1, 1), bdesc(1), idesc, 0);
-                            umma_f16(acc + 192, adesc(0, 1), bdesc(1), idesc, 1);
-                        }
+                        umma_f16_ts(acc + 128, atmem(1, 0), bdesc(1), idesc, 0);
+                        umma_f16_ts(acc + 128, atmem(0, 0), bdesc(1), idesc, 1);
                     }
-                } else {
-                    uint32_t f3 = 0;
-#pragma unroll
-                    for (int half = 1; half >= 0; --half) {
-#pragma unroll
-                        for (int step = 0; step < NSTEP; ++step) {
-                            if (step == 1) continue;
-                            umma_f16(acc, adesc(2 + half, step), bdesc(step), idesc, f3); f3 = 1;
-                        }
-                    }
-                    // e_x = sum_m x_{I_m+1} y_{I_m}: A[step 1] x C[step 0]
-                    umma_f16(acc + 64, adesc(1, 1), bdesc(0), idesc, 0);
-                    umma_f16(acc + 64, adesc(0, 1), bdesc(0), idesc, 1);
                 }
                 umma_commit(op_empty[s]);                                     // operand stage reusable
                 umma_commit(acc_full[sa]);                                    // accumulators ready
@@ -723,12 +803,16 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
-    if (warp < NEPI) build_operand_A<true, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tid, warp, lane, dbg);
+    tc_fence_before();
+    __syncthreads();                                                  // TMEM base address + barriers visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t COL_A = 256;                                   // A images hi | lo | roll hi | roll lo behind two 128-column accumulator slots
+    if (warp < NEPI) build_operand_A<true, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (tid == 0) TC_STAMP(2);
-    const uint32_t tmem_base = *tmem_slot;
     const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
     const int nitem = 3 * ndom + 2 * nbdy;
     // item w -> (tile, kind): domain tiles run kinds 0,1,2; boundary tiles kinds 0,2
@@ -761,20 +845,18 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
     } else if (warp == NEPI + 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TM, TN);
-            const uint32_t aBase = smem_u32(sA);
-            auto adesc = [&](int img, int step) {
-                return make_desc(aBase + (uint32_t)(img * KB + (step >> 2)) * A_BLK + (step & 3) * 32, 1, 64, 2);
-            };
+            auto atmem = [&](int img, int step) { return tmem_base + COL_A + (uint32_t)img * 64u + (uint32_t)step * 8u; };
             for (int w = 0; w < nitem; ++w) {
                 const int q = w & 3;
                 int t, kind; item_of(w, t, kind);
                 const bool dom = t < ndom;
                 mbar_wait(b_full[q], (w >> 2) & 1);
+                if (w >= 2) mbar_wait(b_free[(w - 2) & 3], ((w - 2) >> 2) & 1);   // epilogue of item w-2 drained TMEM slot w & 1
                 tc_fence_after();
                 if (w < 60) TC_STAMP(4 + 4 * w);
                 const uint32_t sB = smem_u32(sStage + (size_t)q * STAGE_BYTES);
                 auto bdesc = [&](int step) { return make_desc(sB + (uint32_t)(step >> 2) * B_BLK + (step & 3) * 32, 1, 64, 2); };
-                const uint32_t acc = tmem_base + (uint32_t)q * 128u;
+                const uint32_t acc = tmem_base + (uint32_t)(w & 1) * 128u;
                 const int aimg = (kind == 2) ? 2 : 0;                  // rolled A images for the kx class
                 uint32_t f = 0;
 #pragma unroll
@@ -782,15 +864,15 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
 #pragma unroll
                     for (int step = 0; step < NSTEP; ++step) {
                         if (step == 1) continue;
-                        umma_f16(acc, adesc(aimg + half, step), bdesc(step), idesc, f); f = 1;
+                        umma_f16_ts(acc, atmem(aimg + half, step), bdesc(step), idesc, f); f = 1;
                     }
                 }
                 if (kind == 0) {
-                    if (dom) { umma_f16(acc + 64, adesc(1, 1), bdesc(1), idesc, 0); umma_f16(acc + 64, adesc(0, 1), bdesc(1), idesc, 1); }
+                    if (dom) { umma_f16_ts(acc + 64, atmem(1, 1), bdesc(1), idesc, 0); umma_f16_ts(acc + 64, atmem(0, 1), bdesc(1), idesc, 1); }
                 } else if (kind == 1) {
-                    umma_f16(acc + 64, adesc(1, 0), bdesc(0), idesc, 0); umma_f16(acc + 64, adesc(0, 0), bdesc(0), idesc, 1);
+                    umma_f16_ts(acc + 64, atmem(1, 0), bdesc(0), idesc, 0); umma_f16_ts(acc + 64, atmem(0, 0), bdesc(0), idesc, 1);
                 } else {
-                    umma_f16(acc + 64, adesc(1, 1), bdesc(0), idesc, 0); umma_f16(acc + 64, adesc(0, 1), bdesc(0), idesc, 1);
+                    umma_f16_ts(acc + 64, atmem(1, 1), bdesc(0), idesc, 0); umma_f16_ts(acc + 64, atmem(0, 1), bdesc(0), idesc, 1);
                 }
                 umma_commit(b_acc[q]);
                 if (w < 60) TC_STAMP(5 + 4 * w);
@@ -814,7 +896,7 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
             mbar_wait(b_acc[q], (w >> 2) & 1);
             tc_fence_after();
             if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
-            const uint32_t acc = tmem_base + (uint32_t)q * 128u + lane_addr + cg * 16;
+            const uint32_t acc = tmem_base + (uint32_t)(w & 1) * 128u + lane_addr + cg * 16;
             float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
             float v1[16], ve[16];
             tmem_ld16(acc, v1);
@@ -1012,6 +1094,12 @@ int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N
     SC_REQUIRE(N % 16 == 0 && N >= 16 && N <= 64, "selftest: N in [16, 64], multiple of 16");
     const size_t smem = 1024 + (size_t)(K / tc::KBLK) * (tc::A_BLK + (size_t)N * 128);
     SC_CUDA(cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (layout == 100) {      // A operand in tensor memory (TS mode)
+        SC_CUDA(cudaFuncSetAttribute(tc::selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::selftest_ts_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N);
+        SC_LAUNCH_CHECK();
+        return OK;
+    }
     tc::selftest_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N, lbo16, sbo16,
                                                   layout, kstep_bytes);
     SC_LAUNCH_CHECK();
