@@ -586,37 +586,40 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TM, TN), idesc2 = make_idesc(TM, 2 * TN);
-            auto atmem = [&](int img, int step) { return tmem_base + COL_A + (uint32_t)img * 64u + (uint32_t)step * 8u; };
+            // Descriptors are precomputed: per MMA only a constant (compile-time, loops are unrolled) is added.  The issuing
+            // thread runs alone, so every dependent integer instruction would otherwise cost its full latency per MMA.
+            const uint32_t aBase = tmem_base + COL_A;
+            uint64_t bstage[NOPS];
+#pragma unroll
+            for (int i = 0; i < NOPS; ++i) bstage[i] = make_desc(smem_u32(sStage + (size_t)i * STAGE_BYTES), 1, 64, 2);
             for (int w = 0; w < nitem; ++w) {
                 const int s = w % NOPS, sa = w & 1;
-                const int t = PDE ? (w >> 1) : w;
-                const bool kindb = PDE && (w & 1);
-                const bool dom = t < st.ntile_dom;
+                const bool dom = w < st.ntile_dom;
                 mbar_wait(op_full[s], (w / NOPS) & 1);
                 if (w >= 2) mbar_wait(acc_free[sa], ((w >> 1) - 1) & 1);      // epilogue of item w-2 drained the TMEM stage
                 tc_fence_after();
                 TC_STAMP(4 + 4 * w);
-                const uint32_t sB = smem_u32(sStage + (size_t)s * STAGE_BYTES);
+                uint64_t bb = bstage[0];
+#pragma unroll
+                for (int i = 1; i < NOPS; ++i) bb = (s == i) ? bstage[i] : bb;
                 // K block kb of the stage: [C rows 0..63 | Croll rows 64..127], 128-byte rows
-                auto bdesc = [&](int step) { return make_desc(sB + (uint32_t)(step >> 2) * (2 * B_BLK) + (step & 3) * 32, 1, 64, 2); };
-                const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)sa * ACC_STRIDE);
-                if (!kindb) {
-                    // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves.
-                    // Domain tiles: one N = 128 MMA per step writes d1 | d2 (the A slice is read once for both).
-                    uint32_t f1 = 0;
+                const uint32_t acc = tmem_base + (uint32_t)sa * ACC_STRIDE;
+                const uint32_t idm = dom ? idesc2 : idesc;              // domain tiles: one N = 128 MMA writes d1 | d2
+                // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves
 #pragma unroll
-                    for (int half = 1; half >= 0; --half) {
+                for (int half = 1; half >= 0; --half) {
 #pragma unroll
-                        for (int step = 0; step < NSTEP; ++step) {
-                            if (step == 1) continue;
-                            umma_f16_ts(acc, atmem(half, step), bdesc(step), dom ? idesc2 : idesc, f1); f1 = 1;
-                        }
+                    for (int step = 0; step < NSTEP; ++step) {
+                        if (step == 1) continue;
+                        const uint64_t bd = bb + (uint64_t)((((step >> 2) * (2 * B_BLK)) + (step & 3) * 32) >> 4);
+                        umma_f16_ts(acc, aBase + (uint32_t)(half * 64 + step * 8), bd, idm, (half == 1 && step == 0) ? 0u : 1u);
                     }
-                    if (dom) {
-                        // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x C[step 1]
-                        umma_f16_ts(acc + 128, atmem(1, 0), bdesc(1), idesc, 0);
-                        umma_f16_ts(acc + 128, atmem(0, 0), bdesc(1), idesc, 1);
-                    }
+                }
+                if (dom) {
+                    // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x C[step 1]
+                    const uint64_t bd1 = bb + (uint64_t)(32 >> 4);
+                    umma_f16_ts(acc + 128, aBase + 64u, bd1, idesc, 0);
+                    umma_f16_ts(acc + 128, aBase, bd1, idesc, 1);
                 }
                 umma_commit(op_empty[s]);                                     // operand stage reusable
                 umma_commit(acc_full[sa]);                                    // accumulators ready
@@ -845,7 +848,10 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
     } else if (warp == NEPI + 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TM, TN);
-            auto atmem = [&](int img, int step) { return tmem_base + COL_A + (uint32_t)img * 64u + (uint32_t)step * 8u; };
+            const uint32_t aBase = tmem_base + COL_A;                  // images at +0 hi, +64 lo, +128 roll hi, +192 roll lo
+            uint64_t bstage[NSLOT];
+#pragma unroll
+            for (int i = 0; i < NSLOT; ++i) bstage[i] = make_desc(smem_u32(sStage + (size_t)i * STAGE_BYTES), 1, 64, 2);
             for (int w = 0; w < nitem; ++w) {
                 const int q = w & 3;
                 int t, kind; item_of(w, t, kind);
@@ -854,25 +860,27 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
                 if (w >= 2) mbar_wait(b_free[(w - 2) & 3], ((w - 2) >> 2) & 1);   // epilogue of item w-2 drained TMEM slot w & 1
                 tc_fence_after();
                 if (w < 60) TC_STAMP(4 + 4 * w);
-                const uint32_t sB = smem_u32(sStage + (size_t)q * STAGE_BYTES);
-                auto bdesc = [&](int step) { return make_desc(sB + (uint32_t)(step >> 2) * B_BLK + (step & 3) * 32, 1, 64, 2); };
+                uint64_t bb = bstage[0];
+#pragma unroll
+                for (int i = 1; i < NSLOT; ++i) bb = (q == i) ? bstage[i] : bb;
                 const uint32_t acc = tmem_base + (uint32_t)(w & 1) * 128u;
-                const int aimg = (kind == 2) ? 2 : 0;                  // rolled A images for the kx class
-                uint32_t f = 0;
+                const uint32_t aimg = aBase + ((kind == 2) ? 128u : 0u);    // rolled A images for the kx class
 #pragma unroll
                 for (int half = 1; half >= 0; --half) {
 #pragma unroll
                     for (int step = 0; step < NSTEP; ++step) {
                         if (step == 1) continue;
-                        umma_f16_ts(acc, atmem(aimg + half, step), bdesc(step), idesc, f); f = 1;
+                        const uint64_t bd = bb + (uint64_t)((((step >> 2) * B_BLK) + (step & 3) * 32) >> 4);
+                        umma_f16_ts(acc, aimg + (uint32_t)(half * 64 + step * 8), bd, idesc, (half == 1 && step == 0) ? 0u : 1u);
                     }
                 }
-                if (kind == 0) {
-                    if (dom) { umma_f16_ts(acc + 64, atmem(1, 1), bdesc(1), idesc, 0); umma_f16_ts(acc + 64, atmem(0, 1), bdesc(1), idesc, 1); }
-                } else if (kind == 1) {
-                    umma_f16_ts(acc + 64, atmem(1, 0), bdesc(0), idesc, 0); umma_f16_ts(acc + 64, atmem(0, 0), bdesc(0), idesc, 1);
-                } else {
-                    umma_f16_ts(acc + 64, atmem(1, 1), bdesc(0), idesc, 0); umma_f16_ts(acc + 64, atmem(0, 1), bdesc(0), idesc, 1);
+                const uint64_t bd0 = bb, bd1 = bb + (uint64_t)(32 >> 4);
+                if (kind == 0) {          // e_q = A[step 1] x C[step 1]
+                    if (dom) { umma_f16_ts(acc + 64, aBase + 64u + 8u, bd1, idesc, 0); umma_f16_ts(acc + 64, aBase + 8u, bd1, idesc, 1); }
+                } else if (kind == 1) {   // e_y = A[step 0] x Croll[step 0]
+                    umma_f16_ts(acc + 64, aBase + 64u, bd0, idesc, 0); umma_f16_ts(acc + 64, aBase, bd0, idesc, 1);
+                } else {                  // e_x = A[step 1] x C[step 0]
+                    umma_f16_ts(acc + 64, aBase + 64u + 8u, bd0, idesc, 0); umma_f16_ts(acc + 64, aBase + 8u, bd0, idesc, 1);
                 }
                 umma_commit(b_acc[q]);
                 if (w < 60) TC_STAMP(5 + 4 * w);
