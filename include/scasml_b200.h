@@ -153,6 +153,9 @@ SCASML_API int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_d
  * [6+4w] epilogue start, [7+4w] epilogue end */
 SCASML_API int scasml_debug_tc_timeline(const scasml_gp* gp, const double* X_dev, long long R, int mode, int block,
                              long long* stamps_dev, double* scratch_dev, void* stream);
+/* micro-benchmark: cycles per tcgen05.mma (M=128, K=16, f16) for N, `nchains` independent accumulators, A from smem (0) / TMEM (1);
+ * cycles_dev[0] = issue span, cycles_dev[1] = span until the commit arrives */
+SCASML_API int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, void* stream);
 /* 1 if this handle can use SCASML_ROUTE_TC (d <= 100) */
 SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 

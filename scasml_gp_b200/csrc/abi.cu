@@ -349,6 +349,10 @@ int scasml_debug_tc_timeline(const scasml_gp* g, const double* X_dev, long long 
     return tc_timeline(g->v, g->tc, X_dev, (long)R, mode, block, stamps_dev, scratch_dev, (cudaStream_t)stream);
 }
 
+int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, void* stream) {
+    return tc_mma_bench(N, nchains, ts_mode, iters, cycles_dev, (cudaStream_t)stream);
+}
+
 int scasml_gp_tc_supported(const scasml_gp* g) { return (g && g->tc.images) ? 1 : 0; }
 
 int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream) {

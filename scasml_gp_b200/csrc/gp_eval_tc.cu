@@ -97,6 +97,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -257,6 +262,67 @@ selftest_ts_kernel(const __half* __restrict__ A, const __half* __restrict__ B, f
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+
+// ---- micro-benchmark: cycles per tcgen05.mma (M = 128, K = 16, f16) for a given N, number of independent
+//      accumulator chains and A source; one CTA per SM, no epilogue.  Used to size tiles (profiles/). -----------------
+__global__ void __launch_bounds__(128, 1)
+mma_bench_kernel(int N, int nchains, int ts_mode, int iters, long long* __restrict__ cycles_out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    uint8_t* sA = smem;                       // [128 x 64] f16 block
+    uint8_t* sB = smem + A_BLK;               // [256 x 64] f16 block
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (A_BLK + 256 * 128) / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;   // f16 ones
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    if (warp == 0) {
+        // converged warp, one elected lane issues: operands are warp-uniform, so UTCHMMA takes them from uniform
+        // registers without the per-lane serialisation loop a divergent `if (lane == 0)` block compiles to
+        const uint32_t idesc = make_idesc(TM, N);
+        const uint64_t ad = make_desc(smem_u32(sA), 1, 64, 2), bd = make_desc(smem_u32(sB), 1, 64, 2);
+        const uint32_t chain_stride = (uint32_t)N;
+        const uint32_t el = elect_one();
+        const long long t0 = clock64();
+        if (ts_mode >= 2) {
+            // unrolled by 4, fixed operands per slot
+            const uint32_t acc0 = tmem_base, acc1 = tmem_base + (nchains > 1 ? chain_stride : 0u);
+            for (int it = 0; it < iters; it += 4) {
+                if (el) {
+                    umma_f16_ts(acc0, tmem_base + 480u, bd, idesc, 1u);
+                    umma_f16_ts(acc1, tmem_base + 480u, bd + 2ull, idesc, 1u);
+                    umma_f16_ts(acc0, tmem_base + 488u, bd + 4ull, idesc, 1u);
+                    umma_f16_ts(acc1, tmem_base + 488u, bd + 6ull, idesc, 1u);
+                }
+            }
+        } else {
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t acc = tmem_base + (uint32_t)(it % nchains) * chain_stride;
+                const uint32_t ks = (uint32_t)(it & 3);
+                if (el) {
+                    if (ts_mode) umma_f16_ts(acc, tmem_base + 480u, bd + (uint64_t)(ks * 2), idesc, it >= nchains ? 1u : 0u);
+                    else umma_f16(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, it >= nchains ? 1u : 0u);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if (el) umma_commit(smem_u32(&bar));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && el) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- operand images + coefficient records of the centres (built once per fit) ------------------------------------
@@ -537,7 +603,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     tc_fence_before();
     __syncthreads();                                                  // TMEM base address + barriers visible
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t COL_A = 384;                                   // A images (hi | lo) behind the two accumulator stages
 
     if (warp < NEPI) build_operand_A<PDE, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
@@ -583,12 +649,15 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         }
         __syncwarp();
     } else if (warp == NEPI + 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the warp stays converged and one elected lane issues, so every operand is warp-uniform and
+        // UTCHMMA reads it from uniform registers (a divergent `if (lane == 0)` block compiles to a per-lane serialisation
+        // loop around each MMA: ~95 cycles per instruction instead of the 32/64-cycle hardware floor, profiles/) =====
+        {
+            const uint32_t el = elect_one();
             const uint32_t idesc = make_idesc(TM, TN), idesc2 = make_idesc(TM, 2 * TN);
             // Descriptors are precomputed: per MMA only a constant (compile-time, loops are unrolled) is added.  The issuing
             // thread runs alone, so every dependent integer instruction would otherwise cost its full latency per MMA.
-            const uint32_t aBase = tmem_base + COL_A;
+            const uint32_t aBase = tmem_base + COL_A;                  // tmem_base was broadcast with a shuffle: uniform
             uint64_t bstage[NOPS];
 #pragma unroll
             for (int i = 0; i < NOPS; ++i) bstage[i] = make_desc(smem_u32(sStage + (size_t)i * STAGE_BYTES), 1, 64, 2);
@@ -598,13 +667,14 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 mbar_wait(op_full[s], (w / NOPS) & 1);
                 if (w >= 2) mbar_wait(acc_free[sa], ((w >> 1) - 1) & 1);      // epilogue of item w-2 drained the TMEM stage
                 tc_fence_after();
-                TC_STAMP(4 + 4 * w);
+                if (el) TC_STAMP(4 + 4 * w);
                 uint64_t bb = bstage[0];
 #pragma unroll
                 for (int i = 1; i < NOPS; ++i) bb = (s == i) ? bstage[i] : bb;
                 // K block kb of the stage: [C rows 0..63 | Croll rows 64..127], 128-byte rows
                 const uint32_t acc = tmem_base + (uint32_t)sa * ACC_STRIDE;
                 const uint32_t idm = dom ? idesc2 : idesc;              // domain tiles: one N = 128 MMA writes d1 | d2
+                if (el) {
                 // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves
 #pragma unroll
                 for (int half = 1; half >= 0; --half) {
@@ -624,6 +694,8 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 umma_commit(op_empty[s]);                                     // operand stage reusable
                 umma_commit(acc_full[sa]);                                    // accumulators ready
                 TC_STAMP(5 + 4 * w);
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -809,7 +881,7 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
     tc_fence_before();
     __syncthreads();                                                  // TMEM base address + barriers visible
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t COL_A = 256;                                   // A images hi | lo | roll hi | roll lo behind two 128-column accumulator slots
     if (warp < NEPI) build_operand_A<true, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
     tc_fence_before();
@@ -846,7 +918,8 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
         }
         __syncwarp();
     } else if (warp == NEPI + 1) {
-        if (lane == 0) {
+        {   // converged warp, elected lane issues (see eval_tc_kernel)
+            const uint32_t el = elect_one();
             const uint32_t idesc = make_idesc(TM, TN);
             const uint32_t aBase = tmem_base + COL_A;                  // images at +0 hi, +64 lo, +128 roll hi, +192 roll lo
             uint64_t bstage[NSLOT];
@@ -859,12 +932,13 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
                 mbar_wait(b_full[q], (w >> 2) & 1);
                 if (w >= 2) mbar_wait(b_free[(w - 2) & 3], ((w - 2) >> 2) & 1);   // epilogue of item w-2 drained TMEM slot w & 1
                 tc_fence_after();
-                if (w < 60) TC_STAMP(4 + 4 * w);
+                if (el && w < 60) TC_STAMP(4 + 4 * w);
                 uint64_t bb = bstage[0];
 #pragma unroll
                 for (int i = 1; i < NSLOT; ++i) bb = (q == i) ? bstage[i] : bb;
                 const uint32_t acc = tmem_base + (uint32_t)(w & 1) * 128u;
                 const uint32_t aimg = aBase + ((kind == 2) ? 128u : 0u);    // rolled A images for the kx class
+                if (el) {
 #pragma unroll
                 for (int half = 1; half >= 0; --half) {
 #pragma unroll
@@ -884,6 +958,8 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
                 }
                 umma_commit(b_acc[q]);
                 if (w < 60) TC_STAMP(5 + 4 * w);
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -1094,6 +1170,15 @@ int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, in
     dbgst.dbg = stamps_dev;
     dbgst.dbg_block = block;
     return launch_eval_tc(gp, &dbgst, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream);
+}
+
+int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream) {
+    SC_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && nchains >= 1 && nchains * N <= 448, "mma_bench: shape");
+    const size_t smem = tc::A_BLK + 256 * 128 + 1024;
+    SC_CUDA(cudaFuncSetAttribute(tc::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::mma_bench_kernel<<<148, 128, smem, stream>>>(N, nchains, ts_mode, iters, cycles_dev);
+    SC_LAUNCH_CHECK();
+    return OK;
 }
 
 int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
