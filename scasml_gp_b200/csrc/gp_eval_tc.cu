@@ -293,7 +293,7 @@ mma_bench_kernel(int N, int nchains, int ts_mode, int iters, long long* __restri
         const uint32_t el = elect_one();
         const long long t0 = clock64();
         if (ts_mode >= 2) {
-            // unrolled by 4, fixed operands per slot
+            // unrolled by 4, fixed operands per slot (ts_mode 4 / 8: with concurrent tcgen05.ld traffic from the other warps)
             const uint32_t acc0 = tmem_base, acc1 = tmem_base + (nchains > 1 ? chain_stride : 0u);
             for (int it = 0; it < iters; it += 4) {
                 if (el) {
@@ -319,6 +319,18 @@ mma_bench_kernel(int N, int nchains, int ts_mode, int iters, long long* __restri
         mbar_wait(smem_u32(&bar), 0);
         const long long t2 = clock64();
         if (blockIdx.x == 0 && el) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
+    } else if (ts_mode >= 4) {
+        // interference probe: the other warps stream accumulator columns out of tensor memory while the MMAs run
+        float acc = 0.f;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const int nld = (ts_mode >= 8) ? iters * 2 : iters / 2;
+        for (int it = 0; it < nld; ++it) {
+            float v[16];
+            tmem_ld16(tmem_base + lane_addr + 256u + (uint32_t)((it & 7) * 16), v);
+            tmem_ld_wait();
+            acc += v[it & 15];
+        }
+        if (acc == 12345.678f) cycles_out[3] = 1;
     }
     tc_fence_before();
     __syncthreads();
