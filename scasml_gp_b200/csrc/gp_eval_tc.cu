@@ -432,7 +432,7 @@ struct XF { float sx, xt, sx2, sxxt, xt2, P1, P2, R1, R2, x0, sxr, pad; };
 // ---- A operand builder: a' x = hi + lo, permuted + swizzled f16 (and the rolled copy for the PDE rows) ----
 // All global loads of a warp's 8 rows are issued before the first use (the prologue is latency-bound otherwise).
 // Row r of warp `warp` is r = warp + 16 i, so the swizzle term (r & 7) is a per-warp constant.
-template <bool PDE, int KB>
+template <bool PDE, int KB, bool TO_TMEM>
 __device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState& st, const double* __restrict__ X, long R,
                                                 long row0, uint8_t* sA, XF* xfeat, double* Ki, double* gterm,
                                                 uint32_t tmemA, int tid, int warp, int lane, long long* dbg) {
@@ -518,11 +518,12 @@ __device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState&
             for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
             if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
         }
+        fence_proxy_async();                                          // generic-proxy smem writes -> visible to SS-mode UMMA reads
         if (tid == 0) TC_STAMP(1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
         // stage the images into tensor memory: the MMAs take the A operand from TMEM (lane = row, 32-bit column c =
         // K slots 2c, 2c+1), so the 128-row A strip is not re-read from shared memory by every instruction
-        if (warp < 4 * (PDE ? 4 : 2)) {
+        if (TO_TMEM && warp < 4 * (PDE ? 4 : 2)) {
             const int img = warp >> 2;
             const int r = (warp & 3) * 32 + lane;
             const uint32_t taddr = tmemA + (uint32_t)img * 64u + ((uint32_t)((warp & 3) * 32) << 16);
@@ -618,7 +619,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint32_t COL_A = 384;                                   // A images (hi | lo) behind the two accumulator stages
 
-    if (warp < NEPI) build_operand_A<PDE, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
+    if (warp < NEPI) build_operand_A<PDE, KB, true>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -894,8 +895,9 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
     __syncthreads();                                                  // TMEM base address + barriers visible
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    constexpr uint32_t COL_A = 256;                                   // A images hi | lo | roll hi | roll lo behind two 128-column accumulator slots
-    if (warp < NEPI) build_operand_A<true, KB>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
+    // A operand stays in shared memory here (SS-mode MMAs run at the same rate, tools/tc_mma_bench.py): all 512 TMEM
+    // columns go to four 128-column accumulator slots, so the MMA warp can run three items ahead of the epilogue.
+    if (warp < NEPI) build_operand_A<true, KB, false>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, 0u, tid, warp, lane, dbg);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -933,7 +935,8 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
         {   // converged warp, elected lane issues (see eval_tc_kernel)
             const uint32_t el = elect_one();
             const uint32_t idesc = make_idesc(TM, TN);
-            const uint32_t aBase = tmem_base + COL_A;                  // images at +0 hi, +64 lo, +128 roll hi, +192 roll lo
+            const uint64_t abase = make_desc(smem_u32(sA), 1, 64, 2);   // images hi | lo | roll hi | roll lo, KB blocks each
+            auto aoff = [](int img, int step) { return (uint64_t)((((img * KB) + (step >> 2)) * A_BLK + (step & 3) * 32) >> 4); };
             uint64_t bstage[NSLOT];
 #pragma unroll
             for (int i = 0; i < NSLOT; ++i) bstage[i] = make_desc(smem_u32(sStage + (size_t)i * STAGE_BYTES), 1, 64, 2);
@@ -941,15 +944,14 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
                 const int q = w & 3;
                 int t, kind; item_of(w, t, kind);
                 const bool dom = t < ndom;
-                mbar_wait(b_full[q], (w >> 2) & 1);
-                if (w >= 2) mbar_wait(b_free[(w - 2) & 3], ((w - 2) >> 2) & 1);   // epilogue of item w-2 drained TMEM slot w & 1
+                mbar_wait(b_full[q], (w >> 2) & 1);                     // operands landed; the slot's accumulators were drained before the refill
                 tc_fence_after();
                 if (el && w < 60) TC_STAMP(4 + 4 * w);
                 uint64_t bb = bstage[0];
 #pragma unroll
                 for (int i = 1; i < NSLOT; ++i) bb = (q == i) ? bstage[i] : bb;
-                const uint32_t acc = tmem_base + (uint32_t)(w & 1) * 128u;
-                const uint32_t aimg = aBase + ((kind == 2) ? 128u : 0u);    // rolled A images for the kx class
+                const uint32_t acc = tmem_base + (uint32_t)q * 128u;
+                const uint64_t aimg = abase + ((kind == 2) ? aoff(2, 0) : 0ull);    // rolled A images for the kx class
                 if (el) {
 #pragma unroll
                 for (int half = 1; half >= 0; --half) {
@@ -957,16 +959,16 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
                     for (int step = 0; step < NSTEP; ++step) {
                         if (step == 1) continue;
                         const uint64_t bd = bb + (uint64_t)((((step >> 2) * B_BLK) + (step & 3) * 32) >> 4);
-                        umma_f16_ts(acc, aimg + (uint32_t)(half * 64 + step * 8), bd, idesc, (half == 1 && step == 0) ? 0u : 1u);
+                        umma_f16(acc, aimg + aoff(half, step), bd, idesc, (half == 1 && step == 0) ? 0u : 1u);
                     }
                 }
                 const uint64_t bd0 = bb, bd1 = bb + (uint64_t)(32 >> 4);
                 if (kind == 0) {          // e_q = A[step 1] x C[step 1]
-                    if (dom) { umma_f16_ts(acc + 64, aBase + 64u + 8u, bd1, idesc, 0); umma_f16_ts(acc + 64, aBase + 8u, bd1, idesc, 1); }
+                    if (dom) { umma_f16(acc + 64, abase + aoff(1, 1), bd1, idesc, 0); umma_f16(acc + 64, abase + aoff(0, 1), bd1, idesc, 1); }
                 } else if (kind == 1) {   // e_y = A[step 0] x Croll[step 0]
-                    umma_f16_ts(acc + 64, aBase + 64u, bd0, idesc, 0); umma_f16_ts(acc + 64, aBase, bd0, idesc, 1);
+                    umma_f16(acc + 64, abase + aoff(1, 0), bd0, idesc, 0); umma_f16(acc + 64, abase + aoff(0, 0), bd0, idesc, 1);
                 } else {                  // e_x = A[step 1] x C[step 0]
-                    umma_f16_ts(acc + 64, aBase + 64u + 8u, bd0, idesc, 0); umma_f16_ts(acc + 64, aBase + 8u, bd0, idesc, 1);
+                    umma_f16(acc + 64, abase + aoff(1, 1), bd0, idesc, 0); umma_f16(acc + 64, abase + aoff(0, 1), bd0, idesc, 1);
                 }
                 umma_commit(b_acc[q]);
                 if (w < 60) TC_STAMP(5 + 4 * w);
@@ -992,7 +994,7 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
             mbar_wait(b_acc[q], (w >> 2) & 1);
             tc_fence_after();
             if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
-            const uint32_t acc = tmem_base + (uint32_t)(w & 1) * 128u + lane_addr + cg * 16;
+            const uint32_t acc = tmem_base + (uint32_t)q * 128u + lane_addr + cg * 16;
             float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
             float v1[16], ve[16];
             tmem_ld16(acc, v1);
