@@ -678,6 +678,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                 const int s = w % NOPS, sa = w & 1;
                 const bool dom = w < st.ntile_dom;
                 mbar_wait(op_full[s], (w / NOPS) & 1);
+                mbar_wait(rec_full[w & 3], (w >> 2) & 1);                     // records too: acc_full then covers them for the epilogue
                 if (w >= 2) mbar_wait(acc_free[sa], ((w >> 1) - 1) & 1);      // epilogue of item w-2 drained the TMEM stage
                 tc_fence_after();
                 if (el) TC_STAMP(4 + 4 * w);
@@ -722,14 +723,16 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
         const float a2_5 = a2 / MC_IDX;
         double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        bool ready = false;
         for (int w = 0; w < nitem; ++w) {
             const int s = w & 1;
             const int t = PDE ? (w >> 1) : w;
             const bool kindb = PDE && (w & 1);
             const bool dom = t < st.ntile_dom;
             const int q = w & 3;
-            mbar_wait(rec_full[q], (w >> 2) & 1);                     // coefficient records landed
-            mbar_wait(acc_full[s], (w >> 1) & 1);
+            // records of item w landed before the copy of item w+... ; they were complete before its MMAs were issued, so
+            // acc_full covers them.  The next item's barrier was probed while computing (see the PDE kernel).
+            if (!ready) mbar_wait(acc_full[s], (w >> 1) & 1);
             tc_fence_after();
             if (tid == 0) TC_STAMP(6 + 4 * w);
             const uint8_t* stage = sRec + (size_t)q * REC_BYTES;
@@ -748,6 +751,7 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
                     if (dom) { tmem_ld16(acc + 64, v2); tmem_ld16(acc + 128, ve); }
                 }
                 tmem_ld_wait();
+                ready = (w + 1 < nitem) ? mbar_try_wait(acc_full[(w + 1) & 1], ((w + 1) >> 1) & 1) : true;
                 const float* rec = (const float*)stage + (cg * 16 + cb) * NFA;
 #pragma unroll
                 for (int i = 0; i < CH; ++i) {
@@ -986,12 +990,15 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
         const float a2_5 = a2 / MC_IDX;
         double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        // Barrier operations are long-latency: the next item's "accumulators ready" barrier is probed (non-blocking) while the
+        // current item is being computed, so a warp pays a blocking wait only when the MMA warp is genuinely behind.  The
+        // coefficient records of item w were complete before its MMAs were issued, so b_acc also covers them.
+        bool ready = false;
+        int t = 0, kind = 0;                                          // item 0 = (tile 0, kind 0)
         for (int w = 0; w < nitem; ++w) {
             const int q = w & 3;
-            int t, kind; item_of(w, t, kind);
             const bool dom = t < ndom;
-            mbar_wait(b_full[q], (w >> 2) & 1);                       // records landed (slot is refilled only after our release)
-            mbar_wait(b_acc[q], (w >> 2) & 1);
+            if (!ready) mbar_wait(b_acc[q], (w >> 2) & 1);
             tc_fence_after();
             if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
             const uint32_t acc = tmem_base + (uint32_t)q * 128u + lane_addr + cg * 16;
@@ -1000,6 +1007,7 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
             tmem_ld16(acc, v1);
             if (kind != 0 || dom) tmem_ld16(acc + 64, ve);
             tmem_ld_wait();
+            ready = (w + 1 < nitem) ? mbar_try_wait(b_acc[(w + 1) & 3], ((w + 1) >> 2) & 1) : true;
             if (kind == 0) {
                 const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * TC_NF0;
 #pragma unroll
@@ -1050,6 +1058,8 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
             __syncwarp();
             if (tid == 0 && w < 60) TC_STAMP(7 + 4 * w);
             if (lane == 0) mbar_arrive(b_free[q]);
+            // next item: domain tiles run kinds 0,1,2; boundary tiles kinds 0,2
+            if (kind == 2) { kind = 0; ++t; } else kind = (t < ndom) ? kind + 1 : 2;
         }
         double* xchg = (double*)sA;                                   // the A images are dead now
         if (cg > 0) { double* p = xchg + ((size_t)cg * TM + r) * 4; p[0] = U; p[1] = G; p[2] = L; p[3] = T; }
