@@ -156,6 +156,9 @@ SCASML_API int scasml_debug_tc_timeline(const scasml_gp* gp, const double* X_dev
 /* micro-benchmark: cycles per tcgen05.mma (M=128, K=16, f16) for N, `nchains` independent accumulators, A from smem (0) / TMEM (1);
  * cycles_dev[0] = issue span, cycles_dev[1] = span until the commit arrives */
 SCASML_API int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, void* stream);
+/* micro-benchmark of the epilogue pipes (csrc/tc_bench.cu: TMEM load/store, MUFU, split chunk, MMA interference);
+ * out_dev: 8 int64: [0] epilogue-warp cycles, [1] MMA issue cycles, [2] MMA cycles until commit, [3] MMA count */
+SCASML_API int scasml_debug_tc_pipe_bench(int mode, int N, int iters, long long* out_dev, void* stream);
 /* 1 if this handle can use SCASML_ROUTE_TC (d <= 100) */
 SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 

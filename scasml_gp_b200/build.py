@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscasml_b200.so")
-SOURCES = ["abi.cu", "gp_eval.cu", "gp_eval_tc.cu", "gp_fit.cu", "picard.cu"]
+SOURCES = ["abi.cu", "gp_eval.cu", "gp_eval_tc.cu", "tc_bench.cu", "gp_fit.cu", "picard.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

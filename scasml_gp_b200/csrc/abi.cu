@@ -353,6 +353,10 @@ int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int iters, long l
     return tc_mma_bench(N, nchains, ts_mode, iters, cycles_dev, (cudaStream_t)stream);
 }
 
+int scasml_debug_tc_pipe_bench(int mode, int N, int iters, long long* out_dev, void* stream) {
+    return tc_pipe_bench(mode, N, iters, out_dev, (cudaStream_t)stream);
+}
+
 int scasml_gp_tc_supported(const scasml_gp* g) { return (g && g->tc.images) ? 1 : 0; }
 
 int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream) {

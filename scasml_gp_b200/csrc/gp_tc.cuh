@@ -43,6 +43,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);
+int tc_pipe_bench(int mode, int N, int iters, long long* out_dev, cudaStream_t stream);   // tc_bench.cu
 int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
                 unsigned layout, unsigned kstep_bytes, cudaStream_t stream);
 
