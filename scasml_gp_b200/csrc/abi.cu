@@ -107,7 +107,6 @@ static int gp_alloc(scasml_gp* g) {
         const size_t bytes = tc_image_bytes(g->v, &g->tc);
         SC_CUDA(cudaMalloc(&g->tc.images, bytes));
         SC_CUDA(cudaMemset(g->tc.images, 0, bytes));
-        g->tc.tabs = (const short*)(g->tc.images + (bytes - 1024));
         g->v.tc = &g->tc;
     }
     return OK;
@@ -195,8 +194,7 @@ int scasml_gp_clone(const scasml_gp* src, scasml_gp** out) {
     SC_CUDA(cudaMemcpy(g->feat, src->feat, (size_t)nc * CF_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice));
     SC_CUDA(cudaMemcpy(g->alpha, src->alpha, (size_t)g->phi() * sizeof(double), cudaMemcpyDeviceToDevice));
     if (g->tc.images && src->tc.images)
-        SC_CUDA(cudaMemcpy(g->tc.images, src->tc.images, (size_t)(g->tc.ntile_dom + g->tc.ntile_bdy) * g->tc.tile_bytes + 1024,
-                           cudaMemcpyDeviceToDevice));
+        SC_CUDA(cudaMemcpy(g->tc.images, src->tc.images, g->tc.total_bytes, cudaMemcpyDeviceToDevice));
     *out = g;
     return OK;
 }

@@ -1,25 +1,29 @@
-// tcgen05 route of the fused surrogate evaluation (sm_100a).
+// tcgen05 route of the fused surrogate evaluation (sm_100a): two chained GEMMs per (128 points x 64 centres) tile.
 //
-// Same contract as gp_eval.cu (reference models/GP.py:630-687, 326-411, 746-769), different arithmetic:
-//   * the three distance contractions x.y, x.roll(y), roll(x).y run on the 5th-gen tensor cores:
-//     tcgen05.mma kind::f16, M = 128 points x N = 64 centres per instruction, FP32 accumulators in TMEM;
-//   * centres are float16-valued (DeepXDE float16 collocation points), so the B operand is EXACT in f16;
-//     sampled points are split  a' x = hi + lo  (two f16 terms, |error| <= 2^-22 |a' x|) and both halves are
-//     accumulated into the same TMEM tile: 2 MMA passes instead of 3xTF32, at twice the TF32 rate;
-//   * the Gaussian factorises, k(x,y) = K_i K_j exp(a x.y) with K = exp(-a |.|^2 / 2): K_j is folded into the GP
-//     weights once per fit, K_i is applied once per point, so the epilogue does one ex2 per pair-distance
-//     directly on the accumulator (the scale a log2 e is folded into the A operand);
-//   * every functional is (polynomial in separable pair quantities) x Gaussian, so it is expanded once per fit into
-//     per-centre coefficient records against per-point monomials (sx, xt, sx^2, ...): the epilogue is a handful
-//     of FMAs per pair instead of the closed forms of SURVEY App. B evaluated pair by pair;
-//   * the 5-index sums of the rotated "Laplacian" (sum_m x_{I_m} y_{I_m+1} etc.) are partial sums of the same
-//     contractions: the K axis is permuted so the index-set columns sit in k-step 0 and their successors in an
-//     extra k-step 1, and three small MMAs (A[step a] x B[step b]) deliver them as extra TMEM accumulators;
-//   * centre tiles (operand images in the 128B-swizzled K-major layout + FP32 coefficient records) are built once
-//     per fit and streamed with cp.async.bulk into a 2-stage ring; MMA of item t+1 overlaps the epilogue of t;
-//   * epilogue: 16 warps, thread <-> (point row, quarter of the tile's centres), tcgen05.ld 32x32b.x16, FP32
-//     per-tile partial sums flushed into FP64 accumulators.
-// Accuracy: ~1e-7 absolute on u_hat (FP32 exponent); parity with the FP64 route is tested under the "nocast" policy.
+// Same contract as gp_eval.cu (reference models/GP.py:630-687, 326-411, 746-769), different arithmetic.  Every functional the
+// ScaSML correction needs of the surrogate is  sum_j kernel_c(x, y_j) polynomial(x, y_j)  with kernel_c one of
+// k (x - y), ky (x - roll y), kx (roll x - y), and the Gaussian factorises, kernel_c = K_i K_j exp(a x . perm_c(y_j)).
+// Expanding the polynomial in per-point monomials F[f1] F[f2] with per-centre coefficients C (tests/tc_expansion_ref.py
+// states and checks the algebra against the closed forms of SURVEY App. B) turns the evaluation into
+//     S = (a' x) perm_c(Y)^T          stage 1: distance GEMM, tcgen05.mma kind::f16, SS mode, FP32 accumulators in TMEM
+//     P = 2^6 ex2(S)                  epilogue warps: tcgen05.ld -> ex2 -> f16 hi/lo split -> tcgen05.st, IN PLACE over S
+//     T += P C_c                      stage 2: coefficient GEMM, A operand = P straight from tensor memory (TS mode)
+//     out_o(x_i) = K_i sum_col F_i[f1] F_i[f2] T[i, col] / scale_col        once per point, FP64
+// so the per-pair work outside the tensor pipe is one TMEM load, one ex2 and three conversion/subtract instructions: both
+// measured per-pair limits of the SM (TMEM read ~16 FP32/clk, MUFU 16 ex2/clk; tools/tc_pipe_bench.py) instead of the
+// 10-45 FP32 instructions per pair of a closed-form epilogue.
+//   * centres are float16-valued (DeepXDE float16 collocation points): the stage-1 B operand is EXACT in f16; sampled
+//     points are split a' x = hi + lo (two f16 terms, 2 MMA passes into the same accumulator);
+//   * the exponent shift 2^6 rides in a spare K column (A = 1, B = 6);
+//   * P and the column-scaled coefficients are split hi + lo in f16; products hh + hl + lh accumulate into the same FP32
+//     TMEM columns over all centre tiles (relative error ~2e-7 rms, tests/test_tc_expansion.py emulates it);
+//   * one N = 192 (PDE) / N = 128 (u, u + div) MMA per k-step serves all kernel classes: the centre image rows are
+//     [C | rollinv(C) | roll(C)], because roll(x) . y = x . rollinv(y) needs no second A operand;
+//   * warp roles: 16 epilogue warps (thread <-> point row x 16 centres), 1 producer warp (cp.async.bulk rings),
+//     1 MMA warp (converged, one elected lane issues); S/P is double-buffered so stage 1 of tile t+1 and stage 2 of
+//     tile t-1 overlap the epilogue of tile t.
+// Accuracy: ~2e-7 relative rms on every output; parity with the FP64 route is tested under the "nocast" policy.
+#include <cmath>
 #include <cstring>
 #include "picard.cuh"
 #include "gp_tc.cuh"
@@ -30,458 +34,195 @@ namespace scasml {
 namespace tc {
 
 constexpr int TM = 128;              // points per CTA (UMMA M)
-constexpr int TN = 64;               // centres per tile (UMMA N)
+constexpr int TN = 64;               // centres per tile
 constexpr int A_BLK = TM * 128;      // bytes of one [128 x 64] f16 block
-constexpr int B_BLK = TN * 128;      // bytes of one [64 x 64] f16 block
-constexpr int NFA = TC_NFA;          // floats per centre record, k / ky classes
-constexpr int NFB = TC_NFB;          // floats per centre record, kx class
 constexpr int NEPI = 16;             // epilogue warps
 constexpr int NTHREADS = (NEPI + 2) * 32;   // + producer warp + MMA warp
 
+// slim device view of TcState
+struct TcDev {
+    const uint8_t* b1;               // stage-1 centre images
+    const uint8_t* b3;               // stage-2 coefficient images of this evaluation class
+    const TcColDesc* desc;           // column table of this evaluation class
+    size_t b1_tile_bytes, b3_tile_bytes;
+    int nstep, ntile_dom, ntile_bdy;
+    long long* dbg;
+    int dbg_block;
+};
 
-// ---- self test: D[128 x N] = A[128 x K] B[N x K]^T with runtime descriptor fields -------------------------------
-__global__ void __launch_bounds__(128, 1)
-selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ Dout, int K, int N,
-                uint32_t lbo16, uint32_t sbo16, uint32_t layout, uint32_t kstep_bytes) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int KB = K / KBLK;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)KB * A_BLK;
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int idx = tid; idx < TM * K; idx += 128) {
-        const int r = idx / K, c = idx % K;
-        *(__half*)(sA + (size_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK)) = A[(size_t)r * K + c];
+// ---- per-centre coefficient of one column (NumPy statement: tests/tc_expansion_ref.py::centre_coefficient) --------------
+__device__ double coef_of(const TcColSpec& sp, const double* __restrict__ f, double a, int d) {
+    const double Kj = exp(-0.5 * a * f[CF_NY]);
+    const double A1 = f[CF_A1] * Kj, A3 = f[CF_A3] * Kj, A4 = f[CF_A4] * Kj, A5 = f[CF_A5] * Kj;
+    const double sy = f[CF_SY], yt = f[CF_YT], y0 = f[CF_Y0], syr = f[CF_SYROLL], dd = (double)d;
+    const double a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
+    double Q1 = 0, Q2 = 0, T1 = 0, T2 = 0;
+    for (int m = 0; m < MC_IDX; ++m) {
+        Q1 += f[CF_YI + m]; Q2 += f[CF_YI + m] * f[CF_YI + m];
+        T1 += f[CF_YIR + m]; T2 += f[CF_YIR + m] * f[CF_YIR + m];
     }
-    for (int idx = tid; idx < N * K; idx += 128) {
-        const int r = idx / K, c = idx % K;
-        *(__half*)(sB + (size_t)(c / KBLK) * (N * 128) + sw128_off(r, c % KBLK)) = B[(size_t)r * K + c];
+    const int m = sp.m, n = sp.n;
+    const double LW = A3 * dd * dd / (MC_IDX * MC_IDX);
+    const double w3 = A3 * dd;
+    auto hc = [&](int i) {             // h = w3 (a^2/5 (P2 + T2 - 2 sum xI yr) - a) against [1, P2, xI_0..4]
+        return i == 0 ? w3 * (a2 / MC_IDX * T2 - a) : (i == 1 ? w3 * a2 / MC_IDX : -2.0 * w3 * a2 / MC_IDX * f[CF_YIR + i - 2]);
+    };
+    switch (sp.coef) {
+        case TCF_U0: return A1 - a * A4 * yt - a * A5 * sy;
+        case TCF_U1: return a * A4;
+        case TCF_U2: return a * A5;
+        case TCF_G0: return a * A1 * sy - a2 * A4 * yt * sy + a * dd * A5 - a2 * A5 * sy * sy;
+        case TCF_GSX: return -a * A1 + a2 * A4 * yt + 2.0 * a2 * A5 * sy;
+        case TCF_GXT: return a2 * A4 * sy;
+        case TCF_GSXXT: return -a2 * A4;
+        case TCF_GSX2: return -a2 * A5;
+        case TCF_T0: return a * A1 * yt + a * A4 - a2 * A4 * yt * yt - a2 * A5 * yt * sy;
+        case TCF_TXT: return -a * A1 + 2.0 * a2 * A4 * yt + a2 * A5 * sy;
+        case TCF_TSX: return a2 * A5 * yt;
+        case TCF_TXT2: return -a2 * A4;
+        case TCF_TSXXT: return -a2 * A5;
+        // lap_x lap_y = LW (a^4 q2^2 - 14 a^3 q2 + 35 a^2), q2 = R2 + T2 - 2 sum xr yr
+        case TCF_L1: return LW * (a4 * T2 * T2 - 14.0 * a3 * T2 + 35.0 * a2);
+        case TCF_LR2: return LW * (2.0 * a4 * T2 - 14.0 * a3);
+        case TCF_LR22: return LW * a4;
+        case TCF_LX: return LW * (-4.0 * a4 * T2 + 28.0 * a3) * f[CF_YIR + m];
+        case TCF_LXR2: return -4.0 * LW * a4 * f[CF_YIR + m];
+        case TCF_LXX: return LW * 4.0 * a4 * f[CF_YIR + m] * f[CF_YIR + n] * (m == n ? 1.0 : 2.0);
+        case TCF_H: return hc(m);
+        case TCF_HSX: return -a * hc(m);
+        case TCF_HG: return a * syr * hc(m) + (m == 0 ? -w3 * 2.0 * a2 / MC_IDX * T1 : (m >= 2 ? w3 * 2.0 * a2 / MC_IDX : 0.0));
+        case TCF_HXT: return -a * hc(m);
+        case TCF_HT: return a * y0 * hc(m);
+        case TCF_MX: {                 // kx class: (a^2/5 (R2 + Q2 - 2 sum xr yI) - a) (X0 + X1 x0 + X2 sxr) + X3 + X4 R1
+            const double mc = m == 0 ? a2 / MC_IDX * Q2 - a : (m == 1 ? a2 / MC_IDX : -2.0 * a2 / MC_IDX * f[CF_YI + m - 2]);
+            const double pc = n == 0 ? dd * (A1 - a * A4 * yt - a * A5 * sy) : (n == 1 ? dd * a * A4 : dd * a * A5);
+            double v = mc * pc;
+            if (n == 0 && m == 0) v += dd * 2.0 * a2 / MC_IDX * A5 * Q1;
+            if (n == 0 && m >= 2) v += -dd * 2.0 * a2 / MC_IDX * A5;
+            return v;
+        }
+        default: return 0.0;
     }
-    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 64);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    if (tid == 0) {
-        const uint32_t idesc = make_idesc(TM, N);
-        uint32_t acc = 0;
-        for (int kb = 0; kb < KB; ++kb)
-            for (int ks = 0; ks < KBLK / 16; ++ks) {
-                const uint64_t ad = make_desc(smem_u32(sA + (size_t)kb * A_BLK) + ks * kstep_bytes, lbo16, sbo16, layout);
-                const uint64_t bd = make_desc(smem_u32(sB + (size_t)kb * (N * 128)) + ks * kstep_bytes, lbo16, sbo16, layout);
-                umma_f16(tmem_base, ad, bd, idesc, acc);
-                acc = 1;
-            }
-        umma_commit(smem_u32(&bar));
-    }
-    mbar_wait(smem_u32(&bar), 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        for (int i = 0; i < 16; ++i) Dout[(size_t)tid * N + c0 + i] = v[i];
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
-
-
-// ---- self test, A operand in tensor memory: D[128 x N] = A[128 x K] B[N x K]^T -------------------------------------
-__global__ void __launch_bounds__(128, 1)
-selftest_ts_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ Dout, int K, int N) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int KB = K / KBLK;
-    uint8_t* sB = smem;
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int idx = tid; idx < N * K; idx += 128) {
-        const int r = idx / K, c = idx % K;
-        *(__half*)(sB + (size_t)(c / KBLK) * (N * 128) + sw128_off(r, c % KBLK)) = B[(size_t)r * K + c];
-    }
-    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    const uint32_t colA = 64;                                   // A image at columns [64, 64 + K/2)
-    {   // thread = row: pack two consecutive K elements per 32-bit column
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        for (int c0 = 0; c0 < K / 2; c0 += 16) {
-            uint32_t w[16];
-            for (int i = 0; i < 16; ++i) {
-                const __half lo = A[(size_t)tid * K + 2 * (c0 + i)], hi = A[(size_t)tid * K + 2 * (c0 + i) + 1];
-                w[i] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
-            }
-            tmem_st16(tmem_base + lane_addr + colA + c0, w);
-        }
-        tmem_st_wait();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-        const uint32_t idesc = make_idesc(TM, N);
-        uint32_t acc = 0;
-        for (int kb = 0; kb < KB; ++kb)
-            for (int ks = 0; ks < KBLK / 16; ++ks) {
-                const uint64_t bd = make_desc(smem_u32(sB + (size_t)kb * (N * 128)) + ks * 32, 1, 64, 2);
-                umma_f16_ts(tmem_base, tmem_base + colA + (uint32_t)(kb * 4 + ks) * 8u, bd, idesc, acc);
-                acc = 1;
-            }
-        umma_commit(smem_u32(&bar));
-    }
-    mbar_wait(smem_u32(&bar), 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
-        tmem_ld_wait();
-        for (int i = 0; i < 16; ++i) Dout[(size_t)tid * N + c0 + i] = v[i];
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+// pass 1: FP64 coefficient matrix [class][centre][TC_MAXCOL] + per-column maxima (column scaling of the f16 split)
+__global__ void coef_kernel(GpView gp, const TcColSpec* __restrict__ spec, int ncentres, double* __restrict__ coef,
+                            unsigned long long* __restrict__ colmax) {
+    const int cls = blockIdx.y;
+    const int j = blockIdx.x;                                  // padded centre index
+    const int col = threadIdx.x;                               // TC_MAXCOL threads
+    const TcColSpec sp = spec[cls * TC_MAXCOL + col];
+    double v = 0.0;
+    const bool dom = j < gp.NdPad;
+    if (sp.out != TO_PAD && (dom || sp.kern != TK_KY)) v = coef_of(sp, gp.feat + (size_t)j * CF_STRIDE, gp.a, gp.d);
+    coef[((size_t)cls * ncentres + j) * TC_MAXCOL + col] = v;
+    const double av = fabs(v);
+    if (av > 0.0 && av < 1e300) atomicMax(colmax + cls * TC_MAXCOL + col, (unsigned long long)__double_as_longlong(av));
 }
 
-
-// ---- micro-benchmark: cycles per tcgen05.mma (M = 128, K = 16, f16) for a given N, number of independent
-//      accumulator chains and A source; one CTA per SM, no epilogue.  Used to size tiles (profiles/). -----------------
-__global__ void __launch_bounds__(128, 1)
-mma_bench_kernel(int N, int nchains, int ts_mode, int iters, long long* __restrict__ cycles_out) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw;
-    uint8_t* sA = smem;                       // [128 x 64] f16 block
-    uint8_t* sB = smem + A_BLK;               // [256 x 64] f16 block
-    __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < (A_BLK + 256 * 128) / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;   // f16 ones
-    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-    if (warp == 0) {
-        // converged warp, one elected lane issues: operands are warp-uniform, so UTCHMMA takes them from uniform
-        // registers without the per-lane serialisation loop a divergent `if (lane == 0)` block compiles to
-        const uint32_t idesc = make_idesc(TM, N);
-        const uint64_t ad = make_desc(smem_u32(sA), 1, 64, 2), bd = make_desc(smem_u32(sB), 1, 64, 2);
-        const uint32_t chain_stride = (uint32_t)N;
-        const uint32_t el = elect_one();
-        const long long t0 = clock64();
-        if (ts_mode >= 2) {
-            // unrolled by 4, fixed operands per slot (ts_mode 4 / 8: with concurrent tcgen05.ld traffic from the other warps)
-            const uint32_t acc0 = tmem_base, acc1 = tmem_base + (nchains > 1 ? chain_stride : 0u);
-            for (int it = 0; it < iters; it += 4) {
-                if (el) {
-                    umma_f16_ts(acc0, tmem_base + 480u, bd, idesc, 1u);
-                    umma_f16_ts(acc1, tmem_base + 480u, bd + 2ull, idesc, 1u);
-                    umma_f16_ts(acc0, tmem_base + 488u, bd + 4ull, idesc, 1u);
-                    umma_f16_ts(acc1, tmem_base + 488u, bd + 6ull, idesc, 1u);
-                }
-            }
-        } else {
-            for (int it = 0; it < iters; ++it) {
-                const uint32_t acc = tmem_base + (uint32_t)(it % nchains) * chain_stride;
-                const uint32_t ks = (uint32_t)(it & 3);
-                if (el) {
-                    if (ts_mode) umma_f16_ts(acc, tmem_base + 480u, bd + (uint64_t)(ks * 2), idesc, it >= nchains ? 1u : 0u);
-                    else umma_f16(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, it >= nchains ? 1u : 0u);
-                }
-            }
-        }
-        const long long t1 = clock64();
-        if (el) umma_commit(smem_u32(&bar));
-        __syncwarp();
-        mbar_wait(smem_u32(&bar), 0);
-        const long long t2 = clock64();
-        if (blockIdx.x == 0 && el) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
-    } else if (ts_mode >= 4) {
-        // interference probe: the other warps stream accumulator columns out of tensor memory while the MMAs run
-        float acc = 0.f;
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        const int nld = (ts_mode >= 8) ? iters * 2 : iters / 2;
-        for (int it = 0; it < nld; ++it) {
-            float v[16];
-            tmem_ld16(tmem_base + lane_addr + 256u + (uint32_t)((it & 7) * 16), v);
-            tmem_ld_wait();
-            acc += v[it & 15];
-        }
-        if (acc == 12345.678f) cycles_out[3] = 1;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+// byte offset of element (row r, col c) inside a [rows x 64] f16 block, Swizzle<3,4,3> (r may exceed 63: 8-row groups are 1024 B apart)
+__device__ __forceinline__ uint32_t sw_off(int r, int c) {
+    return (uint32_t)(r * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
 }
 
-// ---- operand images + coefficient records of the centres (built once per fit) ------------------------------------
-// per tile t: [C image: KB blocks of [64 x 64] f16][Croll image (zeros for boundary tiles)][recA 64 x NFA f32][recB 64 x NFB f32]
-// K axis permuted by st.perm: k-step 0 = index-set columns I_m, k-step 1 = I_m + 1, k-steps >= 2 = all other columns.
-__global__ void build_images_kernel(GpView gp, TcState st) {
+// pass 2a: stage-1 centre images.  Per tile, per K block: rows [C (64) | rollinv(C) (64) | roll(C) (64)], f16, 128 B swizzle.
+// Column D carries the exponent shift (TC_P_SHIFT in every row); columns > D are zero.
+__global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile_bytes, int KB) {
     const int tile = blockIdx.x;
-    const bool dom = tile < st.ntile_dom;
-    const int c0 = tile * TN;                          // padded centre index of the tile's first centre
-    uint8_t* base = st.images + (size_t)tile * st.tile_bytes;
-    const int D = gp.D, d = gp.d, KB = st.KB;
-    const double a = gp.a, a2 = a * a, a3 = a2 * a;
+    uint8_t* base = b1 + (size_t)tile * tile_bytes;
+    const int D = gp.D;
     for (int idx = threadIdx.x; idx < TN * KB * KBLK; idx += blockDim.x) {
         const int r = idx / (KB * KBLK), c = idx % (KB * KBLK);
-        const int src = st.perm[c];
-        const double* y = gp.C + (size_t)(c0 + r) * D;
-        const double v = (src >= 0) ? y[src] : 0.0;
-        const bool step1 = (c >= 16 && c < 32);
-        const double vr = (src >= 0 && !step1 && dom) ? y[(src + 1 == D) ? 0 : src + 1] : 0.0;
-        // K block kb holds [C rows 0..63 | Croll rows 0..63]: one 128-row operand for the merged d1|d2 MMA
-        const uint32_t off = (uint32_t)(c / KBLK) * (2 * B_BLK) + sw128_off(r, c % KBLK);
-        *(__half*)(base + off) = __double2half(v);
-        *(__half*)(base + B_BLK + off) = __double2half(vr);
-    }
-    float* recA = (float*)(base + 2 * (size_t)KB * B_BLK);
-    float* recB = recA + TN * NFA;
-    const double inv = st.inv_ascale;                  // accumulators carry a log2(e) x (dot product)
-    for (int r = threadIdx.x; r < TN; r += blockDim.x) {
-        const double* f = gp.feat + (size_t)(c0 + r) * CF_STRIDE;
-        const double Kj = exp(-0.5 * a * f[CF_NY]);
-        const double A1 = f[CF_A1] * Kj, A3 = f[CF_A3] * Kj, A4 = f[CF_A4] * Kj, A5 = f[CF_A5] * Kj;
-        const double sy = f[CF_SY], yt = f[CF_YT], y0 = f[CF_Y0], syr = f[CF_SYROLL], dd = (double)d;
-        double Q1 = 0, Q2 = 0, T1 = 0, T2 = 0;
-        for (int m = 0; m < MC_IDX; ++m) {
-            Q1 += f[CF_YI + m]; Q2 += f[CF_YI + m] * f[CF_YI + m];
-            T1 += f[CF_YIR + m]; T2 += f[CF_YIR + m] * f[CF_YIR + m];
+        const double* y = gp.C + (size_t)(tile * TN + r) * D;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        if (c < D) {
+            v0 = y[c];
+            v1 = y[(c == 0) ? D - 1 : c - 1];            // roll(x) . y = x . rollinv(y),  rollinv(y)_c = y_{c-1}
+            v2 = y[(c + 1 == D) ? 0 : c + 1];            // roll(y)_c = y_{c+1}            (models/GP.py:91-93)
+        } else if (c == D) {
+            v0 = v1 = v2 = (double)TC_P_SHIFT;
         }
-        float* o = recA + r * NFA;
-        // k class, u:  A1 + a A4 (xt - yt) + a A5 (sx - sy)
-        o[RA_U0] = (float)(A1 - a * A4 * yt - a * A5 * sy);
-        o[RA_U1] = (float)(a * A4);
-        o[RA_U2] = (float)(a * A5);
-        // ky class, h = w3 (a^2/5 m2 - a), m2 = P2 + T2 - 2 e_y ; w3 = A3 d
-        const double w3 = A3 * dd;
-        o[RA_Y0] = (float)(w3 * (a2 / MC_IDX * T2 - a));
-        o[RA_Y1] = (float)(w3 * a2 / MC_IDX);
-        o[RA_Y2] = (float)(-2.0 * w3 * a2 / MC_IDX * inv);
-        // ky class, div_x:  w3 (2a^2/5 (P1 - T1)) - a Sy h
-        o[RA_Y3] = (float)(-w3 * 2.0 * a2 / MC_IDX * T1);
-        o[RA_Y4] = (float)(w3 * 2.0 * a2 / MC_IDX);
-        // k class, div_x:  -a S A1 - a^2 rt S A4 + (a d - a^2 S^2) A5
-        o[RA_G0] = (float)(a * A1 * sy - a2 * A4 * yt * sy + a * dd * A5 - a2 * A5 * sy * sy);
-        o[RA_GSX] = (float)(-a * A1 + a2 * A4 * yt + 2.0 * a2 * A5 * sy);
-        o[RA_GXT] = (float)(a2 * A4 * sy);
-        o[RA_GSXXT] = (float)(-a2 * A4);
-        o[RA_GSX2] = (float)(-a2 * A5);
-        o[RA_SYR] = (float)syr;
-        o[RA_Y0T] = (float)y0;
-        o[RA_T2] = (float)T2;
-        // k class, dt_x:  -a rt A1 + (a - a^2 rt^2) A4 - a^2 rt S A5
-        o[RA_T0] = (float)(a * A1 * yt + a * A4 - a2 * A4 * yt * yt - a2 * A5 * yt * sy);
-        o[RA_TXT] = (float)(-a * A1 + 2.0 * a2 * A4 * yt + a2 * A5 * sy);
-        o[RA_TSX] = (float)(a2 * A5 * yt);
-        o[RA_TXT2] = (float)(-a2 * A4);
-        o[RA_TSXXT] = (float)(-a2 * A5);
-        // k class, lap_x lap_y:  A3 d^2/25 (a^4 q2^2 - 14 a^3 q2 + 35 a^2)
-        o[RA_LW] = (float)(A3 * dd * dd / (MC_IDX * MC_IDX));
-        o[22] = 0.f; o[23] = 0.f;
-        // kx class:  d [ MHx (A1 + a A4 (x0 - yt) + a A5 (sxr - sy)) - 2a^2/5 A5 (R1 - Q1) ]
-        float* p = recB + r * NFB;
-        p[RB_X0] = (float)(dd * (A1 - a * A4 * yt - a * A5 * sy));
-        p[RB_X1] = (float)(dd * a * A4);
-        p[RB_X2] = (float)(dd * a * A5);
-        p[RB_X3] = (float)(dd * 2.0 * a2 / MC_IDX * A5 * Q1);
-        p[RB_X4] = (float)(-dd * 2.0 * a2 / MC_IDX * A5);
-        p[RB_Q2] = (float)Q2;
-        p[6] = 0.f; p[7] = 0.f;
-        (void)a3;
-        // PDE kernel: the same coefficients regrouped per item kind
-        float* r0 = recB + TN * NFB + r * TC_NF0;
-        r0[0] = o[RA_U0]; r0[1] = o[RA_U1]; r0[2] = o[RA_U2]; r0[3] = o[RA_GSX2];
-        r0[4] = o[RA_G0]; r0[5] = o[RA_GSX]; r0[6] = o[RA_GXT]; r0[7] = o[RA_GSXXT];
-        r0[8] = o[RA_T0]; r0[9] = o[RA_TXT]; r0[10] = o[RA_TSX]; r0[11] = o[RA_TXT2];
-        r0[12] = o[RA_TSXXT]; r0[13] = o[RA_T2]; r0[14] = o[RA_LW]; r0[15] = 0.f;
-        float* r1 = recB + TN * NFB + TN * TC_NF0 + r * TC_NF1;
-        r1[0] = o[RA_Y0]; r1[1] = o[RA_Y1]; r1[2] = o[RA_Y2]; r1[3] = o[RA_Y3];
-        r1[4] = o[RA_Y4]; r1[5] = o[RA_SYR]; r1[6] = o[RA_Y0T]; r1[7] = 0.f;
+        uint8_t* blk = base + (size_t)(c / KBLK) * (3 * TN * 128);
+        *(__half*)(blk + sw_off(r, c % KBLK)) = __double2half(v0);
+        *(__half*)(blk + sw_off(TN + r, c % KBLK)) = __double2half(v1);
+        *(__half*)(blk + sw_off(2 * TN + r, c % KBLK)) = __double2half(v2);
+    }
+}
+
+// pass 2b: stage-2 coefficient images of one evaluation class: per tile [k hi | k lo | ky hi | ky lo | kx hi | kx lo],
+// each [ncol rows x 64 centres] f16 (K-major B operand, 128 B swizzle); column table with the inverse scales.
+__global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, int cls, int ncentres, const double* __restrict__ coef,
+                                const unsigned long long* __restrict__ colmax, uint8_t* __restrict__ b3, size_t tile_bytes,
+                                int nk, int nky, int nkx, TcColDesc* __restrict__ desc) {
+    const int tile = blockIdx.x;
+    uint8_t* base = b3 + (size_t)tile * tile_bytes;
+    const int ntot = nk + nky + nkx;
+    for (int idx = threadIdx.x; idx < ntot * TN; idx += blockDim.x) {
+        const int col = idx / TN, j = idx % TN;
+        const double cm = __longlong_as_double((long long)colmax[cls * TC_MAXCOL + col]);
+        int e = 0;
+        if (cm > 0.0) frexp(cm, &e);
+        const double scale = (cm > 0.0) ? ldexp(1.0, 13 - e) : 1.0;       // column maximum -> [2^12, 2^13)
+        const double v = coef[((size_t)cls * ncentres + (size_t)tile * TN + j) * TC_MAXCOL + col] * scale;
+        const __half hi = __double2half(v);
+        const __half lo = __double2half(v - (double)__half2float(hi));
+        int row = col;
+        size_t off = 0;
+        int n = nk;
+        if (col >= nk + nky) { row = col - nk - nky; off = (size_t)2 * (nk + nky) * 128; n = nkx; }
+        else if (col >= nk) { row = col - nk; off = (size_t)2 * nk * 128; n = nky; }
+        *(__half*)(base + off + sw_off(row, j)) = hi;
+        *(__half*)(base + off + (size_t)n * 128 + sw_off(row, j)) = lo;
+        if (tile == 0 && j == 0) {
+            const TcColSpec sp = spec[cls * TC_MAXCOL + col];
+            TcColDesc dsc;
+            dsc.f1 = sp.f1; dsc.f2 = sp.f2; dsc.out = sp.out;
+            for (int q = 0; q < 5; ++q) dsc.pad[q] = 0;
+            dsc.inv_scale = 1.0 / (scale * (double)(1 << TC_P_SHIFT));
+            desc[col] = dsc;
+        }
     }
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
-// CLASS 0: u (EVAL_U / EVAL_TERMINAL), 1: u + div_x u, 2: PDE residual.  KB: 64-wide K blocks (1 or 2).
-struct XF { float sx, xt, sx2, sxxt, xt2, P1, P2, R1, R2, x0, sxr, pad; };
+template <int CLASS> struct Cfg;
+template <> struct Cfg<TC_U>   { static constexpr int NS = 128, NK = 16, NKY = 16, NKX = 0,  NB1 = 4; };
+template <> struct Cfg<TC_UG>  { static constexpr int NS = 128, NK = 16, NKY = 32, NKX = 0,  NB1 = 4; };
+template <> struct Cfg<TC_PDE> { static constexpr int NS = 192, NK = 48, NKY = 48, NKX = 32, NB1 = 3; };
 
-// ---- A operand builder: a' x = hi + lo, permuted + swizzled f16 (and the rolled copy for the PDE rows) ----
-// All global loads of a warp's 8 rows are issued before the first use (the prologue is latency-bound otherwise).
-// Row r of warp `warp` is r = warp + 16 i, so the swizzle term (r & 7) is a per-warp constant.
-template <bool PDE, int KB, bool TO_TMEM>
-__device__ __forceinline__ void build_operand_A(const GpView& gp, const TcState& st, const double* __restrict__ X, long R,
-                                                long row0, uint8_t* sA, XF* xfeat, double* Ki, double* gterm,
-                                                uint32_t tmemA, int tid, int warp, int lane, long long* dbg) {
-    const int D = gp.D, d = gp.d;
-    const double ascale = gp.a * 1.4426950408889634;                  // a log2(e): accumulator = log2 of exp(a x.y)
-#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
-        constexpr int RPW = TM / NEPI;                                // rows per warp
-        int slot_m[4], slot_1[4], slot_r[4];                          // this lane's columns -> permuted slots
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = lane + 32 * q;
-            slot_m[q] = (c < D) ? __ldg(st.tabs + 128 + c) : 0;
-            slot_1[q] = (c < D) ? __ldg(st.tabs + 256 + c) : -1;
-            slot_r[q] = (c < D) ? __ldg(st.tabs + 128 + ((c == 0) ? D - 1 : c - 1)) : 0;
-        }
-        bool padslot[KB * 2];                                         // this lane's slots c = lane + 32 i: zero padding?
-#pragma unroll
-        for (int i = 0; i < KB * 2; ++i) padslot[i] = __ldg(st.tabs + lane + 32 * i) < 0;
-        // byte offset of (row r, slot) = base(slot) + 128 r, where base folds the per-warp-constant swizzle (r & 7 == warp & 7)
-        const int x7 = warp & 7;
-        auto slot_base = [&](int slot) {
-            return (uint32_t)(slot / KBLK) * A_BLK + (uint32_t)(((((slot % KBLK) >> 3) ^ x7) & 7) << 4) + (uint32_t)(slot & 7) * 2u;
-        };
-        uint32_t base_m[4], base_1[4], base_r[4], base_p[KB * 2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { base_m[q] = slot_base(slot_m[q]); base_1[q] = slot_base(slot_1[q] < 0 ? 0 : slot_1[q]); base_r[q] = slot_base(slot_r[q]); }
-#pragma unroll
-        for (int i = 0; i < KB * 2; ++i) base_p[i] = slot_base(lane + 32 * i);
-        constexpr uint32_t IMG = (uint32_t)KB * A_BLK;                // bytes per A image
-        double v[RPW][4];
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const long row = row0 + warp + NEPI * i;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = lane + 32 * q;
-                v[i][q] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
-            }
-        }
-        // zero padding slots (k-step padding and, for the rolled images, the whole k-step 1)
-        const __half hz = __float2half_rn(0.f);
-#pragma unroll
-        for (int ri = 0; ri < RPW; ++ri) {
-            uint8_t* rowp = sA + (uint32_t)(warp + NEPI * ri) * 128u;
-#pragma unroll
-            for (int i = 0; i < KB * 2; ++i) {
-                const int c = lane + 32 * i;
-                if (padslot[i]) { *(__half*)(rowp + base_p[i]) = hz; *(__half*)(rowp + IMG + base_p[i]) = hz; }
-                if (PDE && (padslot[i] || (c >= 16 && c < 32))) {
-                    *(__half*)(rowp + 2 * IMG + base_p[i]) = hz;
-                    *(__half*)(rowp + 3 * IMG + base_p[i]) = hz;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const int r = warp + NEPI * i;
-            uint8_t* rowp = sA + (uint32_t)r * 128u;
-            double nx = 0.0, sxs = 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = lane + 32 * q;
-                if (c < D) {
-                    const double val = v[i][q];
-                    nx = fma(val, val, nx);
-                    if (c < d) sxs += val;
-                    // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
-                    const float sv = (float)(ascale * val);
-                    const __half h = __float2half_rn(sv);
-                    const __half lo = __float2half_rn(sv - __half2float(h));
-                    *(__half*)(rowp + base_m[q]) = h;
-                    *(__half*)(rowp + IMG + base_m[q]) = lo;
-                    if (slot_1[q] >= 0) {
-                        *(__half*)(rowp + base_1[q]) = h;
-                        *(__half*)(rowp + IMG + base_1[q]) = lo;
-                    }
-                    if (PDE) {                                        // roll(x)_{c-1} = x_c
-                        *(__half*)(rowp + 2 * IMG + base_r[q]) = h;
-                        *(__half*)(rowp + 3 * IMG + base_r[q]) = lo;
-                    }
-                }
-            }
-            for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sxs += __shfl_xor_sync(0xffffffffu, sxs, o); }
-            if (lane == 0) { Ki[r] = nx; gterm[r] = sxs; }            // raw sums; finalised per row below
-        }
-        fence_proxy_async();                                          // generic-proxy smem writes -> visible to SS-mode UMMA reads
-        if (tid == 0) TC_STAMP(1);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        // stage the images into tensor memory: the MMAs take the A operand from TMEM (lane = row, 32-bit column c =
-        // K slots 2c, 2c+1), so the 128-row A strip is not re-read from shared memory by every instruction
-        if (TO_TMEM && warp < 4 * (PDE ? 4 : 2)) {
-            const int img = warp >> 2;
-            const int r = (warp & 3) * 32 + lane;
-            const uint32_t taddr = tmemA + (uint32_t)img * 64u + ((uint32_t)((warp & 3) * 32) << 16);
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-                const uint8_t* rowp = sA + (size_t)img * IMG + (size_t)kb * A_BLK + (uint32_t)r * 128u;
-#pragma unroll
-                for (int j0 = 0; j0 < 8; j0 += 4) {
-                    uint32_t wv[16];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 ch = *(const uint4*)(rowp + ((((j0 + j) ^ (r & 7)) & 7) << 4));
-                        wv[4 * j] = ch.x; wv[4 * j + 1] = ch.y; wv[4 * j + 2] = ch.z; wv[4 * j + 3] = ch.w;
-                    }
-                    tmem_st16(taddr + (uint32_t)(kb * 32 + j0 * 4), wv);
-                }
-            }
-            tmem_st_wait();
-        }
-        if (tid < TM) {
-            const int r = tid;
-            const long row = row0 + r;
-            const bool ok = row < R;
-            const double* xr = X + row * (long)D;
-            const double nx = Ki[r], sxs = gterm[r];
-            const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
-            double P1 = 0, P2 = 0, R1 = 0, R2 = 0;
-#pragma unroll
-            for (int m = 0; m < MC_IDX; ++m) {
-                const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                P1 += xi; P2 = fma(xi, xi, P2); R1 += xir; R2 = fma(xir, xir, R2);
-            }
-            XF f;
-            f.sx = (float)sxs; f.xt = (float)xt; f.sx2 = (float)(sxs * sxs); f.sxxt = (float)(sxs * xt); f.xt2 = (float)(xt * xt);
-            f.P1 = (float)P1; f.P2 = (float)P2; f.R1 = (float)R1; f.R2 = (float)R2;
-            f.x0 = (float)x0; f.sxr = (float)(sxs - x0 + xt); f.pad = 0.f;
-            xfeat[r] = f;
-            Ki[r] = exp(-0.5 * gp.a * nx);
-            gterm[r] = 1.0 - 1.0 / (1.0 + exp(sxs + xt));                     // equations.py:259
-        }
-#undef TC_STAMP
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
 }
 
-
-// CLASS 0 / 1 only (the PDE residual has its own kernel below)
 template <int CLASS, int KB>
 __global__ void __launch_bounds__(NTHREADS, 1)
-eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int mode,
+eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode,
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
-    constexpr bool PDE = (CLASS == 2);
-    constexpr int NA = PDE ? 4 : 2;                                   // A images: hi, lo (, roll hi, roll lo)
-    constexpr int NSTEP = 4 * KB;                                     // k-steps of 16
-    constexpr uint32_t STAGE_BYTES = 2 * KB * B_BLK;                  // operand stage: per K block [C rows | Croll rows]
-    constexpr uint32_t REC_BYTES = TN * NFA * 4;                      // coefficient-record slot
-    constexpr int NREC = 4;
-    constexpr int NOPS = PDE ? 2 : 3;                                 // operand stages (shared-memory budget)
-    extern __shared__ __align__(1024) uint8_t smem_raw[];             // no static smem in this kernel: window offset 0
-    uint8_t* smem = smem_raw;                                         // (plain pointer arithmetic keeps LDS/STS codegen)
+    using C = Cfg<CLASS>;
+    constexpr bool PDE = (CLASS == TC_PDE);
+    constexpr int NS = C::NS;                                        // S columns of a domain tile
+    constexpr int NT = C::NK + C::NKY + C::NKX;                      // T columns
+    constexpr int NB1 = C::NB1;                                      // stage-1 operand ring: K blocks
+    constexpr uint32_t B1_SLOT = NS * 128;                           // one K block of one tile
+    constexpr uint32_t B3_SLOT = 2 * NT * 128;                       // one tile's coefficient images (hi + lo)
+    constexpr uint32_t COL_T = 2 * NS;                               // TMEM: S/P buffers at 0 and NS, T behind them
+    // S column offset of each kernel class inside a buffer; PDE: [k | kx | ky], else [k | ky]
+    constexpr int SC_K = 0, SC_KY = PDE ? 128 : 64, SC_KX = 64;
+    constexpr int TC_K = 0, TC_KY = C::NK, TC_KX = C::NK + C::NKY;   // T column offsets
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
+    uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
-    uint8_t* sA = smem;                                               // NA * KB * A_BLK (re-used as exchange buffer at the end)
-    uint8_t* sStage = sA + (size_t)NA * KB * A_BLK;                   // NOPS operand stages, freed by the MMA commit
-    uint8_t* sRec = sStage + NOPS * (size_t)STAGE_BYTES;              // 4 record slots, freed by the epilogue
-    uint8_t* sMisc = sRec + NREC * (size_t)REC_BYTES;
-    XF* xfeat = (XF*)sMisc;                                           // [128]
-    double* Ki = (double*)(sMisc + TM * sizeof(XF));                  // [128]
-    double* gterm = Ki + TM;                                          // [128]
-    uint64_t* bars = (uint64_t*)(gterm + TM);                         // op_full[3] op_empty[3] acc_full[2] acc_free[2] rec_full[4] rec_free[4]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+    uint8_t* sA = smem;                                              // [hi | lo] x KB blocks of [128 x 64] f16
+    uint8_t* sB1 = sA + 2 * (size_t)KB * A_BLK;
+    uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;
+    uint8_t* sMisc = sB3 + 2 * (size_t)B3_SLOT;
+    double* Ki = (double*)sMisc;                                     // [128] exp(-a |x|^2 / 2)
+    double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i
+    uint64_t* bars = (uint64_t*)(sxs + TM);                          // b1_full[4] b1_empty[4] b3_full[2] b3_empty[2] s_full[2] p_ready[2] t_full
+    uint32_t* tmem_slot = (uint32_t*)(bars + 17);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
@@ -489,486 +230,329 @@ eval_tc_kernel(GpView gp, TcState st, const double* __restrict__ X, long R, int 
     long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
 #define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
-    const uint32_t op_full[3] = {smem_u32(&bars[0]), smem_u32(&bars[1]), smem_u32(&bars[2])};
-    const uint32_t op_empty[3] = {smem_u32(&bars[3]), smem_u32(&bars[4]), smem_u32(&bars[5])};
-    const uint32_t acc_full[2] = {smem_u32(&bars[6]), smem_u32(&bars[7])};
-    const uint32_t acc_free[2] = {smem_u32(&bars[8]), smem_u32(&bars[9])};
-    const uint32_t rec_full[4] = {smem_u32(&bars[10]), smem_u32(&bars[11]), smem_u32(&bars[12]), smem_u32(&bars[13])};
-    const uint32_t rec_free[4] = {smem_u32(&bars[14]), smem_u32(&bars[15]), smem_u32(&bars[16]), smem_u32(&bars[17])};
+    uint32_t b1_full[4], b1_empty[4], b3_full[2], b3_empty[2], s_full[2], p_ready[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { b1_full[i] = smem_u32(&bars[i]); b1_empty[i] = smem_u32(&bars[4 + i]); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        b3_full[i] = smem_u32(&bars[8 + i]); b3_empty[i] = smem_u32(&bars[10 + i]);
+        s_full[i] = smem_u32(&bars[12 + i]); p_ready[i] = smem_u32(&bars[14 + i]);
+    }
+    const uint32_t t_full = smem_u32(&bars[16]);
 
     if (tid == 0) {
-        for (int s = 0; s < 3; ++s) { mbar_init(op_full[s], 1); mbar_init(op_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full[s], 1); mbar_init(acc_free[s], NEPI); }
-        for (int q = 0; q < NREC; ++q) { mbar_init(rec_full[q], 1); mbar_init(rec_free[q], NEPI); }
+        for (int i = 0; i < 4; ++i) { mbar_init(b1_full[i], 1); mbar_init(b1_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(b3_full[i], 1); mbar_init(b3_empty[i], 1); mbar_init(s_full[i], 1); mbar_init(p_ready[i], NEPI); }
+        mbar_init(t_full, 1);
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
-    __syncthreads();                                                  // TMEM base address + barriers visible
+    __syncthreads();                                                 // TMEM base address + barriers visible
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    constexpr uint32_t COL_A = 384;                                   // A images (hi | lo) behind the two accumulator stages
-
-    if (warp < NEPI) build_operand_A<PDE, KB, true>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, tmem_base + COL_A, tid, warp, lane, dbg);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) TC_STAMP(2);
-    const int ntile = st.ntile_dom + st.ntile_bdy;
-    const int nitem = PDE ? 2 * ntile : ntile;
-    // TMEM columns.  CLASS 0/1: stage s at 192 s: d1 | d2 | e_y.  PDE: kind a at 0: d1 | d2 | e_y | e_q ; kind b at 256: d3 | e_x.
-    constexpr uint32_t ACC_STRIDE = PDE ? 256 : 192;
+    const int ndom = st.ntile_dom, ntile = st.ntile_dom + st.ntile_bdy;
+    const int nstep = st.nstep;
 
     if (warp == NEPI) {
-        // ===== producer: stream centre tiles (operand images) and coefficient records =====
+        // ===== producer: centre images (one K block per ring slot) and coefficient images (one tile per slot) =====
+        // issue order = consumption order of the MMA warp: B1(0), B1(1), B3(0), B1(2), B3(1), ...
         if (lane == 0) {
-            for (int w = 0; w < nitem; ++w) {
-                const int s = w % NOPS, q = w & 3;
-                if (w >= NOPS) mbar_wait(op_empty[s], ((w / NOPS) - 1) & 1);  // MMAs of item w-NOPS have read the stage
-                if (w >= 4) mbar_wait(rec_free[q], ((w >> 2) - 1) & 1);       // epilogue of item w-4 is done with the slot
-                const int t = PDE ? (w >> 1) : w;
-                const bool kindb = PDE && (w & 1);
-                const bool dom = t < st.ntile_dom;
-                const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
-                uint8_t* dst = sStage + (size_t)s * STAGE_BYTES;
-                uint8_t* rdst = sRec + (size_t)q * REC_BYTES;
-                if (dom && !kindb) {                                  // C and Croll rows of every K block
-                    mbar_expect_tx(op_full[s], STAGE_BYTES);
-                    bulk_g2s(smem_u32(dst), src, STAGE_BYTES, op_full[s]);
-                } else {                                              // C rows only
-                    mbar_expect_tx(op_full[s], KB * B_BLK);
+            int i1 = 0;
+            auto load_b1 = [&](int t) {
+                const bool dom = t < ndom;
+                const uint8_t* src = st.b1 + (size_t)t * st.b1_tile_bytes;
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb)
-                        bulk_g2s(smem_u32(dst + kb * 2 * B_BLK), src + (size_t)kb * 2 * B_BLK, B_BLK, op_full[s]);
+                for (int kb = 0; kb < KB; ++kb, ++i1) {
+                    const int s = i1 % NB1;
+                    if (i1 >= NB1) mbar_wait(b1_empty[s], ((i1 / NB1) - 1) & 1);
+                    uint8_t* dst = sB1 + (size_t)s * B1_SLOT;
+                    const uint8_t* blk = src + (size_t)kb * (3 * TN * 128);
+                    if (PDE) {                                       // rows [C | Crollinv (| Croll)]
+                        const uint32_t bytes = dom ? 3 * TN * 128 : 2 * TN * 128;
+                        mbar_expect_tx(b1_full[s], bytes);
+                        bulk_g2s(smem_u32(dst), blk, bytes, b1_full[s]);
+                    } else if (dom) {                                // rows [C | Croll]
+                        mbar_expect_tx(b1_full[s], 2 * TN * 128);
+                        bulk_g2s(smem_u32(dst), blk, TN * 128, b1_full[s]);
+                        bulk_g2s(smem_u32(dst + TN * 128), blk + 2 * TN * 128, TN * 128, b1_full[s]);
+                    } else {
+                        mbar_expect_tx(b1_full[s], TN * 128);
+                        bulk_g2s(smem_u32(dst), blk, TN * 128, b1_full[s]);
+                    }
                 }
-                if (!kindb) {
-                    mbar_expect_tx(rec_full[q], TN * NFA * 4);
-                    bulk_g2s(smem_u32(rdst), src + STAGE_BYTES, TN * NFA * 4, rec_full[q]);
-                } else {
-                    mbar_expect_tx(rec_full[q], TN * NFB * 4);
-                    bulk_g2s(smem_u32(rdst), src + STAGE_BYTES + TN * NFA * 4, TN * NFB * 4, rec_full[q]);
+            };
+            auto load_b3 = [&](int t) {
+                const int s = t & 1;
+                if (t >= 2) mbar_wait(b3_empty[s], ((t >> 1) - 1) & 1);
+                const uint8_t* src = st.b3 + (size_t)t * st.b3_tile_bytes;
+                uint8_t* dst = sB3 + (size_t)s * B3_SLOT;
+                if (t < ndom) {
+                    mbar_expect_tx(b3_full[s], B3_SLOT);
+                    bulk_g2s(smem_u32(dst), src, B3_SLOT, b3_full[s]);
+                } else {                                             // boundary tiles: no ky class
+                    mbar_expect_tx(b3_full[s], 2 * (C::NK + C::NKX) * 128);
+                    bulk_g2s(smem_u32(dst), src, 2 * C::NK * 128, b3_full[s]);
+                    if (C::NKX > 0)
+                        bulk_g2s(smem_u32(dst + 2 * (C::NK + C::NKY) * 128), src + 2 * (C::NK + C::NKY) * 128, 2 * C::NKX * 128, b3_full[s]);
                 }
+            };
+            load_b1(0);
+            for (int t = 0; t < ntile; ++t) {
+                if (t + 1 < ntile) load_b1(t + 1);
+                load_b3(t);
             }
         }
         __syncwarp();
     } else if (warp == NEPI + 1) {
-        // ===== MMA issuer: the warp stays converged and one elected lane issues, so every operand is warp-uniform and
-        // UTCHMMA reads it from uniform registers (a divergent `if (lane == 0)` block compiles to a per-lane serialisation
-        // loop around each MMA: ~95 cycles per instruction instead of the 32/64-cycle hardware floor, profiles/) =====
-        {
-            const uint32_t el = elect_one();
-            const uint32_t idesc = make_idesc(TM, TN), idesc2 = make_idesc(TM, 2 * TN);
-            // Descriptors are precomputed: per MMA only a constant (compile-time, loops are unrolled) is added.  The issuing
-            // thread runs alone, so every dependent integer instruction would otherwise cost its full latency per MMA.
-            const uint32_t aBase = tmem_base + COL_A;                  // tmem_base was broadcast with a shuffle: uniform
-            uint64_t bstage[NOPS];
+        // ===== MMA issuer: the warp stays converged and one elected lane issues (warp-uniform operands come from uniform
+        // registers; a divergent `if (lane == 0)` block compiles to a per-lane serialisation loop around each MMA) =====
+        const uint32_t el = elect_one();
+        // wait for the A images (epilogue warps build them; named barrier 2 = epilogue warps + this warp)
+        asm volatile("bar.sync 2, %0;" ::"n"((NEPI + 1) * 32) : "memory");
+        tc_fence_after();
+        const uint64_t adesc = make_desc(smem_u32(sA), 1, 64, 2);
+        uint64_t b1desc[NB1];
 #pragma unroll
-            for (int i = 0; i < NOPS; ++i) bstage[i] = make_desc(smem_u32(sStage + (size_t)i * STAGE_BYTES), 1, 64, 2);
-            for (int w = 0; w < nitem; ++w) {
-                const int s = w % NOPS, sa = w & 1;
-                const bool dom = w < st.ntile_dom;
-                mbar_wait(op_full[s], (w / NOPS) & 1);
-                mbar_wait(rec_full[w & 3], (w >> 2) & 1);                     // records too: acc_full then covers them for the epilogue
-                if (w >= 2) mbar_wait(acc_free[sa], ((w >> 1) - 1) & 1);      // epilogue of item w-2 drained the TMEM stage
+        for (int i = 0; i < NB1; ++i) b1desc[i] = make_desc(smem_u32(sB1 + (size_t)i * B1_SLOT), 1, 64, 2);
+        const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
+        const uint32_t idS_dom = make_idesc(TM, NS), idS_bdy = make_idesc(TM, PDE ? 128 : 64);
+        const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
+        int i1 = 0;
+        auto stage1 = [&](int t) {
+            const uint32_t accS = tmem_base + (uint32_t)(t & 1) * NS;
+            const uint32_t idesc = (t < ndom) ? idS_dom : idS_bdy;
+            if (el) TC_STAMP(4 + 4 * t);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb, ++i1) {
+                const int s = i1 % NB1;
+                mbar_wait(b1_full[s], (i1 / NB1) & 1);
                 tc_fence_after();
-                if (el) TC_STAMP(4 + 4 * w);
-                uint64_t bb = bstage[0];
+                uint64_t bb = b1desc[0];
 #pragma unroll
-                for (int i = 1; i < NOPS; ++i) bb = (s == i) ? bstage[i] : bb;
-                // K block kb of the stage: [C rows 0..63 | Croll rows 64..127], 128-byte rows
-                const uint32_t acc = tmem_base + (uint32_t)sa * ACC_STRIDE;
-                const uint32_t idm = dom ? idesc2 : idesc;              // domain tiles: one N = 128 MMA writes d1 | d2
+                for (int i = 1; i < NB1; ++i) bb = (s == i) ? b1desc[i] : bb;
                 if (el) {
-                // main contractions over k-steps {0, 2, 3, ...}: low halves first (tiny terms), then the high halves
 #pragma unroll
-                for (int half = 1; half >= 0; --half) {
+                    for (int half = 1; half >= 0; --half) {          // low halves first (tiny terms), then the high halves
 #pragma unroll
-                    for (int step = 0; step < NSTEP; ++step) {
-                        if (step == 1) continue;
-                        const uint64_t bd = bb + (uint64_t)((((step >> 2) * (2 * B_BLK)) + (step & 3) * 32) >> 4);
-                        umma_f16_ts(acc, aBase + (uint32_t)(half * 64 + step * 8), bd, idm, (half == 1 && step == 0) ? 0u : 1u);
-                    }
-                }
-                if (dom) {
-                    // e_y = sum_m x_{I_m} y_{I_m+1}: A[step 0] x C[step 1]
-                    const uint64_t bd1 = bb + (uint64_t)(32 >> 4);
-                    umma_f16_ts(acc + 128, aBase + 64u, bd1, idesc, 0);
-                    umma_f16_ts(acc + 128, aBase, bd1, idesc, 1);
-                }
-                umma_commit(op_empty[s]);                                     // operand stage reusable
-                umma_commit(acc_full[sa]);                                    // accumulators ready
-                TC_STAMP(5 + 4 * w);
-                }
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===== epilogue: thread <-> (point row, 16 of the tile's 64 centres) =====
-        const int r = (warp & 3) * 32 + lane;
-        const int cg = warp >> 2;                                    // centres [16 cg, 16 cg + 16) of each tile
-        const XF xf = xfeat[r];
-        const float a = (float)gp.a, a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
-        const float m2inv = (float)(-2.0 * st.inv_ascale);
-        const float a2_5 = a2 / MC_IDX;
-        double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        bool ready = false;
-        for (int w = 0; w < nitem; ++w) {
-            const int s = w & 1;
-            const int t = PDE ? (w >> 1) : w;
-            const bool kindb = PDE && (w & 1);
-            const bool dom = t < st.ntile_dom;
-            const int q = w & 3;
-            // records of item w landed before the copy of item w+... ; they were complete before its MMAs were issued, so
-            // acc_full covers them.  The next item's barrier was probed while computing (see the PDE kernel).
-            if (!ready) mbar_wait(acc_full[s], (w >> 1) & 1);
-            tc_fence_after();
-            if (tid == 0) TC_STAMP(6 + 4 * w);
-            const uint8_t* stage = sRec + (size_t)q * REC_BYTES;
-            const uint32_t acc = tmem_base + (PDE ? (kindb ? 256u : 0u) : (uint32_t)s * ACC_STRIDE) + lane_addr + cg * 16;
-            float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
-            if (!kindb) {
-                constexpr int CH = PDE ? 8 : 16;                      // centres per TMEM load batch (register budget)
-#pragma unroll
-                for (int cb = 0; cb < 16; cb += CH) {
-                float v1[CH], v2[CH], ve[CH], vq[PDE ? CH : 1];
-                if (PDE) {
-                    tmem_ld8(acc + cb, v1);
-                    if (dom) { tmem_ld8(acc + 64 + cb, v2); tmem_ld8(acc + 128 + cb, ve); tmem_ld8(acc + 192 + cb, vq); }
-                } else {
-                    tmem_ld16(acc, v1);
-                    if (dom) { tmem_ld16(acc + 64, v2); tmem_ld16(acc + 128, ve); }
-                }
-                tmem_ld_wait();
-                ready = (w + 1 < nitem) ? mbar_try_wait(acc_full[(w + 1) & 1], ((w + 1) >> 1) & 1) : true;
-                const float* rec = (const float*)stage + (cg * 16 + cb) * NFA;
-#pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    const float* c = rec + i * NFA;
-                    const float4 f0 = *(const float4*)(c);            // U0 U1 U2 Y0
-                    const float k = ex2f(v1[i]);
-                    pu = fmaf(k, fmaf(f0.z, xf.sx, fmaf(f0.y, xf.xt, f0.x)), pu);
-                    float ky = 0.f, h = 0.f;
-                    float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (dom) {
-                        f1 = *(const float4*)(c + 4);                 // Y1 Y2 Y3 Y4
-                        ky = ex2f(v2[i]);
-                        h = fmaf(f1.y, ve[i], fmaf(f1.x, xf.P2, f0.w));
-                        pu = fmaf(ky, h, pu);
-                    }
-                    if (CLASS >= 1) {
-                        const float4 f2 = *(const float4*)(c + 8);    // G0 Gsx Gxt Gsxxt
-                        const float4 f3 = *(const float4*)(c + 12);   // Gsx2 syr y0 T2
-                        const float g = fmaf(f3.x, xf.sx2, fmaf(f2.w, xf.sxxt, fmaf(f2.z, xf.xt, fmaf(f2.y, xf.sx, f2.x))));
-                        pg = fmaf(k, g, pg);
-                        if (dom) {
-                            const float Sy = xf.sx - f3.y;
-                            pg = fmaf(ky, fmaf(-a * Sy, h, fmaf(f1.w, xf.P1, f1.z)), pg);
-                        }
-                        if (PDE) {
-                            const float4 f4 = *(const float4*)(c + 16);   // T0 Txt Tsx Txt2
-                            const float2 f5 = *(const float2*)(c + 20);   // Tsxxt Lw
-                            const float tt = fmaf(f5.x, xf.sxxt, fmaf(f4.w, xf.xt2, fmaf(f4.z, xf.sx, fmaf(f4.y, xf.xt, f4.x))));
-                            pt = fmaf(k, tt, pt);
-                            if (dom) {
-                                pt = fmaf(ky * h, -a * (xf.xt - f3.z), pt);
-                                const float q2 = fmaf(m2inv, vq[i], xf.R2 + f3.w);
-                                pl = fmaf(k * f5.y, fmaf(fmaf(a4, q2, -14.f * a3), q2, 35.f * a2), pl);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (kb * 4 + ks < nstep) {
+                                const uint64_t ad = adesc + (uint64_t)((((half * KB + kb) * A_BLK) + ks * 32) >> 4);
+                                umma_f16(accS, ad, bb + (uint64_t)((ks * 32) >> 4), idesc, (kb == 0 && half == 1 && ks == 0) ? 0u : 1u);
                             }
                         }
                     }
-                }
-                }
-            } else {
-                float v3[16], vx[16];
-                tmem_ld16(acc, v3);
-                tmem_ld16(acc + 64, vx);
-                tmem_ld_wait();
-                const float* rec = (const float*)stage + (cg * 16) * NFB;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float* c = rec + i * NFB;
-                    const float4 f0 = *(const float4*)(c);            // X0 X1 X2 X3
-                    const float2 f1 = *(const float2*)(c + 4);        // X4 Q2
-                    const float kx = ex2f(v3[i]);
-                    const float n2 = fmaf(m2inv, vx[i], xf.R2 + f1.y);
-                    const float MHx = fmaf(a2_5, n2, -a);
-                    const float p1 = fmaf(f0.z, xf.sxr, fmaf(f0.y, xf.x0, f0.x));
-                    pl = fmaf(kx, fmaf(MHx, p1, fmaf(f1.x, xf.R1, f0.w)), pl);
-                }
-            }
-            U += (double)pu;
-            if (CLASS >= 1) G += (double)pg;
-            if (PDE) { L += (double)pl; T += (double)pt; }
-            tc_fence_before();
-            __syncwarp();
-            if (tid == 0) TC_STAMP(7 + 4 * w);
-            if (lane == 0) { mbar_arrive(acc_free[s]); mbar_arrive(rec_free[q]); }
-        }
-        // combine the four centre groups of each point (the A images are dead now: reuse them), apply K_i, write
-        double* xchg = (double*)sA;                                   // [4 groups][128 rows][4]
-        if (cg > 0) { double* p = xchg + ((size_t)cg * TM + r) * 4; p[0] = U; p[1] = G; p[2] = L; p[3] = T; }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (cg == 0) {
-            const long row = row0 + r;
-            if (row < R) {
-#pragma unroll
-                for (int g2 = 1; g2 < 4; ++g2) {
-                    const double* p = xchg + ((size_t)g2 * TM + r) * 4;
-                    U += p[0]; G += p[1]; L += p[2]; T += p[3];
-                }
-                const double ki = Ki[r];
-                const double u = ki * U;
-                if (CLASS == 0) {
-                    out0[row] = (mode == EVAL_TERMINAL) ? gterm[r] - u : u;
-                } else if (CLASS == 1) {
-                    out0[row] = u;
-                    out1[row] = ki * G;
-                } else {
-                    const double g = ki * G, l = ki * L, tt = ki * T;
-                    const double s2 = gp.sig2;
-                    out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;   // GP.py:767-768
-                    if (out1) out1[row] = g;
-                    if (out2) out2[row] = l;
-                    if (out3) out3[row] = tt;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) TC_STAMP(3);
-    if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
-#undef TC_STAMP
-}
-
-
-// ---- PDE-residual kernel: three 128-column item kinds on a 4-slot ring ------------------------------------------------
-// kind 0 (k class,  x - y):       d1 = A x C        (+ e_q = A[step 1] x C[step 1] on domain tiles)
-// kind 1 (ky class, x - roll y):  d2 = A x Croll     + e_y = A[step 0] x Croll[step 0]        (domain tiles only)
-// kind 2 (kx class, roll x - y):  d3 = Aroll x C     + e_x = A[step 1] x C[step 0]
-// Every kind needs 128 TMEM columns, so operands, records and accumulators share one 4-slot ring (slot = item & 3):
-// the MMA warp runs up to three items ahead of the epilogue, which is the binding stage of this mode.
-template <int KB>
-__global__ void __launch_bounds__(NTHREADS, 1)
-eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
-                   double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
-    constexpr int NSTEP = 4 * KB;
-    constexpr uint32_t STAGE_BYTES = KB * B_BLK;                      // one operand image (C or Croll)
-    constexpr uint32_t REC_BYTES = TN * TC_NF0 * 4;
-    constexpr int NSLOT = 4;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw;
-    if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
-    uint8_t* sA = smem;                                               // hi | lo | roll hi | roll lo
-    uint8_t* sStage = sA + 4 * (size_t)KB * A_BLK;
-    uint8_t* sRec = sStage + NSLOT * (size_t)STAGE_BYTES;
-    uint8_t* sMisc = sRec + NSLOT * (size_t)REC_BYTES;
-    XF* xfeat = (XF*)sMisc;
-    double* Ki = (double*)(sMisc + TM * sizeof(XF));
-    double* gterm = Ki + TM;
-    uint64_t* bars = (uint64_t*)(gterm + TM);                         // full[4] acc[4] free[4]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = gp.d;
-    const long row0 = (long)blockIdx.x * TM;
-    long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
-#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
-    if (tid == 0) TC_STAMP(0);
-    uint32_t b_full[NSLOT], b_acc[NSLOT], b_free[NSLOT];
-#pragma unroll
-    for (int q = 0; q < NSLOT; ++q) { b_full[q] = smem_u32(&bars[q]); b_acc[q] = smem_u32(&bars[4 + q]); b_free[q] = smem_u32(&bars[8 + q]); }
-    if (tid == 0) {
-        for (int q = 0; q < NSLOT; ++q) { mbar_init(b_full[q], 1); mbar_init(b_acc[q], 1); mbar_init(b_free[q], NEPI); }
-        fence_barrier_init();
-    }
-    if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
-    tc_fence_before();
-    __syncthreads();                                                  // TMEM base address + barriers visible
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    // A operand stays in shared memory here (SS-mode MMAs run at the same rate, tools/tc_mma_bench.py): all 512 TMEM
-    // columns go to four 128-column accumulator slots, so the MMA warp can run three items ahead of the epilogue.
-    if (warp < NEPI) build_operand_A<true, KB, false>(gp, st, X, R, row0, sA, xfeat, Ki, gterm, 0u, tid, warp, lane, dbg);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) TC_STAMP(2);
-    const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
-    const int nitem = 3 * ndom + 2 * nbdy;
-    // item w -> (tile, kind): domain tiles run kinds 0,1,2; boundary tiles kinds 0,2
-    auto item_of = [&](int w, int& t, int& kind) {
-        if (w < 3 * ndom) { t = w / 3; kind = w - 3 * t; }
-        else { const int v = w - 3 * ndom; t = ndom + (v >> 1); kind = (v & 1) * 2; }
-    };
-    const size_t rec_base = 2 * (size_t)KB * B_BLK + (size_t)TN * (NFA + NFB) * 4;   // rec0 | rec1 after recA | recB
-
-    if (warp == NEPI) {
-        if (lane == 0) {
-            for (int w = 0; w < nitem; ++w) {
-                const int q = w & 3;
-                if (w >= NSLOT) mbar_wait(b_free[q], ((w >> 2) - 1) & 1);     // epilogue of item w-4 released the slot
-                int t, kind; item_of(w, t, kind);
-                const uint8_t* src = st.images + (size_t)t * st.tile_bytes;
-                uint8_t* dst = sStage + (size_t)q * STAGE_BYTES;
-                const uint32_t recbytes = (kind == 0) ? TN * TC_NF0 * 4 : TN * TC_NF1 * 4;
-                mbar_expect_tx(b_full[q], STAGE_BYTES + recbytes);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb)     // global image: per K block [C rows | Croll rows]
-                    bulk_g2s(smem_u32(dst + kb * B_BLK), src + (size_t)kb * 2 * B_BLK + (kind == 1 ? B_BLK : 0), B_BLK, b_full[q]);
-                const uint8_t* rsrc = (kind == 0) ? src + rec_base
-                                    : (kind == 1) ? src + rec_base + TN * TC_NF0 * 4
-                                                  : src + 2 * (size_t)KB * B_BLK + TN * NFA * 4;      // recB
-                bulk_g2s(smem_u32(sRec + (size_t)q * REC_BYTES), rsrc, recbytes, b_full[q]);
-            }
-        }
-        __syncwarp();
-    } else if (warp == NEPI + 1) {
-        {   // converged warp, elected lane issues (see eval_tc_kernel)
-            const uint32_t el = elect_one();
-            const uint32_t idesc = make_idesc(TM, TN);
-            const uint64_t abase = make_desc(smem_u32(sA), 1, 64, 2);   // images hi | lo | roll hi | roll lo, KB blocks each
-            auto aoff = [](int img, int step) { return (uint64_t)((((img * KB) + (step >> 2)) * A_BLK + (step & 3) * 32) >> 4); };
-            uint64_t bstage[NSLOT];
-#pragma unroll
-            for (int i = 0; i < NSLOT; ++i) bstage[i] = make_desc(smem_u32(sStage + (size_t)i * STAGE_BYTES), 1, 64, 2);
-            for (int w = 0; w < nitem; ++w) {
-                const int q = w & 3;
-                int t, kind; item_of(w, t, kind);
-                const bool dom = t < ndom;
-                mbar_wait(b_full[q], (w >> 2) & 1);                     // operands landed; the slot's accumulators were drained before the refill
-                tc_fence_after();
-                if (el && w < 60) TC_STAMP(4 + 4 * w);
-                uint64_t bb = bstage[0];
-#pragma unroll
-                for (int i = 1; i < NSLOT; ++i) bb = (q == i) ? bstage[i] : bb;
-                const uint32_t acc = tmem_base + (uint32_t)q * 128u;
-                const uint64_t aimg = abase + ((kind == 2) ? aoff(2, 0) : 0ull);    // rolled A images for the kx class
-                if (el) {
-#pragma unroll
-                for (int half = 1; half >= 0; --half) {
-#pragma unroll
-                    for (int step = 0; step < NSTEP; ++step) {
-                        if (step == 1) continue;
-                        const uint64_t bd = bb + (uint64_t)((((step >> 2) * B_BLK) + (step & 3) * 32) >> 4);
-                        umma_f16(acc, aimg + aoff(half, step), bd, idesc, (half == 1 && step == 0) ? 0u : 1u);
-                    }
-                }
-                const uint64_t bd0 = bb, bd1 = bb + (uint64_t)(32 >> 4);
-                if (kind == 0) {          // e_q = A[step 1] x C[step 1]
-                    if (dom) { umma_f16(acc + 64, abase + aoff(1, 1), bd1, idesc, 0); umma_f16(acc + 64, abase + aoff(0, 1), bd1, idesc, 1); }
-                } else if (kind == 1) {   // e_y = A[step 0] x Croll[step 0]
-                    umma_f16(acc + 64, abase + aoff(1, 0), bd0, idesc, 0); umma_f16(acc + 64, abase + aoff(0, 0), bd0, idesc, 1);
-                } else {                  // e_x = A[step 1] x C[step 0]
-                    umma_f16(acc + 64, abase + aoff(1, 1), bd0, idesc, 0); umma_f16(acc + 64, abase + aoff(0, 1), bd0, idesc, 1);
-                }
-                umma_commit(b_acc[q]);
-                if (w < 60) TC_STAMP(5 + 4 * w);
+                    umma_commit(b1_empty[s]);                        // operand slot reusable
                 }
                 __syncwarp();
             }
+            if (el) umma_commit(s_full[t & 1]);                      // accumulators ready for the epilogue warps
+            __syncwarp();
+        };
+        auto stage2 = [&](int t) {
+            const int s = t & 1;
+            const bool dom = t < ndom;
+            mbar_wait(p_ready[s], (t >> 1) & 1);                     // P(t) written over S(t) by all epilogue warps
+            mbar_wait(b3_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t pbase = tmem_base + (uint32_t)s * NS;
+            const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT) >> 4);
+            if (el) {
+                auto cls_mma = [&](uint32_t pcol, uint32_t tcol, uint32_t off_hi, uint32_t nrows, uint32_t idesc, bool first) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t chi = b3 + (uint64_t)((off_hi + ks * 32) >> 4);
+                        const uint64_t clo = b3 + (uint64_t)((off_hi + nrows * 128 + ks * 32) >> 4);
+                        const uint32_t phi = pbase + pcol + (uint32_t)ks * 16u, plo = phi + 8u;
+                        umma_f16_ts(tmem_base + COL_T + tcol, phi, chi, idesc, (first && ks == 0) ? 0u : 1u);
+                        umma_f16_ts(tmem_base + COL_T + tcol, phi, clo, idesc, 1u);
+                        umma_f16_ts(tmem_base + COL_T + tcol, plo, chi, idesc, 1u);
+                    }
+                };
+                cls_mma(SC_K, TC_K, 0u, C::NK, idK, t == 0);
+                if (dom) cls_mma(SC_KY, TC_KY, 2u * C::NK * 128u, C::NKY, idKY, t == 0);
+                if (C::NKX > 0) cls_mma(SC_KX, TC_KX, 2u * (C::NK + C::NKY) * 128u, C::NKX, idKX, t == 0);
+                umma_commit(b3_empty[s]);
+                TC_STAMP(5 + 4 * t);
+            }
+            __syncwarp();
+        };
+        stage1(0);
+        for (int t = 0; t < ntile; ++t) {
+            if (t + 1 < ntile) stage1(t + 1);
+            stage2(t);
         }
+        if (el) umma_commit(t_full);
         __syncwarp();
     } else {
-        const int r = (warp & 3) * 32 + lane;
-        const int cg = warp >> 2;
-        const XF xf = xfeat[r];
-        const float a = (float)gp.a, a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
-        const float m2inv = (float)(-2.0 * st.inv_ascale);
-        const float a2_5 = a2 / MC_IDX;
-        double U = 0.0, G = 0.0, L = 0.0, T = 0.0;
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        // Barrier operations are long-latency: the next item's "accumulators ready" barrier is probed (non-blocking) while the
-        // current item is being computed, so a warp pays a blocking wait only when the MMA warp is genuinely behind.  The
-        // coefficient records of item w were complete before its MMAs were issued, so b_acc also covers them.
-        bool ready = false;
-        int t = 0, kind = 0;                                          // item 0 = (tile 0, kind 0)
-        for (int w = 0; w < nitem; ++w) {
-            const int q = w & 3;
-            const bool dom = t < ndom;
-            if (!ready) mbar_wait(b_acc[q], (w >> 2) & 1);
-            tc_fence_after();
-            if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
-            const uint32_t acc = tmem_base + (uint32_t)q * 128u + lane_addr + cg * 16;
-            float pu = 0.f, pg = 0.f, pl = 0.f, pt = 0.f;
-            float v1[16], ve[16];
-            tmem_ld16(acc, v1);
-            if (kind != 0 || dom) tmem_ld16(acc + 64, ve);
-            tmem_ld_wait();
-            ready = (w + 1 < nitem) ? mbar_try_wait(b_acc[(w + 1) & 3], ((w + 1) >> 2) & 1) : true;
-            if (kind == 0) {
-                const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * TC_NF0;
+        // ===== epilogue warps =====
+        // --- prologue: A images a' x = hi + lo (f16, 128 B swizzle), row sums.  Two rows per warp pass (16 lanes x 8 columns).
+        {
+            const double ascale = gp.a * 1.4426950408889634;           // a log2(e): S = log2 of exp(a x.y)
+            const int hl = lane & 15, sub = lane >> 4;
+            const int c0 = hl * 8;
+            const bool active = c0 < KB * KBLK;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float* c = rec + i * TC_NF0;
-                    const float4 f0 = *(const float4*)(c);            // U0 U1 U2 Gsx2
-                    const float4 f1 = *(const float4*)(c + 4);        // G0 Gsx Gxt Gsxxt
-                    const float4 f2 = *(const float4*)(c + 8);        // T0 Txt Tsx Txt2
-                    const float4 f3 = *(const float4*)(c + 12);       // Tsxxt T2 Lw -
-                    const float k = ex2f(v1[i]);
-                    pu = fmaf(k, fmaf(f0.z, xf.sx, fmaf(f0.y, xf.xt, f0.x)), pu);
-                    pg = fmaf(k, fmaf(f0.w, xf.sx2, fmaf(f1.w, xf.sxxt, fmaf(f1.z, xf.xt, fmaf(f1.y, xf.sx, f1.x)))), pg);
-                    pt = fmaf(k, fmaf(f3.x, xf.sxxt, fmaf(f2.w, xf.xt2, fmaf(f2.z, xf.sx, fmaf(f2.y, xf.xt, f2.x)))), pt);
-                    if (dom) {
-                        const float q2 = fmaf(m2inv, ve[i], xf.R2 + f3.y);
-                        pl = fmaf(k * f3.z, fmaf(fmaf(a4, q2, -14.f * a3), q2, 35.f * a2), pl);
+            for (int pass = 0; pass < 2; ++pass) {
+                double v[2][8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = warp * 8 + (pass * 2 + i) * 2 + sub;
+                    const long row = row0 + r;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c0 + e;
+                        v[i][e] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
                     }
                 }
-            } else if (kind == 1) {
-                const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * TC_NF1;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float* c = rec + i * TC_NF1;
-                    const float4 f0 = *(const float4*)(c);            // Y0 Y1 Y2 Y3
-                    const float4 f1 = *(const float4*)(c + 4);        // Y4 syr y0 -
-                    const float ky = ex2f(v1[i]);
-                    const float h = fmaf(f0.z, ve[i], fmaf(f0.y, xf.P2, f0.x));
-                    pu = fmaf(ky, h, pu);
-                    pg = fmaf(ky, fmaf(-a * (xf.sx - f1.y), h, fmaf(f1.x, xf.P1, f0.w)), pg);
-                    pt = fmaf(ky * h, -a * (xf.xt - f1.z), pt);
-                }
-            } else {
-                const float* rec = (const float*)(sRec + (size_t)q * REC_BYTES) + (cg * 16) * NFB;
+                for (int i = 0; i < 2; ++i) {
+                    const int r = warp * 8 + (pass * 2 + i) * 2 + sub;
+                    double nx = 0.0, sx = 0.0;
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float* c = rec + i * NFB;
-                    const float4 f0 = *(const float4*)(c);            // X0 X1 X2 X3
-                    const float2 f1 = *(const float2*)(c + 4);        // X4 Q2
-                    const float kx = ex2f(v1[i]);
-                    const float n2 = fmaf(m2inv, ve[i], xf.R2 + f1.y);
-                    const float MHx = fmaf(a2_5, n2, -a);
-                    const float p1 = fmaf(f0.z, xf.sxr, fmaf(f0.y, xf.x0, f0.x));
-                    pl = fmaf(kx, fmaf(MHx, p1, fmaf(f1.x, xf.R1, f0.w)), pl);
+                    for (int e = 0; e < 8; e += 2) {
+                        float sv[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int c = c0 + e + q;
+                            const double val = v[i][e + q];
+                            nx = fma(val, val, nx);
+                            if (c < d) sx += val;
+                            sv[q] = (c == D) ? 1.0f : (float)(ascale * val);   // column D: exponent shift (B holds TC_P_SHIFT)
+                        }
+                        // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
+                        const __half2 h = __floats2half2_rn(sv[0], sv[1]);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(sv[0] - hf.x, sv[1] - hf.y);
+                        hi[e >> 1] = *(const uint32_t*)&h;
+                        lo[e >> 1] = *(const uint32_t*)&l;
+                    }
+                    if (active) {
+                        const uint32_t off = (uint32_t)(c0 / KBLK) * A_BLK + (uint32_t)r * 128u + (uint32_t)(((((c0 % KBLK) >> 3) ^ (r & 7)) & 7) << 4);
+                        *(uint4*)(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *(uint4*)(sA + (size_t)KB * A_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
+                    if (hl == 0) { Ki[r] = exp(-0.5 * gp.a * nx); sxs[r] = sx; }
                 }
             }
-            U += (double)pu; G += (double)pg; L += (double)pl; T += (double)pt;
+            fence_proxy_async();                                     // generic-proxy smem writes -> visible to the MMA (async proxy)
+            if (tid == 0) TC_STAMP(1);
+            asm volatile("bar.sync 2, %0;" ::"n"((NEPI + 1) * 32) : "memory");
+            if (tid == 0) TC_STAMP(2);
+        }
+        // --- main loop: S -> P in place.  thread <-> (point row r, centres [16 cg, 16 cg + 16) of the tile)
+        const int r = (warp & 3) * 32 + lane;
+        const int cg = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        constexpr int NCLS = PDE ? 3 : 2;
+        for (int t = 0; t < ntile; ++t) {
+            const int s = t & 1;
+            const bool dom = t < ndom;
+            mbar_wait(s_full[s], (t >> 1) & 1);
+            tc_fence_after();
+            if (tid == 0) TC_STAMP(6 + 4 * t);
+            const uint32_t base = tmem_base + lane_addr + (uint32_t)s * NS + (uint32_t)cg * 16u;
+            // boundary tiles have no ky class: PDE columns [k | kx], else [k]
+            const int ncls = dom ? NCLS : NCLS - 1;
+            float v[NCLS][16];
+#pragma unroll
+            for (int c = 0; c < NCLS; ++c) if (c < ncls) tmem_ld16(base + (uint32_t)c * 64u, v[c]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < NCLS; ++c) {
+                if (c < ncls) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float p0 = ex2f(v[c][2 * i]), p1 = ex2f(v[c][2 * i + 1]);
+                        hi[i] = pack_f16x2_sat(p0, p1);
+                        const float2 hf = __half22float2(*(const __half2*)&hi[i]);
+                        lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                    }
+                    tmem_st8(base + (uint32_t)c * 64u, hi);
+                    tmem_st8(base + (uint32_t)c * 64u + 8u, lo);
+                }
+            }
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (tid == 0 && w < 60) TC_STAMP(7 + 4 * w);
-            if (lane == 0) mbar_arrive(b_free[q]);
-            // next item: domain tiles run kinds 0,1,2; boundary tiles kinds 0,2
-            if (kind == 2) { kind = 0; ++t; } else kind = (t < ndom) ? kind + 1 : 2;
+            if (tid == 0) TC_STAMP(7 + 4 * t);
+            if (lane == 0) mbar_arrive(p_ready[s]);
         }
-        double* xchg = (double*)sA;                                   // the A images are dead now
-        if (cg > 0) { double* p = xchg + ((size_t)cg * TM + r) * 4; p[0] = U; p[1] = G; p[2] = L; p[3] = T; }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        // --- final contraction: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
+        mbar_wait(t_full, 0);
+        tc_fence_after();
+        double* feat = (double*)sA;                                  // the A images are dead: [128][TF_COUNT] features
+        double* xchg = feat + TM * TF_COUNT;                         // [3][128][4] partial sums of column groups 1..3
         if (cg == 0) {
             const long row = row0 + r;
-            if (row < R) {
+            const bool ok = row < R;
+            const double* xr = X + row * (long)D;
+            double* F = feat + r * TF_COUNT;
+            const double sx = sxs[r];
+            const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+            double P2 = 0.0, R2 = 0.0;
 #pragma unroll
-                for (int g2 = 1; g2 < 4; ++g2) {
-                    const double* p = xchg + ((size_t)g2 * TM + r) * 4;
-                    U += p[0]; G += p[1]; L += p[2]; T += p[3];
+            for (int m = 0; m < MC_IDX; ++m) {
+                const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+            }
+            F[TF_ONE] = 1.0; F[TF_SX] = sx; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+        {
+            constexpr int NPER = NT / 4;                             // T columns per column group
+            const double* F = feat + r * TF_COUNT;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const bool have_ky = ndom > 0;
+#pragma unroll
+            for (int c0 = 0; c0 < NPER; c0 += 4) {
+                const int col0 = cg * NPER + c0;
+                float tv[4];
+                tmem_ld4(tmem_base + lane_addr + COL_T + (uint32_t)col0, tv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int col = col0 + i;
+                    const TcColDesc dsc = st.desc[col];
+                    const bool skip = dsc.out == TO_PAD || (!have_ky && col >= TC_KY && col < TC_KX);
+                    if (!skip) acc[dsc.out & 3] = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, acc[dsc.out & 3]);
                 }
-                const double ki = Ki[r];
-                const double u = ki * U, g = ki * G, l = ki * L, tt = ki * T;
-                const double s2 = gp.sig2;
-                out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;       // GP.py:767-768
-                if (out1) out1[row] = g;
-                if (out2) out2[row] = l;
-                if (out3) out3[row] = tt;
+            }
+            if (cg > 0) {
+                double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
+                p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            if (cg == 0) {
+                const long row = row0 + r;
+                if (row < R) {
+#pragma unroll
+                    for (int g2 = 1; g2 < 4; ++g2) {
+                        const double* p = xchg + ((size_t)(g2 - 1) * TM + r) * 4;
+                        acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+                    }
+                    const double ki = Ki[r];
+                    const double u = ki * acc[TO_U];
+                    if (CLASS == TC_U) {
+                        const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));          // equations.py:259
+                        out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
+                    } else if (CLASS == TC_UG) {
+                        out0[row] = u;
+                        out1[row] = ki * acc[TO_G];
+                    } else {
+                        const double g = ki * acc[TO_G], l = ki * acc[TO_L], tt = ki * acc[TO_T];
+                        const double s2 = gp.sig2;
+                        out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;   // GP.py:767-768
+                        if (out1) out1[row] = g;
+                        if (out2) out2[row] = l;
+                        if (out3) out3[row] = tt;
+                    }
+                }
             }
         }
     }
@@ -977,35 +561,21 @@ eval_tc_pde_kernel(GpView gp, TcState st, const double* __restrict__ X, long R,
     if (tid == 0) TC_STAMP(3);
     if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
 #undef TC_STAMP
-}
-
-template <int KB>
-static int launch_pde(const GpView& gp, const TcState& st, const double* X, long R,
-                      double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
-    static bool configured = false;
-    const size_t smem = 1024 + 4 * (size_t)KB * A_BLK + 4 * (size_t)(KB * B_BLK) + 4 * (size_t)(TN * TC_NF0 * 4)
-                        + TM * sizeof(XF) + 2 * TM * 8 + 256;
-    if (!configured) {
-        SC_CUDA(cudaFuncSetAttribute(eval_tc_pde_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    eval_tc_pde_kernel<KB><<<(unsigned)cdiv(R, TM), NTHREADS, smem, stream>>>(gp, st, X, R, o0, o1, o2, o3);
-    SC_LAUNCH_CHECK();
-    return OK;
 }
 
 template <int CLASS, int KB>
 static size_t smem_bytes() {
-    constexpr int NA = (CLASS == 2) ? 4 : 2;
-    constexpr int NOPS = (CLASS == 2) ? 2 : 3;
-    return 1024 + (size_t)NA * KB * A_BLK + NOPS * (size_t)(2 * KB * B_BLK) + 4 * (size_t)(TN * NFA * 4) + TM * sizeof(XF) + 2 * TM * 8 + 256;
+    using C = Cfg<CLASS>;
+    constexpr int NT = C::NK + C::NKY + C::NKX;
+    return 2 * (size_t)KB * A_BLK + C::NB1 * (size_t)(C::NS * 128) + 2 * (size_t)(2 * NT * 128) + 2 * TM * 8 + 17 * 8 + 16;
 }
 
 template <int CLASS, int KB>
-static int launch(const GpView& gp, const TcState& st, const double* X, long R, int mode,
+static int launch(const GpView& gp, const TcDev& st, const double* X, long R, int mode,
                   double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
     static bool configured = false;
     const size_t smem = smem_bytes<CLASS, KB>();
+    static_assert(2 * KB * A_BLK >= (int)(TM * TF_COUNT * 8 + 3 * TM * 4 * 8), "feature / exchange buffers alias the A images");
     if (!configured) {
         SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -1019,39 +589,109 @@ static int launch(const GpView& gp, const TcState& st, const double* X, long R, 
 
 // ---- host API --------------------------------------------------------------------------------------------------
 
-// k-steps 0 and 1 hold the index-set columns and their successors; the other d + 1 - 5 columns need <= 96 slots
-int tc_supported(const GpView& gp) { return gp.D - MC_IDX <= 2 * tc::KBLK - 32; }
+// the contraction axis (d + 1 coordinates + the exponent-shift column) must fit two 64-wide K blocks
+int tc_supported(const GpView& gp) { return gp.D + 1 <= 2 * tc::KBLK; }
+
+static void add_col(TcState* st, int cls, int& n, int kern, int out, int f1, int f2, int coef, int m = 0, int nn = 0) {
+    TcColSpec& s = st->spec[cls][n++];
+    s.kern = (unsigned char)kern; s.out = (unsigned char)out; s.f1 = (unsigned char)f1; s.f2 = (unsigned char)f2;
+    s.coef = (unsigned char)coef; s.m = (unsigned char)m; s.n = (unsigned char)nn; s.pad = 0;
+}
+
+// column table: same order as tests/tc_expansion_ref.py::columns, each kernel class padded to its UMMA N
+static void build_columns(TcState* st) {
+    static const int NCOL[3][3] = {{16, 16, 0}, {16, 32, 0}, {48, 48, 32}};
+    const int H[7] = {TF_ONE, TF_P2, TF_XI, TF_XI + 1, TF_XI + 2, TF_XI + 3, TF_XI + 4};
+    const int MX[7] = {TF_ONE, TF_R2, TF_XR, TF_XR + 1, TF_XR + 2, TF_XR + 3, TF_XR + 4};
+    const int G3[3] = {TF_ONE, TF_X0, TF_SXR};
+    for (int cls = 0; cls < 3; ++cls) {
+        for (int c = 0; c < TC_MAXCOL; ++c) { TcColSpec z{}; z.out = TO_PAD; z.coef = TCF_ZERO; st->spec[cls][c] = z; }
+        int n = 0;
+        // k class
+        add_col(st, cls, n, TK_K, TO_U, TF_ONE, TF_ONE, TCF_U0); add_col(st, cls, n, TK_K, TO_U, TF_XT, TF_ONE, TCF_U1);
+        add_col(st, cls, n, TK_K, TO_U, TF_SX, TF_ONE, TCF_U2);
+        if (cls >= TC_UG) {
+            add_col(st, cls, n, TK_K, TO_G, TF_ONE, TF_ONE, TCF_G0); add_col(st, cls, n, TK_K, TO_G, TF_SX, TF_ONE, TCF_GSX);
+            add_col(st, cls, n, TK_K, TO_G, TF_XT, TF_ONE, TCF_GXT); add_col(st, cls, n, TK_K, TO_G, TF_SX, TF_XT, TCF_GSXXT);
+            add_col(st, cls, n, TK_K, TO_G, TF_SX, TF_SX, TCF_GSX2);
+        }
+        if (cls == TC_PDE) {
+            add_col(st, cls, n, TK_K, TO_T, TF_ONE, TF_ONE, TCF_T0); add_col(st, cls, n, TK_K, TO_T, TF_XT, TF_ONE, TCF_TXT);
+            add_col(st, cls, n, TK_K, TO_T, TF_SX, TF_ONE, TCF_TSX); add_col(st, cls, n, TK_K, TO_T, TF_XT, TF_XT, TCF_TXT2);
+            add_col(st, cls, n, TK_K, TO_T, TF_SX, TF_XT, TCF_TSXXT);
+            add_col(st, cls, n, TK_K, TO_L, TF_ONE, TF_ONE, TCF_L1); add_col(st, cls, n, TK_K, TO_L, TF_R2, TF_ONE, TCF_LR2);
+            add_col(st, cls, n, TK_K, TO_L, TF_R2, TF_R2, TCF_LR22);
+            for (int m = 0; m < MC_IDX; ++m) add_col(st, cls, n, TK_K, TO_L, TF_XR + m, TF_ONE, TCF_LX, m);
+            for (int m = 0; m < MC_IDX; ++m) add_col(st, cls, n, TK_K, TO_L, TF_XR + m, TF_R2, TCF_LXR2, m);
+            for (int m = 0; m < MC_IDX; ++m)
+                for (int q = m; q < MC_IDX; ++q) add_col(st, cls, n, TK_K, TO_L, TF_XR + m, TF_XR + q, TCF_LXX, m, q);
+        }
+        st->ncol[cls][TK_K] = NCOL[cls][TK_K];
+        n = NCOL[cls][TK_K];
+        // ky class
+        for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_U, H[i], TF_ONE, TCF_H, i);
+        if (cls >= TC_UG) {
+            for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_G, H[i], TF_SX, TCF_HSX, i);
+            for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_G, H[i], TF_ONE, TCF_HG, i);
+        }
+        if (cls == TC_PDE) {
+            for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_T, H[i], TF_XT, TCF_HXT, i);
+            for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_T, H[i], TF_ONE, TCF_HT, i);
+        }
+        st->ncol[cls][TK_KY] = NCOL[cls][TK_KY];
+        n = NCOL[cls][TK_K] + NCOL[cls][TK_KY];
+        // kx class
+        if (cls == TC_PDE)
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 3; ++j) add_col(st, cls, n, TK_KX, TO_L, MX[i], G3[j], TCF_MX, i, j);
+        st->ncol[cls][TK_KX] = NCOL[cls][TK_KX];
+    }
+}
 
 size_t tc_image_bytes(const GpView& gp, TcState* st) {
-    const int rest = gp.D - MC_IDX;
-    st->KB = (32 + rest + tc::KBLK - 1) / tc::KBLK;
+    st->nstep = (gp.D + 1 + 15) / 16;
+    st->KB = (st->nstep + 3) / 4;
     st->ntile_dom = gp.NdPad / tc::TN;
     st->ntile_bdy = gp.NbPad / tc::TN;
-    st->tile_bytes = 2 * (size_t)st->KB * tc::B_BLK + (size_t)tc::TN * (tc::NFA + tc::NFB + TC_NF0 + TC_NF1) * 4;
-    st->inv_ascale = 1.0 / (gp.a * 1.4426950408889634);
-    for (int c = 0; c < 128; ++c) st->perm[c] = -1;
-    bool in_set[1024] = {false};
-    for (int m = 0; m < MC_IDX; ++m) { st->perm[m] = (short)gp.I[m]; st->perm[16 + m] = (short)(gp.I[m] + 1); in_set[gp.I[m]] = true; }
-    int slot = 32;
-    for (int c = 0; c < gp.D && slot < 128; ++c) if (!in_set[c]) st->perm[slot++] = (short)c;
-    for (int c = 0; c < 128; ++c) { st->iperm[c] = 0; st->iperm1[c] = -1; }
-    for (int k = 0; k < 128; ++k) {
-        const int c = st->perm[k];
-        if (c < 0) continue;
-        if (k >= 16 && k < 32) st->iperm1[c] = (short)k; else st->iperm[c] = (short)k;
+    build_columns(st);
+    const int ntile = st->ntile_dom + st->ntile_bdy;
+    const size_t ncentres = (size_t)ntile * tc::TN;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
+    st->b1_tile_bytes = (size_t)st->KB * 3 * tc::TN * 128;
+    st->b1_off = take((size_t)ntile * st->b1_tile_bytes);
+    for (int cls = 0; cls < 3; ++cls) {
+        const int nt = st->ncol[cls][0] + st->ncol[cls][1] + st->ncol[cls][2];
+        st->b3_tile_bytes[cls] = (size_t)2 * nt * 128;
+        st->b3_off[cls] = take((size_t)ntile * st->b3_tile_bytes[cls]);
     }
-    return (size_t)(st->ntile_dom + st->ntile_bdy) * st->tile_bytes + 1024;    // + device copy of the permutation tables
+    for (int cls = 0; cls < 3; ++cls) st->desc_off[cls] = take(TC_MAXCOL * sizeof(TcColDesc));
+    st->spec_off = take(3 * TC_MAXCOL * sizeof(TcColSpec));
+    st->scratch_off = take(3 * ncentres * TC_MAXCOL * sizeof(double) + 3 * TC_MAXCOL * sizeof(unsigned long long));
+    st->total_bytes = off;
+    return off;
 }
 
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
-    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 100 (larger d: FP64 route)");
-    SC_REQUIRE(st.images != nullptr && st.tabs != nullptr, "tc: image buffer is null");
-    short host_tabs[384];
-    for (int i = 0; i < 128; ++i) { host_tabs[i] = st.perm[i]; host_tabs[128 + i] = st.iperm[i]; host_tabs[256 + i] = st.iperm1[i]; }
-    SC_CUDA(cudaMemcpyAsync((void*)st.tabs, host_tabs, sizeof(host_tabs), cudaMemcpyHostToDevice, stream));
-    SC_CUDA(cudaStreamSynchronize(stream));                       // host_tabs is a stack buffer
-    tc::build_images_kernel<<<st.ntile_dom + st.ntile_bdy, 256, 0, stream>>>(gp, st);
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 126 (larger d: FP64 route)");
+    SC_REQUIRE(st.images != nullptr, "tc: image buffer is null");
+    const int ntile = st.ntile_dom + st.ntile_bdy;
+    const int ncentres = ntile * tc::TN;
+    TcColSpec* spec_dev = (TcColSpec*)(st.images + st.spec_off);
+    double* coef = (double*)(st.images + st.scratch_off);
+    unsigned long long* colmax = (unsigned long long*)(coef + 3 * (size_t)ncentres * TC_MAXCOL);
+    SC_CUDA(cudaMemcpyAsync(spec_dev, st.spec, sizeof(st.spec), cudaMemcpyHostToDevice, stream));   // st lives in the handle
+    SC_CUDA(cudaMemsetAsync(colmax, 0, 3 * TC_MAXCOL * sizeof(unsigned long long), stream));
+    tc::coef_kernel<<<dim3(ncentres, 3), TC_MAXCOL, 0, stream>>>(gp, spec_dev, ncentres, coef, colmax);
     SC_LAUNCH_CHECK();
+    tc::b1_image_kernel<<<ntile, 256, 0, stream>>>(gp, st.images + st.b1_off, st.b1_tile_bytes, st.KB);
+    SC_LAUNCH_CHECK();
+    for (int cls = 0; cls < 3; ++cls) {
+        tc::b3_image_kernel<<<ntile, 256, 0, stream>>>(gp, spec_dev, cls, ncentres, coef, colmax, st.images + st.b3_off[cls],
+                                                        st.b3_tile_bytes[cls], st.ncol[cls][0], st.ncol[cls][1], st.ncol[cls][2],
+                                                        (TcColDesc*)(st.images + st.desc_off[cls]));
+        SC_LAUNCH_CHECK();
+    }
     return OK;
 }
 
@@ -1060,57 +700,38 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
-    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route unavailable for this GP (d > 100 or not fitted): use the FP64 route");
-    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 100 (larger d: FP64 route)");
+    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route unavailable for this GP (d > 126 or not fitted): use the FP64 route");
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 126 (larger d: FP64 route)");
     SC_REQUIRE(X && out0, "eval: null pointer");
-    const int KB = st->KB;
-    const int cls = (mode == EVAL_PDE) ? 2 : (mode == EVAL_UG ? 1 : 0);
-    if (cls == 1) SC_REQUIRE(out1 != nullptr, "eval UG: out1 is null");
-    if (KB == 1) {
-        if (cls == 0) return tc::launch<0, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
-        if (cls == 1) return tc::launch<1, 1>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
-        return tc::launch_pde<1>(gp, *st, X, R, out0, out1, out2, out3, stream);
+    const int cls = (mode == EVAL_PDE) ? TC_PDE : (mode == EVAL_UG ? TC_UG : TC_U);
+    if (cls == TC_UG) SC_REQUIRE(out1 != nullptr, "eval UG: out1 is null");
+    tc::TcDev dv;
+    dv.b1 = st->images + st->b1_off;
+    dv.b3 = st->images + st->b3_off[cls];
+    dv.desc = (const TcColDesc*)(st->images + st->desc_off[cls]);
+    dv.b1_tile_bytes = st->b1_tile_bytes;
+    dv.b3_tile_bytes = st->b3_tile_bytes[cls];
+    dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
+    dv.dbg = st->dbg; dv.dbg_block = st->dbg_block;
+    if (st->KB == 1) {
+        if (cls == TC_U) return tc::launch<TC_U, 1>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
+        if (cls == TC_UG) return tc::launch<TC_UG, 1>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
+        return tc::launch<TC_PDE, 1>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
     }
-    if (cls == 0) return tc::launch<0, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
-    if (cls == 1) return tc::launch<1, 2>(gp, *st, X, R, mode, out0, out1, out2, out3, stream);
-    return tc::launch_pde<2>(gp, *st, X, R, out0, out1, out2, out3, stream);
+    if (cls == TC_U) return tc::launch<TC_U, 2>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
+    if (cls == TC_UG) return tc::launch<TC_UG, 2>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
+    return tc::launch<TC_PDE, 2>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
 }
 
-// timeline of one CTA: stamps[0] entry, [1] operand scatter done, [2] prologue done, [3] exit,
-// item w: [4+4w] MMA issue start, [5+4w] MMA issue end, [6+4w] epilogue start, [7+4w] epilogue end   (SM clock cycles)
+// timeline of one CTA: stamps[0] entry, [1] A images built, [2] prologue done, [3] exit,
+// tile t: [4+4t] stage-1 issue start, [5+4t] stage-2 issue end, [6+4t] epilogue start, [7+4t] epilogue end   (SM clock cycles)
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream) {
-    TcState dbgst = st;
+    static TcState dbgst;                          // TcState is large: keep the debug copy off the stack
+    dbgst = st;
     dbgst.dbg = stamps_dev;
     dbgst.dbg_block = block;
     return launch_eval_tc(gp, &dbgst, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream);
-}
-
-int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream) {
-    SC_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && nchains >= 1 && nchains * N <= 448, "mma_bench: shape");
-    const size_t smem = tc::A_BLK + 256 * 128 + 1024;
-    SC_CUDA(cudaFuncSetAttribute(tc::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::mma_bench_kernel<<<148, 128, smem, stream>>>(N, nchains, ts_mode, iters, cycles_dev);
-    SC_LAUNCH_CHECK();
-    return OK;
-}
-
-int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
-                unsigned layout, unsigned kstep_bytes, cudaStream_t stream) {
-    SC_REQUIRE(K % tc::KBLK == 0 && K >= 64 && K <= 256, "selftest: K must be a multiple of 64");
-    SC_REQUIRE(N % 16 == 0 && N >= 16 && N <= 64, "selftest: N in [16, 64], multiple of 16");
-    const size_t smem = 1024 + (size_t)(K / tc::KBLK) * (tc::A_BLK + (size_t)N * 128);
-    SC_CUDA(cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (layout == 100) {      // A operand in tensor memory (TS mode)
-        SC_CUDA(cudaFuncSetAttribute(tc::selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::selftest_ts_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N);
-        SC_LAUNCH_CHECK();
-        return OK;
-    }
-    tc::selftest_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N, lbo16, sbo16,
-                                                  layout, kstep_bytes);
-    SC_LAUNCH_CHECK();
-    return OK;
 }
 
 }  // namespace scasml

@@ -1,45 +1,56 @@
-// tcgen05 route: per-fit operand images and coefficient records (gp_eval_tc.cu).
+// tcgen05 route: per-fit operand images of the two chained GEMMs (gp_eval_tc.cu).
 #pragma once
 #include "gp.cuh"
 
 namespace scasml {
 
-// FP32 coefficient records of the tcgen05 epilogue.  Every GP weight is pre-multiplied by K_j = exp(-a |y_j|^2 / 2);
-// the closed-form functionals are expanded against the per-point monomials
-// 1, sx, xt, sx^2, sx xt, xt^2 (sx = sum_i x_i, xt = time) and the 5-index sums P1, P2, R1, R2.
-enum TcRecA : int {          // k class (distance x - y) and ky class (x - roll y)
-    RA_U0 = 0, RA_U1 = 1, RA_U2 = 2, RA_Y0 = 3,
-    RA_Y1 = 4, RA_Y2 = 5, RA_Y3 = 6, RA_Y4 = 7,
-    RA_G0 = 8, RA_GSX = 9, RA_GXT = 10, RA_GSXXT = 11,
-    RA_GSX2 = 12, RA_SYR = 13, RA_Y0T = 14, RA_T2 = 15,
-    RA_T0 = 16, RA_TXT = 17, RA_TSX = 18, RA_TXT2 = 19,
-    RA_TSXXT = 20, RA_LW = 21,
+// evaluation classes of the tcgen05 route
+enum TcClass : int { TC_U = 0, TC_UG = 1, TC_PDE = 2 };
+// kernel classes: k (x - y), ky (x - roll y), kx (roll x - y)
+enum TcKernel : int { TK_K = 0, TK_KY = 1, TK_KX = 2 };
+// outputs a coefficient column contributes to
+enum TcOut : int { TO_U = 0, TO_G = 1, TO_L = 2, TO_T = 3, TO_PAD = 255 };
+// per-point features: a column's monomial is F[f1] * F[f2]
+enum TcFeat : int { TF_ONE = 0, TF_SX = 1, TF_XT = 2, TF_X0 = 3, TF_SXR = 4, TF_P2 = 5, TF_R2 = 6, TF_XI = 7, TF_XR = 12, TF_COUNT = 17 };
+// per-centre coefficient formulas (coef_of() in gp_eval_tc.cu; NumPy statement: tests/tc_expansion_ref.py)
+enum TcCoef : int {
+    TCF_U0, TCF_U1, TCF_U2, TCF_G0, TCF_GSX, TCF_GXT, TCF_GSXXT, TCF_GSX2, TCF_T0, TCF_TXT, TCF_TSX, TCF_TXT2, TCF_TSXXT,
+    TCF_L1, TCF_LR2, TCF_LR22, TCF_LX, TCF_LXR2, TCF_LXX, TCF_H, TCF_HSX, TCF_HG, TCF_HXT, TCF_HT, TCF_MX, TCF_ZERO
 };
-enum TcRecB : int { RB_X0 = 0, RB_X1 = 1, RB_X2 = 2, RB_X3 = 3, RB_X4 = 4, RB_Q2 = 5 };   // kx class (roll x - y)
-constexpr int TC_NFA = 24;
-constexpr int TC_NFB = 8;
-// PDE kernel records (three item kinds): kind 0 = k class [U0 U1 U2 Gsx2 | G0 Gsx Gxt Gsxxt | T0 Txt Tsx Txt2 | Tsxxt T2 Lw 0],
-// kind 1 = ky class [Y0 Y1 Y2 Y3 | Y4 syr y0 0], kind 2 = kx class (= TcRecB)
-constexpr int TC_NF0 = 16;
-constexpr int TC_NF1 = 8;
+
+constexpr int TC_MAXCOL = 128;       // accumulator columns of the coefficient GEMM (all kernel classes of one evaluation class)
+constexpr int TC_P_SHIFT = 6;        // P = 2^6 exp(a x.y): keeps the low halves of the f16 split in the normal range
+
+struct TcColSpec {                   // one coefficient column (host-built table, mirrored on the device)
+    unsigned char kern, out, f1, f2, coef, m, n, pad;
+};
+struct TcColDesc {                   // what the kernel's final contraction needs of a column
+    unsigned char f1, f2, out, pad[5];
+    double inv_scale;                // 1 / (column scale 2^s * 2^TC_P_SHIFT)
+};
 
 struct TcState {
-    uint8_t* images = nullptr;   // per centre tile: [C image][Croll image][records A][records B]
-    size_t tile_bytes = 0;
-    int KB = 0;                  // 64-wide K blocks of the permuted contraction axis
+    uint8_t* images = nullptr;       // one allocation: [B1 images][B3 images x 3 classes][column tables][scratch]
+    size_t total_bytes = 0;
+    int KB = 0;                      // 64-wide K blocks of the contraction axis
+    int nstep = 0;                   // k-steps of 16 actually used: ceil((D + 1) / 16) (column D carries the exponent shift)
     int ntile_dom = 0, ntile_bdy = 0;
-    double inv_ascale = 0.0;     // 1 / (a log2 e): un-scales the 5-index accumulators
-    short perm[128];             // permuted K slot -> source coordinate (-1: zero padding)
-    short iperm[128];            // source coordinate -> slot in k-steps {0, 2, 3, ...}
-    short iperm1[128];           // source coordinate -> slot in k-step 1 (successors of the index set), else -1
-    const short* tabs = nullptr; // device copy of [perm | iperm | iperm1] (constant-bank lookups with divergent indices serialise)
-    long long* dbg = nullptr;    // optional timeline buffer (clock64 stamps of CTA dbg_block), see scasml_debug_tc_timeline
+    size_t b1_off = 0, b1_tile_bytes = 0;            // per tile, per K block: rows [C | Crollinv | Croll] x 128 B
+    int ncol[3][3] = {};                             // padded column count per (evaluation class, kernel class)
+    size_t b3_off[3] = {}, b3_tile_bytes[3] = {};    // per tile: [k hi | k lo | ky hi | ky lo | kx hi | kx lo], ncol x 128 B each
+    size_t desc_off[3] = {};                         // TcColDesc[TC_MAXCOL] per evaluation class
+    size_t spec_off = 0;                             // TcColSpec[3][TC_MAXCOL]
+    size_t scratch_off = 0;                          // double [3][ncentres][TC_MAXCOL] + column maxima
+    TcColSpec spec[3][TC_MAXCOL];                    // host copy
+    long long* dbg = nullptr;        // optional timeline buffer (clock64 stamps of CTA dbg_block), see scasml_debug_tc_timeline
     int dbg_block = 0;
 };
 
 int tc_supported(const GpView& gp);
-size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills KB / tile counts / tile_bytes / perm
+size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills the layout fields and the column table
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
+int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
+                   double* out0, double* out1, double* out2, double* out3, cudaStream_t stream);
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);

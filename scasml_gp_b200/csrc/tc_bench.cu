@@ -8,15 +8,204 @@
 //   mode 5  MMA warp alone: SS-mode N = `N` MMAs
 //   mode 6  MMA warp alone: TS-mode N = `N` MMAs (A operand in tensor memory)
 #include "common.cuh"
+#include "gp_tc.cuh"
 #include "tc_ptx.cuh"
 
 namespace scasml {
 namespace tc {
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+constexpr int TM = 128;
+constexpr int A_BLK = TM * 128;      // bytes of one [128 x 64] f16 block
+
+// ---- self test: D[128 x N] = A[128 x K] B[N x K]^T with runtime descriptor fields -------------------------------
+__global__ void __launch_bounds__(128, 1)
+selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ Dout, int K, int N,
+                uint32_t lbo16, uint32_t sbo16, uint32_t layout, uint32_t kstep_bytes) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int KB = K / KBLK;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)KB * A_BLK;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < TM * K; idx += 128) {
+        const int r = idx / K, c = idx % K;
+        *(__half*)(sA + (size_t)(c / KBLK) * A_BLK + sw128_off(r, c % KBLK)) = A[(size_t)r * K + c];
+    }
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int r = idx / K, c = idx % K;
+        *(__half*)(sB + (size_t)(c / KBLK) * (N * 128) + sw128_off(r, c % KBLK)) = B[(size_t)r * K + c];
+    }
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 64);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(TM, N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb)
+            for (int ks = 0; ks < KBLK / 16; ++ks) {
+                const uint64_t ad = make_desc(smem_u32(sA + (size_t)kb * A_BLK) + ks * kstep_bytes, lbo16, sbo16, layout);
+                const uint64_t bd = make_desc(smem_u32(sB + (size_t)kb * (N * 128)) + ks * kstep_bytes, lbo16, sbo16, layout);
+                umma_f16(tmem_base, ad, bd, idesc, acc);
+                acc = 1;
+            }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) Dout[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
+
+
+
+// ---- self test, A operand in tensor memory: D[128 x N] = A[128 x K] B[N x K]^T -------------------------------------
+__global__ void __launch_bounds__(128, 1)
+selftest_ts_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ Dout, int K, int N) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int KB = K / KBLK;
+    uint8_t* sB = smem;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int r = idx / K, c = idx % K;
+        *(__half*)(sB + (size_t)(c / KBLK) * (N * 128) + sw128_off(r, c % KBLK)) = B[(size_t)r * K + c];
+    }
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t colA = 64;                                   // A image at columns [64, 64 + K/2)
+    {   // thread = row: pack two consecutive K elements per 32-bit column
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        for (int c0 = 0; c0 < K / 2; c0 += 16) {
+            uint32_t w[16];
+            for (int i = 0; i < 16; ++i) {
+                const __half lo = A[(size_t)tid * K + 2 * (c0 + i)], hi = A[(size_t)tid * K + 2 * (c0 + i) + 1];
+                w[i] = (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+            }
+            tmem_st16(tmem_base + lane_addr + colA + c0, w);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(TM, N);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb)
+            for (int ks = 0; ks < KBLK / 16; ++ks) {
+                const uint64_t bd = make_desc(smem_u32(sB + (size_t)kb * (N * 128)) + ks * 32, 1, 64, 2);
+                umma_f16_ts(tmem_base, tmem_base + colA + (uint32_t)(kb * 4 + ks) * 8u, bd, idesc, acc);
+                acc = 1;
+            }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) Dout[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+
+// ---- micro-benchmark: cycles per tcgen05.mma (M = 128, K = 16, f16) for a given N, number of independent
+//      accumulator chains and A source; one CTA per SM, no epilogue.  Used to size tiles (profiles/). -----------------
+__global__ void __launch_bounds__(128, 1)
+mma_bench_kernel(int N, int nchains, int ts_mode, int iters, long long* __restrict__ cycles_out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    uint8_t* sA = smem;                       // [128 x 64] f16 block
+    uint8_t* sB = smem + A_BLK;               // [256 x 64] f16 block
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (A_BLK + 256 * 128) / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;   // f16 ones
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    if (warp == 0) {
+        // converged warp, one elected lane issues: operands are warp-uniform, so UTCHMMA takes them from uniform
+        // registers without the per-lane serialisation loop a divergent `if (lane == 0)` block compiles to
+        const uint32_t idesc = make_idesc(TM, N);
+        const uint64_t ad = make_desc(smem_u32(sA), 1, 64, 2), bd = make_desc(smem_u32(sB), 1, 64, 2);
+        const uint32_t chain_stride = (uint32_t)N;
+        const uint32_t el = elect_one();
+        const long long t0 = clock64();
+        if (ts_mode >= 2) {
+            // unrolled by 4, fixed operands per slot (ts_mode 4 / 8: with concurrent tcgen05.ld traffic from the other warps)
+            const uint32_t acc0 = tmem_base, acc1 = tmem_base + (nchains > 1 ? chain_stride : 0u);
+            for (int it = 0; it < iters; it += 4) {
+                if (el) {
+                    umma_f16_ts(acc0, tmem_base + 480u, bd, idesc, 1u);
+                    umma_f16_ts(acc1, tmem_base + 480u, bd + 2ull, idesc, 1u);
+                    umma_f16_ts(acc0, tmem_base + 488u, bd + 4ull, idesc, 1u);
+                    umma_f16_ts(acc1, tmem_base + 488u, bd + 6ull, idesc, 1u);
+                }
+            }
+        } else {
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t acc = tmem_base + (uint32_t)(it % nchains) * chain_stride;
+                const uint32_t ks = (uint32_t)(it & 3);
+                if (el) {
+                    if (ts_mode) umma_f16_ts(acc, tmem_base + 480u, bd + (uint64_t)(ks * 2), idesc, it >= nchains ? 1u : 0u);
+                    else umma_f16(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, it >= nchains ? 1u : 0u);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if (el) umma_commit(smem_u32(&bar));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && el) { cycles_out[0] = t1 - t0; cycles_out[1] = t2 - t0; }
+    } else if (ts_mode >= 4) {
+        // interference probe: the other warps stream accumulator columns out of tensor memory while the MMAs run
+        float acc = 0.f;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const int nld = (ts_mode >= 8) ? iters * 2 : iters / 2;
+        for (int it = 0; it < nld; ++it) {
+            float v[16];
+            tmem_ld16(tmem_base + lane_addr + 256u + (uint32_t)((it & 7) * 16), v);
+            tmem_ld_wait();
+            acc += v[it & 15];
+        }
+        if (acc == 12345.678f) cycles_out[3] = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+
 
 __global__ void __launch_bounds__(17 * 32, 1)
 pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
@@ -149,6 +338,33 @@ int tc_pipe_bench(int mode, int N, int iters, long long* out_dev, cudaStream_t s
     SC_CUDA(cudaFuncSetAttribute(tc::pipe_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SC_CUDA(cudaMemsetAsync(out_dev, 0, 8 * sizeof(long long), stream));
     tc::pipe_bench_kernel<<<148, 17 * 32, smem, stream>>>(mode, N, iters, out_dev);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream) {
+    SC_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && nchains >= 1 && nchains * N <= 448, "mma_bench: shape");
+    const size_t smem = tc::A_BLK + 256 * 128 + 1024;
+    SC_CUDA(cudaFuncSetAttribute(tc::mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc::mma_bench_kernel<<<148, 128, smem, stream>>>(N, nchains, ts_mode, iters, cycles_dev);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
+int tc_selftest(const void* A_dev, const void* B_dev, float* D_dev, int K, int N, unsigned lbo16, unsigned sbo16,
+                unsigned layout, unsigned kstep_bytes, cudaStream_t stream) {
+    SC_REQUIRE(K % tc::KBLK == 0 && K >= 64 && K <= 256, "selftest: K must be a multiple of 64");
+    SC_REQUIRE(N % 16 == 0 && N >= 16 && N <= 64, "selftest: N in [16, 64], multiple of 16");
+    const size_t smem = 1024 + (size_t)(K / tc::KBLK) * (tc::A_BLK + (size_t)N * 128);
+    SC_CUDA(cudaFuncSetAttribute(tc::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (layout == 100) {      // A operand in tensor memory (TS mode)
+        SC_CUDA(cudaFuncSetAttribute(tc::selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::selftest_ts_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N);
+        SC_LAUNCH_CHECK();
+        return OK;
+    }
+    tc::selftest_kernel<<<1, 128, smem, stream>>>((const __half*)A_dev, (const __half*)B_dev, D_dev, K, N, lbo16, sbo16,
+                                                  layout, kstep_bytes);
     SC_LAUNCH_CHECK();
     return OK;
 }
