@@ -48,6 +48,7 @@ struct TcDev {
     int nstep, ntile_dom, ntile_bdy;
     long long* dbg;
     int dbg_block;
+    int dbg_flags;                   // timeline experiments: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 8 no operand copies (garbage operands)
 };
 
 // ---- per-centre coefficient of one column (NumPy statement: tests/tc_expansion_ref.py::centre_coefficient) --------------
@@ -149,14 +150,14 @@ __global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile
     }
 }
 
-// pass 2b: stage-2 coefficient images of one evaluation class: per tile [k hi | k lo | ky hi | ky lo | kx hi | kx lo],
+// pass 2b: stage-2 coefficient images of one evaluation class: per tile [k hi | k lo | kx hi | kx lo | ky hi | ky lo],
 // each [ncol rows x 64 centres] f16 (K-major B operand, 128 B swizzle); column table with the inverse scales.
 __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, int cls, int ncentres, const double* __restrict__ coef,
                                 const unsigned long long* __restrict__ colmax, uint8_t* __restrict__ b3, size_t tile_bytes,
-                                int nk, int nky, int nkx, TcColDesc* __restrict__ desc) {
+                                int nk, int nkx, int nky, TcColDesc* __restrict__ desc) {
     const int tile = blockIdx.x;
     uint8_t* base = b3 + (size_t)tile * tile_bytes;
-    const int ntot = nk + nky + nkx;
+    const int ntot = nk + nkx + nky;
     for (int idx = threadIdx.x; idx < ntot * TN; idx += blockDim.x) {
         const int col = idx / TN, j = idx % TN;
         const double cm = __longlong_as_double((long long)colmax[cls * TC_MAXCOL + col]);
@@ -169,8 +170,8 @@ __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, i
         int row = col;
         size_t off = 0;
         int n = nk;
-        if (col >= nk + nky) { row = col - nk - nky; off = (size_t)2 * (nk + nky) * 128; n = nkx; }
-        else if (col >= nk) { row = col - nk; off = (size_t)2 * nk * 128; n = nky; }
+        if (col >= nk + nkx) { row = col - nk - nkx; off = (size_t)2 * (nk + nkx) * 128; n = nky; }
+        else if (col >= nk) { row = col - nk; off = (size_t)2 * nk * 128; n = nkx; }
         *(__half*)(base + off + sw_off(row, j)) = hi;
         *(__half*)(base + off + (size_t)n * 128 + sw_off(row, j)) = lo;
         if (tile == 0 && j == 0) {
@@ -185,10 +186,23 @@ __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, i
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
+// Work item = (64-centre tile, kernel class): 14 stage-1 MMAs (N = 64, A = a' x hi | lo from tensor memory) into one of
+// four 64-column S slots, the epilogue turns S into P in place, 12 stage-2 MMAs (A = P from tensor memory) add P C into T.
+//   u / u + div:  domain tile -> k, ky;      boundary tile -> k
+//   PDE:          domain tile -> k, kx, ky;  boundary tile -> k, kx
+// Four slots decouple the two pipelines: the MMA warp issues stage 1 three items ahead of the epilogue warps, so the
+// barrier round trip (commit -> epilogue -> arrive -> stage 2) is off the critical path (tools/tc_timeline.py).
+// Tensor memory: S/P slots at columns 0, 64, 128, 192; T at 256; A images (hi | lo, 64 columns apart) at 384.
 template <int CLASS> struct Cfg;
-template <> struct Cfg<TC_U>   { static constexpr int NS = 128, NK = 16, NKY = 16, NKX = 0,  NB1 = 4; };
-template <> struct Cfg<TC_UG>  { static constexpr int NS = 128, NK = 16, NKY = 32, NKX = 0,  NB1 = 4; };
-template <> struct Cfg<TC_PDE> { static constexpr int NS = 192, NK = 48, NKY = 48, NKX = 32, NB1 = 3; };
+template <> struct Cfg<TC_U>   { static constexpr int NK = 16, NKX = 0,  NKY = 16; };
+template <> struct Cfg<TC_UG>  { static constexpr int NK = 16, NKX = 0,  NKY = 32; };
+template <> struct Cfg<TC_PDE> { static constexpr int NK = 48, NKX = 32, NKY = 48; };
+
+constexpr uint32_t COL_T = 256, COL_A = 384, A_IMG_COLS = 64;
+constexpr int NSLOT = 4;                                             // S/P slots = items in flight
+constexpr uint32_t B1_BLK = TN * 128;                                // one K block of one class: [64 rows x 128 B]
+constexpr int A_PITCH = 240;                                         // staging row pitch (bytes): 16-byte reads of 8 rows hit 8 bank groups
+constexpr int NBAR = 5 * NSLOT + 1;                                  // b1_full b3_full b3_empty s_full p_ready | t_full
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -196,33 +210,38 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem)
     return r;
 }
 
-template <int CLASS, int KB>
+// compile-time accumulate flag: the issuing thread runs alone, every extra (uniform-datapath) instruction per MMA costs its
+// full latency, so operands are immediates off a per-item base and the k-step count is a template parameter
+template <bool ACC>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+
+template <int CLASS, int NSTEP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode,
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
     using C = Cfg<CLASS>;
     constexpr bool PDE = (CLASS == TC_PDE);
-    constexpr int NS = C::NS;                                        // S columns of a domain tile
-    constexpr int NT = C::NK + C::NKY + C::NKX;                      // T columns
-    constexpr int NB1 = C::NB1;                                      // stage-1 operand ring: K blocks
-    constexpr uint32_t B1_SLOT = NS * 128;                           // one K block of one tile
-    constexpr uint32_t B3_SLOT = 2 * NT * 128;                       // one tile's coefficient images (hi + lo)
-    constexpr uint32_t COL_T = 2 * NS;                               // TMEM: S/P buffers at 0 and NS, T behind them
-    // S column offset of each kernel class inside a buffer; PDE: [k | kx | ky], else [k | ky]
-    constexpr int SC_K = 0, SC_KY = PDE ? 128 : 64, SC_KX = 64;
-    constexpr int TC_K = 0, TC_KY = C::NK, TC_KX = C::NK + C::NKY;   // T column offsets
+    constexpr int KB = (NSTEP + 3) / 4;                              // 64-wide K blocks
+    constexpr int NT = C::NK + C::NKX + C::NKY;                      // T columns: [k | kx | ky]
+    constexpr int NMAX = C::NK > C::NKY ? C::NK : C::NKY;
+    constexpr uint32_t B3_SLOT = 2 * NMAX * 128;                     // one class's coefficient images (hi | lo)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
-    uint8_t* sA = smem;                                              // [hi | lo] x KB blocks of [128 x 64] f16
-    uint8_t* sB1 = sA + 2 * (size_t)KB * A_BLK;
-    uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;
-    uint8_t* sMisc = sB3 + 2 * (size_t)B3_SLOT;
+    constexpr uint32_t B1_SLOT = KB * B1_BLK;                        // one item's centre rows, all K blocks
+    uint8_t* sB1 = smem;                                             // NSLOT item slots
+    uint8_t* sB3 = sB1 + NSLOT * (size_t)B1_SLOT;                    // NSLOT item slots
+    uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH]; reused at the end
+    uint8_t* sMisc = sStage + 2 * (size_t)TM * A_PITCH;
     double* Ki = (double*)sMisc;                                     // [128] exp(-a |x|^2 / 2)
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i
-    uint64_t* bars = (uint64_t*)(sxs + TM);                          // b1_full[4] b1_empty[4] b3_full[2] b3_empty[2] s_full[2] p_ready[2] t_full
-    uint32_t* tmem_slot = (uint32_t*)(bars + 17);
+    uint64_t* bars = (uint64_t*)(sxs + TM);
+    uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
@@ -230,19 +249,16 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
 #define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
-    uint32_t b1_full[4], b1_empty[4], b3_full[2], b3_empty[2], s_full[2], p_ready[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { b1_full[i] = smem_u32(&bars[i]); b1_empty[i] = smem_u32(&bars[4 + i]); }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        b3_full[i] = smem_u32(&bars[8 + i]); b3_empty[i] = smem_u32(&bars[10 + i]);
-        s_full[i] = smem_u32(&bars[12 + i]); p_ready[i] = smem_u32(&bars[14 + i]);
-    }
-    const uint32_t t_full = smem_u32(&bars[16]);
+    const uint32_t bar0 = smem_u32(bars);
+    auto b1_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto b3_full = [&](int i) { return bar0 + 8u * (uint32_t)(NSLOT + i); };
+    auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NSLOT + i); };
+    auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(3 * NSLOT + i); };
+    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(4 * NSLOT + i); };
+    const uint32_t t_full = bar0 + 8u * (uint32_t)(NBAR - 1);
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(b1_full[i], 1); mbar_init(b1_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(b3_full[i], 1); mbar_init(b3_empty[i], 1); mbar_init(s_full[i], 1); mbar_init(p_ready[i], NEPI); }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(b1_full(i), 1); mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI); }
         mbar_init(t_full, 1);
         fence_barrier_init();
     }
@@ -251,56 +267,53 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     __syncthreads();                                                 // TMEM base address + barriers visible
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    const int ndom = st.ntile_dom, ntile = st.ntile_dom + st.ntile_bdy;
-    const int nstep = st.nstep;
+    const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
+    constexpr int nstep = NSTEP;
+    constexpr int CPD = PDE ? 3 : 2;                                 // kernel classes of a domain tile
+    const int nitem = CPD * ndom + (CPD - 1) * nbdy;
+    // item w -> (tile, kernel class).  Class order inside a tile: k, (kx,) ky; boundary tiles have no ky class.
+    auto item_of = [&](int w, int& t, int& kc) {
+        if (w < CPD * ndom) {
+            t = w / CPD;
+            const int c = w - t * CPD;
+            kc = PDE ? (c == 0 ? TK_K : (c == 1 ? TK_KX : TK_KY)) : (c == 0 ? TK_K : TK_KY);
+        } else {
+            const int v = w - CPD * ndom;
+            t = ndom + (PDE ? (v >> 1) : v);
+            kc = (PDE && (v & 1)) ? TK_KX : TK_K;
+        }
+    };
 
     if (warp == NEPI) {
-        // ===== producer: centre images (one K block per ring slot) and coefficient images (one tile per slot) =====
-        // issue order = consumption order of the MMA warp: B1(0), B1(1), B3(0), B1(2), B3(1), ...
-        if (lane == 0) {
-            int i1 = 0;
-            auto load_b1 = [&](int t) {
-                const bool dom = t < ndom;
-                const uint8_t* src = st.b1 + (size_t)t * st.b1_tile_bytes;
+        // ===== producer: per item, the class's centre rows of every K block (B1 ring) and its coefficient images (B3 ring);
+        // issue order = consumption order of the MMA warp: B1(0..2), then B1(w+3), B3(w) =====
+        // One "full" barrier per item and ring; the centre-row slot of item w is reusable once s_full(w) fired (stage 1 done),
+        // the coefficient slot once the MMA warp committed b3_empty(w).  Issue order = consumption order of the MMA warp.
+        if (lane == 0 && !(st.dbg_flags & 8)) {
+            auto load_b1 = [&](int w) {
+                int t, kc; item_of(w, t, kc);
+                const int s = w % NSLOT;
+                if (w >= NSLOT) mbar_wait(s_full(s), ((w / NSLOT) - 1) & 1);
+                const uint8_t* src = st.b1 + (size_t)t * st.b1_tile_bytes
+                                   + (size_t)(kc == TK_K ? 0 : (kc == TK_KX ? 1 : 2)) * B1_BLK;       // rows [C | Crollinv | Croll]
+                mbar_expect_tx(b1_full(s), B1_SLOT);
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb, ++i1) {
-                    const int s = i1 % NB1;
-                    if (i1 >= NB1) mbar_wait(b1_empty[s], ((i1 / NB1) - 1) & 1);
-                    uint8_t* dst = sB1 + (size_t)s * B1_SLOT;
-                    const uint8_t* blk = src + (size_t)kb * (3 * TN * 128);
-                    if (PDE) {                                       // rows [C | Crollinv (| Croll)]
-                        const uint32_t bytes = dom ? 3 * TN * 128 : 2 * TN * 128;
-                        mbar_expect_tx(b1_full[s], bytes);
-                        bulk_g2s(smem_u32(dst), blk, bytes, b1_full[s]);
-                    } else if (dom) {                                // rows [C | Croll]
-                        mbar_expect_tx(b1_full[s], 2 * TN * 128);
-                        bulk_g2s(smem_u32(dst), blk, TN * 128, b1_full[s]);
-                        bulk_g2s(smem_u32(dst + TN * 128), blk + 2 * TN * 128, TN * 128, b1_full[s]);
-                    } else {
-                        mbar_expect_tx(b1_full[s], TN * 128);
-                        bulk_g2s(smem_u32(dst), blk, TN * 128, b1_full[s]);
-                    }
-                }
+                for (int kb = 0; kb < KB; ++kb)
+                    bulk_g2s(smem_u32(sB1 + (size_t)s * B1_SLOT + (size_t)kb * B1_BLK), src + (size_t)kb * (3 * B1_BLK), B1_BLK, b1_full(s));
             };
-            auto load_b3 = [&](int t) {
-                const int s = t & 1;
-                if (t >= 2) mbar_wait(b3_empty[s], ((t >> 1) - 1) & 1);
-                const uint8_t* src = st.b3 + (size_t)t * st.b3_tile_bytes;
-                uint8_t* dst = sB3 + (size_t)s * B3_SLOT;
-                if (t < ndom) {
-                    mbar_expect_tx(b3_full[s], B3_SLOT);
-                    bulk_g2s(smem_u32(dst), src, B3_SLOT, b3_full[s]);
-                } else {                                             // boundary tiles: no ky class
-                    mbar_expect_tx(b3_full[s], 2 * (C::NK + C::NKX) * 128);
-                    bulk_g2s(smem_u32(dst), src, 2 * C::NK * 128, b3_full[s]);
-                    if (C::NKX > 0)
-                        bulk_g2s(smem_u32(dst + 2 * (C::NK + C::NKY) * 128), src + 2 * (C::NK + C::NKY) * 128, 2 * C::NKX * 128, b3_full[s]);
-                }
+            auto load_b3 = [&](int w) {
+                int t, kc; item_of(w, t, kc);
+                const int s = w % NSLOT;
+                if (w >= NSLOT) mbar_wait(b3_empty(s), ((w / NSLOT) - 1) & 1);
+                const uint32_t off = kc == TK_K ? 0u : (kc == TK_KX ? 2u * C::NK * 128u : 2u * (C::NK + C::NKX) * 128u);
+                const uint32_t bytes = 2u * 128u * (uint32_t)(kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY));
+                mbar_expect_tx(b3_full(s), bytes);
+                bulk_g2s(smem_u32(sB3 + (size_t)s * B3_SLOT), st.b3 + (size_t)t * st.b3_tile_bytes + off, bytes, b3_full(s));
             };
-            load_b1(0);
-            for (int t = 0; t < ntile; ++t) {
-                if (t + 1 < ntile) load_b1(t + 1);
-                load_b3(t);
+            for (int w = 0; w < NSLOT - 1 && w < nitem; ++w) load_b1(w);
+            for (int w = 0; w < nitem; ++w) {
+                if (w + NSLOT - 1 < nitem) load_b1(w + NSLOT - 1);
+                load_b3(w);
             }
         }
         __syncwarp();
@@ -308,90 +321,105 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         // ===== MMA issuer: the warp stays converged and one elected lane issues (warp-uniform operands come from uniform
         // registers; a divergent `if (lane == 0)` block compiles to a per-lane serialisation loop around each MMA) =====
         const uint32_t el = elect_one();
-        // wait for the A images (epilogue warps build them; named barrier 2 = epilogue warps + this warp)
+        // wait for the A images (epilogue warps stage them into tensor memory; named barrier 2 = epilogue warps + this warp)
         asm volatile("bar.sync 2, %0;" ::"n"((NEPI + 1) * 32) : "memory");
         tc_fence_after();
-        const uint64_t adesc = make_desc(smem_u32(sA), 1, 64, 2);
-        uint64_t b1desc[NB1];
-#pragma unroll
-        for (int i = 0; i < NB1; ++i) b1desc[i] = make_desc(smem_u32(sB1 + (size_t)i * B1_SLOT), 1, 64, 2);
+        const uint64_t b1desc0 = make_desc(smem_u32(sB1), 1, 64, 2);
         const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
-        const uint32_t idS_dom = make_idesc(TM, NS), idS_bdy = make_idesc(TM, PDE ? 128 : 64);
+        const uint32_t idS = make_idesc(TM, TN);
         const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
-        int i1 = 0;
-        auto stage1 = [&](int t) {
-            const uint32_t accS = tmem_base + (uint32_t)(t & 1) * NS;
-            const uint32_t idesc = (t < ndom) ? idS_dom : idS_bdy;
-            if (el) TC_STAMP(4 + 4 * t);
+        const uint32_t aBase = tmem_base + COL_A;
+        bool first_k = true, first_kx = true, first_ky = true;
+        // Every barrier operation of this lone issuing thread costs ~100 cycles of latency (measured, tools/tc_timeline.py), so
+        // an item is one wait + 14 MMAs + one commit in stage 1 and one (combined) wait + 12 MMAs + one commit in stage 2.
+        auto stage1 = [&](int w) {
+            const int s = w % NSLOT;
+            const uint32_t accS = tmem_base + (uint32_t)s * 64u;
+            if (el && w < 60) TC_STAMP(4 + 4 * w);
+            if (!(st.dbg_flags & 8)) mbar_wait(b1_full(s), (w / NSLOT) & 1);
+            tc_fence_after();
+            const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s * B1_SLOT) >> 4);
+            if (el) {
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb, ++i1) {
-                const int s = i1 % NB1;
-                mbar_wait(b1_full[s], (i1 / NB1) & 1);
-                tc_fence_after();
-                uint64_t bb = b1desc[0];
-#pragma unroll
-                for (int i = 1; i < NB1; ++i) bb = (s == i) ? b1desc[i] : bb;
-                if (el) {
+                for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                     for (int half = 1; half >= 0; --half) {          // low halves first (tiny terms), then the high halves
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            if (kb * 4 + ks < nstep) {
-                                const uint64_t ad = adesc + (uint64_t)((((half * KB + kb) * A_BLK) + ks * 32) >> 4);
-                                umma_f16(accS, ad, bb + (uint64_t)((ks * 32) >> 4), idesc, (kb == 0 && half == 1 && ks == 0) ? 0u : 1u);
+                            if (kb * 4 + ks < NSTEP) {
+                                const uint32_t aa = aBase + (uint32_t)half * A_IMG_COLS + (uint32_t)(kb * 4 + ks) * 8u;
+                                const uint64_t bd = bb + (uint64_t)((kb * B1_BLK + ks * 32) >> 4);
+                                if (kb == 0 && half == 1 && ks == 0) umma_ts<false>(accS, aa, bd, idS);
+                                else umma_ts<true>(accS, aa, bd, idS);
                             }
                         }
                     }
-                    umma_commit(b1_empty[s]);                        // operand slot reusable
                 }
-                __syncwarp();
+                umma_commit(s_full(s));                              // accumulators ready; the centre-row slot is reusable
             }
-            if (el) umma_commit(s_full[t & 1]);                      // accumulators ready for the epilogue warps
             __syncwarp();
         };
-        auto stage2 = [&](int t) {
-            const int s = t & 1;
-            const bool dom = t < ndom;
-            mbar_wait(p_ready[s], (t >> 1) & 1);                     // P(t) written over S(t) by all epilogue warps
-            mbar_wait(b3_full[s], (t >> 1) & 1);
+        int kc2 = TK_K, t2 = 0;                                      // (tile, class) of the next stage-2 item
+        auto stage2 = [&](int w) {
+            const int s = w % NSLOT;
+            {   // P written over S by all epilogue warps + coefficient images landed: one polling loop for both barriers
+                const uint32_t par = (uint32_t)(w / NSLOT) & 1u;
+                uint32_t spins = 0;
+                bool a = false, b = (st.dbg_flags & 8) != 0;
+                while (true) {
+                    if (!a) a = mbar_test_wait(p_ready(s), par);
+                    if (!b) b = mbar_test_wait(b3_full(s), par);
+                    if (a && b) break;
+                    if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
+                }
+            }
             tc_fence_after();
-            const uint32_t pbase = tmem_base + (uint32_t)s * NS;
+            const uint32_t pbase = tmem_base + (uint32_t)s * 64u;
             const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT) >> 4);
+            const int kc = kc2;
+            const uint32_t tacc = tmem_base + COL_T + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
+            const uint32_t nrows = kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY);
+            const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
+            const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
+            const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
             if (el) {
-                auto cls_mma = [&](uint32_t pcol, uint32_t tcol, uint32_t off_hi, uint32_t nrows, uint32_t idesc, bool first) {
+                if (!(st.dbg_flags & 1)) {
+                    if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
+                    umma_ts<true>(tacc, pbase, clo0, idesc);
+                    umma_ts<true>(tacc, pbase + 8u, b3, idesc);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t chi = b3 + (uint64_t)((off_hi + ks * 32) >> 4);
-                        const uint64_t clo = b3 + (uint64_t)((off_hi + nrows * 128 + ks * 32) >> 4);
-                        const uint32_t phi = pbase + pcol + (uint32_t)ks * 16u, plo = phi + 8u;
-                        umma_f16_ts(tmem_base + COL_T + tcol, phi, chi, idesc, (first && ks == 0) ? 0u : 1u);
-                        umma_f16_ts(tmem_base + COL_T + tcol, phi, clo, idesc, 1u);
-                        umma_f16_ts(tmem_base + COL_T + tcol, plo, chi, idesc, 1u);
+                    for (int ks = 1; ks < 4; ++ks) {
+                        umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                        umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
+                        umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
                     }
-                };
-                cls_mma(SC_K, TC_K, 0u, C::NK, idK, t == 0);
-                if (dom) cls_mma(SC_KY, TC_KY, 2u * C::NK * 128u, C::NKY, idKY, t == 0);
-                if (C::NKX > 0) cls_mma(SC_KX, TC_KX, 2u * (C::NK + C::NKY) * 128u, C::NKX, idKX, t == 0);
-                umma_commit(b3_empty[s]);
-                TC_STAMP(5 + 4 * t);
+                }
+                umma_commit(b3_empty(s));
+                if (w < 60) TC_STAMP(5 + 4 * w);
             }
             __syncwarp();
+            if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
+            // next item: k, (kx,) ky on domain tiles; k (, kx) on boundary tiles
+            if (kc == TK_K) kc2 = PDE ? TK_KX : (t2 < ndom ? TK_KY : TK_K);
+            else if (kc == TK_KX) kc2 = (t2 < ndom) ? TK_KY : TK_K;
+            else kc2 = TK_K;
+            if (kc2 == TK_K) ++t2;
         };
-        stage1(0);
-        for (int t = 0; t < ntile; ++t) {
-            if (t + 1 < ntile) stage1(t + 1);
-            stage2(t);
+        for (int w = 0; w < NSLOT - 1 && w < nitem; ++w) stage1(w);
+        for (int w = 0; w < nitem; ++w) {
+            if (w + NSLOT - 1 < nitem) stage1(w + NSLOT - 1);
+            stage2(w);
         }
         if (el) umma_commit(t_full);
         __syncwarp();
     } else {
         // ===== epilogue warps =====
-        // --- prologue: A images a' x = hi + lo (f16, 128 B swizzle), row sums.  Two rows per warp pass (16 lanes x 8 columns).
+        // --- prologue: a' x = hi + lo (f16) into the staging buffer, row sums; then into tensor memory (lane = row).
         {
             const double ascale = gp.a * 1.4426950408889634;           // a log2(e): S = log2 of exp(a x.y)
             const int hl = lane & 15, sub = lane >> 4;
             const int c0 = hl * 8;
-            const bool active = c0 < KB * KBLK;
+            const bool active = c0 < nstep * 16;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 double v[2][8];
@@ -429,17 +457,30 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         lo[e >> 1] = *(const uint32_t*)&l;
                     }
                     if (active) {
-                        const uint32_t off = (uint32_t)(c0 / KBLK) * A_BLK + (uint32_t)r * 128u + (uint32_t)(((((c0 % KBLK) >> 3) ^ (r & 7)) & 7) << 4);
-                        *(uint4*)(sA + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *(uint4*)(sA + (size_t)KB * A_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        uint8_t* p = sStage + (size_t)r * A_PITCH + (size_t)hl * 16;
+                        *(uint4*)p = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *(uint4*)(p + (size_t)TM * A_PITCH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
 #pragma unroll
                     for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
                     if (hl == 0) { Ki[r] = exp(-0.5 * gp.a * nx); sxs[r] = sx; }
                 }
             }
-            fence_proxy_async();                                     // generic-proxy smem writes -> visible to the MMA (async proxy)
             if (tid == 0) TC_STAMP(1);
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            if (warp < 8) {                                          // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
+                const int img = warp >> 2;
+                const int r = (warp & 3) * 32 + lane;
+                const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
+                const uint32_t taddr = tmem_base + COL_A + (uint32_t)img * A_IMG_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+                for (int ks = 0; ks < nstep; ++ks) {
+                    const uint4 q0 = *(const uint4*)(rowp + ks * 32), q1 = *(const uint4*)(rowp + ks * 32 + 16);
+                    const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    tmem_st8(taddr + (uint32_t)ks * 8u, wv);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
             asm volatile("bar.sync 2, %0;" ::"n"((NEPI + 1) * 32) : "memory");
             if (tid == 0) TC_STAMP(2);
         }
@@ -447,45 +488,38 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const int r = (warp & 3) * 32 + lane;
         const int cg = warp >> 2;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        constexpr int NCLS = PDE ? 3 : 2;
-        for (int t = 0; t < ntile; ++t) {
-            const int s = t & 1;
-            const bool dom = t < ndom;
-            mbar_wait(s_full[s], (t >> 1) & 1);
+        const bool skip_math = (st.dbg_flags & 2) != 0;
+        for (int w = 0; w < nitem; ++w) {
+            const int s = w % NSLOT;
+            mbar_wait(s_full(s), (w / NSLOT) & 1);
             tc_fence_after();
-            if (tid == 0) TC_STAMP(6 + 4 * t);
-            const uint32_t base = tmem_base + lane_addr + (uint32_t)s * NS + (uint32_t)cg * 16u;
-            // boundary tiles have no ky class: PDE columns [k | kx], else [k]
-            const int ncls = dom ? NCLS : NCLS - 1;
-            float v[NCLS][16];
+            if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
+            const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 64u + (uint32_t)cg * 16u;
+            if (!skip_math) {
+                float v[16];
+                tmem_ld16(base, v);
+                tmem_ld_wait();
+                uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int c = 0; c < NCLS; ++c) if (c < ncls) tmem_ld16(base + (uint32_t)c * 64u, v[c]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < NCLS; ++c) {
-                if (c < ncls) {
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float p0 = ex2f(v[c][2 * i]), p1 = ex2f(v[c][2 * i + 1]);
-                        hi[i] = pack_f16x2_sat(p0, p1);
-                        const float2 hf = __half22float2(*(const __half2*)&hi[i]);
-                        lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
-                    }
-                    tmem_st8(base + (uint32_t)c * 64u, hi);
-                    tmem_st8(base + (uint32_t)c * 64u + 8u, lo);
+                for (int i = 0; i < 8; ++i) {
+                    const float p0 = ex2f(v[2 * i]), p1 = ex2f(v[2 * i + 1]);
+                    hi[i] = pack_f16x2_sat(p0, p1);
+                    const float2 hf = __half22float2(*(const __half2*)&hi[i]);
+                    lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
                 }
+                tmem_st8(base, hi);
+                tmem_st8(base + 8u, lo);
+                tmem_st_wait();
             }
-            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (tid == 0) TC_STAMP(7 + 4 * t);
-            if (lane == 0) mbar_arrive(p_ready[s]);
+            if (tid == 0 && w < 60) TC_STAMP(7 + 4 * w);
+            if (lane == 0) mbar_arrive(p_ready(s));
         }
         // --- final contraction: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
         mbar_wait(t_full, 0);
         tc_fence_after();
-        double* feat = (double*)sA;                                  // the A images are dead: [128][TF_COUNT] features
+        double* feat = (double*)sStage;                              // the staging buffer is dead: [128][TF_COUNT] features
         double* xchg = feat + TM * TF_COUNT;                         // [3][128][4] partial sums of column groups 1..3
         if (cg == 0) {
             const long row = row0 + r;
@@ -507,7 +541,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         {
             constexpr int NPER = NT / 4;                             // T columns per column group
             const double* F = feat + r * TF_COUNT;
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
             const bool have_ky = ndom > 0;
 #pragma unroll
             for (int c0 = 0; c0 < NPER; c0 += 4) {
@@ -519,13 +553,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 for (int i = 0; i < 4; ++i) {
                     const int col = col0 + i;
                     const TcColDesc dsc = st.desc[col];
-                    const bool skip = dsc.out == TO_PAD || (!have_ky && col >= TC_KY && col < TC_KX);
-                    if (!skip) acc[dsc.out & 3] = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, acc[dsc.out & 3]);
+                    const bool skip = dsc.out == TO_PAD || (!have_ky && col >= C::NK + C::NKX);
+                    const double term = skip ? 0.0 : F[dsc.f1] * F[dsc.f2] * ((double)tv[i] * dsc.inv_scale);
+                    aU += (dsc.out == TO_U) ? term : 0.0;
+                    aG += (dsc.out == TO_G) ? term : 0.0;
+                    aL += (dsc.out == TO_L) ? term : 0.0;
+                    aT += (dsc.out == TO_T) ? term : 0.0;
                 }
             }
             if (cg > 0) {
                 double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
-                p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2]; p[3] = acc[3];
+                p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
             if (cg == 0) {
@@ -534,18 +572,18 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #pragma unroll
                     for (int g2 = 1; g2 < 4; ++g2) {
                         const double* p = xchg + ((size_t)(g2 - 1) * TM + r) * 4;
-                        acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+                        aU += p[0]; aG += p[1]; aL += p[2]; aT += p[3];
                     }
                     const double ki = Ki[r];
-                    const double u = ki * acc[TO_U];
+                    const double u = ki * aU;
                     if (CLASS == TC_U) {
                         const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));          // equations.py:259
                         out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
                     } else if (CLASS == TC_UG) {
                         out0[row] = u;
-                        out1[row] = ki * acc[TO_G];
+                        out1[row] = ki * aG;
                     } else {
-                        const double g = ki * acc[TO_G], l = ki * acc[TO_L], tt = ki * acc[TO_T];
+                        const double g = ki * aG, l = ki * aL, tt = ki * aT;
                         const double s2 = gp.sig2;
                         out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;   // GP.py:767-768
                         if (out1) out1[row] = g;
@@ -563,24 +601,24 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #undef TC_STAMP
 }
 
-template <int CLASS, int KB>
+template <int CLASS, int NSTEP>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
-    constexpr int NT = C::NK + C::NKY + C::NKX;
-    return 2 * (size_t)KB * A_BLK + C::NB1 * (size_t)(C::NS * 128) + 2 * (size_t)(2 * NT * 128) + 2 * TM * 8 + 17 * 8 + 16;
+    constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
+    return NSLOT * (size_t)(((NSTEP + 3) / 4) * B1_BLK) + NSLOT * (2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH + 2 * TM * 8 + NBAR * 8 + 16;
 }
 
-template <int CLASS, int KB>
+template <int CLASS, int NSTEP>
 static int launch(const GpView& gp, const TcDev& st, const double* X, long R, int mode,
                   double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
     static bool configured = false;
-    const size_t smem = smem_bytes<CLASS, KB>();
-    static_assert(2 * KB * A_BLK >= (int)(TM * TF_COUNT * 8 + 3 * TM * 4 * 8), "feature / exchange buffers alias the A images");
+    const size_t smem = smem_bytes<CLASS, NSTEP>();
+    static_assert(2 * TM * A_PITCH >= (int)(TM * TF_COUNT * 8 + 3 * TM * 4 * 8), "feature / exchange buffers alias the staging buffer");
     if (!configured) {
-        SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    eval_tc_kernel<CLASS, KB><<<(unsigned)cdiv(R, TM), NTHREADS, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
+    eval_tc_kernel<CLASS, NSTEP><<<(unsigned)cdiv(R, TM), NTHREADS, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -598,7 +636,8 @@ static void add_col(TcState* st, int cls, int& n, int kern, int out, int f1, int
     s.coef = (unsigned char)coef; s.m = (unsigned char)m; s.n = (unsigned char)nn; s.pad = 0;
 }
 
-// column table: same order as tests/tc_expansion_ref.py::columns, each kernel class padded to its UMMA N
+// column table: kernel classes in the order [k | kx | ky] (= accumulator columns), columns of a class in the order of
+// tests/tc_expansion_ref.py::columns, each class padded to its UMMA N
 static void build_columns(TcState* st) {
     static const int NCOL[3][3] = {{16, 16, 0}, {16, 32, 0}, {48, 48, 32}};
     const int H[7] = {TF_ONE, TF_P2, TF_XI, TF_XI + 1, TF_XI + 2, TF_XI + 3, TF_XI + 4};
@@ -628,6 +667,12 @@ static void build_columns(TcState* st) {
         }
         st->ncol[cls][TK_K] = NCOL[cls][TK_K];
         n = NCOL[cls][TK_K];
+        // kx class
+        if (cls == TC_PDE)
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 3; ++j) add_col(st, cls, n, TK_KX, TO_L, MX[i], G3[j], TCF_MX, i, j);
+        st->ncol[cls][TK_KX] = NCOL[cls][TK_KX];
+        n = NCOL[cls][TK_K] + NCOL[cls][TK_KX];
         // ky class
         for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_U, H[i], TF_ONE, TCF_H, i);
         if (cls >= TC_UG) {
@@ -639,17 +684,12 @@ static void build_columns(TcState* st) {
             for (int i = 0; i < 7; ++i) add_col(st, cls, n, TK_KY, TO_T, H[i], TF_ONE, TCF_HT, i);
         }
         st->ncol[cls][TK_KY] = NCOL[cls][TK_KY];
-        n = NCOL[cls][TK_K] + NCOL[cls][TK_KY];
-        // kx class
-        if (cls == TC_PDE)
-            for (int i = 0; i < 7; ++i)
-                for (int j = 0; j < 3; ++j) add_col(st, cls, n, TK_KX, TO_L, MX[i], G3[j], TCF_MX, i, j);
-        st->ncol[cls][TK_KX] = NCOL[cls][TK_KX];
     }
 }
 
 size_t tc_image_bytes(const GpView& gp, TcState* st) {
     st->nstep = (gp.D + 1 + 15) / 16;
+    st->nstep = st->nstep <= 2 ? 2 : (st->nstep <= 4 ? 4 : (st->nstep <= 7 ? 7 : 8));   // instantiated k-step counts
     st->KB = (st->nstep + 3) / 4;
     st->ntile_dom = gp.NdPad / tc::TN;
     st->ntile_bdy = gp.NbPad / tc::TN;
@@ -688,7 +728,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
     SC_LAUNCH_CHECK();
     for (int cls = 0; cls < 3; ++cls) {
         tc::b3_image_kernel<<<ntile, 256, 0, stream>>>(gp, spec_dev, cls, ncentres, coef, colmax, st.images + st.b3_off[cls],
-                                                        st.b3_tile_bytes[cls], st.ncol[cls][0], st.ncol[cls][1], st.ncol[cls][2],
+                                                        st.b3_tile_bytes[cls], st.ncol[cls][TK_K], st.ncol[cls][TK_KX], st.ncol[cls][TK_KY],
                                                         (TcColDesc*)(st.images + st.desc_off[cls]));
         SC_LAUNCH_CHECK();
     }
@@ -712,15 +752,19 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.b1_tile_bytes = st->b1_tile_bytes;
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
-    dv.dbg = st->dbg; dv.dbg_block = st->dbg_block;
-    if (st->KB == 1) {
-        if (cls == TC_U) return tc::launch<TC_U, 1>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
-        if (cls == TC_UG) return tc::launch<TC_UG, 1>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
-        return tc::launch<TC_PDE, 1>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
-    }
-    if (cls == TC_U) return tc::launch<TC_U, 2>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
-    if (cls == TC_UG) return tc::launch<TC_UG, 2>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
-    return tc::launch<TC_PDE, 2>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);
+    dv.dbg = st->dbg; dv.dbg_block = st->dbg_block & 0xFFFFFF; dv.dbg_flags = st->dbg ? (st->dbg_block >> 24) : 0;
+#define SC_TC_DISPATCH(NS)                                                                                     \
+    do {                                                                                                       \
+        if (cls == TC_U) return tc::launch<TC_U, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);       \
+        if (cls == TC_UG) return tc::launch<TC_UG, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);     \
+        return tc::launch<TC_PDE, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                      \
+    } while (0)
+    // the k-step count is a template parameter (lean single-thread MMA issue): images are zero-padded up to it
+    if (st->nstep <= 2) SC_TC_DISPATCH(2);
+    if (st->nstep <= 4) SC_TC_DISPATCH(4);
+    if (st->nstep <= 7) SC_TC_DISPATCH(7);
+    SC_TC_DISPATCH(8);
+#undef SC_TC_DISPATCH
 }
 
 // timeline of one CTA: stamps[0] entry, [1] A images built, [2] prologue done, [3] exit,

@@ -7,6 +7,9 @@
 //   mode 4  mode 3 with the MMA warp issuing SS-mode N = `N` MMAs concurrently (interference)
 //   mode 5  MMA warp alone: SS-mode N = `N` MMAs
 //   mode 6  MMA warp alone: TS-mode N = `N` MMAs (A operand in tensor memory)
+//   mode 7  mode 6 with a tcgen05.commit (to a barrier nobody waits on) after every 7 MMAs
+//   mode 8  mode 6 with commit + tcgen05.fence + an mbarrier poll on an already-completed barrier after every 7 MMAs
+//   mode 9  mode 3 (epilogue chunk loop) with the MMA warp issuing TS-mode MMAs concurrently
 #include "common.cuh"
 #include "gp_tc.cuh"
 #include "tc_ptx.cuh"
@@ -265,7 +268,7 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) sink += v[i];
-        } else if (mode == 3 || mode == 4) {
+        } else if (mode == 3 || mode == 4 || mode == 9) {
             for (int it = 0; it < iters; ++it) {
                 const uint32_t col = tmem_base + lane_addr + (uint32_t)((it & 3) * 64 + cg * 16);
                 float v[16];
@@ -299,12 +302,27 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
         if (mode >= 4) {
             const uint32_t idesc = make_idesc(128, N);
             const uint64_t ad = make_desc(smem_u32(sA), 1, 64, 2), bd = make_desc(smem_u32(sB), 1, 64, 2);
-            const int nmma = (mode == 4) ? iters * 2 : iters;
+            const int nmma = (mode == 4 || mode == 9) ? iters * 2 : iters;
+            uint64_t& bar2 = *(uint64_t*)(smem + 128 * 128 + 256 * 128 + 16);
+            uint64_t& bar3 = *(uint64_t*)(smem + 128 * 128 + 256 * 128 + 24);
+            if (el) { mbar_init(smem_u32(&bar2), 1); mbar_init(smem_u32(&bar3), 1); mbar_arrive(smem_u32(&bar3)); fence_barrier_init(); }
+            __syncwarp();
             const uint32_t acc = tmem_base + 256u;
             const long long t0 = clock64();
+            if (mode == 7 || mode == 8) {
+                for (int it = 0; it < nmma; it += 7) {
+                    if (mode == 8) { mbar_wait(smem_u32(&bar3), 0); tc_fence_after(); }
+                    if (el) {
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) umma_f16_ts(acc, tmem_base + 480u + (uint32_t)(q & 1) * 8u, bd + (uint64_t)((q & 3) * 2), idesc, 1u);
+                        umma_commit(smem_u32(&bar2));
+                    }
+                    __syncwarp();
+                }
+            } else
             for (int it = 0; it < nmma; it += 4) {
                 if (el) {
-                    if (mode == 6) {
+                    if (mode == 6 || mode == 9) {
                         umma_f16_ts(acc, tmem_base + 480u, bd, idesc, 1u);
                         umma_f16_ts(acc, tmem_base + 488u, bd + 2ull, idesc, 1u);
                         umma_f16_ts(acc, tmem_base + 480u, bd + 4ull, idesc, 1u);
@@ -333,7 +351,7 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
 }  // namespace tc
 
 int tc_pipe_bench(int mode, int N, int iters, long long* out_dev, cudaStream_t stream) {
-    SC_REQUIRE(mode >= 0 && mode <= 6 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && iters % 64 == 0, "pipe_bench: arguments");
+    SC_REQUIRE(mode >= 0 && mode <= 9 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && iters % 448 == 0, "pipe_bench: arguments");
     const size_t smem = 128 * 128 + 256 * 128 + 64;
     SC_CUDA(cudaFuncSetAttribute(tc::pipe_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SC_CUDA(cudaMemsetAsync(out_dev, 0, 8 * sizeof(long long), stream));

@@ -28,10 +28,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU box
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU box.  Polls with the non-blocking test_wait: try_wait may
+// suspend the thread for an implementation-defined time, which adds its wake-up latency to every pipeline hand-off.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_test_wait(bar, parity)) {
         if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
     }
 }

@@ -6,7 +6,7 @@ import torch
 from scasml_gp_b200 import _lib as lib
 L = lib.load()
 out = torch.zeros(8, dtype=torch.int64, device="cuda")
-iters = 1024
+iters = 448 * 2
 
 
 def run(mode, N=64):
@@ -32,3 +32,10 @@ for mode, name in ((5, "SS"), (6, "TS")):
     for N in (16, 32, 48, 64, 96, 128, 192):
         o = run(mode, N)
         print(f"MMA {name} N={N:3d}: issue {o[1]/o[3]:.1f}  total {o[2]/o[3]:.1f} cyc/instr")
+for mode, name in ((7, "TS + commit/7"), (8, "TS + commit/7 + poll")):
+    for N in (16, 64, 128):
+        o = run(mode, N)
+        print(f"MMA {name} N={N:3d}: issue {o[1]/o[3]:.1f}  total {o[2]/o[3]:.1f} cyc/instr")
+for N in (16, 64, 128):
+    o = run(9, N)
+    print(f"split chunk + TS MMA N={N}: {o[0]/iters:.1f} cyc per chunk/warp ({512*16*iters/o[0]:.2f} pairs/clk/SM); MMA {o[2]/max(o[3],1):.1f} cyc/instr")

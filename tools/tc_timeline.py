@@ -17,15 +17,19 @@ gp.set_right_vector(np.random.default_rng(0).standard_normal(4 * nd + nb) * 0.1)
 xd = _lib.to_device(X)
 R = xd.shape[0]
 lib = _lib.load()
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0     # 1 skip stage-2 MMAs, 2 skip epilogue arithmetic, 4 skip low-half pass
 for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PDE")):
     stamps = torch.zeros(256, dtype=torch.int64, device="cuda")
     scratch = torch.empty(4 * R, dtype=torch.float64, device="cuda")
     for rep in range(2):
-        _lib.check(lib.scasml_debug_tc_timeline(gp._handle, _lib.ptr(xd), R, mode, 300, _lib.ptr(stamps), _lib.ptr(scratch), _lib.stream_ptr()))
+        _lib.check(lib.scasml_debug_tc_timeline(gp._handle, _lib.ptr(xd), R, mode, 300 | (flags << 24), _lib.ptr(stamps), _lib.ptr(scratch), _lib.stream_ptr()))
     torch.cuda.synchronize()
     t = stamps.cpu().numpy().astype(np.int64)
     t0 = t[0]
-    nitem = int(((t[4:] > 0).sum()) // 4)
+    nitem = int(((t[4:244] > 0).sum()) // 4)
+    starts = [t[4 + 4 * w] for w in range(nitem)]
+    period = (starts[-3] - starts[3]) / max(1, nitem - 6) if nitem > 8 else 0
+    print(f"== {name} flags={flags}: steady-state period {period:.0f} cycles/item")
     print(f"== {name}: entry 0, scatter {t[1]-t0}, prologue {t[2]-t0}, exit {t[3]-t0} cycles; items {nitem}")
     for w in range(min(nitem, 44)):
         a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
