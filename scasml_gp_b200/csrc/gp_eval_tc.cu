@@ -186,23 +186,30 @@ __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, i
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
-// Work item = (64-centre tile, kernel class): 14 stage-1 MMAs (N = 64, A = a' x hi | lo from tensor memory) into one of
-// four 64-column S slots, the epilogue turns S into P in place, 12 stage-2 MMAs (A = P from tensor memory) add P C into T.
+// Persistent CTAs (one per SM) loop over 128-point tiles.  Sub-item = (64-centre tile, kernel class); the sub-item stream
 //   u / u + div:  domain tile -> k, ky;      boundary tile -> k
 //   PDE:          domain tile -> k, kx, ky;  boundary tile -> k, kx
-// Four slots decouple the two pipelines: the MMA warp issues stage 1 three items ahead of the epilogue warps, so the
-// barrier round trip (commit -> epilogue -> arrive -> stage 2) is off the critical path (tools/tc_timeline.py).
-// Tensor memory: S/P slots at columns 0, 64, 128, 192; T at 256; A images (hi | lo, 64 columns apart) at 384.
+// is consumed in PAIRS: 14 stage-1 MMAs (N = 128: both sub-items' centre rows, A = a' x hi | lo from tensor memory) into one
+// of two 128-column S slots, the epilogue warps turn S into P in place, 2 x 12 stage-2 MMAs (A = P from tensor memory) add
+// P C into T.  Pairing halves the barrier operations per MMA: every mbarrier wait / tcgen05.commit of the lone issuing
+// thread costs ~100 cycles (tools/tc_timeline.py), which bounds the kernel once the MMAs themselves are cheap.
+// Warp roles: 16 epilogue warps, 1 producer warp (cp.async.bulk rings of centre rows / coefficient images), 1 MMA warp
+// (converged, one elected lane issues), 4 loader warps (the NEXT point tile: a' x = hi + lo in f16 into the staging buffer,
+// K_i, row sums) so the operand prologue overlaps the current tile's main loop.
+// Tensor memory: S/P pair slots at columns 0 and 128; T at 256; A images (hi | lo, 64 columns apart) at 384.
 template <int CLASS> struct Cfg;
 template <> struct Cfg<TC_U>   { static constexpr int NK = 16, NKX = 0,  NKY = 16; };
 template <> struct Cfg<TC_UG>  { static constexpr int NK = 16, NKX = 0,  NKY = 32; };
 template <> struct Cfg<TC_PDE> { static constexpr int NK = 48, NKX = 32, NKY = 48; };
 
 constexpr uint32_t COL_T = 256, COL_A = 384, A_IMG_COLS = 64;
-constexpr int NSLOT = 4;                                             // S/P slots = items in flight
+constexpr int NSLOT = 2;                                             // S/P pair slots
 constexpr uint32_t B1_BLK = TN * 128;                                // one K block of one class: [64 rows x 128 B]
 constexpr int A_PITCH = 240;                                         // staging row pitch (bytes): 16-byte reads of 8 rows hit 8 bank groups
-constexpr int NBAR = 5 * NSLOT + 1;                                  // b1_full b3_full b3_empty s_full p_ready | t_full
+constexpr int NLOAD = 4;                                             // loader warps
+constexpr int NTHREADS_P = (NEPI + 2 + NLOAD) * 32;
+// barriers: b1_full b3_full b3_empty s_full p_ready (NSLOT each) | t_full t_free a_ready stage_full stage_free
+constexpr int NBAR = 5 * NSLOT + 5;
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -220,7 +227,7 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 }
 
 template <int CLASS, int NSTEP>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_P, 1)
 eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode,
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
     using C = Cfg<CLASS>;
@@ -228,25 +235,28 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     constexpr int KB = (NSTEP + 3) / 4;                              // 64-wide K blocks
     constexpr int NT = C::NK + C::NKX + C::NKY;                      // T columns: [k | kx | ky]
     constexpr int NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    constexpr uint32_t B3_SLOT = 2 * NMAX * 128;                     // one class's coefficient images (hi | lo)
+    constexpr uint32_t B3_SUB = 2 * NMAX * 128;                      // one class's coefficient images (hi | lo)
+    constexpr uint32_t B3_SLOT = 2 * B3_SUB;                         // a pair
+    constexpr uint32_t B1_SLOT = KB * 2 * B1_BLK;                    // a pair's centre rows: per K block [sub-item a rows | sub-item b rows]
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
-    constexpr uint32_t B1_SLOT = KB * B1_BLK;                        // one item's centre rows, all K blocks
     uint8_t* sB1 = smem;                                             // NSLOT item slots
     uint8_t* sB3 = sB1 + NSLOT * (size_t)B1_SLOT;                    // NSLOT item slots
-    uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH]; reused at the end
-    uint8_t* sMisc = sStage + 2 * (size_t)TM * A_PITCH;
-    double* Ki = (double*)sMisc;                                     // [128] exp(-a |x|^2 / 2)
-    double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i
+    uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
+    double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
+    double* xchg = feat + TM * TF_COUNT;                             // [3][128][4] partial sums of column groups 1..3
+    double* Ki = xchg + 3 * TM * 4;                                  // [128] exp(-a |x|^2 / 2) of the staged tile
+    double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
     uint64_t* bars = (uint64_t*)(sxs + TM);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
-    const long row0 = (long)blockIdx.x * TM;
-    long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;
+    const long ntiles = (R + TM - 1) / TM;
+    const int nit = (int)((ntiles - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x);   // point tiles of this CTA
+    long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;   // stamps: first tile of that CTA
 #define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
     const uint32_t bar0 = smem_u32(bars);
@@ -255,11 +265,14 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NSLOT + i); };
     auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(3 * NSLOT + i); };
     auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(4 * NSLOT + i); };
-    const uint32_t t_full = bar0 + 8u * (uint32_t)(NBAR - 1);
+    const uint32_t t_full = bar0 + 8u * (uint32_t)(5 * NSLOT), t_free = t_full + 8u, a_ready = t_full + 16u,
+                   stage_full = t_full + 24u, stage_free = t_full + 32u;
 
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(b1_full(i), 1); mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI); }
-        mbar_init(t_full, 1);
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(b1_full(i), 1); mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI);
+        }
+        mbar_init(t_full, 1); mbar_init(t_free, NEPI); mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -268,164 +281,196 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
-    constexpr int nstep = NSTEP;
     constexpr int CPD = PDE ? 3 : 2;                                 // kernel classes of a domain tile
-    const int nitem = CPD * ndom + (CPD - 1) * nbdy;
-    // item w -> (tile, kernel class).  Class order inside a tile: k, (kx,) ky; boundary tiles have no ky class.
-    auto item_of = [&](int w, int& t, int& kc) {
-        if (w < CPD * ndom) {
-            t = w / CPD;
-            const int c = w - t * CPD;
-            kc = PDE ? (c == 0 ? TK_K : (c == 1 ? TK_KX : TK_KY)) : (c == 0 ? TK_K : TK_KY);
-        } else {
-            const int v = w - CPD * ndom;
-            t = ndom + (PDE ? (v >> 1) : v);
-            kc = (PDE && (v & 1)) ? TK_KX : TK_K;
-        }
+    const int nitem = CPD * ndom + (CPD - 1) * nbdy;                 // sub-items per point tile
+    const int npair = (nitem + 1) >> 1;
+    // (tile, class) successor.  Class order inside a centre tile: k, (kx,) ky; boundary tiles have no ky class.
+    auto next_item = [&](int& t, int& kc) {
+        if (kc == TK_K) kc = PDE ? TK_KX : (t < ndom ? TK_KY : TK_K);
+        else if (kc == TK_KX) kc = (t < ndom) ? TK_KY : TK_K;
+        else kc = TK_K;
+        if (kc == TK_K) ++t;
     };
 
     if (warp == NEPI) {
-        // ===== producer: per item, the class's centre rows of every K block (B1 ring) and its coefficient images (B3 ring);
-        // issue order = consumption order of the MMA warp: B1(0..2), then B1(w+3), B3(w) =====
-        // One "full" barrier per item and ring; the centre-row slot of item w is reusable once s_full(w) fired (stage 1 done),
-        // the coefficient slot once the MMA warp committed b3_empty(w).  Issue order = consumption order of the MMA warp.
+        // ===== producer: per item, the class's centre rows (all K blocks) and its coefficient images.  The item stream
+        // simply repeats for every point tile, so the rings run across tile boundaries.  A centre-row slot is reusable once
+        // s_full of its previous item fired (stage 1 done), a coefficient slot once the MMA warp committed b3_empty. =====
         if (lane == 0 && !(st.dbg_flags & 8)) {
-            auto load_b1 = [&](int w) {
-                int t, kc; item_of(w, t, kc);
-                const int s = w % NSLOT;
-                if (w >= NSLOT) mbar_wait(s_full(s), ((w / NSLOT) - 1) & 1);
-                const uint8_t* src = st.b1 + (size_t)t * st.b1_tile_bytes
-                                   + (size_t)(kc == TK_K ? 0 : (kc == TK_KX ? 1 : 2)) * B1_BLK;       // rows [C | Crollinv | Croll]
-                mbar_expect_tx(b1_full(s), B1_SLOT);
+            const int ptotal = nit * npair;
+            int t1 = 0, k1 = TK_K, j1 = 0, t3 = 0, k3 = TK_K, j3 = 0;    // sub-item cursors / pair index inside the point tile
+            int p1 = 0;
+            auto load_b1 = [&]() {
+                const int s = p1 % NSLOT;
+                if (p1 >= NSLOT) mbar_wait(s_full(s), (uint32_t)((p1 / NSLOT) - 1) & 1u);
+                const bool two = 2 * j1 + 1 < nitem;
+                mbar_expect_tx(b1_full(s), (two ? 2u : 1u) * KB * B1_BLK);
+                uint8_t* dst = sB1 + (size_t)s * B1_SLOT;
+                for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
+                    const uint8_t* src = st.b1 + (size_t)t1 * st.b1_tile_bytes
+                                       + (size_t)(k1 == TK_K ? 0 : (k1 == TK_KX ? 1 : 2)) * B1_BLK;   // rows [C | Crollinv | Croll]
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-                    bulk_g2s(smem_u32(sB1 + (size_t)s * B1_SLOT + (size_t)kb * B1_BLK), src + (size_t)kb * (3 * B1_BLK), B1_BLK, b1_full(s));
+                    for (int kb = 0; kb < KB; ++kb)
+                        bulk_g2s(smem_u32(dst + (size_t)kb * 2 * B1_BLK + (size_t)sub * B1_BLK), src + (size_t)kb * (3 * B1_BLK), B1_BLK, b1_full(s));
+                    next_item(t1, k1);
+                }
+                if (++j1 == npair) { j1 = 0; t1 = 0; k1 = TK_K; }
+                ++p1;
             };
-            auto load_b3 = [&](int w) {
-                int t, kc; item_of(w, t, kc);
-                const int s = w % NSLOT;
-                if (w >= NSLOT) mbar_wait(b3_empty(s), ((w / NSLOT) - 1) & 1);
-                const uint32_t off = kc == TK_K ? 0u : (kc == TK_KX ? 2u * C::NK * 128u : 2u * (C::NK + C::NKX) * 128u);
-                const uint32_t bytes = 2u * 128u * (uint32_t)(kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY));
-                mbar_expect_tx(b3_full(s), bytes);
-                bulk_g2s(smem_u32(sB3 + (size_t)s * B3_SLOT), st.b3 + (size_t)t * st.b3_tile_bytes + off, bytes, b3_full(s));
-            };
-            for (int w = 0; w < NSLOT - 1 && w < nitem; ++w) load_b1(w);
-            for (int w = 0; w < nitem; ++w) {
-                if (w + NSLOT - 1 < nitem) load_b1(w + NSLOT - 1);
-                load_b3(w);
+            for (int p = 0; p < ptotal; ++p) {
+                while (p1 < ptotal && p1 < p + NSLOT) load_b1();
+                const int s = p % NSLOT;
+                if (p >= NSLOT) mbar_wait(b3_empty(s), (uint32_t)((p / NSLOT) - 1) & 1u);
+                const bool two = 2 * j3 + 1 < nitem;
+                uint32_t off[2], bytes[2];
+                int tt[2];
+                for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
+                    off[sub] = k3 == TK_K ? 0u : (k3 == TK_KX ? 2u * C::NK * 128u : 2u * (C::NK + C::NKX) * 128u);
+                    bytes[sub] = 2u * 128u * (uint32_t)(k3 == TK_K ? C::NK : (k3 == TK_KX ? C::NKX : C::NKY));
+                    tt[sub] = t3;
+                    next_item(t3, k3);
+                }
+                mbar_expect_tx(b3_full(s), bytes[0] + (two ? bytes[1] : 0u));
+                for (int sub = 0; sub < (two ? 2 : 1); ++sub)
+                    bulk_g2s(smem_u32(sB3 + (size_t)s * B3_SLOT + (size_t)sub * B3_SUB), st.b3 + (size_t)tt[sub] * st.b3_tile_bytes + off[sub],
+                             bytes[sub], b3_full(s));
+                if (++j3 == npair) { j3 = 0; t3 = 0; k3 = TK_K; }
             }
         }
         __syncwarp();
     } else if (warp == NEPI + 1) {
         // ===== MMA issuer: the warp stays converged and one elected lane issues (warp-uniform operands come from uniform
-        // registers; a divergent `if (lane == 0)` block compiles to a per-lane serialisation loop around each MMA) =====
+        // registers; a divergent `if (lane == 0)` block compiles to a per-lane serialisation loop around each MMA).
+        // Every barrier operation of this lone thread costs ~100 cycles of latency (tools/tc_timeline.py), so an item is one
+        // wait + 14 MMAs + one commit in stage 1 and one combined wait + 12 MMAs + one commit in stage 2, and the barrier of
+        // the NEXT batch is probed (non-blocking) in the middle of the current batch, while the MMA queue is full. =====
         const uint32_t el = elect_one();
-        // wait for the A images (epilogue warps stage them into tensor memory; named barrier 2 = epilogue warps + this warp)
-        asm volatile("bar.sync 2, %0;" ::"n"((NEPI + 1) * 32) : "memory");
-        tc_fence_after();
         const uint64_t b1desc0 = make_desc(smem_u32(sB1), 1, 64, 2);
         const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
-        const uint32_t idS = make_idesc(TM, TN);
+        const uint32_t idS2 = make_idesc(TM, 2 * TN), idS1 = make_idesc(TM, TN);
         const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
         const uint32_t aBase = tmem_base + COL_A;
-        bool first_k = true, first_kx = true, first_ky = true;
-        // Every barrier operation of this lone issuing thread costs ~100 cycles of latency (measured, tools/tc_timeline.py), so
-        // an item is one wait + 14 MMAs + one commit in stage 1 and one (combined) wait + 12 MMAs + one commit in stage 2.
-        auto stage1 = [&](int w) {
-            const int s = w % NSLOT;
-            const uint32_t accS = tmem_base + (uint32_t)s * 64u;
-            if (el && w < 60) TC_STAMP(4 + 4 * w);
-            if (!(st.dbg_flags & 8)) mbar_wait(b1_full(s), (w / NSLOT) & 1);
+        const bool nocopy = (st.dbg_flags & 8) != 0;
+        int p1 = 0, p2 = 0;                                          // global pair counters of the two stages
+        bool rdy1 = false, rdy2 = false;                             // early probe results for the next stage-1 / stage-2 batch
+        auto probe1 = [&]() { rdy1 = nocopy || mbar_test_wait(b1_full(p1 % NSLOT), (uint32_t)(p1 / NSLOT) & 1u); };
+        auto probe2 = [&]() {
+            const int s = p2 % NSLOT;
+            const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
+            const bool a = mbar_test_wait(p_ready(s), par);
+            const bool b = nocopy || mbar_test_wait(b3_full(s), par);
+            rdy2 = a && b;
+            if (rdy2) tc_fence_after();                              // hoisted: the MMA queue is full while this executes
+        };
+        for (int it = 0; it < nit; ++it) {
+            const bool stamp = (it == 0);
+            mbar_wait(a_ready, (uint32_t)it & 1u);                   // A images of this point tile are in tensor memory
             tc_fence_after();
-            const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s * B1_SLOT) >> 4);
-            if (el) {
+            bool first_k = true, first_kx = true, first_ky = true;
+            int kc2 = TK_K, t2 = 0;                                  // (tile, class) of the next stage-2 sub-item
+            auto stage1 = [&](int j) {
+                const int s = p1 % NSLOT;
+                const uint32_t accS = tmem_base + (uint32_t)s * 128u;
+                const uint32_t idesc = (2 * j + 1 < nitem) ? idS2 : idS1;
+                if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
+                if (!rdy1 && !nocopy) mbar_wait(b1_full(s), (uint32_t)(p1 / NSLOT) & 1u);   // bulk-copy bytes landed (async proxy)
+                const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s * B1_SLOT) >> 4);
+                ++p1;
+                rdy1 = false;
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                     for (int half = 1; half >= 0; --half) {          // low halves first (tiny terms), then the high halves
+                        if (el) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            if (kb * 4 + ks < NSTEP) {
-                                const uint32_t aa = aBase + (uint32_t)half * A_IMG_COLS + (uint32_t)(kb * 4 + ks) * 8u;
-                                const uint64_t bd = bb + (uint64_t)((kb * B1_BLK + ks * 32) >> 4);
-                                if (kb == 0 && half == 1 && ks == 0) umma_ts<false>(accS, aa, bd, idS);
-                                else umma_ts<true>(accS, aa, bd, idS);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                if (kb * 4 + ks < NSTEP) {
+                                    const uint32_t aa = aBase + (uint32_t)half * A_IMG_COLS + (uint32_t)(kb * 4 + ks) * 8u;
+                                    const uint64_t bd = bb + (uint64_t)((kb * 2 * B1_BLK + ks * 32) >> 4);
+                                    if (kb == 0 && half == 1 && ks == 0) umma_ts<false>(accS, aa, bd, idesc);
+                                    else umma_ts<true>(accS, aa, bd, idesc);
+                                }
                             }
                         }
+                        if (kb == 0 && half == 1) probe2();          // the queue is full: probe the barriers of the next stage-2 batch
                     }
                 }
-                umma_commit(s_full(s));                              // accumulators ready; the centre-row slot is reusable
-            }
-            __syncwarp();
-        };
-        int kc2 = TK_K, t2 = 0;                                      // (tile, class) of the next stage-2 item
-        auto stage2 = [&](int w) {
-            const int s = w % NSLOT;
-            {   // P written over S by all epilogue warps + coefficient images landed: one polling loop for both barriers
-                const uint32_t par = (uint32_t)(w / NSLOT) & 1u;
-                uint32_t spins = 0;
-                bool a = false, b = (st.dbg_flags & 8) != 0;
-                while (true) {
-                    if (!a) a = mbar_test_wait(p_ready(s), par);
-                    if (!b) b = mbar_test_wait(b3_full(s), par);
-                    if (a && b) break;
-                    if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
+                if (el) umma_commit(s_full(s));                      // accumulators ready; the centre-row slot is reusable
+                __syncwarp();
+            };
+            auto stage2 = [&](int j) {
+                const int s = p2 % NSLOT;
+                if (!rdy2) {   // P written over S by all epilogue warps + coefficient images landed: one polling loop for both
+                    const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
+                    uint32_t spins = 0;
+                    bool a = false, b = nocopy;
+                    while (true) {
+                        if (!a) a = mbar_test_wait(p_ready(s), par);
+                        if (!b) b = mbar_test_wait(b3_full(s), par);
+                        if (a && b) break;
+                        if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
+                    }
+                    tc_fence_after();
                 }
-            }
-            tc_fence_after();
-            const uint32_t pbase = tmem_base + (uint32_t)s * 64u;
-            const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT) >> 4);
-            const int kc = kc2;
-            const uint32_t tacc = tmem_base + COL_T + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
-            const uint32_t nrows = kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY);
-            const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
-            const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
-            const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
-            if (el) {
-                if (!(st.dbg_flags & 1)) {
-                    if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
-                    umma_ts<true>(tacc, pbase, clo0, idesc);
-                    umma_ts<true>(tacc, pbase + 8u, b3, idesc);
+                if (j == 0 && it > 0) { mbar_wait(t_free, (uint32_t)(it - 1) & 1u); tc_fence_after(); }   // T of the previous point tile was read
+                ++p2;
+                rdy2 = false;
+                const int nsub = (2 * j + 1 < nitem) ? 2 : 1;
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const uint32_t pbase = tmem_base + (uint32_t)s * 128u + (uint32_t)sub * 64u;
+                    const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT + (uint32_t)sub * B3_SUB) >> 4);
+                    const int kc = kc2;
+                    const uint32_t tacc = tmem_base + COL_T + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
+                    const uint32_t nrows = kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY);
+                    const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
+                    const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
+                    const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
+                    if (el && !(st.dbg_flags & 1)) {
+                        if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
+                        umma_ts<true>(tacc, pbase, clo0, idesc);
+                        umma_ts<true>(tacc, pbase + 8u, b3, idesc);
 #pragma unroll
-                    for (int ks = 1; ks < 4; ++ks) {
-                        umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
-                        umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
-                        umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                        for (int ks = 1; ks < 4; ++ks) {
+                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
+                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                        }
                     }
+                    if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
+                    next_item(t2, kc2);
+                    if (sub == 0 && (j + NSLOT < npair || it + 1 < nit)) probe1();   // probe the centre rows of the next stage-1 batch
                 }
-                umma_commit(b3_empty(s));
-                if (w < 60) TC_STAMP(5 + 4 * w);
+                if (el) { umma_commit(b3_empty(s)); if (stamp && j < 60) TC_STAMP(5 + 4 * j); }
+                __syncwarp();
+            };
+            // stage 2 of pair j is followed by stage 1 of pair j + 2 (same S slot): the big MMAs sit in the queue while this
+            // thread works through the next barrier operations
+            for (int j = 0; j < NSLOT && j < npair; ++j) stage1(j);
+            for (int j = 0; j < npair; ++j) {
+                stage2(j);
+                if (j + NSLOT < npair) stage1(j + NSLOT);
             }
+            if (el) umma_commit(t_full);
             __syncwarp();
-            if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
-            // next item: k, (kx,) ky on domain tiles; k (, kx) on boundary tiles
-            if (kc == TK_K) kc2 = PDE ? TK_KX : (t2 < ndom ? TK_KY : TK_K);
-            else if (kc == TK_KX) kc2 = (t2 < ndom) ? TK_KY : TK_K;
-            else kc2 = TK_K;
-            if (kc2 == TK_K) ++t2;
-        };
-        for (int w = 0; w < NSLOT - 1 && w < nitem; ++w) stage1(w);
-        for (int w = 0; w < nitem; ++w) {
-            if (w + NSLOT - 1 < nitem) stage1(w + NSLOT - 1);
-            stage2(w);
         }
-        if (el) umma_commit(t_full);
-        __syncwarp();
-    } else {
-        // ===== epilogue warps =====
-        // --- prologue: a' x = hi + lo (f16) into the staging buffer, row sums; then into tensor memory (lane = row).
-        {
-            const double ascale = gp.a * 1.4426950408889634;           // a log2(e): S = log2 of exp(a x.y)
-            const int hl = lane & 15, sub = lane >> 4;
-            const int c0 = hl * 8;
-            const bool active = c0 < nstep * 16;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
+    } else if (warp >= NEPI + 2) {
+        // ===== loader warps: stage the NEXT point tile while the current one is in the main loop.
+        // a' x = hi + lo (f16) into the staging buffer, K_i and row sums.  Two rows per warp pass (16 lanes x 8 columns). =====
+        const int lw = warp - (NEPI + 2);
+        const double ascale = gp.a * 1.4426950408889634;             // a log2(e): S = log2 of exp(a x.y)
+        const int hl = lane & 15, sub = lane >> 4;
+        const int c0 = hl * 8;
+        const bool active = c0 < NSTEP * 16;
+        for (int it = 0; it < nit; ++it) {
+            const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
+            if (it > 0) mbar_wait(stage_free, (uint32_t)(it - 1) & 1u);     // the previous tile's images are in tensor memory
+            constexpr int RPW = TM / NLOAD;                          // rows per loader warp
+#pragma unroll 1
+            for (int pass = 0; pass < RPW / 4; ++pass) {
                 double v[2][8];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int r = warp * 8 + (pass * 2 + i) * 2 + sub;
+                    const int r = lw * RPW + (pass * 2 + i) * 2 + sub;
                     const long row = row0 + r;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -435,7 +480,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int r = warp * 8 + (pass * 2 + i) * 2 + sub;
+                    const int r = lw * RPW + (pass * 2 + i) * 2 + sub;
                     double nx = 0.0, sx = 0.0;
                     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -466,92 +511,77 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     if (hl == 0) { Ki[r] = exp(-0.5 * gp.a * nx); sxs[r] = sx; }
                 }
             }
-            if (tid == 0) TC_STAMP(1);
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
-            if (warp < 8) {                                          // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
-                const int img = warp >> 2;
-                const int r = (warp & 3) * 32 + lane;
-                const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
-                const uint32_t taddr = tmem_base + COL_A + (uint32_t)img * A_IMG_COLS + ((uint32_t)((warp & 3) * 32) << 16);
-                for (int ks = 0; ks < nstep; ++ks) {
-                    const uint4 q0 = *(const uint4*)(rowp + ks * 32), q1 = *(const uint4*)(rowp + ks * 32 + 16);
-                    const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                    tmem_st8(taddr + (uint32_t)ks * 8u, wv);
-                }
-                tmem_st_wait();
-            }
-            tc_fence_before();
-            asm volatile("bar.sync 2, %0;" ::"n"((NEPI + 1) * 32) : "memory");
-            if (tid == 0) TC_STAMP(2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
+            if (it == 0 && lw == 0 && lane == 0) TC_STAMP(1);
         }
-        // --- main loop: S -> P in place.  thread <-> (point row r, centres [16 cg, 16 cg + 16) of the tile)
+    } else {
+        // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
         const int r = (warp & 3) * 32 + lane;
         const int cg = warp >> 2;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const bool skip_math = (st.dbg_flags & 2) != 0;
-        for (int w = 0; w < nitem; ++w) {
-            const int s = w % NSLOT;
-            mbar_wait(s_full(s), (w / NSLOT) & 1);
-            tc_fence_after();
-            if (tid == 0 && w < 60) TC_STAMP(6 + 4 * w);
-            const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 64u + (uint32_t)cg * 16u;
-            if (!skip_math) {
-                float v[16];
-                tmem_ld16(base, v);
-                tmem_ld_wait();
-                uint32_t hi[8], lo[8];
+        long g = 0;                                                  // global item counter
+        double ki_cur = 0.0, sx_cur = 0.0, ki_prev = 0.0, sx_prev = 0.0;
+        for (int it = 0; it <= nit; ++it) {
+            ki_prev = ki_cur; sx_prev = sx_cur;
+            if (it < nit) {
+                // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
+                // have completed (this warp saw s_full of its last item), so the images can be overwritten.
+                mbar_wait(stage_full, (uint32_t)it & 1u);
+                if (cg == 0) { ki_cur = Ki[r]; sx_cur = sxs[r]; }
+                if (warp < 8) {                                      // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
+                    const int img = warp >> 2;
+                    const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
+                    const uint32_t taddr = tmem_base + COL_A + (uint32_t)img * A_IMG_COLS + lane_addr;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float p0 = ex2f(v[2 * i]), p1 = ex2f(v[2 * i + 1]);
-                    hi[i] = pack_f16x2_sat(p0, p1);
-                    const float2 hf = __half22float2(*(const __half2*)&hi[i]);
-                    lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                    for (int ks = 0; ks < NSTEP; ++ks) {
+                        const uint4 q0 = *(const uint4*)(rowp + ks * 32), q1 = *(const uint4*)(rowp + ks * 32 + 16);
+                        const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        tmem_st8(taddr + (uint32_t)ks * 8u, wv);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(stage_free); }
                 }
-                tmem_st8(base, hi);
-                tmem_st8(base + 8u, lo);
-                tmem_st_wait();
+                if (it == 0 && tid == 0) TC_STAMP(2);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (tid == 0 && w < 60) TC_STAMP(7 + 4 * w);
-            if (lane == 0) mbar_arrive(p_ready(s));
-        }
-        // --- final contraction: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
-        mbar_wait(t_full, 0);
-        tc_fence_after();
-        double* feat = (double*)sStage;                              // the staging buffer is dead: [128][TF_COUNT] features
-        double* xchg = feat + TM * TF_COUNT;                         // [3][128][4] partial sums of column groups 1..3
-        if (cg == 0) {
-            const long row = row0 + r;
-            const bool ok = row < R;
-            const double* xr = X + row * (long)D;
-            double* F = feat + r * TF_COUNT;
-            const double sx = sxs[r];
-            const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
-            double P2 = 0.0, R2 = 0.0;
+            if (it > 0) {
+                // --- final contraction of tile it - 1: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
+                const long row0 = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM;
+                const long row = row0 + r;
+                const bool ok = row < R;
+                if (cg == 0) {
+                    const double* xr = X + row * (long)D;
+                    double* F = feat + r * TF_COUNT;
+                    const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+                    double P2 = 0.0, R2 = 0.0;
 #pragma unroll
-            for (int m = 0; m < MC_IDX; ++m) {
-                const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                F[TF_XI + m] = xi; F[TF_XR + m] = xir;
-                P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
-            }
-            F[TF_ONE] = 1.0; F[TF_SX] = sx; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
-        {
-            constexpr int NPER = NT / 4;                             // T columns per column group
-            const double* F = feat + r * TF_COUNT;
-            double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
-            const bool have_ky = ndom > 0;
+                    for (int m = 0; m < MC_IDX; ++m) {
+                        const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                        F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                        P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+                    }
+                    F[TF_ONE] = 1.0; F[TF_SX] = sx_prev; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx_prev - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+                }
+                mbar_wait(t_full, (uint32_t)(it - 1) & 1u);         // all stage-2 MMAs of the tile have completed
+                tc_fence_after();
+                constexpr int NPER = NT / 4;                         // T columns per column group
+                float tv[NPER];
 #pragma unroll
-            for (int c0 = 0; c0 < NPER; c0 += 4) {
-                const int col0 = cg * NPER + c0;
-                float tv[4];
-                tmem_ld4(tmem_base + lane_addr + COL_T + (uint32_t)col0, tv);
+                for (int c4 = 0; c4 < NPER; c4 += 4) tmem_ld4(tmem_base + lane_addr + COL_T + (uint32_t)(cg * NPER + c4), tv + c4);
                 tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_free);                  // T may be overwritten by the next tile's stage 2
+                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // features visible
+                const double* F = feat + r * TF_COUNT;
+                double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
+                const bool have_ky = ndom > 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int col = col0 + i;
+                for (int i = 0; i < NPER; ++i) {
+                    const int col = cg * NPER + i;
                     const TcColDesc dsc = st.desc[col];
                     const bool skip = dsc.out == TO_PAD || (!have_ky && col >= C::NK + C::NKX);
                     const double term = skip ? 0.0 : F[dsc.f1] * F[dsc.f2] * ((double)tv[i] * dsc.inv_scale);
@@ -560,36 +590,72 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     aL += (dsc.out == TO_L) ? term : 0.0;
                     aT += (dsc.out == TO_T) ? term : 0.0;
                 }
-            }
-            if (cg > 0) {
-                double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
-                p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
-            if (cg == 0) {
-                const long row = row0 + r;
-                if (row < R) {
+                if (cg > 0) {
+                    double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
+                    p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+                if (cg == 0 && ok) {
 #pragma unroll
                     for (int g2 = 1; g2 < 4; ++g2) {
                         const double* p = xchg + ((size_t)(g2 - 1) * TM + r) * 4;
                         aU += p[0]; aG += p[1]; aL += p[2]; aT += p[3];
                     }
-                    const double ki = Ki[r];
+                    const double ki = ki_prev;
                     const double u = ki * aU;
                     if (CLASS == TC_U) {
-                        const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));          // equations.py:259
+                        const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));              // equations.py:259
                         out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
                     } else if (CLASS == TC_UG) {
                         out0[row] = u;
                         out1[row] = ki * aG;
                     } else {
-                        const double g = ki * aG, l = ki * aL, tt = ki * aT;
+                        const double gg = ki * aG, l = ki * aL, tt = ki * aT;
                         const double s2 = gp.sig2;
-                        out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * g + 0.5 * s2 * l;   // GP.py:767-768
-                        if (out1) out1[row] = g;
+                        out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * gg + 0.5 * s2 * l;   // GP.py:767-768
+                        if (out1) out1[row] = gg;
                         if (out2) out2[row] = l;
                         if (out3) out3[row] = tt;
                     }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // feat / xchg reusable
+            }
+            if (it < nit) {
+                // --- main loop: S -> P in place, one pair (two sub-items, 2 x 16 columns per thread) per barrier round trip
+                const bool stamp = (it == 0);
+                for (int j = 0; j < npair; ++j, ++g) {
+                    const int s = (int)(g % NSLOT);
+                    const bool two = 2 * j + 1 < nitem;
+                    mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
+                    tc_fence_after();
+                    if (tid == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
+                    const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + (uint32_t)cg * 16u;
+                    if (!skip_math) {
+                        float v[2][16];
+                        tmem_ld16(base, v[0]);
+                        if (two) tmem_ld16(base + 64u, v[1]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (c == 0 || two) {
+                                uint32_t hi[8], lo[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float p0 = ex2f(v[c][2 * i]), p1 = ex2f(v[c][2 * i + 1]);
+                                    hi[i] = pack_f16x2_sat(p0, p1);
+                                    const float2 hf = __half22float2(*(const __half2*)&hi[i]);
+                                    lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                                }
+                                tmem_st8(base + (uint32_t)c * 64u, hi);
+                                tmem_st8(base + (uint32_t)c * 64u + 8u, lo);
+                            }
+                        }
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (tid == 0 && stamp && j < 60) TC_STAMP(7 + 4 * j);
+                    if (lane == 0) mbar_arrive(p_ready(s));
                 }
             }
         }
@@ -605,20 +671,26 @@ template <int CLASS, int NSTEP>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    return NSLOT * (size_t)(((NSTEP + 3) / 4) * B1_BLK) + NSLOT * (2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH + 2 * TM * 8 + NBAR * 8 + 16;
+    return NSLOT * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
+           + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8 + 2 * TM * 8 + NBAR * 8 + 16;
 }
 
 template <int CLASS, int NSTEP>
 static int launch(const GpView& gp, const TcDev& st, const double* X, long R, int mode,
                   double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
     static bool configured = false;
+    static int nsm = 0;
     const size_t smem = smem_bytes<CLASS, NSTEP>();
-    static_assert(2 * TM * A_PITCH >= (int)(TM * TF_COUNT * 8 + 3 * TM * 4 * 8), "feature / exchange buffers alias the staging buffer");
     if (!configured) {
         SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        SC_CUDA(cudaGetDevice(&dev));
+        SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    eval_tc_kernel<CLASS, NSTEP><<<(unsigned)cdiv(R, TM), NTHREADS, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
+    const long ntiles = cdiv(R, TM);
+    const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);   // persistent: one CTA per SM
+    eval_tc_kernel<CLASS, NSTEP><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
     SC_LAUNCH_CHECK();
     return OK;
 }

@@ -34,11 +34,12 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU box.  Polls with the non-blocking test_wait: try_wait may
-// suspend the thread for an implementation-defined time, which adds its wake-up latency to every pipeline hand-off.
+// bounded wait: a protocol bug traps instead of hanging the GPU box.  try_wait suspends the warp in hardware while the phase
+// is pending, so waiting warps do not take issue slots from the (latency-bound) MMA-issuing warp on the same scheduler;
+// mbar_test_wait is the non-blocking probe.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_test_wait(bar, parity)) {
+    while (!mbar_try_wait(bar, parity)) {
         if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
     }
 }

@@ -22,7 +22,7 @@ for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PD
     stamps = torch.zeros(256, dtype=torch.int64, device="cuda")
     scratch = torch.empty(4 * R, dtype=torch.float64, device="cuda")
     for rep in range(2):
-        _lib.check(lib.scasml_debug_tc_timeline(gp._handle, _lib.ptr(xd), R, mode, 300 | (flags << 24), _lib.ptr(stamps), _lib.ptr(scratch), _lib.stream_ptr()))
+        _lib.check(lib.scasml_debug_tc_timeline(gp._handle, _lib.ptr(xd), R, mode, 100 | (flags << 24), _lib.ptr(stamps), _lib.ptr(scratch), _lib.stream_ptr()))
     torch.cuda.synchronize()
     t = stamps.cpu().numpy().astype(np.int64)
     t0 = t[0]
