@@ -192,8 +192,8 @@ def main():
     eq = Grad_Dependent_Nonlinear(d + 1)
     gp = GP_Grad_Dependent_Nonlinear(eq, idx_set=idx)
     route = args.route
-    if route == "auto":
-        route = "tc" if os.environ.get("SCASML_TC_DEFAULT", "0") == "1" else "f64"
+    if route == "auto":     # the tcgen05 route is the product path wherever it applies (d <= 126); FP64 is the parity anchor
+        route = "tc" if d + 2 <= 128 else "f64"
     gp.route = _lib.ROUTE_TC if route == "tc" else _lib.ROUTE_F64
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -202,6 +202,7 @@ def main():
     fit_ms = 1e3 * (time.perf_counter() - t0)
 
     solver = (ScaSML_full_history if fh else ScaSML)(eq, gp)
+    solver.route = gp.route
     solver.quadrature = args.quadrature
     solver.distributed = world > 1
     x_dev = _lib.to_device(X)
@@ -279,7 +280,8 @@ def main():
     if route == "tc":
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_note = "measured cuBLAS bf16 sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PFLOP/s sustained"
-        flop_note = "kind::f16 tcgen05, x split hi+lo (2 MMA passes); credited flops are the algorithmic 2(d+1) per pair-distance"
+        flop_note = ("kind::f16 tcgen05, two chained GEMMs, operands split hi+lo in f16 (2 distance passes, 3 coefficient products); "
+                     "credited flops are the algorithmic 2(d+1) per pair-distance only")
     else:
         # FP64 route: the governing pipe is the FP64 FMA pipe; measure its peak here with a torch fp64 GEMM
         a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
@@ -294,15 +296,19 @@ def main():
         peak = 3 * 2 * 4096 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
         peak_note = "FP64 route: cuBLAS fp64 4096^3 GEMM measured in this run (MEASURED_PEAKS.json has no fp64 figure)"
         flop_note = "FP64 FMA pipe (SIMT contraction); credited flops are the algorithmic 2(d+1) per pair-distance"
+    # DRAM traffic of the evaluation launches: ncu --set full on one launch (profiles/r1_ncu_eval_tc.md) measured
+    # dram__bytes_read + write = 819 B per evaluated point (algorithmic: 808 B point row + 8..32 B of outputs)
+    traffic = 819.0 * tstats["eval_points_total"] / max(tstats["eval_launches"], 1) if route == "tc" else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak,
-                "traffic": None, "kernel": "fused surrogate evaluation (gp_eval*.cu)", "peak_source": peak_note,
+                "traffic": traffic, "traffic_note": "bytes per evaluation launch (mean): 819 B/point from the ncu capture in profiles/ x points per launch",
+                "kernel": "fused surrogate evaluation (gp_eval*.cu)", "peak_source": peak_note,
                 "note": flop_note, "eval_share_of_step": tstats["eval_time_ns"] / max(
                     tstats["eval_time_ns"] + tstats["sample_time_ns"] + tstats["reduce_time_ns"], 1),
                 "eval_ms": 1e-6 * tstats["eval_time_ns"], "sample_ms": 1e-6 * tstats["sample_time_ns"],
                 "reduce_ms": 1e-6 * tstats["reduce_time_ns"], "eval_launches": tstats["eval_launches"]}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         nb, dt, s = cpu_oracle_rate(cfg, dom, bdy, X, gp.right_vector[:, 0], idx, args.quadrature, args.cpu_seconds)
         cpu = {"value": _exec_sp(s, nb) / dt, "unit": "sample-points/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{nb} test points of the same workload, {dt:.1f} s (NumPy+OpenBLAS oracle, all host threads)"}
@@ -310,7 +316,7 @@ def main():
     D = d + 1
     line = {"metric": "ScaSML correction sample-points/s", "value": value, "unit": "sample-points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if route == "f64" else "f16x2->f32 (tcgen05) + f64 epilogue sums",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if route == "f64" else "f16 (split operands, fp32 tensor-core accumulate, f64 final contraction)",
             "data": "synthetic", "config": dict(config, route=route),
             "reference_equivalent_value": ref_equiv, "fit_ms": fit_ms, "newton_steps": gp.newton_steps,
             "finite_fraction": finite,

@@ -335,7 +335,14 @@ __device__ __forceinline__ uint32_t read_chunk(const uint4* buf, unsigned long l
     return (uint32_t)((const unsigned short*)buf)[(int)(f - ((fstart >> 3) << 3))];
 }
 
-// Monte-Carlo means of one level: terminal part + all step sets + clip (solvers/ScaSML.py:211-215,252-284)
+// Monte-Carlo means of one level: terminal part + all step sets + clip (solvers/ScaSML.py:211-215,252-284).
+// One warp per parent row.  The Brownian increments are not regenerated: a sampled point carries them,
+//   N = (X_T - x - mu (T-t)) / (sigma sqrt(T-t)),    W_k = (X_k - x - mu (t_k - t)) / sigma      (ScaSML.py:190-194,228-233)
+// so  z_j = sum_p c_p X_pj - x_j sum_p c_p - sum_p c_p drift_p  is a weighted row sum of the level's point buffer.
+// The warp works in chunks of 32 sample points: every lane computes the scalar weight of ONE point (its loads of the
+// evaluation outputs and child results are 32 independent requests), then the weights are broadcast with shuffles and the
+// point rows are streamed, four rows in flight per lane.  Degenerate steps (a sampled point equal to its parent: T == t, or
+// tau == 0 in the full-history variant) fall back to regenerating the Philox normals.
 template <int JCH>
 __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
     __shared__ uint4 wbuf_all[4][4 * JCH + 3];
@@ -351,51 +358,99 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
     const double t = x[d], T = lv.T, Tt = T - t;
     const PhiloxKey kT = make_key(0u, 0u, lv.seed);
     const long long world = lv.world, rank = lv.rank;
+    const double sig = lv.sigma;
 
     double zs = 0.0, uacc = 0.0;
     const bool top = (lv.out_uz != nullptr);
     // coordinates are processed in passes of 32*JCH so the per-lane accumulators stay in registers
     for (int jpass = 0; jpass < d; jpass += 32 * JCH) {
-    double zacc[JCH];
+    double zacc[JCH], zdir[JCH];                   // weighted row sums; directly accumulated (fallback) terms
 #pragma unroll
-    for (int i = 0; i < JCH; ++i) zacc[i] = 0.0;
-    uacc = 0.0;
+    for (int i = 0; i < JCH; ++i) { zacc[i] = 0.0; zdir[i] = 0.0; }
+    double Sc = 0.0, Sd = 0.0, ul = 0.0;           // sum of weights, sum of weight * drift (warp-uniform); per-lane part of u
+    const int cnt = (d - jpass < 32 * JCH) ? (d - jpass) : 32 * JCH;
 
-    {   // terminal condition
+    // stream the rows of a chunk: weight cw (0 for inactive lanes) and point index pt live in the lanes
+    auto stream_rows = [&](int n, double cw, long long pt) {
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+            double ci[4]; const double* xp[4]; double v[4][JCH];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { ci[u] = __shfl_sync(0xffffffffu, cw, i + u); xp[u] = lv.P + __shfl_sync(0xffffffffu, pt, i + u) * D; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; v[u][q] = (j < d) ? __ldg(xp[u] + j) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < JCH; ++q) zacc[q] = fma(ci[u], v[u][q], zacc[q]);
+        }
+        for (; i < n; ++i) {
+            const double ci = __shfl_sync(0xffffffffu, cw, i);
+            const double* xp = lv.P + __shfl_sync(0xffffffffu, pt, i) * D;
+#pragma unroll
+            for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; if (j < d) zacc[q] = fma(ci, __ldg(xp + j), zacc[q]); }
+        }
+    };
+    // fallback for the lanes flagged in `mask`: z_j += w * N_j with regenerated normals of flat index base f0
+    auto direct_normals = [&](unsigned mask, double w, unsigned long long f0, PhiloxKey key) {
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const double wi = __shfl_sync(0xffffffffu, w, src);
+            const unsigned long long f0i = __shfl_sync(0xffffffffu, f0, src);
+            const unsigned long long fs = f0i + (unsigned long long)jpass;
+            fill_chunks(wbuf, fs, cnt, key, lane);
+#pragma unroll
+            for (int q = 0; q < JCH; ++q) {
+                const int j = jpass + lane + 32 * q;
+                if (j < d) zdir[q] = fma(wi, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0i + j)), zdir[q]);
+            }
+        }
+    };
+
+    {   // terminal condition: u = mean g, z = mean(g N) / delta0
         const int MCg = lv.MCg;
         const long long s_lo = ceil_div_pos(R * MCg - rank, world), s_hi = ceil_div_pos((R + 1) * MCg - rank, world);
-        for (long long s = s_lo; s < s_hi; ++s) {
-            const int m = (int)(rank + world * s - R * MCg);
-            const double gt = lv.ev0[lv.term_off + s];
-            const unsigned long long f0 = (unsigned long long)(gidrow * MCg + m) * (unsigned long long)d;
-            const unsigned long long fs = f0 + (unsigned long long)jpass;
-            const int cnt = (d - jpass < 32 * JCH) ? (d - jpass) : 32 * JCH;
-            fill_chunks(wbuf, fs, cnt, kT, lane);
-#pragma unroll
-            for (int i = 0; i < JCH; ++i) {
-                const int j = jpass + lane + 32 * i;
-                if (j < d) zacc[i] = fma(gt, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
-            }
-            uacc += gt;
-        }
         const double delta0 = (lv.variant == 0) ? (Tt + 1e-6) : Tt;    // ScaSML.py:213 vs ScaSML_full_history.py:133
-        uacc = uacc / MCg;
+        const double sqT = sqrt(Tt), driftT = lv.mu * Tt;
+        const double scale = 1.0 / ((double)MCg * delta0);
+        const double invT = scale / (sig * sqT);
+        for (long long base = s_lo; base < s_hi; base += 32) {
+            const long long sidx = base + lane;
+            const bool valid = sidx < s_hi;
+            const double gt = valid ? lv.ev0[lv.term_off + sidx] : 0.0;
+            ul += gt / MCg;
+            const int n = (int)((s_hi - base < 32) ? (s_hi - base) : 32);
+            if (sqT > 0.0) {
+                const double cw = gt * invT;
+                double csum = cw;
+                for (int o = 16; o >= 1; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+                Sc += csum; Sd += csum * driftT;
+                stream_rows(n, cw, lv.term_off + sidx);
+            } else {
+                const int m = (int)(rank + world * sidx - R * MCg);
+                direct_normals(__ballot_sync(0xffffffffu, valid), gt,
+                               (unsigned long long)(gidrow * MCg + m) * (unsigned long long)d, kT);
+            }
+        }
+        // sum first, scale afterwards: with delta0 == 0 (full history at t == T) the reference's mean(g N) / 0 is +-inf, not NaN
+        if (!(sqT > 0.0)) {
 #pragma unroll
-        for (int i = 0; i < JCH; ++i) zacc[i] = zacc[i] / MCg / delta0;
+            for (int q = 0; q < JCH; ++q) zdir[q] *= scale;
+        }
     }
 
     double delta = Tt + 1e-6;                  // running delta_t of solvers/MLP.py (stale-delta quirk)
-    const double sig = lv.sigma;
     for (int l = 0; l < L; ++l) {
         const int q = lv.q[l], MCf = lv.MCf[l];
-        double sqk[MAX_Q], cu[MAX_Q], ca[MAX_Q], cs[MAX_Q];
+        double drk[MAX_Q], cu[MAX_Q], ca[MAX_Q], cs[MAX_Q];
         if (lv.variant == 0) {
-            double tprev = t;
             for (int k = 0; k < q; ++k) {
                 const int lk = l * MAX_Q + k;
                 const double tk = cloc_of(T, t, lv.cnode[lk]);
-                sqk[k] = sqrt(__dsub_rn(tk, tprev));
-                tprev = tk;
+                drk[k] = lv.mu * (tk - t);                          // accumulated drift of the path up to node k
                 const double wk = wloc_of(T, t, lv.wnode[lk]);
                 const double dnew = (tk - t) + 1e-6;
                 const double dadd = lv.stale_delta ? delta : dnew;
@@ -407,25 +462,20 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
         }
         if (!lv.scasml && l == 0) continue;       // MLP: f(x, 0, 0) = 0 at level 0, nothing to add (solvers/MLP.py:243)
         const long long s_lo = ceil_div_pos(R * MCf - rank, world), s_hi = ceil_div_pos((R + 1) * MCf - rank, world);
-        for (long long s = s_lo; s < s_hi; ++s) {
-            const int m = (int)(rank + world * s - R * MCf);
+        const long long ne = (s_hi - s_lo) * q;                    // sample points of this row in step set l: (sample, node)
+        for (long long base = 0; base < ne; base += 32) {
+            const long long e = base + lane;
+            const bool valid = e < ne;
+            const long long si = valid ? e / q : 0;
+            const int k = valid ? (int)(e - si * q) : 0;
+            const long long sidx = s_lo + si;
+            const int lk = l * MAX_Q + k;
+            const long long pt = lv.set_off[lk] + sidx;
+            const int m = (int)(rank + world * sidx - R * MCf);
             const long long pgid = gidrow * MCf + m;
-            const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
-            const unsigned long long fs = f0 + (unsigned long long)jpass;
-            const int cnt = (d - jpass < 32 * JCH) ? (d - jpass) : 32 * JCH;
-            const long long crow = s - c.rowbase * MCf;            // row of this sample inside the child calls
-            double W[JCH];
-#pragma unroll
-            for (int i = 0; i < JCH; ++i) W[i] = 0.0;
-            double dsq = 1.0;
-            if (lv.variant == 1) {
-                const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
-                dsq = sqrt(tau * Tt + 1e-6);                       // ScaSML_full_history.py:169
-            }
-            for (int k = 0; k < q; ++k) {
-                const int lk = l * MAX_Q + k;
-                const long long pt = lv.set_off[lk] + s;
-                double y1 = 0.0, y2 = 0.0;
+            const long long crow = sidx - c.rowbase * MCf;        // row of this sample inside the child calls
+            double y1 = 0.0, y2 = 0.0;
+            if (valid) {
                 if (l >= 1) {
                     double uh = 0.0, sG = 0.0;
                     if (lv.scasml) { uh = lv.ev0[pt]; sG = sig * lv.ev1[pt]; }
@@ -438,40 +488,44 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
                 } else if (lv.scasml) {
                     y1 = lv.ev0[pt];                                 // PDE residual of the surrogate (ScaSML.py:275)
                 }
-                if (lv.variant == 0) {
-                    uacc += cu[k] * (y1 - y2);
-                    const double yc = y1 * ca[k] - y2 * cs[k];
-                    const PhiloxKey key = make_key(c.key[lk], 1u, lv.seed);
-                    fill_chunks(wbuf, fs, cnt, key, lane);
-#pragma unroll
-                    for (int i = 0; i < JCH; ++i) {
-                        const int j = jpass + lane + 32 * i;
-                        if (j < d) {
-                            W[i] = fma(sqk[k], chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), W[i]);
-                            zacc[i] = fma(yc, W[i], zacc[i]);
-                        }
-                    }
-                } else {
-                    const double yc = Tt * (y1 - y2) / MCf;
-                    uacc += yc;
-                    const double yz = yc / dsq;
-                    fill_chunks(wbuf, fs, cnt, kT, lane);
-#pragma unroll
-                    for (int i = 0; i < JCH; ++i) {
-                        const int j = jpass + lane + 32 * i;
-                        if (j < d) zacc[i] = fma(yz, chunk_to_normal(lv.ntab, read_chunk(wbuf, fs, f0 + j)), zacc[i]);
-                    }
-                }
             }
+            double cw = 0.0, dr = 0.0;
+            unsigned degenerate = 0u;
+            double wdir = 0.0;
+            if (lv.variant == 0) {
+                if (valid) {
+                    ul += cu[k] * (y1 - y2);
+                    cw = (y1 * ca[k] - y2 * cs[k]) / sig;            // z += (y1 / delta_a - y2 / delta_s) w_k / MC_f * W_k
+                    dr = drk[k];
+                }
+            } else {
+                const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
+                const double steps = tau * Tt;
+                const double yc = valid ? Tt * (y1 - y2) / MCf : 0.0;
+                ul += yc;
+                const double yz = yc / sqrt(steps + 1e-6);           // ScaSML_full_history.py:169
+                const double sqs = sqrt(steps);
+                if (sqs > 0.0) { cw = yz / (sig * sqs); dr = lv.mu * steps; }     // N = (X - x - mu steps) / (sigma sqrt(steps))
+                else { wdir = yz; degenerate = valid ? 1u : 0u; }
+            }
+            double csum = cw, dsum = cw * dr;
+            for (int o = 16; o >= 1; o >>= 1) { csum += __shfl_xor_sync(0xffffffffu, csum, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o); }
+            Sc += csum; Sd += dsum;
+            const int n = (int)((ne - base < 32) ? (ne - base) : 32);
+            stream_rows(n, cw, pt);
+            const unsigned dmask = __ballot_sync(0xffffffffu, degenerate != 0u);
+            if (dmask) direct_normals(dmask, wdir, (unsigned long long)pgid * (unsigned long long)d, kT);
         }
     }
 
     // clip / cast / row sum (solvers/ScaSML.py:281-284)
+    for (int o = 16; o >= 1; o >>= 1) ul += __shfl_xor_sync(0xffffffffu, ul, o);
+    uacc = ul;
 #pragma unroll
     for (int i = 0; i < JCH; ++i) {
         const int j = jpass + lane + 32 * i;
         if (j < d) {
-            double z = zacc[i];
+            double z = (zacc[i] - x[j] * Sc - Sd) + zdir[i];
             if (!lv.partial) {
                 z = clip_keep_nan(z, lv.clip);
                 if (lv.cast_levels && !top) z = round_f16(z);

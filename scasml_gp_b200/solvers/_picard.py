@@ -86,7 +86,7 @@ class PicardSolverBase(object):
     variant = 0                 # 0 quadrature, 1 full history
     scasml = False              # defect form with the surrogate
     stale_delta = False         # solvers/MLP.py:201,249,270
-    route = None                # None: follow GP.route ; else ROUTE_F64 / ROUTE_TC
+    route = None                # None: tcgen05 route for the sampled points when the GP supports it (d <= 126), else FP64
     quadrature = "reference"    # "reference" (bug-compatible lgwt) or "gauss_legendre" (flagged deviation)
     cast_levels = False         # round inner uz_solve returns to float16 like solvers/ScaSML.py:284
     seed = 0
@@ -179,10 +179,12 @@ class PicardSolverBase(object):
         _lib.ensure_normal_table()
         B, D = x_dev.shape
         rank, world, dist = self._dist()
-        route = self.route if self.route is not None else (getattr(self.GP, "route", _lib.ROUTE_F64) if self.scasml else _lib.ROUTE_F64)
         gp_handle = self.GP._handle if self.scasml else C.c_void_p(0)
         if self.scasml:
             self.GP._require_fit()
+        route = self.route
+        if route is None:     # the top-level u_hat(x) of u_solve always goes through GP.predict (GP.route, FP64 by default)
+            route = _lib.ROUTE_TC if (self.scasml and lib.scasml_gp_tc_supported(gp_handle) == 1) else _lib.ROUTE_F64
         out = torch.empty((B, D), dtype=torch.float64, device="cuda")
         p = self._params(n, rho, M, rank, world)
         # batch over test points so the level buffers fit the workspace budget

@@ -16,6 +16,18 @@ from oracle.gp import GPOracle
 from oracle.solvers import (MLPFullHistoryOracle, MLPOracle, ScaSMLFullHistoryOracle, ScaSMLOracle)
 
 
+@pytest.fixture(autouse=True)
+def _fp64_route_for_this_module():
+    """This module checks the FP64 parity-anchor route against the oracle at 1e-9..1e-10; the solvers' default for the
+    sampled points is the tcgen05 route, which has its own (north-star tolerance) tests in test_gpu_tc.py."""
+    from scasml_gp_b200 import _lib
+    from scasml_gp_b200.solvers._picard import PicardSolverBase
+    old = PicardSolverBase.route
+    PicardSolverBase.route = _lib.ROUTE_F64
+    yield
+    PicardSolverBase.route = old
+
+
 def _product():
     import torch
     from scasml_gp_b200 import _lib
@@ -193,6 +205,34 @@ def test_scasml_quadrature_parity(small, n):
     first = prod.last_raw.copy()
     _check_solver(prod, orac, (n, n, X), (n, n, X), X, exact)
     assert not np.array_equal(first, prod.last_raw)
+
+
+def test_degenerate_steps_fall_back_to_regenerated_normals(small):
+    """The reduction recovers the Brownian increments from the sampled points; when a point equals its parent (test point
+    at the terminal time T, so every step has zero length) it must regenerate the Philox normals instead: the terminal
+    z = mean(g N) / (T - t + 1e-6) of solvers/ScaSML.py:211-215 and the full-history y N / sqrt(step + 1e-6) still need N."""
+    F, P = small, small.P
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(14, 4)
+    X[::2, -1] = F.eq_o.T                                  # every other test point sits at the terminal time
+    exact = F.eq_o.exact_solution(X)
+    prod, orac = P["ScaSML"](F.eq, F.gp), ScaSMLOracle(F.eq_o, F.gp_o, cast=False)
+    prod.quadrature = "gauss_legendre"
+    orac.true_gl = True
+    prod.uz_solve(2, 2, X)
+    orac.uz_solve(2, 2, X)
+    np.testing.assert_allclose(prod.last_raw, orac.last_raw, rtol=1e-8, atol=1e-11)
+    assert np.all(np.isfinite(prod.last_raw)) and np.abs(prod.last_raw[::2, 1:]).max() > 0
+    prod, orac = P["ScaSMLfh"](F.eq, F.gp), ScaSMLFullHistoryOracle(F.eq_o, F.gp_o, cast=False)
+    prod.uz_solve(2, None, X, 3)
+    orac.uz_solve(2, None, X, M=3)
+    np.testing.assert_allclose(prod.last_raw, orac.last_raw, rtol=1e-8, atol=1e-11)
+    prod, orac = P["MLP"](F.eq), MLPOracle(F.eq_o, cast=False)
+    prod.quadrature = "gauss_legendre"
+    orac.true_gl = True
+    prod.uz_solve(2, 2, X)
+    orac.uz_solve(2, 2, X)
+    np.testing.assert_allclose(prod.last_raw, orac.last_raw, rtol=1e-8, atol=1e-11)
 
 
 def test_scasml_reference_tables_nan_semantics(small):
