@@ -247,7 +247,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
     double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
     double* xchg = feat + TM * TF_COUNT;                             // [3][128][4] partial sums of column groups 1..3
-    double* Ki = xchg + 3 * TM * 4;                                  // [128] exp(-a |x|^2 / 2) of the staged tile
+    TcColDesc* sdesc = (TcColDesc*)(xchg + 3 * TM * 4);              // [TC_MAXCOL] column table (f1, f2, output, 1 / scale)
+    double* Ki = (double*)(sdesc + TC_MAXCOL);                       // [128] exp(-a |x|^2 / 2) of the staged tile
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
     uint64_t* bars = (uint64_t*)(sxs + TM);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
@@ -276,8 +277,13 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int c = tid; c < TC_MAXCOL; c += NTHREADS_P) {              // column table -> shared memory (read by every final contraction)
+        TcColDesc dsc = st.desc[c < NT ? c : 0];
+        if (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX)) { dsc.out = TO_PAD; dsc.f1 = 0; dsc.f2 = 0; dsc.inv_scale = 0.0; }
+        sdesc[c] = dsc;
+    }
     tc_fence_before();
-    __syncthreads();                                                 // TMEM base address + barriers visible
+    __syncthreads();                                                 // TMEM base address + barriers + column table visible
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
@@ -363,7 +369,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             if (rdy2) tc_fence_after();                              // hoisted: the MMA queue is full while this executes
         };
         for (int it = 0; it < nit; ++it) {
-            const bool stamp = (it == 0);
+            const bool stamp = (it == 1);
+            if (el && it == 1) TC_STAMP(244);
             mbar_wait(a_ready, (uint32_t)it & 1u);                   // A images of this point tile are in tensor memory
             tc_fence_after();
             bool first_k = true, first_kx = true, first_ky = true;
@@ -451,6 +458,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (j + NSLOT < npair) stage1(j + NSLOT);
             }
             if (el) umma_commit(t_full);
+            if (el && it == 0) TC_STAMP(248);
             __syncwarp();
         }
     } else if (warp >= NEPI + 2) {
@@ -513,7 +521,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
-            if (it == 0 && lw == 0 && lane == 0) TC_STAMP(1);
+            if (it == 1 && lw == 0 && lane == 0) TC_STAMP(1);
         }
     } else {
         // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
@@ -525,6 +533,23 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         double ki_cur = 0.0, sx_cur = 0.0, ki_prev = 0.0, sx_prev = 0.0;
         for (int it = 0; it <= nit; ++it) {
             ki_prev = ki_cur; sx_prev = sx_cur;
+            if (it > 0 && cg == 0) {
+                // features of the tile about to be finalised: issue the (scattered, L2-latency) loads first so that they overlap
+                // the A-image copy of the next tile and the drain of the tensor pipe
+                const long rowp = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM + r;
+                const bool okp = rowp < R;
+                const double* xr = X + rowp * (long)D;
+                double* F = feat + r * TF_COUNT;
+                const double xt = okp ? __ldg(xr + d) : 0.0, x0 = okp ? __ldg(xr) : 0.0;
+                double P2 = 0.0, R2 = 0.0;
+#pragma unroll
+                for (int m = 0; m < MC_IDX; ++m) {
+                    const double xi = okp ? __ldg(xr + gp.I[m]) : 0.0, xir = okp ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                    F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                    P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+                }
+                F[TF_ONE] = 1.0; F[TF_SX] = sx_prev; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx_prev - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+            }
             if (it < nit) {
                 // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
                 // have completed (this warp saw s_full of its last item), so the images can be overwritten.
@@ -545,28 +570,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(stage_free); }
                 }
-                if (it == 0 && tid == 0) TC_STAMP(2);
+                if (it == 1 && tid == 0) TC_STAMP(2);
             }
+            if (it == 1 && tid == 0) TC_STAMP(245);
             if (it > 0) {
                 // --- final contraction of tile it - 1: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
                 const long row0 = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM;
                 const long row = row0 + r;
                 const bool ok = row < R;
-                if (cg == 0) {
-                    const double* xr = X + row * (long)D;
-                    double* F = feat + r * TF_COUNT;
-                    const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
-                    double P2 = 0.0, R2 = 0.0;
-#pragma unroll
-                    for (int m = 0; m < MC_IDX; ++m) {
-                        const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                        F[TF_XI + m] = xi; F[TF_XR + m] = xir;
-                        P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
-                    }
-                    F[TF_ONE] = 1.0; F[TF_SX] = sx_prev; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx_prev - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
-                }
                 mbar_wait(t_full, (uint32_t)(it - 1) & 1u);         // all stage-2 MMAs of the tile have completed
                 tc_fence_after();
+                if (it == 1 && tid == 0) TC_STAMP(246);
                 constexpr int NPER = NT / 4;                         // T columns per column group
                 float tv[NPER];
 #pragma unroll
@@ -578,18 +592,22 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // features visible
                 const double* F = feat + r * TF_COUNT;
                 double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
-                const bool have_ky = ndom > 0;
+                // columns of one output are contiguous: accumulate a run (2 multiplies + 1 FMA per column) and fold it into
+                // its output accumulator only when the output changes
+                double run = 0.0;
+                int cur = TO_PAD;
+                auto flush = [&](int o) {
+                    aU += (o == TO_U) ? run : 0.0; aG += (o == TO_G) ? run : 0.0;
+                    aL += (o == TO_L) ? run : 0.0; aT += (o == TO_T) ? run : 0.0;
+                    run = 0.0;
+                };
 #pragma unroll
                 for (int i = 0; i < NPER; ++i) {
-                    const int col = cg * NPER + i;
-                    const TcColDesc dsc = st.desc[col];
-                    const bool skip = dsc.out == TO_PAD || (!have_ky && col >= C::NK + C::NKX);
-                    const double term = skip ? 0.0 : F[dsc.f1] * F[dsc.f2] * ((double)tv[i] * dsc.inv_scale);
-                    aU += (dsc.out == TO_U) ? term : 0.0;
-                    aG += (dsc.out == TO_G) ? term : 0.0;
-                    aL += (dsc.out == TO_L) ? term : 0.0;
-                    aT += (dsc.out == TO_T) ? term : 0.0;
+                    const TcColDesc dsc = sdesc[cg * NPER + i];
+                    if ((int)dsc.out != cur) { flush(cur); cur = dsc.out; }
+                    run = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, run);      // padded columns: inv_scale = 0
                 }
+                flush(cur);
                 if (cg > 0) {
                     double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
                     p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
@@ -619,14 +637,15 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // feat / xchg reusable
+                if (it == 1 && tid == 0) TC_STAMP(247);
             }
             if (it < nit) {
                 // --- main loop: S -> P in place, one pair (two sub-items, 2 x 16 columns per thread) per barrier round trip
-                const bool stamp = (it == 0);
+                const bool stamp = (it == 1);
                 for (int j = 0; j < npair; ++j, ++g) {
                     const int s = (int)(g % NSLOT);
                     const bool two = 2 * j + 1 < nitem;
-                    mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
+                    if (st.dbg_flags & 16) mbar_spin(s_full(s), (uint32_t)(g / NSLOT) & 1u); else mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
                     tc_fence_after();
                     if (tid == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
                     const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + (uint32_t)cg * 16u;
@@ -672,7 +691,7 @@ static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     return NSLOT * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
-           + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8 + 2 * TM * 8 + NBAR * 8 + 16;
+           + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8 + TC_MAXCOL * sizeof(TcColDesc) + 2 * TM * 8 + NBAR * 8 + 16;
 }
 
 template <int CLASS, int NSTEP>

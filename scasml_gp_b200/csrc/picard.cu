@@ -157,6 +157,7 @@ int PicardPlan::build(const PicardParams& p, long B) {
         lv.off_ev1 = take((size_t)pt * sizeof(double));
         lv.off_us = take((size_t)lv.NR * 2 * sizeof(double));
         lv.off_calls = take(lv.calls.size() * sizeof(CallDev));
+        lv.off_rowbase = take(lv.calls.size() * sizeof(long long));
     }
     stats_.executed_points = executed;
     ws_bytes_ = off + 256;
@@ -167,14 +168,15 @@ int PicardPlan::build(const PicardParams& p, long B) {
 
 namespace {
 
-__device__ __forceinline__ int find_call(const LevelDev& lv, long long R) {
-    int lo = 0, hi = lv.ncalls - 1;
+__device__ __forceinline__ int find_call(const long long* __restrict__ rowbase, int ncalls, long long R) {
+    int lo = 0, hi = ncalls - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (lv.calls[mid].rowbase <= R) lo = mid; else hi = mid - 1;
+        if (rowbase[mid] <= R) lo = mid; else hi = mid - 1;
     }
     return lo;
 }
+__device__ __forceinline__ int find_call(const LevelDev& lv, long long R) { return find_call(lv.rowbase, lv.ncalls, R); }
 
 __device__ __forceinline__ long long ceil_div_pos(long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; }
 
@@ -575,12 +577,14 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
     char* ws = (char*)workspace;
     std::vector<LevelDev> lvs(n + 1);
     std::vector<std::vector<CallDev>> host_calls(n + 1);
+    std::vector<std::vector<long long>> rowbases(MAX_LEVEL + 1);    // must outlive the async copies (synchronised below)
     for (int L = 1; L <= n; ++L) {
         const LevelRec& lr = levels_[L];
         LevelDev& lv = lvs[L];
         std::memset(&lv, 0, sizeof(lv));
         lv.L = L; lv.ncalls = (int)lr.calls.size();
         lv.calls = (const CallDev*)(ws + lr.off_calls);
+        lv.rowbase = (const long long*)(ws + lr.off_rowbase);
         lv.NR = lr.NR;
         const bool strided = (L == n) && p_.world > 1;
         lv.world = strided ? p_.world : 1; lv.rank = strided ? p_.rank : 0;
@@ -634,6 +638,10 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
             }
         }
         SC_CUDA(cudaMemcpyAsync(ws + lr.off_calls, hc.data(), hc.size() * sizeof(CallDev), cudaMemcpyHostToDevice, stream));
+        std::vector<long long>& rb = rowbases[L];
+        rb.resize(hc.size());
+        for (size_t i = 0; i < hc.size(); ++i) rb[i] = hc[i].rowbase;
+        SC_CUDA(cudaMemcpyAsync(ws + lr.off_rowbase, rb.data(), rb.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
     }
     const int nslot = (d + 14) / 8;
     SC_REQUIRE(nslot <= SAMPLE_THREADS, "picard: d > 2034 is not supported by the sampler");

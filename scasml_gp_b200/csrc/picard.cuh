@@ -59,6 +59,7 @@ struct CallDev {
 struct LevelDev {
     int L, ncalls;
     const CallDev* calls;
+    const long long* rowbase;           // [ncalls] compact copy of calls[i].rowbase: the binary search touches 1-2 cache lines, not one per probe
     long long NR;                       // rows at this level
     int world, rank;                    // unit striding (top level only; else 1,0)
     int MCg; long long NT;              // terminal samples per row; owned terminal points
@@ -100,7 +101,7 @@ public:
         long long NP[MAX_LEVEL] = {0};
         long long set_off[MAXLK] = {0};
         long long term_off = 0, ug_off = 0, pde_off = 0;
-        size_t off_P = 0, off_gid = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0;
+        size_t off_P = 0, off_gid = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0;
     };
     const std::vector<CallRec>& calls() const { return calls_; }
     const std::vector<LevelRec>& levels() const { return levels_; }

@@ -43,6 +43,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
     }
 }
+// spinning wait (non-blocking probe in a tight loop): lowest wake-up latency, takes issue slots while waiting
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
+    }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

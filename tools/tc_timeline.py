@@ -31,6 +31,9 @@ for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PD
     period = (starts[-3] - starts[3]) / max(1, nitem - 6) if nitem > 8 else 0
     print(f"== {name} flags={flags}: steady-state period {period:.0f} cycles/item")
     print(f"== {name}: entry 0, scatter {t[1]-t0}, prologue {t[2]-t0}, exit {t[3]-t0} cycles; items {nitem}")
+    f = [int(x - t0) for x in t[244:249]]
+    print(f"   tile boundary (stamps of the CTA's SECOND point tile): tile-0 t_full committed {f[4]}, MMA warp enters tile 1 {f[0]}, epilogue enters "
+          f"tile-1 iteration {f[1]}, A images copied {t[2]-t0}, t_full(0) seen {f[2]}, tile-0 outputs written {f[3]}, loader staged tile 1 at {t[1]-t0}")
     for w in range(min(nitem, 44)):
         a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
         print(f"  item {w:2d}: mma issue {a:7d}..{b:7d} ({b-a:5d})   epilogue {c:7d}..{e:7d} ({e-c:5d})")
