@@ -46,6 +46,8 @@ struct TcDev {
     const TcColDesc* desc;           // column table of this evaluation class
     size_t b1_tile_bytes, b3_tile_bytes;
     int nstep, ntile_dom, ntile_bdy;
+    const LevelDev* gen;             // non-null: the loader warps GENERATE the points (fused sampler) instead of reading X
+    long long gen_off;               // index of the launch's first point in the level's point buffer
     long long* dbg;
     int dbg_block;
     int dbg_flags;                   // timeline experiments: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 8 no operand copies (garbage operands)
@@ -226,7 +228,131 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
 }
 
-template <int CLASS, int NSTEP>
+// ---- fused sampler -----------------------------------------------------------------------------------------------------------
+// Same arithmetic, operation order and Philox addressing as picard.cu::sample_terminal_kernel / sample_paths_kernel (the
+// solvers give bit-identical results with the fusion switched off): terminal points X_T = (x + mu (T-t)) + sigma sqrt(T-t) N
+// (solvers/ScaSML.py:190-198), path points X_k = X_{k-1} + (mu d_k + sigma sqrt(d_k) N_k) accumulated from the level row for
+// k' = 0..k (:220-238), full-history points x + (mu tau (T-t) + sigma sqrt(tau (T-t)) N) (ScaSML_full_history.py:142-154).
+// Two phases per point tile so that the long dependent-load chain (owner row -> call record -> parent row pointer -> global id)
+// runs for 32 points per warp at once: (1) lane <-> point: resolve the point into a GenRec in shared memory;
+// (2) 16 lanes <-> point: lane hl owns coordinates [8 hl, 8 hl + 8); flat normal index of coordinate j is f0 + j, so the lane
+// needs the tail of Philox block B0 + hl and the head of block B0 + hl + 1: it generates one block and takes the next from its
+// neighbour lane.
+struct GenRec {
+    const double* x;                 // parent (level) row
+    const CallDev* call;
+    unsigned long long f0;           // flat index of the point's first normal
+    long long pgid;                  // global sample id
+    double t;                        // time of the level row
+    int l, k;                        // step set (l, k); l = -1: terminal point
+};
+
+__device__ __forceinline__ void gen_setup(const LevelDev& lv, long long pt, bool valid, GenRec* __restrict__ rec) {
+    GenRec g;
+    g.x = nullptr; g.call = nullptr; g.f0 = 0ull; g.pgid = 0; g.t = 0.0; g.l = -1; g.k = 0;
+    if (valid) {
+        int MC = lv.MCg;
+        long long s = pt - lv.term_off;
+        if (!(pt >= lv.term_off && pt < lv.term_off + lv.NT)) {
+            for (int ll = 0; ll < lv.L; ++ll) {
+                const long long o0 = lv.set_off[ll * MAX_Q];
+                const long long np = lv.NP[ll];
+                if (np > 0 && pt >= o0 && pt < o0 + np * lv.q[ll]) { g.l = ll; g.k = (int)((pt - o0) / np); s = pt - o0 - (long long)g.k * np; MC = lv.MCf[ll]; }
+            }
+        }
+        const long long u = lv.rank + (long long)lv.world * s;
+        const long long R = u / MC;
+        const int m = (int)(u - R * MC);
+        int lo = 0, hi = lv.ncalls - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(lv.rowbase + mid) <= R) lo = mid; else hi = mid - 1;
+        }
+        const CallDev* c = lv.calls + lo;
+        const long long i = R - __ldg(lv.rowbase + lo);
+        g.call = c;
+        g.x = c->xsrc + i * lv.D;
+        const long long gidrow = c->gidsrc ? c->gidsrc[i] : lv.gid0 + i;
+        g.pgid = gidrow * MC + m;
+        g.f0 = (unsigned long long)g.pgid * (unsigned long long)lv.d;
+        g.t = __ldg(g.x + lv.d);
+    }
+    *rec = g;
+}
+
+__device__ __forceinline__ void gen_point(const LevelDev& lv, const GenRec& g, long long pt, int hl, int lane, double* __restrict__ v, bool valid) {
+    const int d = lv.d, D = lv.D;
+    const int c0 = hl * 8;
+    const int l = g.l, k = g.k;
+    const double t = g.t;
+    const double* x = g.x;
+    double X[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { v[e] = 0.0; X[e] = (valid && c0 + e < d) ? __ldg(x + c0 + e) : 0.0; }
+    const unsigned long long B0 = g.f0 >> 3;
+    const int sh = (int)(g.f0 & 7ull);
+    const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+    const bool mine = c0 < d;                                       // this lane owns real coordinates
+    const bool last_owner = mine && (c0 + 8 >= d || hl == 15);      // its right neighbour generates no block (or is another point's lane)
+    auto normals = [&](PhiloxKey key, double* N) {
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = make_uint4(0u, 0u, 0u, 0u);
+        if (mine) w0 = philox4x32_10(B0 + (unsigned long long)hl, key);
+        // the two half-warps work on different points (different step counts): shuffle inside the 16-lane group only
+        w1.x = __shfl_down_sync(hmask, w0.x, 1); w1.y = __shfl_down_sync(hmask, w0.y, 1);
+        w1.z = __shfl_down_sync(hmask, w0.z, 1); w1.w = __shfl_down_sync(hmask, w0.w, 1);
+        if (last_owner && sh != 0) w1 = philox4x32_10(B0 + (unsigned long long)hl + 1ull, key);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = sh + e;
+            const uint32_t ch = (idx < 8) ? chunk_of(w0, idx) : chunk_of(w1, idx - 8);
+            N[e] = chunk_to_normal(lv.ntab, ch);
+        }
+    };
+    double tcol = lv.T;
+    if (l < 0) {
+        const double Tt = lv.T - t, sq = sqrt(Tt), drift = lv.mu * Tt;
+        double N[8];
+        normals(make_key(0u, 0u, lv.seed), N);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) X[e] = (X[e] + drift) + lv.sigma * (sq * N[e]);
+    } else if (lv.variant == 0) {
+        double tprev = t;
+        for (int kk = 0; kk <= k; ++kk) {
+            const int lk = l * MAX_Q + kk;
+            const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
+            const double dk = __dsub_rn(tk, tprev);
+            const double sq = sqrt(dk), drift = lv.mu * dk;
+            double N[8];
+            normals(make_key(valid ? g.call->key[lk] : 0u, 1u, lv.seed), N);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) X[e] = X[e] + (drift + lv.sigma * (sq * N[e]));
+            tprev = tk;
+        }
+        tcol = tprev;
+    } else {
+        const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+        const double tau = chunk_to_uniform(chunk16((unsigned long long)g.pgid, kT));
+        const double steps = tau * (lv.T - t);
+        const double sq = sqrt(steps), drift = lv.mu * steps;
+        double N[8];
+        normals(kT, N);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) X[e] = X[e] + (drift + lv.sigma * (sq * N[e]));
+        tcol = t + steps;
+    }
+    if (valid) {
+        double* dst = lv.P + pt * D;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int cc = c0 + e;
+            if (cc < d) { v[e] = X[e]; dst[cc] = X[e]; }
+            else if (cc == d) { v[e] = tcol; dst[cc] = tcol; }
+        }
+        if (hl == 0 && l >= 0) lv.gid[pt] = g.pgid;
+    }
+}
+
+template <int CLASS, int NSTEP, bool GEN>
 __global__ void __launch_bounds__(NTHREADS_P, 1)
 eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode,
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
@@ -248,7 +374,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
     double* xchg = feat + TM * TF_COUNT;                             // [3][128][4] partial sums of column groups 1..3
     TcColDesc* sdesc = (TcColDesc*)(xchg + 3 * TM * 4);              // [TC_MAXCOL] column table (f1, f2, output, 1 / scale)
-    double* Ki = (double*)(sdesc + TC_MAXCOL);                       // [128] exp(-a |x|^2 / 2) of the staged tile
+    GenRec* grec = (GenRec*)(sdesc + TC_MAXCOL);                     // [128] fused sampler: resolved points of the tile being staged
+    double* Ki = (double*)(grec + (GEN ? TM : 0));                       // [128] exp(-a |x|^2 / 2) of the staged tile
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
     uint64_t* bars = (uint64_t*)(sxs + TM);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
@@ -473,6 +600,11 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
             if (it > 0) mbar_wait(stage_free, (uint32_t)(it - 1) & 1u);     // the previous tile's images are in tensor memory
             constexpr int RPW = TM / NLOAD;                          // rows per loader warp
+            if (GEN) {                                               // phase 1: lane <-> point (32 dependent-load chains in flight per warp)
+                const int rr = lw * RPW + lane;
+                gen_setup(*st.gen, st.gen_off + row0 + rr, row0 + rr < R, grec + rr);
+                __syncwarp();
+            }
 #pragma unroll 1
             for (int pass = 0; pass < RPW / 4; ++pass) {
                 double v[2][8];
@@ -480,10 +612,14 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 for (int i = 0; i < 2; ++i) {
                     const int r = lw * RPW + (pass * 2 + i) * 2 + sub;
                     const long row = row0 + r;
+                    if (GEN) {
+                        gen_point(*st.gen, grec[r], st.gen_off + row, hl, lane, v[i], row < R);   // fused sampler: draw, write to HBM, stage
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = c0 + e;
-                        v[i][e] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
+                        for (int e = 0; e < 8; ++e) {
+                            const int c = c0 + e;
+                            v[i][e] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
+                        }
                     }
                 }
 #pragma unroll
@@ -519,6 +655,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     if (hl == 0) { Ki[r] = exp(-0.5 * gp.a * nx); sxs[r] = sx; }
                 }
             }
+            if (GEN) __threadfence_block();                         // generated rows (global) are re-read by the epilogue warps of this CTA
             __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
             if (it == 1 && lw == 0 && lane == 0) TC_STAMP(1);
@@ -686,22 +823,22 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #undef TC_STAMP
 }
 
-template <int CLASS, int NSTEP>
+template <int CLASS, int NSTEP, bool GEN>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     return NSLOT * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
-           + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8 + TC_MAXCOL * sizeof(TcColDesc) + 2 * TM * 8 + NBAR * 8 + 16;
+           + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8 + TC_MAXCOL * sizeof(TcColDesc) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + NBAR * 8 + 16;
 }
 
-template <int CLASS, int NSTEP>
+template <int CLASS, int NSTEP, bool GEN>
 static int launch(const GpView& gp, const TcDev& st, const double* X, long R, int mode,
                   double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
     static bool configured = false;
     static int nsm = 0;
-    const size_t smem = smem_bytes<CLASS, NSTEP>();
+    const size_t smem = smem_bytes<CLASS, NSTEP, GEN>();
     if (!configured) {
-        SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
         SC_CUDA(cudaGetDevice(&dev));
         SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -709,7 +846,7 @@ static int launch(const GpView& gp, const TcDev& st, const double* X, long R, in
     }
     const long ntiles = cdiv(R, TM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);   // persistent: one CTA per SM
-    eval_tc_kernel<CLASS, NSTEP><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
+    eval_tc_kernel<CLASS, NSTEP, GEN><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -827,7 +964,8 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
 }
 
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
-                   double* out0, double* out1, double* out2, double* out3, cudaStream_t stream) {
+                   double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
+                   const LevelDev* gen_level_dev, long long gen_off) {
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
@@ -843,12 +981,18 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.b1_tile_bytes = st->b1_tile_bytes;
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
+    dv.gen = gen_level_dev; dv.gen_off = gen_off;
     dv.dbg = st->dbg; dv.dbg_block = st->dbg_block & 0xFFFFFF; dv.dbg_flags = st->dbg ? (st->dbg_block >> 24) : 0;
-#define SC_TC_DISPATCH(NS)                                                                                     \
-    do {                                                                                                       \
-        if (cls == TC_U) return tc::launch<TC_U, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);       \
-        if (cls == TC_UG) return tc::launch<TC_UG, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);     \
-        return tc::launch<TC_PDE, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                      \
+#define SC_TC_DISPATCH(NS)                                                                                                  \
+    do {                                                                                                                    \
+        if (dv.gen != nullptr) {                                                                                            \
+            if (cls == TC_U) return tc::launch<TC_U, NS, true>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);          \
+            if (cls == TC_UG) return tc::launch<TC_UG, NS, true>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);        \
+            return tc::launch<TC_PDE, NS, true>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                         \
+        }                                                                                                                   \
+        if (cls == TC_U) return tc::launch<TC_U, NS, false>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);             \
+        if (cls == TC_UG) return tc::launch<TC_UG, NS, false>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);           \
+        return tc::launch<TC_PDE, NS, false>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                            \
     } while (0)
     // the k-step count is a template parameter (lean single-thread MMA issue): images are zero-padded up to it
     if (st->nstep <= 2) SC_TC_DISPATCH(2);

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstring>
 #include "picard.cuh"
+#include "gp_tc.cuh"
 
 namespace scasml {
 
@@ -158,6 +159,7 @@ int PicardPlan::build(const PicardParams& p, long B) {
         lv.off_us = take((size_t)lv.NR * 2 * sizeof(double));
         lv.off_calls = take(lv.calls.size() * sizeof(CallDev));
         lv.off_rowbase = take(lv.calls.size() * sizeof(long long));
+        lv.off_lvdev = take(sizeof(LevelDev));
     }
     stats_.executed_points = executed;
     ws_bytes_ = off + 256;
@@ -643,6 +645,11 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         for (size_t i = 0; i < hc.size(); ++i) rb[i] = hc[i].rowbase;
         SC_CUDA(cudaMemcpyAsync(ws + lr.off_rowbase, rb.data(), rb.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
     }
+    // fused sampler (tcgen05 route, ScaSML): the evaluation kernel's loader warps draw the points; needs the level records on the device
+    const bool fused = (route == 1) && p_.scasml && !(p_.reserved & 1);
+    if (fused)
+        for (int L = 1; L <= n; ++L)
+            SC_CUDA(cudaMemcpyAsync(ws + levels_[L].off_lvdev, &lvs[L], sizeof(LevelDev), cudaMemcpyHostToDevice, stream));
     const int nslot = (d + 14) / 8;
     SC_REQUIRE(nslot <= SAMPLE_THREADS, "picard: d > 2034 is not supported by the sampler");
     const int ppb = SAMPLE_THREADS / nslot;            // points per sampler CTA
@@ -664,11 +671,11 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         const LevelDev& lv = lvs[L];
         const LevelRec& lr = levels_[L];
         begin_span(0);
-        if (lv.NT > 0) {
+        if (!fused && lv.NT > 0) {
             sample_terminal_kernel<<<(unsigned)cdiv(lv.NT, ppb), SAMPLE_THREADS, 0, stream>>>(lv, ppb);
             SC_LAUNCH_CHECK(); ++launches;
         }
-        for (int l = 0; l < L; ++l) {
+        for (int l = 0; l < L && !fused; ++l) {
             if (lv.NP[l] == 0) continue;
             sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l], ppb), SAMPLE_THREADS, 0, stream>>>(lv, l, ppb);
             SC_LAUNCH_CHECK(); ++launches;
@@ -684,7 +691,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
                 begin_span(1);
                 if (route == 1)
                     rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
-                                        nullptr, nullptr, stream);
+                                        nullptr, nullptr, stream, fused ? (const LevelDev*)(ws + lr.off_lvdev) : nullptr, s.off);
                 else
                     rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                          nullptr, nullptr, stream);

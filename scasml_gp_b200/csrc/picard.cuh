@@ -30,7 +30,7 @@ struct PicardParams {
     int rank, world;          // top-level sample sharding: unit u owned iff u % world == rank
     long long gid0;           // global index of the first test point of this batch
     int timing;               // 1: CUDA-event timing of kernel groups (adds a stream sync)
-    int reserved;
+    int reserved;             // bit 0: keep the stand-alone sampler kernels on the tcgen05 route (no fused sampler)
 };
 
 struct PicardStats {
@@ -101,7 +101,7 @@ public:
         long long NP[MAX_LEVEL] = {0};
         long long set_off[MAXLK] = {0};
         long long term_off = 0, ug_off = 0, pde_off = 0;
-        size_t off_P = 0, off_gid = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0;
+        size_t off_P = 0, off_gid = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
     };
     const std::vector<CallRec>& calls() const { return calls_; }
     const std::vector<LevelRec>& levels() const { return levels_; }
@@ -121,9 +121,5 @@ private:
     unsigned keyctr_ = 0;
     size_t ws_bytes_ = 0;
 };
-
-// tcgen05 route (gp_eval_tc.cu); returns ERR_INVALID if the shape is unsupported
-int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
-                   double* out0, double* out1, double* out2, double* out3, cudaStream_t stream);
 
 }  // namespace scasml

@@ -109,6 +109,26 @@ def test_tc_solver_meets_north_star_criterion(mid):
         assert prod.evaluation_counter == orac.evaluation_counter
 
 
+def test_fused_sampler_is_bit_identical_to_the_sampler_kernels(mid):
+    """On the tcgen05 route the evaluation kernel's loader warps draw the Brownian increments themselves (fused sampler).
+    Same Philox addressing, same operation order: switching the fusion off (stand-alone sampler kernels) must not change a bit."""
+    F, P = mid, mid.P
+    lib = P["lib"]
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(150, 31)                              # 181 points: partial tiles, several CTAs
+    X[::7, -1] = F.eq_o.T                                   # degenerate steps included
+    for cls, args in ((P["ScaSML"], (3, 3, X)), (P["ScaSMLfh"], (3, None, X, 3))):
+        outs = []
+        for fused in (True, False):
+            s = cls(F.eq, F.gp)
+            s.route = lib.ROUTE_TC
+            s.quadrature = "gauss_legendre"
+            s.fused_sampler = fused
+            s.uz_solve(*args)
+            outs.append(s.last_raw.copy())
+        assert np.array_equal(outs[0], outs[1], equal_nan=True)
+
+
 def test_tc_route_rejects_large_d():
     P = _product()
     lib = P["lib"]
