@@ -29,6 +29,8 @@ CONFIGS = {
                desc="Grad_Dependent_Nonlinear d=20, ScaSML n=rho=3, GP 1000+200 collocation points"),
     "C3": dict(d=100, nd=1000, nb=200, n=4, rho=4, variant="quadrature", M=None,
                desc="Grad_Dependent_Nonlinear d=100, ScaSML n=rho=4, GP 1000+200 collocation points (phi=4200)"),
+    "C5": dict(d=1000, nd=4000, nb=800, n=4, rho=4, variant="quadrature", M=None,
+               desc="Grad_Dependent_Nonlinear d=1000, ScaSML n=rho=4, GP 4000+800 collocation points (phi=16800); K-streamed tcgen05 kernel"),
     "C4": dict(d=60, nd=1000, nb=200, n=4, rho=None, variant="full_history", M=3,
                desc="Grad_Dependent_Nonlinear d=60, ScaSML_full_history n=4 M=3"),
 }
@@ -192,8 +194,8 @@ def main():
     eq = Grad_Dependent_Nonlinear(d + 1)
     gp = GP_Grad_Dependent_Nonlinear(eq, idx_set=idx)
     route = args.route
-    if route == "auto":     # the tcgen05 route is the product path wherever it applies (d <= 126); FP64 is the parity anchor
-        route = "tc" if d + 2 <= 128 else "f64"
+    if route == "auto":     # the tcgen05 route is the product path wherever it applies (d <= 1022); FP64 is the parity anchor
+        route = "tc" if d + 2 <= 1024 else "f64"
     gp.route = _lib.ROUTE_TC if route == "tc" else _lib.ROUTE_F64
     torch.cuda.synchronize()
     t0 = time.perf_counter()

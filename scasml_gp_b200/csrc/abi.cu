@@ -175,7 +175,7 @@ int scasml_gp_create(int d, int n_dom, int n_bdy, const int* idx_set5, double ke
 
 int scasml_gp_destroy(scasml_gp* g) {
     if (!g) return OK;
-    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha); cudaFree(g->tc.images);
+    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha); cudaFree(g->tc.images); cudaFree(g->tc.ks_scratch);
     delete g;
     return OK;
 }

@@ -851,12 +851,408 @@ static int launch(const GpView& gp, const TcDev& st, const double* X, long R, in
     return OK;
 }
 
+// ---- K-streamed variant for d + 2 > 128 (up to 1024 contraction columns) --------------------------------------------------
+// The point images no longer fit tensor memory (or shared memory), so a pre-pass (`ks_image_kernel`) writes them to a global
+// scratch buffer in the MMA's shared-memory layout (per 128-point tile, per 64-wide K block: [hi 16 KB | lo 16 KB], f16,
+// 128 B swizzle) together with K_i and the row sums, and the evaluation kernel streams A AND B K-blocks through a 3-stage
+// ring: 8 SS-mode N = 128 MMAs per stage (4 k-steps x hi/lo), one barrier wait + one commit per stage.  Everything after
+// stage 1 (in-place ex2 / split, coefficient GEMM from tensor memory, FP64 final contraction) is the same as above; with the
+// A images out of tensor memory the layout is two 128-column S/P slots + T.  At d = 1000 the distance GEMM dominates
+// (128 MMAs per pair against 24 small ones), so the hand-off latencies that bind the small-d kernel are amortised.
+constexpr int KS_STAGES = 3;
+constexpr uint32_t KS_STAGE_BYTES = 2 * A_BLK + 2 * B1_BLK;          // A hi | A lo | B rows of sub-item a | sub-item b
+constexpr int KS_NBAR = 2 * KS_STAGES + 4 * NSLOT + 2;               // full empty | b3_full b3_empty s_full p_ready | t_full t_free
+constexpr int KS_THREADS = (NEPI + 2) * 32;
+
+__global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* __restrict__ X, long R, int KB,
+                                                       uint8_t* __restrict__ img, double* __restrict__ Ki, double* __restrict__ sxs) {
+    const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = gp.D, d = gp.d;
+    const double ascale = gp.a * 1.4426950408889634;
+    uint8_t* base = img + (size_t)tile * KB * 2 * A_BLK;
+    const int hl = lane & 15, sub = lane >> 4;
+    for (int rp = warp; rp < TM / 2; rp += 8) {                    // two rows per warp pass
+        const int r = rp * 2 + sub;
+        const long row = (long)tile * TM + r;
+        double nx = 0.0, sx = 0.0;
+        for (int cb = 0; cb < KB * KBLK; cb += 128) {              // 16 lanes x 8 columns per pass
+            const int c0 = cb + hl * 8;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                float sv[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + e + q;
+                    const double val = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
+                    nx = fma(val, val, nx);
+                    if (c < d) sx += val;
+                    sv[q] = (c == D) ? 1.0f : (float)(ascale * val);
+                }
+                const __half2 h = __floats2half2_rn(sv[0], sv[1]);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(sv[0] - hf.x, sv[1] - hf.y);
+                hi[e >> 1] = *(const uint32_t*)&h;
+                lo[e >> 1] = *(const uint32_t*)&l;
+            }
+            if (c0 < KB * KBLK) {
+                const int kb = c0 / KBLK;
+                const uint32_t off = (uint32_t)r * 128u + (uint32_t)(((((c0 % KBLK) >> 3) ^ (r & 7)) & 7) << 4);
+                *(uint4*)(base + (size_t)kb * 2 * A_BLK + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *(uint4*)(base + (size_t)kb * 2 * A_BLK + A_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
+        if (hl == 0) { Ki[(size_t)tile * TM + r] = exp(-0.5 * gp.a * nx); sxs[(size_t)tile * TM + r] = sx; }
+    }
+}
+
+template <int CLASS>
+__global__ void __launch_bounds__(KS_THREADS, 1)
+eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode, const uint8_t* __restrict__ img,
+                  const double* __restrict__ Kig, const double* __restrict__ sxg,
+                  double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
+    using C = Cfg<CLASS>;
+    constexpr bool PDE = (CLASS == TC_PDE);
+    constexpr int NT = C::NK + C::NKX + C::NKY;
+    constexpr int NMAX = C::NK > C::NKY ? C::NK : C::NKY;
+    constexpr uint32_t B3_SUB = 2 * NMAX * 128, B3_SLOT = 2 * B3_SUB;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
+    uint8_t* sRing = smem;                                           // KS_STAGES x [A hi | A lo | B a | B b]
+    uint8_t* sB3 = sRing + KS_STAGES * (size_t)KS_STAGE_BYTES;       // NSLOT pair slots
+    double* feat = (double*)(sB3 + NSLOT * (size_t)B3_SLOT);
+    double* xchg = feat + TM * TF_COUNT;
+    TcColDesc* sdesc = (TcColDesc*)(xchg + 3 * TM * 4);
+    uint64_t* bars = (uint64_t*)(sdesc + TC_MAXCOL);
+    uint32_t* tmem_slot = (uint32_t*)(bars + KS_NBAR);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = gp.D, d = gp.d;
+    const long ntiles = (R + TM - 1) / TM;
+    const int nit = (int)((ntiles - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x);
+    const int KB = (st.nstep + 3) / 4;
+    const uint32_t bar0 = smem_u32(bars);
+    auto k_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    auto k_empty = [&](int i) { return bar0 + 8u * (uint32_t)(KS_STAGES + i); };
+    auto b3_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * KS_STAGES + i); };
+    auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * KS_STAGES + NSLOT + i); };
+    auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * KS_STAGES + 2 * NSLOT + i); };
+    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * KS_STAGES + 3 * NSLOT + i); };
+    const uint32_t t_full = bar0 + 8u * (uint32_t)(2 * KS_STAGES + 4 * NSLOT), t_free = t_full + 8u;
+
+    if (tid == 0) {
+        for (int i = 0; i < KS_STAGES; ++i) { mbar_init(k_full(i), 1); mbar_init(k_empty(i), 1); }
+        for (int i = 0; i < NSLOT; ++i) { mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI); }
+        mbar_init(t_full, 1); mbar_init(t_free, NEPI);
+        fence_barrier_init();
+    }
+    if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int c = tid; c < TC_MAXCOL; c += KS_THREADS) {
+        TcColDesc dsc = st.desc[c < NT ? c : 0];
+        if (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX)) { dsc.out = TO_PAD; dsc.f1 = 0; dsc.f2 = 0; dsc.inv_scale = 0.0; }
+        sdesc[c] = dsc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
+    constexpr int CPD = PDE ? 3 : 2;
+    const int nitem = CPD * ndom + (CPD - 1) * nbdy;
+    const int npair = (nitem + 1) >> 1;
+    auto next_item = [&](int& t, int& kc) {
+        if (kc == TK_K) kc = PDE ? TK_KX : (t < ndom ? TK_KY : TK_K);
+        else if (kc == TK_KX) kc = (t < ndom) ? TK_KY : TK_K;
+        else kc = TK_K;
+        if (kc == TK_K) ++t;
+    };
+
+    if (warp == NEPI) {
+        // ===== producer: per pair and K block one ring stage [A hi | A lo | B rows a | B rows b]; per pair the coefficient images
+        if (lane == 0) {
+            long gs = 0;                                             // global stage counter
+            int p3 = 0;
+            for (int it = 0; it < nit; ++it) {
+                const long tile = (long)blockIdx.x + (long)it * gridDim.x;
+                const uint8_t* aimg = img + (size_t)tile * KB * 2 * A_BLK;
+                int t1 = 0, k1 = TK_K, t3 = 0, k3 = TK_K;
+                for (int j = 0; j < npair; ++j) {
+                    const bool two = 2 * j + 1 < nitem;
+                    int ta = t1, ka = k1; next_item(t1, k1);
+                    int tb = t1, kbb = k1; if (two) next_item(t1, k1);
+                    const uint8_t* srca = st.b1 + (size_t)ta * st.b1_tile_bytes + (size_t)(ka == TK_K ? 0 : (ka == TK_KX ? 1 : 2)) * B1_BLK;
+                    const uint8_t* srcb = st.b1 + (size_t)tb * st.b1_tile_bytes + (size_t)(kbb == TK_K ? 0 : (kbb == TK_KX ? 1 : 2)) * B1_BLK;
+                    // coefficient images of the pair first (small; needed after the K loop)
+                    {
+                        const int s = p3 % NSLOT;
+                        if (p3 >= NSLOT) mbar_wait(b3_empty(s), (uint32_t)((p3 / NSLOT) - 1) & 1u);
+                        uint32_t off[2], bytes[2]; int tt[2];
+                        for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
+                            off[sub] = k3 == TK_K ? 0u : (k3 == TK_KX ? 2u * C::NK * 128u : 2u * (C::NK + C::NKX) * 128u);
+                            bytes[sub] = 2u * 128u * (uint32_t)(k3 == TK_K ? C::NK : (k3 == TK_KX ? C::NKX : C::NKY));
+                            tt[sub] = t3;
+                            next_item(t3, k3);
+                        }
+                        mbar_expect_tx(b3_full(s), bytes[0] + (two ? bytes[1] : 0u));
+                        for (int sub = 0; sub < (two ? 2 : 1); ++sub)
+                            bulk_g2s(smem_u32(sB3 + (size_t)s * B3_SLOT + (size_t)sub * B3_SUB), st.b3 + (size_t)tt[sub] * st.b3_tile_bytes + off[sub],
+                                     bytes[sub], b3_full(s));
+                        ++p3;
+                    }
+                    for (int kb = 0; kb < KB; ++kb, ++gs) {
+                        const int sg = (int)(gs % KS_STAGES);
+                        if (gs >= KS_STAGES) mbar_wait(k_empty(sg), (uint32_t)((gs / KS_STAGES) - 1) & 1u);
+                        uint8_t* dst = sRing + (size_t)sg * KS_STAGE_BYTES;
+                        mbar_expect_tx(k_full(sg), 2 * A_BLK + (two ? 2u : 1u) * B1_BLK);
+                        bulk_g2s(smem_u32(dst), aimg + (size_t)kb * 2 * A_BLK, 2 * A_BLK, k_full(sg));
+                        bulk_g2s(smem_u32(dst + 2 * A_BLK), srca + (size_t)kb * (3 * B1_BLK), B1_BLK, k_full(sg));
+                        if (two) bulk_g2s(smem_u32(dst + 2 * A_BLK + B1_BLK), srcb + (size_t)kb * (3 * B1_BLK), B1_BLK, k_full(sg));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == NEPI + 1) {
+        // ===== MMA issuer =====
+        const uint32_t el = elect_one();
+        const uint64_t ring0 = make_desc(smem_u32(sRing), 1, 64, 2);
+        const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
+        const uint32_t idS2 = make_idesc(TM, 2 * TN), idS1 = make_idesc(TM, TN);
+        const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
+        long gs = 0;
+        int p1 = 0, p2 = 0;
+        for (int it = 0; it < nit; ++it) {
+            bool first_k = true, first_kx = true, first_ky = true;
+            int kc2 = TK_K, t2 = 0;
+            auto stage1 = [&](int j) {
+                const int s = p1 % NSLOT;
+                const uint32_t accS = tmem_base + (uint32_t)s * 128u;
+                const uint32_t idesc = (2 * j + 1 < nitem) ? idS2 : idS1;
+                ++p1;
+                for (int kb = 0; kb < KB; ++kb, ++gs) {
+                    const int sg = (int)(gs % KS_STAGES);
+                    mbar_wait(k_full(sg), (uint32_t)(gs / KS_STAGES) & 1u);
+                    const uint64_t ad = ring0 + (uint64_t)(((uint32_t)sg * KS_STAGE_BYTES) >> 4);
+                    const uint64_t bd = ad + (uint64_t)((2 * A_BLK) >> 4);
+                    const int nks = (st.nstep - kb * 4 < 4) ? (st.nstep - kb * 4) : 4;
+                    if (el) {
+#pragma unroll
+                        for (int half = 1; half >= 0; --half) {      // low halves first (tiny terms), then the high halves
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                if (ks < nks)
+                                    umma_f16(accS, ad + (uint64_t)((half * A_BLK + ks * 32) >> 4), bd + (uint64_t)((ks * 32) >> 4), idesc,
+                                             (kb == 0 && half == 1 && ks == 0) ? 0u : 1u);
+                            }
+                        }
+                        umma_commit(k_empty(sg));
+                    }
+                    __syncwarp();
+                }
+                if (el) umma_commit(s_full(s));
+                __syncwarp();
+            };
+            auto stage2 = [&](int j) {
+                const int s = p2 % NSLOT;
+                {
+                    const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
+                    uint32_t spins = 0;
+                    bool a = false, b = false;
+                    while (true) {
+                        if (!a) a = mbar_test_wait(p_ready(s), par);
+                        if (!b) b = mbar_test_wait(b3_full(s), par);
+                        if (a && b) break;
+                        if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
+                    }
+                }
+                if (j == 0 && it > 0) mbar_wait(t_free, (uint32_t)(it - 1) & 1u);
+                tc_fence_after();
+                ++p2;
+                const int nsub = (2 * j + 1 < nitem) ? 2 : 1;
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const uint32_t pbase = tmem_base + (uint32_t)s * 128u + (uint32_t)sub * 64u;
+                    const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT + (uint32_t)sub * B3_SUB) >> 4);
+                    const int kc = kc2;
+                    const uint32_t tacc = tmem_base + COL_T + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
+                    const uint32_t nrows = kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY);
+                    const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
+                    const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
+                    const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
+                    if (el) {
+                        if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
+                        umma_ts<true>(tacc, pbase, clo0, idesc);
+                        umma_ts<true>(tacc, pbase + 8u, b3, idesc);
+#pragma unroll
+                        for (int ks = 1; ks < 4; ++ks) {
+                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
+                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                        }
+                    }
+                    if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
+                    next_item(t2, kc2);
+                }
+                if (el) umma_commit(b3_empty(s));
+                __syncwarp();
+            };
+            for (int j = 0; j < NSLOT && j < npair; ++j) stage1(j);
+            for (int j = 0; j < npair; ++j) {
+                stage2(j);
+                if (j + NSLOT < npair) stage1(j + NSLOT);
+            }
+            if (el) umma_commit(t_full);
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int r = (warp & 3) * 32 + lane;
+        const int cg = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        long g = 0;
+        for (int it = 0; it < nit; ++it) {
+            const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
+            for (int j = 0; j < npair; ++j, ++g) {
+                const int s = (int)(g % NSLOT);
+                const bool two = 2 * j + 1 < nitem;
+                mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
+                tc_fence_after();
+                const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + (uint32_t)cg * 16u;
+                float v[2][16];
+                tmem_ld16(base, v[0]);
+                if (two) tmem_ld16(base + 64u, v[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c == 0 || two) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float p0 = ex2f(v[c][2 * i]), p1 = ex2f(v[c][2 * i + 1]);
+                            hi[i] = pack_f16x2_sat(p0, p1);
+                            const float2 hf = __half22float2(*(const __half2*)&hi[i]);
+                            lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                        }
+                        tmem_st8(base + (uint32_t)c * 64u, hi);
+                        tmem_st8(base + (uint32_t)c * 64u + 8u, lo);
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_ready(s));
+            }
+            // --- final contraction (same as the small-d kernel)
+            const long row = row0 + r;
+            const bool ok = row < R;
+            if (cg == 0) {
+                const double* xr = X + row * (long)D;
+                double* F = feat + r * TF_COUNT;
+                const double sx = ok ? sxg[row0 + r] : 0.0;
+                const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+                double P2 = 0.0, R2 = 0.0;
+#pragma unroll
+                for (int m = 0; m < MC_IDX; ++m) {
+                    const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                    F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                    P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+                }
+                F[TF_ONE] = 1.0; F[TF_SX] = sx; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+            }
+            mbar_wait(t_full, (uint32_t)it & 1u);
+            tc_fence_after();
+            constexpr int NPER = NT / 4;
+            float tv[NPER];
+#pragma unroll
+            for (int c4 = 0; c4 < NPER; c4 += 4) tmem_ld4(tmem_base + lane_addr + COL_T + (uint32_t)(cg * NPER + c4), tv + c4);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_free);
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            const double* F = feat + r * TF_COUNT;
+            double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0, run = 0.0;
+            int cur = TO_PAD;
+            auto flush = [&](int o) {
+                aU += (o == TO_U) ? run : 0.0; aG += (o == TO_G) ? run : 0.0;
+                aL += (o == TO_L) ? run : 0.0; aT += (o == TO_T) ? run : 0.0;
+                run = 0.0;
+            };
+#pragma unroll
+            for (int i = 0; i < NPER; ++i) {
+                const TcColDesc dsc = sdesc[cg * NPER + i];
+                if ((int)dsc.out != cur) { flush(cur); cur = dsc.out; }
+                run = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, run);
+            }
+            flush(cur);
+            if (cg > 0) {
+                double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
+                p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            if (cg == 0 && ok) {
+#pragma unroll
+                for (int g2 = 1; g2 < 4; ++g2) {
+                    const double* p = xchg + ((size_t)(g2 - 1) * TM + r) * 4;
+                    aU += p[0]; aG += p[1]; aL += p[2]; aT += p[3];
+                }
+                const double ki = Kig[row0 + r];
+                const double u = ki * aU;
+                if (CLASS == TC_U) {
+                    const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));                  // equations.py:259
+                    out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
+                } else if (CLASS == TC_UG) {
+                    out0[row] = u;
+                    out1[row] = ki * aG;
+                } else {
+                    const double gg = ki * aG, l = ki * aL, tt = ki * aT;
+                    const double s2 = gp.sig2;
+                    out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * gg + 0.5 * s2 * l;       // GP.py:767-768
+                    if (out1) out1[row] = gg;
+                    if (out2) out2[row] = l;
+                    if (out3) out3[row] = tt;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int CLASS>
+static int launch_ks(const GpView& gp, const TcDev& st, const double* X, long R, int mode, const uint8_t* img, const double* Ki,
+                     const double* sxs, double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
+    using C = Cfg<CLASS>;
+    constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
+    const size_t smem = KS_STAGES * (size_t)KS_STAGE_BYTES + NSLOT * (2 * 2 * NMAX * 128) + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8
+                        + TC_MAXCOL * sizeof(TcColDesc) + KS_NBAR * 8 + 16;
+    static bool configured = false;
+    static int nsm = 0;
+    if (!configured) {
+        SC_CUDA(cudaFuncSetAttribute(eval_tc_ks_kernel<CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        SC_CUDA(cudaGetDevice(&dev));
+        SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const long ntiles = cdiv(R, TM);
+    const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
+    eval_tc_ks_kernel<CLASS><<<grid, KS_THREADS, smem, stream>>>(gp, st, X, R, mode, img, Ki, sxs, o0, o1, o2, o3);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+
 }  // namespace tc
 
 // ---- host API --------------------------------------------------------------------------------------------------
 
-// the contraction axis (d + 1 coordinates + the exponent-shift column) must fit two 64-wide K blocks
-int tc_supported(const GpView& gp) { return gp.D + 1 <= 2 * tc::KBLK; }
+// the contraction axis (d + 1 coordinates + the exponent-shift column): up to two 64-wide K blocks stay resident in tensor
+// memory (small-d kernel), up to sixteen are streamed (K-streamed kernel)
+int tc_supported(const GpView& gp) { return gp.D + 1 <= 16 * tc::KBLK; }
 
 static void add_col(TcState* st, int cls, int& n, int kern, int out, int f1, int f2, int coef, int m = 0, int nn = 0) {
     TcColSpec& s = st->spec[cls][n++];
@@ -917,7 +1313,7 @@ static void build_columns(TcState* st) {
 
 size_t tc_image_bytes(const GpView& gp, TcState* st) {
     st->nstep = (gp.D + 1 + 15) / 16;
-    st->nstep = st->nstep <= 2 ? 2 : (st->nstep <= 4 ? 4 : (st->nstep <= 7 ? 7 : 8));   // instantiated k-step counts
+    if (st->nstep <= 8) st->nstep = st->nstep <= 2 ? 2 : (st->nstep <= 4 ? 4 : (st->nstep <= 7 ? 7 : 8));   // instantiated k-step counts (small-d kernel)
     st->KB = (st->nstep + 3) / 4;
     st->ntile_dom = gp.NdPad / tc::TN;
     st->ntile_bdy = gp.NbPad / tc::TN;
@@ -941,7 +1337,7 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
 }
 
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
-    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 126 (larger d: FP64 route)");
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 1022 (larger d: FP64 route)");
     SC_REQUIRE(st.images != nullptr, "tc: image buffer is null");
     const int ntile = st.ntile_dom + st.ntile_bdy;
     const int ncentres = ntile * tc::TN;
@@ -969,8 +1365,8 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
-    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route unavailable for this GP (d > 126 or not fitted): use the FP64 route");
-    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 126 (larger d: FP64 route)");
+    SC_REQUIRE(st != nullptr && st->images != nullptr, "tcgen05 route unavailable for this GP (d > 1022 or not fitted): use the FP64 route");
+    SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 1022 (larger d: FP64 route)");
     SC_REQUIRE(X && out0, "eval: null pointer");
     const int cls = (mode == EVAL_PDE) ? TC_PDE : (mode == EVAL_UG ? TC_UG : TC_U);
     if (cls == TC_UG) SC_REQUIRE(out1 != nullptr, "eval UG: out1 is null");
@@ -983,6 +1379,37 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
     dv.gen = gen_level_dev; dv.gen_off = gen_off;
     dv.dbg = st->dbg; dv.dbg_block = st->dbg_block & 0xFFFFFF; dv.dbg_flags = st->dbg ? (st->dbg_block >> 24) : 0;
+    if (st->nstep > 8) {
+        // K-streamed kernel: point images in a scratch buffer owned by the handle's TcState (grown on demand), processed in chunks
+        SC_REQUIRE(gen_level_dev == nullptr, "the fused sampler is not available on the K-streamed kernel");
+        TcState* mst = const_cast<TcState*>(st);
+        const int KB = (st->nstep + 3) / 4;
+        const long chunk_pts = 148L * tc::TM * 4;                     // four point tiles per SM per launch
+        const size_t per_tile = (size_t)KB * 2 * tc::A_BLK + 2 * tc::TM * sizeof(double);
+        const size_t need = (size_t)cdiv(R < chunk_pts ? R : chunk_pts, tc::TM) * per_tile;
+        if (mst->ks_scratch_bytes < need) {
+            if (mst->ks_scratch) { SC_CUDA(cudaStreamSynchronize(stream)); SC_CUDA(cudaFree(mst->ks_scratch)); mst->ks_scratch = nullptr; mst->ks_scratch_bytes = 0; }
+            SC_CUDA(cudaMalloc(&mst->ks_scratch, need));
+            mst->ks_scratch_bytes = need;
+        }
+        for (long r0 = 0; r0 < R; r0 += chunk_pts) {
+            const long rc = (R - r0 < chunk_pts) ? (R - r0) : chunk_pts;
+            const long nt = cdiv(rc, tc::TM);
+            uint8_t* img = mst->ks_scratch;
+            double* Ki = (double*)(img + (size_t)nt * KB * 2 * tc::A_BLK);
+            double* sx = Ki + nt * tc::TM;
+            const double* Xc = X + r0 * (long)gp.D;
+            tc::ks_image_kernel<<<(unsigned)nt, 256, 0, stream>>>(gp, Xc, rc, KB, img, Ki, sx);
+            SC_LAUNCH_CHECK();
+            double* p0 = out0 + r0; double* p1 = out1 ? out1 + r0 : nullptr; double* p2 = out2 ? out2 + r0 : nullptr; double* p3 = out3 ? out3 + r0 : nullptr;
+            int rcode;
+            if (cls == TC_U) rcode = tc::launch_ks<TC_U>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
+            else if (cls == TC_UG) rcode = tc::launch_ks<TC_UG>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
+            else rcode = tc::launch_ks<TC_PDE>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
+            if (rcode != OK) return rcode;
+        }
+        return OK;
+    }
 #define SC_TC_DISPATCH(NS)                                                                                                  \
     do {                                                                                                                    \
         if (dv.gen != nullptr) {                                                                                            \

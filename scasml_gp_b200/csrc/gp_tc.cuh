@@ -42,6 +42,8 @@ struct TcState {
     size_t spec_off = 0;                             // TcColSpec[3][TC_MAXCOL]
     size_t scratch_off = 0;                          // double [3][ncentres][TC_MAXCOL] + column maxima
     TcColSpec spec[3][TC_MAXCOL];                    // host copy
+    uint8_t* ks_scratch = nullptr;   // K-streamed kernel (d + 2 > 128): point images of the chunk being evaluated (grown on demand)
+    size_t ks_scratch_bytes = 0;
     long long* dbg = nullptr;        // optional timeline buffer (clock64 stamps of CTA dbg_block), see scasml_debug_tc_timeline
     int dbg_block = 0;
 };

@@ -68,7 +68,12 @@ def _eval_both(F, X):
     return out
 
 
-@pytest.mark.parametrize("which", ["mid", "wide"])
+@pytest.fixture(scope="module")
+def huge():
+    return Fitted(d=300, nd=150, nb=40)      # d + 2 > 128: K-streamed kernel (5 K blocks, partial last block)
+
+
+@pytest.mark.parametrize("which", ["mid", "wide", "huge"])
 def test_tc_eval_matches_fp64_route_and_oracle(which, request):
     F = request.getfixturevalue(which)
     lib = F.P["lib"]
@@ -129,14 +134,33 @@ def test_fused_sampler_is_bit_identical_to_the_sampler_kernels(mid):
         assert np.array_equal(outs[0], outs[1], equal_nan=True)
 
 
+def test_k_streamed_kernel_in_the_solver(huge):
+    """d = 300: the solver's sampled points go through the K-streamed tcgen05 kernel (point images streamed per 64-wide K block)."""
+    F, P = huge, huge.P
+    lib = P["lib"]
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(20, 5)
+    exact = F.eq_o.exact_solution(X)
+    prod = P["ScaSML"](F.eq, F.gp)
+    assert prod.route is None                                # default: tcgen05 wherever the GP supports it
+    prod.quadrature = "gauss_legendre"
+    prod.u_solve(2, 2, X)
+    orac = ScaSMLOracle(F.eq_o, F.gp_o, cast=False, true_gl=True)
+    orac.u_solve(2, 2, X)
+    assert np.max(np.abs(prod.last_raw_u - orac.last_raw_u)) < 5e-6
+    l2_p, l1_p = _rel_l2(prod.last_raw_u, exact)
+    l2_o, l1_o = _rel_l2(orac.last_raw_u, exact)
+    assert abs(l2_p - l2_o) <= 1e-5 * l2_o and abs(l1_p - l1_o) <= 1e-5 * l1_o
+
+
 def test_tc_route_rejects_large_d():
     P = _product()
     lib = P["lib"]
-    eq = P["Eq"](201)
+    eq = P["Eq"](1031)
     gp = P["GP"](eq)
     rng = np.random.default_rng(0)
-    dom = rng.uniform(-0.5, 0.5, (64, 201)).astype(np.float16)
-    bdy = rng.uniform(-0.5, 0.5, (16, 201)).astype(np.float16)
+    dom = rng.uniform(-0.5, 0.5, (64, 1031)).astype(np.float16)
+    bdy = rng.uniform(-0.5, 0.5, (16, 1031)).astype(np.float16)
     gp._bind(dom, bdy)
     gp.set_right_vector(np.zeros(4 * 64 + 16))
     assert lib.load().scasml_gp_tc_supported(gp._handle) == 0
