@@ -71,7 +71,7 @@ typedef struct scasml_picard_params {
     int rank, world;                 /* top-level sample sharding (unit u owned iff u % world == rank) */
     long long gid0;                  /* global index of the first row of x_t (RNG addressing) */
     int timing;                      /* 1: bracket kernel groups with CUDA events (adds a stream sync at the end) */
-    int reserved;
+    int reserved;                    /* flags; bit 0: tcgen05 route draws the points inside the evaluation kernel (fused sampler, opt-in) */
 } scasml_picard_params;
 
 typedef struct scasml_picard_stats {
@@ -159,7 +159,7 @@ SCASML_API int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int it
 /* micro-benchmark of the epilogue pipes (csrc/tc_bench.cu: TMEM load/store, MUFU, split chunk, MMA interference);
  * out_dev: 8 int64: [0] epilogue-warp cycles, [1] MMA issue cycles, [2] MMA cycles until commit, [3] MMA count */
 SCASML_API int scasml_debug_tc_pipe_bench(int mode, int N, int iters, long long* out_dev, void* stream);
-/* 1 if this handle can use SCASML_ROUTE_TC (d <= 100) */
+/* 1 if this handle can use SCASML_ROUTE_TC (d <= 1022: resident-operand kernel up to d = 126, K-streamed kernel above) */
 SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 
 #ifdef __cplusplus

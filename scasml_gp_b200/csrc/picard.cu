@@ -376,17 +376,18 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
 
     // stream the rows of a chunk: weight cw (0 for inactive lanes) and point index pt live in the lanes
     auto stream_rows = [&](int n, double cw, long long pt) {
+        constexpr int UNR = 4;                                        // rows in flight per lane (fewer rows for more occupancy measured slower)
         int i = 0;
-        for (; i + 4 <= n; i += 4) {
-            double ci[4]; const double* xp[4]; double v[4][JCH];
+        for (; i + UNR <= n; i += UNR) {
+            double ci[UNR]; const double* xp[UNR]; double v[UNR][JCH];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { ci[u] = __shfl_sync(0xffffffffu, cw, i + u); xp[u] = lv.P + __shfl_sync(0xffffffffu, pt, i + u) * D; }
+            for (int u = 0; u < UNR; ++u) { ci[u] = __shfl_sync(0xffffffffu, cw, i + u); xp[u] = lv.P + __shfl_sync(0xffffffffu, pt, i + u) * D; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < UNR; ++u)
 #pragma unroll
                 for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; v[u][q] = (j < d) ? __ldg(xp[u] + j) : 0.0; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < UNR; ++u)
 #pragma unroll
                 for (int q = 0; q < JCH; ++q) zacc[q] = fma(ci[u], v[u][q], zacc[q]);
         }
@@ -646,7 +647,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         SC_CUDA(cudaMemcpyAsync(ws + lr.off_rowbase, rb.data(), rb.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
     }
     // fused sampler (tcgen05 route, ScaSML): the evaluation kernel's loader warps draw the points; needs the level records on the device
-    const bool fused = (route == 1) && p_.scasml && !(p_.reserved & 1);
+    const bool fused = (route == 1) && p_.scasml && (p_.reserved & 1) && gp->D + 1 <= 128;
     if (fused)
         for (int L = 1; L <= n; ++L)
             SC_CUDA(cudaMemcpyAsync(ws + levels_[L].off_lvdev, &lvs[L], sizeof(LevelDev), cudaMemcpyHostToDevice, stream));

@@ -30,7 +30,7 @@ struct PicardParams {
     int rank, world;          // top-level sample sharding: unit u owned iff u % world == rank
     long long gid0;           // global index of the first test point of this batch
     int timing;               // 1: CUDA-event timing of kernel groups (adds a stream sync)
-    int reserved;             // bit 0: keep the stand-alone sampler kernels on the tcgen05 route (no fused sampler)
+    int reserved;             // flags; bit 0: fused sampler on the tcgen05 route (the evaluation kernel's loader warps draw the points)
 };
 
 struct PicardStats {

@@ -157,7 +157,7 @@ class PicardSolverBase(object):
         p.seed, p.key_counter = int(self.seed), int(self.key) & 0xFFFFFFFF
         p.rank, p.world, p.gid0 = int(rank), int(world), 0
         p.timing = int(self.timing)
-        p.reserved = 0 if self.fused_sampler else 1
+        p.reserved = 1 if self.fused_sampler else 0
         return p
 
     def plan(self, n, rho, B, M=None, rank=0, world=1):
