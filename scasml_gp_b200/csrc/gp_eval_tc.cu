@@ -210,8 +210,10 @@ constexpr uint32_t B1_BLK = TN * 128;                                // one K bl
 constexpr int A_PITCH = 240;                                         // staging row pitch (bytes): 16-byte reads of 8 rows hit 8 bank groups
 constexpr int NLOAD = 4;                                             // loader warps
 constexpr int NTHREADS_P = (NEPI + 2 + NLOAD) * 32;
-// barriers: b1_full b3_full b3_empty s_full p_ready (NSLOT each) | t_full t_free a_ready stage_full stage_free
-constexpr int NBAR = 5 * NSLOT + 5;
+constexpr int NB1_MAX = 4;                                           // centre-row ring (decoupled from the S/P slots: the bulk-copy latency
+                                                                     // of pair j + 2 must not wait for stage 1 of pair j)
+// barriers: b1_full b1_empty (NB1_MAX each) | b3_full b3_empty s_full p_ready (NSLOT each) | t_full t_free a_ready stage_full stage_free
+constexpr int NBAR = 2 * NB1_MAX + 4 * NSLOT + 5;
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -364,16 +366,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     constexpr uint32_t B3_SUB = 2 * NMAX * 128;                      // one class's coefficient images (hi | lo)
     constexpr uint32_t B3_SLOT = 2 * B3_SUB;                         // a pair
     constexpr uint32_t B1_SLOT = KB * 2 * B1_BLK;                    // a pair's centre rows: per K block [sub-item a rows | sub-item b rows]
+    constexpr int NB1 = (PDE && GEN) ? 2 : 3;                        // centre-row ring depth (shared-memory budget)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
-    uint8_t* sB1 = smem;                                             // NSLOT item slots
-    uint8_t* sB3 = sB1 + NSLOT * (size_t)B1_SLOT;                    // NSLOT item slots
+    uint8_t* sB1 = smem;                                             // NB1 pair slots
+    uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NSLOT pair slots
     uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
     double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
-    double* xchg = feat + TM * TF_COUNT;                             // [3][128][4] partial sums of column groups 1..3
-    TcColDesc* sdesc = (TcColDesc*)(xchg + 3 * TM * 4);              // [TC_MAXCOL] column table (f1, f2, output, 1 / scale)
+    double* xchg = feat;                                             // [3][128][4] partial sums of column groups 1..3 (aliases feat, see below)
+    TcColDesc* sdesc = (TcColDesc*)(feat + TM * TF_COUNT);              // [TC_MAXCOL] column table (f1, f2, output, 1 / scale)
     GenRec* grec = (GenRec*)(sdesc + TC_MAXCOL);                     // [128] fused sampler: resolved points of the tile being staged
     double* Ki = (double*)(grec + (GEN ? TM : 0));                       // [128] exp(-a |x|^2 / 2) of the staged tile
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
@@ -389,16 +392,18 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     if (tid == 0) TC_STAMP(0);
     const uint32_t bar0 = smem_u32(bars);
     auto b1_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    auto b3_full = [&](int i) { return bar0 + 8u * (uint32_t)(NSLOT + i); };
-    auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NSLOT + i); };
-    auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(3 * NSLOT + i); };
-    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(4 * NSLOT + i); };
-    const uint32_t t_full = bar0 + 8u * (uint32_t)(5 * NSLOT), t_free = t_full + 8u, a_ready = t_full + 16u,
+    auto b1_empty = [&](int i) { return bar0 + 8u * (uint32_t)(NB1_MAX + i); };
+    auto b3_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + i); };
+    auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + NSLOT + i); };
+    auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NSLOT + i); };
+    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 3 * NSLOT + i); };
+    const uint32_t t_full = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 4 * NSLOT), t_free = t_full + 8u, a_ready = t_full + 16u,
                    stage_full = t_full + 24u, stage_free = t_full + 32u;
 
     if (tid == 0) {
+        for (int i = 0; i < NB1_MAX; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
         for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(b1_full(i), 1); mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI);
+            mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI);
         }
         mbar_init(t_full, 1); mbar_init(t_free, NEPI); mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
         fence_barrier_init();
@@ -434,8 +439,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             int t1 = 0, k1 = TK_K, j1 = 0, t3 = 0, k3 = TK_K, j3 = 0;    // sub-item cursors / pair index inside the point tile
             int p1 = 0;
             auto load_b1 = [&]() {
-                const int s = p1 % NSLOT;
-                if (p1 >= NSLOT) mbar_wait(s_full(s), (uint32_t)((p1 / NSLOT) - 1) & 1u);
+                const int s = p1 % NB1;
+                if (p1 >= NB1) mbar_wait(b1_empty(s), (uint32_t)((p1 / NB1) - 1) & 1u);
                 const bool two = 2 * j1 + 1 < nitem;
                 mbar_expect_tx(b1_full(s), (two ? 2u : 1u) * KB * B1_BLK);
                 uint8_t* dst = sB1 + (size_t)s * B1_SLOT;
@@ -451,7 +456,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 ++p1;
             };
             for (int p = 0; p < ptotal; ++p) {
-                while (p1 < ptotal && p1 < p + NSLOT) load_b1();
+                while (p1 < ptotal && p1 < p + NB1) load_b1();               // centre rows run NB1 - 1 pairs ahead of the coefficient images
                 const int s = p % NSLOT;
                 if (p >= NSLOT) mbar_wait(b3_empty(s), (uint32_t)((p / NSLOT) - 1) & 1u);
                 const bool two = 2 * j3 + 1 < nitem;
@@ -486,7 +491,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const bool nocopy = (st.dbg_flags & 8) != 0;
         int p1 = 0, p2 = 0;                                          // global pair counters of the two stages
         bool rdy1 = false, rdy2 = false;                             // early probe results for the next stage-1 / stage-2 batch
-        auto probe1 = [&]() { rdy1 = nocopy || mbar_test_wait(b1_full(p1 % NSLOT), (uint32_t)(p1 / NSLOT) & 1u); };
+        auto probe1 = [&]() { rdy1 = nocopy || mbar_test_wait(b1_full(p1 % NB1), (uint32_t)(p1 / NB1) & 1u); };
         auto probe2 = [&]() {
             const int s = p2 % NSLOT;
             const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
@@ -507,8 +512,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 const uint32_t accS = tmem_base + (uint32_t)s * 128u;
                 const uint32_t idesc = (2 * j + 1 < nitem) ? idS2 : idS1;
                 if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
-                if (!rdy1 && !nocopy) mbar_wait(b1_full(s), (uint32_t)(p1 / NSLOT) & 1u);   // bulk-copy bytes landed (async proxy)
-                const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s * B1_SLOT) >> 4);
+                const int s1 = p1 % NB1;
+                if (!rdy1 && !nocopy) mbar_wait(b1_full(s1), (uint32_t)(p1 / NB1) & 1u);   // bulk-copy bytes landed (async proxy)
+                const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
                 ++p1;
                 rdy1 = false;
 #pragma unroll
@@ -529,7 +535,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         if (kb == 0 && half == 1) probe2();          // the queue is full: probe the barriers of the next stage-2 batch
                     }
                 }
-                if (el) umma_commit(s_full(s));                      // accumulators ready; the centre-row slot is reusable
+                if (el) { umma_commit(b1_empty(s1)); umma_commit(s_full(s)); }   // centre-row slot reusable; accumulators ready
                 __syncwarp();
             };
             auto stage2 = [&](int j) {
@@ -560,14 +566,19 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
                     const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
                     if (el && !(st.dbg_flags & 1)) {
+                        const bool only_hh = (st.dbg_flags & 32) != 0;   // timeline experiment: 4 instead of 12 MMAs (wrong results)
                         if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
-                        umma_ts<true>(tacc, pbase, clo0, idesc);
-                        umma_ts<true>(tacc, pbase + 8u, b3, idesc);
+                        if (!only_hh) {
+                            umma_ts<true>(tacc, pbase, clo0, idesc);
+                            umma_ts<true>(tacc, pbase + 8u, b3, idesc);
+                        }
 #pragma unroll
                         for (int ks = 1; ks < 4; ++ks) {
                             umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
-                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
-                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                            if (!only_hh) {
+                                umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
+                                umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                            }
                         }
                     }
                     if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
@@ -745,6 +756,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     run = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, run);      // padded columns: inv_scale = 0
                 }
                 flush(cur);
+                const double f_sx = F[TF_SX], f_xt = F[TF_XT];
+                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // everyone is done with the features: xchg reuses their storage
                 if (cg > 0) {
                     double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
                     p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
@@ -759,7 +772,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const double ki = ki_prev;
                     const double u = ki * aU;
                     if (CLASS == TC_U) {
-                        const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));              // equations.py:259
+                        const double gt = 1.0 - 1.0 / (1.0 + exp(f_sx + f_xt));                      // equations.py:259
                         out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
                     } else if (CLASS == TC_UG) {
                         out0[row] = u;
@@ -827,8 +840,8 @@ template <int CLASS, int NSTEP, bool GEN>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    return NSLOT * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
-           + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8 + TC_MAXCOL * sizeof(TcColDesc) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + NBAR * 8 + 16;
+    return ((CLASS == TC_PDE && GEN) ? 2 : 3) * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
+           + (size_t)TM * TF_COUNT * 8 + TC_MAXCOL * sizeof(TcColDesc) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + NBAR * 8 + 16;
 }
 
 template <int CLASS, int NSTEP, bool GEN>
