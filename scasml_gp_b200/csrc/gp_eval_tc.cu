@@ -209,11 +209,11 @@ constexpr int NSLOT = 2;                                             // S/P pair
 constexpr uint32_t B1_BLK = TN * 128;                                // one K block of one class: [64 rows x 128 B]
 constexpr int A_PITCH = 240;                                         // staging row pitch (bytes): 16-byte reads of 8 rows hit 8 bank groups
 constexpr int NLOAD = 4;                                             // loader warps
-constexpr int NTHREADS_P = (NEPI + 2 + NLOAD) * 32;
+constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 1) * 32;             // epilogue | producer | stage-1 issuer | loaders | stage-2 issuer
 constexpr int NB1_MAX = 4;                                           // centre-row ring (decoupled from the S/P slots: the bulk-copy latency
                                                                      // of pair j + 2 must not wait for stage 1 of pair j)
-// barriers: b1_full b1_empty (NB1_MAX each) | b3_full b3_empty s_full p_ready (NSLOT each) | t_full t_free a_ready stage_full stage_free
-constexpr int NBAR = 2 * NB1_MAX + 4 * NSLOT + 5;
+// barriers: b1_full b1_empty (NB1_MAX each) | b3_full b3_empty s_full p_ready s2_issued (NSLOT each) | t_full t_free a_ready stage_full stage_free
+constexpr int NBAR = 2 * NB1_MAX + 5 * NSLOT + 5;
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -397,13 +397,14 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + NSLOT + i); };
     auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NSLOT + i); };
     auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 3 * NSLOT + i); };
-    const uint32_t t_full = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 4 * NSLOT), t_free = t_full + 8u, a_ready = t_full + 16u,
+    auto s2_issued = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 4 * NSLOT + i); };
+    const uint32_t t_full = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 5 * NSLOT), t_free = t_full + 8u, a_ready = t_full + 16u,
                    stage_full = t_full + 24u, stage_free = t_full + 32u;
 
     if (tid == 0) {
         for (int i = 0; i < NB1_MAX; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
         for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI);
+            mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI); mbar_init(s2_issued(i), 1);
         }
         mbar_init(t_full, 1); mbar_init(t_free, NEPI); mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
         fence_barrier_init();
@@ -477,42 +478,31 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         }
         __syncwarp();
     } else if (warp == NEPI + 1) {
-        // ===== MMA issuer: the warp stays converged and one elected lane issues (warp-uniform operands come from uniform
-        // registers; a divergent `if (lane == 0)` block compiles to a per-lane serialisation loop around each MMA).
-        // Every barrier operation of this lone thread costs ~100 cycles of latency (tools/tc_timeline.py), so an item is one
-        // wait + 14 MMAs + one commit in stage 1 and one combined wait + 12 MMAs + one commit in stage 2, and the barrier of
-        // the NEXT batch is probed (non-blocking) in the middle of the current batch, while the MMA queue is full. =====
+        // ===== stage-1 issuer.  The MMA queue is shallow (the issuing thread is blocked until its MMAs are almost done) and every
+        // barrier operation of a lone thread costs ~100 cycles, so with ONE issuer the tensor pipe drains during the commits /
+        // waits between batches (~700 cycles per pair, tools/tc_timeline.py).  Two issuers -- this warp for the distance GEMMs,
+        // warp NEPI + 2 + NLOAD for the coefficient GEMMs -- keep it fed: while one does its housekeeping the other one issues.
+        // Each warp stays converged and one elected lane issues (warp-uniform operands come from uniform registers). =====
         const uint32_t el = elect_one();
         const uint64_t b1desc0 = make_desc(smem_u32(sB1), 1, 64, 2);
-        const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
         const uint32_t idS2 = make_idesc(TM, 2 * TN), idS1 = make_idesc(TM, TN);
-        const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
         const uint32_t aBase = tmem_base + COL_A;
         const bool nocopy = (st.dbg_flags & 8) != 0;
-        int p1 = 0, p2 = 0;                                          // global pair counters of the two stages
-        bool rdy1 = false, rdy2 = false;                             // early probe results for the next stage-1 / stage-2 batch
-        auto probe1 = [&]() { rdy1 = nocopy || mbar_test_wait(b1_full(p1 % NB1), (uint32_t)(p1 / NB1) & 1u); };
-        auto probe2 = [&]() {
-            const int s = p2 % NSLOT;
-            const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
-            const bool a = mbar_test_wait(p_ready(s), par);
-            const bool b = nocopy || mbar_test_wait(b3_full(s), par);
-            rdy2 = a && b;
-            if (rdy2) tc_fence_after();                              // hoisted: the MMA queue is full while this executes
-        };
+        int p1 = 0;                                                  // global pair counter
+        bool rdy1 = false;                                           // early probe result for the next batch's centre rows
         for (int it = 0; it < nit; ++it) {
             const bool stamp = (it == 1);
             if (el && it == 1) TC_STAMP(244);
             mbar_wait(a_ready, (uint32_t)it & 1u);                   // A images of this point tile are in tensor memory
             tc_fence_after();
-            bool first_k = true, first_kx = true, first_ky = true;
-            int kc2 = TK_K, t2 = 0;                                  // (tile, class) of the next stage-2 sub-item
-            auto stage1 = [&](int j) {
-                const int s = p1 % NSLOT;
+            for (int j = 0; j < npair; ++j) {
+                const int s = p1 % NSLOT, s1 = p1 % NB1;
                 const uint32_t accS = tmem_base + (uint32_t)s * 128u;
                 const uint32_t idesc = (2 * j + 1 < nitem) ? idS2 : idS1;
                 if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
-                const int s1 = p1 % NB1;
+                // the slot's previous P has been consumed: stage 2 of pair p1 - NSLOT (issued by the other warp) has COMPLETED (handing the
+                // slot back as soon as those MMAs are issued -- tcgen05.mma executes in issue order -- measured no faster)
+                if (p1 >= NSLOT) { mbar_spin(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); tc_fence_after(); }
                 if (!rdy1 && !nocopy) mbar_wait(b1_full(s1), (uint32_t)(p1 / NB1) & 1u);   // bulk-copy bytes landed (async proxy)
                 const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
                 ++p1;
@@ -532,15 +522,28 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                                 }
                             }
                         }
-                        if (kb == 0 && half == 1) probe2();          // the queue is full: probe the barriers of the next stage-2 batch
+                        if (kb == 0 && half == 1 && !nocopy && (j + 1 < npair || it + 1 < nit))      // probe the next batch's centre rows
+                            rdy1 = mbar_test_wait(b1_full(p1 % NB1), (uint32_t)(p1 / NB1) & 1u);
                     }
                 }
                 if (el) { umma_commit(b1_empty(s1)); umma_commit(s_full(s)); }   // centre-row slot reusable; accumulators ready
                 __syncwarp();
-            };
-            auto stage2 = [&](int j) {
+            }
+        }
+    } else if (warp == NEPI + 2 + NLOAD) {
+        // ===== stage-2 issuer: T += P C for every sub-item of a pair, in pair order (deterministic accumulation order) =====
+        const uint32_t el = elect_one();
+        const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
+        const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
+        const bool nocopy = (st.dbg_flags & 8) != 0;
+        int p2 = 0;
+        for (int it = 0; it < nit; ++it) {
+            const bool stamp = (it == 1);
+            bool first_k = true, first_kx = true, first_ky = true;
+            int kc2 = TK_K, t2 = 0;                                  // (tile, class) of the next sub-item
+            for (int j = 0; j < npair; ++j) {
                 const int s = p2 % NSLOT;
-                if (!rdy2) {   // P written over S by all epilogue warps + coefficient images landed: one polling loop for both
+                {   // P written over S by all epilogue warps + coefficient images landed: one polling loop for both barriers
                     const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
                     uint32_t spins = 0;
                     bool a = false, b = nocopy;
@@ -550,11 +553,10 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         if (a && b) break;
                         if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
                     }
-                    tc_fence_after();
                 }
-                if (j == 0 && it > 0) { mbar_wait(t_free, (uint32_t)(it - 1) & 1u); tc_fence_after(); }   // T of the previous point tile was read
+                if (j == 0 && it > 0) mbar_wait(t_free, (uint32_t)(it - 1) & 1u);   // T of the previous point tile was read
+                tc_fence_after();
                 ++p2;
-                rdy2 = false;
                 const int nsub = (2 * j + 1 < nitem) ? 2 : 1;
                 for (int sub = 0; sub < nsub; ++sub) {
                     const uint32_t pbase = tmem_base + (uint32_t)s * 128u + (uint32_t)sub * 64u;
@@ -583,23 +585,15 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
                     if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
                     next_item(t2, kc2);
-                    if (sub == 0 && (j + NSLOT < npair || it + 1 < nit)) probe1();   // probe the centre rows of the next stage-1 batch
                 }
-                if (el) { umma_commit(b3_empty(s)); if (stamp && j < 60) TC_STAMP(5 + 4 * j); }
+                if (el) { umma_commit(b3_empty(s)); if (stamp && j < 60) TC_STAMP(5 + 4 * j); }   // P consumed (stage-1 issuer, producer)
                 __syncwarp();
-            };
-            // stage 2 of pair j is followed by stage 1 of pair j + 2 (same S slot): the big MMAs sit in the queue while this
-            // thread works through the next barrier operations
-            for (int j = 0; j < NSLOT && j < npair; ++j) stage1(j);
-            for (int j = 0; j < npair; ++j) {
-                stage2(j);
-                if (j + NSLOT < npair) stage1(j + NSLOT);
             }
             if (el) umma_commit(t_full);
             if (el && it == 0) TC_STAMP(248);
             __syncwarp();
         }
-    } else if (warp >= NEPI + 2) {
+    } else if (warp >= NEPI + 2 && warp < NEPI + 2 + NLOAD) {
         // ===== loader warps: stage the NEXT point tile while the current one is in the main loop.
         // a' x = hi + lo (f16) into the staging buffer, K_i and row sums.  Two rows per warp pass (16 lanes x 8 columns). =====
         const int lw = warp - (NEPI + 2);

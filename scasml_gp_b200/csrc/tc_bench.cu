@@ -10,6 +10,8 @@
 //   mode 7  mode 6 with a tcgen05.commit (to a barrier nobody waits on) after every 7 MMAs
 //   mode 8  mode 6 with commit + tcgen05.fence + an mbarrier poll on an already-completed barrier after every 7 MMAs
 //   mode 9  mode 3 (epilogue chunk loop) with the MMA warp issuing TS-mode MMAs concurrently
+//   mode 10 MMA warp alone: TS-mode, one N = 128 MMA followed by two N = 16 MMAs into another accumulator (shape switching)
+//   mode 11 like 10, batched: 14 x N = 128 then 24 x N = 16
 #include "common.cuh"
 #include "gp_tc.cuh"
 #include "tc_ptx.cuh"
@@ -302,14 +304,36 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
         if (mode >= 4) {
             const uint32_t idesc = make_idesc(128, N);
             const uint64_t ad = make_desc(smem_u32(sA), 1, 64, 2), bd = make_desc(smem_u32(sB), 1, 64, 2);
-            const int nmma = (mode == 4 || mode == 9) ? iters * 2 : iters;
+            const int nmma = (mode == 4 || mode == 9) ? iters * 2 : (mode >= 10 ? 38 * 32 : iters);
             uint64_t& bar2 = *(uint64_t*)(smem + 128 * 128 + 256 * 128 + 16);
             uint64_t& bar3 = *(uint64_t*)(smem + 128 * 128 + 256 * 128 + 24);
             if (el) { mbar_init(smem_u32(&bar2), 1); mbar_init(smem_u32(&bar3), 1); mbar_arrive(smem_u32(&bar3)); fence_barrier_init(); }
             __syncwarp();
             const uint32_t acc = tmem_base + 256u;
             const long long t0 = clock64();
-            if (mode == 7 || mode == 8) {
+            if (mode == 10 || mode == 11) {
+                const uint32_t id128 = make_idesc(128, 128), id16 = make_idesc(128, 16);
+                for (int it = 0; it < nmma; it += 38) {
+                    if (el) {
+                        if (mode == 10) {
+#pragma unroll
+                            for (int q = 0; q < 12; ++q) {
+                                umma_f16_ts(acc, tmem_base + 480u + (uint32_t)(q & 1) * 8u, bd + (uint64_t)((q & 3) * 2), id128, 1u);
+                                umma_f16_ts(tmem_base + 448u, tmem_base + 496u, bd, id16, 1u);
+                                umma_f16_ts(tmem_base + 448u, tmem_base + 504u, bd + 2ull, id16, 1u);
+                            }
+                            umma_f16_ts(acc, tmem_base + 480u, bd, id128, 1u);
+                            umma_f16_ts(acc, tmem_base + 488u, bd + 2ull, id128, 1u);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 14; ++q) umma_f16_ts(acc, tmem_base + 480u + (uint32_t)(q & 1) * 8u, bd + (uint64_t)((q & 3) * 2), id128, 1u);
+#pragma unroll
+                            for (int q = 0; q < 24; ++q) umma_f16_ts(tmem_base + 448u, tmem_base + 496u + (uint32_t)(q & 1) * 8u, bd + (uint64_t)((q & 3) * 2), id16, 1u);
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else if (mode == 7 || mode == 8) {
                 for (int it = 0; it < nmma; it += 7) {
                     if (mode == 8) { mbar_wait(smem_u32(&bar3), 0); tc_fence_after(); }
                     if (el) {
@@ -351,7 +375,7 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
 }  // namespace tc
 
 int tc_pipe_bench(int mode, int N, int iters, long long* out_dev, cudaStream_t stream) {
-    SC_REQUIRE(mode >= 0 && mode <= 9 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && iters % 448 == 0, "pipe_bench: arguments");
+    SC_REQUIRE(mode >= 0 && mode <= 11 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && iters % 448 == 0, "pipe_bench: arguments");
     const size_t smem = 128 * 128 + 256 * 128 + 64;
     SC_CUDA(cudaFuncSetAttribute(tc::pipe_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SC_CUDA(cudaMemsetAsync(out_dev, 0, 8 * sizeof(long long), stream));

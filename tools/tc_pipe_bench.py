@@ -39,3 +39,6 @@ for mode, name in ((7, "TS + commit/7"), (8, "TS + commit/7 + poll")):
 for N in (16, 64, 128):
     o = run(9, N)
     print(f"split chunk + TS MMA N={N}: {o[0]/iters:.1f} cyc per chunk/warp ({512*16*iters/o[0]:.2f} pairs/clk/SM); MMA {o[2]/max(o[3],1):.1f} cyc/instr")
+for mode, name in ((10, "TS interleaved 1 x N=128 + 2 x N=16"), (11, "TS batched 14 x N=128 then 24 x N=16")):
+    o = run(mode, 128)
+    print(f"MMA {name}: {38 * o[2] / o[3]:.0f} cycles per (14 + 24) MMAs (expected 14 x 68 + 24 x 17 = 1360)")
