@@ -841,16 +841,12 @@ static size_t smem_bytes() {
 template <int CLASS, int NSTEP, bool GEN>
 static int launch(const GpView& gp, const TcDev& st, const double* X, long R, int mode,
                   double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
-    static bool configured = false;
-    static int nsm = 0;
+    // per-device attributes: set / queried on every launch (microseconds) so that a process may use several devices
     const size_t smem = smem_bytes<CLASS, NSTEP, GEN>();
-    if (!configured) {
-        SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0;
-        SC_CUDA(cudaGetDevice(&dev));
-        SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
-    }
+    int dev = 0, nsm = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long ntiles = cdiv(R, TM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);   // persistent: one CTA per SM
     eval_tc_kernel<CLASS, NSTEP, GEN><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
@@ -1237,15 +1233,10 @@ static int launch_ks(const GpView& gp, const TcDev& st, const double* X, long R,
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     const size_t smem = KS_STAGES * (size_t)KS_STAGE_BYTES + NSLOT * (2 * 2 * NMAX * 128) + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8
                         + TC_MAXCOL * sizeof(TcColDesc) + KS_NBAR * 8 + 16;
-    static bool configured = false;
-    static int nsm = 0;
-    if (!configured) {
-        SC_CUDA(cudaFuncSetAttribute(eval_tc_ks_kernel<CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0;
-        SC_CUDA(cudaGetDevice(&dev));
-        SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
-    }
+    int dev = 0, nsm = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SC_CUDA(cudaFuncSetAttribute(eval_tc_ks_kernel<CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long ntiles = cdiv(R, TM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
     eval_tc_ks_kernel<CLASS><<<grid, KS_THREADS, smem, stream>>>(gp, st, X, R, mode, img, Ki, sxs, o0, o1, o2, o3);
