@@ -316,7 +316,7 @@ __device__ __forceinline__ void gen_point(const LevelDev& lv, const GenRec& g, l
         double N[8];
         normals(make_key(0u, 0u, lv.seed), N);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) X[e] = (X[e] + drift) + lv.sigma * (sq * N[e]);
+        for (int e = 0; e < 8; ++e) X[e] = __dadd_rn(__dadd_rn(X[e], drift), __dmul_rn(lv.sigma, __dmul_rn(sq, N[e])));   // explicit roundings, as picard.cu
     } else if (lv.variant == 0) {
         double tprev = t;
         for (int kk = 0; kk <= k; ++kk) {
@@ -327,7 +327,7 @@ __device__ __forceinline__ void gen_point(const LevelDev& lv, const GenRec& g, l
             double N[8];
             normals(make_key(valid ? g.call->key[lk] : 0u, 1u, lv.seed), N);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) X[e] = X[e] + (drift + lv.sigma * (sq * N[e]));
+            for (int e = 0; e < 8; ++e) X[e] = __dadd_rn(X[e], __dadd_rn(drift, __dmul_rn(lv.sigma, __dmul_rn(sq, N[e]))));
             tprev = tk;
         }
         tcol = tprev;
@@ -339,7 +339,7 @@ __device__ __forceinline__ void gen_point(const LevelDev& lv, const GenRec& g, l
         double N[8];
         normals(kT, N);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) X[e] = X[e] + (drift + lv.sigma * (sq * N[e]));
+        for (int e = 0; e < 8; ++e) X[e] = __dadd_rn(X[e], __dadd_rn(drift, __dmul_rn(lv.sigma, __dmul_rn(sq, N[e]))));
         tcol = t + steps;
     }
     if (valid) {

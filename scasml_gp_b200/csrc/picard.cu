@@ -154,6 +154,7 @@ int PicardPlan::build(const PicardParams& p, long B) {
         executed += pt;
         lv.off_P = take((size_t)pt * D * sizeof(double));
         lv.off_gid = take((size_t)pt * sizeof(long long));
+        lv.off_rows = take((size_t)lv.NR * sizeof(RowRec));
         lv.off_ev0 = take((size_t)pt * sizeof(double));
         lv.off_ev1 = take((size_t)pt * sizeof(double));
         lv.off_us = take((size_t)lv.NR * 2 * sizeof(double));
@@ -182,133 +183,225 @@ __device__ __forceinline__ int find_call(const LevelDev& lv, long long R) { retu
 
 __device__ __forceinline__ long long ceil_div_pos(long long a, long long b) { return a <= 0 ? 0 : (a + b - 1) / b; }
 
-// Sampler kernels.  A thread owns one Philox block (8 consecutive flat indices) of one point; the CTA stages its
-// points in shared memory and writes them out as one contiguous, fully coalesced range of the level's point buffer.
-constexpr int SAMPLE_THREADS = 256;
-constexpr int SAMPLE_TILE = 2304;      // doubles; (256 / nslot) * (d + 1) < 2048 for every d with nslot <= 256
+// Row records of a level: one thread per row resolves (call, parent point, global id, time) once; the samplers and the
+// reduction then start from a single 32-byte load.
+__global__ void __launch_bounds__(256) row_setup_kernel(LevelDev lv) {
+    const long long R = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (R >= lv.NR) return;
+    const int ci = find_call(lv, R);
+    const CallDev& c = lv.calls[ci];
+    const long long i = R - c.rowbase;
+    RowRec r;
+    r.x = c.xsrc + i * lv.D;
+    r.gid = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
+    r.t = r.x[lv.d];
+    r.call = ci; r.pad = 0;
+    lv.rows[R] = r;
+}
 
-// terminal points X_T = x + mu (T-t) + sigma sqrt(T-t) N   (solvers/ScaSML.py:190-198)
-__global__ void __launch_bounds__(SAMPLE_THREADS) sample_terminal_kernel(LevelDev lv, int ppb) {
-    __shared__ double tile[SAMPLE_TILE];
-    const int d = lv.d, D = lv.D;
-    const int nslot = (d + 14) / 8;
-    const int p = threadIdx.x / nslot, b = threadIdx.x % nslot;
-    const long long s0 = (long long)blockIdx.x * ppb;
-    const long long s = s0 + p;
-    const bool active = (p < ppb) && (s < lv.NT);
-    if (active) {
-        const long long u = lv.rank + (long long)lv.world * s;
-        const long long R = u / lv.MCg;
-        const int m = (int)(u - R * lv.MCg);
-        const CallDev& c = lv.calls[find_call(lv, R)];
-        const long long i = R - c.rowbase;
-        const double* x = c.xsrc + i * D;
-        const long long gidrow = c.gidsrc ? c.gidsrc[i] : lv.gid0 + i;
-        const double t = x[d];
-        const double Tt = lv.T - t, sq = sqrt(Tt), drift = lv.mu * Tt;
-        const unsigned long long f0 = (unsigned long long)(gidrow * lv.MCg + m) * (unsigned long long)d;
-        const unsigned long long blk = (f0 >> 3) + (unsigned long long)b;
-        const uint4 w = philox4x32_10(blk, make_key(0u, 0u, lv.seed));
-        double* dst = tile + p * D;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const long long j = (long long)(blk * 8ull + e) - (long long)f0;
-            if (j >= 0 && j < d) {
-                const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
-                dst[j] = (x[j] + drift) + lv.sigma * (sq * N);
-            }
-        }
-        if (b == 0) dst[d] = lv.T;
-    }
+// Sampler kernels.  Persistent CTAs keep the 64 KB inverse-CDF table in shared memory (the 16-bit gathers were the dominant
+// L1 wavefront source when the table was read through the global path).  A warp owns chunks of 32 consecutive points:
+//   phase 1  lane <-> point: row record, flat normal index, step scalars (one load chain per 32 points);
+//   phase 2  two points at a time: each half-warp generates the Philox blocks of one point into the warp's buffer, then all
+//            32 lanes walk the coordinates of a point (lane <-> coordinate j, j + 32, ...): 16-bit chunk -> table -> point,
+//            so every store instruction writes 256 contiguous bytes of the level's point buffer.
+constexpr int SMP_MAX_WARPS = 16;
+constexpr int SMP_TABLE_BYTES = 65536;
+
+__device__ __forceinline__ void load_normal_table(__half* stab, const __half* __restrict__ gtab) {
+    const uint4* src = (const uint4*)gtab;
+    uint4* dst = (uint4*)stab;
+    for (int i = threadIdx.x; i < SMP_TABLE_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
-    const long long npt = (lv.NT - s0 < ppb) ? (lv.NT - s0) : ppb;
-    double* out = lv.P + (lv.term_off + s0) * D;
-    for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
+}
+__device__ __forceinline__ double chunk_to_normal_s(const __half* stab, uint32_t c) {
+    const bool neg = c < 32768u;
+    const uint32_t idx = neg ? (32767u - c) : (c - 32768u);
+    const float v = __half2float(stab[idx]);
+    return (double)(neg ? -v : v);
+}
+// X + (drift + sigma (sq N)) with every rounding explicit (no FMA contraction: NumPy's operation order for any sigma)
+__device__ __forceinline__ double step_add(double X, double drift, double sigma, double sq, double N) {
+    return __dadd_rn(X, __dadd_rn(drift, __dmul_rn(sigma, __dmul_rn(sq, N))));
+}
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// half-warp h generates the Philox blocks covering the flat indices [f0, f0 + d) of its point into buf
+__device__ __forceinline__ void philox_blocks(uint4* buf, unsigned long long f0, int d, PhiloxKey key, int hl) {
+    const unsigned long long B0 = f0 >> 3;
+    const int nblk = (int)(((f0 + (unsigned long long)d - 1ull) >> 3) - B0) + 1;
+    for (int b = hl; b < nblk; b += 16) buf[b] = philox4x32_10(B0 + (unsigned long long)b, key);
+}
+
+// terminal points X_T = (x + mu (T-t)) + sigma (sqrt(T-t) N)   (solvers/ScaSML.py:190-198)
+template <int JP>
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(LevelDev lv, int nslot) {
+    extern __shared__ __align__(16) uint8_t smp_smem[];
+    __half* stab = (__half*)smp_smem;
+    load_normal_table(stab, lv.ntab);
+    constexpr bool REG = JP <= 4;                            // parent coordinates prefetched into registers
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, hl = lane & 15;
+    uint4* pbuf = (uint4*)(smp_smem + SMP_TABLE_BYTES) + (size_t)warp * 2 * nslot;
+    const unsigned short* pch = (const unsigned short*)pbuf;
+    const int d = lv.d, D = lv.D, MCg = lv.MCg;
+    const PhiloxKey key = make_key(0u, 0u, lv.seed);
+    const long long nchunk = (lv.NT + 31) >> 5;
+    for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
+        const long long s = ch * 32 + lane;
+        unsigned long long xp = 0ull, f0 = 0ull;
+        double sq = 0.0, drift = 0.0;
+        if (s < lv.NT) {
+            const long long u = lv.rank + (long long)lv.world * s;
+            const long long R = u / MCg;
+            const int m = (int)(u - R * MCg);
+            const RowRec rr = lv.rows[R];
+            xp = (unsigned long long)rr.x;
+            f0 = (unsigned long long)(rr.gid * MCg + m) * (unsigned long long)d;
+            const double Tt = lv.T - rr.t;
+            sq = sqrt(Tt); drift = lv.mu * Tt;
+        }
+        const int npt = (int)((lv.NT - ch * 32 < 32) ? (lv.NT - ch * 32) : 32);
+        double* out = lv.P + (lv.term_off + ch * 32) * D;
+        for (int pp = 0; pp < npt; pp += 2) {
+            const int pb = (pp + 1 < npt) ? pp + 1 : pp;
+            const double* xs[2] = {(const double*)shfl_u64(xp, pp), (const double*)shfl_u64(xp, pb)};
+            double xv[2][REG ? JP : 1];
+            if (REG) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                    for (int q = 0; q < JP; ++q) { const int j = lane + 32 * q; xv[hh][q] = (j < d) ? __ldg(xs[hh] + j) : 0.0; }
+            }
+            const unsigned long long f0h = shfl_u64(f0, h ? pb : pp);
+            if (pp + h < npt) philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int p = pp + hh;
+                if (p < npt) {                                       // warp-uniform
+                    const unsigned long long f0p = shfl_u64(f0, p);
+                    const double sqp = __shfl_sync(0xffffffffu, sq, p), drp = __shfl_sync(0xffffffffu, drift, p);
+                    const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
+                    double* dst = out + (long long)p * D;
+#pragma unroll
+                    for (int q = 0; q < JP; ++q) {
+                        const int j = lane + 32 * q;
+                        if (j < d) {
+                            const double N = chunk_to_normal_s(stab, cp[j]);
+                            const double xin = REG ? xv[hh][q] : __ldg(xs[hh] + j);
+                            dst[j] = __dadd_rn(__dadd_rn(xin, drp), __dmul_rn(lv.sigma, __dmul_rn(sqp, N)));
+                        } else if (j == d) {
+                            dst[j] = lv.T;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
 }
 
 // interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
-__global__ void __launch_bounds__(SAMPLE_THREADS) sample_paths_kernel(LevelDev lv, int l, int ppb) {
-    __shared__ double tile[SAMPLE_TILE];
-    const int d = lv.d, D = lv.D;
-    const int nslot = (d + 14) / 8;
-    const int p = threadIdx.x / nslot, b = threadIdx.x % nslot;
-    const long long s0 = (long long)blockIdx.x * ppb;
-    const long long s = s0 + p;
-    const bool active = (p < ppb) && (s < lv.NP[l]);
-    const long long npt = (lv.NP[l] - s0 < ppb) ? (lv.NP[l] - s0) : ppb;
-    const int MCf = lv.MCf[l];
-    double Xr[8];
-    bool ok[8];
-    const CallDev* cp = nullptr;
-    double t = 0.0;
-    long long pgid = 0, jbase = 0;
-    unsigned long long blk = 0;
-    if (active) {
-        const long long u = lv.rank + (long long)lv.world * s;
-        const long long R = u / MCf;
-        const int m = (int)(u - R * MCf);
-        cp = &lv.calls[find_call(lv, R)];
-        const long long i = R - cp->rowbase;
-        const double* x = cp->xsrc + i * D;
-        const long long gidrow = cp->gidsrc ? cp->gidsrc[i] : lv.gid0 + i;
-        t = x[d];
-        pgid = gidrow * MCf + m;
-        const unsigned long long f0 = (unsigned long long)pgid * (unsigned long long)d;
-        blk = (f0 >> 3) + (unsigned long long)b;
-        jbase = (long long)(blk * 8ull) - (long long)f0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const long long j = jbase + e;
-            ok[e] = (j >= 0 && j < d);
-            Xr[e] = ok[e] ? x[j] : 0.0;
+template <int JP>
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(LevelDev lv, int l, int nslot) {
+    extern __shared__ __align__(16) uint8_t smp_smem[];
+    __half* stab = (__half*)smp_smem;
+    load_normal_table(stab, lv.ntab);
+    constexpr bool REG = JP <= 4;                            // running path state in registers; else re-read from the previous step's point
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, hl = lane & 15;
+    const int nq = (lv.variant == 0) ? lv.q[l] : 1;
+    uint8_t* wbase = smp_smem + SMP_TABLE_BYTES + (size_t)warp * ((size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8);
+    uint4* pbuf = (uint4*)wbase;
+    const unsigned short* pch = (const unsigned short*)pbuf;
+    double* scal = (double*)(wbase + (size_t)2 * nslot * 16);        // [nq][3][32]: t_k, sqrt(d_k), mu d_k per (step, point of the chunk)
+    const int d = lv.d, D = lv.D, MCf = lv.MCf[l];
+    const long long NP = lv.NP[l];
+    const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+    const long long nchunk = (NP + 31) >> 5;
+    for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
+        const long long s = ch * 32 + lane;
+        unsigned long long xp = 0ull, f0 = 0ull;
+        int ci = 0;
+        __syncwarp();                                                // the previous chunk's scalars have been consumed
+        if (s < NP) {
+            const long long u = lv.rank + (long long)lv.world * s;
+            const long long R = u / MCf;
+            const int m = (int)(u - R * MCf);
+            const RowRec rr = lv.rows[R];
+            const long long pgid = rr.gid * MCf + m;
+            xp = (unsigned long long)rr.x; ci = rr.call;
+            f0 = (unsigned long long)pgid * (unsigned long long)d;
+            const double t = rr.t;
+            if (lv.variant == 0) {
+                double tprev = t;
+                for (int k = 0; k < nq; ++k) {
+                    const int lk = l * MAX_Q + k;
+                    const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
+                    const double dk = __dsub_rn(tk, tprev);
+                    scal[(k * 3 + 0) * 32 + lane] = tk;
+                    scal[(k * 3 + 1) * 32 + lane] = sqrt(dk);
+                    scal[(k * 3 + 2) * 32 + lane] = lv.mu * dk;
+                    lv.gid[lv.set_off[lk] + s] = pgid;
+                    tprev = tk;
+                }
+            } else {
+                const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
+                const double steps = tau * (lv.T - t);
+                scal[0 * 32 + lane] = t + steps;
+                scal[1 * 32 + lane] = sqrt(steps);
+                scal[2 * 32 + lane] = lv.mu * steps;
+                lv.gid[lv.set_off[l * MAX_Q] + s] = pgid;
+            }
         }
-    }
-    double* dstt = tile + p * D;
-    if (lv.variant == 0) {
-        double tprev = t;
-        const int q = lv.q[l];
-        for (int k = 0; k < q; ++k) {
-            const int lk = l * MAX_Q + k;
-            if (active) {
-                const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
-                const double dk = __dsub_rn(tk, tprev);
-                const double sq = sqrt(dk), drift = lv.mu * dk;
-                const uint4 w = philox4x32_10(blk, make_key(cp->key[lk], 1u, lv.seed));
+        __syncwarp();
+        const int npt = (int)((NP - ch * 32 < 32) ? (NP - ch * 32) : 32);
+        for (int pp = 0; pp < npt; pp += 2) {
+            const int pb = (pp + 1 < npt) ? pp + 1 : pp;
+            const double* xs[2] = {(const double*)shfl_u64(xp, pp), (const double*)shfl_u64(xp, pb)};
+            double xv[2][REG ? JP : 1];
+            if (REG) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if (ok[e]) {
-                        const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
-                        Xr[e] = Xr[e] + (drift + lv.sigma * (sq * N));
-                        dstt[jbase + e] = Xr[e];
+                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                    for (int q = 0; q < JP; ++q) { const int j = lane + 32 * q; xv[hh][q] = (j < d) ? __ldg(xs[hh] + j) : 0.0; }
+            }
+            const unsigned long long f0h = shfl_u64(f0, h ? pb : pp);
+            const int cih = __shfl_sync(0xffffffffu, ci, h ? pb : pp);
+            for (int k = 0; k < nq; ++k) {
+                const int lk = l * MAX_Q + k;
+                if (pp + h < npt) {
+                    const PhiloxKey key = (lv.variant == 0) ? make_key(__ldg(&lv.calls[cih].key[lk]), 1u, lv.seed) : kT;
+                    philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
+                }
+                __syncwarp();
+                double* out = lv.P + (lv.set_off[lk] + ch * 32) * D;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int p = pp + hh;
+                    if (p < npt) {                                   // warp-uniform
+                        const unsigned long long f0p = shfl_u64(f0, p);
+                        const double tk = scal[(k * 3 + 0) * 32 + p], sqp = scal[(k * 3 + 1) * 32 + p], drp = scal[(k * 3 + 2) * 32 + p];
+                        const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
+                        double* dst = out + (long long)p * D;
+                        const double* prev = (k == 0) ? xs[hh] : lv.P + (lv.set_off[lk - 1] + ch * 32 + p) * D;
+#pragma unroll
+                        for (int q = 0; q < JP; ++q) {
+                            const int j = lane + 32 * q;
+                            if (j < d) {
+                                const double N = chunk_to_normal_s(stab, cp[j]);
+                                const double xin = REG ? xv[hh][q] : prev[j];   // !REG: written by this very thread one step earlier
+                                const double xn = step_add(xin, drp, lv.sigma, sqp, N);
+                                if (REG) xv[hh][q] = xn;
+                                dst[j] = xn;
+                            } else if (j == d) {
+                                dst[j] = tk;
+                            }
+                        }
                     }
                 }
-                if (b == 0) { dstt[d] = tk; lv.gid[lv.set_off[lk] + s] = pgid; }
-                tprev = tk;
+                __syncwarp();
             }
-            __syncthreads();
-            double* out = lv.P + (lv.set_off[lk] + s0) * D;
-            for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
-            __syncthreads();
         }
-    } else {
-        if (active) {
-            const PhiloxKey kT = make_key(0u, 0u, lv.seed);
-            const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
-            const double steps = tau * (lv.T - t);
-            const double sq = sqrt(steps), drift = lv.mu * steps;
-            const uint4 w = philox4x32_10(blk, kT);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (ok[e]) {
-                    const double N = chunk_to_normal(lv.ntab, chunk_of(w, e));
-                    dstt[jbase + e] = Xr[e] + (drift + lv.sigma * (sq * N));
-                }
-            }
-            if (b == 0) { dstt[d] = t + steps; lv.gid[lv.set_off[l * MAX_Q] + s] = pgid; }
-        }
-        __syncthreads();
-        double* out = lv.P + (lv.set_off[l * MAX_Q] + s0) * D;
-        for (long long e = threadIdx.x; e < npt * D; e += SAMPLE_THREADS) out[e] = tile[e];
     }
 }
 
@@ -355,11 +448,11 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
     const int lane = threadIdx.x & 31;
     if (R >= lv.NR) return;
     const int d = lv.d, D = lv.D, L = lv.L;
-    const CallDev& c = lv.calls[find_call(lv, R)];
-    const long long irow = R - c.rowbase;
-    const double* x = c.xsrc + irow * D;
-    const long long gidrow = c.gidsrc ? c.gidsrc[irow] : lv.gid0 + irow;
-    const double t = x[d], T = lv.T, Tt = T - t;
+    const RowRec rr = lv.rows[R];
+    const CallDev& c = lv.calls[rr.call];
+    const double* x = rr.x;
+    const long long gidrow = rr.gid;
+    const double t = rr.t, T = lv.T, Tt = T - t;
     const PhiloxKey kT = make_key(0u, 0u, lv.seed);
     const long long world = lv.world, rank = lv.rank;
     const double sig = lv.sigma;
@@ -560,6 +653,40 @@ int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
     return OK;
 }
 
+template <int JP>
+int launch_sample_terminal_jp(const LevelDev& lv, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+    SC_CUDA(cudaFuncSetAttribute(sample_terminal_kernel<JP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_terminal_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, nslot);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+template <int JP>
+int launch_sample_paths_jp(const LevelDev& lv, int l, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+    SC_CUDA(cudaFuncSetAttribute(sample_paths_kernel<JP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_paths_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, l, nslot);
+    SC_LAUNCH_CHECK();
+    return OK;
+}
+// JP = passes of 32 columns over the D = d + 1 columns of a point
+int launch_sample_terminal(const LevelDev& lv, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+    const int D = lv.D;
+    if (D <= 32) return launch_sample_terminal_jp<1>(lv, nslot, grid, nwarp, smem, stream);
+    if (D <= 64) return launch_sample_terminal_jp<2>(lv, nslot, grid, nwarp, smem, stream);
+    if (D <= 128) return launch_sample_terminal_jp<4>(lv, nslot, grid, nwarp, smem, stream);
+    if (D <= 256) return launch_sample_terminal_jp<8>(lv, nslot, grid, nwarp, smem, stream);
+    if (D <= 1024) return launch_sample_terminal_jp<32>(lv, nslot, grid, nwarp, smem, stream);
+    return launch_sample_terminal_jp<64>(lv, nslot, grid, nwarp, smem, stream);
+}
+int launch_sample_paths(const LevelDev& lv, int l, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+    const int D = lv.D;
+    if (D <= 32) return launch_sample_paths_jp<1>(lv, l, nslot, grid, nwarp, smem, stream);
+    if (D <= 64) return launch_sample_paths_jp<2>(lv, l, nslot, grid, nwarp, smem, stream);
+    if (D <= 128) return launch_sample_paths_jp<4>(lv, l, nslot, grid, nwarp, smem, stream);
+    if (D <= 256) return launch_sample_paths_jp<8>(lv, l, nslot, grid, nwarp, smem, stream);
+    if (D <= 1024) return launch_sample_paths_jp<32>(lv, l, nslot, grid, nwarp, smem, stream);
+    return launch_sample_paths_jp<64>(lv, l, nslot, grid, nwarp, smem, stream);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ run -----------------------------------
@@ -605,6 +732,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         }
         lv.P = (double*)(ws + lr.off_P);
         lv.gid = (long long*)(ws + lr.off_gid);
+        lv.rows = (RowRec*)(ws + lr.off_rows);
         lv.ev0 = (double*)(ws + lr.off_ev0);
         lv.ev1 = (double*)(ws + lr.off_ev1);
         for (int q = 1; q <= n; ++q) lv.us[q] = (double*)(ws + levels_[q].off_us);
@@ -651,9 +779,21 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
     if (fused)
         for (int L = 1; L <= n; ++L)
             SC_CUDA(cudaMemcpyAsync(ws + levels_[L].off_lvdev, &lvs[L], sizeof(LevelDev), cudaMemcpyHostToDevice, stream));
-    const int nslot = (d + 14) / 8;
-    SC_REQUIRE(nslot <= SAMPLE_THREADS, "picard: d > 2034 is not supported by the sampler");
-    const int ppb = SAMPLE_THREADS / nslot;            // points per sampler CTA
+    // sampler launch shape: persistent CTAs (two per SM when shared memory allows), 64 KB table + per-warp Philox / step buffers
+    const int nslot = (d + 14) / 8;                    // Philox blocks covering d consecutive flat indices from any offset
+    SC_REQUIRE(D <= 2048, "picard: d > 2047 is not supported by the sampler");
+    int dev = 0, nsm = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    auto sampler_shape = [&](int nq, long long npts, int* nwarp, size_t* smem, unsigned* grid) {
+        const size_t per_warp = (size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8;
+        int w = SMP_MAX_WARPS;
+        while (w > 1 && SMP_TABLE_BYTES + w * per_warp > (size_t)110 * 1024) w >>= 1;      // two CTAs per SM
+        if (w < 8) { w = SMP_MAX_WARPS; while (w > 1 && SMP_TABLE_BYTES + w * per_warp > (size_t)220 * 1024) w >>= 1; }
+        *nwarp = w; *smem = SMP_TABLE_BYTES + w * per_warp;
+        const long long need = cdiv(cdiv(npts, 32), w);
+        *grid = (unsigned)std::min<long long>(need, 2LL * nsm);
+    };
     // optional CUDA-event timing of the three kernel groups (sampler / evaluation / reduction)
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
@@ -672,14 +812,22 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         const LevelDev& lv = lvs[L];
         const LevelRec& lr = levels_[L];
         begin_span(0);
+        row_setup_kernel<<<(unsigned)cdiv(lv.NR, 256), 256, 0, stream>>>(lv);
+        SC_LAUNCH_CHECK(); ++launches;
         if (!fused && lv.NT > 0) {
-            sample_terminal_kernel<<<(unsigned)cdiv(lv.NT, ppb), SAMPLE_THREADS, 0, stream>>>(lv, ppb);
-            SC_LAUNCH_CHECK(); ++launches;
+            int nwarp; size_t smem; unsigned grid;
+            sampler_shape(0, lv.NT, &nwarp, &smem, &grid);
+            const int rc = launch_sample_terminal(lv, nslot, grid, nwarp, smem, stream);
+            if (rc != OK) return rc;
+            ++launches;
         }
         for (int l = 0; l < L && !fused; ++l) {
             if (lv.NP[l] == 0) continue;
-            sample_paths_kernel<<<(unsigned)cdiv(lv.NP[l], ppb), SAMPLE_THREADS, 0, stream>>>(lv, l, ppb);
-            SC_LAUNCH_CHECK(); ++launches;
+            int nwarp; size_t smem; unsigned grid;
+            sampler_shape(p_.variant == 0 ? lv.q[l] : 1, lv.NP[l], &nwarp, &smem, &grid);
+            const int rc = launch_sample_paths(lv, l, nslot, grid, nwarp, smem, stream);
+            if (rc != OK) return rc;
+            ++launches;
         }
         end_span();
         if (p_.scasml) {

@@ -56,6 +56,15 @@ struct CallDev {
     long long childbase[MAXLK][2];      // row base of child call (level l / level l-1), -1 = none
 };
 
+// per-row record of a level (row_setup_kernel): what every sampler / reduction warp needs of its parent row in ONE load
+// instead of the dependent chain  call search -> call record -> parent row pointer -> global id -> time column
+struct RowRec {
+    const double* x;                    // the row's point [D] (a row of the parent's point buffer, or of x_t at the top level)
+    long long gid;                      // global row id (RNG addressing independent of batching / sharding)
+    double t;                           // time column of the row
+    int call, pad;                      // index of the owning call in LevelDev::calls
+};
+
 struct LevelDev {
     int L, ncalls;
     const CallDev* calls;
@@ -70,6 +79,7 @@ struct LevelDev {
     double cnode[MAXLK], wnode[MAXLK];  // c[k][q-1], w[k][q-1]
     double* P;                          // point buffer [npoints][D]
     long long* gid;                     // [npoints]
+    RowRec* rows;                       // [NR]
     double* ev0; double* ev1;           // evaluation outputs per point
     double* us[MAX_LEVEL + 1];          // finalized (u, zsum) per row, per level
     double* out_uz;                     // top level: [NR][1+d]
@@ -101,7 +111,7 @@ public:
         long long NP[MAX_LEVEL] = {0};
         long long set_off[MAXLK] = {0};
         long long term_off = 0, ug_off = 0, pde_off = 0;
-        size_t off_P = 0, off_gid = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
+        size_t off_P = 0, off_gid = 0, off_rows = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
     };
     const std::vector<CallRec>& calls() const { return calls_; }
     const std::vector<LevelRec>& levels() const { return levels_; }
