@@ -214,15 +214,20 @@ __device__ __forceinline__ void load_normal_table(__half* stab, const __half* __
     for (int i = threadIdx.x; i < SMP_TABLE_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
 }
+// same map as chunk_to_normal (common.cuh): c >= 32768 -> +tab[c - 32768], c < 32768 -> -tab[32767 - c], branch-free
 __device__ __forceinline__ double chunk_to_normal_s(const __half* stab, uint32_t c) {
-    const bool neg = c < 32768u;
-    const uint32_t idx = neg ? (32767u - c) : (c - 32768u);
-    const float v = __half2float(stab[idx]);
-    return (double)(neg ? -v : v);
+    const uint32_t low = ((c >> 15) & 1u) - 1u;                       // all ones iff c < 32768
+    const uint32_t idx = (c ^ low) & 0x7FFFu;
+    const unsigned short bits = (unsigned short)(((const unsigned short*)stab)[idx] ^ (low & 0x8000u));
+    return (double)__half2float(__ushort_as_half(bits));
 }
 // X + (drift + sigma (sq N)) with every rounding explicit (no FMA contraction: NumPy's operation order for any sigma)
 __device__ __forceinline__ double step_add(double X, double drift, double sigma, double sq, double N) {
     return __dadd_rn(X, __dadd_rn(drift, __dmul_rn(sigma, __dmul_rn(sq, N))));
+}
+// predicated 8-byte store (keeps the column loops branch-free)
+__device__ __forceinline__ void store_pred(double* p, double v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -230,8 +235,18 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
 __device__ __forceinline__ void philox_blocks(uint4* buf, unsigned long long f0, int d, PhiloxKey key, int hl) {
     const unsigned long long B0 = f0 >> 3;
     const int nblk = (int)(((f0 + (unsigned long long)d - 1ull) >> 3) - B0) + 1;
+#pragma unroll 1
     for (int b = hl; b < nblk; b += 16) buf[b] = philox4x32_10(B0 + (unsigned long long)b, key);
 }
+
+// per-point record of a chunk (phase 1 -> phase 2 through the warp's shared memory: broadcast loads instead of shuffles)
+struct PtRec {
+    unsigned long long xp;               // parent row
+    unsigned long long f0;               // flat index of the point's first normal
+    double sq, drift;                    // terminal: sqrt(T-t), mu (T-t);  paths: unused
+    int call, pad;
+};
+constexpr int SMP_WARP_FIXED = 32 * (int)sizeof(PtRec);     // bytes per warp besides the Philox buffer / step scalars
 
 // terminal points X_T = (x + mu (T-t)) + sigma (sqrt(T-t) N)   (solvers/ScaSML.py:190-198)
 template <int JP>
@@ -241,30 +256,37 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
     load_normal_table(stab, lv.ntab);
     constexpr bool REG = JP <= 4;                            // parent coordinates prefetched into registers
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, hl = lane & 15;
-    uint4* pbuf = (uint4*)(smp_smem + SMP_TABLE_BYTES) + (size_t)warp * 2 * nslot;
+    uint8_t* wbase = smp_smem + SMP_TABLE_BYTES + (size_t)warp * (SMP_WARP_FIXED + (size_t)2 * nslot * 16);
+    PtRec* rec = (PtRec*)wbase;
+    uint4* pbuf = (uint4*)(wbase + SMP_WARP_FIXED);
     const unsigned short* pch = (const unsigned short*)pbuf;
     const int d = lv.d, D = lv.D, MCg = lv.MCg;
+    const double sigma = lv.sigma, T = lv.T, mu = lv.mu;
     const PhiloxKey key = make_key(0u, 0u, lv.seed);
-    const long long nchunk = (lv.NT + 31) >> 5;
+    const long long NT = lv.NT, nchunk = (NT + 31) >> 5;
     for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
         const long long s = ch * 32 + lane;
-        unsigned long long xp = 0ull, f0 = 0ull;
-        double sq = 0.0, drift = 0.0;
-        if (s < lv.NT) {
+        __syncwarp();                                                // the previous chunk's records have been consumed
+        if (s < NT) {
             const long long u = lv.rank + (long long)lv.world * s;
             const long long R = u / MCg;
             const int m = (int)(u - R * MCg);
             const RowRec rr = lv.rows[R];
-            xp = (unsigned long long)rr.x;
-            f0 = (unsigned long long)(rr.gid * MCg + m) * (unsigned long long)d;
-            const double Tt = lv.T - rr.t;
-            sq = sqrt(Tt); drift = lv.mu * Tt;
+            const double Tt = T - rr.t;
+            PtRec r;
+            r.xp = (unsigned long long)rr.x;
+            r.f0 = (unsigned long long)(rr.gid * MCg + m) * (unsigned long long)d;
+            r.sq = sqrt(Tt); r.drift = mu * Tt; r.call = 0; r.pad = 0;
+            rec[lane] = r;
         }
-        const int npt = (int)((lv.NT - ch * 32 < 32) ? (lv.NT - ch * 32) : 32);
-        double* out = lv.P + (lv.term_off + ch * 32) * D;
+        __syncwarp();
+        const int npt = (int)((NT - ch * 32 < 32) ? (NT - ch * 32) : 32);
+        double* const outl = lv.P + (lv.term_off + ch * 32) * D + lane;      // this lane's column of the chunk's first point
+        // two points per iteration; an odd tail repeats its last point (same values written twice) so nothing below is conditional
         for (int pp = 0; pp < npt; pp += 2) {
-            const int pb = (pp + 1 < npt) ? pp + 1 : pp;
-            const double* xs[2] = {(const double*)shfl_u64(xp, pp), (const double*)shfl_u64(xp, pb)};
+            const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
+            const PtRec ra = rec[pi[0]], rb = rec[pi[1]];
+            const double* xs[2] = {(const double*)ra.xp, (const double*)rb.xp};
             double xv[2][REG ? JP : 1];
             if (REG) {
 #pragma unroll
@@ -272,28 +294,21 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
 #pragma unroll
                     for (int q = 0; q < JP; ++q) { const int j = lane + 32 * q; xv[hh][q] = (j < d) ? __ldg(xs[hh] + j) : 0.0; }
             }
-            const unsigned long long f0h = shfl_u64(f0, h ? pb : pp);
-            if (pp + h < npt) philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
+            philox_blocks(pbuf + h * nslot, h ? rb.f0 : ra.f0, d, key, hl);
             __syncwarp();
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const int p = pp + hh;
-                if (p < npt) {                                       // warp-uniform
-                    const unsigned long long f0p = shfl_u64(f0, p);
-                    const double sqp = __shfl_sync(0xffffffffu, sq, p), drp = __shfl_sync(0xffffffffu, drift, p);
-                    const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
-                    double* dst = out + (long long)p * D;
+                const unsigned long long f0p = hh ? rb.f0 : ra.f0;
+                const double sqp = hh ? rb.sq : ra.sq, drp = hh ? rb.drift : ra.drift;
+                const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
+                double* const dst = outl + pi[hh] * D;               // 32-bit offset: one wide multiply-add
 #pragma unroll
-                    for (int q = 0; q < JP; ++q) {
-                        const int j = lane + 32 * q;
-                        if (j < d) {
-                            const double N = chunk_to_normal_s(stab, cp[j]);
-                            const double xin = REG ? xv[hh][q] : __ldg(xs[hh] + j);
-                            dst[j] = __dadd_rn(__dadd_rn(xin, drp), __dmul_rn(lv.sigma, __dmul_rn(sqp, N)));
-                        } else if (j == d) {
-                            dst[j] = lv.T;
-                        }
-                    }
+                for (int q = 0; q < JP; ++q) {                       // predicated, no branches: lanes past the row compute garbage and drop it
+                    const int j = lane + 32 * q;
+                    const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
+                    const double xin = REG ? xv[hh][q] : ((j < d) ? __ldg(xs[hh] + j) : 0.0);
+                    const double val = __dadd_rn(__dadd_rn(xin, drp), __dmul_rn(sigma, __dmul_rn(sqp, N)));
+                    store_pred(dst + 32 * q, (j == d) ? T : val, j <= d);
                 }
             }
             __syncwarp();
@@ -310,54 +325,58 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
     constexpr bool REG = JP <= 4;                            // running path state in registers; else re-read from the previous step's point
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, hl = lane & 15;
     const int nq = (lv.variant == 0) ? lv.q[l] : 1;
-    uint8_t* wbase = smp_smem + SMP_TABLE_BYTES + (size_t)warp * ((size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8);
-    uint4* pbuf = (uint4*)wbase;
+    uint8_t* wbase = smp_smem + SMP_TABLE_BYTES + (size_t)warp * (SMP_WARP_FIXED + (size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8);
+    PtRec* rec = (PtRec*)wbase;
+    uint4* pbuf = (uint4*)(wbase + SMP_WARP_FIXED);
     const unsigned short* pch = (const unsigned short*)pbuf;
-    double* scal = (double*)(wbase + (size_t)2 * nslot * 16);        // [nq][3][32]: t_k, sqrt(d_k), mu d_k per (step, point of the chunk)
+    double* scal = (double*)(wbase + SMP_WARP_FIXED + (size_t)2 * nslot * 16);   // [nq][3][32]: t_k, sqrt(d_k), mu d_k per (step, point of the chunk)
     const int d = lv.d, D = lv.D, MCf = lv.MCf[l];
+    const double sigma = lv.sigma, T = lv.T, mu = lv.mu;
     const long long NP = lv.NP[l];
     const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+    const bool quad = lv.variant == 0;
     const long long nchunk = (NP + 31) >> 5;
     for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
         const long long s = ch * 32 + lane;
-        unsigned long long xp = 0ull, f0 = 0ull;
-        int ci = 0;
-        __syncwarp();                                                // the previous chunk's scalars have been consumed
+        __syncwarp();                                                // the previous chunk's records / scalars have been consumed
         if (s < NP) {
             const long long u = lv.rank + (long long)lv.world * s;
             const long long R = u / MCf;
             const int m = (int)(u - R * MCf);
             const RowRec rr = lv.rows[R];
             const long long pgid = rr.gid * MCf + m;
-            xp = (unsigned long long)rr.x; ci = rr.call;
-            f0 = (unsigned long long)pgid * (unsigned long long)d;
+            PtRec r;
+            r.xp = (unsigned long long)rr.x; r.call = rr.call; r.pad = 0; r.sq = 0.0; r.drift = 0.0;
+            r.f0 = (unsigned long long)pgid * (unsigned long long)d;
+            rec[lane] = r;
             const double t = rr.t;
-            if (lv.variant == 0) {
+            if (quad) {
                 double tprev = t;
                 for (int k = 0; k < nq; ++k) {
                     const int lk = l * MAX_Q + k;
-                    const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
+                    const double tk = cloc_of(T, t, lv.cnode[lk]);
                     const double dk = __dsub_rn(tk, tprev);
                     scal[(k * 3 + 0) * 32 + lane] = tk;
                     scal[(k * 3 + 1) * 32 + lane] = sqrt(dk);
-                    scal[(k * 3 + 2) * 32 + lane] = lv.mu * dk;
+                    scal[(k * 3 + 2) * 32 + lane] = mu * dk;
                     lv.gid[lv.set_off[lk] + s] = pgid;
                     tprev = tk;
                 }
             } else {
                 const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
-                const double steps = tau * (lv.T - t);
+                const double steps = tau * (T - t);
                 scal[0 * 32 + lane] = t + steps;
                 scal[1 * 32 + lane] = sqrt(steps);
-                scal[2 * 32 + lane] = lv.mu * steps;
+                scal[2 * 32 + lane] = mu * steps;
                 lv.gid[lv.set_off[l * MAX_Q] + s] = pgid;
             }
         }
         __syncwarp();
         const int npt = (int)((NP - ch * 32 < 32) ? (NP - ch * 32) : 32);
-        for (int pp = 0; pp < npt; pp += 2) {
-            const int pb = (pp + 1 < npt) ? pp + 1 : pp;
-            const double* xs[2] = {(const double*)shfl_u64(xp, pp), (const double*)shfl_u64(xp, pb)};
+        for (int pp = 0; pp < npt; pp += 2) {                        // an odd tail repeats its last point: nothing below is conditional
+            const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
+            const PtRec ra = rec[pi[0]], rb = rec[pi[1]];
+            const double* xs[2] = {(const double*)ra.xp, (const double*)rb.xp};
             double xv[2][REG ? JP : 1];
             if (REG) {
 #pragma unroll
@@ -365,38 +384,31 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
 #pragma unroll
                     for (int q = 0; q < JP; ++q) { const int j = lane + 32 * q; xv[hh][q] = (j < d) ? __ldg(xs[hh] + j) : 0.0; }
             }
-            const unsigned long long f0h = shfl_u64(f0, h ? pb : pp);
-            const int cih = __shfl_sync(0xffffffffu, ci, h ? pb : pp);
+            const unsigned long long f0h = h ? rb.f0 : ra.f0;
+            const unsigned* keys = lv.calls[h ? rb.call : ra.call].key;
+#pragma unroll 1
             for (int k = 0; k < nq; ++k) {
                 const int lk = l * MAX_Q + k;
-                if (pp + h < npt) {
-                    const PhiloxKey key = (lv.variant == 0) ? make_key(__ldg(&lv.calls[cih].key[lk]), 1u, lv.seed) : kT;
-                    philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
-                }
+                const PhiloxKey key = quad ? make_key(__ldg(keys + lk), 1u, lv.seed) : kT;
+                philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
                 __syncwarp();
-                double* out = lv.P + (lv.set_off[lk] + ch * 32) * D;
+                double* const outl = lv.P + (lv.set_off[lk] + ch * 32) * D + lane;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    const int p = pp + hh;
-                    if (p < npt) {                                   // warp-uniform
-                        const unsigned long long f0p = shfl_u64(f0, p);
-                        const double tk = scal[(k * 3 + 0) * 32 + p], sqp = scal[(k * 3 + 1) * 32 + p], drp = scal[(k * 3 + 2) * 32 + p];
-                        const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
-                        double* dst = out + (long long)p * D;
-                        const double* prev = (k == 0) ? xs[hh] : lv.P + (lv.set_off[lk - 1] + ch * 32 + p) * D;
+                    const int p = pi[hh];
+                    const unsigned long long f0p = hh ? rb.f0 : ra.f0;
+                    const double tk = scal[(k * 3 + 0) * 32 + p], sqp = scal[(k * 3 + 1) * 32 + p], drp = scal[(k * 3 + 2) * 32 + p];
+                    const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
+                    double* const dst = outl + p * D;
+                    const double* prev = (k == 0) ? xs[hh] : lv.P + (lv.set_off[lk - 1] + ch * 32 + p) * D;
 #pragma unroll
-                        for (int q = 0; q < JP; ++q) {
-                            const int j = lane + 32 * q;
-                            if (j < d) {
-                                const double N = chunk_to_normal_s(stab, cp[j]);
-                                const double xin = REG ? xv[hh][q] : prev[j];   // !REG: written by this very thread one step earlier
-                                const double xn = step_add(xin, drp, lv.sigma, sqp, N);
-                                if (REG) xv[hh][q] = xn;
-                                dst[j] = xn;
-                            } else if (j == d) {
-                                dst[j] = tk;
-                            }
-                        }
+                    for (int q = 0; q < JP; ++q) {                   // predicated, no branches
+                        const int j = lane + 32 * q;
+                        const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
+                        const double xin = REG ? xv[hh][q] : ((j < d) ? prev[j] : 0.0);   // !REG: written by this very thread one step earlier
+                        const double xn = step_add(xin, drp, sigma, sqp, N);
+                        if (REG) xv[hh][q] = xn;
+                        store_pred(dst + 32 * q, (j == d) ? tk : xn, j <= d);
                     }
                 }
                 __syncwarp();
@@ -786,11 +798,11 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     auto sampler_shape = [&](int nq, long long npts, int* nwarp, size_t* smem, unsigned* grid) {
-        const size_t per_warp = (size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8;
+        const size_t per_warp = SMP_WARP_FIXED + (size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8;
         int w = SMP_MAX_WARPS;
         while (w > 1 && SMP_TABLE_BYTES + w * per_warp > (size_t)110 * 1024) w >>= 1;      // two CTAs per SM
         if (w < 8) { w = SMP_MAX_WARPS; while (w > 1 && SMP_TABLE_BYTES + w * per_warp > (size_t)220 * 1024) w >>= 1; }
-        *nwarp = w; *smem = SMP_TABLE_BYTES + w * per_warp;
+        *nwarp = w; *smem = SMP_TABLE_BYTES + w * per_warp + 512;     // slack: predicated lanes read past the last warp's buffer
         const long long need = cdiv(cdiv(npts, 32), w);
         *grid = (unsigned)std::min<long long>(need, 2LL * nsm);
     };
