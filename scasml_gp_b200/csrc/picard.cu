@@ -8,6 +8,7 @@
 //   one reduction    : warp-per-row Monte-Carlo means, weights, clip (reduce_kernel)
 // Levels are sampled top-down (children's rows are the parents' sample points) and reduced bottom-up.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "picard.cuh"
 #include "gp_tc.cuh"
@@ -444,74 +445,160 @@ __device__ __forceinline__ uint32_t read_chunk(const uint4* buf, unsigned long l
     return (uint32_t)((const unsigned short*)buf)[(int)(f - ((fstart >> 3) << 3))];
 }
 
-// Monte-Carlo means of one level: terminal part + all step sets + clip (solvers/ScaSML.py:211-215,252-284).
-// One warp per parent row.  The Brownian increments are not regenerated: a sampled point carries them,
+// ---- Monte-Carlo means of one level (solvers/ScaSML.py:211-215,252-284), two kernels -------------------------------------
+// The Brownian increments are not regenerated: a sampled point carries them,
 //   N = (X_T - x - mu (T-t)) / (sigma sqrt(T-t)),    W_k = (X_k - x - mu (t_k - t)) / sigma      (ScaSML.py:190-194,228-233)
 // so  z_j = sum_p c_p X_pj - x_j sum_p c_p - sum_p c_p drift_p  is a weighted row sum of the level's point buffer.
-// The warp works in chunks of 32 sample points: every lane computes the scalar weight of ONE point (its loads of the
-// evaluation outputs and child results are 32 independent requests), then the weights are broadcast with shuffles and the
-// point rows are streamed, four rows in flight per lane.  Degenerate steps (a sampled point equal to its parent: T == t, or
-// tau == 0 in the full-history variant) fall back to regenerating the Philox normals.
-template <int JCH>
-__global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
-    __shared__ uint4 wbuf_all[4][4 * JCH + 3];
-    uint4* wbuf = wbuf_all[threadIdx.x >> 5];
-    const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (R >= lv.NR) return;
-    const int d = lv.d, D = lv.D, L = lv.L;
+//   (A) point_weights_kernel: one thread per sample point turns its evaluation outputs / child results into the scalar
+//       weight c_p of its row in z and its contribution to u, IN PLACE over ev0 / ev1 (fully parallel, no per-row chains);
+//   (B) reduce_rows_kernel: one warp per parent row streams the row's points with those weights.
+// Degenerate steps (a sampled point equal to its parent: T == t, or tau == 0 in the full-history variant) have weight 0 in (A)
+// and fall back to regenerated Philox normals in (B).
+
+// owned sample indices [lo, hi) of row R when unit u = R MC + m belongs to rank u % world
+__device__ __forceinline__ void owned_range(long long R, int MC, long long rank, long long world, long long& lo, long long& hi) {
+    if (world == 1) { lo = R * MC; hi = lo + MC; return; }
+    lo = ceil_div_pos(R * MC - rank, world); hi = ceil_div_pos((R + 1) * MC - rank, world);
+}
+
+__global__ void __launch_bounds__(256) point_weights_kernel(LevelDev lv) {
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= lv.npoints) return;
+    const double T = lv.T, sig = lv.sigma;
+    if (pt >= lv.term_off && pt < lv.term_off + lv.NT) {
+        // terminal condition: u += g / MC_g, z += g N / (MC_g delta0)
+        const long long s = pt - lv.term_off;
+        const long long R = (lv.rank + (long long)lv.world * s) / lv.MCg;
+        const double Tt = T - lv.rows[R].t;
+        const double delta0 = (lv.variant == 0) ? (Tt + 1e-6) : Tt;    // ScaSML.py:213 vs ScaSML_full_history.py:133
+        const double sqT = sqrt(Tt);
+        const double gt = lv.ev0[pt];
+        const double invT = (1.0 / ((double)lv.MCg * delta0)) / (sig * sqT);
+        lv.ev0[pt] = (sqT > 0.0) ? gt * invT : 0.0;
+        lv.ev1[pt] = gt / lv.MCg;
+        return;
+    }
+    int l = -1, k = 0;
+    long long s = 0;
+    for (int ll = 0; ll < lv.L; ++ll) {
+        const long long o0 = lv.set_off[ll * MAX_Q], np = lv.NP[ll];
+        if (np > 0 && pt >= o0 && pt < o0 + np * lv.q[ll]) { l = ll; k = (int)((pt - o0) / np); s = pt - o0 - (long long)k * np; }
+    }
+    if (l < 0) return;
+    const int lk = l * MAX_Q + k, MCf = lv.MCf[l];
+    const long long u = lv.rank + (long long)lv.world * s;
+    const long long R = u / MCf;
     const RowRec rr = lv.rows[R];
     const CallDev& c = lv.calls[rr.call];
-    const double* x = rr.x;
-    const long long gidrow = rr.gid;
-    const double t = rr.t, T = lv.T, Tt = T - t;
+    const double t = rr.t, Tt = T - t;
+    const long long crow = s - c.rowbase * MCf;               // row of this sample inside the child calls
+    double y1 = 0.0, y2 = 0.0;
+    if (l >= 1) {
+        double uh = 0.0, sG = 0.0;
+        if (lv.scasml) { uh = lv.ev0[pt]; sG = sig * lv.ev1[pt]; }
+        const double* r1 = lv.us[l] + 2 * (c.childbase[lk][0] + crow);
+        y1 = lv.scasml ? sig * ((r1[0] + uh) * (sG + r1[1]) - uh * sG) : sig * r1[0] * r1[1];
+        if (l >= 2) {
+            const double* r2 = lv.us[l - 1] + 2 * (c.childbase[lk][1] + crow);
+            y2 = lv.scasml ? sig * ((r2[0] + uh) * (sG + r2[1]) - uh * sG) : sig * r2[0] * r2[1];
+        }
+    } else if (lv.scasml) {
+        y1 = lv.ev0[pt];                                       // PDE residual of the surrogate (ScaSML.py:275)
+    }
+    double cw, uc;
+    if (lv.variant == 0) {
+        const double tk = cloc_of(T, t, lv.cnode[lk]);
+        const double wk = wloc_of(T, t, lv.wnode[lk]);
+        const double dnew = (tk - t) + 1e-6;
+        double dadd = dnew, dsub = dnew;
+        if (lv.stale_delta) {
+            // solvers/MLP.py:201,249,270: the z term of y1 divides by the delta_t left over from the previous (l >= 1) node,
+            // level-0 nodes never update it
+            const double d0 = Tt + 1e-6;
+            if (l == 0) { dadd = d0; dsub = d0; }
+            else {
+                int pl = l, pk = k - 1;
+                if (pk < 0) { pl = l - 1; pk = (pl >= 1) ? lv.q[pl] - 1 : 0; }
+                dadd = (pl >= 1) ? (cloc_of(T, t, lv.cnode[pl * MAX_Q + pk]) - t) + 1e-6 : d0;
+            }
+        }
+        uc = (wk / MCf) * (y1 - y2);
+        cw = (y1 * (wk / (MCf * dadd)) - y2 * (wk / (MCf * dsub))) / sig;   // z += (y1 / delta_a - y2 / delta_s) w_k / MC_f * W_k
+    } else {
+        const int m = (int)(u - R * MCf);
+        const long long pgid = rr.gid * MCf + m;
+        const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, make_key(0u, 0u, lv.seed)));
+        const double steps = tau * Tt;
+        uc = Tt * (y1 - y2) / MCf;
+        const double yz = uc / sqrt(steps + 1e-6);               // ScaSML_full_history.py:169
+        const double sqs = sqrt(steps);
+        cw = (sqs > 0.0) ? yz / (sig * sqs) : 0.0;               // N = (X - x - mu steps) / (sigma sqrt(steps))
+        if (!(sqs > 0.0)) atomicOr(&lv.rows[R].pad, 1);           // degenerate step: (B) regenerates its normals
+    }
+    lv.ev0[pt] = cw;
+    lv.ev1[pt] = uc;
+}
+
+// entry e of row R's sample list [terminal samples | step set (l, k) samples ...] -> point index (pure arithmetic)
+struct RowEntries {
+    long long sT_lo, nT, total;
+};
+__device__ __forceinline__ RowEntries row_entries(const LevelDev& lv, long long R) {
+    RowEntries E;
+    long long hi;
+    owned_range(R, lv.MCg, lv.rank, lv.world, E.sT_lo, hi);
+    E.nT = hi - E.sT_lo;
+    E.total = E.nT;
+    for (int l = 0; l < lv.L; ++l) {
+        if (lv.NP[l] == 0) continue;               // MLP: f(x, 0, 0) = 0 at level 0, nothing to add (solvers/MLP.py:243)
+        long long a, b;
+        owned_range(R, lv.MCf[l], lv.rank, lv.world, a, b);
+        E.total += (b - a) * lv.q[l];
+    }
+    return E;
+}
+// kind: 0 terminal, 1 step set, -1 none; sidx: owned sample index; MC: samples per row of the entry's set
+__device__ __forceinline__ long long entry_point(const LevelDev& lv, long long R, const RowEntries& E, long long e, int& kind, long long& sidx, int& MC) {
+    kind = -1; sidx = 0; MC = 1;
+    long long pt = 0;
+    if (e < E.nT) { kind = 0; sidx = E.sT_lo + e; MC = lv.MCg; return lv.term_off + sidx; }
+    long long rem = e - E.nT;
+    for (int l = 0; l < lv.L; ++l) {
+        if (lv.NP[l] == 0) continue;
+        long long a, b;
+        owned_range(R, lv.MCf[l], lv.rank, lv.world, a, b);
+        const long long n = b - a;
+        for (int k = 0; k < lv.q[l]; ++k) {
+            if (kind < 0 && rem >= 0 && rem < n) { kind = 1; sidx = a + rem; pt = lv.set_off[l * MAX_Q + k] + sidx; MC = lv.MCf[l]; }
+            rem -= n;
+        }
+    }
+    return pt;
+}
+
+// Rare path of the reduction (kept out of line so that it costs the streaming kernel no registers): the directly accumulated
+// z terms  sum_p w_p N_p  of a row's degenerate sample points, with REGENERATED Philox normals -- terminal samples of a row
+// with T == t, full-history steps with tau == 0 (flagged in RowRec::pad by point_weights_kernel).  Result: zdir[32 q + lane].
+template <int JCH>
+__device__ __noinline__ void reduce_direct_terms(const LevelDev& lv, long long R, int jpass, uint4* wbuf, double* zdir_out) {
+    const int lane = threadIdx.x & 31;
+    const int d = lv.d;
+    const RowRec rr = lv.rows[R];
+    const double Tt = lv.T - rr.t;
+    const bool term_direct = !(sqrt(Tt) > 0.0);
     const PhiloxKey kT = make_key(0u, 0u, lv.seed);
-    const long long world = lv.world, rank = lv.rank;
-    const double sig = lv.sigma;
-
-    double zs = 0.0, uacc = 0.0;
-    const bool top = (lv.out_uz != nullptr);
-    // coordinates are processed in passes of 32*JCH so the per-lane accumulators stay in registers
-    for (int jpass = 0; jpass < d; jpass += 32 * JCH) {
-    double zacc[JCH], zdir[JCH];                   // weighted row sums; directly accumulated (fallback) terms
-#pragma unroll
-    for (int i = 0; i < JCH; ++i) { zacc[i] = 0.0; zdir[i] = 0.0; }
-    double Sc = 0.0, Sd = 0.0, ul = 0.0;           // sum of weights, sum of weight * drift (warp-uniform); per-lane part of u
     const int cnt = (d - jpass < 32 * JCH) ? (d - jpass) : 32 * JCH;
-
-    // stream the rows of a chunk: weight cw (0 for inactive lanes) and point index pt live in the lanes
-    auto stream_rows = [&](int n, double cw, long long pt) {
-        constexpr int UNR = 4;                                        // rows in flight per lane (fewer rows for more occupancy measured slower)
-        int i = 0;
-        for (; i + UNR <= n; i += UNR) {
-            double ci[UNR]; const double* xp[UNR]; double v[UNR][JCH];
+    double zdir[JCH];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) { ci[u] = __shfl_sync(0xffffffffu, cw, i + u); xp[u] = lv.P + __shfl_sync(0xffffffffu, pt, i + u) * D; }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-                for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; v[u][q] = (j < d) ? __ldg(xp[u] + j) : 0.0; }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-                for (int q = 0; q < JCH; ++q) zacc[q] = fma(ci[u], v[u][q], zacc[q]);
-        }
-        for (; i < n; ++i) {
-            const double ci = __shfl_sync(0xffffffffu, cw, i);
-            const double* xp = lv.P + __shfl_sync(0xffffffffu, pt, i) * D;
-#pragma unroll
-            for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; if (j < d) zacc[q] = fma(ci, __ldg(xp + j), zacc[q]); }
-        }
-    };
-    // fallback for the lanes flagged in `mask`: z_j += w * N_j with regenerated normals of flat index base f0
-    auto direct_normals = [&](unsigned mask, double w, unsigned long long f0, PhiloxKey key) {
+    for (int i = 0; i < JCH; ++i) zdir[i] = 0.0;
+    auto direct_normals = [&](unsigned mask, double w, unsigned long long f0) {
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
             const double wi = __shfl_sync(0xffffffffu, w, src);
             const unsigned long long f0i = __shfl_sync(0xffffffffu, f0, src);
             const unsigned long long fs = f0i + (unsigned long long)jpass;
-            fill_chunks(wbuf, fs, cnt, key, lane);
+            fill_chunks(wbuf, fs, cnt, kT, lane);
 #pragma unroll
             for (int q = 0; q < JCH; ++q) {
                 const int j = jpass + lane + 32 * q;
@@ -519,123 +606,111 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
             }
         }
     };
-
-    {   // terminal condition: u = mean g, z = mean(g N) / delta0
-        const int MCg = lv.MCg;
-        const long long s_lo = ceil_div_pos(R * MCg - rank, world), s_hi = ceil_div_pos((R + 1) * MCg - rank, world);
-        const double delta0 = (lv.variant == 0) ? (Tt + 1e-6) : Tt;    // ScaSML.py:213 vs ScaSML_full_history.py:133
-        const double sqT = sqrt(Tt), driftT = lv.mu * Tt;
-        const double scale = 1.0 / ((double)MCg * delta0);
-        const double invT = scale / (sig * sqT);
-        for (long long base = s_lo; base < s_hi; base += 32) {
-            const long long sidx = base + lane;
-            const bool valid = sidx < s_hi;
-            const double gt = valid ? lv.ev0[lv.term_off + sidx] : 0.0;
-            ul += gt / MCg;
-            const int n = (int)((s_hi - base < 32) ? (s_hi - base) : 32);
-            if (sqT > 0.0) {
-                const double cw = gt * invT;
-                double csum = cw;
-                for (int o = 16; o >= 1; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-                Sc += csum; Sd += csum * driftT;
-                stream_rows(n, cw, lv.term_off + sidx);
-            } else {
-                const int m = (int)(rank + world * sidx - R * MCg);
-                direct_normals(__ballot_sync(0xffffffffu, valid), gt,
-                               (unsigned long long)(gidrow * MCg + m) * (unsigned long long)d, kT);
-            }
+    const RowEntries E = row_entries(lv, R);
+    for (long long base = 0; base < E.total; base += 32) {
+        const long long e = base + lane;
+        const bool valid = e < E.total;
+        int kind, MC; long long sidx;
+        const long long pt = entry_point(lv, R, E, valid ? e : 0, kind, sidx, MC);
+        const double uc = valid ? lv.ev1[pt] : 0.0;
+        if (term_direct) {
+            const int m = (int)(lv.rank + (long long)lv.world * sidx - R * MC);
+            const unsigned tmask = __ballot_sync(0xffffffffu, valid && kind == 0);
+            if (tmask) direct_normals(tmask, uc, (unsigned long long)(rr.gid * MC + m) * (unsigned long long)d);
         }
-        // sum first, scale afterwards: with delta0 == 0 (full history at t == T) the reference's mean(g N) / 0 is +-inf, not NaN
-        if (!(sqT > 0.0)) {
+        if (lv.variant == 1) {
+            const bool sv = valid && kind == 1;
+            const long long pgid = sv ? lv.gid[pt] : 0;
+            const double steps = chunk_to_uniform(chunk16((unsigned long long)pgid, kT)) * Tt;
+            const unsigned dmask = __ballot_sync(0xffffffffu, sv && !(sqrt(steps) > 0.0));
+            if (dmask) direct_normals(dmask, uc / sqrt(steps + 1e-6), (unsigned long long)pgid * (unsigned long long)d);   // ScaSML_full_history.py:169
+        }
+    }
+    // terminal fallback: sum first, scale afterwards: with delta0 == 0 (full history at t == T) the reference's mean(g N) / 0 is +-inf, not
+    // NaN.  A row with T == t has Tt == 0, so its full-history step weights uc = Tt (...) are 0 (the reference's 0 * N): scaling them too is harmless.
+    if (term_direct) {
+        const double delta0 = (lv.variant == 0) ? (Tt + 1e-6) : Tt;
 #pragma unroll
-            for (int q = 0; q < JCH; ++q) zdir[q] *= scale;
-        }
+        for (int q = 0; q < JCH; ++q) zdir[q] *= 1.0 / delta0;         // the weights already carry 1 / MC_g
     }
+#pragma unroll
+    for (int q = 0; q < JCH; ++q) zdir_out[32 * q + lane] = zdir[q];
+}
 
-    double delta = Tt + 1e-6;                  // running delta_t of solvers/MLP.py (stale-delta quirk)
-    for (int l = 0; l < L; ++l) {
-        const int q = lv.q[l], MCf = lv.MCf[l];
-        double drk[MAX_Q], cu[MAX_Q], ca[MAX_Q], cs[MAX_Q];
-        if (lv.variant == 0) {
-            for (int k = 0; k < q; ++k) {
-                const int lk = l * MAX_Q + k;
-                const double tk = cloc_of(T, t, lv.cnode[lk]);
-                drk[k] = lv.mu * (tk - t);                          // accumulated drift of the path up to node k
-                const double wk = wloc_of(T, t, lv.wnode[lk]);
-                const double dnew = (tk - t) + 1e-6;
-                const double dadd = lv.stale_delta ? delta : dnew;
-                if (!lv.stale_delta || l >= 1) delta = dnew;
-                cu[k] = wk / MCf;
-                ca[k] = wk / (MCf * dadd);
-                cs[k] = wk / (MCf * delta);
-            }
+template <int JCH, int UNR, int MINB>
+__global__ void __launch_bounds__(128, MINB) reduce_rows_kernel(const __grid_constant__ LevelDev lv) {
+    __shared__ uint4 wbuf_all[4][4 * JCH + 3];
+    __shared__ double zdir_all[4][32 * JCH];
+    const long long R = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (R >= lv.NR) return;
+    const int d = lv.d, D = lv.D, L = lv.L;
+    const RowRec rr = lv.rows[R];
+    const double* x = rr.x;
+    const double t = rr.t;
+    const bool top = (lv.out_uz != nullptr);
+    const bool direct = rr.pad != 0 || !(sqrt(lv.T - t) > 0.0);       // rare: degenerate sample points (regenerated normals)
+    const RowEntries E = row_entries(lv, R);
+
+    double zs = 0.0, uacc = 0.0;
+    // coordinates are processed in passes of 32*JCH so the per-lane accumulators stay in registers
+    for (int jpass = 0; jpass < d; jpass += 32 * JCH) {
+    double zacc[JCH], xr[JCH];                     // weighted row sums; the row itself
+#pragma unroll
+    for (int i = 0; i < JCH; ++i) { const int j = jpass + lane + 32 * i; zacc[i] = 0.0; xr[i] = (j < d) ? __ldg(x + j) : 0.0; }
+    double Sc = 0.0, Sd = 0.0, ul = 0.0;           // per-lane parts of: sum of weights, sum of weight * drift, u
+
+    // The row's sample points form one entry list; a chunk of 32 entries is resolved lane-parallel, so the weights of ALL segments
+    // load in one round trip and the point rows stream without waiting for them (at level 1 a row owns ~10 points in 4 segments).
+    for (long long base = 0; base < E.total; base += 32) {
+        const long long e = base + lane;
+        const bool valid = e < E.total;
+        int kind, MC; long long sidx;
+        const long long pt = entry_point(lv, R, E, valid ? e : 0, kind, sidx, MC);
+        double cw = 0.0, uc = 0.0, tcol = t;
+        if (valid) { cw = lv.ev0[pt]; uc = lv.ev1[pt]; tcol = __ldg(lv.P + pt * D + d); }
+        const int n = (int)((E.total - base < 32) ? (E.total - base) : 32);
+        // stream the rows of the chunk: weight cw (0 for inactive lanes) and point index pt live in the lanes
+        int i = 0;
+        for (; i + UNR <= n; i += UNR) {
+            double ci[UNR]; const double* xp[UNR]; double v[UNR][JCH];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) xp[u] = lv.P + __shfl_sync(0xffffffffu, pt, i + u) * D + jpass + lane;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; v[u][q] = (j < d) ? __ldg(xp[u] + 32 * q) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) ci[u] = __shfl_sync(0xffffffffu, cw, i + u);     // after the row loads: the weights arrive meanwhile
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int q = 0; q < JCH; ++q) zacc[q] = fma(ci[u], v[u][q], zacc[q]);
         }
-        if (!lv.scasml && l == 0) continue;       // MLP: f(x, 0, 0) = 0 at level 0, nothing to add (solvers/MLP.py:243)
-        const long long s_lo = ceil_div_pos(R * MCf - rank, world), s_hi = ceil_div_pos((R + 1) * MCf - rank, world);
-        const long long ne = (s_hi - s_lo) * q;                    // sample points of this row in step set l: (sample, node)
-        for (long long base = 0; base < ne; base += 32) {
-            const long long e = base + lane;
-            const bool valid = e < ne;
-            const long long si = valid ? e / q : 0;
-            const int k = valid ? (int)(e - si * q) : 0;
-            const long long sidx = s_lo + si;
-            const int lk = l * MAX_Q + k;
-            const long long pt = lv.set_off[lk] + sidx;
-            const int m = (int)(rank + world * sidx - R * MCf);
-            const long long pgid = gidrow * MCf + m;
-            const long long crow = sidx - c.rowbase * MCf;        // row of this sample inside the child calls
-            double y1 = 0.0, y2 = 0.0;
-            if (valid) {
-                if (l >= 1) {
-                    double uh = 0.0, sG = 0.0;
-                    if (lv.scasml) { uh = lv.ev0[pt]; sG = sig * lv.ev1[pt]; }
-                    const double* r1 = lv.us[l] + 2 * (c.childbase[lk][0] + crow);
-                    y1 = lv.scasml ? sig * ((r1[0] + uh) * (sG + r1[1]) - uh * sG) : sig * r1[0] * r1[1];
-                    if (l >= 2) {
-                        const double* r2 = lv.us[l - 1] + 2 * (c.childbase[lk][1] + crow);
-                        y2 = lv.scasml ? sig * ((r2[0] + uh) * (sG + r2[1]) - uh * sG) : sig * r2[0] * r2[1];
-                    }
-                } else if (lv.scasml) {
-                    y1 = lv.ev0[pt];                                 // PDE residual of the surrogate (ScaSML.py:275)
-                }
-            }
-            double cw = 0.0, dr = 0.0;
-            unsigned degenerate = 0u;
-            double wdir = 0.0;
-            if (lv.variant == 0) {
-                if (valid) {
-                    ul += cu[k] * (y1 - y2);
-                    cw = (y1 * ca[k] - y2 * cs[k]) / sig;            // z += (y1 / delta_a - y2 / delta_s) w_k / MC_f * W_k
-                    dr = drk[k];
-                }
-            } else {
-                const double tau = chunk_to_uniform(chunk16((unsigned long long)pgid, kT));
-                const double steps = tau * Tt;
-                const double yc = valid ? Tt * (y1 - y2) / MCf : 0.0;
-                ul += yc;
-                const double yz = yc / sqrt(steps + 1e-6);           // ScaSML_full_history.py:169
-                const double sqs = sqrt(steps);
-                if (sqs > 0.0) { cw = yz / (sig * sqs); dr = lv.mu * steps; }     // N = (X - x - mu steps) / (sigma sqrt(steps))
-                else { wdir = yz; degenerate = valid ? 1u : 0u; }
-            }
-            double csum = cw, dsum = cw * dr;
-            for (int o = 16; o >= 1; o >>= 1) { csum += __shfl_xor_sync(0xffffffffu, csum, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o); }
-            Sc += csum; Sd += dsum;
-            const int n = (int)((ne - base < 32) ? (ne - base) : 32);
-            stream_rows(n, cw, pt);
-            const unsigned dmask = __ballot_sync(0xffffffffu, degenerate != 0u);
-            if (dmask) direct_normals(dmask, wdir, (unsigned long long)pgid * (unsigned long long)d, kT);
+        for (; i < n; ++i) {
+            const double* xp = lv.P + __shfl_sync(0xffffffffu, pt, i) * D + jpass + lane;
+            double v[JCH];
+#pragma unroll
+            for (int q = 0; q < JCH; ++q) { const int j = jpass + lane + 32 * q; v[q] = (j < d) ? __ldg(xp + 32 * q) : 0.0; }
+            const double ci = __shfl_sync(0xffffffffu, cw, i);
+#pragma unroll
+            for (int q = 0; q < JCH; ++q) zacc[q] = fma(ci, v[q], zacc[q]);
         }
+        ul += uc; Sc += cw; Sd = fma(cw, lv.mu * (tcol - t), Sd);
     }
+    if (direct) { reduce_direct_terms<JCH>(lv, R, jpass, wbuf_all[warp], zdir_all[warp]); __syncwarp(); }
 
     // clip / cast / row sum (solvers/ScaSML.py:281-284)
-    for (int o = 16; o >= 1; o >>= 1) ul += __shfl_xor_sync(0xffffffffu, ul, o);
+    for (int o = 16; o >= 1; o >>= 1) {
+        ul += __shfl_xor_sync(0xffffffffu, ul, o); Sc += __shfl_xor_sync(0xffffffffu, Sc, o); Sd += __shfl_xor_sync(0xffffffffu, Sd, o);
+    }
     uacc = ul;
 #pragma unroll
     for (int i = 0; i < JCH; ++i) {
         const int j = jpass + lane + 32 * i;
         if (j < d) {
-            double z = (zacc[i] - x[j] * Sc - Sd) + zdir[i];
+            double z = zacc[i] - xr[i] * Sc - Sd;
+            if (direct) z += zdir_all[warp][32 * i + lane];
             if (!lv.partial) {
                 z = clip_keep_nan(z, lv.clip);
                 if (lv.cast_levels && !top) z = round_f16(z);
@@ -644,6 +719,7 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
             if (top) lv.out_uz[R * (d + 1) + 1 + j] = z;
         }
     }
+    __syncwarp();
     }   // jpass
     if (!lv.partial) {
         uacc = clip_keep_nan(uacc, lv.clip);
@@ -659,8 +735,14 @@ __global__ void __launch_bounds__(128) reduce_kernel(LevelDev lv) {
 
 template <int JCH>
 int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
+    point_weights_kernel<<<(unsigned)cdiv(lv.npoints, 256), 256, 0, stream>>>(lv);
+    SC_LAUNCH_CHECK();
     const long long threads = lv.NR * 32;
-    reduce_kernel<JCH><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
+    static const int variant = getenv("SCASML_REDUCE_VARIANT") ? atoi(getenv("SCASML_REDUCE_VARIANT")) : 1;   // experiment switch (measured at C3: 2.9 / 2.6 / 2.8 ms for 0 / 1 / 2)
+    // UNR = point rows in flight per lane, MINB = resident CTAs per SM the register budget is cut for
+    if (variant == 1) reduce_rows_kernel<JCH, 2, 8><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
+    else if (variant == 2) reduce_rows_kernel<JCH, 2, 6><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
+    else reduce_rows_kernel<JCH, 4, 5><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -744,6 +826,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         }
         lv.P = (double*)(ws + lr.off_P);
         lv.gid = (long long*)(ws + lr.off_gid);
+        lv.npoints = lr.npoints;
         lv.rows = (RowRec*)(ws + lr.off_rows);
         lv.ev0 = (double*)(ws + lr.off_ev0);
         lv.ev1 = (double*)(ws + lr.off_ev1);
@@ -877,7 +960,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         else rc = launch_reduce<8>(lv, stream);
         if (rc != OK) return rc;
         end_span();
-        ++launches;
+        launches += 2;
     }
     stats_.eval_time_ns = stats_.sample_time_ns = stats_.reduce_time_ns = 0;
     if (timing) {

@@ -70,6 +70,7 @@ struct LevelDev {
     const CallDev* calls;
     const long long* rowbase;           // [ncalls] compact copy of calls[i].rowbase: the binary search touches 1-2 cache lines, not one per probe
     long long NR;                       // rows at this level
+    long long npoints;                  // sample points of this level (this rank)
     int world, rank;                    // unit striding (top level only; else 1,0)
     int MCg; long long NT;              // terminal samples per row; owned terminal points
     long long term_off;                 // point offset of the terminal section
