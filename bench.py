@@ -39,7 +39,7 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.03)
 
     def summary(self):
         if not self.rows:
@@ -308,6 +308,14 @@ def main():
                     tstats["eval_time_ns"] + tstats["sample_time_ns"] + tstats["reduce_time_ns"], 1),
                 "eval_ms": 1e-6 * tstats["eval_time_ns"], "sample_ms": 1e-6 * tstats["sample_time_ns"],
                 "reduce_ms": 1e-6 * tstats["reduce_time_ns"], "eval_launches": tstats["eval_launches"]}
+
+    # HBM-bound kernels of the step (samplers write, reduction reads the level point buffers: (d+1) * 8 B per sample point)
+    hbm_peak = peaks.get("hbm_gbs", 6554.0) if peaks else 6554.0
+    pt_bytes = (d + 1) * 8.0 * float(stats["executed_points"])
+    hbm = {"unit": "GB/s", "peak": hbm_peak, "bytes_per_point": (d + 1) * 8,
+           "sampler": {"achieved": pt_bytes / max(tstats["sample_time_ns"], 1), "frac": pt_bytes / max(tstats["sample_time_ns"], 1) / hbm_peak},
+           "reduction": {"achieved": pt_bytes / max(tstats["reduce_time_ns"], 1), "frac": pt_bytes / max(tstats["reduce_time_ns"], 1) / hbm_peak}}
+    roofline["hbm_kernels"] = hbm
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

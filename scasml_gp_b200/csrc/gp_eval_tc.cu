@@ -212,8 +212,8 @@ constexpr int NLOAD = 4;                                             // loader w
 constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 1) * 32;             // epilogue | producer | stage-1 issuer | loaders | stage-2 issuer
 constexpr int NB1_MAX = 4;                                           // centre-row ring (decoupled from the S/P slots: the bulk-copy latency
                                                                      // of pair j + 2 must not wait for stage 1 of pair j)
-// barriers: b1_full b1_empty (NB1_MAX each) | b3_full b3_empty s_full p_ready s2_issued (NSLOT each) | t_full t_free a_ready stage_full stage_free
-constexpr int NBAR = 2 * NB1_MAX + 5 * NSLOT + 5;
+// barriers: b1_full b1_empty (NB1_MAX each) | b3_full b3_empty s_full p_ready s2_issued (NSLOT each) | t_full[2] t_free[2] a_ready stage_full stage_free
+constexpr int NBAR = 2 * NB1_MAX + 5 * NSLOT + 7;
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -375,7 +375,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NSLOT pair slots
     uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
     double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
-    double* xchg = feat;                                             // [3][128][4] partial sums of column groups 1..3 (aliases feat, see below)
+    double* xchg = feat;                                             // PDE class: [3][128][4] partial sums of column groups 1..3 (aliases feat)
     TcColDesc* sdesc = (TcColDesc*)(feat + TM * TF_COUNT);              // [TC_MAXCOL] column table (f1, f2, output, 1 / scale)
     GenRec* grec = (GenRec*)(sdesc + TC_MAXCOL);                     // [128] fused sampler: resolved points of the tile being staged
     double* Ki = (double*)(grec + (GEN ? TM : 0));                       // [128] exp(-a |x|^2 / 2) of the staged tile
@@ -398,15 +398,24 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NSLOT + i); };
     auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 3 * NSLOT + i); };
     auto s2_issued = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 4 * NSLOT + i); };
-    const uint32_t t_full = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 5 * NSLOT), t_free = t_full + 8u, a_ready = t_full + 16u,
-                   stage_full = t_full + 24u, stage_free = t_full + 32u;
+    const uint32_t t_full0 = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 5 * NSLOT), t_free0 = t_full0 + 16u, a_ready = t_full0 + 32u,
+                   stage_full = t_full0 + 40u, stage_free = t_full0 + 48u;
+    // T accumulators: double-buffered by point-tile parity where tensor memory has room (u, u + div classes), so the final
+    // contraction of tile it - 1 (loader warps) never holds up stage 2 of tile it.  One barrier pair per buffer: a waiter is
+    // never more than one phase behind.
+    constexpr bool TDBL = (2 * NT <= (int)(COL_A - COL_T));
+    auto t_buf = [&](int tile) { return TDBL ? (tile & 1) : 0; };
+    auto t_cnt = [&](int tile) { return TDBL ? (tile >> 1) : tile; };      // completion index on that buffer's barriers
+    auto t_full = [&](int tile) { return t_full0 + 8u * (uint32_t)t_buf(tile); };
+    auto t_free = [&](int tile) { return t_free0 + 8u * (uint32_t)t_buf(tile); };
 
     if (tid == 0) {
         for (int i = 0; i < NB1_MAX; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
         for (int i = 0; i < NSLOT; ++i) {
             mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI); mbar_init(s2_issued(i), 1);
         }
-        mbar_init(t_full, 1); mbar_init(t_free, NEPI); mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, TDBL ? NLOAD : NEPI); }
+        mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
         fence_barrier_init();
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -554,7 +563,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
                     }
                 }
-                if (j == 0 && it > 0) mbar_wait(t_free, (uint32_t)(it - 1) & 1u);   // T of the previous point tile was read
+                // the T buffer of this tile has been read by the final contraction of the tile that used it last
+                if (j == 0 && it >= (TDBL ? 2 : 1)) mbar_wait(t_free(it), (uint32_t)(t_cnt(it) - 1) & 1u);
                 tc_fence_after();
                 ++p2;
                 const int nsub = (2 * j + 1 < nitem) ? 2 : 1;
@@ -562,7 +572,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const uint32_t pbase = tmem_base + (uint32_t)s * 128u + (uint32_t)sub * 64u;
                     const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT + (uint32_t)sub * B3_SUB) >> 4);
                     const int kc = kc2;
-                    const uint32_t tacc = tmem_base + COL_T + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
+                    const uint32_t tacc = tmem_base + COL_T + (uint32_t)(t_buf(it) * NT) + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
                     const uint32_t nrows = kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY);
                     const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
                     const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
@@ -589,24 +599,32 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (el) { umma_commit(b3_empty(s)); if (stamp && j < 60) TC_STAMP(5 + 4 * j); }   // P consumed (stage-1 issuer, producer)
                 __syncwarp();
             }
-            if (el) umma_commit(t_full);
+            if (el) umma_commit(t_full(it));
             if (el && it == 0) TC_STAMP(248);
             __syncwarp();
         }
     } else if (warp >= NEPI + 2 && warp < NEPI + 2 + NLOAD) {
-        // ===== loader warps: stage the NEXT point tile while the current one is in the main loop.
-        // a' x = hi + lo (f16) into the staging buffer, K_i and row sums.  Two rows per warp pass (16 lanes x 8 columns). =====
-        const int lw = warp - (NEPI + 2);
+        // ===== loader warps.  (1) Stage the NEXT point tile while the current one is in the main loop: a' x = hi + lo (f16) into
+        // the staging buffer, K_i and row sums, two rows per warp pass (16 lanes x 8 columns).  (2) Final contraction of the
+        // PREVIOUS tile, off the epilogue warps' critical path: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col] (FP64, once per
+        // point).  A loader warp stages exactly the 32 rows it later contracts (its tensor-memory lane quadrant, warp % 4), so K_i and
+        // the row sum of a point stay in that thread's registers and the features need no cross-warp synchronisation. =====
+        const int qd = warp & 3;                                     // tensor-memory lane quadrant = row group of this warp
         const double ascale = gp.a * 1.4426950408889634;             // a log2(e): S = log2 of exp(a x.y)
         const int hl = lane & 15, sub = lane >> 4;
         const int c0 = hl * 8;
         const bool active = c0 < NSTEP * 16;
-        for (int it = 0; it < nit; ++it) {
+        constexpr int RPW = TM / NLOAD;                              // rows per loader warp
+        static_assert(RPW == 32, "a loader warp owns one tensor-memory lane quadrant");
+        const int rq = qd * RPW + lane;                              // this thread's row in the contraction
+        double ki_prev = 0.0, sx_prev = 0.0;
+        for (int it = 0; it <= nit; ++it) {
+            double ki_new = 0.0, sx_new = 0.0;
+            if (it < nit) {
             const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
             if (it > 0) mbar_wait(stage_free, (uint32_t)(it - 1) & 1u);     // the previous tile's images are in tensor memory
-            constexpr int RPW = TM / NLOAD;                          // rows per loader warp
             if (GEN) {                                               // phase 1: lane <-> point (32 dependent-load chains in flight per warp)
-                const int rr = lw * RPW + lane;
+                const int rr = qd * RPW + lane;
                 gen_setup(*st.gen, st.gen_off + row0 + rr, row0 + rr < R, grec + rr);
                 __syncwarp();
             }
@@ -615,7 +633,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 double v[2][8];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int r = lw * RPW + (pass * 2 + i) * 2 + sub;
+                    const int r = qd * RPW + (pass * 2 + i) * 2 + sub;
                     const long row = row0 + r;
                     if (GEN) {
                         gen_point(*st.gen, grec[r], st.gen_off + row, hl, lane, v[i], row < R);   // fused sampler: draw, write to HBM, stage
@@ -629,7 +647,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int r = lw * RPW + (pass * 2 + i) * 2 + sub;
+                    const int r = qd * RPW + (pass * 2 + i) * 2 + sub;
                     double nx = 0.0, sx = 0.0;
                     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -657,13 +675,110 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
 #pragma unroll
                     for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
-                    if (hl == 0) { Ki[r] = exp(-0.5 * gp.a * nx); sxs[r] = sx; }
+                    if (hl == 0) { Ki[r] = nx; sxs[r] = sx; }
                 }
             }
-            if (GEN) __threadfence_block();                         // generated rows (global) are re-read by the epilogue warps of this CTA
+            if (GEN) __threadfence_block();                         // generated rows (global) are re-read by this warp's contraction
+            __syncwarp();
+            ki_new = exp(-0.5 * gp.a * Ki[rq]); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
+                                                                     // (one FP64 exp per lane instead of one per row pass)
+            __syncwarp();
+            if (!TDBL) Ki[rq] = ki_new;                              // PDE class: the epilogue warps finalise the tile and read K_i from here
             __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
-            if (it == 1 && lw == 0 && lane == 0) TC_STAMP(1);
+            if (it == 1 && qd == 0 && lane == 0) TC_STAMP(1);
+            if (!GEN && it + 1 < nit) {
+                // pull this warp's 32 rows of the NEXT tile into L2 now: its staging passes (eight dependent load rounds a tile
+                // later) then see L2 latency instead of HBM latency -- staging was finishing after the main loop it should hide behind
+                const long rn = ((long)blockIdx.x + (long)(it + 1) * gridDim.x) * TM + qd * RPW;
+                if (rn < R) {
+                    const long nrow = (R - rn < RPW) ? (R - rn) : RPW;
+                    const char* p0 = (const char*)(X + rn * (long)D);
+                    const long nbytes = nrow * (long)D * 8;
+                    for (long o = (long)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+                }
+            }
+            }
+            if (TDBL && it > 0) {
+                // --- final contraction of tile it - 1 (u, u + div classes: double-buffered T)
+                const int tp = it - 1;
+                const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
+                const bool ok = row < R;
+                const double* xr = X + row * (long)D;
+                double* F = feat + rq * TF_COUNT;                    // private to this thread
+                {
+                    const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+                    double P2 = 0.0, R2 = 0.0;
+#pragma unroll
+                    for (int m = 0; m < MC_IDX; ++m) {
+                        const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                        F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                        P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+                    }
+                    F[TF_ONE] = 1.0; F[TF_SX] = sx_prev; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx_prev - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+                }
+                mbar_wait(t_full(tp), (uint32_t)t_cnt(tp) & 1u);     // all stage-2 MMAs of the tile have completed
+                tc_fence_after();
+                if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(246);
+                const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_T + (uint32_t)(t_buf(tp) * NT);
+                double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
+                // columns of one output are contiguous: accumulate a run (2 multiplies + 1 FMA per column) and fold it into
+                // its output accumulator only when the output changes
+                double run = 0.0;
+                int cur = TO_PAD;
+                auto flush = [&](int o) {
+                    aU += (o == TO_U) ? run : 0.0; aG += (o == TO_G) ? run : 0.0;
+                    aL += (o == TO_L) ? run : 0.0; aT += (o == TO_T) ? run : 0.0;
+                    run = 0.0;
+                };
+                constexpr int CH = 16;                               // T columns per tensor-memory load round (register budget)
+#pragma unroll 1
+                for (int cb = 0; cb < NT; cb += CH) {
+                    float tv[CH];
+                    tmem_ld16(tbase + (uint32_t)cb, tv);
+                    tmem_ld_wait();
+                    if (cb + CH >= NT) {                             // last round: this T buffer may be overwritten (two tiles later)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(t_free(tp));
+                    }
+                    // independent products first (shared-memory loads and multiplies pipeline), then the sequential run bookkeeping
+                    double term[CH];
+                    int outc[CH];
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const TcColDesc dsc = sdesc[cb + i];
+                        outc[i] = dsc.out;
+                        term[i] = (F[dsc.f1] * F[dsc.f2]) * ((double)tv[i] * dsc.inv_scale);       // padded columns: inv_scale = 0
+                    }
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        if (outc[i] != cur) { flush(cur); cur = outc[i]; }
+                        run += term[i];
+                    }
+                }
+                flush(cur);
+                if (ok) {
+                    const double ki = ki_prev;
+                    const double u = ki * aU;
+                    if (CLASS == TC_U) {
+                        const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));              // equations.py:259
+                        out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
+                    } else if (CLASS == TC_UG) {
+                        out0[row] = u;
+                        out1[row] = ki * aG;
+                    } else {
+                        const double gg = ki * aG, l = ki * aL, tt = ki * aT;
+                        const double s2 = gp.sig2;
+                        out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * gg + 0.5 * s2 * l;   // GP.py:767-768
+                        if (out1) out1[row] = gg;
+                        if (out2) out2[row] = l;
+                        if (out3) out3[row] = tt;
+                    }
+                }
+                if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(247);
+            }
+            ki_prev = ki_new; sx_prev = sx_new;
         }
     } else {
         // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
@@ -673,9 +788,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const bool skip_math = (st.dbg_flags & 2) != 0;
         long g = 0;                                                  // global item counter
         double ki_cur = 0.0, sx_cur = 0.0, ki_prev = 0.0, sx_prev = 0.0;
-        for (int it = 0; it <= nit; ++it) {
+        for (int it = 0; it < nit + (TDBL ? 0 : 1); ++it) {
             ki_prev = ki_cur; sx_prev = sx_cur;
-            if (it > 0 && cg == 0) {
+            if (!TDBL && it > 0 && cg == 0) {
                 // features of the tile about to be finalised: issue the (scattered, L2-latency) loads first so that they overlap
                 // the A-image copy of the next tile and the drain of the tensor pipe
                 const long rowp = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM + r;
@@ -696,7 +811,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
                 // have completed (this warp saw s_full of its last item), so the images can be overwritten.
                 mbar_wait(stage_full, (uint32_t)it & 1u);
-                if (cg == 0) { ki_cur = Ki[r]; sx_cur = sxs[r]; }
+                if (!TDBL && cg == 0) { ki_cur = Ki[r]; sx_cur = sxs[r]; }
                 if (warp < 8) {                                      // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
                     const int img = warp >> 2;
                     const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
@@ -715,12 +830,12 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (it == 1 && tid == 0) TC_STAMP(2);
             }
             if (it == 1 && tid == 0) TC_STAMP(245);
-            if (it > 0) {
-                // --- final contraction of tile it - 1: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
+            if (!TDBL && it > 0) {
+                // --- single T buffer (PDE class): final contraction of tile it - 1 here, by all epilogue warps at the tile boundary: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
                 const long row0 = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM;
                 const long row = row0 + r;
                 const bool ok = row < R;
-                mbar_wait(t_full, (uint32_t)(it - 1) & 1u);         // all stage-2 MMAs of the tile have completed
+                mbar_wait(t_full(it - 1), (uint32_t)(it - 1) & 1u);         // all stage-2 MMAs of the tile have completed
                 tc_fence_after();
                 if (it == 1 && tid == 0) TC_STAMP(246);
                 constexpr int NPER = NT / 4;                         // T columns per column group
@@ -730,7 +845,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(t_free);                  // T may be overwritten by the next tile's stage 2
+                if (lane == 0) mbar_arrive(t_free(it - 1));                 // T may be overwritten by the next tile's stage 2
                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // features visible
                 const double* F = feat + r * TF_COUNT;
                 double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
