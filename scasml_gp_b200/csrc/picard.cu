@@ -251,7 +251,7 @@ constexpr int SMP_WARP_FIXED = 32 * (int)sizeof(PtRec);     // bytes per warp be
 
 // terminal points X_T = (x + mu (T-t)) + sigma (sqrt(T-t) N)   (solvers/ScaSML.py:190-198)
 template <int JP>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(LevelDev lv, int nslot) {
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(LevelDev lv, int nslot, int cpts) {
     extern __shared__ __align__(16) uint8_t smp_smem[];
     __half* stab = (__half*)smp_smem;
     load_normal_table(stab, lv.ntab);
@@ -264,11 +264,11 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
     const int d = lv.d, D = lv.D, MCg = lv.MCg;
     const double sigma = lv.sigma, T = lv.T, mu = lv.mu;
     const PhiloxKey key = make_key(0u, 0u, lv.seed);
-    const long long NT = lv.NT, nchunk = (NT + 31) >> 5;
+    const long long NT = lv.NT, nchunk = (NT + cpts - 1) / cpts;     // cpts <= 32 points per chunk (smaller for small launches)
     for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
-        const long long s = ch * 32 + lane;
+        const long long s = ch * cpts + lane;
         __syncwarp();                                                // the previous chunk's records have been consumed
-        if (s < NT) {
+        if (lane < cpts && s < NT) {
             const long long u = lv.rank + (long long)lv.world * s;
             const long long R = u / MCg;
             const int m = (int)(u - R * MCg);
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
             rec[lane] = r;
         }
         __syncwarp();
-        const int npt = (int)((NT - ch * 32 < 32) ? (NT - ch * 32) : 32);
-        double* const outl = lv.P + (lv.term_off + ch * 32) * D + lane;      // this lane's column of the chunk's first point
+        const int npt = (int)((NT - ch * cpts < cpts) ? (NT - ch * cpts) : cpts);
+        double* const outl = lv.P + (lv.term_off + ch * cpts) * D + lane;      // this lane's column of the chunk's first point
         // two points per iteration; an odd tail repeats its last point (same values written twice) so nothing below is conditional
         for (int pp = 0; pp < npt; pp += 2) {
             const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
@@ -303,13 +303,21 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
                 const double sqp = hh ? rb.sq : ra.sq, drp = hh ? rb.drift : ra.drift;
                 const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
                 double* const dst = outl + pi[hh] * D;               // 32-bit offset: one wide multiply-add
+                constexpr int QB = JP < 8 ? JP : 8;                  // column passes per load round (large d: the loads of a round are
+                                                                     // issued together, ahead of the round's stores)
+#pragma unroll 1
+                for (int q0 = 0; q0 < JP; q0 += QB) {
+                    if (!REG && 32 * q0 > d) break;                 // warp-uniform: nothing left in this row
+                    double xin[QB];
 #pragma unroll
-                for (int q = 0; q < JP; ++q) {                       // predicated, no branches: lanes past the row compute garbage and drop it
-                    const int j = lane + 32 * q;
-                    const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
-                    const double xin = REG ? xv[hh][q] : ((j < d) ? __ldg(xs[hh] + j) : 0.0);
-                    const double val = __dadd_rn(__dadd_rn(xin, drp), __dmul_rn(sigma, __dmul_rn(sqp, N)));
-                    store_pred(dst + 32 * q, (j == d) ? T : val, j <= d);
+                    for (int qq = 0; qq < QB; ++qq) { const int j = lane + 32 * (q0 + qq); xin[qq] = REG ? xv[hh][q0 + qq] : ((j < d) ? __ldg(xs[hh] + j) : 0.0); }
+#pragma unroll
+                    for (int qq = 0; qq < QB; ++qq) {                // predicated, no branches: lanes past the row compute garbage and drop it
+                        const int j = lane + 32 * (q0 + qq);
+                        const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
+                        const double val = __dadd_rn(__dadd_rn(xin[qq], drp), __dmul_rn(sigma, __dmul_rn(sqp, N)));
+                        store_pred(dst + 32 * (q0 + qq), (j == d) ? T : val, j <= d);
+                    }
                 }
             }
             __syncwarp();
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
 
 // interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
 template <int JP>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(LevelDev lv, int l, int nslot) {
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(LevelDev lv, int l, int nslot, int cpts) {
     extern __shared__ __align__(16) uint8_t smp_smem[];
     __half* stab = (__half*)smp_smem;
     load_normal_table(stab, lv.ntab);
@@ -336,11 +344,11 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
     const long long NP = lv.NP[l];
     const PhiloxKey kT = make_key(0u, 0u, lv.seed);
     const bool quad = lv.variant == 0;
-    const long long nchunk = (NP + 31) >> 5;
+    const long long nchunk = (NP + cpts - 1) / cpts;
     for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
-        const long long s = ch * 32 + lane;
+        const long long s = ch * cpts + lane;
         __syncwarp();                                                // the previous chunk's records / scalars have been consumed
-        if (s < NP) {
+        if (lane < cpts && s < NP) {
             const long long u = lv.rank + (long long)lv.world * s;
             const long long R = u / MCf;
             const int m = (int)(u - R * MCf);
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
             }
         }
         __syncwarp();
-        const int npt = (int)((NP - ch * 32 < 32) ? (NP - ch * 32) : 32);
+        const int npt = (int)((NP - ch * cpts < cpts) ? (NP - ch * cpts) : cpts);
         for (int pp = 0; pp < npt; pp += 2) {                        // an odd tail repeats its last point: nothing below is conditional
             const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
             const PtRec ra = rec[pi[0]], rb = rec[pi[1]];
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
                 const PhiloxKey key = quad ? make_key(__ldg(keys + lk), 1u, lv.seed) : kT;
                 philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
                 __syncwarp();
-                double* const outl = lv.P + (lv.set_off[lk] + ch * 32) * D + lane;
+                double* const outl = lv.P + (lv.set_off[lk] + ch * cpts) * D + lane;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int p = pi[hh];
@@ -401,15 +409,25 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
                     const double tk = scal[(k * 3 + 0) * 32 + p], sqp = scal[(k * 3 + 1) * 32 + p], drp = scal[(k * 3 + 2) * 32 + p];
                     const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
                     double* const dst = outl + p * D;
-                    const double* prev = (k == 0) ? xs[hh] : lv.P + (lv.set_off[lk - 1] + ch * 32 + p) * D;
+                    const double* prev = (k == 0) ? xs[hh] : lv.P + (lv.set_off[lk - 1] + ch * cpts + p) * D;
+                    constexpr int QB = JP < 8 ? JP : 8;              // column passes per load round
+#pragma unroll 1
+                    for (int q0 = 0; q0 < JP; q0 += QB) {
+                        if (!REG && 32 * q0 > d) break;             // warp-uniform: nothing left in this row
+                        double xin[QB];
 #pragma unroll
-                    for (int q = 0; q < JP; ++q) {                   // predicated, no branches
-                        const int j = lane + 32 * q;
-                        const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
-                        const double xin = REG ? xv[hh][q] : ((j < d) ? prev[j] : 0.0);   // !REG: written by this very thread one step earlier
-                        const double xn = step_add(xin, drp, sigma, sqp, N);
-                        if (REG) xv[hh][q] = xn;
-                        store_pred(dst + 32 * q, (j == d) ? tk : xn, j <= d);
+                        for (int qq = 0; qq < QB; ++qq) {            // !REG: prev was written by this very thread one step earlier
+                            const int j = lane + 32 * (q0 + qq);
+                            xin[qq] = REG ? xv[hh][q0 + qq] : ((j < d) ? prev[j] : 0.0);
+                        }
+#pragma unroll
+                        for (int qq = 0; qq < QB; ++qq) {            // predicated, no branches
+                            const int j = lane + 32 * (q0 + qq);
+                            const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
+                            const double xn = step_add(xin[qq], drp, sigma, sqp, N);
+                            if (REG) xv[hh][q0 + qq] = xn;
+                            store_pred(dst + 32 * (q0 + qq), (j == d) ? tk : xn, j <= d);
+                        }
                     }
                 }
                 __syncwarp();
@@ -748,37 +766,37 @@ int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
 }
 
 template <int JP>
-int launch_sample_terminal_jp(const LevelDev& lv, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+int launch_sample_terminal_jp(const LevelDev& lv, int nslot, int cpts, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
     SC_CUDA(cudaFuncSetAttribute(sample_terminal_kernel<JP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_terminal_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, nslot);
+    sample_terminal_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, nslot, cpts);
     SC_LAUNCH_CHECK();
     return OK;
 }
 template <int JP>
-int launch_sample_paths_jp(const LevelDev& lv, int l, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+int launch_sample_paths_jp(const LevelDev& lv, int l, int nslot, int cpts, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
     SC_CUDA(cudaFuncSetAttribute(sample_paths_kernel<JP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_paths_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, l, nslot);
+    sample_paths_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, l, nslot, cpts);
     SC_LAUNCH_CHECK();
     return OK;
 }
 // JP = passes of 32 columns over the D = d + 1 columns of a point
-int launch_sample_terminal(const LevelDev& lv, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+int launch_sample_terminal(const LevelDev& lv, int nslot, int cpts, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
     const int D = lv.D;
-    if (D <= 32) return launch_sample_terminal_jp<1>(lv, nslot, grid, nwarp, smem, stream);
-    if (D <= 64) return launch_sample_terminal_jp<2>(lv, nslot, grid, nwarp, smem, stream);
-    if (D <= 128) return launch_sample_terminal_jp<4>(lv, nslot, grid, nwarp, smem, stream);
-    if (D <= 256) return launch_sample_terminal_jp<8>(lv, nslot, grid, nwarp, smem, stream);
-    if (D <= 1024) return launch_sample_terminal_jp<32>(lv, nslot, grid, nwarp, smem, stream);
-    return launch_sample_terminal_jp<64>(lv, nslot, grid, nwarp, smem, stream);
+    if (D <= 32) return launch_sample_terminal_jp<1>(lv, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 64) return launch_sample_terminal_jp<2>(lv, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 128) return launch_sample_terminal_jp<4>(lv, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 256) return launch_sample_terminal_jp<8>(lv, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 1024) return launch_sample_terminal_jp<32>(lv, nslot, cpts, grid, nwarp, smem, stream);
+    return launch_sample_terminal_jp<64>(lv, nslot, cpts, grid, nwarp, smem, stream);
 }
-int launch_sample_paths(const LevelDev& lv, int l, int nslot, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
+int launch_sample_paths(const LevelDev& lv, int l, int nslot, int cpts, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
     const int D = lv.D;
-    if (D <= 32) return launch_sample_paths_jp<1>(lv, l, nslot, grid, nwarp, smem, stream);
-    if (D <= 64) return launch_sample_paths_jp<2>(lv, l, nslot, grid, nwarp, smem, stream);
-    if (D <= 128) return launch_sample_paths_jp<4>(lv, l, nslot, grid, nwarp, smem, stream);
-    if (D <= 256) return launch_sample_paths_jp<8>(lv, l, nslot, grid, nwarp, smem, stream);
-    if (D <= 1024) return launch_sample_paths_jp<32>(lv, l, nslot, grid, nwarp, smem, stream);
-    return launch_sample_paths_jp<64>(lv, l, nslot, grid, nwarp, smem, stream);
+    if (D <= 32) return launch_sample_paths_jp<1>(lv, l, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 64) return launch_sample_paths_jp<2>(lv, l, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 128) return launch_sample_paths_jp<4>(lv, l, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 256) return launch_sample_paths_jp<8>(lv, l, nslot, cpts, grid, nwarp, smem, stream);
+    if (D <= 1024) return launch_sample_paths_jp<32>(lv, l, nslot, cpts, grid, nwarp, smem, stream);
+    return launch_sample_paths_jp<64>(lv, l, nslot, cpts, grid, nwarp, smem, stream);
 }
 
 }  // namespace
@@ -880,13 +898,18 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
     int dev = 0, nsm = 0;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    auto sampler_shape = [&](int nq, long long npts, int* nwarp, size_t* smem, unsigned* grid) {
+    auto sampler_shape = [&](int nq, long long npts, int* nwarp, size_t* smem, unsigned* grid, int* cpts) {
         const size_t per_warp = SMP_WARP_FIXED + (size_t)2 * nslot * 16 + (size_t)nq * 3 * 32 * 8;
         int w = SMP_MAX_WARPS;
         while (w > 1 && SMP_TABLE_BYTES + w * per_warp > (size_t)110 * 1024) w >>= 1;      // two CTAs per SM
         if (w < 8) { w = SMP_MAX_WARPS; while (w > 1 && SMP_TABLE_BYTES + w * per_warp > (size_t)220 * 1024) w >>= 1; }
         *nwarp = w; *smem = SMP_TABLE_BYTES + w * per_warp + 512;     // slack: predicated lanes read past the last warp's buffer
-        const long long need = cdiv(cdiv(npts, 32), w);
+        // points per warp chunk: 32, fewer for small launches so that every resident warp of the machine gets work (a warp walks
+        // its chunk two points at a time; small launches are latency-bound by the longest warp)
+        int c = 32;
+        while (c > 2 && cdiv(npts, c) < 2LL * nsm * w) c >>= 1;
+        *cpts = c;
+        const long long need = cdiv(cdiv(npts, c), w);
         *grid = (unsigned)std::min<long long>(need, 2LL * nsm);
     };
     // optional CUDA-event timing of the three kernel groups (sampler / evaluation / reduction)
@@ -910,17 +933,17 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         row_setup_kernel<<<(unsigned)cdiv(lv.NR, 256), 256, 0, stream>>>(lv);
         SC_LAUNCH_CHECK(); ++launches;
         if (!fused && lv.NT > 0) {
-            int nwarp; size_t smem; unsigned grid;
-            sampler_shape(0, lv.NT, &nwarp, &smem, &grid);
-            const int rc = launch_sample_terminal(lv, nslot, grid, nwarp, smem, stream);
+            int nwarp, cpts; size_t smem; unsigned grid;
+            sampler_shape(0, lv.NT, &nwarp, &smem, &grid, &cpts);
+            const int rc = launch_sample_terminal(lv, nslot, cpts, grid, nwarp, smem, stream);
             if (rc != OK) return rc;
             ++launches;
         }
         for (int l = 0; l < L && !fused; ++l) {
             if (lv.NP[l] == 0) continue;
-            int nwarp; size_t smem; unsigned grid;
-            sampler_shape(p_.variant == 0 ? lv.q[l] : 1, lv.NP[l], &nwarp, &smem, &grid);
-            const int rc = launch_sample_paths(lv, l, nslot, grid, nwarp, smem, stream);
+            int nwarp, cpts; size_t smem; unsigned grid;
+            sampler_shape(p_.variant == 0 ? lv.q[l] : 1, lv.NP[l], &nwarp, &smem, &grid, &cpts);
+            const int rc = launch_sample_paths(lv, l, nslot, cpts, grid, nwarp, smem, stream);
             if (rc != OK) return rc;
             ++launches;
         }
