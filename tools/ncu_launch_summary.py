@@ -5,7 +5,7 @@ import csv
 import re
 import sys
 
-path, nlast = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30
+path, nlast = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 42      # launches of one u_solve at n = 4 (+ the top-level u_hat)
 lines = [l for l in open(path) if not l.startswith("==")]
 items = [it for it in csv.DictReader(lines) if it["Metric Name"] == "gpu__time_duration.sum"]
 rows = [(it["Kernel Name"], float(it["Metric Value"].replace(",", "")), it["Grid Size"]) for it in items]
@@ -24,7 +24,7 @@ allns = sum(v for _, v, _ in rows)
 print("| kernel | launches | total ms | share of run |\n|---|---|---|---|")
 for k, (c, v) in sorted(tot.items(), key=lambda x: -x[1][1]):
     print(f"| `{k}` | {c} | {v/1e6:.3f} | {100*v/allns:.1f}% |")
-pic = [(n, v, g) for n, v, g in rows if re.search("sample_|eval_tc|eval_f64|reduce_kernel|mlp_terminal", n)]
+pic = [(n, v, g) for n, v, g in rows if re.search("sample_|eval_tc|eval_f64|reduce_|point_weights|row_setup|mlp_terminal", n)]
 last = pic[-nlast:]
 t = sum(v for _, v, _ in last)
 print(f"\nLast solve pass ({len(last)} launches, {t/1e6:.3f} ms of kernel time):\n")
