@@ -298,11 +298,11 @@ def main():
         peak = 3 * 2 * 4096 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
         peak_note = "FP64 route: cuBLAS fp64 4096^3 GEMM measured in this run (MEASURED_PEAKS.json has no fp64 figure)"
         flop_note = "FP64 FMA pipe (SIMT contraction); credited flops are the algorithmic 2(d+1) per pair-distance"
-    # DRAM traffic of the evaluation launches: ncu --set full on one launch (profiles/r1_ncu_eval_tc.md) measured
-    # dram__bytes_read + write = 819 B per evaluated point (algorithmic: 808 B point row + 8..32 B of outputs)
-    traffic = 819.0 * tstats["eval_points_total"] / max(tstats["eval_launches"], 1) if route == "tc" else None
+    # DRAM traffic of the evaluation launches: ncu --set full on one launch (profiles/r1_ncu_eval_pde.md) measured
+    # dram__bytes_read + write = 827 B per evaluated point on the PDE launch (algorithmic: 808 B point row + 8..32 B of outputs)
+    traffic = 827.0 * tstats["eval_points_total"] / max(tstats["eval_launches"], 1) if route == "tc" else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak,
-                "traffic": traffic, "traffic_note": "bytes per evaluation launch (mean): 819 B/point from the ncu capture in profiles/ x points per launch",
+                "traffic": traffic, "traffic_note": "bytes per evaluation launch (mean): 827 B/point from the ncu capture profiles/r1_ncu_eval_pde.md x points per launch",
                 "kernel": "fused surrogate evaluation (gp_eval*.cu)", "peak_source": peak_note,
                 "note": flop_note, "eval_share_of_step": tstats["eval_time_ns"] / max(
                     tstats["eval_time_ns"] + tstats["sample_time_ns"] + tstats["reduce_time_ns"], 1),
