@@ -324,7 +324,7 @@ int scasml_debug_spd_inverse(double* A_dev, long long n, double* P_dev, void* ws
     SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
     int rc = cholesky_lower(A_dev, (long)n, invd, d_fail, st);
     if (rc != OK) return rc;
-    rc = tri_inverse_lower(A_dev, (long)n, invd, X, tmp, st);
+    rc = tri_inverse_lower(A_dev, (long)n, invd, X, P_dev, st);     // P_dev is written afterwards: scratch until then
     if (rc != OK) return rc;
     rc = dgemm((int)n, (int)n, (int)n, 1.0, X, 1, n, X, n, 1, 0.0, P_dev, n, 0, st);
     if (rc != OK) return rc;

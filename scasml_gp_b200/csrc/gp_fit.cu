@@ -163,48 +163,193 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int Kd, double
     }
 }
 
+
+// Large-tile variant for the O(n^3) products of the fit (trailing updates of the blocked Cholesky, L^-T L^-1): 128 x 128 tile, 8 x 8
+// accumulators per thread (64 FMAs per 16 shared-memory doubles instead of 16 per 8), K tile 16, next tile's global loads in flight
+// during the current tile's FMAs.  A thread's rows / columns are split 4 + 4 (r, r + 64) so that its 32-byte shared-memory reads are
+// conflict-free.  Same operand conventions as dgemm_kernel.
+constexpr int HM = 128, HN = 128, HK = 16;
+
+__global__ void __launch_bounds__(256) dgemm_big_kernel(int M, int N, int Kd, double alpha,
+                                                        const double* __restrict__ A, long sai, long sak,
+                                                        const double* __restrict__ B, long sbk, long sbj,
+                                                        double beta, double* C, long ldc, int lower_only) {
+    if (lower_only && blockIdx.x > blockIdx.y) return;
+    __shared__ double As[HK][HM + 4], Bs[HK][HN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * HM, j0 = blockIdx.x * HN;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    double pa[8], pb[8];                                   // global -> register staging of the next K tile
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + 256 * e;
+            int r, kk;
+            if (sak == 1) { r = idx / HK; kk = idx % HK; } else { kk = idx / HM; r = idx % HM; }
+            const int gi = i0 + r, gk = k0 + kk;
+            pa[e] = (gi < M && gk < Kd) ? A[gi * sai + gk * sak] : 0.0;
+            int c, kb;
+            if (sbk == 1) { c = idx / HK; kb = idx % HK; } else { kb = idx / HN; c = idx % HN; }
+            const int gj = j0 + c, gk2 = k0 + kb;
+            pb[e] = (gj < N && gk2 < Kd) ? B[gk2 * sbk + gj * sbj] : 0.0;
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + 256 * e;
+            int r, kk;
+            if (sak == 1) { r = idx / HK; kk = idx % HK; } else { kk = idx / HM; r = idx % HM; }
+            As[kk][r] = pa[e];
+            int c, kb;
+            if (sbk == 1) { c = idx / HK; kb = idx % HK; } else { kb = idx / HN; c = idx % HN; }
+            Bs[kb][c] = pb[e];
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < Kd; k0 += HK) {
+        __syncthreads();
+        stash();
+        __syncthreads();
+        if (k0 + HK < Kd) fetch(k0 + HK);
+#pragma unroll
+        for (int kk = 0; kk < HK; ++kk) {
+            double av[8], bv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty * 4 + i]; av[4 + i] = As[kk][64 + ty * 4 + i]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { bv[j] = Bs[kk][tx * 4 + j]; bv[4 + j] = Bs[kk][64 + tx * 4 + j]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gi = i0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gj = j0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            if (gj >= N) continue;
+            double* c = C + gi * ldc + gj;
+            *c = alpha * acc[i][j] + (beta == 0.0 ? 0.0 : beta * (*c));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ Cholesky ------------------------------
 constexpr int CB = 64;
 
-// factor the nb x nb (nb <= 64) diagonal block at A[j0][j0] in place (lower), write its inverse to invL[64][64]
-__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, long n, int j0, int nb,
-                                                        double* __restrict__ invL, int* __restrict__ fail) {
+// factor the nb x nb (nb <= 64) diagonal block at A[j0][j0] in place (lower).  256 threads as a 16 x 16 grid over the block: per
+// column one thread takes the square root, the column is scaled, and every thread updates its 16 elements of the trailing part
+// (no integer divisions, three barriers per column).
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, long n, int j0, int nb, int* __restrict__ fail) {
     __shared__ double Ls[CB][CB + 1];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     for (int idx = tid; idx < CB * CB; idx += 256) {
         const int r = idx / CB, c = idx % CB;
         Ls[r][c] = (r < nb && c < nb && c <= r) ? A[(long)(j0 + r) * n + j0 + c] : (r == c ? 1.0 : 0.0);
     }
     __syncthreads();
     for (int j = 0; j < nb; ++j) {
-        if (tid == 0) {
-            const double p = Ls[j][j];
-            if (!(p > 0.0)) { *fail = 1; Ls[j][j] = 1.0; } else Ls[j][j] = sqrt(p);
+        // column j: every thread below the diagonal reads the raw pivot and scales its element by the reciprocal square root itself
+        // (no separate pivot step, no division); thread j stores the square root after the barrier (the update never reads L[j][j])
+        const double p = Ls[j][j];
+        const bool bad = !(p > 0.0);
+        if (tid > j && tid < nb) Ls[tid][j] *= bad ? 1.0 : rsqrt(p);
+        __syncthreads();
+        if (tid == j) { if (bad) *fail = 1; Ls[j][j] = bad ? 1.0 : sqrt(p); }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int r = ty + 16 * a;
+            const double lrj = Ls[r][j];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = tx + 16 * b;
+                if (c > j && c <= r && r < nb) Ls[r][c] = fma(-lrj, Ls[c][j], Ls[r][c]);
+            }
         }
         __syncthreads();
-        const double ljj = Ls[j][j];
-        for (int r = j + 1 + tid; r < nb; r += 256) Ls[r][j] /= ljj;
-        __syncthreads();
-        for (int idx = tid; idx < (nb - j - 1) * (nb - j - 1); idx += 256) {
-            const int r = j + 1 + idx / (nb - j - 1), c = j + 1 + idx % (nb - j - 1);
-            if (c <= r) Ls[r][c] -= Ls[r][j] * Ls[c][j];
-        }
-        __syncthreads();
-    }
-    // inverse by forward substitution, one column per thread (column c of invL is private to thread c)
-    if (tid < CB) {
-        const int c = tid;
-        for (int r = 0; r < CB; ++r) {
-            double s = (r == c) ? 1.0 : 0.0;
-            for (int k = c; k < r; ++k) s -= Ls[r][k] * invL[k * CB + c];
-            invL[r * CB + c] = (r < c) ? 0.0 : s / Ls[r][r];
-        }
     }
     for (int idx = tid; idx < CB * CB; idx += 256) {
         const int r = idx / CB, c = idx % CB;
         if (r < nb && c < nb) A[(long)(j0 + r) * n + j0 + c] = (c <= r) ? Ls[r][c] : 0.0;
     }
 }
+
+// fused panel solve of the blocked Cholesky: L21 = A21 L11^-T, one thread per row of A21 (forward substitution against the freshly
+// factored diagonal block held in shared memory); the row tile goes through shared memory so that global traffic stays coalesced.
+constexpr int TRSM_ROWS = 128;
+__global__ void __launch_bounds__(TRSM_ROWS) trsm_panel_kernel(double* __restrict__ A, long n, int j0, int nb, long rest) {
+    extern __shared__ double trsm_smem[];
+    double (*L11)[CB + 1] = (double (*)[CB + 1])trsm_smem;
+    double (*Xs)[CB + 1] = (double (*)[CB + 1])(trsm_smem + CB * (CB + 1));   // [TRSM_ROWS][CB + 1]
+    const int tid = threadIdx.x;
+    const long row0 = (long)blockIdx.x * TRSM_ROWS;
+    for (int idx = tid; idx < CB * CB; idx += TRSM_ROWS) {
+        const int r = idx / CB, c = idx % CB;
+        L11[r][c] = (r < nb && c < nb) ? A[(long)(j0 + r) * n + j0 + c] : (r == c ? 1.0 : 0.0);
+    }
+    double* A21 = A + (long)(j0 + nb) * n + j0;
+    for (int idx = tid; idx < TRSM_ROWS * CB; idx += TRSM_ROWS) {
+        const int r = idx / CB, c = idx % CB;
+        Xs[r][c] = (row0 + r < rest && c < nb) ? A21[(row0 + r) * n + c] : 0.0;
+    }
+    __syncthreads();
+    // right-looking substitution with the row in registers (fully unrolled: every FMA of a step is independent, the L11 entries are
+    // shared-memory broadcasts, the diagonal enters through its reciprocal); padded columns (nb < 64) see an identity block
+    __shared__ double rdiag[CB];
+    if (tid < CB) rdiag[tid] = 1.0 / L11[tid][tid];
+    __syncthreads();
+    double x[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) x[c] = Xs[tid][c];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        x[c] *= rdiag[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < CB; ++c2) x[c2] = fma(-x[c], L11[c2][c], x[c2]);
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) Xs[tid][c] = x[c];
+    __syncthreads();
+    for (int idx = tid; idx < TRSM_ROWS * CB; idx += TRSM_ROWS) {
+        const int r = idx / CB, c = idx % CB;
+        if (row0 + r < rest && c < nb) A21[(row0 + r) * n + c] = Xs[r][c];
+    }
+}
+constexpr size_t TRSM_SMEM = (size_t)(CB + TRSM_ROWS) * (CB + 1) * sizeof(double);
+
+// inverses of ALL 64 x 64 diagonal blocks of a factored matrix at once (one CTA per block, off the factorisation's critical path);
+// they seed the explicit triangular inverse and serve the block substitutions of chol_solve.
+__global__ void __launch_bounds__(CB) diag_inverse_kernel(const double* __restrict__ A, long n, double* __restrict__ invdiag) {
+    extern __shared__ double dinv_smem[];
+    double (*Ls)[CB + 1] = (double (*)[CB + 1])dinv_smem;
+    double (*Iv)[CB + 1] = (double (*)[CB + 1])(dinv_smem + CB * (CB + 1));  // TRANSPOSED: Iv[c][r] = inv(L)[r][c]
+    const long j0 = (long)blockIdx.x * CB;
+    const int nb = (int)((n - j0 < CB) ? (n - j0) : CB);
+    const int t = threadIdx.x;
+    for (int rr = 0; rr < CB; ++rr) Ls[rr][t] = (rr < nb && t < nb && t <= rr) ? A[(j0 + rr) * n + j0 + t] : (rr == t ? 1.0 : 0.0);
+    __syncthreads();
+    const int c = t;                                                        // column c of inv(L) = row c of Iv: private to this thread
+    for (int rr = 0; rr < CB; ++rr) {
+        double s0 = (rr == c) ? 1.0 : 0.0, s1 = 0.0;
+        int k = c;
+        for (; k + 1 < rr; k += 2) { s0 = fma(-Ls[rr][k], Iv[c][k], s0); s1 = fma(-Ls[rr][k + 1], Iv[c][k + 1], s1); }
+        if (k < rr) s0 = fma(-Ls[rr][k], Iv[c][k], s0);
+        Iv[c][rr] = (rr < c) ? 0.0 : (s0 + s1) / Ls[rr][rr];
+    }
+    __syncthreads();
+    double* out = invdiag + (size_t)blockIdx.x * CB * CB;
+    for (int rr = 0; rr < CB; ++rr) out[rr * CB + t] = Iv[t][rr];
+}
+constexpr size_t DINV_SMEM = 2 * CB * (CB + 1) * sizeof(double);
 
 __global__ void zero_upper_kernel(double* A, long n) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -427,53 +572,63 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(const double* __restrict
     }
 }
 
-// solve (L L^T) x = rhs for the blocked Cholesky factor (row-major, lower) using the stored inverses of the
-// 64x64 diagonal blocks; single CTA, x overwrites rhs.  Used for the SPD Newton systems.
-__global__ void __launch_bounds__(256) chol_solve_kernel(const double* __restrict__ Lm, long n,
-                                                          const double* __restrict__ invdiag, double* __restrict__ x) {
-    __shared__ double tvec[CB];
-    __shared__ double part[4][CB];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long nblk = (n + CB - 1) / CB;
-    // forward: L y = rhs
-    for (long b = 0; b < nblk; ++b) {
-        const long b0 = b * CB;
-        const int nb = (int)((n - b0 < CB) ? (n - b0) : CB);
-        for (int r = wid; r < nb; r += 8) {
-            const double* row = Lm + (b0 + r) * n;
-            double acc = 0.0;
-            for (long j = lane; j < b0; j += 32) acc = fma(row[j], x[j], acc);
-            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) tvec[r] = x[b0 + r] - acc;
-        }
-        __syncthreads();
-        const double* inv = invdiag + b * CB * CB;
-        if (tid < nb) {
-            double acc = 0.0;
-            for (int c = 0; c <= tid; ++c) acc = fma(inv[tid * CB + c], tvec[c], acc);
-            x[b0 + tid] = acc;
-        }
-        __syncthreads();
-    }
-    // backward: L^T x = y
-    for (long b = nblk - 1; b >= 0; --b) {
-        const long b0 = b * CB;
-        const int nb = (int)((n - b0 < CB) ? (n - b0) : CB);
-        const int g = tid >> 6, c = tid & 63;
+// solve (L L^T) x = rhs for the blocked Cholesky factor (row-major, lower) using the stored inverses of the 64x64 diagonal
+// blocks, x overwrites rhs.  Column-oriented block substitution over the whole machine: per block column one tiny kernel applies the
+// diagonal-block inverse, one grid-wide kernel subtracts the block's contribution from the remaining right-hand side (the single-CTA
+// version of this solve cost 5.9 ms per Newton step at n = 3 000: pure latency).
+__global__ void __launch_bounds__(64) trsv_diag_kernel(const double* __restrict__ inv, int nb, int transpose, double* __restrict__ xb) {
+    __shared__ double t[CB];
+    const int tid = threadIdx.x;
+    t[tid] = (tid < nb) ? xb[tid] : 0.0;
+    __syncthreads();
+    if (tid < nb) {
         double acc = 0.0;
-        if (c < nb) for (long i = b0 + CB + g; i < n; i += 4) acc = fma(Lm[i * n + b0 + c], x[i], acc);
-        part[g][c] = acc;
-        __syncthreads();
-        if (tid < nb) tvec[tid] = x[b0 + tid] - (part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]);
-        __syncthreads();
-        const double* inv = invdiag + b * CB * CB;
-        if (tid < nb) {
-            double a2 = 0.0;
-            for (int r = tid; r < nb; ++r) a2 = fma(inv[r * CB + tid], tvec[r], a2);   // (inv L_bb)^T
-            x[b0 + tid] = a2;
-        }
-        __syncthreads();
+        if (!transpose) { for (int c = 0; c <= tid; ++c) acc = fma(inv[tid * CB + c], t[c], acc); }
+        else { for (int r = tid; r < nb; ++r) acc = fma(inv[r * CB + tid], t[r], acc); }      // (inv L_bb)^T
+        xb[tid] = acc;
     }
+}
+// forward: x[i] -= L[i, b0 : b0+nb] . x[b0 : b0+nb] for the rows i >= b0 + nb; one warp per row
+__global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* __restrict__ Lm, long n, long b0, int nb, double* __restrict__ x) {
+    const long i = b0 + nb + (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const double* row = Lm + i * n + b0;
+    double acc = 0.0;
+    for (int c = lane; c < nb; c += 32) acc = fma(row[c], x[b0 + c], acc);
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) x[i] -= acc;
+}
+// backward: x[i] -= L[b0 : b0+nb, i]^T . x[b0 : b0+nb] for the columns i < b0; one thread per column (coalesced over i)
+__global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __restrict__ Lm, long n, long b0, int nb, double* __restrict__ x) {
+    __shared__ double xb[CB];
+    if (threadIdx.x < CB) xb[threadIdx.x] = (threadIdx.x < nb) ? x[b0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b0) return;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < nb; ++r) acc = fma(Lm[(b0 + r) * n + i], xb[r], acc);
+    x[i] -= acc;
+}
+
+int chol_solve(const double* Lm, long n, const double* invdiag, double* x, cudaStream_t st) {
+    const long nblk = (n + CB - 1) / CB;
+    for (long b = 0; b < nblk; ++b) {                      // L y = rhs
+        const long b0 = b * CB;
+        const int nb = (int)std::min<long>(CB, n - b0);
+        trsv_diag_kernel<<<1, CB, 0, st>>>(invdiag + b * CB * CB, nb, 0, x + b0);
+        const long rest = n - b0 - nb;
+        if (rest > 0) trsv_update_fwd_kernel<<<(unsigned)cdiv(rest * 32, 256), 256, 0, st>>>(Lm, n, b0, nb, x);
+    }
+    for (long b = nblk - 1; b >= 0; --b) {                 // L^T x = y
+        const long b0 = b * CB;
+        const int nb = (int)std::min<long>(CB, n - b0);
+        trsv_diag_kernel<<<1, CB, 0, st>>>(invdiag + b * CB * CB, nb, 1, x + b0);
+        if (b0 > 0) trsv_update_bwd_kernel<<<(unsigned)cdiv(b0, 256), 256, 0, st>>>(Lm, n, b0, nb, x);
+    }
+    SC_LAUNCH_CHECK();
+    return OK;
 }
 
 }  // namespace
@@ -483,6 +638,12 @@ __global__ void __launch_bounds__(256) chol_solve_kernel(const double* __restric
 int dgemm(int M, int N, int Kd, double alpha, const double* A, long sai, long sak, const double* B, long sbk, long sbj,
           double beta, double* C, long ldc, int lower_only, cudaStream_t st) {
     if (M <= 0 || N <= 0) return OK;
+    if (M > 2 * GM && N > 2 * GN) {                        // the O(n^3) products: large tiles
+        dim3 gridb((unsigned)cdiv(N, HN), (unsigned)cdiv(M, HM));
+        dgemm_big_kernel<<<gridb, 256, 0, st>>>(M, N, Kd, alpha, A, sai, sak, B, sbk, sbj, beta, C, ldc, lower_only);
+        SC_LAUNCH_CHECK();
+        return OK;
+    }
     dim3 grid((unsigned)cdiv(N, GN), (unsigned)cdiv(M, GM));
     dgemm_kernel<<<grid, 256, 0, st>>>(M, N, Kd, alpha, A, sai, sak, B, sbk, sbj, beta, C, ldc, lower_only);
     SC_LAUNCH_CHECK();
@@ -501,45 +662,58 @@ int gram_assemble(const GpView& gp, double* K, double nugget, int f16_entries, c
 
 // in-place lower Cholesky of row-major A[n x n]; invdiag: [ceil(n/64)][64*64] inverses of the diagonal blocks
 int cholesky_lower(double* A, long n, double* invdiag, int* d_fail, cudaStream_t st) {
+    SC_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM));
+    SC_CUDA(cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DINV_SMEM));
     for (long j0 = 0; j0 < n; j0 += CB) {
         const int nb = (int)std::min<long>(CB, n - j0);
-        double* inv = invdiag + (j0 / CB) * CB * CB;
-        chol_diag_kernel<<<1, 256, 0, st>>>(A, n, (int)j0, nb, inv, d_fail);
+        chol_diag_kernel<<<1, 256, 0, st>>>(A, n, (int)j0, nb, d_fail);
         SC_LAUNCH_CHECK();
         const long rest = n - j0 - nb;
         if (rest <= 0) break;
-        double* A21 = A + (j0 + nb) * n + j0;
-        // panel: L21 = A21 * inv(L11)^T   (triangular solve fused as a product with the block inverse)
-        int rc = dgemm((int)rest, nb, nb, 1.0, A21, n, 1, inv, 1, CB, 0.0, A21, n, 0, st);
-        if (rc != OK) return rc;
+        // panel: L21 = A21 L11^-T (fused triangular solve)
+        trsm_panel_kernel<<<(unsigned)cdiv(rest, TRSM_ROWS), TRSM_ROWS, TRSM_SMEM, st>>>(A, n, (int)j0, nb, rest);
+        SC_LAUNCH_CHECK();
         // trailing: A22 -= L21 L21^T (lower tiles only)
+        double* A21 = A + (j0 + nb) * n + j0;
         double* A22 = A + (j0 + nb) * n + (j0 + nb);
-        rc = dgemm((int)rest, (int)rest, nb, -1.0, A21, n, 1, A21, 1, n, 1.0, A22, n, 1, st);
+        const int rc = dgemm((int)rest, (int)rest, nb, -1.0, A21, n, 1, A21, 1, n, 1.0, A22, n, 1, st);
         if (rc != OK) return rc;
     }
     zero_upper_kernel<<<(unsigned)cdiv(n * n, 256), 256, 0, st>>>(A, n);
     SC_LAUNCH_CHECK();
+    diag_inverse_kernel<<<(unsigned)cdiv(n, CB), CB, DINV_SMEM, st>>>(A, n, invdiag);
+    SC_LAUNCH_CHECK();
     return OK;
 }
 
-// X = L^{-1} (lower, row-major), using the diagonal-block inverses; tmp: [64 x n]
-int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X, double* tmp, cudaStream_t st) {
-    SC_CUDA(cudaMemsetAsync(X, 0, (size_t)n * n * sizeof(double), st));
-    for (long i0 = 0; i0 < n; i0 += CB) {
+// X = L^{-1} (lower, row-major), using the diagonal-block inverses; scratch: [n x n] (only its leading (n/2)^2 corner is used).
+// Recursive halving  inv([[A, 0], [C, D]]) = [[A^-1, 0], [-D^-1 C A^-1, D^-1]]  so that almost all of the work is two large
+// products per level (the row-panel formulation did n/64 products with M = 64 rows each: 61 ms of the fit at phi = 4 200).
+static int tri_inverse_rec(const double* L, long n, const double* invdiag, double* X, double* scratch, long b_lo, long b_hi, cudaStream_t st) {
+    if (b_hi - b_lo == 1) {
+        const long i0 = b_lo * CB;
         const int nb = (int)std::min<long>(CB, n - i0);
-        const double* inv = invdiag + (i0 / CB) * CB * CB;
-        // diagonal block: X[i0:i0+nb, i0:i0+nb] = inv(L_ii)
-        SC_CUDA(cudaMemcpy2DAsync(X + i0 * n + i0, n * sizeof(double), inv, CB * sizeof(double),
+        SC_CUDA(cudaMemcpy2DAsync(X + i0 * n + i0, n * sizeof(double), invdiag + b_lo * CB * CB, CB * sizeof(double),
                                   nb * sizeof(double), nb, cudaMemcpyDeviceToDevice, st));
-        if (i0 == 0) continue;
-        // tmp[nb x i0] = L[i0:i0+nb, 0:i0] * X[0:i0, 0:i0]
-        int rc = dgemm(nb, (int)i0, (int)i0, 1.0, L + i0 * n, n, 1, X, n, 1, 0.0, tmp, n, 0, st);
-        if (rc != OK) return rc;
-        // X[i0:i0+nb, 0:i0] = -inv * tmp
-        rc = dgemm(nb, (int)i0, nb, -1.0, inv, CB, 1, tmp, n, 1, 0.0, X + i0 * n, n, 0, st);
-        if (rc != OK) return rc;
+        return OK;
     }
-    return OK;
+    const long b_mid = (b_lo + b_hi) / 2;
+    int rc = tri_inverse_rec(L, n, invdiag, X, scratch, b_lo, b_mid, st);
+    if (rc != OK) return rc;
+    rc = tri_inverse_rec(L, n, invdiag, X, scratch, b_mid, b_hi, st);
+    if (rc != OK) return rc;
+    const long r0 = b_mid * CB, c0 = b_lo * CB;
+    const int m = (int)(std::min<long>(b_hi * CB, n) - r0), k = (int)(r0 - c0);
+    // T[m x k] = L21 * X11
+    rc = dgemm(m, k, k, 1.0, L + r0 * n + c0, n, 1, X + c0 * n + c0, n, 1, 0.0, scratch, n, 0, st);
+    if (rc != OK) return rc;
+    // X21 = -X22 * T
+    return dgemm(m, k, m, -1.0, X + r0 * n + r0, n, 1, scratch, n, 1, 0.0, X + r0 * n + c0, n, 0, st);
+}
+
+int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X, double* scratch, cudaStream_t st) {
+    SC_CUDA(cudaMemsetAsync(X, 0, (size_t)n * n * sizeof(double), st));
+    return tri_inverse_rec(L, n, invdiag, X, scratch, 0, cdiv(n, CB), st);
 }
 
 int lu_solve_inplace(double* H, long n, double* rhs, int* d_fail, cudaStream_t st) {
@@ -612,7 +786,7 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
         set_error("Cholesky decomposition of K + nugget*I failed (non-positive pivot / NaN)");
         return ERR_NUMERIC;
     }
-    rc = tri_inverse_lower(K, phi, invd, X, tmp, st);
+    rc = tri_inverse_lower(K, phi, invd, X, P, st);      // P is formed afterwards: scratch until then
     if (rc != OK) return rc;
     // P = X^T X (lower tiles, then mirrored)
     rc = dgemm((int)phi, (int)phi, (int)phi, 1.0, X, 1, phi, X, phi, 1, 0.0, P, phi, 1, st);
@@ -653,7 +827,7 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
         SC_CUDA(cudaMemcpyAsync(&h_fail2, d_fail2, sizeof(int), cudaMemcpyDeviceToHost, st));
         SC_CUDA(cudaStreamSynchronize(st));
         if (!h_fail2) {
-            chol_solve_kernel<<<1, 256, 0, st>>>(H, n3, invh, rhs);
+            { const int rcs = chol_solve(H, n3, invh, rhs, st); if (rcs != OK) return rcs; }
             SC_LAUNCH_CHECK();
         } else {
             hessian_kernel<<<(unsigned)cdiv(n3 * n3, 256), 256, 0, st>>>(f, sol, w, P, damping, H);

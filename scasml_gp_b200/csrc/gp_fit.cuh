@@ -6,7 +6,7 @@ namespace scasml {
 
 int gram_assemble(const GpView& gp, double* K /*[phi][phi]*/, double nugget, int f16_entries, cudaStream_t st);
 int cholesky_lower(double* A, long n, double* invdiag, int* d_fail, cudaStream_t st);
-int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X, double* tmp, cudaStream_t st);
+int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X, double* scratch /* [n x n] */, cudaStream_t st);
 int lu_solve_inplace(double* H, long n, double* rhs, int* d_fail, cudaStream_t st);
 int dgemm(int M, int N, int Kd, double alpha, const double* A, long sai, long sak, const double* B, long sbk, long sbj,
           double beta, double* C, long ldc, int lower_only, cudaStream_t st);
