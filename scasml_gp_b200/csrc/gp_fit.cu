@@ -453,51 +453,82 @@ __global__ void axpy_kernel(long n, double alpha, const double* __restrict__ x, 
 // ------------------------------------------------------------------ LU (partial pivoting) -----------------
 constexpr int LB = 32;
 
-// factor panel columns [j0, j0+nb) of row-major A[n x n]; row swaps applied to whole rows and to rhs
-__global__ void __launch_bounds__(1024) lu_panel_kernel(double* __restrict__ A, long n, int j0, int nb,
-                                                        double* __restrict__ rhs, int* __restrict__ fail) {
+
+// ---- pivoted LU, panel on a column-major copy --------------------------------------------------------------------------------
+// The single-CTA panel factorisation used to scan matrix columns in place (stride n doubles: one DRAM sector per element, ~50 us per
+// column at n = 12 000).  Now the (rows x nb) panel is gathered into a column-major buffer, factored there with coalesced column
+// scans, scattered back, and its row interchanges are applied to the rest of the matrix (and to rhs) by a row-coalesced kernel.
+__global__ void __launch_bounds__(256) lu_panel_gather_kernel(const double* __restrict__ A, long n, long j0, int nb, long rows, double* __restrict__ W) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * nb) return;
+    const long i = idx / nb; const int c = (int)(idx % nb);
+    W[(long)c * rows + i] = A[(j0 + i) * n + j0 + c];
+}
+__global__ void __launch_bounds__(256) lu_panel_scatter_kernel(double* __restrict__ A, long n, long j0, int nb, long rows, const double* __restrict__ W) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * nb) return;
+    const long i = idx / nb; const int c = (int)(idx % nb);
+    A[(j0 + i) * n + j0 + c] = W[(long)c * rows + i];
+}
+// W: [nb][rows] column-major panel; piv[j] = row (panel-relative) exchanged with row j.  Pivot = largest |.|, lowest index on ties.
+__global__ void __launch_bounds__(1024) lu_panel_factor_kernel(double* __restrict__ W, long rows, int nb, int* __restrict__ piv, int* __restrict__ fail) {
     __shared__ double s_val[32];
-    __shared__ int s_idx[32];
-    __shared__ int s_piv;
+    __shared__ long s_idx[32];
+    __shared__ long s_piv;
+    __shared__ double s_rowj[LB];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int j = j0; j < j0 + nb; ++j) {
-        double best = -1.0; int bi = j;
-        for (long i = j + tid; i < n; i += 1024) {
-            const double v = fabs(A[i * n + j]);
-            if (v > best) { best = v; bi = (int)i; }
+    for (int j = 0; j < nb; ++j) {
+        double* colj = W + (long)j * rows;
+        double best = -1.0; long bi = j;
+        for (long i = j + tid; i < rows; i += 1024) {
+            const double v = fabs(colj[i]);
+            if (v > best) { best = v; bi = i; }
         }
         for (int o = 16; o >= 1; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const long oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
         if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
         __syncthreads();
         if (tid == 0) {
-            double b = s_val[0]; int ix = s_idx[0];
+            double b = s_val[0]; long ix = s_idx[0];
             for (int w = 1; w < 32; ++w)
                 if (s_val[w] > b || (s_val[w] == b && s_idx[w] < ix)) { b = s_val[w]; ix = s_idx[w]; }
             if (!(b > 0.0)) { *fail = 1; ix = j; }
             s_piv = ix;
-            if (ix != j) { const double t = rhs[j]; rhs[j] = rhs[ix]; rhs[ix] = t; }
+            piv[j] = (int)ix;
         }
         __syncthreads();
-        const int p = s_piv;
-        if (p != j)
-            for (long c = tid; c < n; c += 1024) {
-                const double t = A[(long)j * n + c]; A[(long)j * n + c] = A[(long)p * n + c]; A[(long)p * n + c] = t;
-            }
-        __syncthreads();
-        const double piv = A[(long)j * n + j];
-        const int w = j0 + nb - j - 1;               // remaining panel columns
-        // each warp takes rows; lanes take panel columns (coalesced along the row)
-        for (long i = j + 1 + wid; i < n; i += 32) {
-            double lij = 0.0;
-            if (lane == 0) { lij = A[i * n + j] / piv; A[i * n + j] = lij; }
-            lij = __shfl_sync(0xffffffffu, lij, 0);
-            if (lane < w) A[i * n + j + 1 + lane] -= lij * A[(long)j * n + j + 1 + lane];
+        const long p = s_piv;
+        if (tid < nb) {                                        // interchange rows j and p of the panel; keep row j for the update
+            double* col = W + (long)tid * rows;
+            const double a = col[j], b = col[p];
+            col[j] = b; col[p] = a;
+            s_rowj[tid] = b;
         }
         __syncthreads();
+        const double pivv = s_rowj[j];
+        for (long i = j + 1 + tid; i < rows; i += 1024) {
+            const double lij = colj[i] / pivv;
+            colj[i] = lij;
+            for (int c = j + 1; c < nb; ++c) W[(long)c * rows + i] = fma(-lij, s_rowj[c], W[(long)c * rows + i]);
+        }
+        __syncthreads();
+    }
+}
+// apply the panel's row interchanges to the columns outside the panel (one thread per column: coalesced along the rows) and to rhs
+__global__ void __launch_bounds__(256) lu_apply_swaps_kernel(double* __restrict__ A, long n, long j0, int nb, const int* __restrict__ piv, double* __restrict__ rhs) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n) return;
+    if (c == n) {                                              // the extra thread: right-hand side
+        for (int j = 0; j < nb; ++j) { const long p = j0 + piv[j]; if (p != j0 + j) { const double t = rhs[j0 + j]; rhs[j0 + j] = rhs[p]; rhs[p] = t; } }
+        return;
+    }
+    if (c >= j0 && c < j0 + nb) return;
+    for (int j = 0; j < nb; ++j) {
+        const long p = j0 + piv[j];
+        if (p != j0 + j) { const double t = A[(j0 + j) * n + c]; A[(j0 + j) * n + c] = A[p * n + c]; A[p * n + c] = t; }
     }
 }
 
@@ -717,19 +748,29 @@ int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X,
 }
 
 int lu_solve_inplace(double* H, long n, double* rhs, int* d_fail, cudaStream_t st) {
-    for (long j0 = 0; j0 < n; j0 += LB) {
+    double* W = nullptr;                                    // column-major panel copy + pivots
+    int* piv = nullptr;
+    SC_CUDA(cudaMallocAsync((void**)&W, (size_t)n * LB * sizeof(double), st));
+    SC_CUDA(cudaMallocAsync((void**)&piv, LB * sizeof(int), st));
+    int rc = OK;
+    for (long j0 = 0; j0 < n && rc == OK; j0 += LB) {
         const int nb = (int)std::min<long>(LB, n - j0);
-        lu_panel_kernel<<<1, 1024, 0, st>>>(H, n, (int)j0, nb, rhs, d_fail);
-        SC_LAUNCH_CHECK();
+        const long rows = n - j0;
+        const unsigned g = (unsigned)cdiv(rows * nb, 256);
+        lu_panel_gather_kernel<<<g, 256, 0, st>>>(H, n, j0, nb, rows, W);
+        lu_panel_factor_kernel<<<1, 1024, 0, st>>>(W, rows, nb, piv, d_fail);
+        lu_panel_scatter_kernel<<<g, 256, 0, st>>>(H, n, j0, nb, rows, W);
+        lu_apply_swaps_kernel<<<(unsigned)cdiv(n + 1, 256), 256, 0, st>>>(H, n, j0, nb, piv, rhs);
         const long rest = n - j0 - nb;
         if (rest <= 0) break;
         lu_trsm_kernel<<<(unsigned)cdiv(rest, 256), 256, 0, st>>>(H, n, (int)j0, nb);
-        SC_LAUNCH_CHECK();
-        int rc = dgemm((int)rest, (int)rest, nb, -1.0, H + (j0 + nb) * n + j0, n, 1, H + j0 * n + j0 + nb, n, 1,
-                       1.0, H + (j0 + nb) * n + j0 + nb, n, 0, st);
-        if (rc != OK) return rc;
+        rc = dgemm((int)rest, (int)rest, nb, -1.0, H + (j0 + nb) * n + j0, n, 1, H + j0 * n + j0 + nb, n, 1,
+                   1.0, H + (j0 + nb) * n + j0 + nb, n, 0, st);
     }
-    lu_solve_kernel<<<1, 1024, 0, st>>>(H, n, rhs);
+    if (rc == OK) lu_solve_kernel<<<1, 1024, 0, st>>>(H, n, rhs);
+    cudaFreeAsync(W, st);
+    cudaFreeAsync(piv, st);
+    if (rc != OK) return rc;
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -807,6 +848,7 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
     int nh = 0, steps = 0;
     rc = loss_now(&loss_hist_host[nh++]);
     if (rc != OK) return rc;
+    bool chol_gave_up = false;
     for (int it = 0; it < gn_steps; ++it) {
         // b, w are current (computed by loss_now)
         grad_kernel<<<(unsigned)cdiv(n3, 256), 256, 0, st>>>(f, sol, w, grad, rhs);
@@ -820,12 +862,16 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
         SC_LAUNCH_CHECK();
         // The damped Hessian is symmetric and, near the solution, positive definite: blocked Cholesky first.
         // A non-positive pivot falls back to LU with partial pivoting (what the reference's jnp.linalg.solve does).
-        SC_CUDA(cudaMemsetAsync(d_fail2, 0, sizeof(int), st));
-        rc = cholesky_lower(H, n3, invh, d_fail2, st);
-        if (rc != OK) return rc;
-        int h_fail2 = 0;
-        SC_CUDA(cudaMemcpyAsync(&h_fail2, d_fail2, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SC_CUDA(cudaStreamSynchronize(st));
+        // Once a Hessian of this fit was not SPD the later ones go to LU directly (a failed attempt costs a full factorisation).
+        int h_fail2 = chol_gave_up ? 1 : 0;
+        if (!chol_gave_up) {
+            SC_CUDA(cudaMemsetAsync(d_fail2, 0, sizeof(int), st));
+            rc = cholesky_lower(H, n3, invh, d_fail2, st);
+            if (rc != OK) return rc;
+            SC_CUDA(cudaMemcpyAsync(&h_fail2, d_fail2, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SC_CUDA(cudaStreamSynchronize(st));
+            if (h_fail2) chol_gave_up = true;
+        }
         if (!h_fail2) {
             { const int rcs = chol_solve(H, n3, invh, rhs, st); if (rcs != OK) return rcs; }
             SC_LAUNCH_CHECK();
