@@ -3,9 +3,10 @@
 // The reference walks the Picard tree depth-first in Python, one batch of XLA ops per uz_solve call
 // (solvers/ScaSML.py:149-305; 473 calls at n = rho = 4).  Here the tree is enumerated once on the host
 // (PicardPlan::build), every call of one level is packed into a single level-wise batch, and a level costs
+//   row records      : parent point / global id / time of every row, once (row_setup_kernel)
 //   sampler kernels  : Philox increments + path/terminal points (sample_terminal_kernel, sample_paths_kernel)
 //   evaluation       : fused surrogate kernels over the level's whole point buffer (gp_eval*.cu)
-//   one reduction    : warp-per-row Monte-Carlo means, weights, clip (reduce_kernel)
+//   reduction        : per-point weights (point_weights_kernel), then warp-per-row Monte-Carlo means, clip (reduce_rows_kernel)
 // Levels are sampled top-down (children's rows are the parents' sample points) and reduced bottom-up.
 #include <algorithm>
 #include <cstdlib>
