@@ -330,7 +330,7 @@ def main():
             "data": "synthetic", "config": dict(config, route=route),
             "reference_equivalent_value": ref_equiv, "fit_ms": fit_ms, "newton_steps": gp.newton_steps,
             "finite_fraction": finite,
-            "e2e": {"value": e2e_value, "unit": "sample-points/s", "h2d_bytes_per_step": 2 * B_total * D * 8,
+            "e2e": {"value": e2e_value, "unit": "sample-points/s", "h2d_bytes_per_step": B_total * D * 8,
                     "d2h_bytes_per_step": B_total * D * 8 + B_total * 8, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int((stats["launches"] + 1) * args.steps),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}

@@ -132,16 +132,28 @@ def ensure_normal_table():
     _table_devices.add(dev)
 
 
+_pin = {"buf": None, "evt": None}
+
+
 def to_device(a, pinned=True):
-    """NumPy (any float dtype) -> contiguous float64 CUDA tensor, staged through pinned memory."""
+    """NumPy (any float dtype) -> contiguous float64 CUDA tensor, staged through a cached pinned buffer (page-locking a fresh
+    buffer per call costs more than the copy for the [B, d+1] inputs of a solve)."""
     torch = torch_cuda()
     if isinstance(a, torch.Tensor):
         return a.to(device="cuda", dtype=torch.float64).contiguous()
     a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
-    t = torch.from_numpy(a)
-    if pinned and a.size:
-        t = t.pin_memory()
-    return t.to("cuda", non_blocking=True)
+    if not (pinned and a.size) or a.size > (1 << 26):      # empty, or too large to page-lock a staging copy (> 512 MB)
+        return torch.from_numpy(a).to("cuda")
+    if _pin["evt"] is not None:
+        _pin["evt"].synchronize()                      # the previous copy out of the staging buffer has finished
+    if _pin["buf"] is None or _pin["buf"].numel() < a.size:
+        _pin["buf"] = torch.empty(max(a.size, 1 << 16), dtype=torch.float64).pin_memory()
+    stage = _pin["buf"][:a.size].view(a.shape)
+    stage.copy_(torch.from_numpy(a))
+    out = stage.to("cuda", non_blocking=True)
+    _pin["evt"] = torch.cuda.Event()
+    _pin["evt"].record()
+    return out
 
 
 def ptr(t):

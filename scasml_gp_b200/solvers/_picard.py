@@ -238,11 +238,18 @@ class PicardSolverBase(object):
         return raw
 
     def _u_solve(self, n, rho, x_t, M=None):
-        raw = self._uz(n, rho, x_t, M)
-        u_breve = raw[:, 0][:, np.newaxis].astype(np.float16)
+        x_dev = _lib.to_device(x_t)                               # one host -> device copy serves the correction and u_hat
+        out = self._uz_device(n, rho, x_dev, M)
         if not self.scasml:
+            raw = out.cpu().numpy()
+            self.last_raw = raw
             self.last_raw_u = raw[:, :1]
-            return u_breve
-        u_hat_raw = self.GP.predict_raw(x_t)[:, np.newaxis]
+            return raw[:, 0][:, np.newaxis].astype(np.float16)
+        torch = _lib.torch_cuda()
+        (uh,) = self.GP._eval(x_dev, _lib.EVAL_U)                 # top-level u_hat(x): GP.route (FP64 by default)
+        both = torch.cat((out, uh[:, None]), dim=1).cpu().numpy()  # one device -> host copy
+        raw, u_hat_raw = both[:, :-1], both[:, -1:]
+        self.last_raw = raw
+        u_breve = raw[:, 0][:, np.newaxis].astype(np.float16)
         self.last_raw_u = u_hat_raw + raw[:, :1]
         return u_hat_raw.astype(np.float16) + u_breve             # solvers/ScaSML.py:300-305 (float16 + float16)
