@@ -372,3 +372,20 @@ def test_config2_size_properties():
     b.workspace_budget_bytes = 500 * ws1
     b.u_solve(3, 3, X)
     assert np.array_equal(np.nan_to_num(b.last_raw, nan=7.0), np.nan_to_num(raw_full, nan=7.0))
+
+
+@pytest.mark.parametrize("d", [33, 150, 1100])
+def test_sampler_column_pass_variants_through_the_mlp_solvers(d):
+    """The samplers are templated on the number of 32-column passes over a point (d + 1 <= 32, 64, 128 keep the point in registers;
+    d + 1 <= 256, 1024, 2048 walk it in load rounds): the surrogate-free MLP solvers exercise them at any d against the oracle
+    (quadrature: terminal + chained path kernels; full history: uniform time draws)."""
+    P = _product()
+    eq_o = EquationOracle(d + 1)
+    eq = P["Eq"](d + 1)
+    X = np.concatenate(eq_o.generate_test_data(9, 3, seed=5), axis=0)
+    X[3, -1] = eq_o.T                                       # a degenerate row (T == t)
+    exact = eq_o.exact_solution(X)
+    prod, orac = P["MLP"](eq), MLPOracle(eq_o, cast=False)
+    _check_solver(prod, orac, (2, 2, X), (2, 2, X), X, exact)
+    prod, orac = P["MLPfh"](eq), MLPFullHistoryOracle(eq_o, cast=False)
+    _check_solver(prod, orac, (2, None, X, 3), (2, None, X, 3), X, exact)
