@@ -412,7 +412,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     if (tid == 0) {
         for (int i = 0; i < NB1_MAX; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
         for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI); mbar_init(s2_issued(i), 1);
+            mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(s2_issued(i), 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, TDBL ? NLOAD : NEPI); }
         mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
@@ -899,41 +899,59 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (it == 1 && tid == 0) TC_STAMP(247);
             }
             if (it < nit) {
-                // --- main loop: S -> P in place, one pair (two sub-items, 2 x 16 columns per thread) per barrier round trip
+                // --- main loop: S -> P in place.  The 16 epilogue warps form two groups of 8; group g owns S/P slot g, i.e. every other pair,
+                // and a thread converts 32 centres of BOTH sub-items of its pair (4 chunks of 16 columns).  The fixed cost of a round trip
+                // (barrier wake-up, first tcgen05.ld, tcgen05.wait::st, fence, arrive: ~500 cycles, measured with one-sub-item slots) is paid
+                // once per 64 columns per thread instead of once per 32, and the next chunk's tcgen05.ld is in flight during the current
+                // chunk's ex2 work.  The two groups run half a period apart.
+                static_assert(NSLOT == 2, "one epilogue group per S/P slot");
                 const bool stamp = (it == 1);
+                const int grp = warp >> 3;                           // slot owned by this warp
+                const uint32_t chalf = (uint32_t)((warp >> 2) & 1) * 32u;   // which 32 of a sub-item's 64 centres
                 for (int j = 0; j < npair; ++j, ++g) {
                     const int s = (int)(g % NSLOT);
+                    if (s != grp) continue;
                     const bool two = 2 * j + 1 < nitem;
                     if (st.dbg_flags & 16) mbar_spin(s_full(s), (uint32_t)(g / NSLOT) & 1u); else mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
                     tc_fence_after();
-                    if (tid == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
-                    const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + (uint32_t)cg * 16u;
+                    if ((tid & 255) == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
+                    const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + chalf;
                     if (!skip_math) {
+                        const int nch = two ? 4 : 2;                 // chunk c: sub-item c >> 1, columns 16 (c & 1) .. + 16 of this thread's 32
                         float v[2][16];
                         tmem_ld16(base, v[0]);
-                        if (two) tmem_ld16(base + 64u, v[1]);
-                        tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            if (c == 0 || two) {
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nch) {
+                                tmem_ld_wait();                      // chunk c has arrived
+                                if (c + 1 < nch) tmem_ld16(base + (uint32_t)((c + 1) >> 1) * 64u + (uint32_t)((c + 1) & 1) * 16u, v[(c + 1) & 1]);
                                 uint32_t hi[8], lo[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float p0 = ex2f(v[c][2 * i]), p1 = ex2f(v[c][2 * i + 1]);
+                                    const float p0 = ex2f(v[c & 1][2 * i]), p1 = ex2f(v[c & 1][2 * i + 1]);
                                     hi[i] = pack_f16x2_sat(p0, p1);
                                     const float2 hf = __half22float2(*(const __half2*)&hi[i]);
                                     lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
                                 }
-                                tmem_st8(base + (uint32_t)c * 64u, hi);
-                                tmem_st8(base + (uint32_t)c * 64u + 8u, lo);
+                                // P over S in place: 16 FP32 columns -> [8 columns of hi pairs | 8 columns of lo pairs] (the A operand of stage 2)
+                                const uint32_t cb = base + (uint32_t)(c >> 1) * 64u + (uint32_t)(c & 1) * 16u;
+                                tmem_st8(cb, hi);
+                                tmem_st8(cb + 8u, lo);
                             }
                         }
                         tmem_st_wait();
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (tid == 0 && stamp && j < 60) TC_STAMP(7 + 4 * j);
+                    if ((tid & 255) == 0 && stamp && j < 60) TC_STAMP(7 + 4 * j);
                     if (lane == 0) mbar_arrive(p_ready(s));
+                }
+                // the A images of the next tile overwrite this tile's: every stage-1 MMA of the tile must have completed, also the last pair's,
+                // which may belong to the other group -- the copying warps wait for the final pair's accumulators explicitly
+                if (warp < 8) {                                      // the warps that copy the A images (group 0)
+                    const long gl = g - 1;                           // the tile's last pair (g was advanced past it)
+                    mbar_wait(s_full((int)(gl % NSLOT)), (uint32_t)(gl / NSLOT) & 1u);
+                    tc_fence_after();
                 }
             }
         }
