@@ -180,8 +180,10 @@ __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, i
             const TcColSpec sp = spec[cls * TC_MAXCOL + col];
             TcColDesc dsc;
             dsc.f1 = sp.f1; dsc.f2 = sp.f2; dsc.out = sp.out;
-            for (int q = 0; q < 5; ++q) dsc.pad[q] = 0;
             dsc.inv_scale = 1.0 / (scale * (double)(1 << TC_P_SHIFT));
+            const bool f32ok = dsc.inv_scale > 1e-30 && dsc.inv_scale < 1e30;      // a power of two: exact in FP32 when in range
+            dsc.pad = f32ok ? 0 : 1;                                               // 1: the contraction scales this column in FP64
+            dsc.inv_scale_f = f32ok ? (float)dsc.inv_scale : 1.0f;
             desc[col] = dsc;
         }
     }
@@ -376,8 +378,13 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
     double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
     double* xchg = feat;                                             // PDE class: [3][128][4] partial sums of column groups 1..3 (aliases feat)
-    TcColDesc* sdesc = (TcColDesc*)(feat + TM * TF_COUNT);              // [TC_MAXCOL] column table (f1, f2, output, 1 / scale)
-    GenRec* grec = (GenRec*)(sdesc + TC_MAXCOL);                     // [128] fused sampler: resolved points of the tile being staged
+    // column table of the final contraction, in the form its inner loop wants: per column the byte offsets of its two features in a
+    // row's float feature vector (f1 | f2 << 16) and its scale 1 / (2^s 2^TC_P_SHIFT) spread over the four outputs as a one-hot float4
+    // (the contraction is issue-bound: 44 instructions per column with byte extraction, an output-change test and a select chain per
+    // column became ~14 with this layout, tools/tc_timeline.py)
+    float4* smask = (float4*)(feat + TM * TF_COUNT);                 // [TC_MAXCOL]
+    uint32_t* soff = (uint32_t*)(smask + TC_MAXCOL);                 // [TC_MAXCOL]
+    GenRec* grec = (GenRec*)(soff + TC_MAXCOL);                      // [128] fused sampler: resolved points of the tile being staged
     double* Ki = (double*)(grec + (GEN ? TM : 0));                       // [128] exp(-a |x|^2 / 2) of the staged tile
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
     uint64_t* bars = (uint64_t*)(sxs + TM);
@@ -420,9 +427,11 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     }
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
     for (int c = tid; c < TC_MAXCOL; c += NTHREADS_P) {              // column table -> shared memory (read by every final contraction)
-        TcColDesc dsc = st.desc[c < NT ? c : 0];
-        if (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX)) { dsc.out = TO_PAD; dsc.f1 = 0; dsc.f2 = 0; dsc.inv_scale = 0.0; }
-        sdesc[c] = dsc;
+        const TcColDesc dsc = st.desc[c < NT ? c : 0];
+        const bool dead = (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX));
+        const float sc = dead ? 0.0f : (float)dsc.inv_scale;        // a power of two: exact in FP32 (range checked when the images are built)
+        soff[c] = dead ? 0u : ((uint32_t)dsc.f1 * 4u) | (((uint32_t)dsc.f2 * 4u) << 16);
+        smask[c] = make_float4(dsc.out == TO_U ? sc : 0.0f, dsc.out == TO_G ? sc : 0.0f, dsc.out == TO_L ? sc : 0.0f, dsc.out == TO_T ? sc : 0.0f);
     }
     tc_fence_before();
     __syncthreads();                                                 // TMEM base address + barriers + column table visible
@@ -705,33 +714,31 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
                 const bool ok = row < R;
                 const double* xr = X + row * (long)D;
-                double* F = feat + rq * TF_COUNT;                    // private to this thread
+                // FP64 runs at 1/8 of the FP32 rate on this part (a warp-wide FP64 instruction holds its pipe 8 cycles): the column products
+                // F[f1] F[f2] T[col] are formed in FP32 (their rounding, ~2e-7, is of the size of T's own FP32 accumulation error) and only the
+                // sums over columns stay in FP64.  The features are kept as floats; the few the outputs need exactly stay in registers.
+                float* F = (float*)feat + rq * TF_COUNT;             // private to this thread
+                double f_xt = 0.0;
                 {
                     const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
                     double P2 = 0.0, R2 = 0.0;
 #pragma unroll
                     for (int m = 0; m < MC_IDX; ++m) {
                         const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                        F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                        F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
                         P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
                     }
-                    F[TF_ONE] = 1.0; F[TF_SX] = sx_prev; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx_prev - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+                    F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
+                    F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
+                    f_xt = xt;
                 }
                 mbar_wait(t_full(tp), (uint32_t)t_cnt(tp) & 1u);     // all stage-2 MMAs of the tile have completed
                 tc_fence_after();
                 if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(246);
                 const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_T + (uint32_t)(t_buf(tp) * NT);
                 double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
-                // columns of one output are contiguous: accumulate a run (2 multiplies + 1 FMA per column) and fold it into
-                // its output accumulator only when the output changes
-                double run = 0.0;
-                int cur = TO_PAD;
-                auto flush = [&](int o) {
-                    aU += (o == TO_U) ? run : 0.0; aG += (o == TO_G) ? run : 0.0;
-                    aL += (o == TO_L) ? run : 0.0; aT += (o == TO_T) ? run : 0.0;
-                    run = 0.0;
-                };
                 constexpr int CH = 16;                               // T columns per tensor-memory load round (register budget)
+                const char* Fb = (const char*)F;
 #pragma unroll 1
                 for (int cb = 0; cb < NT; cb += CH) {
                     float tv[CH];
@@ -742,27 +749,22 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         __syncwarp();
                         if (lane == 0) mbar_arrive(t_free(tp));
                     }
-                    // independent products first (shared-memory loads and multiplies pipeline), then the sequential run bookkeeping
-                    double term[CH];
-                    int outc[CH];
+                    // FP32 products and FP32 partial sums per output over the round (one-hot scale masks: no output bookkeeping), FP64 across rounds
+                    float pU = 0.0f, pG = 0.0f, pL = 0.0f, pT = 0.0f;
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
-                        const TcColDesc dsc = sdesc[cb + i];
-                        outc[i] = dsc.out;
-                        term[i] = (F[dsc.f1] * F[dsc.f2]) * ((double)tv[i] * dsc.inv_scale);       // padded columns: inv_scale = 0
+                        const uint32_t o = soff[cb + i];
+                        const float4 m = smask[cb + i];
+                        const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * tv[i];
+                        pU = fmaf(t, m.x, pU); pG = fmaf(t, m.y, pG); pL = fmaf(t, m.z, pL); pT = fmaf(t, m.w, pT);
                     }
-#pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        if (outc[i] != cur) { flush(cur); cur = outc[i]; }
-                        run += term[i];
-                    }
+                    aU += (double)pU; aG += (double)pG; aL += (double)pL; aT += (double)pT;
                 }
-                flush(cur);
                 if (ok) {
                     const double ki = ki_prev;
                     const double u = ki * aU;
                     if (CLASS == TC_U) {
-                        const double gt = 1.0 - 1.0 / (1.0 + exp(F[TF_SX] + F[TF_XT]));              // equations.py:259
+                        const double gt = 1.0 - 1.0 / (1.0 + exp(sx_prev + f_xt));                    // equations.py:259
                         out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
                     } else if (CLASS == TC_UG) {
                         out0[row] = u;
@@ -796,16 +798,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 const long rowp = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM + r;
                 const bool okp = rowp < R;
                 const double* xr = X + rowp * (long)D;
-                double* F = feat + r * TF_COUNT;
+                float* F = (float*)feat + r * TF_COUNT;              // features as floats: the column products are formed in FP32 (see the loader warps)
                 const double xt = okp ? __ldg(xr + d) : 0.0, x0 = okp ? __ldg(xr) : 0.0;
                 double P2 = 0.0, R2 = 0.0;
 #pragma unroll
                 for (int m = 0; m < MC_IDX; ++m) {
                     const double xi = okp ? __ldg(xr + gp.I[m]) : 0.0, xir = okp ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                    F[TF_XI + m] = xi; F[TF_XR + m] = xir;
+                    F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
                     P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
                 }
-                F[TF_ONE] = 1.0; F[TF_SX] = sx_prev; F[TF_XT] = xt; F[TF_X0] = x0; F[TF_SXR] = sx_prev - x0 + xt; F[TF_P2] = P2; F[TF_R2] = R2;
+                F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
+                F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
             }
             if (it < nit) {
                 // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
@@ -839,34 +842,41 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 tc_fence_after();
                 if (it == 1 && tid == 0) TC_STAMP(246);
                 constexpr int NPER = NT / 4;                         // T columns per column group
+                // T is read in rounds of 8 columns: the round's 8 products are independent (their shared-memory loads and FP64
+                // multiplies overlap), only the run bookkeeping is serial.  (One round of 32 columns with a serial chain per column
+                // took 234 cycles per column: 7.5 k cycles of tensor-pipe idle time per point tile, tools/tc_timeline.py.)
+                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // features visible
+                if (it == 1 && tid == 0) TC_STAMP(250);
+                const float* F = (const float*)feat + r * TF_COUNT;
+                double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
+                const char* Fb = (const char*)F;
+                // all of this thread's T columns in one load round (the reads queue behind the next tile's distance MMAs: a round trip
+                // costs ~900 cycles here), then T is free for the next tile's stage 2
                 float tv[NPER];
 #pragma unroll
-                for (int c4 = 0; c4 < NPER; c4 += 4) tmem_ld4(tmem_base + lane_addr + COL_T + (uint32_t)(cg * NPER + c4), tv + c4);
+                for (int c8 = 0; c8 < NPER; c8 += 8) tmem_ld8(tmem_base + lane_addr + COL_T + (uint32_t)(cg * NPER + c8), tv + c8);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(t_free(it - 1));                 // T may be overwritten by the next tile's stage 2
-                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // features visible
-                const double* F = feat + r * TF_COUNT;
-                double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
-                // columns of one output are contiguous: accumulate a run (2 multiplies + 1 FMA per column) and fold it into
-                // its output accumulator only when the output changes
-                double run = 0.0;
-                int cur = TO_PAD;
-                auto flush = [&](int o) {
-                    aU += (o == TO_U) ? run : 0.0; aG += (o == TO_G) ? run : 0.0;
-                    aL += (o == TO_L) ? run : 0.0; aT += (o == TO_T) ? run : 0.0;
-                    run = 0.0;
-                };
+                if (lane == 0) mbar_arrive(t_free(it - 1));
+                if (it == 1 && tid == 0) TC_STAMP(249);
 #pragma unroll
-                for (int i = 0; i < NPER; ++i) {
-                    const TcColDesc dsc = sdesc[cg * NPER + i];
-                    if ((int)dsc.out != cur) { flush(cur); cur = dsc.out; }
-                    run = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, run);      // padded columns: inv_scale = 0
+                for (int cb = 0; cb < NPER; cb += 16) {
+                    // FP32 products and FP32 partial sums per output over 16 columns (one-hot scale masks: no output bookkeeping), FP64 across rounds
+                    float pU = 0.0f, pG = 0.0f, pL = 0.0f, pT = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t o = soff[cg * NPER + cb + i];
+                        const float4 m = smask[cg * NPER + cb + i];
+                        const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * tv[cb + i];
+                        pU = fmaf(t, m.x, pU); pG = fmaf(t, m.y, pG); pL = fmaf(t, m.z, pL); pT = fmaf(t, m.w, pT);
+                    }
+                    aU += (double)pU; aG += (double)pG; aL += (double)pL; aT += (double)pT;
                 }
-                flush(cur);
-                const double f_sx = F[TF_SX], f_xt = F[TF_XT];
+                const double f_sx = (double)F[TF_SX], f_xt = (double)F[TF_XT];       // only the (unused here) terminal form of the u class reads them
+                if (it == 1 && tid == 0) TC_STAMP(251);
                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // everyone is done with the features: xchg reuses their storage
+                if (it == 1 && tid == 0) TC_STAMP(252);
                 if (cg > 0) {
                     double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
                     p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
@@ -968,7 +978,7 @@ static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     return ((CLASS == TC_PDE && GEN) ? 2 : 3) * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
-           + (size_t)TM * TF_COUNT * 8 + TC_MAXCOL * sizeof(TcColDesc) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + NBAR * 8 + 16;
+           + (size_t)TM * TF_COUNT * 8 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t)) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + NBAR * 8 + 16;
 }
 
 template <int CLASS, int NSTEP, bool GEN>

@@ -25,7 +25,8 @@ struct TcColSpec {                   // one coefficient column (host-built table
     unsigned char kern, out, f1, f2, coef, m, n, pad;
 };
 struct TcColDesc {                   // what the kernel's final contraction needs of a column
-    unsigned char f1, f2, out, pad[5];
+    unsigned char f1, f2, out, pad;
+    float inv_scale_f;               // the same power of two in FP32 (exact; 0 when it leaves the FP32 range: the FP64 path is used then)
     double inv_scale;                // 1 / (column scale 2^s * 2^TC_P_SHIFT)
 };
 
