@@ -164,11 +164,17 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int Kd, double
 }
 
 
-// Large-tile variant for the O(n^3) products of the fit (trailing updates of the blocked Cholesky, L^-T L^-1): 128 x 128 tile, 8 x 8
-// accumulators per thread (64 FMAs per 16 shared-memory doubles instead of 16 per 8), K tile 16, next tile's global loads in flight
-// during the current tile's FMAs.  A thread's rows / columns are split 4 + 4 (r, r + 64) so that its 32-byte shared-memory reads are
-// conflict-free.  Same operand conventions as dgemm_kernel.
+// Large-tile variant for the O(n^3) products of the fit (trailing updates of the blocked Cholesky / LU, L^-T L^-1) on the FP64 TENSOR
+// cores: mma.sync.m8n8k4.f64 (DMMA).  Vector FP64 runs at ~1/8 of the FP32 rate on this part (an 8 x 8-per-thread FMA tile topped out at
+// 5.3 TFLOP/s), the FP64 tensor path is what cuBLAS' 35 TFLOP/s comes from.  128 x 128 tile, K tile 16, 8 warps as 4 (M) x 2 (N): a warp
+// owns 32 x 64 = 4 x 8 DMMA tiles (64 accumulator doubles per thread); next K tile's global loads in flight during the current tile's MMAs.
+// Fragment layout (PTX ISA, m8n8k4 .f64): a = A[row lane/4][k lane%4], b = B[k lane%4][col lane/4], c0,c1 = C[row lane/4][col 2 (lane%4) + {0,1}].
+// Shared-memory pitch 132 doubles: the 16 lanes of a half-warp (4 rows x 4 k) hit 16 distinct banks.  Same operand conventions as dgemm_kernel.
 constexpr int HM = 128, HN = 128, HK = 16;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 __global__ void __launch_bounds__(256) dgemm_big_kernel(int M, int N, int Kd, double alpha,
                                                         const double* __restrict__ A, long sai, long sak,
@@ -176,13 +182,15 @@ __global__ void __launch_bounds__(256) dgemm_big_kernel(int M, int N, int Kd, do
                                                         double beta, double* C, long ldc, int lower_only) {
     if (lower_only && blockIdx.x > blockIdx.y) return;
     __shared__ double As[HK][HM + 4], Bs[HK][HN + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2;               // warp tile: rows 32 wm .., columns 64 wn ..
+    const int fr = lane >> 2, fk = lane & 3;               // fragment row / k (A), column / k (B)
     const int i0 = blockIdx.y * HM, j0 = blockIdx.x * HN;
-    double acc[8][8];
+    double acc[4][8][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     double pa[8], pb[8];                                   // global -> register staging of the next K tile
     auto fetch = [&](int k0) {
 #pragma unroll
@@ -217,28 +225,31 @@ __global__ void __launch_bounds__(256) dgemm_big_kernel(int M, int N, int Kd, do
         __syncthreads();
         if (k0 + HK < Kd) fetch(k0 + HK);
 #pragma unroll
-        for (int kk = 0; kk < HK; ++kk) {
-            double av[8], bv[8];
+        for (int k4 = 0; k4 < HK; k4 += 4) {
+            double a[4], b[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty * 4 + i]; av[4 + i] = As[kk][64 + ty * 4 + i]; }
+            for (int mt = 0; mt < 4; ++mt) a[mt] = As[k4 + fk][wm * 32 + mt * 8 + fr];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { bv[j] = Bs[kk][tx * 4 + j]; bv[4 + j] = Bs[kk][64 + tx * 4 + j]; }
+            for (int nt = 0; nt < 8; ++nt) b[nt] = Bs[k4 + fk][wn * 64 + nt * 8 + fr];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+                for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int gi = i0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    for (int mt = 0; mt < 4; ++mt) {
+        const int gi = i0 + wm * 32 + mt * 8 + fr;
         if (gi >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int gj = j0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
-            if (gj >= N) continue;
-            double* c = C + gi * ldc + gj;
-            *c = alpha * acc[i][j] + (beta == 0.0 ? 0.0 : beta * (*c));
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int gj = j0 + wn * 64 + nt * 8 + fk * 2 + q;
+                if (gj >= N) continue;
+                double* c = C + gi * ldc + gj;
+                *c = alpha * acc[mt][nt][q] + (beta == 0.0 ? 0.0 : beta * (*c));
+            }
         }
     }
 }
