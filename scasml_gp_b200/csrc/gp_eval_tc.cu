@@ -411,6 +411,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     // contraction of tile it - 1 (loader warps) never holds up stage 2 of tile it.  One barrier pair per buffer: a waiter is
     // never more than one phase behind.
     constexpr bool TDBL = (2 * NT <= (int)(COL_A - COL_T));
+    constexpr bool LOADER_FIN = true;                                // final contraction on the loader warps (false: single-T classes finalise on the epilogue warps at the tile boundary)
+    constexpr bool EPI_FIN = !TDBL && !LOADER_FIN;
     auto t_buf = [&](int tile) { return TDBL ? (tile & 1) : 0; };
     auto t_cnt = [&](int tile) { return TDBL ? (tile >> 1) : tile; };      // completion index on that buffer's barriers
     auto t_full = [&](int tile) { return t_full0 + 8u * (uint32_t)t_buf(tile); };
@@ -421,7 +423,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int i = 0; i < NSLOT; ++i) {
             mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(s2_issued(i), 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, TDBL ? NLOAD : NEPI); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, EPI_FIN ? NEPI : NLOAD); }
         mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
         fence_barrier_init();
     }
@@ -692,7 +694,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             ki_new = exp(-0.5 * gp.a * Ki[rq]); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
                                                                      // (one FP64 exp per lane instead of one per row pass)
             __syncwarp();
-            if (!TDBL) Ki[rq] = ki_new;                              // PDE class: the epilogue warps finalise the tile and read K_i from here
+            if (EPI_FIN) Ki[rq] = ki_new;                            // the epilogue warps finalise the tile and read K_i from here
             __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
             if (it == 1 && qd == 0 && lane == 0) TC_STAMP(1);
@@ -708,8 +710,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 }
             }
             }
-            if (TDBL && it > 0) {
-                // --- final contraction of tile it - 1 (u, u + div classes: double-buffered T)
+            if (LOADER_FIN && it > 0) {
+                // --- final contraction of tile it - 1
                 const int tp = it - 1;
                 const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
                 const bool ok = row < R;
@@ -739,15 +741,41 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
                 constexpr int CH = 16;                               // T columns per tensor-memory load round (register budget)
                 const char* Fb = (const char*)F;
+                // Single T buffer (PDE class): stage 2 of the next tile waits for T, so it is copied out first -- all but the last round go to
+                // the staging buffer, idle between the A-image copy of tile `it` and the staging of tile it + 1 ([column][row] floats) --
+                // T is released, and the arithmetic follows.
+                float* tsm = (float*)sStage;
+                float tlast[CH];
+                if (!TDBL) {
+                    if (it < nit) mbar_wait(stage_free, (uint32_t)it & 1u);      // tile `it`'s images have left the staging buffer
+#pragma unroll 1
+                    for (int cb = 0; cb + CH < NT; cb += CH) {
+                        float tv[CH];
+                        tmem_ld16(tbase + (uint32_t)cb, tv);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) tsm[(cb + i) * TM + rq] = tv[i];
+                    }
+                    tmem_ld16(tbase + (uint32_t)(NT - CH), tlast);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_free(tp));
+                }
 #pragma unroll 1
                 for (int cb = 0; cb < NT; cb += CH) {
                     float tv[CH];
-                    tmem_ld16(tbase + (uint32_t)cb, tv);
-                    tmem_ld_wait();
-                    if (cb + CH >= NT) {                             // last round: this T buffer may be overwritten (two tiles later)
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(t_free(tp));
+                    if (TDBL) {
+                        tmem_ld16(tbase + (uint32_t)cb, tv);
+                        tmem_ld_wait();
+                        if (cb + CH >= NT) {                         // last round: this T buffer may be overwritten (two tiles later)
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(t_free(tp));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) tv[i] = (cb + CH < NT) ? tsm[(cb + i) * TM + rq] : tlast[i];
                     }
                     // FP32 products and FP32 partial sums per output over the round (one-hot scale masks: no output bookkeeping), FP64 across rounds
                     float pU = 0.0f, pG = 0.0f, pL = 0.0f, pT = 0.0f;
@@ -779,6 +807,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
                 }
                 if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(247);
+                if (!TDBL) asm volatile("bar.sync 2, %0;" ::"n"(NLOAD * 32) : "memory");   // every loader warp is done with the T copy in the staging buffer
             }
             ki_prev = ki_new; sx_prev = sx_new;
         }
@@ -790,9 +819,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const bool skip_math = (st.dbg_flags & 2) != 0;
         long g = 0;                                                  // global item counter
         double ki_cur = 0.0, sx_cur = 0.0, ki_prev = 0.0, sx_prev = 0.0;
-        for (int it = 0; it < nit + (TDBL ? 0 : 1); ++it) {
+        for (int it = 0; it < nit + (EPI_FIN ? 1 : 0); ++it) {
             ki_prev = ki_cur; sx_prev = sx_cur;
-            if (!TDBL && it > 0 && cg == 0) {
+            if (EPI_FIN && it > 0 && cg == 0) {
                 // features of the tile about to be finalised: issue the (scattered, L2-latency) loads first so that they overlap
                 // the A-image copy of the next tile and the drain of the tensor pipe
                 const long rowp = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM + r;
@@ -814,7 +843,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
                 // have completed (this warp saw s_full of its last item), so the images can be overwritten.
                 mbar_wait(stage_full, (uint32_t)it & 1u);
-                if (!TDBL && cg == 0) { ki_cur = Ki[r]; sx_cur = sxs[r]; }
+                if (EPI_FIN && cg == 0) { ki_cur = Ki[r]; sx_cur = sxs[r]; }
                 if (warp < 8) {                                      // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
                     const int img = warp >> 2;
                     const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
@@ -833,7 +862,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (it == 1 && tid == 0) TC_STAMP(2);
             }
             if (it == 1 && tid == 0) TC_STAMP(245);
-            if (!TDBL && it > 0) {
+            if (EPI_FIN && it > 0) {
                 // --- single T buffer (PDE class): final contraction of tile it - 1 here, by all epilogue warps at the tile boundary: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
                 const long row0 = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM;
                 const long row = row0 + r;
