@@ -80,6 +80,23 @@ class ClockSampler(threading.Thread):
         self.index, self.stop_flag, self.rows = index, False, []
 
     def run(self):
+        # NVML in-process (nvidia_ml_py): ~10 ms per sample, so even a half-second timed region gets dozens of samples;
+        # nvidia-smi as a subprocess (~0.3 s per call) is the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            while not self.stop_flag:
+                r = int(get_reasons(h))
+                self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx)]
+                                 + ["Active" if r & b else "Not Active" for _, b in bits])
+                time.sleep(0.01)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
