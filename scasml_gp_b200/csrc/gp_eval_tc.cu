@@ -50,7 +50,7 @@ struct TcDev {
     long long gen_off;               // index of the launch's first point in the level's point buffer
     long long* dbg;
     int dbg_block;
-    int dbg_flags;                   // timeline experiments: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 8 no operand copies (garbage operands)
+    int dbg_flags;                   // timeline experiments: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 8 no operand copies (garbage operands), 16 epilogue spins on s_full, 64 MMA issuers spin
 };
 
 // ---- per-centre coefficient of one column (NumPy statement: tests/tc_expansion_ref.py::centre_coefficient) --------------
@@ -522,7 +522,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
                 // the slot's previous P has been consumed: stage 2 of pair p1 - NSLOT (issued by the other warp) has COMPLETED (handing the
                 // slot back as soon as those MMAs are issued -- tcgen05.mma executes in issue order -- measured no faster)
-                if (p1 >= NSLOT) { mbar_spin(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); tc_fence_after(); }
+                // (suspending wait: with two epilogue groups the issue slots a spinning warp takes cost more than its faster wake-up gains; flag 64 = spin)
+                if (p1 >= NSLOT) { if (st.dbg_flags & 64) mbar_spin(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); else mbar_wait(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); tc_fence_after(); }
                 if (!rdy1 && !nocopy) mbar_wait(b1_full(s1), (uint32_t)(p1 / NB1) & 1u);   // bulk-copy bytes landed (async proxy)
                 const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
                 ++p1;
@@ -567,7 +568,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
                     uint32_t spins = 0;
                     bool a = false, b = nocopy;
-                    while (true) {
+                    if (!(st.dbg_flags & 64)) { mbar_wait(p_ready(s), par); if (!b) mbar_wait(b3_full(s), par); a = b = true; }   // suspending waits (flag 64: poll both barriers in a spin loop)
+                    while (!(a && b)) {
                         if (!a) a = mbar_test_wait(p_ready(s), par);
                         if (!b) b = mbar_test_wait(b3_full(s), par);
                         if (a && b) break;
