@@ -377,7 +377,6 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NSLOT pair slots
     uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
     double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
-    double* xchg = feat;                                             // PDE class: [3][128][4] partial sums of column groups 1..3 (aliases feat)
     // column table of the final contraction, in the form its inner loop wants: per column the byte offsets of its two features in a
     // row's float feature vector (f1 | f2 << 16) and its scale 1 / (2^s 2^TC_P_SHIFT) spread over the four outputs as a one-hot float4
     // (the contraction is issue-bound: 44 instructions per column with byte extraction, an output-change test and a select chain per
@@ -411,8 +410,6 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     // contraction of tile it - 1 (loader warps) never holds up stage 2 of tile it.  One barrier pair per buffer: a waiter is
     // never more than one phase behind.
     constexpr bool TDBL = (2 * NT <= (int)(COL_A - COL_T));
-    constexpr bool LOADER_FIN = true;                                // final contraction on the loader warps (false: single-T classes finalise on the epilogue warps at the tile boundary)
-    constexpr bool EPI_FIN = !TDBL && !LOADER_FIN;
     auto t_buf = [&](int tile) { return TDBL ? (tile & 1) : 0; };
     auto t_cnt = [&](int tile) { return TDBL ? (tile >> 1) : tile; };      // completion index on that buffer's barriers
     auto t_full = [&](int tile) { return t_full0 + 8u * (uint32_t)t_buf(tile); };
@@ -423,7 +420,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int i = 0; i < NSLOT; ++i) {
             mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(s2_issued(i), 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, EPI_FIN ? NEPI : NLOAD); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, NLOAD); }
         mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
         fence_barrier_init();
     }
@@ -696,8 +693,6 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             ki_new = exp(-0.5 * gp.a * Ki[rq]); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
                                                                      // (one FP64 exp per lane instead of one per row pass)
             __syncwarp();
-            if (EPI_FIN) Ki[rq] = ki_new;                            // the epilogue warps finalise the tile and read K_i from here
-            __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
             if (it == 1 && qd == 0 && lane == 0) TC_STAMP(1);
             if (!GEN && it + 1 < nit) {
@@ -712,7 +707,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 }
             }
             }
-            if (LOADER_FIN && it > 0) {
+            if (it > 0) {
                 // --- final contraction of tile it - 1
                 const int tp = it - 1;
                 const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
@@ -816,36 +811,14 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     } else {
         // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
         const int r = (warp & 3) * 32 + lane;
-        const int cg = warp >> 2;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const bool skip_math = (st.dbg_flags & 2) != 0;
         long g = 0;                                                  // global item counter
-        double ki_cur = 0.0, sx_cur = 0.0, ki_prev = 0.0, sx_prev = 0.0;
-        for (int it = 0; it < nit + (EPI_FIN ? 1 : 0); ++it) {
-            ki_prev = ki_cur; sx_prev = sx_cur;
-            if (EPI_FIN && it > 0 && cg == 0) {
-                // features of the tile about to be finalised: issue the (scattered, L2-latency) loads first so that they overlap
-                // the A-image copy of the next tile and the drain of the tensor pipe
-                const long rowp = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM + r;
-                const bool okp = rowp < R;
-                const double* xr = X + rowp * (long)D;
-                float* F = (float*)feat + r * TF_COUNT;              // features as floats: the column products are formed in FP32 (see the loader warps)
-                const double xt = okp ? __ldg(xr + d) : 0.0, x0 = okp ? __ldg(xr) : 0.0;
-                double P2 = 0.0, R2 = 0.0;
-#pragma unroll
-                for (int m = 0; m < MC_IDX; ++m) {
-                    const double xi = okp ? __ldg(xr + gp.I[m]) : 0.0, xir = okp ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                    F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
-                    P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
-                }
-                F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
-                F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
-            }
+        for (int it = 0; it < nit; ++it) {
             if (it < nit) {
                 // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
                 // have completed (this warp saw s_full of its last item), so the images can be overwritten.
                 mbar_wait(stage_full, (uint32_t)it & 1u);
-                if (EPI_FIN && cg == 0) { ki_cur = Ki[r]; sx_cur = sxs[r]; }
                 if (warp < 8) {                                      // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
                     const int img = warp >> 2;
                     const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
@@ -864,81 +837,6 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (it == 1 && tid == 0) TC_STAMP(2);
             }
             if (it == 1 && tid == 0) TC_STAMP(245);
-            if (EPI_FIN && it > 0) {
-                // --- single T buffer (PDE class): final contraction of tile it - 1 here, by all epilogue warps at the tile boundary: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col]   (FP64, once per point)
-                const long row0 = ((long)blockIdx.x + (long)(it - 1) * gridDim.x) * TM;
-                const long row = row0 + r;
-                const bool ok = row < R;
-                mbar_wait(t_full(it - 1), (uint32_t)(it - 1) & 1u);         // all stage-2 MMAs of the tile have completed
-                tc_fence_after();
-                if (it == 1 && tid == 0) TC_STAMP(246);
-                constexpr int NPER = NT / 4;                         // T columns per column group
-                // T is read in rounds of 8 columns: the round's 8 products are independent (their shared-memory loads and FP64
-                // multiplies overlap), only the run bookkeeping is serial.  (One round of 32 columns with a serial chain per column
-                // took 234 cycles per column: 7.5 k cycles of tensor-pipe idle time per point tile, tools/tc_timeline.py.)
-                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // features visible
-                if (it == 1 && tid == 0) TC_STAMP(250);
-                const float* F = (const float*)feat + r * TF_COUNT;
-                double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
-                const char* Fb = (const char*)F;
-                // all of this thread's T columns in one load round (the reads queue behind the next tile's distance MMAs: a round trip
-                // costs ~900 cycles here), then T is free for the next tile's stage 2
-                float tv[NPER];
-#pragma unroll
-                for (int c8 = 0; c8 < NPER; c8 += 8) tmem_ld8(tmem_base + lane_addr + COL_T + (uint32_t)(cg * NPER + c8), tv + c8);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_free(it - 1));
-                if (it == 1 && tid == 0) TC_STAMP(249);
-#pragma unroll
-                for (int cb = 0; cb < NPER; cb += 16) {
-                    // FP32 products and FP32 partial sums per output over 16 columns (one-hot scale masks: no output bookkeeping), FP64 across rounds
-                    float pU = 0.0f, pG = 0.0f, pL = 0.0f, pT = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t o = soff[cg * NPER + cb + i];
-                        const float4 m = smask[cg * NPER + cb + i];
-                        const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * tv[cb + i];
-                        pU = fmaf(t, m.x, pU); pG = fmaf(t, m.y, pG); pL = fmaf(t, m.z, pL); pT = fmaf(t, m.w, pT);
-                    }
-                    aU += (double)pU; aG += (double)pG; aL += (double)pL; aT += (double)pT;
-                }
-                const double f_sx = (double)F[TF_SX], f_xt = (double)F[TF_XT];       // only the (unused here) terminal form of the u class reads them
-                if (it == 1 && tid == 0) TC_STAMP(251);
-                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // everyone is done with the features: xchg reuses their storage
-                if (it == 1 && tid == 0) TC_STAMP(252);
-                if (cg > 0) {
-                    double* p = xchg + ((size_t)(cg - 1) * TM + r) * 4;
-                    p[0] = aU; p[1] = aG; p[2] = aL; p[3] = aT;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
-                if (cg == 0 && ok) {
-#pragma unroll
-                    for (int g2 = 1; g2 < 4; ++g2) {
-                        const double* p = xchg + ((size_t)(g2 - 1) * TM + r) * 4;
-                        aU += p[0]; aG += p[1]; aL += p[2]; aT += p[3];
-                    }
-                    const double ki = ki_prev;
-                    const double u = ki * aU;
-                    if (CLASS == TC_U) {
-                        const double gt = 1.0 - 1.0 / (1.0 + exp(f_sx + f_xt));                      // equations.py:259
-                        out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
-                    } else if (CLASS == TC_UG) {
-                        out0[row] = u;
-                        out1[row] = ki * aG;
-                    } else {
-                        const double gg = ki * aG, l = ki * aL, tt = ki * aT;
-                        const double s2 = gp.sig2;
-                        out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * gg + 0.5 * s2 * l;   // GP.py:767-768
-                        if (out1) out1[row] = gg;
-                        if (out2) out2[row] = l;
-                        if (out3) out3[row] = tt;
-                    }
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");      // feat / xchg reusable
-                if (it == 1 && tid == 0) TC_STAMP(247);
-            }
             if (it < nit) {
                 // --- main loop: S -> P in place.  The 16 epilogue warps form two groups of 8; group g owns S/P slot g, i.e. every other pair,
                 // and a thread converts 32 centres of BOTH sub-items of its pair (4 chunks of 16 columns).  The fixed cost of a round trip

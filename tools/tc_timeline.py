@@ -33,9 +33,7 @@ for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PD
     print(f"== {name}: entry 0, scatter {t[1]-t0}, prologue {t[2]-t0}, exit {t[3]-t0} cycles; items {nitem}")
     f = [int(x - t0) for x in t[244:249]]
     print(f"   tile boundary (stamps of the CTA's SECOND point tile): tile-0 t_full committed {f[4]}, MMA warp enters tile 1 {f[0]}, epilogue enters "
-          f"tile-1 iteration {f[1]}, A images copied {t[2]-t0}, t_full(0) seen {f[2]}, tile-0 outputs written {f[3]}, loader staged tile 1 at {t[1]-t0}")
-    e = [int(x - t0) for x in t[249:253]]
-    print(f"   epilogue-side contraction (PDE class): T loaded {e[0]}, features barrier passed {e[1]}, column loop done {e[2]}, second barrier passed {e[3]}")
+          f"tile-1 iteration {f[1]}, A images copied {t[2]-t0}, loader warp 0 saw t_full(0) {f[2]}, tile-0 outputs written {f[3]}, loader staged tile 1 at {t[1]-t0}")
     for w in range(min(nitem, 44)):
         a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
         print(f"  item {w:2d}: mma issue {a:7d}..{b:7d} ({b-a:5d})   epilogue {c:7d}..{e:7d} ({e-c:5d})")
