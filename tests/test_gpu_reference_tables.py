@@ -36,3 +36,6 @@ def test_simple_uniform_repeated_and_inference_scaling_at_d20():
     # evaluation_counter of the quadrature ScaSML at rho = 2 (83 per u_solve(2, 2))
     assert out["counter_scasml_rho2"] == 83
     assert np.isfinite(out["fit_s"]) and out["newton_steps"] <= 20
+    # ConvergenceRate: slopes of the reference's committed plot (GP 0.37, SCaSML 0.57); ten refits of one GP object
+    assert abs(out["slope_gp"] - ref["slope_gp"][20]) < 0.12, out["slope_gp"]
+    assert abs(out["slope_scasml"] - ref["slope_scasml"][20]) < 0.16, out["slope_scasml"]

@@ -7,6 +7,8 @@ Same call patterns as the reference drivers, without matplotlib / wandb / cProfi
   * SimpleUniform      (tests/SimpleUniform.py:46-136): fit on 1000 + 200 points, 1000 + 200 test points, GP.predict,
                         MLP.u_solve(2, 2), ScaSML.u_solve(2, 2), NaN-masked relative L2, PDE residual statistics;
   * RepeatedExperiment (tests/RepeatedExperiment.py:90-126): the same ten times on fresh test sets, mean relative L2 / mean L1;
+  * ConvergenceRate    (tests/ConvergenceRate.py:85-158): ONE GP object re-fitted on 100 + 20 ... 1000 + 200 points, ScaSML.u_solve(3, 3) on a
+                        fixed test set, slopes of log10(rel-L2) against log10(training size);
   * InferenceScaling   (tests/InferenceScaling.py:99-157): full-history solvers, ONE solver object, rho = 1, 2, 3 (M = 3),
                         improvement of ScaSML over min(GP, MLP) and the cumulative evaluation counter.
 The collocation / test points come from NumPy's global generator (the reference draws them from DeepXDE's pseudo-random sampler,
@@ -38,6 +40,8 @@ REF = {
     "pde_std":    {20: 1.56e-2, 40: 2.43e-2, 60: 2.31e-2, 80: 2.28e-2},
     "improvement": {20: (35.2, 54.8, 56.6), 40: (31.6, 50.4, 51.7), 60: (26.3, 45.5, 47.3), 80: (14.8, 34.4, 41.0)},
     "counter": (10, 64, 310),
+    "slope_gp": {20: 0.37, 40: 0.37, 60: 0.36, 80: 0.35},          # legend of results/**/ConvergenceRate_Verification.pdf
+    "slope_scasml": {20: 0.57, 40: 0.56, 60: 0.53, 80: 0.50},
     "time_scasml": {20: 353.14, 40: 340.37, 60: 347.24, 80: 367.29},
     "time_fit": {20: 63.2, 80: 66.8},
 }
@@ -118,6 +122,28 @@ def run_dim(d, reps, seed=0):
         imp.append(float((min(e1, e2) - e3) / min(e1, e2) * 100))      # tests/InferenceScaling.py:157
         ctr.append(int(g3.evaluation_counter))
     out["improvement"], out["counter"] = imp, ctr
+
+    # ---- ConvergenceRate (quadrature ScaSML, rho = int(ln N / ln ln N) = 3 for N = 120 ... 1200, GN_steps = 20) ----
+    X, exact = one_test_set()
+    gpc = GP_Grad_Dependent_Nonlinear(eq)
+    sc = ScaSML(eq, gpc)
+    sizes, e_gp, e_sc = [], [], []
+    for nd_, nb_ in zip(range(100, 1100, 100), range(20, 220, 20)):
+        a, b = eq.generate_data(nd_, nb_)
+        N = nd_ + nb_
+        rho = int(np.log(N) / np.log(np.log(N)))
+        gpc.GPsolver(a, b, GN_steps=20)
+        s1 = gpc.predict(X).astype(np.float64)
+        s3 = sc.u_solve(rho, rho, X).astype(np.float64)
+        m = ~(np.isnan(s1) | np.isnan(s3) | np.isnan(exact)).flatten()
+        nrm = np.linalg.norm(exact)
+        sizes.append(N)
+        e_gp.append(np.linalg.norm(np.abs(s1.flatten()[m] - exact.flatten()[m])) / nrm)
+        e_sc.append(np.linalg.norm(np.abs(s3.flatten()[m] - exact.flatten()[m])) / nrm)
+    lx = np.log10(np.array(sizes) + 1e-10)
+    out["slope_gp"] = float(-np.polyfit(lx, np.log10(np.array(e_gp) + 1e-10), 1)[0])
+    out["slope_scasml"] = float(-np.polyfit(lx, np.log10(np.array(e_sc) + 1e-10), 1)[0])
+    out["convergence_errors"] = [sizes, [float(v) for v in e_gp], [float(v) for v in e_sc]]
     return out
 
 
@@ -140,7 +166,9 @@ def main():
             ("rel-L2 ScaSML, mean of fresh test sets", "scasml_rep"), ("mean L1 ScaSML, same", "scasml_rep_l1"),
             ("rel-L2 MLP full history n=2 M=3", "mlp_fh"), ("rel-L2 ScaSML full history n=2 M=3", "scasml_fh"),
             ("rel-L2 ScaSML full history, mean of fresh test sets", "scasml_fh_rep"),
-            ("PDE residual of the fitted GP, mean", "pde_mean"), ("PDE residual, std", "pde_std")]
+            ("PDE residual of the fitted GP, mean", "pde_mean"), ("PDE residual, std", "pde_std"),
+            ("convergence slope gamma of the GP (rel-L2 ~ N^-gamma, N = 120 ... 1200)", "slope_gp"),
+            ("convergence slope gamma of ScaSML n = rho = 3", "slope_scasml")]
     for label, key in rows:
         L.append(f"| {label} | " + " | ".join(f"{fmt(REF[key].get(d))} / {fmt(res[d][key])}" for d in args.dims) + " |")
     L.append("| improvement % over min(GP, MLP), full history rho = 1 / 2 / 3 | " + " | ".join(
