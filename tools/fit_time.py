@@ -1,3 +1,4 @@
+"""Wall time of repeated GP fits at the C3 size (d = 100, 1000 + 200 collocation points), steady state (debug aid; needs a GPU)."""
 import sys, time, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
