@@ -95,9 +95,6 @@ SCASML_API int scasml_abi_version(void);
 /* Sampler table: 32768 float16 bit patterns, T[i] = ndtri(0.5 + (i + 0.5)/65536), built on the host.
  * Replaces jax.random.normal(..., dtype=float16) (solvers/ScaSML.py:190,229). Per current device. */
 SCASML_API int scasml_set_normal_table(const uint16_t* half_bits_host);
-/* test hook: normals / uniforms for flat indices start..start+count-1 of stream (k0, domain, seed) */
-SCASML_API int scasml_debug_draw(unsigned stream_id, unsigned domain, unsigned seed, long long start, long long count,
-                      int uniform, double* out_dev, void* stream);
 
 /* equations/equations.py:248-261 (terminal g / exact solution) and :290-304 (generator f) */
 SCASML_API int scasml_equation_g(const double* x_t_dev, long long R, int d, double* out_dev, void* stream);
@@ -140,25 +137,6 @@ SCASML_API int scasml_uz_solve(const scasml_gp* gp, const scasml_picard_params* 
 /* jnp.clip(output_uz, -c, c) of solvers/ScaSML.py:284 (NaN preserved), in place */
 SCASML_API int scasml_clip(double* x_dev, long long count, double c, void* stream);
 
-/* test hooks for the dense FP64 pieces of the fit */
-SCASML_API int scasml_debug_spd_inverse(double* A_dev /*in: SPD, out: L*/, long long n, double* P_dev, void* ws_dev,
-                             size_t ws_bytes, void* stream); /* ws >= (n*n + 64*64*ceil(n/64) + 64*n)*8 */
-SCASML_API int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream);
-/* tcgen05 plumbing self-test: D[128][N] (f32) = A[128][K] (f16) x B[N][K]^T (f16) through the same shared-memory
- * layout, descriptors, tcgen05.mma and tcgen05.ld helpers as the evaluation kernel (descriptor fields at run time) */
-SCASML_API int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* D_dev, int K, int N, unsigned lbo16,
-                         unsigned sbo16, unsigned layout, unsigned kstep_bytes, void* stream);
-/* test hook: SM-clock timeline of CTA `block` of one tcgen05 evaluation launch (stamps_dev: 256 int64; scratch_dev: 4 R doubles).
- * [0] entry [1] operand scatter done [2] prologue done [3] exit; item w: [4+4w] MMA issue start, [5+4w] MMA issue end,
- * [6+4w] epilogue start, [7+4w] epilogue end */
-SCASML_API int scasml_debug_tc_timeline(const scasml_gp* gp, const double* X_dev, long long R, int mode, int block,
-                             long long* stamps_dev, double* scratch_dev, void* stream);
-/* micro-benchmark: cycles per tcgen05.mma (M=128, K=16, f16) for N, `nchains` independent accumulators, A from smem (0) / TMEM (1);
- * cycles_dev[0] = issue span, cycles_dev[1] = span until the commit arrives */
-SCASML_API int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, void* stream);
-/* micro-benchmark of the epilogue pipes (csrc/tc_bench.cu: TMEM load/store, MUFU, split chunk, MMA interference);
- * out_dev: 8 int64: [0] epilogue-warp cycles, [1] MMA issue cycles, [2] MMA cycles until commit, [3] MMA count */
-SCASML_API int scasml_debug_tc_pipe_bench(int mode, int N, int iters, long long* out_dev, void* stream);
 /* 1 if this handle can use SCASML_ROUTE_TC (d <= 1022: resident-operand kernel up to d = 126, K-streamed kernel above) */
 SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 

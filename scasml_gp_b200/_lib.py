@@ -9,6 +9,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libscasml_b200.so")
+LIB_DBG_PATH = os.path.join(HERE, "libscasml_b200_dbg.so")      # test hooks + micro-benchmarks (include/scasml_b200_debug.h)
 
 MAX_LEVEL = 8
 MAX_Q = 8
@@ -38,7 +39,6 @@ _SIGNATURES = {
     "scasml_last_error": (C.c_char_p, []),
     "scasml_abi_version": (C.c_int, []),
     "scasml_set_normal_table": (C.c_int, [C.c_void_p]),
-    "scasml_debug_draw": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "scasml_equation_g": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "scasml_equation_f": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "scasml_gp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double, C.POINTER(C.c_void_p)]),
@@ -58,17 +58,24 @@ _SIGNATURES = {
     "scasml_uz_solve": (C.c_int, [C.c_void_p, C.POINTER(PicardParams), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.POINTER(PicardStats), C.c_void_p]),
     "scasml_clip": (C.c_int, [C.c_void_p, C.c_longlong, C.c_double, C.c_void_p]),
+    "scasml_gp_tc_supported": (C.c_int, [C.c_void_p]),
+}
+
+# exported by libscasml_b200_dbg.so only (tests/, tools/)
+_DEBUG_SIGNATURES = {
+    "scasml_debug_draw": (C.c_int, [C.c_uint, C.c_uint, C.c_uint, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "scasml_debug_spd_inverse": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scasml_debug_lu_solve": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "scasml_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]),
-    "scasml_gp_tc_supported": (C.c_int, [C.c_void_p]),
     "scasml_debug_tc_mma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "scasml_debug_tc_pipe_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "scasml_debug_tc_timeline": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
+_lib_dbg = None
 _table_devices = set()
+_table_devices_dbg = set()
 
 
 class ScasmlError(RuntimeError):
@@ -93,10 +100,27 @@ def load():
     return lib
 
 
-def check(rc):
+def load_debug():
+    """The debug build of the library (same sources + -DSCASML_DEBUG_HOOKS): test hooks and micro-benchmarks only.
+    Handles created by the product library may be passed to it (identical structs); it has its own sampler table."""
+    global _lib_dbg
+    if _lib_dbg is not None:
+        return _lib_dbg
+    if not os.path.exists(LIB_DBG_PATH):
+        raise ScasmlError(f"{LIB_DBG_PATH} is missing: build it with `python -m scasml_gp_b200.build`")
+    lib = C.CDLL(LIB_DBG_PATH)
+    for name, (res, args) in {**_SIGNATURES, **_DEBUG_SIGNATURES}.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib_dbg = lib
+    return lib
+
+
+def check(rc, lib=None):
     if rc == 0:
         return
-    msg = load().scasml_last_error()
+    msg = (lib or load()).scasml_last_error()
     msg = msg.decode() if msg else "unknown error"
     if rc == ERR_NUMERIC:
         raise ValueError(msg)                      # mirrors models/GP.py:264-265
@@ -122,14 +146,16 @@ def normal_half_table():
     return ndtri(0.5 + (i + 0.5) / 65536.0).astype(np.float16)
 
 
-def ensure_normal_table():
+def ensure_normal_table(debug=False):
     torch = torch_cuda()
     dev = torch.cuda.current_device()
-    if dev in _table_devices:
+    seen = _table_devices_dbg if debug else _table_devices
+    if dev in seen:
         return
     tab = np.ascontiguousarray(normal_half_table().view(np.uint16))
-    check(load().scasml_set_normal_table(tab.ctypes.data_as(C.c_void_p)))
-    _table_devices.add(dev)
+    lib = load_debug() if debug else load()
+    check(lib.scasml_set_normal_table(tab.ctypes.data_as(C.c_void_p)), lib)
+    seen.add(dev)
 
 
 _pin = {"buf": None, "evt": None}
@@ -154,6 +180,25 @@ def to_device(a, pinned=True):
     _pin["evt"] = torch.cuda.Event()
     _pin["evt"].record()
     return out
+
+
+_pin_out = {"buf": None}
+
+
+def to_host(t):
+    """CUDA tensor -> NumPy array through a cached pinned staging buffer (a pageable `.cpu()` goes through the driver's own
+    bounce buffers and, with eight ranks on one host, serialises on them)."""
+    torch = torch_cuda()
+    t = t.contiguous()
+    n = t.numel()
+    if n == 0 or t.dtype != torch.float64 or n > (1 << 26):
+        return t.cpu().numpy()
+    if _pin_out["buf"] is None or _pin_out["buf"].numel() < n:
+        _pin_out["buf"] = torch.empty(max(n, 1 << 16), dtype=torch.float64).pin_memory()
+    stage = _pin_out["buf"][:n].view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return stage.numpy().copy()
 
 
 def ptr(t):

@@ -3,12 +3,9 @@
 #include <mutex>
 #include <new>
 #include <vector>
-#include "../../include/scasml_b200.h"
-#include "common.cuh"
-#include "gp.cuh"
+#include "abi_handle.cuh"
 #include "gp_fit.cuh"
 #include "picard.cuh"
-#include "gp_tc.cuh"
 
 static_assert(sizeof(scasml_picard_params) == sizeof(scasml::PicardParams), "ABI struct mismatch");
 static_assert(sizeof(scasml_picard_stats) == sizeof(scasml::PicardStats), "ABI struct mismatch");
@@ -23,21 +20,13 @@ const char* last_error_cstr() { return g_err.c_str(); }
 
 static __half* g_ntab[64] = {nullptr};
 
-static const __half* normal_table_for_current_device() {
+const __half* normal_table_for_current_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     return g_ntab[dev];
 }
 
 namespace {
-
-__global__ void debug_draw_kernel(PhiloxKey key, unsigned long long start, long long count, int uniform,
-                                  const __half* __restrict__ tab, double* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t c = chunk16(start + (unsigned long long)i, key);
-    out[i] = uniform ? chunk_to_uniform(c) : chunk_to_normal(tab, c);
-}
 
 __global__ void equation_g_kernel(const double* __restrict__ x, long long R, int d, double* __restrict__ out) {
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -69,28 +58,18 @@ __global__ void clip_kernel(double* __restrict__ x, long long n, double c) {
     x[i] = (v < -c) ? -c : ((v > c) ? c : v);
 }
 
-__global__ void add_diag_kernel(double* K, long n, double v) {
+// flag = 1 if some centre coordinate is not a float16 value (the tcgen05 route's stage-1 B operand would not be exact)
+__global__ void centres_f16_check_kernel(const double* __restrict__ C, long n, int* __restrict__ flag) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) K[i * n + i] += v;
+    if (i >= n) return;
+    const double v = C[i];
+    if ((double)__half2float(__double2half(v)) != v) *flag = 1;      // NaN centres fail too
 }
 
 }  // namespace
 }  // namespace scasml
 
 using namespace scasml;
-
-struct scasml_gp {
-    GpView v{};
-    double nugget = 1e-2;
-    double sigma_eq = 0.25;
-    double* C = nullptr;      // [NdPad + NbPad][D]
-    double* feat = nullptr;   // [NdPad + NbPad][CF_STRIDE]
-    double* alpha = nullptr;  // [4 Nd + Nb]
-    TcState tc{};             // tcgen05 route: operand images (rebuilt with every set_alpha)
-    bool has_centres = false, has_alpha = false;
-    long phi() const { return 4L * v.Nd + v.Nb; }
-    long ncpad() const { return (long)v.NdPad + v.NbPad; }
-};
 
 static int gp_alloc(scasml_gp* g) {
     const long nc = g->ncpad();
@@ -124,17 +103,6 @@ int scasml_set_normal_table(const uint16_t* half_bits_host) {
     SC_REQUIRE(dev >= 0 && dev < 64, "device index");
     if (!g_ntab[dev]) SC_CUDA(cudaMalloc(&g_ntab[dev], 32768 * sizeof(__half)));
     SC_CUDA(cudaMemcpy(g_ntab[dev], half_bits_host, 32768 * sizeof(__half), cudaMemcpyHostToDevice));
-    return OK;
-}
-
-int scasml_debug_draw(unsigned stream_id, unsigned domain, unsigned seed, long long start, long long count,
-                      int uniform, double* out_dev, void* stream) {
-    const __half* tab = normal_table_for_current_device();
-    SC_REQUIRE(tab != nullptr, "normal table not set");
-    if (count <= 0) return OK;
-    debug_draw_kernel<<<(unsigned)cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(
-        make_key(stream_id, domain, seed), (unsigned long long)start, count, uniform, tab, out_dev);
-    SC_LAUNCH_CHECK();
     return OK;
 }
 
@@ -175,7 +143,7 @@ int scasml_gp_create(int d, int n_dom, int n_bdy, const int* idx_set5, double ke
 
 int scasml_gp_destroy(scasml_gp* g) {
     if (!g) return OK;
-    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha); cudaFree(g->tc.images); cudaFree(g->tc.ks_scratch);
+    cudaFree(g->C); cudaFree(g->feat); cudaFree(g->alpha); cudaFree(g->tc.images);
     delete g;
     return OK;
 }
@@ -185,7 +153,7 @@ int scasml_gp_clone(const scasml_gp* src, scasml_gp** out) {
     scasml_gp* g = new (std::nothrow) scasml_gp();
     SC_REQUIRE(g != nullptr, "gp_clone: out of host memory");
     g->v = src->v; g->nugget = src->nugget; g->sigma_eq = src->sigma_eq;
-    g->has_centres = src->has_centres; g->has_alpha = src->has_alpha;
+    g->has_centres = src->has_centres; g->has_alpha = src->has_alpha; g->centres_f16 = src->centres_f16;
     g->C = nullptr; g->feat = nullptr; g->alpha = nullptr;
     int rc = gp_alloc(g);
     if (rc != OK) { scasml_gp_destroy(g); return rc; }
@@ -209,6 +177,22 @@ int scasml_gp_set_centres(scasml_gp* g, const double* x_dom_dev, const double* x
         SC_CUDA(cudaMemcpyAsync(g->C + (size_t)g->v.NdPad * D, x_bdy_dev, (size_t)g->v.Nb * D * sizeof(double),
                                 cudaMemcpyDeviceToDevice, st));
     g->has_centres = true; g->has_alpha = false;
+    // The tcgen05 route takes the centres as an EXACT f16 operand (DeepXDE float16 collocation points, the reference's
+    // experiment_run.py:46): verify it instead of assuming it; other centres keep the FP64 route (scasml_gp_tc_supported = 0).
+    g->centres_f16 = true;
+    if (g->tc.images) {
+        int* flag = nullptr;
+        int h = 0;
+        SC_CUDA(cudaMallocAsync((void**)&flag, sizeof(int), st));
+        SC_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        const long n = (long)g->ncpad() * D;
+        centres_f16_check_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(g->C, n, flag);
+        SC_LAUNCH_CHECK();
+        SC_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SC_CUDA(cudaStreamSynchronize(st));
+        SC_CUDA(cudaFreeAsync(flag, st));
+        g->centres_f16 = (h == 0);
+    }
     return build_centre_features(g->v, nullptr, g->feat, st);
 }
 
@@ -221,7 +205,7 @@ int scasml_gp_set_alpha(scasml_gp* g, const double* alpha_dev, void* stream) {
     g->has_alpha = true;
     int rc = build_centre_features(g->v, g->alpha, g->feat, st);
     if (rc != OK) return rc;
-    if (g->tc.images) rc = tc_build_images(g->v, g->tc, st);
+    if (g->tc.images && g->centres_f16) rc = tc_build_images(g->v, g->tc, st);
     return rc;
 }
 
@@ -258,6 +242,7 @@ int scasml_gp_eval(const scasml_gp* g, const double* X_dev, long long R, int mod
                    double* out1_dev, double* out2_dev, double* out3_dev, void* stream) {
     SC_REQUIRE(g != nullptr, "gp_eval: null handle");
     SC_REQUIRE(g->has_alpha, "gp_eval: GP is not fitted (call GPsolver first)");
+    if (route == SCASML_ROUTE_TC) SC_REQUIRE(g->centres_f16, "tcgen05 route needs float16-valued collocation points (use SCASML_ROUTE_F64)");
     if (route == SCASML_ROUTE_TC)
         return launch_eval_tc(g->v, nullptr, X_dev, (long)R, mode, out0_dev, out1_dev, out2_dev, out3_dev, (cudaStream_t)stream);
     SC_REQUIRE(route == SCASML_ROUTE_F64, "gp_eval: unknown route");
@@ -294,6 +279,8 @@ int scasml_uz_solve(const scasml_gp* g, const scasml_picard_params* p, int route
     std::memcpy(&pp, p, sizeof(pp));
     SC_REQUIRE(!pp.scasml || (g && g->has_alpha), "uz_solve: ScaSML needs a fitted GP");
     SC_REQUIRE(!pp.scasml || g->v.d == pp.d, "uz_solve: dimension mismatch between GP and params");
+    SC_REQUIRE(!(pp.scasml && route == SCASML_ROUTE_TC) || (g->tc.images && g->centres_f16),
+               "uz_solve: tcgen05 route unavailable for this GP (d > 1022 or collocation points not float16-valued): use SCASML_ROUTE_F64");
     PicardPlan plan;
     int rc = plan.build(pp, (long)B);
     if (rc != OK) return rc;
@@ -312,66 +299,6 @@ int scasml_clip(double* x_dev, long long count, double c, void* stream) {
     return OK;
 }
 
-int scasml_debug_spd_inverse(double* A_dev, long long n, double* P_dev, void* ws_dev, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const long nblk = cdiv(n, 64);
-    const size_t need = ((size_t)n * n + (size_t)nblk * 64 * 64 + 64 * (size_t)n) * 8 + 1024;
-    SC_REQUIRE(ws_bytes >= need, "debug_spd_inverse: workspace too small");
-    double* X = (double*)ws_dev;
-    double* invd = X + (size_t)n * n;
-    double* tmp = invd + (size_t)nblk * 64 * 64;
-    int* d_fail = (int*)(tmp + 64 * (size_t)n);
-    SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
-    int rc = cholesky_lower(A_dev, (long)n, invd, d_fail, st);
-    if (rc != OK) return rc;
-    rc = tri_inverse_lower(A_dev, (long)n, invd, X, P_dev, st);     // P_dev is written afterwards: scratch until then
-    if (rc != OK) return rc;
-    rc = dgemm((int)n, (int)n, (int)n, 1.0, X, 1, n, X, n, 1, 0.0, P_dev, n, 0, st);
-    if (rc != OK) return rc;
-    int h_fail = 0;
-    SC_CUDA(cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SC_CUDA(cudaStreamSynchronize(st));
-    if (h_fail) { set_error("matrix is not positive definite"); return ERR_NUMERIC; }
-    return OK;
-}
-
-int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* D_dev, int K, int N, unsigned lbo16,
-                         unsigned sbo16, unsigned layout, unsigned kstep_bytes, void* stream) {
-    SC_REQUIRE(A_half_dev && B_half_dev && D_dev, "debug_tc_gemm: null");
-    return tc_selftest(A_half_dev, B_half_dev, D_dev, K, N, lbo16, sbo16, layout, kstep_bytes, (cudaStream_t)stream);
-}
-
-int scasml_debug_tc_timeline(const scasml_gp* g, const double* X_dev, long long R, int mode, int block,
-                             long long* stamps_dev, double* scratch_dev, void* stream) {
-    SC_REQUIRE(g && g->has_alpha && g->tc.images, "debug_tc_timeline: tcgen05 route unavailable");
-    return tc_timeline(g->v, g->tc, X_dev, (long)R, mode, block, stamps_dev, scratch_dev, (cudaStream_t)stream);
-}
-
-int scasml_debug_tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, void* stream) {
-    return tc_mma_bench(N, nchains, ts_mode, iters, cycles_dev, (cudaStream_t)stream);
-}
-
-int scasml_debug_tc_pipe_bench(int mode, int N, int iters, long long* out_dev, void* stream) {
-    return tc_pipe_bench(mode, N, iters, out_dev, (cudaStream_t)stream);
-}
-
-int scasml_gp_tc_supported(const scasml_gp* g) { return (g && g->tc.images) ? 1 : 0; }
-
-int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    int* d_fail = nullptr;
-    SC_CUDA(cudaMalloc(&d_fail, sizeof(int)));
-    SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
-    int rc = lu_solve_inplace(A_dev, (long)n, rhs_dev, d_fail, st);
-    int h_fail = 0;
-    if (rc == OK) {
-        cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-    }
-    cudaFree(d_fail);
-    if (rc != OK) return rc;
-    if (h_fail) { set_error("singular matrix in LU"); return ERR_NUMERIC; }
-    return OK;
-}
+int scasml_gp_tc_supported(const scasml_gp* g) { return (g && g->tc.images && g->centres_f16) ? 1 : 0; }
 
 }  // extern "C"

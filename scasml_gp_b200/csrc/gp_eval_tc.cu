@@ -5,24 +5,28 @@
 // k (x - y), ky (x - roll y), kx (roll x - y), and the Gaussian factorises, kernel_c = K_i K_j exp(a x . perm_c(y_j)).
 // Expanding the polynomial in per-point monomials F[f1] F[f2] with per-centre coefficients C (tests/tc_expansion_ref.py
 // states and checks the algebra against the closed forms of SURVEY App. B) turns the evaluation into
-//     S = (a' x) perm_c(Y)^T          stage 1: distance GEMM, tcgen05.mma kind::f16, SS mode, FP32 accumulators in TMEM
-//     P = 2^6 ex2(S)                  epilogue warps: tcgen05.ld -> ex2 -> f16 hi/lo split -> tcgen05.st, IN PLACE over S
+//     S = (a' x) perm_c(Y)^T          stage 1: distance GEMM, tcgen05.mma kind::f16, TS mode (A = point images in tensor memory),
+//                                     FP32 accumulators in TMEM
+//     P = 2^s ex2(S)                  epilogue warps: tcgen05.ld -> ex2 -> f16 hi/lo split -> tcgen05.st, IN PLACE over S
 //     T += P C_c                      stage 2: coefficient GEMM, A operand = P straight from tensor memory (TS mode)
-//     out_o(x_i) = K_i sum_col F_i[f1] F_i[f2] T[i, col] / scale_col        once per point, FP64
+//     out_o(x_i) = K_i sum_col F_i[f1] F_i[f2] T[i, col] / scale_col        once per point (FP32 products, FP64 sums)
 // so the per-pair work outside the tensor pipe is one TMEM load, one ex2 and three conversion/subtract instructions: both
 // measured per-pair limits of the SM (TMEM read ~16 FP32/clk, MUFU 16 ex2/clk; tools/tc_pipe_bench.py) instead of the
 // 10-45 FP32 instructions per pair of a closed-form epilogue.
-//   * centres are float16-valued (DeepXDE float16 collocation points): the stage-1 B operand is EXACT in f16; sampled
-//     points are split a' x = hi + lo (two f16 terms, 2 MMA passes into the same accumulator);
-//   * the exponent shift 2^6 rides in a spare K column (A = 1, B = 6);
+//   * centres must be float16-valued (DeepXDE float16 collocation points; checked in scasml_gp_set_centres, otherwise the
+//     route is refused): the stage-1 B operand is EXACT in f16; sampled points are split a' x = hi + lo (two f16 terms,
+//     2 MMA passes into the same accumulator);
+//   * the exponent shift s (2^6 by default, lowered per point row when a |x| max|y| would overflow f16) rides in a spare K
+//     column (A = s, B = 1) and is divided out again with K_i;
 //   * P and the column-scaled coefficients are split hi + lo in f16; products hh + hl + lh accumulate into the same FP32
 //     TMEM columns over all centre tiles (relative error ~2e-7 rms, tests/test_tc_expansion.py emulates it);
-//   * one N = 192 (PDE) / N = 128 (u, u + div) MMA per k-step serves all kernel classes: the centre image rows are
+//   * one N = 128 MMA per k-step serves a PAIR of sub-items (centre tile x kernel class): the centre image rows are
 //     [C | rollinv(C) | roll(C)], because roll(x) . y = x . rollinv(y) needs no second A operand;
-//   * warp roles: 16 epilogue warps (thread <-> point row x 16 centres), 1 producer warp (cp.async.bulk rings),
-//     1 MMA warp (converged, one elected lane issues); S/P is double-buffered so stage 1 of tile t+1 and stage 2 of
-//     tile t-1 overlap the epilogue of tile t.
+//   * warp roles (23 warps, NTHREADS_P): 16 epilogue warps in two groups of 8 (one group per S/P slot), 1 producer warp
+//     (cp.async.bulk rings), 2 MMA-issuing warps (distance GEMMs / coefficient GEMMs; converged, one elected lane issues),
+//     4 loader warps (stage the next point tile, contract the previous one).
 // Accuracy: ~2e-7 relative rms on every output; parity with the FP64 route is tested under the "nocast" policy.
+// Timeline stamps and experiment flags exist only in the debug build (-DSCASML_DEBUG_HOOKS, libscasml_b200_dbg.so).
 #include <cmath>
 #include <cstring>
 #include "picard.cuh"
@@ -37,7 +41,11 @@ constexpr int TM = 128;              // points per CTA (UMMA M)
 constexpr int TN = 64;               // centres per tile
 constexpr int A_BLK = TM * 128;      // bytes of one [128 x 64] f16 block
 constexpr int NEPI = 16;             // epilogue warps
-constexpr int NTHREADS = (NEPI + 2) * 32;   // + producer warp + MMA warp
+#ifdef SCASML_DEBUG_HOOKS
+constexpr bool DBG = true;           // clock64 stamps + run-time experiment flags (tools/tc_timeline.py)
+#else
+constexpr bool DBG = false;          // product build: every dbg branch below folds away
+#endif
 
 // slim device view of TcState
 struct TcDev {
@@ -46,6 +54,7 @@ struct TcDev {
     const TcColDesc* desc;           // column table of this evaluation class
     size_t b1_tile_bytes, b3_tile_bytes;
     int nstep, ntile_dom, ntile_bdy;
+    const double* ymax2;             // device scalar: max_j |y_j|^2 over the centres (per-row exponent shift, row_shift())
     const LevelDev* gen;             // non-null: the loader warps GENERATE the points (fused sampler) instead of reading X
     long long gen_off;               // index of the launch's first point in the level's point buffer
     long long* dbg;
@@ -129,7 +138,7 @@ __device__ __forceinline__ uint32_t sw_off(int r, int c) {
 }
 
 // pass 2a: stage-1 centre images.  Per tile, per K block: rows [C (64) | rollinv(C) (64) | roll(C) (64)], f16, 128 B swizzle.
-// Column D carries the exponent shift (TC_P_SHIFT in every row); columns > D are zero.
+// Column D is 1 in every row: the A operand carries the exponent shift of its point row there (row_shift()); columns > D are zero.
 __global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile_bytes, int KB) {
     const int tile = blockIdx.x;
     uint8_t* base = b1 + (size_t)tile * tile_bytes;
@@ -143,7 +152,7 @@ __global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile
             v1 = y[(c == 0) ? D - 1 : c - 1];            // roll(x) . y = x . rollinv(y),  rollinv(y)_c = y_{c-1}
             v2 = y[(c + 1 == D) ? 0 : c + 1];            // roll(y)_c = y_{c+1}            (models/GP.py:91-93)
         } else if (c == D) {
-            v0 = v1 = v2 = (double)TC_P_SHIFT;
+            v0 = v1 = v2 = 1.0;
         }
         uint8_t* blk = base + (size_t)(c / KBLK) * (3 * TN * 128);
         *(__half*)(blk + sw_off(r, c % KBLK)) = __double2half(v0);
@@ -187,6 +196,25 @@ __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, i
             desc[col] = dsc;
         }
     }
+}
+
+// Exponent shift of a point row: P = 2^s exp(a x.y) must stay below the f16 maximum (2^16) for every centre, and
+// |a x.y| log2(e) <= a log2(e) |x| max|y| (Cauchy-Schwarz).  s = TC_P_SHIFT inside the collocation box (a x.y <= 4 + 4/d);
+// points that left it far enough -- small d, long Brownian excursions, user test points outside the box -- get a smaller,
+// still integer (exact in f16) shift instead of saturated P values.  The final contraction multiplies 2^(TC_P_SHIFT - s) back.
+__device__ __forceinline__ int row_shift(double a, double nx, double ymax2) {
+    const double smax = a * 1.4426950408889634 * sqrt(nx * ymax2);
+    if (!(smax > 15.9 - (double)TC_P_SHIFT)) return TC_P_SHIFT;      // also NaN rows (they poison only themselves)
+    const double s = floor(15.9 - smax);
+    return s < -14.0 ? -14 : (int)s;
+}
+
+// max_j |y_j|^2 over all (padded) centres -> one device double (bit pattern of a non-negative double orders like an integer)
+__global__ void ymax_kernel(GpView gp, int ncentres, unsigned long long* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncentres) return;
+    const double ny = gp.feat[(size_t)j * CF_STRIDE + CF_NY];
+    if (ny > 0.0 && ny < 1e300) atomicMax(out, (unsigned long long)__double_as_longlong(ny));
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
@@ -393,8 +421,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     const int D = gp.D, d = gp.d;
     const long ntiles = (R + TM - 1) / TM;
     const int nit = (int)((ntiles - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x);   // point tiles of this CTA
-    long long* const dbg = (st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;   // stamps: first tile of that CTA
-#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
+    long long* const dbg = (DBG && st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;   // stamps: first tile of that CTA
+    const int dflags = DBG ? st.dbg_flags : 0;                        // experiment switches (debug build only)
+#define TC_STAMP(slot) do { if (DBG && dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
     const uint32_t bar0 = smem_u32(bars);
     auto b1_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -452,7 +481,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         // ===== producer: per item, the class's centre rows (all K blocks) and its coefficient images.  The item stream
         // simply repeats for every point tile, so the rings run across tile boundaries.  A centre-row slot is reusable once
         // s_full of its previous item fired (stage 1 done), a coefficient slot once the MMA warp committed b3_empty. =====
-        if (lane == 0 && !(st.dbg_flags & 8)) {
+        if (lane == 0 && !(dflags & 8)) {
             const int ptotal = nit * npair;
             int t1 = 0, k1 = TK_K, j1 = 0, t3 = 0, k3 = TK_K, j3 = 0;    // sub-item cursors / pair index inside the point tile
             int p1 = 0;
@@ -504,7 +533,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const uint64_t b1desc0 = make_desc(smem_u32(sB1), 1, 64, 2);
         const uint32_t idS2 = make_idesc(TM, 2 * TN), idS1 = make_idesc(TM, TN);
         const uint32_t aBase = tmem_base + COL_A;
-        const bool nocopy = (st.dbg_flags & 8) != 0;
+        const bool nocopy = (dflags & 8) != 0;
         int p1 = 0;                                                  // global pair counter
         bool rdy1 = false;                                           // early probe result for the next batch's centre rows
         for (int it = 0; it < nit; ++it) {
@@ -520,7 +549,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 // the slot's previous P has been consumed: stage 2 of pair p1 - NSLOT (issued by the other warp) has COMPLETED (handing the
                 // slot back as soon as those MMAs are issued -- tcgen05.mma executes in issue order -- measured no faster)
                 // (suspending wait: with two epilogue groups the issue slots a spinning warp takes cost more than its faster wake-up gains; flag 64 = spin)
-                if (p1 >= NSLOT) { if (st.dbg_flags & 64) mbar_spin(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); else mbar_wait(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); tc_fence_after(); }
+                if (p1 >= NSLOT) { if (dflags & 64) mbar_spin(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); else mbar_wait(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); tc_fence_after(); }
                 if (!rdy1 && !nocopy) mbar_wait(b1_full(s1), (uint32_t)(p1 / NB1) & 1u);   // bulk-copy bytes landed (async proxy)
                 const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
                 ++p1;
@@ -553,7 +582,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const uint32_t el = elect_one();
         const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
         const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
-        const bool nocopy = (st.dbg_flags & 8) != 0;
+        const bool nocopy = (dflags & 8) != 0;
         int p2 = 0;
         for (int it = 0; it < nit; ++it) {
             const bool stamp = (it == 1);
@@ -565,7 +594,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
                     uint32_t spins = 0;
                     bool a = false, b = nocopy;
-                    if (!(st.dbg_flags & 64)) { mbar_wait(p_ready(s), par); if (!b) mbar_wait(b3_full(s), par); a = b = true; }   // suspending waits (flag 64: poll both barriers in a spin loop)
+                    if (!(dflags & 64)) { mbar_wait(p_ready(s), par); if (!b) mbar_wait(b3_full(s), par); a = b = true; }   // suspending waits (flag 64: poll both barriers in a spin loop)
                     while (!(a && b)) {
                         if (!a) a = mbar_test_wait(p_ready(s), par);
                         if (!b) b = mbar_test_wait(b3_full(s), par);
@@ -587,8 +616,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
                     const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
                     const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
-                    if (el && !(st.dbg_flags & 1)) {
-                        const bool only_hh = (st.dbg_flags & 32) != 0;   // timeline experiment: 4 instead of 12 MMAs (wrong results)
+                    if (el && !(dflags & 1)) {
+                        const bool only_hh = (dflags & 32) != 0;   // timeline experiment: 4 instead of 12 MMAs (wrong results)
                         if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
                         if (!only_hh) {
                             umma_ts<true>(tacc, pbase, clo0, idesc);
@@ -623,6 +652,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const double ascale = gp.a * 1.4426950408889634;             // a log2(e): S = log2 of exp(a x.y)
         const int hl = lane & 15, sub = lane >> 4;
         const int c0 = hl * 8;
+        const double ymax2 = __ldg(st.ymax2);
         const bool active = c0 < NSTEP * 16;
         constexpr int RPW = TM / NLOAD;                              // rows per loader warp
         static_assert(RPW == 32, "a loader warp owns one tensor-memory lane quadrant");
@@ -669,7 +699,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                             const double val = v[i][e + q];
                             nx = fma(val, val, nx);
                             if (c < d) sx += val;
-                            sv[q] = (c == D) ? 1.0f : (float)(ascale * val);   // column D: exponent shift (B holds TC_P_SHIFT)
+                            sv[q] = (c == D) ? (float)TC_P_SHIFT : (float)(ascale * val);   // column D: exponent shift (B holds 1), patched below for far-out rows
                         }
                         // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
                         const __half2 h = __floats2half2_rn(sv[0], sv[1]);
@@ -686,11 +716,14 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #pragma unroll
                     for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
                     if (hl == 0) { Ki[r] = nx; sxs[r] = sx; }
+                    const int sh = row_shift(gp.a, nx, ymax2);
+                    if (sh != TC_P_SHIFT && hl == (D >> 3))           // rare: the lane that staged column D overwrites its entry
+                        *(__half*)(sStage + (size_t)r * A_PITCH + (size_t)D * 2) = __int2half_rn(sh);
                 }
             }
             if (GEN) __threadfence_block();                         // generated rows (global) are re-read by this warp's contraction
             __syncwarp();
-            ki_new = exp(-0.5 * gp.a * Ki[rq]); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
+            ki_new = ldexp(exp(-0.5 * gp.a * Ki[rq]), TC_P_SHIFT - row_shift(gp.a, Ki[rq], ymax2)); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
                                                                      // (one FP64 exp per lane instead of one per row pass)
             __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
@@ -812,7 +845,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
         const int r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const bool skip_math = (st.dbg_flags & 2) != 0;
+        const bool skip_math = (dflags & 2) != 0;
         long g = 0;                                                  // global item counter
         for (int it = 0; it < nit; ++it) {
             if (it < nit) {
@@ -851,7 +884,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const int s = (int)(g % NSLOT);
                     if (s != grp) continue;
                     const bool two = 2 * j + 1 < nitem;
-                    if (st.dbg_flags & 16) mbar_spin(s_full(s), (uint32_t)(g / NSLOT) & 1u); else mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
+                    if (dflags & 16) mbar_spin(s_full(s), (uint32_t)(g / NSLOT) & 1u); else mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
                     tc_fence_after();
                     if ((tid & 255) == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
                     const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + chalf;
@@ -939,7 +972,7 @@ constexpr uint32_t KS_STAGE_BYTES = 2 * A_BLK + 2 * B1_BLK;          // A hi | A
 constexpr int KS_NBAR = 2 * KS_STAGES + 4 * NSLOT + 2;               // full empty | b3_full b3_empty s_full p_ready | t_full t_free
 constexpr int KS_THREADS = (NEPI + 2) * 32;
 
-__global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* __restrict__ X, long R, int KB,
+__global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* __restrict__ X, long R, int KB, const double* __restrict__ ymax2p,
                                                        uint8_t* __restrict__ img, double* __restrict__ Ki, double* __restrict__ sxs) {
     const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = gp.D, d = gp.d;
@@ -962,7 +995,7 @@ __global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* 
                     const double val = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
                     nx = fma(val, val, nx);
                     if (c < d) sx += val;
-                    sv[q] = (c == D) ? 1.0f : (float)(ascale * val);
+                    sv[q] = (c == D) ? (float)TC_P_SHIFT : (float)(ascale * val);
                 }
                 const __half2 h = __floats2half2_rn(sv[0], sv[1]);
                 const float2 hf = __half22float2(h);
@@ -978,7 +1011,12 @@ __global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* 
             }
         }
         for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
-        if (hl == 0) { Ki[(size_t)tile * TM + r] = exp(-0.5 * gp.a * nx); sxs[(size_t)tile * TM + r] = sx; }
+        const int sh = row_shift(gp.a, nx, __ldg(ymax2p));
+        if (sh != TC_P_SHIFT && hl == ((D % 128) >> 3)) {              // the lane that wrote column D patches it (its own earlier store)
+            const int cD = D % KBLK;
+            *(__half*)(base + (size_t)(D / KBLK) * 2 * A_BLK + (uint32_t)r * 128u + (uint32_t)(((((cD) >> 3) ^ (r & 7)) & 7) << 4) + (uint32_t)(cD & 7) * 2u) = __int2half_rn(sh);
+        }
+        if (hl == 0) { Ki[(size_t)tile * TM + r] = ldexp(exp(-0.5 * gp.a * nx), TC_P_SHIFT - sh); sxs[(size_t)tile * TM + r] = sx; }
     }
 }
 
@@ -1401,6 +1439,7 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
     }
     for (int cls = 0; cls < 3; ++cls) st->desc_off[cls] = take(TC_MAXCOL * sizeof(TcColDesc));
     st->spec_off = take(3 * TC_MAXCOL * sizeof(TcColSpec));
+    st->ymax_off = take(sizeof(double));
     st->scratch_off = take(3 * ncentres * TC_MAXCOL * sizeof(double) + 3 * TC_MAXCOL * sizeof(unsigned long long));
     st->total_bytes = off;
     return off;
@@ -1418,6 +1457,9 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
     SC_CUDA(cudaMemsetAsync(colmax, 0, 3 * TC_MAXCOL * sizeof(unsigned long long), stream));
     tc::coef_kernel<<<dim3(ncentres, 3), TC_MAXCOL, 0, stream>>>(gp, spec_dev, ncentres, coef, colmax);
     SC_LAUNCH_CHECK();
+    SC_CUDA(cudaMemsetAsync(st.images + st.ymax_off, 0, sizeof(double), stream));
+    tc::ymax_kernel<<<(unsigned)cdiv(ncentres, 256), 256, 0, stream>>>(gp, ncentres, (unsigned long long*)(st.images + st.ymax_off));
+    SC_LAUNCH_CHECK();
     tc::b1_image_kernel<<<ntile, 256, 0, stream>>>(gp, st.images + st.b1_off, st.b1_tile_bytes, st.KB);
     SC_LAUNCH_CHECK();
     for (int cls = 0; cls < 3; ++cls) {
@@ -1431,7 +1473,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
 
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const LevelDev* gen_level_dev, long long gen_off) {
+                   const LevelDev* gen_level_dev, long long gen_off, const TcDebug* dbg) {
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
@@ -1447,38 +1489,37 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.b1_tile_bytes = st->b1_tile_bytes;
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
+    dv.ymax2 = (const double*)(st->images + st->ymax_off);
     dv.gen = gen_level_dev; dv.gen_off = gen_off;
-    dv.dbg = st->dbg; dv.dbg_block = st->dbg_block & 0xFFFFFF; dv.dbg_flags = st->dbg ? (st->dbg_block >> 24) : 0;
+    dv.dbg = dbg ? dbg->stamps : nullptr; dv.dbg_block = dbg ? (dbg->block & 0xFFFFFF) : 0; dv.dbg_flags = dbg ? (dbg->block >> 24) : 0;
     if (st->nstep > 8) {
-        // K-streamed kernel: point images in a scratch buffer owned by the handle's TcState (grown on demand), processed in chunks
+        // K-streamed kernel: point images in a stream-ordered scratch buffer of this call (cudaMallocAsync: concurrent evaluations of
+        // one handle on different streams never share it), processed in chunks
         SC_REQUIRE(gen_level_dev == nullptr, "the fused sampler is not available on the K-streamed kernel");
-        TcState* mst = const_cast<TcState*>(st);
         const int KB = (st->nstep + 3) / 4;
         const long chunk_pts = 148L * tc::TM * 4;                     // four point tiles per SM per launch
         const size_t per_tile = (size_t)KB * 2 * tc::A_BLK + 2 * tc::TM * sizeof(double);
         const size_t need = (size_t)cdiv(R < chunk_pts ? R : chunk_pts, tc::TM) * per_tile;
-        if (mst->ks_scratch_bytes < need) {
-            if (mst->ks_scratch) { SC_CUDA(cudaStreamSynchronize(stream)); SC_CUDA(cudaFree(mst->ks_scratch)); mst->ks_scratch = nullptr; mst->ks_scratch_bytes = 0; }
-            SC_CUDA(cudaMalloc(&mst->ks_scratch, need));
-            mst->ks_scratch_bytes = need;
-        }
+        uint8_t* scratch = nullptr;
+        SC_CUDA(cudaMallocAsync((void**)&scratch, need, stream));
+        int rcode = OK;
         for (long r0 = 0; r0 < R; r0 += chunk_pts) {
             const long rc = (R - r0 < chunk_pts) ? (R - r0) : chunk_pts;
             const long nt = cdiv(rc, tc::TM);
-            uint8_t* img = mst->ks_scratch;
+            uint8_t* img = scratch;
             double* Ki = (double*)(img + (size_t)nt * KB * 2 * tc::A_BLK);
             double* sx = Ki + nt * tc::TM;
             const double* Xc = X + r0 * (long)gp.D;
-            tc::ks_image_kernel<<<(unsigned)nt, 256, 0, stream>>>(gp, Xc, rc, KB, img, Ki, sx);
-            SC_LAUNCH_CHECK();
+            tc::ks_image_kernel<<<(unsigned)nt, 256, 0, stream>>>(gp, Xc, rc, KB, dv.ymax2, img, Ki, sx);
+            if (cudaGetLastError() != cudaSuccess) { rcode = ERR_CUDA; set_error("ks_image_kernel launch failed"); break; }
             double* p0 = out0 + r0; double* p1 = out1 ? out1 + r0 : nullptr; double* p2 = out2 ? out2 + r0 : nullptr; double* p3 = out3 ? out3 + r0 : nullptr;
-            int rcode;
             if (cls == TC_U) rcode = tc::launch_ks<TC_U>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
             else if (cls == TC_UG) rcode = tc::launch_ks<TC_UG>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
             else rcode = tc::launch_ks<TC_PDE>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
-            if (rcode != OK) return rcode;
+            if (rcode != OK) break;
         }
-        return OK;
+        cudaFreeAsync(scratch, stream);
+        return rcode;
     }
 #define SC_TC_DISPATCH(NS)                                                                                                  \
     do {                                                                                                                    \
@@ -1499,15 +1540,16 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
 #undef SC_TC_DISPATCH
 }
 
+#ifdef SCASML_DEBUG_HOOKS
 // timeline of one CTA: stamps[0] entry, [1] A images built, [2] prologue done, [3] exit,
 // tile t: [4+4t] stage-1 issue start, [5+4t] stage-2 issue end, [6+4t] epilogue start, [7+4t] epilogue end   (SM clock cycles)
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream) {
-    static TcState dbgst;                          // TcState is large: keep the debug copy off the stack
-    dbgst = st;
-    dbgst.dbg = stamps_dev;
-    dbgst.dbg_block = block;
-    return launch_eval_tc(gp, &dbgst, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream);
+    TcDebug dbg;
+    dbg.stamps = stamps_dev;
+    dbg.block = block;
+    return launch_eval_tc(gp, &st, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream, nullptr, 0, &dbg);
 }
+#endif
 
 }  // namespace scasml

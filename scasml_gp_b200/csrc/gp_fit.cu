@@ -834,6 +834,18 @@ int gp_fit_device(const GpView& gp, const double* g_bdy, const double* sol0, int
     int h_fail = 0;
     SC_CUDA(cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
     SC_CUDA(cudaStreamSynchronize(st));
+    if (h_fail && f16_entries) {
+        // The float16 rounding of the Gram entries (models/GP.py:258) is a symmetric perturbation of spectral norm ~1e-2 at phi = 4 200 --
+        // the size of the nugget -- so a near-singular Gram can turn indefinite.  The reference never sees that: its factor comes from the
+        // SVD (|K| + nugget I, always positive definite, models/GP.py:260-268).  Retry once with the un-rounded entries (K itself is PSD).
+        SC_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+        rc = gram_assemble(gp, K, nugget, 0, st);
+        if (rc != OK) return rc;
+        rc = cholesky_lower(K, phi, invd, d_fail, st);
+        if (rc != OK) return rc;
+        SC_CUDA(cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SC_CUDA(cudaStreamSynchronize(st));
+    }
     if (h_fail) {   // mirrors the ValueError of models/GP.py:264-265
         set_error("Cholesky decomposition of K + nugget*I failed (non-positive pivot / NaN)");
         return ERR_NUMERIC;

@@ -41,12 +41,13 @@ struct TcState {
     size_t b3_off[3] = {}, b3_tile_bytes[3] = {};    // per tile: [k hi | k lo | ky hi | ky lo | kx hi | kx lo], ncol x 128 B each
     size_t desc_off[3] = {};                         // TcColDesc[TC_MAXCOL] per evaluation class
     size_t spec_off = 0;                             // TcColSpec[3][TC_MAXCOL]
+    size_t ymax_off = 0;                             // one double: max_j |y_j|^2 (per-row exponent shift)
     size_t scratch_off = 0;                          // double [3][ncentres][TC_MAXCOL] + column maxima
     TcColSpec spec[3][TC_MAXCOL];                    // host copy
-    uint8_t* ks_scratch = nullptr;   // K-streamed kernel (d + 2 > 128): point images of the chunk being evaluated (grown on demand)
-    size_t ks_scratch_bytes = 0;
-    long long* dbg = nullptr;        // optional timeline buffer (clock64 stamps of CTA dbg_block), see scasml_debug_tc_timeline
-    int dbg_block = 0;
+};
+struct TcDebug {                     // debug build only: clock64 stamps of CTA (block & 0xFFFFFF), experiment flags in block >> 24
+    long long* stamps = nullptr;
+    int block = 0;
 };
 
 int tc_supported(const GpView& gp);
@@ -57,7 +58,7 @@ struct LevelDev;
 // (device copy of its LevelDev) into X instead of reading them
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const LevelDev* gen_level_dev = nullptr, long long gen_off = 0);
+                   const LevelDev* gen_level_dev = nullptr, long long gen_off = 0, const TcDebug* dbg = nullptr);
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);

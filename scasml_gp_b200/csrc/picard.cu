@@ -9,7 +9,6 @@
 //   reduction        : per-point weights (point_weights_kernel), then warp-per-row Monte-Carlo means, clip (reduce_rows_kernel)
 // Levels are sampled top-down (children's rows are the parents' sample points) and reduced bottom-up.
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 #include "picard.cuh"
 #include "gp_tc.cuh"
@@ -754,14 +753,16 @@ __global__ void __launch_bounds__(128, MINB) reduce_rows_kernel(const __grid_con
 
 template <int JCH>
 int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
-    point_weights_kernel<<<(unsigned)cdiv(lv.npoints, 256), 256, 0, stream>>>(lv);
-    SC_LAUNCH_CHECK();
+    // a sharded rank may own no sample unit of a level (world > units): no points, and below the top level no rows either
+    if (lv.npoints > 0) {
+        point_weights_kernel<<<(unsigned)cdiv(lv.npoints, 256), 256, 0, stream>>>(lv);
+        SC_LAUNCH_CHECK();
+    }
+    if (lv.NR == 0) return OK;
     const long long threads = lv.NR * 32;
-    static const int variant = getenv("SCASML_REDUCE_VARIANT") ? atoi(getenv("SCASML_REDUCE_VARIANT")) : 1;   // experiment switch (measured at C3: 2.9 / 2.6 / 2.8 ms for 0 / 1 / 2)
-    // UNR = point rows in flight per lane, MINB = resident CTAs per SM the register budget is cut for
-    if (variant == 1) reduce_rows_kernel<JCH, 2, 8><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
-    else if (variant == 2) reduce_rows_kernel<JCH, 2, 6><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
-    else reduce_rows_kernel<JCH, 4, 5><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
+    // UNR = 2 point rows in flight per lane, register budget cut for 8 resident CTAs per SM (measured at C3 against
+    // <4, 5> and <2, 6>: 2.6 ms vs 2.9 / 2.8 ms, profiles/r1_sampler_reduce.md)
+    reduce_rows_kernel<JCH, 2, 8><<<(unsigned)cdiv(threads, 128), 128, 0, stream>>>(lv);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -931,8 +932,10 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         const LevelDev& lv = lvs[L];
         const LevelRec& lr = levels_[L];
         begin_span(0);
-        row_setup_kernel<<<(unsigned)cdiv(lv.NR, 256), 256, 0, stream>>>(lv);
-        SC_LAUNCH_CHECK(); ++launches;
+        if (lv.NR > 0) {                                 // a sharded rank may own nothing below the top level
+            row_setup_kernel<<<(unsigned)cdiv(lv.NR, 256), 256, 0, stream>>>(lv);
+            SC_LAUNCH_CHECK(); ++launches;
+        }
         if (!fused && lv.NT > 0) {
             int nwarp, cpts; size_t smem; unsigned grid;
             sampler_shape(0, lv.NT, &nwarp, &smem, &grid, &cpts);
@@ -984,7 +987,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         else rc = launch_reduce<8>(lv, stream);
         if (rc != OK) return rc;
         end_span();
-        launches += 2;
+        launches += (lv.npoints > 0 ? 1 : 0) + (lv.NR > 0 ? 1 : 0);
     }
     stats_.eval_time_ns = stats_.sample_time_ns = stats_.reduce_time_ns = 0;
     if (timing) {

@@ -89,7 +89,8 @@ class PicardSolverBase(object):
     fused_sampler = False       # tcgen05 route: True = the evaluation kernel's loader warps draw the Brownian increments themselves
                                 # (bit-identical; measured slower at C3: 55 ms vs 29 ms per step, the four loader warps cannot
                                 # sustain the Philox + inverse-CDF gather work)
-    route = None                # None: tcgen05 route for the sampled points when the GP supports it (d <= 126), else FP64
+    route = None                # None: tcgen05 route for the sampled points when the GP supports it (d <= 1022 and float16-valued
+                                # collocation points: resident-operand kernel up to d = 126, K-streamed kernel above), else FP64
     quadrature = "reference"    # "reference" (bug-compatible lgwt) or "gauss_legendre" (flagged deviation)
     cast_levels = False         # round inner uz_solve returns to float16 like solvers/ScaSML.py:284
     seed = 0
@@ -192,11 +193,12 @@ class PicardSolverBase(object):
         out = torch.empty((B, D), dtype=torch.float64, device="cuda")
         p = self._params(n, rho, M, rank, world)
         # batch over test points so the level buffers fit the workspace budget
+        # (sharded runs too: every rank sees the same B and budget, so all ranks cut the same chunks; a chunk is a complete
+        # sharded solve of its rows -- unit ownership is defined inside the chunk, the RNG is addressed by global row ids --
+        # and the partial sums of all chunks go through ONE all-reduce at the end)
         ws1, st1 = self.plan(n, rho, 1, M, 0, 1)
-        per_row = max(ws1, 1)
+        per_row = max(ws1 // max(world, 1), 1)
         chunk = int(max(1, min(B, self.workspace_budget_bytes // per_row)))
-        if world > 1:
-            chunk = B                      # sharded runs keep one batch (unit ownership is defined on the whole batch)
         stats = _lib.PicardStats()
         agg = None
         ws_t = None
@@ -233,7 +235,7 @@ class PicardSolverBase(object):
     def _uz(self, n, rho, x_t, M=None):
         x_dev = _lib.to_device(x_t)
         out = self._uz_device(n, rho, x_dev, M)
-        raw = out.cpu().numpy()
+        raw = _lib.to_host(out)
         self.last_raw = raw
         return raw
 
@@ -241,13 +243,13 @@ class PicardSolverBase(object):
         x_dev = _lib.to_device(x_t)                               # one host -> device copy serves the correction and u_hat
         out = self._uz_device(n, rho, x_dev, M)
         if not self.scasml:
-            raw = out.cpu().numpy()
+            raw = _lib.to_host(out)
             self.last_raw = raw
             self.last_raw_u = raw[:, :1]
             return raw[:, 0][:, np.newaxis].astype(np.float16)
         torch = _lib.torch_cuda()
         (uh,) = self.GP._eval(x_dev, _lib.EVAL_U)                 # top-level u_hat(x): GP.route (FP64 by default)
-        both = torch.cat((out, uh[:, None]), dim=1).cpu().numpy()  # one device -> host copy
+        both = _lib.to_host(torch.cat((out, uh[:, None]), dim=1))  # one device -> host copy (pinned staging)
         raw, u_hat_raw = both[:, :-1], both[:, -1:]
         self.last_raw = raw
         u_breve = raw[:, 0][:, np.newaxis].astype(np.float16)

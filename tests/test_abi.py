@@ -27,6 +27,22 @@ def test_header_symbols_are_exported(lib):
         assert hasattr(cdll, n), n
     assert set(names) == set(lib._SIGNATURES), set(names) ^ set(lib._SIGNATURES)
     assert lib.load().scasml_abi_version() == 1
+    # the product library exports nothing else: test hooks and micro-benchmarks live in the debug build only
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert exported == set(names), exported ^ set(names)
+
+
+def test_debug_header_symbols_are_exported_by_the_debug_build_only(lib):
+    hdr = open(os.path.join(ROOT, "include", "scasml_b200_debug.h")).read()
+    names = re.findall(r"SCASML_API\s+[\w\s\*]+?\b(scasml_\w+)\s*\(", hdr)
+    assert set(names) == set(lib._DEBUG_SIGNATURES), set(names) ^ set(lib._DEBUG_SIGNATURES)
+    dbg = C.CDLL(lib.LIB_DBG_PATH)
+    prod = C.CDLL(lib.LIB_PATH)
+    for n in names:
+        assert hasattr(dbg, n), n
+        assert not hasattr(prod, n), n
 
 
 def test_struct_layout_matches_header(lib):

@@ -75,12 +75,12 @@ def mid():
 def test_sampler_bit_exact():
     P = _product()
     torch, lib = P["torch"], P["lib"]
-    lib.ensure_normal_table()
+    lib.ensure_normal_table(debug=True)                 # the draw hook lives in the debug build of the library (same sampler code)
     assert np.array_equal(lib.normal_half_table().view(np.uint16), orng.normal_half_table().view(np.uint16))
     for (stream, domain, seed, start, count) in [(0, 0, 0, 0, 4099), (17, 1, 0, 123457, 3001), (3, 1, 9, 2**33 + 5, 1000)]:
         out = torch.empty(count, dtype=torch.float64, device="cuda")
         for uniform in (0, 1):
-            lib.check(lib.load().scasml_debug_draw(stream, domain, seed, start, count, uniform, lib.ptr(out), lib.stream_ptr()))
+            lib.check(lib.load_debug().scasml_debug_draw(stream, domain, seed, start, count, uniform, lib.ptr(out), lib.stream_ptr()))
             key = orng.make_key(stream, domain, seed)
             want = orng.uniforms(key, start, count) if uniform else orng.normals(key, start, count)
             assert np.array_equal(out.cpu().numpy(), want)
@@ -122,13 +122,13 @@ def test_dense_pieces(small):
         Sd = torch.from_numpy(S.copy()).cuda()
         Pd = torch.empty((n, n), dtype=torch.float64, device="cuda")
         ws = torch.empty((n * n + 64 * 64 * ((n + 63) // 64) + 64 * n) * 8 + 4096, dtype=torch.uint8, device="cuda")
-        lib.check(lib.load().scasml_debug_spd_inverse(lib.ptr(Sd), n, lib.ptr(Pd), lib.ptr(ws), ws.numel(), lib.stream_ptr()))
+        lib.check(lib.load_debug().scasml_debug_spd_inverse(lib.ptr(Sd), n, lib.ptr(Pd), lib.ptr(ws), ws.numel(), lib.stream_ptr()))
         np.testing.assert_allclose(Pd.cpu().numpy(), np.linalg.inv(S), rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(np.tril(Sd.cpu().numpy()), np.linalg.cholesky(S), rtol=1e-10, atol=1e-12)
         H = rng.standard_normal((n, n)) + 0.1 * np.eye(n)                    # indefinite, needs pivoting
         b = rng.standard_normal(n)
         Hd, bd = torch.from_numpy(H.copy()).cuda(), torch.from_numpy(b.copy()).cuda()
-        lib.check(lib.load().scasml_debug_lu_solve(lib.ptr(Hd), n, lib.ptr(bd), lib.stream_ptr()))
+        lib.check(lib.load_debug().scasml_debug_lu_solve(lib.ptr(Hd), n, lib.ptr(bd), lib.stream_ptr()))
         want = np.linalg.solve(H, b)
         np.testing.assert_allclose(bd.cpu().numpy(), want, rtol=1e-7, atol=1e-9 * np.abs(want).max())
 

@@ -16,7 +16,7 @@ def _tc_gemm(lib, torch, A, B, lbo=1, sbo=64, layout=2, kstep=32):
     Ad = torch.from_numpy(A).cuda()
     Bd = torch.from_numpy(B).cuda()
     Dd = torch.full((128, N), float("nan"), dtype=torch.float32, device="cuda")
-    lib.check(lib.load().scasml_debug_tc_gemm(lib.ptr(Ad), lib.ptr(Bd), lib.ptr(Dd), K, N, lbo, sbo, layout, kstep, lib.stream_ptr()))
+    lib.check(lib.load_debug().scasml_debug_tc_gemm(lib.ptr(Ad), lib.ptr(Bd), lib.ptr(Dd), K, N, lbo, sbo, layout, kstep, lib.stream_ptr()))
     torch.cuda.synchronize()
     return Dd.cpu().numpy()
 

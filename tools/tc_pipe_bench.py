@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from scasml_gp_b200 import _lib as lib
-L = lib.load()
+L = lib.load_debug()
 out = torch.zeros(8, dtype=torch.int64, device="cuda")
 iters = 448 * 2
 

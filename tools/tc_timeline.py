@@ -16,7 +16,7 @@ gp._bind(dom, bdy)
 gp.set_right_vector(np.random.default_rng(0).standard_normal(4 * nd + nb) * 0.1)
 xd = _lib.to_device(X)
 R = xd.shape[0]
-lib = _lib.load()
+lib = _lib.load_debug()          # stamps / experiment flags exist only in the debug build
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0     # 1 skip stage-2 MMAs, 2 skip epilogue arithmetic, 4 skip low-half pass
 for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PDE")):
     stamps = torch.zeros(256, dtype=torch.int64, device="cuda")

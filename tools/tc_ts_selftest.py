@@ -8,7 +8,7 @@ for (K, N) in [(64, 64), (128, 64), (128, 32)]:
     want = A.astype(np.float64) @ B.astype(np.float64).T
     Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     Dd = torch.full((128, N), float("nan"), dtype=torch.float32, device="cuda")
-    lib.check(lib.load().scasml_debug_tc_gemm(lib.ptr(Ad), lib.ptr(Bd), lib.ptr(Dd), K, N, 1, 64, 100, 32, lib.stream_ptr()))
+    lib.check(lib.load_debug().scasml_debug_tc_gemm(lib.ptr(Ad), lib.ptr(Bd), lib.ptr(Dd), K, N, 1, 64, 100, 32, lib.stream_ptr()))
     torch.cuda.synchronize()
     got = Dd.cpu().numpy()
     print("TS", K, N, "max err", float(np.nanmax(np.abs(got - want))), "nan", int(np.isnan(got).sum()))
