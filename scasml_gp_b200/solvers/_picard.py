@@ -177,8 +177,10 @@ class PicardSolverBase(object):
             return 0, 1, None
         return dist.get_rank(), dist.get_world_size(), dist
 
-    def _uz_device(self, n, rho, x_dev, M=None):
-        """x_dev: [B, d+1] float64 CUDA tensor -> [B, 1+d] float64 CUDA tensor (clipped, un-rounded)."""
+    def _uz_device(self, n, rho, x_dev, M=None, with_u_hat=False):
+        """x_dev: [B, d+1] float64 CUDA tensor -> [B, 1+d] float64 CUDA tensor (clipped, un-rounded).
+        with_u_hat: also return the top-level u_hat(x) [B] (GP.route); in sharded runs every rank evaluates only the rows
+        r = rank (mod world) and the values travel in the same all-reduce as the partial sums."""
         lib = _lib.load()
         torch = _lib.torch_cuda()
         _lib.ensure_normal_table()
@@ -190,7 +192,9 @@ class PicardSolverBase(object):
         route = self.route
         if route is None:     # the top-level u_hat(x) of u_solve always goes through GP.predict (GP.route, FP64 by default)
             route = _lib.ROUTE_TC if (self.scasml and lib.scasml_gp_tc_supported(gp_handle) == 1) else _lib.ROUTE_F64
-        out = torch.empty((B, D), dtype=torch.float64, device="cuda")
+        buf = torch.empty(B * D + (B if with_u_hat else 0), dtype=torch.float64, device="cuda")
+        out = buf[:B * D].view(B, D)
+        uh = buf[B * D:] if with_u_hat else None
         p = self._params(n, rho, M, rank, world)
         # batch over test points so the level buffers fit the workspace budget
         # (sharded runs too: every rank sees the same B and budget, so all ranks cut the same chunks; a chunk is a complete
@@ -224,13 +228,22 @@ class PicardSolverBase(object):
         if B == 0:
             _, st = self.plan(n, rho, 0, M)
             agg = {f: getattr(st, f) for f, _ in _lib.PicardStats._fields_}
-        if world > 1 and n > 0:
-            dist.all_reduce(out, op=dist.ReduceOp.SUM)           # the single collective of the path
-            _lib.check(lib.scasml_clip(_lib.ptr(out), out.numel(), float(self._clip()), _lib.stream_ptr()))
+        if with_u_hat and B > 0:
+            if world > 1:
+                uh.zero_()
+                mine = torch.arange(rank, B, world, device="cuda")
+                if mine.numel():
+                    uh[mine] = self.GP._eval(x_dev[mine].contiguous(), _lib.EVAL_U)[0]
+            else:
+                uh.copy_(self.GP._eval(x_dev, _lib.EVAL_U)[0])
+        if world > 1 and (n > 0 or with_u_hat):
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)           # the single collective of the path
+            if n > 0:
+                _lib.check(lib.scasml_clip(_lib.ptr(out), out.numel(), float(self._clip()), _lib.stream_ptr()))
         self.evaluation_counter += int(agg["eval_counter"])
         self.key += int(agg["keys_used"])
         self.last_stats = agg
-        return out
+        return (out, uh) if with_u_hat else out
 
     def _uz(self, n, rho, x_t, M=None):
         x_dev = _lib.to_device(x_t)
@@ -241,14 +254,16 @@ class PicardSolverBase(object):
 
     def _u_solve(self, n, rho, x_t, M=None):
         x_dev = _lib.to_device(x_t)                               # one host -> device copy serves the correction and u_hat
-        out = self._uz_device(n, rho, x_dev, M)
+        if self.scasml:
+            out, uh = self._uz_device(n, rho, x_dev, M, with_u_hat=True)   # top-level u_hat(x): GP.route (FP64 by default)
+        else:
+            out = self._uz_device(n, rho, x_dev, M)
         if not self.scasml:
             raw = _lib.to_host(out)
             self.last_raw = raw
             self.last_raw_u = raw[:, :1]
             return raw[:, 0][:, np.newaxis].astype(np.float16)
         torch = _lib.torch_cuda()
-        (uh,) = self.GP._eval(x_dev, _lib.EVAL_U)                 # top-level u_hat(x): GP.route (FP64 by default)
         both = _lib.to_host(torch.cat((out, uh[:, None]), dim=1))  # one device -> host copy (pinned staging)
         raw, u_hat_raw = both[:, :-1], both[:, -1:]
         self.last_raw = raw

@@ -1,0 +1,287 @@
+"""GPU parity at the configurations the numbers are quoted on (BASELINE.json configs 2-5), through the reference-shaped
+classes / the C ABI, against the CPU oracle on identical inputs:
+
+  C3  d = 100, 1000 + 200 collocation points, ScaSML n = rho = 4 (q = 5 nodes, MC_f = 16, 97 calls of level >= 1)
+      -- solvers/ScaSML.py:149-305 with the true Gauss-Legendre tables (the reference's own n = 4 table is NaN, SURVEY quirk 1,
+      which is checked too), fit included (models/GP.py:487-604), both arithmetic routes;
+  C4  d = 60, ScaSML_full_history n = 4, M = 3 -- solvers/ScaSML_full_history.py:75-221, both routes;
+  C5  shape d = 1000, 4000 + 800 collocation points (phi = 16 800): every evaluation mode on the K-streamed tcgen05 kernel and
+      the FP64 route vs the oracle, and a level-2 solve (the oracle needs minutes per test point at n = 4 here);
+  C2  d = 20, n = rho = 3 on the tcgen05 route at the full 1 200-point batch.
+Criterion (north_star): rel-L2 / L1 error vs the exact solution within 1e-6 relative of the oracle's on identical increments
+(tests/SimpleUniform.py:110-136 metrics); FP64 route additionally 1e-8 on the raw (u, z) rows; counters exact."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.solvers import ScaSMLFullHistoryOracle, ScaSMLOracle
+from tests.test_gpu_parity import Fitted, _product, _rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _criterion(prod, orac, exact, tol=1e-6):
+    l2_p, l1_p = _rel_l2(prod.last_raw_u, exact)
+    l2_o, l1_o = _rel_l2(orac.last_raw_u, exact)
+    assert abs(l2_p - l2_o) <= tol * l2_o, (l2_p, l2_o)
+    assert abs(l1_p - l1_o) <= tol * l1_o, (l1_p, l1_o)
+
+
+@pytest.fixture(scope="module")
+def c3():
+    return Fitted(d=100, nd=1000, nb=200)
+
+
+def test_c3_fit_matches_oracle(c3):
+    a_o, a_p = c3.gp_o.right_vector[:, 0], c3.gp.right_vector[:, 0]
+    assert np.linalg.norm(a_p - a_o) / np.linalg.norm(a_o) < 1e-6
+    assert c3.gp.newton_steps == c3.gp_o.newton_steps
+    np.testing.assert_allclose(c3.gp.loss_history, c3.gp_o.loss_history, rtol=1e-7)
+
+
+def test_c3_headline_config_matches_oracle_on_both_routes(c3):
+    F, P = c3, c3.P
+    lib = P["lib"]
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(6, 2)                                   # the oracle needs 1-2 s per test point at n = rho = 4
+    exact = F.eq_o.exact_solution(X)
+    orac = ScaSMLOracle(F.eq_o, F.gp_o, cast=False, true_gl=True)
+    want = orac.u_solve(4, 4, X)
+    assert orac.evaluation_counter == 3659
+    for route, raw_tol in ((lib.ROUTE_F64, 1e-8), (lib.ROUTE_TC, None)):
+        prod = P["ScaSML"](F.eq, F.gp)
+        prod.route = route
+        prod.quadrature = "gauss_legendre"
+        got = prod.u_solve(4, 4, X)
+        assert got.dtype == np.float16 and got.shape == (len(X), 1)
+        assert prod.evaluation_counter == 3659 and prod.key == orac.key_counter
+        assert prod.last_stats["n_calls"] == 97 and prod.last_stats["sample_points"] == 13426
+        assert prod.last_stats["executed_points"] == 8582 * len(X)
+        if raw_tol is not None:
+            np.testing.assert_allclose(prod.last_raw, orac.last_raw, rtol=raw_tol, atol=1e-11)
+        else:                                                 # tcgen05 route: ~2e-7 relative per evaluation, averaged by the Monte-Carlo means
+            assert np.max(np.abs(prod.last_raw[:, 0] - orac.last_raw[:, 0])) < 5e-7
+            assert np.max(np.abs(prod.last_raw[:, 1:] - orac.last_raw[:, 1:])) < 2e-5
+        _criterion(prod, orac, exact)
+        assert np.mean(got.astype(np.float64) != want.astype(np.float64)) <= 0.25      # float16 flips only (8 values)
+        assert np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))) <= 2 ** -10
+
+
+def test_c3_reference_tables_are_nan_at_level_four(c3):
+    """with the reference's own lgwt tables ScaSML n = rho = 4 returns NaN for every test point."""
+    F, P = c3, c3.P
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(2, 1)
+    orac = ScaSMLOracle(F.eq_o, F.gp_o, cast=False)
+    want = orac.u_solve(4, 4, X).astype(np.float64)
+    for route in (P["lib"].ROUTE_F64, P["lib"].ROUTE_TC):
+        prod = P["ScaSML"](F.eq, F.gp)
+        prod.route = route
+        got = prod.u_solve(4, 4, X).astype(np.float64)
+        assert np.all(np.isnan(got)) and np.all(np.isnan(want))
+        assert prod.evaluation_counter == orac.evaluation_counter
+
+
+def test_c4_full_history_level_four():
+    F = Fitted(d=60, nd=1000, nb=200)
+    P, lib = F.P, F.P["lib"]
+    assert np.linalg.norm(F.gp.right_vector - F.gp_o.right_vector) / np.linalg.norm(F.gp_o.right_vector) < 1e-6
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(10, 2)
+    exact = F.eq_o.exact_solution(X)
+    orac = ScaSMLFullHistoryOracle(F.eq_o, F.gp_o, cast=False)
+    want = orac.u_solve(4, None, X, M=3)
+    assert orac.evaluation_counter == 2714                   # SURVEY App. C (ScaSML_full_history counts MC_g, quirk A.3-7)
+    for route in (lib.ROUTE_F64, lib.ROUTE_TC):
+        prod = P["ScaSMLfh"](F.eq, F.gp)
+        prod.route = route
+        got = prod.u_solve(4, None, X, 3)
+        assert prod.evaluation_counter == 2714
+        assert prod.last_stats["sample_points"] == 2523
+        if route == lib.ROUTE_F64:
+            np.testing.assert_allclose(prod.last_raw, orac.last_raw, rtol=1e-8, atol=1e-11)
+        else:
+            assert np.max(np.abs(prod.last_raw[:, 0] - orac.last_raw[:, 0])) < 5e-7
+        _criterion(prod, orac, exact)
+        assert np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))) <= 2 ** -10
+
+
+def test_c5_shape_eval_modes_and_level_two_solve():
+    """d = 1000, 4000 + 800 collocation points: the GP weights come from the PRODUCT's own fit (20 Newton steps on 12 000^2
+    systems; the oracle's fit takes minutes on the host and is compared at C2 / C3 size instead) and are installed in the oracle."""
+    P = _product()
+    lib = P["lib"]
+    from oracle.equation import EquationOracle
+    from oracle.gp import GPOracle
+    d, nd, nb = 1000, 4000, 800
+    eq_o = EquationOracle(d + 1)
+    dom, bdy = eq_o.generate_data(nd, nb, seed=1234)
+    idx = np.random.default_rng(7).choice(d, 5, replace=False)
+    eq = P["Eq"](d + 1)
+    gp = P["GP"](eq, idx_set=idx)
+    gp.GPsolver(dom, bdy, GN_steps=3)                         # three Newton steps are enough for realistic (cancelling) weights
+    assert lib.load().scasml_gp_tc_supported(gp._handle) == 1
+    gp_o = GPOracle(eq_o, idx_set=idx)
+    gp_o.x_t_domain, gp_o.x_t_boundary = dom, bdy
+    gp_o.N_domain, gp_o.N_boundary = nd, nb
+    gp_o.right_vector = gp.right_vector.copy()
+    X = np.concatenate(eq_o.generate_test_data(70, 13, seed=42), axis=0)
+    X[:5] += 0.0123456789                                     # not float16-representable
+    eps_o, u_o, dv_o, lp_o, dt_o = gp_o.pde_terms_raw(X)
+    G_o = gp_o.gradient_raw(X)[:, :-1].sum(1)
+    gt_o = eq_o.g(X, cast=False)[:, 0] - u_o
+    for route, tu, tg in ((lib.ROUTE_F64, 1e-9, 1e-8), (lib.ROUTE_TC, 2e-6, 5e-5)):
+        gp.route = route
+        u = gp.predict_raw(X)
+        eps, dv, lp, dt = gp.pde_terms_raw(X)
+        uu, G = [t.cpu().numpy() for t in gp._eval(X, lib.EVAL_UG, nout=2)]
+        gt = gp._eval(X, lib.EVAL_TERMINAL)[0].cpu().numpy()
+        for name, a, b, tol in (("u", u, u_o, tu), ("uu", uu, u_o, tu), ("gt", gt, gt_o, tu), ("G", G, G_o, tg), ("dv", dv, dv_o, tg),
+                                ("lp", lp, lp_o, tg), ("dt", dt, dt_o, tg), ("eps", eps, eps_o, tg)):
+            scale = max(1.0, float(np.abs(b).max()))
+            assert np.max(np.abs(a - b)) < tol * scale, (route, name, float(np.max(np.abs(a - b))), scale)
+    gp.route = lib.ROUTE_F64
+    Xs = X[:6]
+    exact = eq_o.exact_solution(Xs)
+    orac = ScaSMLOracle(eq_o, gp_o, cast=False)
+    orac.u_solve(2, 2, Xs)
+    for route in (lib.ROUTE_F64, None):                        # None: the solver's default = K-streamed tcgen05 kernel at this d
+        prod = P["ScaSML"](eq, gp)
+        prod.route = route
+        prod.u_solve(2, 2, Xs)
+        assert prod.evaluation_counter == orac.evaluation_counter == 83
+        assert np.max(np.abs(prod.last_raw_u - orac.last_raw_u)) < (1e-9 if route is not None else 5e-6)
+        _criterion(prod, orac, exact, tol=1e-6 if route is not None else 1e-5)
+
+
+def test_c2_full_batch_on_the_tcgen05_route():
+    F = Fitted(d=20, nd=1000, nb=200)
+    P, lib = F.P, F.P["lib"]
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(1000, 200)
+    exact = F.eq_o.exact_solution(X)
+    prod = P["ScaSML"](F.eq, F.gp)
+    prod.route = lib.ROUTE_TC
+    u = prod.u_solve(3, 3, X).astype(np.float64)
+    raw = prod.last_raw.copy()
+    assert prod.evaluation_counter == 549
+    assert np.all(np.abs(raw[~np.isnan(raw)]) <= 0.1 + 1e-12)
+    l2_gp, _ = _rel_l2(F.gp.predict(X), exact)
+    l2_sc, _ = _rel_l2(u, exact)
+    assert l2_sc < l2_gp
+    # against the FP64 route on the whole batch, against the oracle on a slice (global row ids)
+    ref = P["ScaSML"](F.eq, F.gp)
+    ref.route = lib.ROUTE_F64
+    ref.u_solve(3, 3, X)
+    m = ~np.isnan(ref.last_raw[:, 0])
+    assert np.array_equal(np.isnan(raw), np.isnan(ref.last_raw))
+    assert np.max(np.abs(raw[m, 0] - ref.last_raw[m, 0])) < 1e-6
+    l2_t, l1_t = _rel_l2(prod.last_raw_u, exact)
+    l2_f, l1_f = _rel_l2(ref.last_raw_u, exact)
+    assert abs(l2_t - l2_f) <= 1e-6 * l2_f and abs(l1_t - l1_f) <= 1e-6 * l1_f
+    sl = slice(300, 306)
+    orac = ScaSMLOracle(F.eq_o, F.gp_o, cast=False)
+    orac.uz_solve(3, 3, X[sl], gid0=300)
+    assert np.max(np.abs(raw[sl, 0] - orac.last_raw[:, 0])) < 1e-6
+
+
+def test_non_float16_centres_keep_the_fp64_route():
+    """the tcgen05 route takes the collocation points as an exact f16 operand.  float64 centres must not go there
+    silently: scasml_gp_tc_supported is 0, the solver's default falls back to FP64 and an explicit ROUTE_TC raises."""
+    P = _product()
+    lib = P["lib"]
+    from oracle.equation import EquationOracle
+    from oracle.gp import GPOracle
+    d, nd, nb = 20, 120, 30
+    eq_o = EquationOracle(d + 1)
+    rng = np.random.default_rng(5)
+    dom = np.hstack([rng.uniform(-0.5, 0.5, (nd, d)), rng.uniform(0, 0.5, (nd, 1))])          # float64, not float16-valued
+    bdy = np.hstack([rng.uniform(-0.5, 0.5, (nb, d)), rng.uniform(0, 0.5, (nb, 1))])
+    bdy[np.arange(nb), rng.integers(0, d, nb)] = 0.5
+    idx = np.random.default_rng(7).choice(d, 5, replace=False)
+    sol0 = np.random.default_rng(0).standard_normal(3 * nd) * 1e-3
+    gp_o = GPOracle(eq_o, idx_set=idx)
+    gp_o.GPsolver(dom, bdy, sol0=sol0)
+    eq = P["Eq"](d + 1)
+    gp = P["GP"](eq, idx_set=idx)
+    gp.GPsolver(dom, bdy, sol0=sol0)
+    assert lib.load().scasml_gp_tc_supported(gp._handle) == 0
+    gp.set_right_vector(gp_o.right_vector)
+    X = np.concatenate(eq_o.generate_test_data(10, 3, seed=3), axis=0)
+    orac = ScaSMLOracle(eq_o, gp_o, cast=False)
+    orac.u_solve(2, 2, X)
+    prod = P["ScaSML"](eq, gp)
+    assert prod.route is None
+    prod.u_solve(2, 2, X)                                     # default route: FP64 here
+    np.testing.assert_allclose(prod.last_raw, orac.last_raw, rtol=1e-8, atol=1e-11)
+    prod.route = lib.ROUTE_TC
+    with pytest.raises(lib.ScasmlError):
+        prod.u_solve(2, 2, X)
+    gp.route = lib.ROUTE_TC
+    with pytest.raises(lib.ScasmlError):
+        gp.predict(X)
+
+
+def test_points_far_outside_the_box_do_not_saturate_the_tcgen05_route():
+    """P = 2^s exp(a x.y) is stored as f16; rows with a |x| max|y| beyond the default shift's range get a smaller
+    per-row shift instead of saturated values.  d = 6 (a = 2.67): corners of a box three times the collocation box."""
+    F = Fitted(d=6, nd=60, nb=16)
+    lib = F.P["lib"]
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(40, 8)
+    X[:, :6] = np.sign(X[:, :6] + 1e-9) * np.linspace(0.5, 1.6, len(X))[:, None]     # a x.y up to ~13 at the far corners
+    want = F.gp_o.predict_raw(X)
+    eps_o = F.gp_o.pde_terms_raw(X)[0]
+    F.gp.route = lib.ROUTE_TC
+    got = F.gp.predict_raw(X)
+    eps = F.gp.pde_terms_raw(X)[0]
+    F.gp.route = lib.ROUTE_F64
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - want)) < 2e-6 * max(1.0, np.abs(want).max())
+    assert np.max(np.abs(eps - eps_o)) < 5e-5 * max(1.0, np.abs(eps_o).max())
+
+
+def test_more_ranks_than_sample_units():
+    """a rank that owns no top-level unit (B MC_g < world) must still produce its zero partial sums (and reach the
+    all-reduce) instead of failing on empty grids."""
+    F = Fitted(d=6, nd=40, nb=12)
+    P, lib, torch = F.P, F.P["lib"], F.P["torch"]
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(1, 0)
+    xd = lib.to_device(X)
+    for cls, kw in ((P["ScaSMLfh"], dict(n=1, rho=None, M=1)), (P["ScaSMLfh"], dict(n=2, rho=None, M=2))):
+        want = cls(F.eq, F.gp)._uz_device(kw["n"], kw["rho"], xd, kw["M"]).cpu().numpy()
+        world = 8
+        acc = torch.zeros((1, F.d + 1), dtype=torch.float64, device="cuda")
+        for rank in range(world):
+            s = cls(F.eq, F.gp)
+            p = s._params(kw["n"], kw["rho"], kw["M"], rank, world)
+            need = C.c_size_t(0)
+            lib.check(lib.load().scasml_picard_plan(C.byref(p), 1, C.byref(need), None))
+            ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+            out = torch.full_like(acc, float("nan"))
+            st = lib.PicardStats()
+            lib.check(lib.load().scasml_uz_solve(F.gp._handle, C.byref(p), 0, lib.ptr(xd), 1, lib.ptr(out), lib.ptr(ws), ws.numel(),
+                                                 C.byref(st), lib.stream_ptr()))
+            torch.cuda.synchronize()
+            acc += out
+        lib.check(lib.load().scasml_clip(lib.ptr(acc), acc.numel(), 0.1, lib.stream_ptr()))
+        np.testing.assert_allclose(acc.cpu().numpy(), want, rtol=1e-9, atol=1e-13)
+
+
+def test_two_rank_nccl_solve_equals_single_gpu():
+    """On a box with >= 2 GPUs: the product's sharded solve (NCCL all-reduce of the weighted partial sums) equals the
+    single-GPU solve.  tools/nrank_check.py prints the maximum difference; bench.py repeats the check in every multi-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29417", os.path.join(ROOT, "tools", "nrank_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "NRANK_CHECK_OK" in out.stdout
