@@ -250,7 +250,8 @@ def main():
     route = args.route
     if route == "auto":     # the tcgen05 route is the product path wherever it applies (d <= 1022); FP64 is the parity anchor
         route = "tc" if d + 2 <= 1024 else "f64"
-    gp.route = _lib.ROUTE_TC if route == "tc" else _lib.ROUTE_F64
+    sroute = _lib.ROUTE_TC if route == "tc" else _lib.ROUTE_F64   # route of the sampled points; the top-level u_hat(x) of u_solve
+                                                                  # stays on GP.route = FP64, the public API's default
     gp.GPsolver(dom, bdy)                                    # first fit: allocations, module load
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -262,7 +263,7 @@ def main():
 
     def new_solver(distributed):
         s = Solver(eq, gp)
-        s.route = gp.route
+        s.route = sroute
         s.quadrature = args.quadrature
         s.distributed = distributed
         s.use_graph = not args.no_graph

@@ -54,6 +54,7 @@ struct TcDev {
     const TcColDesc* desc;           // column table of this evaluation class
     size_t b1_tile_bytes, b3_tile_bytes;
     int nstep, ntile_dom, ntile_bdy;
+    const double* csum;              // [TC_MAXCOL] per column: sum over the centres of the scaled, split coefficients (baseline term of the coefficient GEMM)
     const double* ymax2;             // device scalar: max_j |y_j|^2 over the centres (per-row exponent shift, row_shift())
     const LevelDev* gen;             // non-null: the loader warps GENERATE the points (fused sampler) instead of reading X
     long long gen_off;               // index of the launch's first point in the level's point buffer
@@ -137,22 +138,36 @@ __device__ __forceinline__ uint32_t sw_off(int r, int c) {
     return (uint32_t)(r * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
 }
 
-// pass 2a: stage-1 centre images.  Per tile, per K block: rows [C (64) | rollinv(C) (64) | roll(C) (64)], f16, 128 B swizzle.
-// Column D is 1 in every row: the A operand carries the exponent shift of its point row there (row_shift()); columns > D are zero.
-__global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile_bytes, int KB) {
+// Centre tiles come in two formats (TcState::tn / compact):
+//   resident-operand kernel: 48 centres per tile over the COMPACT centre list [domain 0..Nd) | boundary 0..Nb)] -- 1 200 centres
+//   are exactly 25 tiles, the ky class (domain centres only) runs over the first ceil(Nd / 48) of them (boundary centres carry
+//   zero ky coefficients);
+//   K-streamed kernel: 64 centres per tile over the padded list of GpView ([domain | pad to 64 | boundary | pad to 64]).
+// Row r of tile `tile` -> index into GpView::C / feat, or -1 for a padding row (zero centre, zero coefficients).
+__device__ __forceinline__ int tile_centre(const GpView& gp, int tile, int r, int tn, int compact) {
+    const int jc = tile * tn + r;
+    if (!compact) return jc;
+    if (jc < gp.Nd) return jc;
+    if (jc < gp.Nd + gp.Nb) return gp.NdPad + (jc - gp.Nd);
+    return -1;
+}
+
+// pass 2a: stage-1 centre images.  Per tile, per K block: rows [C (tn) | rollinv(C) (tn) | roll(C) (tn)], f16, 128 B swizzle.
+// Columns >= D are zero (the exponent shift of a point row is applied after ex2, see row_shift()).
+__global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile_bytes, int KB, int tn, int compact) {
     const int tile = blockIdx.x;
     uint8_t* base = b1 + (size_t)tile * tile_bytes;
     const int D = gp.D;
+    const int TN = tn;
     for (int idx = threadIdx.x; idx < TN * KB * KBLK; idx += blockDim.x) {
         const int r = idx / (KB * KBLK), c = idx % (KB * KBLK);
-        const double* y = gp.C + (size_t)(tile * TN + r) * D;
+        const int cj = tile_centre(gp, tile, r, tn, compact);
+        const double* y = gp.C + (size_t)(cj < 0 ? 0 : cj) * D;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-        if (c < D) {
+        if (c < D && cj >= 0) {
             v0 = y[c];
             v1 = y[(c == 0) ? D - 1 : c - 1];            // roll(x) . y = x . rollinv(y),  rollinv(y)_c = y_{c-1}
             v2 = y[(c + 1 == D) ? 0 : c + 1];            // roll(y)_c = y_{c+1}            (models/GP.py:91-93)
-        } else if (c == D) {
-            v0 = v1 = v2 = 1.0;
         }
         uint8_t* blk = base + (size_t)(c / KBLK) * (3 * TN * 128);
         *(__half*)(blk + sw_off(r, c % KBLK)) = __double2half(v0);
@@ -162,20 +177,22 @@ __global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile
 }
 
 // pass 2b: stage-2 coefficient images of one evaluation class: per tile [k hi | k lo | kx hi | kx lo | ky hi | ky lo],
-// each [ncol rows x 64 centres] f16 (K-major B operand, 128 B swizzle); column table with the inverse scales.
+// each [ncol rows x 64 K slots] f16 of which the first tn are centres (K-major B operand, 128 B swizzle); column table with the inverse scales.
 __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, int cls, int ncentres, const double* __restrict__ coef,
                                 const unsigned long long* __restrict__ colmax, uint8_t* __restrict__ b3, size_t tile_bytes,
-                                int nk, int nkx, int nky, TcColDesc* __restrict__ desc) {
+                                int nk, int nkx, int nky, TcColDesc* __restrict__ desc, int tn, int compact) {
     const int tile = blockIdx.x;
     uint8_t* base = b3 + (size_t)tile * tile_bytes;
     const int ntot = nk + nkx + nky;
+    const int TN = tn;
     for (int idx = threadIdx.x; idx < ntot * TN; idx += blockDim.x) {
         const int col = idx / TN, j = idx % TN;
+        const int cj = tile_centre(gp, tile, j, tn, compact);
         const double cm = __longlong_as_double((long long)colmax[cls * TC_MAXCOL + col]);
         int e = 0;
         if (cm > 0.0) frexp(cm, &e);
         const double scale = (cm > 0.0) ? ldexp(1.0, 13 - e) : 1.0;       // column maximum -> [2^12, 2^13)
-        const double v = coef[((size_t)cls * ncentres + (size_t)tile * TN + j) * TC_MAXCOL + col] * scale;
+        const double v = (cj < 0) ? 0.0 : coef[((size_t)cls * ncentres + (size_t)cj) * TC_MAXCOL + col] * scale;
         const __half hi = __double2half(v);
         const __half lo = __double2half(v - (double)__half2float(hi));
         int row = col;
@@ -215,6 +232,34 @@ __global__ void ymax_kernel(GpView gp, int ncentres, unsigned long long* __restr
     if (j >= ncentres) return;
     const double ny = gp.feat[(size_t)j * CF_STRIDE + CF_NY];
     if (ny > 0.0 && ny < 1e300) atomicMax(out, (unsigned long long)__double_as_longlong(ny));
+}
+
+// Column sums of the scaled, split coefficients (exactly the values the stage-2 MMAs multiply with), in a fixed summation order:
+// the coefficient GEMM runs on P - 2^s (the tensor core truncates its FP32 accumulation, ~0.66 ulp per MMA towards zero,
+// tools/tc_accum_probe.py; the bias is proportional to the running sum, so the constant part 2^s sum_j C_j is taken out of it)
+// and the final contraction adds 2^s csum[col] back.
+__global__ void __launch_bounds__(256) csum_kernel(int ncentres, const double* __restrict__ coef, const unsigned long long* __restrict__ colmax,
+                                                   double* __restrict__ csum) {
+    __shared__ double part[256];
+    const int cls = blockIdx.y, col = blockIdx.x;
+    const double cm = __longlong_as_double((long long)colmax[cls * TC_MAXCOL + col]);
+    int e = 0;
+    if (cm > 0.0) frexp(cm, &e);
+    const double scale = (cm > 0.0) ? ldexp(1.0, 13 - e) : 1.0;           // same scale as b3_image_kernel
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < ncentres; j += 256) {
+        const double v = coef[((size_t)cls * ncentres + j) * TC_MAXCOL + col] * scale;
+        const __half hi = __double2half(v);
+        const __half lo = __double2half(v - (double)__half2float(hi));
+        acc += (double)__half2float(hi) + (double)__half2float(lo);
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o >= 1; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) csum[cls * TC_MAXCOL + col] = part[0];
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
@@ -404,7 +449,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint8_t* sB1 = smem;                                             // NB1 pair slots
     uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NSLOT pair slots
     uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
-    double* feat = (double*)(sStage + 2 * (size_t)TM * A_PITCH);     // [128][TF_COUNT] features of the tile being finalised
+    float* feat = (float*)(sStage + 2 * (size_t)TM * A_PITCH);       // [128][TF_COUNT] features (floats) of the tile being finalised
     // column table of the final contraction, in the form its inner loop wants: per column the byte offsets of its two features in a
     // row's float feature vector (f1 | f2 << 16) and its scale 1 / (2^s 2^TC_P_SHIFT) spread over the four outputs as a one-hot float4
     // (the contraction is issue-bound: 44 instructions per column with byte extraction, an output-change test and a select chain per
@@ -414,7 +459,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     GenRec* grec = (GenRec*)(soff + TC_MAXCOL);                      // [128] fused sampler: resolved points of the tile being staged
     double* Ki = (double*)(grec + (GEN ? TM : 0));                       // [128] exp(-a |x|^2 / 2) of the staged tile
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
-    uint64_t* bars = (uint64_t*)(sxs + TM);
+    float* rsc = (float*)(sxs + TM);                                 // [2][128] 2^s of the point rows, by tile parity (epilogue: P = 2^s ex2(S) - 2^s)
+    float2* scs = (float2*)(rsc + 2 * TM);                           // [TC_MAXCOL] column sums of the coefficients as (hi, lo) floats
+    uint64_t* bars = (uint64_t*)(scs + TC_MAXCOL);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -460,6 +507,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const float sc = dead ? 0.0f : (float)dsc.inv_scale;        // a power of two: exact in FP32 (range checked when the images are built)
         soff[c] = dead ? 0u : ((uint32_t)dsc.f1 * 4u) | (((uint32_t)dsc.f2 * 4u) << 16);
         smask[c] = make_float4(dsc.out == TO_U ? sc : 0.0f, dsc.out == TO_G ? sc : 0.0f, dsc.out == TO_L ? sc : 0.0f, dsc.out == TO_T ? sc : 0.0f);
+        const double cs = dead ? 0.0 : st.csum[c];
+        const float csh = (float)cs;
+        scs[c] = make_float2(csh, (float)(cs - (double)csh));
     }
     tc_fence_before();
     __syncthreads();                                                 // TMEM base address + barriers + column table visible
@@ -658,8 +708,10 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         static_assert(RPW == 32, "a loader warp owns one tensor-memory lane quadrant");
         const int rq = qd * RPW + lane;                              // this thread's row in the contraction
         double ki_prev = 0.0, sx_prev = 0.0;
+        float sc_prev = 0.0f;
         for (int it = 0; it <= nit; ++it) {
             double ki_new = 0.0, sx_new = 0.0;
+            float sc_new = 0.0f;
             if (it < nit) {
             const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
             if (it > 0) mbar_wait(stage_free, (uint32_t)(it - 1) & 1u);     // the previous tile's images are in tensor memory
@@ -699,7 +751,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                             const double val = v[i][e + q];
                             nx = fma(val, val, nx);
                             if (c < d) sx += val;
-                            sv[q] = (c == D) ? (float)TC_P_SHIFT : (float)(ascale * val);   // column D: exponent shift (B holds 1), patched below for far-out rows
+                            sv[q] = (float)(ascale * val);                 // columns >= D are zero
                         }
                         // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
                         const __half2 h = __floats2half2_rn(sv[0], sv[1]);
@@ -715,14 +767,12 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
 #pragma unroll
                     for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
-                    if (hl == 0) { Ki[r] = nx; sxs[r] = sx; }
-                    const int sh = row_shift(gp.a, nx, ymax2);
-                    if (sh != TC_P_SHIFT && hl == (D >> 3))           // rare: the lane that staged column D overwrites its entry
-                        *(__half*)(sStage + (size_t)r * A_PITCH + (size_t)D * 2) = __int2half_rn(sh);
+                    if (hl == 0) { Ki[r] = nx; sxs[r] = sx; rsc[(it & 1) * TM + r] = exp2f((float)row_shift(gp.a, nx, ymax2)); }
                 }
             }
             if (GEN) __threadfence_block();                         // generated rows (global) are re-read by this warp's contraction
             __syncwarp();
+            sc_new = rsc[(it & 1) * TM + rq];
             ki_new = ldexp(exp(-0.5 * gp.a * Ki[rq]), TC_P_SHIFT - row_shift(gp.a, Ki[rq], ymax2)); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
                                                                      // (one FP64 exp per lane instead of one per row pass)
             __syncwarp();
@@ -749,7 +799,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 // FP64 runs at 1/8 of the FP32 rate on this part (a warp-wide FP64 instruction holds its pipe 8 cycles): the column products
                 // F[f1] F[f2] T[col] are formed in FP32 (their rounding, ~2e-7, is of the size of T's own FP32 accumulation error) and only the
                 // sums over columns stay in FP64.  The features are kept as floats; the few the outputs need exactly stay in registers.
-                float* F = (float*)feat + rq * TF_COUNT;             // private to this thread
+                float* F = feat + rq * TF_COUNT;                     // private to this thread
                 double f_xt = 0.0;
                 {
                     const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
@@ -813,7 +863,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     for (int i = 0; i < CH; ++i) {
                         const uint32_t o = soff[cb + i];
                         const float4 m = smask[cb + i];
-                        const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * tv[i];
+                        const float2 cs = scs[cb + i];
+                        const float w = fmaf(sc_prev, cs.x, fmaf(sc_prev, cs.y, tv[i]));      // sum_j P C = T + 2^s sum_j C (baseline term)
+                        const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * w;
                         pU = fmaf(t, m.x, pU); pG = fmaf(t, m.y, pG); pL = fmaf(t, m.z, pL); pT = fmaf(t, m.w, pT);
                     }
                     aU += (double)pU; aG += (double)pG; aL += (double)pL; aT += (double)pT;
@@ -839,7 +891,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(247);
                 if (!TDBL) asm volatile("bar.sync 2, %0;" ::"n"(NLOAD * 32) : "memory");   // every loader warp is done with the T copy in the staging buffer
             }
-            ki_prev = ki_new; sx_prev = sx_new;
+            ki_prev = ki_new; sx_prev = sx_new; sc_prev = sc_new;
         }
     } else {
         // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
@@ -878,6 +930,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 // chunk's ex2 work.  The two groups run half a period apart.
                 static_assert(NSLOT == 2, "one epilogue group per S/P slot");
                 const bool stamp = (it == 1);
+                const float sc = rsc[(it & 1) * TM + r], nsc = -sc;  // 2^s of this thread's point row (written before stage_full of the tile)
                 const int grp = warp >> 3;                           // slot owned by this warp
                 const uint32_t chalf = (uint32_t)((warp >> 2) & 1) * 32u;   // which 32 of a sub-item's 64 centres
                 for (int j = 0; j < npair; ++j, ++g) {
@@ -900,7 +953,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                                 uint32_t hi[8], lo[8];
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float p0 = ex2f(v[c & 1][2 * i]), p1 = ex2f(v[c & 1][2 * i + 1]);
+                                    const float p0 = fmaf(ex2f(v[c & 1][2 * i]), sc, nsc), p1 = fmaf(ex2f(v[c & 1][2 * i + 1]), sc, nsc);   // P - 2^s
                                     hi[i] = pack_f16x2_sat(p0, p1);
                                     const float2 hf = __half22float2(*(const __half2*)&hi[i]);
                                     lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
@@ -940,7 +993,8 @@ static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     return ((CLASS == TC_PDE && GEN) ? 2 : 3) * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
-           + (size_t)TM * TF_COUNT * 8 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t)) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + NBAR * 8 + 16;
+           + (size_t)TM * TF_COUNT * 4 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t)) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8
+           + 2 * TM * sizeof(float) + TC_MAXCOL * sizeof(float2) + NBAR * 8 + 16;
 }
 
 template <int CLASS, int NSTEP, bool GEN>
@@ -973,7 +1027,7 @@ constexpr int KS_NBAR = 2 * KS_STAGES + 4 * NSLOT + 2;               // full emp
 constexpr int KS_THREADS = (NEPI + 2) * 32;
 
 __global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* __restrict__ X, long R, int KB, const double* __restrict__ ymax2p,
-                                                       uint8_t* __restrict__ img, double* __restrict__ Ki, double* __restrict__ sxs) {
+                                                       uint8_t* __restrict__ img, double* __restrict__ Ki, double* __restrict__ sxs, float* __restrict__ rscg) {
     const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = gp.D, d = gp.d;
     const double ascale = gp.a * 1.4426950408889634;
@@ -995,7 +1049,7 @@ __global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* 
                     const double val = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
                     nx = fma(val, val, nx);
                     if (c < d) sx += val;
-                    sv[q] = (c == D) ? (float)TC_P_SHIFT : (float)(ascale * val);
+                    sv[q] = (float)(ascale * val);
                 }
                 const __half2 h = __floats2half2_rn(sv[0], sv[1]);
                 const float2 hf = __half22float2(h);
@@ -1012,18 +1066,17 @@ __global__ void __launch_bounds__(256) ks_image_kernel(GpView gp, const double* 
         }
         for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
         const int sh = row_shift(gp.a, nx, __ldg(ymax2p));
-        if (sh != TC_P_SHIFT && hl == ((D % 128) >> 3)) {              // the lane that wrote column D patches it (its own earlier store)
-            const int cD = D % KBLK;
-            *(__half*)(base + (size_t)(D / KBLK) * 2 * A_BLK + (uint32_t)r * 128u + (uint32_t)(((((cD) >> 3) ^ (r & 7)) & 7) << 4) + (uint32_t)(cD & 7) * 2u) = __int2half_rn(sh);
+        if (hl == 0) {
+            Ki[(size_t)tile * TM + r] = ldexp(exp(-0.5 * gp.a * nx), TC_P_SHIFT - sh); sxs[(size_t)tile * TM + r] = sx;
+            rscg[(size_t)tile * TM + r] = exp2f((float)sh);
         }
-        if (hl == 0) { Ki[(size_t)tile * TM + r] = ldexp(exp(-0.5 * gp.a * nx), TC_P_SHIFT - sh); sxs[(size_t)tile * TM + r] = sx; }
     }
 }
 
 template <int CLASS>
 __global__ void __launch_bounds__(KS_THREADS, 1)
 eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode, const uint8_t* __restrict__ img,
-                  const double* __restrict__ Kig, const double* __restrict__ sxg,
+                  const double* __restrict__ Kig, const double* __restrict__ sxg, const float* __restrict__ rscg,
                   double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
     using C = Cfg<CLASS>;
     constexpr bool PDE = (CLASS == TC_PDE);
@@ -1039,7 +1092,8 @@ eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int
     double* feat = (double*)(sB3 + NSLOT * (size_t)B3_SLOT);
     double* xchg = feat + TM * TF_COUNT;
     TcColDesc* sdesc = (TcColDesc*)(xchg + 3 * TM * 4);
-    uint64_t* bars = (uint64_t*)(sdesc + TC_MAXCOL);
+    double* scsum = (double*)(sdesc + TC_MAXCOL);                    // [TC_MAXCOL] column sums of the coefficients (baseline term)
+    uint64_t* bars = (uint64_t*)(scsum + TC_MAXCOL);
     uint32_t* tmem_slot = (uint32_t*)(bars + KS_NBAR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1065,8 +1119,10 @@ eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int
     if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
     for (int c = tid; c < TC_MAXCOL; c += KS_THREADS) {
         TcColDesc dsc = st.desc[c < NT ? c : 0];
-        if (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX)) { dsc.out = TO_PAD; dsc.f1 = 0; dsc.f2 = 0; dsc.inv_scale = 0.0; }
+        const bool dead = (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX));
+        if (dead) { dsc.out = TO_PAD; dsc.f1 = 0; dsc.f2 = 0; dsc.inv_scale = 0.0; }
         sdesc[c] = dsc;
+        scsum[c] = dead ? 0.0 : st.csum[c];
     }
     tc_fence_before();
     __syncthreads();
@@ -1227,6 +1283,7 @@ eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int
         long g = 0;
         for (int it = 0; it < nit; ++it) {
             const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
+            const float sc = __ldg(rscg + row0 + r), nsc = -sc;     // 2^s of this thread's point row (scratch rows are padded to whole tiles)
             for (int j = 0; j < npair; ++j, ++g) {
                 const int s = (int)(g % NSLOT);
                 const bool two = 2 * j + 1 < nitem;
@@ -1243,7 +1300,7 @@ eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float p0 = ex2f(v[c][2 * i]), p1 = ex2f(v[c][2 * i + 1]);
+                            const float p0 = fmaf(ex2f(v[c][2 * i]), sc, nsc), p1 = fmaf(ex2f(v[c][2 * i + 1]), sc, nsc);   // P - 2^s
                             hi[i] = pack_f16x2_sat(p0, p1);
                             const float2 hf = __half22float2(*(const __half2*)&hi[i]);
                             lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
@@ -1297,7 +1354,7 @@ eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int
             for (int i = 0; i < NPER; ++i) {
                 const TcColDesc dsc = sdesc[cg * NPER + i];
                 if ((int)dsc.out != cur) { flush(cur); cur = dsc.out; }
-                run = fma(F[dsc.f1] * F[dsc.f2], (double)tv[i] * dsc.inv_scale, run);
+                run = fma(F[dsc.f1] * F[dsc.f2], ((double)tv[i] + (double)sc * scsum[cg * NPER + i]) * dsc.inv_scale, run);   // + 2^s sum_j C: baseline term
             }
             flush(cur);
             if (cg > 0) {
@@ -1338,18 +1395,18 @@ eval_tc_ks_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int
 
 template <int CLASS>
 static int launch_ks(const GpView& gp, const TcDev& st, const double* X, long R, int mode, const uint8_t* img, const double* Ki,
-                     const double* sxs, double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
+                     const double* sxs, const float* rsc, double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     const size_t smem = KS_STAGES * (size_t)KS_STAGE_BYTES + NSLOT * (2 * 2 * NMAX * 128) + (size_t)TM * TF_COUNT * 8 + 3 * (size_t)TM * 4 * 8
-                        + TC_MAXCOL * sizeof(TcColDesc) + KS_NBAR * 8 + 16;
+                        + TC_MAXCOL * (sizeof(TcColDesc) + sizeof(double)) + KS_NBAR * 8 + 16;
     int dev = 0, nsm = 0;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     SC_CUDA(cudaFuncSetAttribute(eval_tc_ks_kernel<CLASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long ntiles = cdiv(R, TM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
-    eval_tc_ks_kernel<CLASS><<<grid, KS_THREADS, smem, stream>>>(gp, st, X, R, mode, img, Ki, sxs, o0, o1, o2, o3);
+    eval_tc_ks_kernel<CLASS><<<grid, KS_THREADS, smem, stream>>>(gp, st, X, R, mode, img, Ki, sxs, rsc, o0, o1, o2, o3);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -1440,6 +1497,7 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
     for (int cls = 0; cls < 3; ++cls) st->desc_off[cls] = take(TC_MAXCOL * sizeof(TcColDesc));
     st->spec_off = take(3 * TC_MAXCOL * sizeof(TcColSpec));
     st->ymax_off = take(sizeof(double));
+    st->csum_off = take(3 * TC_MAXCOL * sizeof(double));
     st->scratch_off = take(3 * ncentres * TC_MAXCOL * sizeof(double) + 3 * TC_MAXCOL * sizeof(unsigned long long));
     st->total_bytes = off;
     return off;
@@ -1468,6 +1526,8 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
                                                         (TcColDesc*)(st.images + st.desc_off[cls]));
         SC_LAUNCH_CHECK();
     }
+    tc::csum_kernel<<<dim3(TC_MAXCOL, 3), 256, 0, stream>>>(ncentres, coef, colmax, (double*)(st.images + st.csum_off));
+    SC_LAUNCH_CHECK();
     return OK;
 }
 
@@ -1490,6 +1550,7 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
     dv.ymax2 = (const double*)(st->images + st->ymax_off);
+    dv.csum = (const double*)(st->images + st->csum_off) + cls * TC_MAXCOL;
     dv.gen = gen_level_dev; dv.gen_off = gen_off;
     dv.dbg = dbg ? dbg->stamps : nullptr; dv.dbg_block = dbg ? (dbg->block & 0xFFFFFF) : 0; dv.dbg_flags = dbg ? (dbg->block >> 24) : 0;
     if (st->nstep > 8) {
@@ -1498,7 +1559,7 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
         SC_REQUIRE(gen_level_dev == nullptr, "the fused sampler is not available on the K-streamed kernel");
         const int KB = (st->nstep + 3) / 4;
         const long chunk_pts = 148L * tc::TM * 4;                     // four point tiles per SM per launch
-        const size_t per_tile = (size_t)KB * 2 * tc::A_BLK + 2 * tc::TM * sizeof(double);
+        const size_t per_tile = (size_t)KB * 2 * tc::A_BLK + 2 * tc::TM * sizeof(double) + tc::TM * sizeof(float);
         const size_t need = (size_t)cdiv(R < chunk_pts ? R : chunk_pts, tc::TM) * per_tile;
         uint8_t* scratch = nullptr;
         SC_CUDA(cudaMallocAsync((void**)&scratch, need, stream));
@@ -1509,13 +1570,14 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
             uint8_t* img = scratch;
             double* Ki = (double*)(img + (size_t)nt * KB * 2 * tc::A_BLK);
             double* sx = Ki + nt * tc::TM;
+            float* rsc = (float*)(sx + nt * tc::TM);
             const double* Xc = X + r0 * (long)gp.D;
-            tc::ks_image_kernel<<<(unsigned)nt, 256, 0, stream>>>(gp, Xc, rc, KB, dv.ymax2, img, Ki, sx);
+            tc::ks_image_kernel<<<(unsigned)nt, 256, 0, stream>>>(gp, Xc, rc, KB, dv.ymax2, img, Ki, sx, rsc);
             if (cudaGetLastError() != cudaSuccess) { rcode = ERR_CUDA; set_error("ks_image_kernel launch failed"); break; }
             double* p0 = out0 + r0; double* p1 = out1 ? out1 + r0 : nullptr; double* p2 = out2 ? out2 + r0 : nullptr; double* p3 = out3 ? out3 + r0 : nullptr;
-            if (cls == TC_U) rcode = tc::launch_ks<TC_U>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
-            else if (cls == TC_UG) rcode = tc::launch_ks<TC_UG>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
-            else rcode = tc::launch_ks<TC_PDE>(gp, dv, Xc, rc, mode, img, Ki, sx, p0, p1, p2, p3, stream);
+            if (cls == TC_U) rcode = tc::launch_ks<TC_U>(gp, dv, Xc, rc, mode, img, Ki, sx, rsc, p0, p1, p2, p3, stream);
+            else if (cls == TC_UG) rcode = tc::launch_ks<TC_UG>(gp, dv, Xc, rc, mode, img, Ki, sx, rsc, p0, p1, p2, p3, stream);
+            else rcode = tc::launch_ks<TC_PDE>(gp, dv, Xc, rc, mode, img, Ki, sx, rsc, p0, p1, p2, p3, stream);
             if (rcode != OK) break;
         }
         cudaFreeAsync(scratch, stream);

@@ -42,6 +42,7 @@ struct TcState {
     size_t desc_off[3] = {};                         // TcColDesc[TC_MAXCOL] per evaluation class
     size_t spec_off = 0;                             // TcColSpec[3][TC_MAXCOL]
     size_t ymax_off = 0;                             // one double: max_j |y_j|^2 (per-row exponent shift)
+    size_t csum_off = 0;                             // double [3][TC_MAXCOL]: column sums of the split coefficients (baseline term)
     size_t scratch_off = 0;                          // double [3][ncentres][TC_MAXCOL] + column maxima
     TcColSpec spec[3][TC_MAXCOL];                    // host copy
 };
