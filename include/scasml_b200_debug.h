@@ -28,7 +28,7 @@ SCASML_API int scasml_debug_lu_solve(double* A_dev, long long n, double* rhs_dev
 SCASML_API int scasml_debug_tc_gemm(const void* A_half_dev, const void* B_half_dev, float* D_dev, int K, int N, unsigned lbo16,
                          unsigned sbo16, unsigned layout, unsigned kstep_bytes, void* stream);
 /* SM-clock timeline of CTA `block & 0xFFFFFF` of one tcgen05 evaluation launch, experiment flags in `block >> 24`
- * (stamps_dev: 256 int64; scratch_dev: 4 R doubles) */
+ * (stamps_dev: 1024 int64; scratch_dev: 4 R doubles) */
 SCASML_API int scasml_debug_tc_timeline(const scasml_gp* gp, const double* X_dev, long long R, int mode, int block,
                              long long* stamps_dev, double* scratch_dev, void* stream);
 /* micro-benchmark: cycles per tcgen05.mma (M=128, K=16, f16) for N, `nchains` independent accumulators, A from smem (0) / TMEM (1);

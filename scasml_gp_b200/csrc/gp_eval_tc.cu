@@ -7,24 +7,25 @@
 // states and checks the algebra against the closed forms of SURVEY App. B) turns the evaluation into
 //     S = (a' x) perm_c(Y)^T          stage 1: distance GEMM, tcgen05.mma kind::f16, TS mode (A = point images in tensor memory),
 //                                     FP32 accumulators in TMEM
-//     P = 2^s ex2(S)                  epilogue warps: tcgen05.ld -> ex2 -> f16 hi/lo split -> tcgen05.st, IN PLACE over S
-//     T += P C_c                      stage 2: coefficient GEMM, A operand = P straight from tensor memory (TS mode)
-//     out_o(x_i) = K_i sum_col F_i[f1] F_i[f2] T[i, col] / scale_col        once per point (FP32 products, FP64 sums)
+//     P' = 2^s ex2(S) - 2^s           epilogue warps: tcgen05.ld -> ex2 -> f16 hi/lo split -> tcgen05.st, IN PLACE over S
+//     T += P' C_c                     stage 2: coefficient GEMM, A operand = P' straight from tensor memory (TS mode)
+//     out_o(x_i) = K_i sum_col F_i[f1] F_i[f2] (T[i, col] + 2^s sum_j C[j, col]) / scale_col     (FP32 products, FP64 sums)
 // so the per-pair work outside the tensor pipe is one TMEM load, one ex2 and three conversion/subtract instructions: both
 // measured per-pair limits of the SM (TMEM read ~16 FP32/clk, MUFU 16 ex2/clk; tools/tc_pipe_bench.py) instead of the
 // 10-45 FP32 instructions per pair of a closed-form epilogue.
 //   * centres must be float16-valued (DeepXDE float16 collocation points; checked in scasml_gp_set_centres, otherwise the
 //     route is refused): the stage-1 B operand is EXACT in f16; sampled points are split a' x = hi + lo (two f16 terms,
 //     2 MMA passes into the same accumulator);
-//   * the exponent shift s (2^6 by default, lowered per point row when a |x| max|y| would overflow f16) rides in a spare K
-//     column (A = s, B = 1) and is divided out again with K_i;
+//   * the exponent shift s (6 by default, lowered per point row when a |x| max|y| would overflow f16) is applied after ex2 and
+//     divided out again with K_i; the constant 2^s is subtracted before the coefficient GEMM because the tensor core TRUNCATES its
+//     FP32 accumulation (~0.66 ulp per MMA towards zero, tools/tc_accum_probe.py): the bias is proportional to the running sum;
 //   * P and the column-scaled coefficients are split hi + lo in f16; products hh + hl + lh accumulate into the same FP32
 //     TMEM columns over all centre tiles (relative error ~2e-7 rms, tests/test_tc_expansion.py emulates it);
-//   * one N = 128 MMA per k-step serves a PAIR of sub-items (centre tile x kernel class): the centre image rows are
+//   * one N = 96 MMA per k-step serves a PAIR of sub-items (48-centre tile x kernel class): the centre image rows are
 //     [C | rollinv(C) | roll(C)], because roll(x) . y = x . rollinv(y) needs no second A operand;
-//   * warp roles (23 warps, NTHREADS_P): 16 epilogue warps in two groups of 8 (one group per S/P slot), 1 producer warp
+//   * warp roles (23 warps, NTHREADS_P): 16 epilogue warps in two groups of 8 (group = pair parity), 1 producer warp
 //     (cp.async.bulk rings), 2 MMA-issuing warps (distance GEMMs / coefficient GEMMs; converged, one elected lane issues),
-//     4 loader warps (stage the next point tile, contract the previous one).
+//     4 loader warps (stage the next point tile, contract the finished classes of the current one); three S/P slots.
 // Accuracy: ~2e-7 relative rms on every output; parity with the FP64 route is tested under the "nocast" policy.
 // Timeline stamps and experiment flags exist only in the debug build (-DSCASML_DEBUG_HOOKS, libscasml_b200_dbg.so).
 #include <cmath>
@@ -53,8 +54,11 @@ struct TcDev {
     const uint8_t* b3;               // stage-2 coefficient images of this evaluation class
     const TcColDesc* desc;           // column table of this evaluation class
     size_t b1_tile_bytes, b3_tile_bytes;
-    int nstep, ntile_dom, ntile_bdy;
+    int nstep, ntile_dom, ntile_bdy;  // K-streamed kernel: 64-centre tiles of the padded domain / boundary sets
+    int npair_all;                   // resident-operand kernel: pairs of 48-centre tiles in the images (compact format)
+    int ntile_all;                   // resident-operand kernel: 48-centre tiles of the compact centre list (k, kx classes); ntile_dom = those of the ky class
     const double* csum;              // [TC_MAXCOL] per column: sum over the centres of the scaled, split coefficients (baseline term of the coefficient GEMM)
+    const double* pstat;             // [R][2] (|x|^2, sum_i x_i) per point, or null: the loader warps compute them (public evaluation API, fused sampler)
     const double* ymax2;             // device scalar: max_j |y_j|^2 over the centres (per-row exponent shift, row_shift())
     const LevelDev* gen;             // non-null: the loader warps GENERATE the points (fused sampler) instead of reading X
     long long gen_off;               // index of the launch's first point in the level's point buffer
@@ -152,13 +156,18 @@ __device__ __forceinline__ int tile_centre(const GpView& gp, int tile, int r, in
     return -1;
 }
 
-// pass 2a: stage-1 centre images.  Per tile, per K block: rows [C (tn) | rollinv(C) (tn) | roll(C) (tn)], f16, 128 B swizzle.
-// Columns >= D are zero (the exponent shift of a point row is applied after ex2, see row_shift()).
-__global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile_bytes, int KB, int tn, int compact) {
+// pass 2a: stage-1 centre images, f16, 128 B swizzle.  Columns >= D are zero (the exponent shift of a point row is applied after
+// ex2, see row_shift()).
+//   padded format (K-streamed kernel): per tile, per K block: rows [C (64) | rollinv(C) (64) | roll(C) (64)];
+//   compact format (resident-operand kernel): per row set v in {C, rollinv(C), roll(C)}, per PAIR of tiles, per K block: [tile 2p rows (48) |
+//   tile 2p + 1 rows (48)] -- exactly the shared-memory image of a pair's ring slot, so the producer moves a pair with ONE bulk copy (the lone
+//   producer thread needed ~1 300 cycles per pair for six copies, two waits and two expect_tx: tools/tc_timeline.py).
+__global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile_bytes, int KB, int tn, int compact, int npair_all) {
     const int tile = blockIdx.x;
     uint8_t* base = b1 + (size_t)tile * tile_bytes;
     const int D = gp.D;
     const int TN = tn;
+    const size_t pairb = (size_t)KB * 2 * TN * 128;                   // compact: bytes of a pair block
     for (int idx = threadIdx.x; idx < TN * KB * KBLK; idx += blockDim.x) {
         const int r = idx / (KB * KBLK), c = idx % (KB * KBLK);
         const int cj = tile_centre(gp, tile, r, tn, compact);
@@ -169,18 +178,27 @@ __global__ void b1_image_kernel(GpView gp, uint8_t* __restrict__ b1, size_t tile
             v1 = y[(c == 0) ? D - 1 : c - 1];            // roll(x) . y = x . rollinv(y),  rollinv(y)_c = y_{c-1}
             v2 = y[(c + 1 == D) ? 0 : c + 1];            // roll(y)_c = y_{c+1}            (models/GP.py:91-93)
         }
-        uint8_t* blk = base + (size_t)(c / KBLK) * (3 * TN * 128);
-        *(__half*)(blk + sw_off(r, c % KBLK)) = __double2half(v0);
-        *(__half*)(blk + sw_off(TN + r, c % KBLK)) = __double2half(v1);
-        *(__half*)(blk + sw_off(2 * TN + r, c % KBLK)) = __double2half(v2);
+        if (compact) {
+            uint8_t* blk = b1 + (size_t)(tile >> 1) * pairb + (size_t)(c / KBLK) * (2 * TN * 128) + (size_t)(tile & 1) * (TN * 128) + sw_off(r, c % KBLK);
+            *(__half*)(blk) = __double2half(v0);
+            *(__half*)(blk + (size_t)npair_all * pairb) = __double2half(v1);
+            *(__half*)(blk + (size_t)2 * npair_all * pairb) = __double2half(v2);
+        } else {
+            uint8_t* blk = base + (size_t)(c / KBLK) * (3 * TN * 128);
+            *(__half*)(blk + sw_off(r, c % KBLK)) = __double2half(v0);
+            *(__half*)(blk + sw_off(TN + r, c % KBLK)) = __double2half(v1);
+            *(__half*)(blk + sw_off(2 * TN + r, c % KBLK)) = __double2half(v2);
+        }
     }
 }
 
-// pass 2b: stage-2 coefficient images of one evaluation class: per tile [k hi | k lo | kx hi | kx lo | ky hi | ky lo],
-// each [ncol rows x 64 K slots] f16 of which the first tn are centres (K-major B operand, 128 B swizzle); column table with the inverse scales.
+// pass 2b: stage-2 coefficient images of one evaluation class, each [ncol rows x 64 K slots] f16 of which the first tn are centres
+// (K-major B operand, 128 B swizzle); column table with the inverse scales.
+//   padded format: per tile [k hi | k lo | kx hi | kx lo | ky hi | ky lo];
+//   compact format: per kernel class, per PAIR of tiles: [tile 2p hi | tile 2p lo | tile 2p + 1 hi | tile 2p + 1 lo] (one bulk copy per pair).
 __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, int cls, int ncentres, const double* __restrict__ coef,
                                 const unsigned long long* __restrict__ colmax, uint8_t* __restrict__ b3, size_t tile_bytes,
-                                int nk, int nkx, int nky, TcColDesc* __restrict__ desc, int tn, int compact) {
+                                int nk, int nkx, int nky, TcColDesc* __restrict__ desc, int tn, int compact, int npair_all) {
     const int tile = blockIdx.x;
     uint8_t* base = b3 + (size_t)tile * tile_bytes;
     const int ntot = nk + nkx + nky;
@@ -200,8 +218,15 @@ __global__ void b3_image_kernel(GpView gp, const TcColSpec* __restrict__ spec, i
         int n = nk;
         if (col >= nk + nkx) { row = col - nk - nkx; off = (size_t)2 * (nk + nkx) * 128; n = nky; }
         else if (col >= nk) { row = col - nk; off = (size_t)2 * nk * 128; n = nkx; }
-        *(__half*)(base + off + sw_off(row, j)) = hi;
-        *(__half*)(base + off + (size_t)n * 128 + sw_off(row, j)) = lo;
+        if (compact) {
+            // kernel-class regions in the column-table order [k | kx | ky]; `off` = 2 * 128 * (columns before this class)
+            uint8_t* blk = b3 + (size_t)npair_all * 2 * off + (size_t)(tile >> 1) * (4 * n * 128) + (size_t)(tile & 1) * (2 * n * 128);
+            *(__half*)(blk + sw_off(row, j)) = hi;
+            *(__half*)(blk + (size_t)n * 128 + sw_off(row, j)) = lo;
+        } else {
+            *(__half*)(base + off + sw_off(row, j)) = hi;
+            *(__half*)(base + off + (size_t)n * 128 + sw_off(row, j)) = lo;
+        }
         if (tile == 0 && j == 0) {
             const TcColSpec sp = spec[cls * TC_MAXCOL + col];
             TcColDesc dsc;
@@ -263,32 +288,60 @@ __global__ void __launch_bounds__(256) csum_kernel(int ncentres, const double* _
 }
 
 // ---- the fused evaluation kernel ---------------------------------------------------------------------------
-// Persistent CTAs (one per SM) loop over 128-point tiles.  Sub-item = (64-centre tile, kernel class); the sub-item stream
-//   u / u + div:  domain tile -> k, ky;      boundary tile -> k
-//   PDE:          domain tile -> k, kx, ky;  boundary tile -> k, kx
-// is consumed in PAIRS: 14 stage-1 MMAs (N = 128: both sub-items' centre rows, A = a' x hi | lo from tensor memory) into one
-// of two 128-column S slots, the epilogue warps turn S into P in place, 2 x 12 stage-2 MMAs (A = P from tensor memory) add
-// P C into T.  Pairing halves the barrier operations per MMA: every mbarrier wait / tcgen05.commit of the lone issuing
-// thread costs ~100 cycles (tools/tc_timeline.py), which bounds the kernel once the MMAs themselves are cheap.
-// Warp roles: 16 epilogue warps, 1 producer warp (cp.async.bulk rings of centre rows / coefficient images), 1 MMA warp
-// (converged, one elected lane issues), 4 loader warps (the NEXT point tile: a' x = hi + lo in f16 into the staging buffer,
-// K_i, row sums) so the operand prologue overlaps the current tile's main loop.
-// Tensor memory: S/P pair slots at columns 0 and 128; T at 256; A images (hi | lo, 64 columns apart) at 384.
+// Persistent CTAs (one per SM) loop over 128-point tiles.  Sub-item = (48-centre tile, kernel class).  The sub-item stream of a
+// point tile is CLASS-MAJOR,
+//   u / u + div:  k over all centre tiles, then ky over the domain tiles
+//   PDE:          k, then kx over all centre tiles, then ky over the domain tiles
+// so only ONE class's coefficient accumulator T (<= 48 columns) is live at a time; it is double-buffered by class epoch, and the
+// tensor-memory columns that frees hold a THIRD S/P slot.  Sub-items are consumed in PAIRS of the same class (an odd class ends in
+// a single): 14 stage-1 MMAs (N = 96: both sub-items' centre rows, A = a' x hi | lo from tensor memory) into one of three
+// 96-column S slots, one group of epilogue warps turns S into P - 2^s in place, 2 x 9 stage-2 MMAs (A = P from tensor memory)
+// add P C into T.  With two slots the period of a pair was its tensor work plus three serial hand-offs (profiles/r1_tc_timeline.md);
+// the third slot keeps stage-1 / stage-2 work of other pairs available while a pair is in its epilogue.
+// Warp roles (23 warps): 16 epilogue warps in two groups of 8 (group = pair parity; a warp converts one sub-item of its pair for one
+// lane quadrant: three 16-column chunks, the next chunk's tcgen05.ld in flight), 1 producer warp (cp.async.bulk rings: centre rows
+// three pairs deep, coefficient images two pairs deep), 2 MMA-issuing warps (distance GEMMs / coefficient GEMMs; converged, one
+// elected lane issues), 4 loader warps: stage the NEXT point tile (a' x = hi + lo in f16, K_i, row sums, exponent shift) in slices
+// and, between the slices, contract each finished class of the CURRENT tile (FP32 column products, FP64 sums).
+// Tensor memory (512 columns): S/P slots at 0 / 96 / 192; T buffers at 288 / 336; A images (hi | lo, 64 columns apart) at 384.
 template <int CLASS> struct Cfg;
 template <> struct Cfg<TC_U>   { static constexpr int NK = 16, NKX = 0,  NKY = 16; };
 template <> struct Cfg<TC_UG>  { static constexpr int NK = 16, NKX = 0,  NKY = 32; };
 template <> struct Cfg<TC_PDE> { static constexpr int NK = 48, NKX = 32, NKY = 48; };
 
+// K-streamed kernel (64-centre tiles, two 128-column slots)
 constexpr uint32_t COL_T = 256, COL_A = 384, A_IMG_COLS = 64;
 constexpr int NSLOT = 2;                                             // S/P pair slots
 constexpr uint32_t B1_BLK = TN * 128;                                // one K block of one class: [64 rows x 128 B]
-constexpr int A_PITCH = 240;                                         // staging row pitch (bytes): 16-byte reads of 8 rows hit 8 bank groups
+// resident-operand kernel (48-centre tiles, three 96-column slots)
+constexpr int TN2 = 48;                                              // centres per sub-item
+constexpr int NSLOT2 = 3;                                            // S/P pair slots
+constexpr uint32_t SLOTC = 2 * TN2;                                  // columns of a slot
+constexpr uint32_t COL_T2 = NSLOT2 * SLOTC;                          // 288: T buffers (class epoch parity), NTMAX columns each
+constexpr uint32_t NTMAX = 48;
+constexpr uint32_t B1_BLK2 = TN2 * 128;                              // one K block of one class: [48 rows x 128 B]
+constexpr int NB1_MAX = 6;                                           // centre-row ring depth (pairs): Ring<>::NB1 <= NB1_MAX
+// coefficient-image ring depth (pairs).  A slot is refilled only after stage 2 of its previous pair COMPLETED, and a bulk copy out of
+// L2 takes ~1 000 cycles to land: with two slots the coefficient GEMM of pair p waited for its images whenever the pair period fell
+// below ~1 600 cycles (tools/tc_timeline.py: the stage-2 issuer never waited for P, yet needed 1 300 - 1 600 cycles per pair)
+template <int CLASS, int NSTEP, bool GEN> struct Ring {
+    static constexpr int NB3 = (CLASS == TC_PDE) ? ((GEN || NSTEP == 8) ? 2 : 3) : (CLASS == TC_UG ? 2 : 4);
+    static constexpr int NB1 = (CLASS == TC_PDE || GEN) ? 3 : 4;
+};
+// staging row pitch (bytes): the row's f16 image + 16, an odd multiple of 16, so that 16-byte reads of 8 rows hit 8 bank groups
+template <int NSTEP> struct Stage { static constexpr int PITCH = NSTEP * 32 + 16; };
 constexpr int NLOAD = 4;                                             // loader warps
-constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 1) * 32;             // epilogue | producer | stage-1 issuer | loaders | stage-2 issuer
-constexpr int NB1_MAX = 4;                                           // centre-row ring (decoupled from the S/P slots: the bulk-copy latency
-                                                                     // of pair j + 2 must not wait for stage 1 of pair j)
-// barriers: b1_full b1_empty (NB1_MAX each) | b3_full b3_empty s_full p_ready s2_issued (NSLOT each) | t_full[2] t_free[2] a_ready stage_full stage_free
-constexpr int NBAR = 2 * NB1_MAX + 5 * NSLOT + 7;
+constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 3) * 32;             // loaders | epilogue | producer | stage-1 issuer 0 | stage-2 issuer 0 | stage-1 issuer 1 | stage-2 issuer 1
+// The loader warps take the LOWEST warp ids: the warp scheduler favours them, and their background work (staging the next point tile,
+// contracting finished classes) otherwise crawled behind the epilogue warps of its scheduler and set the tile period.  Epilogue warp e
+// (0..15) = warp W_EPI0 + e; W_EPI0 is a multiple of 4, so warp % 4 is still the tensor-memory lane quadrant of every loader / epilogue warp.
+constexpr int W_LOAD0 = 0, W_EPI0 = NLOAD, W_PROD = W_EPI0 + NEPI, W_S1A = W_PROD + 1, W_S2A = W_PROD + 2, W_S1B = W_PROD + 3, W_S2B = W_PROD + 4;
+static_assert(W_EPI0 % 4 == 0, "lane quadrant = warp % 4");
+constexpr int MAX_PAIRS = 1024;                                      // pair table entries (16 bits each): kernel class | two | first | last | centre tile
+// barriers: b1_full b1_empty (NB1 each) | b3_full b3_empty (NB3 <= 4 each) | s_full p_ready slot_free (NSLOT2 each) | t_full[2] t_free[2] | a_ready stage_full stage_free | ord[2]
+constexpr int NB3_MAX = 4;
+constexpr int NBAR = 2 * NB1_MAX + 2 * NB3_MAX + 3 * NSLOT2 + 4 + 3 + 2;   // + ord[2]: stage-2 issue order hand-off between the two stage-2 issuers
+static_assert(COL_T2 + 2 * NTMAX == COL_A && COL_A + 2 * A_IMG_COLS == 512, "tensor-memory map");
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -304,6 +357,19 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
 }
+
+// class list of an evaluation class (class-major sub-item stream): kernel class, coefficient columns, first column in the
+// column table [k | kx | ky], byte offset of its images inside a tile's coefficient-image record
+template <int CLASS> struct ClsList {
+    using C = Cfg<CLASS>;
+    static constexpr int NCLS = (CLASS == TC_PDE) ? 3 : 2;
+    __device__ __forceinline__ static int kern(int ci) { return (CLASS == TC_PDE) ? (ci == 0 ? TK_K : (ci == 1 ? TK_KX : TK_KY)) : (ci == 0 ? TK_K : TK_KY); }
+    __device__ __forceinline__ static int ncol(int kc) { return kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY); }
+    __device__ __forceinline__ static int coloff(int kc) { return kc == TK_K ? 0 : (kc == TK_KX ? C::NK : C::NK + C::NKX); }
+    __device__ __forceinline__ static uint32_t b3off(int kc) { return 2u * 128u * (uint32_t)coloff(kc); }
+    __device__ __forceinline__ static uint32_t b1row(int kc) { return kc == TK_K ? 0u : (kc == TK_KX ? 1u : 2u); }   // rows [C | Crollinv | Croll]
+};
+
 
 // ---- fused sampler -----------------------------------------------------------------------------------------------------------
 // Same arithmetic, operation order and Philox addressing as picard.cu::sample_terminal_kernel / sample_paths_kernel (the
@@ -429,81 +495,81 @@ __device__ __forceinline__ void gen_point(const LevelDev& lv, const GenRec& g, l
     }
 }
 
+
 template <int CLASS, int NSTEP, bool GEN>
 __global__ void __launch_bounds__(NTHREADS_P, 1)
 eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode,
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
     using C = Cfg<CLASS>;
-    constexpr bool PDE = (CLASS == TC_PDE);
+    using CL = ClsList<CLASS>;
+    constexpr int NCLS = CL::NCLS;
     constexpr int KB = (NSTEP + 3) / 4;                              // 64-wide K blocks
-    constexpr int NT = C::NK + C::NKX + C::NKY;                      // T columns: [k | kx | ky]
+    constexpr int NT = C::NK + C::NKX + C::NKY;                      // columns of the column table: [k | kx | ky]
     constexpr int NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    constexpr uint32_t B3_SUB = 2 * NMAX * 128;                      // one class's coefficient images (hi | lo)
+    constexpr uint32_t B3_SUB = 2 * NMAX * 128;                      // one sub-item's coefficient images (hi | lo)
     constexpr uint32_t B3_SLOT = 2 * B3_SUB;                         // a pair
-    constexpr uint32_t B1_SLOT = KB * 2 * B1_BLK;                    // a pair's centre rows: per K block [sub-item a rows | sub-item b rows]
-    constexpr int NB1 = (PDE && GEN) ? 2 : 3;                        // centre-row ring depth (shared-memory budget)
+    constexpr uint32_t B1_SLOT = KB * 2 * B1_BLK2;                   // a pair's centre rows: per K block [sub-item a rows | sub-item b rows]
+    constexpr int NB3 = Ring<CLASS, NSTEP, GEN>::NB3, NB1 = Ring<CLASS, NSTEP, GEN>::NB1;
+    constexpr int A_PITCH = Stage<NSTEP>::PITCH;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
     uint8_t* sB1 = smem;                                             // NB1 pair slots
-    uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NSLOT pair slots
-    uint8_t* sStage = sB3 + NSLOT * (size_t)B3_SLOT;                 // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
-    float* feat = (float*)(sStage + 2 * (size_t)TM * A_PITCH);       // [128][TF_COUNT] features (floats) of the tile being finalised
-    // column table of the final contraction, in the form its inner loop wants: per column the byte offsets of its two features in a
-    // row's float feature vector (f1 | f2 << 16) and its scale 1 / (2^s 2^TC_P_SHIFT) spread over the four outputs as a one-hot float4
-    // (the contraction is issue-bound: 44 instructions per column with byte extraction, an output-change test and a select chain per
-    // column became ~14 with this layout, tools/tc_timeline.py)
+    uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NB3 pair slots
+    uint8_t* sStage = sB3 + NB3 * (size_t)B3_SLOT;                   // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
+    float* feat = (float*)(sStage + 2 * (size_t)TM * A_PITCH);       // [128][TF_COUNT] features (floats) of the tile being contracted
+    // column table of the contraction, in the form its inner loop wants: per column the byte offsets of its two features in a
+    // row's float feature vector (f1 | f2 << 16), its scale 1 / (2^s 2^TC_P_SHIFT) spread over the four outputs as a one-hot float4
+    // (the contraction is issue-bound) and the column sum of its coefficients as (hi, lo) floats (baseline term)
     float4* smask = (float4*)(feat + TM * TF_COUNT);                 // [TC_MAXCOL]
     uint32_t* soff = (uint32_t*)(smask + TC_MAXCOL);                 // [TC_MAXCOL]
-    GenRec* grec = (GenRec*)(soff + TC_MAXCOL);                      // [128] fused sampler: resolved points of the tile being staged
-    double* Ki = (double*)(grec + (GEN ? TM : 0));                       // [128] exp(-a |x|^2 / 2) of the staged tile
+    float2* scs = (float2*)(soff + TC_MAXCOL);                       // [TC_MAXCOL]
+    double* acc4 = (double*)(scs + TC_MAXCOL);                       // [128][4] output sums (u, div, lap, dt) of the tile being contracted, across its classes
+    GenRec* grec = (GenRec*)(acc4 + TM * 4);                         // [128] fused sampler: resolved points of the tile being staged
+    double* Ki = (double*)(grec + (GEN ? TM : 0));                   // [128] |x|^2 of the staged tile
     double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
-    float* rsc = (float*)(sxs + TM);                                 // [2][128] 2^s of the point rows, by tile parity (epilogue: P = 2^s ex2(S) - 2^s)
-    float2* scs = (float2*)(rsc + 2 * TM);                           // [TC_MAXCOL] column sums of the coefficients as (hi, lo) floats
-    uint64_t* bars = (uint64_t*)(scs + TC_MAXCOL);
+    float* rsc = (float*)(sxs + TM);                                 // [2][128] 2^s of the point rows, by tile parity (epilogue: P - 2^s = 2^s ex2(S) - 2^s)
+    uint64_t* bars = (uint64_t*)(rsc + 2 * TM);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
+    uint16_t* ptab = (uint16_t*)(tmem_slot + 4);                     // [npair] pairs of the class-major stream of one point tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = gp.D, d = gp.d;
     const long ntiles = (R + TM - 1) / TM;
     const int nit = (int)((ntiles - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x);   // point tiles of this CTA
-    long long* const dbg = (DBG && st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;   // stamps: first tile of that CTA
-    const int dflags = DBG ? st.dbg_flags : 0;                        // experiment switches (debug build only)
+    long long* const dbg = (DBG && st.dbg != nullptr && (int)blockIdx.x == st.dbg_block) ? st.dbg : nullptr;   // stamps: second tile of that CTA
+    const int dflags = DBG ? st.dbg_flags : 0;                        // experiment switches (debug build only): 1 no stage-2 MMAs, 2 no epilogue arithmetic
 #define TC_STAMP(slot) do { if (DBG && dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
     const uint32_t bar0 = smem_u32(bars);
     auto b1_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     auto b1_empty = [&](int i) { return bar0 + 8u * (uint32_t)(NB1_MAX + i); };
     auto b3_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + i); };
-    auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + NSLOT + i); };
-    auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NSLOT + i); };
-    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 3 * NSLOT + i); };
-    auto s2_issued = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 4 * NSLOT + i); };
-    const uint32_t t_full0 = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 5 * NSLOT), t_free0 = t_full0 + 16u, a_ready = t_full0 + 32u,
-                   stage_full = t_full0 + 40u, stage_free = t_full0 + 48u;
-    // T accumulators: double-buffered by point-tile parity where tensor memory has room (u, u + div classes), so the final
-    // contraction of tile it - 1 (loader warps) never holds up stage 2 of tile it.  One barrier pair per buffer: a waiter is
-    // never more than one phase behind.
-    constexpr bool TDBL = (2 * NT <= (int)(COL_A - COL_T));
-    auto t_buf = [&](int tile) { return TDBL ? (tile & 1) : 0; };
-    auto t_cnt = [&](int tile) { return TDBL ? (tile >> 1) : tile; };      // completion index on that buffer's barriers
-    auto t_full = [&](int tile) { return t_full0 + 8u * (uint32_t)t_buf(tile); };
-    auto t_free = [&](int tile) { return t_free0 + 8u * (uint32_t)t_buf(tile); };
+    auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + NB3_MAX + i); };
+    auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + i); };
+    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSLOT2 + i); };
+    auto slot_free = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + 2 * NSLOT2 + i); };
+    const uint32_t t_full0 = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + 3 * NSLOT2), t_free0 = t_full0 + 16u, a_ready = t_full0 + 32u,
+                   stage_full = t_full0 + 40u, stage_free = t_full0 + 48u, ord0 = t_full0 + 56u;
+    // T accumulators: one per class epoch e = tile * NCLS + class, double-buffered by epoch parity.  One barrier pair per buffer: a
+    // waiter is never more than one phase behind.
+    auto t_full = [&](int e) { return t_full0 + 8u * (uint32_t)(e & 1); };
+    auto t_free = [&](int e) { return t_free0 + 8u * (uint32_t)(e & 1); };
 
     if (tid == 0) {
-        for (int i = 0; i < NB1_MAX; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
-        for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(s2_issued(i), 1);
-        }
+        for (int i = 0; i < NB1; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
+        for (int i = 0; i < NB3; ++i) { mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); }
+        for (int i = 0; i < NSLOT2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(slot_free(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, NLOAD); }
         mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
+        mbar_init(ord0, 1); mbar_init(ord0 + 8u, 1);
         fence_barrier_init();
     }
-    if (warp == NEPI + 1) tmem_alloc(smem_u32(tmem_slot), 512);
-    for (int c = tid; c < TC_MAXCOL; c += NTHREADS_P) {              // column table -> shared memory (read by every final contraction)
+    if (warp == W_S1A) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int c = tid; c < TC_MAXCOL; c += NTHREADS_P) {              // column table -> shared memory (read by every contraction)
         const TcColDesc dsc = st.desc[c < NT ? c : 0];
-        const bool dead = (c >= NT || dsc.out == TO_PAD || (st.ntile_dom == 0 && c >= C::NK + C::NKX));
+        const bool dead = (c >= NT || dsc.out == TO_PAD);
         const float sc = dead ? 0.0f : (float)dsc.inv_scale;        // a power of two: exact in FP32 (range checked when the images are built)
         soff[c] = dead ? 0u : ((uint32_t)dsc.f1 * 4u) | (((uint32_t)dsc.f2 * 4u) << 16);
         smask[c] = make_float4(dsc.out == TO_U ? sc : 0.0f, dsc.out == TO_G ? sc : 0.0f, dsc.out == TO_L ? sc : 0.0f, dsc.out == TO_T ? sc : 0.0f);
@@ -515,194 +581,201 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     __syncthreads();                                                 // TMEM base address + barriers + column table visible
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    const int ndom = st.ntile_dom, nbdy = st.ntile_bdy;
-    constexpr int CPD = PDE ? 3 : 2;                                 // kernel classes of a domain tile
-    const int nitem = CPD * ndom + (CPD - 1) * nbdy;                 // sub-items per point tile
-    const int npair = (nitem + 1) >> 1;
-    // (tile, class) successor.  Class order inside a centre tile: k, (kx,) ky; boundary tiles have no ky class.
-    auto next_item = [&](int& t, int& kc) {
-        if (kc == TK_K) kc = PDE ? TK_KX : (t < ndom ? TK_KY : TK_K);
-        else if (kc == TK_KX) kc = (t < ndom) ? TK_KY : TK_K;
-        else kc = TK_K;
-        if (kc == TK_K) ++t;
-    };
+    const int nt_all = st.ntile_all, nt_dom = st.ntile_dom;          // 48-centre tiles of the k / kx classes and of the ky class
+    auto ntile_of = [&](int ci) { return CL::kern(ci) == TK_KY ? nt_dom : nt_all; };
+    int npair = 0;
+    for (int ci = 0; ci < NCLS; ++ci) npair += (ntile_of(ci) + 1) >> 1;   // pairs per point tile (an odd class ends in a single)
+    // pair table (every role walks the same stream; the issuing threads run alone, so their bookkeeping is one shared-memory load):
+    // bits 0-1 kernel class, 2 two sub-items, 3 first pair of its class, 4 last pair of its class, 5.. centre tile of the first sub-item
+    if (tid == 0) {
+        int n = 0;
+        for (int ci = 0; ci < NCLS; ++ci) {
+            const int nt = ntile_of(ci);
+            for (int t = 0; t < nt; t += 2)
+                ptab[n++] = (uint16_t)(CL::kern(ci) | ((t + 1 < nt) ? 4 : 0) | (t == 0 ? 8 : 0) | ((t + 2 >= nt) ? 16 : 0) | (t << 5));
+        }
+    }
+    __syncthreads();
+#define PT_KERN(e) ((int)((e) & 3u))
+#define PT_TWO(e) (((e) & 4u) != 0u)
+#define PT_FIRST(e) (((e) & 8u) != 0u)
+#define PT_LAST(e) (((e) & 16u) != 0u)
+#define PT_TILE(e) ((int)((e) >> 5))
 
-    if (warp == NEPI) {
-        // ===== producer: per item, the class's centre rows (all K blocks) and its coefficient images.  The item stream
-        // simply repeats for every point tile, so the rings run across tile boundaries.  A centre-row slot is reusable once
-        // s_full of its previous item fired (stage 1 done), a coefficient slot once the MMA warp committed b3_empty. =====
-        if (lane == 0 && !(dflags & 8)) {
+    if (warp == W_PROD) {
+        // ===== producer: per pair, its sub-items' centre rows (all K blocks) and coefficient images.  The pair stream simply
+        // repeats for every point tile, so the rings run across tile boundaries.  A centre-row slot is reusable once stage 1 of its
+        // previous pair completed (b1_empty), a coefficient slot once stage 2 of its previous pair completed (b3_empty). =====
+        if (lane == 0) {
             const int ptotal = nit * npair;
-            int t1 = 0, k1 = TK_K, j1 = 0, t3 = 0, k3 = TK_K, j3 = 0;    // sub-item cursors / pair index inside the point tile
-            int p1 = 0;
+            int p1 = 0, j1 = 0, j3 = 0;
             auto load_b1 = [&]() {
                 const int s = p1 % NB1;
                 if (p1 >= NB1) mbar_wait(b1_empty(s), (uint32_t)((p1 / NB1) - 1) & 1u);
-                const bool two = 2 * j1 + 1 < nitem;
-                mbar_expect_tx(b1_full(s), (two ? 2u : 1u) * KB * B1_BLK);
-                uint8_t* dst = sB1 + (size_t)s * B1_SLOT;
-                for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
-                    const uint8_t* src = st.b1 + (size_t)t1 * st.b1_tile_bytes
-                                       + (size_t)(k1 == TK_K ? 0 : (k1 == TK_KX ? 1 : 2)) * B1_BLK;   // rows [C | Crollinv | Croll]
-#pragma unroll
-                    for (int kb = 0; kb < KB; ++kb)
-                        bulk_g2s(smem_u32(dst + (size_t)kb * 2 * B1_BLK + (size_t)sub * B1_BLK), src + (size_t)kb * (3 * B1_BLK), B1_BLK, b1_full(s));
-                    next_item(t1, k1);
-                }
-                if (++j1 == npair) { j1 = 0; t1 = 0; k1 = TK_K; }
+                const uint32_t e = ptab[j1];
+                const int kc = PT_KERN(e), t0 = PT_TILE(e);
+                const bool two = PT_TWO(e);
+                if (++j1 == npair) j1 = 0;
+                // one bulk copy per pair: the image holds a pair's slot layout [K block][sub-item][48 rows x 128 B] contiguously (a single's second
+                // half is zero padding in the image)
+                (void)two;
+                mbar_expect_tx(b1_full(s), B1_SLOT);
+                bulk_g2s(smem_u32(sB1 + (size_t)s * B1_SLOT), st.b1 + ((size_t)CL::b1row(kc) * st.npair_all + (size_t)(t0 >> 1)) * B1_SLOT, B1_SLOT, b1_full(s));
                 ++p1;
             };
             for (int p = 0; p < ptotal; ++p) {
                 while (p1 < ptotal && p1 < p + NB1) load_b1();               // centre rows run NB1 - 1 pairs ahead of the coefficient images
-                const int s = p % NSLOT;
-                if (p >= NSLOT) mbar_wait(b3_empty(s), (uint32_t)((p / NSLOT) - 1) & 1u);
-                const bool two = 2 * j3 + 1 < nitem;
-                uint32_t off[2], bytes[2];
-                int tt[2];
-                for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
-                    off[sub] = k3 == TK_K ? 0u : (k3 == TK_KX ? 2u * C::NK * 128u : 2u * (C::NK + C::NKX) * 128u);
-                    bytes[sub] = 2u * 128u * (uint32_t)(k3 == TK_K ? C::NK : (k3 == TK_KX ? C::NKX : C::NKY));
-                    tt[sub] = t3;
-                    next_item(t3, k3);
-                }
-                mbar_expect_tx(b3_full(s), bytes[0] + (two ? bytes[1] : 0u));
-                for (int sub = 0; sub < (two ? 2 : 1); ++sub)
-                    bulk_g2s(smem_u32(sB3 + (size_t)s * B3_SLOT + (size_t)sub * B3_SUB), st.b3 + (size_t)tt[sub] * st.b3_tile_bytes + off[sub],
-                             bytes[sub], b3_full(s));
-                if (++j3 == npair) { j3 = 0; t3 = 0; k3 = TK_K; }
+                const int q = p % NB3;
+                if (p >= NB3) mbar_wait(b3_empty(q), (uint32_t)((p / NB3) - 1) & 1u);
+                const uint32_t e = ptab[j3];
+                const int kc = PT_KERN(e), t0 = PT_TILE(e);
+                const bool two = PT_TWO(e);
+                if (++j3 == npair) j3 = 0;
+                // one bulk copy per pair: [sub-item][hi | lo][ncol rows x 128 B]
+                (void)two;
+                const uint32_t bytes = 4u * 128u * (uint32_t)CL::ncol(kc);
+                mbar_expect_tx(b3_full(q), bytes);
+                bulk_g2s(smem_u32(sB3 + (size_t)q * B3_SLOT), st.b3 + (size_t)st.npair_all * 2 * CL::b3off(kc) + (size_t)(t0 >> 1) * bytes, bytes, b3_full(q));
             }
         }
         __syncwarp();
-    } else if (warp == NEPI + 1) {
-        // ===== stage-1 issuer.  The MMA queue is shallow (the issuing thread is blocked until its MMAs are almost done) and every
-        // barrier operation of a lone thread costs ~100 cycles, so with ONE issuer the tensor pipe drains during the commits /
-        // waits between batches (~700 cycles per pair, tools/tc_timeline.py).  Two issuers -- this warp for the distance GEMMs,
-        // warp NEPI + 2 + NLOAD for the coefficient GEMMs -- keep it fed: while one does its housekeeping the other one issues.
-        // Each warp stays converged and one elected lane issues (warp-uniform operands come from uniform registers). =====
+    } else if (warp == W_S1A || warp == W_S1B) {
+        // ===== stage-1 issuers (distance GEMMs), one for the even and one for the odd pairs.  tcgen05.mma is issued by one thread, the
+        // MMA queue is only a few entries deep and every barrier operation of a lone thread costs 100 - 400 cycles: with one issuer per
+        // stage each needed ~1 500 cycles per pair (waits 560, issue 530, commits 360: tools/tc_timeline.py) and the tensor pipe
+        // (~1 200 cycles of work per pair) ran dry while both were between batches.  With two issuers per stage one of them is issuing
+        // while the other one waits / commits.  Pairs of different parity write different S slots: no order between the two is needed.
+        // The warp stays converged and one elected lane issues. =====
+        const int w = (warp == W_S1A) ? 0 : 1;
         const uint32_t el = elect_one();
         const uint64_t b1desc0 = make_desc(smem_u32(sB1), 1, 64, 2);
-        const uint32_t idS2 = make_idesc(TM, 2 * TN), idS1 = make_idesc(TM, TN);
+        const uint32_t idS2 = make_idesc(TM, 2 * TN2), idS1 = make_idesc(TM, TN2);
         const uint32_t aBase = tmem_base + COL_A;
-        const bool nocopy = (dflags & 8) != 0;
-        int p1 = 0;                                                  // global pair counter
-        bool rdy1 = false;                                           // early probe result for the next batch's centre rows
+        int p = 0;                                                   // global pair counter
         for (int it = 0; it < nit; ++it) {
             const bool stamp = (it == 1);
-            if (el && it == 1) TC_STAMP(244);
+            if (el && it == 1 && w == 0) TC_STAMP(244);
             mbar_wait(a_ready, (uint32_t)it & 1u);                   // A images of this point tile are in tensor memory
             tc_fence_after();
-            for (int j = 0; j < npair; ++j) {
-                const int s = p1 % NSLOT, s1 = p1 % NB1;
-                const uint32_t accS = tmem_base + (uint32_t)s * 128u;
-                const uint32_t idesc = (2 * j + 1 < nitem) ? idS2 : idS1;
+            for (int j = 0; j < npair; ++j, ++p) {
+                if ((p & 1) != w) continue;
+                const int s = p % NSLOT2, s1 = p % NB1;
+                const uint32_t accS = tmem_base + (uint32_t)s * SLOTC;
+                const uint32_t idesc = PT_TWO(ptab[j]) ? idS2 : idS1;
                 if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
-                // the slot's previous P has been consumed: stage 2 of pair p1 - NSLOT (issued by the other warp) has COMPLETED (handing the
-                // slot back as soon as those MMAs are issued -- tcgen05.mma executes in issue order -- measured no faster)
-                // (suspending wait: with two epilogue groups the issue slots a spinning warp takes cost more than its faster wake-up gains; flag 64 = spin)
-                if (p1 >= NSLOT) { if (dflags & 64) mbar_spin(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); else mbar_wait(b3_empty(s), (uint32_t)((p1 / NSLOT) - 1) & 1u); tc_fence_after(); }
-                if (!rdy1 && !nocopy) mbar_wait(b1_full(s1), (uint32_t)(p1 / NB1) & 1u);   // bulk-copy bytes landed (async proxy)
+                // the slot's previous P has been consumed: stage 2 of pair p - NSLOT2 has COMPLETED
+                if (p >= NSLOT2) { mbar_wait(slot_free(s), (uint32_t)((p / NSLOT2) - 1) & 1u); tc_fence_after(); }
+                if (el && stamp && j < 60) TC_STAMP(256 + 8 * j);
+                mbar_wait(b1_full(s1), (uint32_t)(p / NB1) & 1u);    // bulk-copy bytes landed (async proxy)
+                if (el && stamp && j < 60) TC_STAMP(257 + 8 * j);
                 const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
-                ++p1;
-                rdy1 = false;
+                if (el) {
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
+                    for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-                    for (int half = 1; half >= 0; --half) {          // low halves first (tiny terms), then the high halves
-                        if (el) {
+                        for (int half = 1; half >= 0; --half) {      // low halves first (tiny terms), then the high halves
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 if (kb * 4 + ks < NSTEP) {
                                     const uint32_t aa = aBase + (uint32_t)half * A_IMG_COLS + (uint32_t)(kb * 4 + ks) * 8u;
-                                    const uint64_t bd = bb + (uint64_t)((kb * 2 * B1_BLK + ks * 32) >> 4);
+                                    const uint64_t bd = bb + (uint64_t)((kb * 2 * B1_BLK2 + ks * 32) >> 4);
                                     if (kb == 0 && half == 1 && ks == 0) umma_ts<false>(accS, aa, bd, idesc);
                                     else umma_ts<true>(accS, aa, bd, idesc);
                                 }
                             }
                         }
-                        if (kb == 0 && half == 1 && !nocopy && (j + 1 < npair || it + 1 < nit))      // probe the next batch's centre rows
-                            rdy1 = mbar_test_wait(b1_full(p1 % NB1), (uint32_t)(p1 / NB1) & 1u);
                     }
                 }
+                if (el && stamp && j < 60) TC_STAMP(258 + 8 * j);
                 if (el) { umma_commit(b1_empty(s1)); umma_commit(s_full(s)); }   // centre-row slot reusable; accumulators ready
+                if (el && stamp && j < 60) TC_STAMP(259 + 8 * j);
                 __syncwarp();
             }
         }
-    } else if (warp == NEPI + 2 + NLOAD) {
-        // ===== stage-2 issuer: T += P C for every sub-item of a pair, in pair order (deterministic accumulation order) =====
+    } else if (warp == W_S2A || warp == W_S2B) {
+        // ===== stage-2 issuers: T += (P - 2^s) C for the sub-items of a pair; per 16 centres the three split products hh + hl + lh.
+        // Even / odd pairs alternate between the two issuers; the accumulation into T keeps the stream order (deterministic results,
+        // and the class's first MMA, which overwrites T, stays first): an issuer starts issuing pair p only after the other one has
+        // issued pair p - 1 (ord barriers; tcgen05.mma executes in issue order). =====
+        const int w = (warp == W_S2A) ? 0 : 1;
         const uint32_t el = elect_one();
         const uint64_t b3desc0 = make_desc(smem_u32(sB3), 1, 64, 2);
-        const uint32_t idK = make_idesc(TM, C::NK), idKY = make_idesc(TM, C::NKY), idKX = make_idesc(TM, C::NKX > 0 ? C::NKX : 16);
-        const bool nocopy = (dflags & 8) != 0;
-        int p2 = 0;
+        const uint32_t ord_mine = ord0 + 8u * (uint32_t)w, ord_other = ord0 + 8u * (uint32_t)(1 - w);
+        int p = 0, epoch = 0;                                        // global pair counter; class epochs started
         for (int it = 0; it < nit; ++it) {
             const bool stamp = (it == 1);
-            bool first_k = true, first_kx = true, first_ky = true;
-            int kc2 = TK_K, t2 = 0;                                  // (tile, class) of the next sub-item
-            for (int j = 0; j < npair; ++j) {
-                const int s = p2 % NSLOT;
-                {   // P written over S by all epilogue warps + coefficient images landed: one polling loop for both barriers
-                    const uint32_t par = (uint32_t)(p2 / NSLOT) & 1u;
-                    uint32_t spins = 0;
-                    bool a = false, b = nocopy;
-                    if (!(dflags & 64)) { mbar_wait(p_ready(s), par); if (!b) mbar_wait(b3_full(s), par); a = b = true; }   // suspending waits (flag 64: poll both barriers in a spin loop)
-                    while (!(a && b)) {
-                        if (!a) a = mbar_test_wait(p_ready(s), par);
-                        if (!b) b = mbar_test_wait(b3_full(s), par);
-                        if (a && b) break;
-                        if (++spins > SPIN_LIMIT) { asm volatile("trap;"); }
-                    }
-                }
-                // the T buffer of this tile has been read by the final contraction of the tile that used it last
-                if (j == 0 && it >= (TDBL ? 2 : 1)) mbar_wait(t_free(it), (uint32_t)(t_cnt(it) - 1) & 1u);
-                tc_fence_after();
-                ++p2;
-                const int nsub = (2 * j + 1 < nitem) ? 2 : 1;
-                for (int sub = 0; sub < nsub; ++sub) {
-                    const uint32_t pbase = tmem_base + (uint32_t)s * 128u + (uint32_t)sub * 64u;
-                    const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)s * B3_SLOT + (uint32_t)sub * B3_SUB) >> 4);
-                    const int kc = kc2;
-                    const uint32_t tacc = tmem_base + COL_T + (uint32_t)(t_buf(it) * NT) + (kc == TK_K ? 0u : (kc == TK_KX ? (uint32_t)C::NK : (uint32_t)(C::NK + C::NKX)));
-                    const uint32_t nrows = kc == TK_K ? C::NK : (kc == TK_KX ? C::NKX : C::NKY);
-                    const uint32_t idesc = kc == TK_K ? idK : (kc == TK_KX ? idKX : idKY);
-                    const bool first = kc == TK_K ? first_k : (kc == TK_KX ? first_kx : first_ky);
-                    const uint64_t clo0 = b3 + (uint64_t)((nrows * 128) >> 4);
+            for (int j = 0; j < npair; ++j, ++p) {
+                const uint32_t e = ptab[j];
+                if ((p & 1) == w) {
+                    const int s = p % NSLOT2, q = p % NB3;
+                    const int kc = PT_KERN(e);
+                    const bool two = PT_TWO(e), first = PT_FIRST(e);
+                    // P written over S by the pair's epilogue group + coefficient images landed
+                    mbar_wait(p_ready(s), (uint32_t)(p / NSLOT2) & 1u);
+                    if (el && stamp && j < 60) TC_STAMP(260 + 8 * j);
+                    mbar_wait(b3_full(q), (uint32_t)(p / NB3) & 1u);
+                    if (el && stamp && j < 60) TC_STAMP(261 + 8 * j);
+                    // first pair of a class: its T buffer has been contracted by the loader warps (class epoch - 2)
+                    if (first && epoch >= 2) mbar_wait(t_free(epoch), (uint32_t)((epoch >> 1) - 1) & 1u);
+                    // the other issuer has issued pair p - 1
+                    if (p >= 1) mbar_wait(ord_mine, (uint32_t)(w == 1 ? (p >> 1) : ((p >> 1) - 1)) & 1u);
+                    tc_fence_after();
+                    const uint32_t ncol = (uint32_t)CL::ncol(kc);
+                    const uint32_t idesc = make_idesc(TM, (int)ncol);
+                    const uint32_t tacc = tmem_base + COL_T2 + (uint32_t)(epoch & 1) * NTMAX;
                     if (el && !(dflags & 1)) {
-                        const bool only_hh = (dflags & 32) != 0;   // timeline experiment: 4 instead of 12 MMAs (wrong results)
-                        if (first) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
-                        if (!only_hh) {
-                            umma_ts<true>(tacc, pbase, clo0, idesc);
-                            umma_ts<true>(tacc, pbase + 8u, b3, idesc);
-                        }
-#pragma unroll
-                        for (int ks = 1; ks < 4; ++ks) {
-                            umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                        // timeline experiments (debug build, wrong results): 32 = hh products only; 128 = hl / lh products into the other T buffer
+                        // (two accumulation chains instead of one)
+                        const bool only_hh = (dflags & 32) != 0;
+                        const uint32_t tacc2 = (dflags & 128) ? (tmem_base + COL_T2 + (uint32_t)((epoch + 1) & 1) * NTMAX) : tacc;
+#pragma unroll 1
+                        for (int sub = 0; sub < (two ? 2 : 1); ++sub) {
+                            const uint32_t pbase = tmem_base + (uint32_t)s * SLOTC + (uint32_t)sub * TN2;
+                            const uint64_t b3 = b3desc0 + (uint64_t)(((uint32_t)q * B3_SLOT + (uint32_t)sub * (2u * ncol * 128u)) >> 4);
+                            const uint64_t clo0 = b3 + (uint64_t)((ncol * 128u) >> 4);
+                            if (first && sub == 0) umma_ts<false>(tacc, pbase, b3, idesc); else umma_ts<true>(tacc, pbase, b3, idesc);
                             if (!only_hh) {
-                                umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
-                                umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                                umma_ts<true>(tacc2, pbase, clo0, idesc);
+                                umma_ts<true>(tacc2, pbase + 8u, b3, idesc);
+                            }
+#pragma unroll
+                            for (int ks = 1; ks < TN2 / 16; ++ks) {
+                                umma_ts<true>(tacc, pbase + (uint32_t)ks * 16u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                                if (!only_hh) {
+                                    umma_ts<true>(tacc2, pbase + (uint32_t)ks * 16u, clo0 + (uint64_t)((ks * 32) >> 4), idesc);
+                                    umma_ts<true>(tacc2, pbase + (uint32_t)ks * 16u + 8u, b3 + (uint64_t)((ks * 32) >> 4), idesc);
+                                }
                             }
                         }
                     }
-                    if (kc == TK_K) first_k = false; else if (kc == TK_KX) first_kx = false; else first_ky = false;
-                    next_item(t2, kc2);
+                    if (el && stamp && j < 60) TC_STAMP(262 + 8 * j);
+                    if (el) {
+                        mbar_arrive(ord_other);                       // the other issuer may issue pair p + 1
+                        umma_commit(b3_empty(q));                     // coefficient slot reusable (producer)
+                        umma_commit(slot_free(s));                    // P consumed (stage-1 issuers)
+                        if (PT_LAST(e)) umma_commit(t_full(epoch));   // the class's T is complete (loader warps)
+                        if (stamp && j < 60) TC_STAMP(5 + 4 * j);
+                    }
+                    __syncwarp();
                 }
-                if (el) { umma_commit(b3_empty(s)); if (stamp && j < 60) TC_STAMP(5 + 4 * j); }   // P consumed (stage-1 issuer, producer)
-                __syncwarp();
+                if (PT_LAST(e)) ++epoch;
             }
-            if (el) umma_commit(t_full(it));
-            if (el && it == 0) TC_STAMP(248);
-            __syncwarp();
+            if (el && it == 0 && w == 0) TC_STAMP(248);
         }
-    } else if (warp >= NEPI + 2 && warp < NEPI + 2 + NLOAD) {
+    } else if (warp >= W_LOAD0 && warp < W_LOAD0 + NLOAD) {
         // ===== loader warps.  (1) Stage the NEXT point tile while the current one is in the main loop: a' x = hi + lo (f16) into
-        // the staging buffer, K_i and row sums, two rows per warp pass (16 lanes x 8 columns).  (2) Final contraction of the
-        // PREVIOUS tile, off the epilogue warps' critical path: out_o = K_i sum_col F[f1] F[f2] T[col] inv_scale[col] (FP64, once per
-        // point).  A loader warp stages exactly the 32 rows it later contracts (its tensor-memory lane quadrant, warp % 4), so K_i and
-        // the row sum of a point stay in that thread's registers and the features need no cross-warp synchronisation. =====
+        // the staging buffer, |x|^2, row sums and the exponent shift, two rows per warp pass (16 lanes x 8 columns).  (2) Contract
+        // each finished class of the CURRENT tile (class epochs arrive roughly every third of the main loop): out_o += K_i sum_col
+        // F[f1] F[f2] (T[col] + 2^s csum[col]) inv_scale[col].  A loader warp stages exactly the 32 rows it later contracts (its
+        // tensor-memory lane quadrant, warp % 4), so the features need no cross-warp synchronisation.  The class contractions are
+        // polled between the staging passes; what is left is waited for after the last pass. =====
         const int qd = warp & 3;                                     // tensor-memory lane quadrant = row group of this warp
         const double ascale = gp.a * 1.4426950408889634;             // a log2(e): S = log2 of exp(a x.y)
         const int hl = lane & 15, sub = lane >> 4;
         const int c0 = hl * 8;
         const double ymax2 = __ldg(st.ymax2);
+        const float ascale_f = (float)ascale;
+        const bool has_stats = !GEN && st.pstat != nullptr;         // the samplers already reduced |x|^2 and sum x of every point (opt-in)
         const bool active = c0 < NSTEP * 16;
         constexpr int RPW = TM / NLOAD;                              // rows per loader warp
         static_assert(RPW == 32, "a loader warp owns one tensor-memory lane quadrant");
@@ -712,8 +785,104 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int it = 0; it <= nit; ++it) {
             double ki_new = 0.0, sx_new = 0.0;
             float sc_new = 0.0f;
+            // --- class contractions of tile it - 1 (tp): epochs tp * NCLS .. + NCLS - 1
+            const int tp = it - 1;
+            int ce = 0;                                              // classes of tile tp contracted so far
+            const int nce = (it > 0) ? NCLS : 0;
+            auto class_ends = [&](bool block) {
+                while (ce < nce) {
+                    const int e = tp * NCLS + ce;
+                    if (block) mbar_wait(t_full(e), (uint32_t)(e >> 1) & 1u);
+                    else if (!mbar_test_wait(t_full(e), (uint32_t)(e >> 1) & 1u)) break;
+                    tc_fence_after();
+                    const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
+                    const bool ok = row < R;
+                    float* F = feat + rq * TF_COUNT;                 // private to this thread
+                    if (ce == 0) {                                   // features of the row, once per tile (floats; FP64 runs at 1/8 rate here)
+                        const double* xr = X + row * (long)D;
+                        const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
+                        double P2 = 0.0, R2 = 0.0;
+#pragma unroll
+                        for (int m = 0; m < MC_IDX; ++m) {
+                            const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
+                            F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
+                            P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+                        }
+                        F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
+                        F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
+                        acc4[rq * 4 + 0] = 0.0; acc4[rq * 4 + 1] = 0.0; acc4[rq * 4 + 2] = 0.0; acc4[rq * 4 + 3] = 0.0;
+                    }
+                    if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(246);
+                    const int kc = CL::kern(ce);
+                    const int ncol = CL::ncol(kc), coff = CL::coloff(kc);
+                    const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_T2 + (uint32_t)(e & 1) * NTMAX;
+                    double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
+                    constexpr int CH = 16;                           // T columns per tensor-memory load round
+                    const char* Fb = (const char*)F;
+#pragma unroll 1
+                    for (int cb = 0; cb < ncol; cb += CH) {
+                        float tv[CH];
+                        tmem_ld16(tbase + (uint32_t)cb, tv);
+                        tmem_ld_wait();
+                        if (cb + CH >= ncol) {                       // last round: this T buffer may be overwritten (two class epochs later)
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(t_free(e));
+                        }
+                        // FP32 products and FP32 partial sums per output over the round (one-hot scale masks: no output bookkeeping), FP64 across rounds
+                        float pU = 0.0f, pG = 0.0f, pL = 0.0f, pT = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            const uint32_t o = soff[coff + cb + i];
+                            const float4 m = smask[coff + cb + i];
+                            const float2 cs = scs[coff + cb + i];
+                            const float w = fmaf(sc_prev, cs.x, fmaf(sc_prev, cs.y, tv[i]));      // sum_j P C = T + 2^s sum_j C (baseline term)
+                            const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * w;
+                            pU = fmaf(t, m.x, pU); pG = fmaf(t, m.y, pG); pL = fmaf(t, m.z, pL); pT = fmaf(t, m.w, pT);
+                        }
+                        aU += (double)pU; aG += (double)pG; aL += (double)pL; aT += (double)pT;
+                    }
+                    if (ce + 1 < NCLS) {
+                        acc4[rq * 4 + 0] += aU; acc4[rq * 4 + 1] += aG; acc4[rq * 4 + 2] += aL; acc4[rq * 4 + 3] += aT;
+                    } else {
+                        aU += acc4[rq * 4 + 0]; aG += acc4[rq * 4 + 1]; aL += acc4[rq * 4 + 2]; aT += acc4[rq * 4 + 3];
+                        if (ok) {
+                            const double ki = ki_prev;
+                            const double u = ki * aU;
+                            if (CLASS == TC_U) {
+                                const double gt = 1.0 - 1.0 / (1.0 + exp(sx_prev + __ldg(X + row * (long)D + d)));   // equations.py:259
+                                out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
+                            } else if (CLASS == TC_UG) {
+                                out0[row] = u;
+                                out1[row] = ki * aG;
+                            } else {
+                                const double gg = ki * aG, l = ki * aL, tt = ki * aT;
+                                const double s2 = gp.sig2;
+                                out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * gg + 0.5 * s2 * l;   // GP.py:767-768
+                                if (out1) out1[row] = gg;
+                                if (out2) out2[row] = l;
+                                if (out3) out3[row] = tt;
+                            }
+                        }
+                        if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(247);
+                    }
+                    ++ce;
+                }
+            };
             if (it < nit) {
             const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
+            if (!GEN) {
+                // pull this warp's 32 rows of the tile AFTER this one into L2, a whole tile period ahead; the very first tile of a CTA also pulls its own rows
+                for (int ahead = (it == 0 ? 0 : 1); ahead <= 1; ++ahead) {
+                    const long rn = ((long)blockIdx.x + (long)(it + ahead) * gridDim.x) * TM + qd * RPW;
+                    if (it + ahead < nit && rn < R) {
+                        const long nrow = (R - rn < RPW) ? (R - rn) : RPW;
+                        const char* p0 = (const char*)(X + rn * (long)D);
+                        const long nbytes = nrow * (long)D * 8;
+                        for (long o = (long)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+                    }
+                }
+            }
             if (it > 0) mbar_wait(stage_free, (uint32_t)(it - 1) & 1u);     // the previous tile's images are in tensor memory
             if (GEN) {                                               // phase 1: lane <-> point (32 dependent-load chains in flight per warp)
                 const int rr = qd * RPW + lane;
@@ -722,6 +891,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             }
 #pragma unroll 1
             for (int pass = 0; pass < RPW / 4; ++pass) {
+                class_ends(false);                                   // a finished class of the current tile goes first: stage 2 of the class after next waits for its T buffer
                 double v[2][8];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -749,9 +919,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         for (int q = 0; q < 2; ++q) {
                             const int c = c0 + e + q;
                             const double val = v[i][e + q];
-                            nx = fma(val, val, nx);
-                            if (c < d) sx += val;
-                            sv[q] = (float)(ascale * val);                 // columns >= D are zero
+                            if (!has_stats) { nx = fma(val, val, nx); if (c < d) sx += val; }
+                            sv[q] = (float)val * ascale_f;                 // columns >= D are zero (FP32 product: one FP64-pipe instruction less per element)
                         }
                         // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
                         const __half2 h = __floats2half2_rn(sv[0], sv[1]);
@@ -765,236 +934,134 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         *(uint4*)p = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *(uint4*)(p + (size_t)TM * A_PITCH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
+                    if (!has_stats) {
 #pragma unroll
-                    for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
-                    if (hl == 0) { Ki[r] = nx; sxs[r] = sx; rsc[(it & 1) * TM + r] = exp2f((float)row_shift(gp.a, nx, ymax2)); }
+                        for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
+                        if (hl == 0) { Ki[r] = nx; sxs[r] = sx; }
+                    }
                 }
             }
             if (GEN) __threadfence_block();                         // generated rows (global) are re-read by this warp's contraction
             __syncwarp();
-            sc_new = rsc[(it & 1) * TM + rq];
-            ki_new = ldexp(exp(-0.5 * gp.a * Ki[rq]), TC_P_SHIFT - row_shift(gp.a, Ki[rq], ymax2)); sx_new = sxs[rq];    // |x|^2, row sum written by this warp: lane <-> row for the contraction
-                                                                     // (one FP64 exp per lane instead of one per row pass)
+            {   // lane <-> row (the row this thread contracts): |x|^2 and the row sum from this warp's reductions (or the sampler's statistics),
+                // exponent shift, K_i (one FP64 exp per lane instead of one per row pass)
+                double nxr, sxr;
+                if (has_stats) {
+                    const bool ok = row0 + rq < R;
+                    nxr = ok ? __ldg(st.pstat + 2 * (row0 + rq)) : 0.0;
+                    sxr = ok ? __ldg(st.pstat + 2 * (row0 + rq) + 1) : 0.0;
+                } else { nxr = Ki[rq]; sxr = sxs[rq]; }
+                const int sh = row_shift(gp.a, nxr, ymax2);
+                sc_new = exp2f((float)sh);
+                rsc[(it & 1) * TM + rq] = sc_new;                     // read by the epilogue warps after stage_full
+                ki_new = ldexp(exp(-0.5 * gp.a * nxr), TC_P_SHIFT - sh); sx_new = sxr;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
             if (it == 1 && qd == 0 && lane == 0) TC_STAMP(1);
-            if (!GEN && it + 1 < nit) {
-                // pull this warp's 32 rows of the NEXT tile into L2 now: its staging passes (eight dependent load rounds a tile
-                // later) then see L2 latency instead of HBM latency -- staging was finishing after the main loop it should hide behind
-                const long rn = ((long)blockIdx.x + (long)(it + 1) * gridDim.x) * TM + qd * RPW;
-                if (rn < R) {
-                    const long nrow = (R - rn < RPW) ? (R - rn) : RPW;
-                    const char* p0 = (const char*)(X + rn * (long)D);
-                    const long nbytes = nrow * (long)D * 8;
-                    for (long o = (long)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
-                }
             }
-            }
-            if (it > 0) {
-                // --- final contraction of tile it - 1
-                const int tp = it - 1;
-                const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
-                const bool ok = row < R;
-                const double* xr = X + row * (long)D;
-                // FP64 runs at 1/8 of the FP32 rate on this part (a warp-wide FP64 instruction holds its pipe 8 cycles): the column products
-                // F[f1] F[f2] T[col] are formed in FP32 (their rounding, ~2e-7, is of the size of T's own FP32 accumulation error) and only the
-                // sums over columns stay in FP64.  The features are kept as floats; the few the outputs need exactly stay in registers.
-                float* F = feat + rq * TF_COUNT;                     // private to this thread
-                double f_xt = 0.0;
-                {
-                    const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
-                    double P2 = 0.0, R2 = 0.0;
-#pragma unroll
-                    for (int m = 0; m < MC_IDX; ++m) {
-                        const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                        F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
-                        P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
-                    }
-                    F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
-                    F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
-                    f_xt = xt;
-                }
-                mbar_wait(t_full(tp), (uint32_t)t_cnt(tp) & 1u);     // all stage-2 MMAs of the tile have completed
-                tc_fence_after();
-                if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(246);
-                const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_T + (uint32_t)(t_buf(tp) * NT);
-                double aU = 0.0, aG = 0.0, aL = 0.0, aT = 0.0;
-                constexpr int CH = 16;                               // T columns per tensor-memory load round (register budget)
-                const char* Fb = (const char*)F;
-                // Single T buffer (PDE class): stage 2 of the next tile waits for T, so it is copied out first -- all but the last round go to
-                // the staging buffer, idle between the A-image copy of tile `it` and the staging of tile it + 1 ([column][row] floats) --
-                // T is released, and the arithmetic follows.
-                float* tsm = (float*)sStage;
-                float tlast[CH];
-                if (!TDBL) {
-                    if (it < nit) mbar_wait(stage_free, (uint32_t)it & 1u);      // tile `it`'s images have left the staging buffer
-#pragma unroll 1
-                    for (int cb = 0; cb + CH < NT; cb += CH) {
-                        float tv[CH];
-                        tmem_ld16(tbase + (uint32_t)cb, tv);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) tsm[(cb + i) * TM + rq] = tv[i];
-                    }
-                    tmem_ld16(tbase + (uint32_t)(NT - CH), tlast);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(t_free(tp));
-                }
-#pragma unroll 1
-                for (int cb = 0; cb < NT; cb += CH) {
-                    float tv[CH];
-                    if (TDBL) {
-                        tmem_ld16(tbase + (uint32_t)cb, tv);
-                        tmem_ld_wait();
-                        if (cb + CH >= NT) {                         // last round: this T buffer may be overwritten (two tiles later)
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(t_free(tp));
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) tv[i] = (cb + CH < NT) ? tsm[(cb + i) * TM + rq] : tlast[i];
-                    }
-                    // FP32 products and FP32 partial sums per output over the round (one-hot scale masks: no output bookkeeping), FP64 across rounds
-                    float pU = 0.0f, pG = 0.0f, pL = 0.0f, pT = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        const uint32_t o = soff[cb + i];
-                        const float4 m = smask[cb + i];
-                        const float2 cs = scs[cb + i];
-                        const float w = fmaf(sc_prev, cs.x, fmaf(sc_prev, cs.y, tv[i]));      // sum_j P C = T + 2^s sum_j C (baseline term)
-                        const float t = (*(const float*)(Fb + (o & 0xffffu)) * *(const float*)(Fb + (o >> 16))) * w;
-                        pU = fmaf(t, m.x, pU); pG = fmaf(t, m.y, pG); pL = fmaf(t, m.z, pL); pT = fmaf(t, m.w, pT);
-                    }
-                    aU += (double)pU; aG += (double)pG; aL += (double)pL; aT += (double)pT;
-                }
-                if (ok) {
-                    const double ki = ki_prev;
-                    const double u = ki * aU;
-                    if (CLASS == TC_U) {
-                        const double gt = 1.0 - 1.0 / (1.0 + exp(sx_prev + f_xt));                    // equations.py:259
-                        out0[row] = (mode == EVAL_TERMINAL) ? gt - u : u;
-                    } else if (CLASS == TC_UG) {
-                        out0[row] = u;
-                        out1[row] = ki * aG;
-                    } else {
-                        const double gg = ki * aG, l = ki * aL, tt = ki * aT;
-                        const double s2 = gp.sig2;
-                        out0[row] = tt + (s2 * u - 1.0 / (double)d - 0.5 * s2) * gg + 0.5 * s2 * l;   // GP.py:767-768
-                        if (out1) out1[row] = gg;
-                        if (out2) out2[row] = l;
-                        if (out3) out3[row] = tt;
-                    }
-                }
-                if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(247);
-                if (!TDBL) asm volatile("bar.sync 2, %0;" ::"n"(NLOAD * 32) : "memory");   // every loader warp is done with the T copy in the staging buffer
-            }
+            class_ends(true);                                        // whatever is left of the current tile's classes
             ki_prev = ki_new; sx_prev = sx_new; sc_prev = sc_new;
         }
     } else {
-        // ===== epilogue warps: thread <-> (point row r, centres [16 cg, 16 cg + 16) of the item) =====
+        // ===== epilogue warps: group = pair parity; warp <-> (lane quadrant, sub-item of the pair); thread <-> point row x 48 centres =====
+        const int ew = warp - W_EPI0;                                // epilogue warp index 0..15
         const int r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const bool skip_math = (dflags & 2) != 0;
-        long g = 0;                                                  // global item counter
+        const int grp = ew >> 3;
+        const int sub = (ew >> 2) & 1;
+        long g = 0;                                                  // global pair counter
         for (int it = 0; it < nit; ++it) {
-            if (it < nit) {
-                // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
-                // have completed (this warp saw s_full of its last item), so the images can be overwritten.
-                mbar_wait(stage_full, (uint32_t)it & 1u);
-                if (warp < 8) {                                      // image = warp >> 2; 32-bit column c = K elements 2c, 2c + 1
-                    const int img = warp >> 2;
-                    const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
-                    const uint32_t taddr = tmem_base + COL_A + (uint32_t)img * A_IMG_COLS + lane_addr;
+            // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
+            // have completed (the copying warps saw s_full of its last pair), so the images can be overwritten.
+            mbar_wait(stage_full, (uint32_t)it & 1u);
+            if (ew < 8) {                                            // image = ew >> 2; 32-bit column c = K elements 2c, 2c + 1
+                const int img = ew >> 2;
+                const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
+                const uint32_t taddr = tmem_base + COL_A + (uint32_t)img * A_IMG_COLS + lane_addr;
 #pragma unroll
-                    for (int ks = 0; ks < NSTEP; ++ks) {
-                        const uint4 q0 = *(const uint4*)(rowp + ks * 32), q1 = *(const uint4*)(rowp + ks * 32 + 16);
-                        const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                        tmem_st8(taddr + (uint32_t)ks * 8u, wv);
+                for (int ks = 0; ks < NSTEP; ++ks) {
+                    const uint4 q0 = *(const uint4*)(rowp + ks * 32), q1 = *(const uint4*)(rowp + ks * 32 + 16);
+                    const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    tmem_st8(taddr + (uint32_t)ks * 8u, wv);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(stage_free); }
+            }
+            if (it == 1 && ew == 0 && lane == 0) TC_STAMP(2);
+            const float sc = rsc[(it & 1) * TM + r], nsc = -sc;      // 2^s of this thread's point row (written before stage_full of the tile)
+            const bool stamp = (it == 1);
+            // --- main loop: S -> P - 2^s in place.  The fixed cost of a round trip (barrier wake-up, first tcgen05.ld, tcgen05.wait::st,
+            // fence, arrive) is paid once per 48 columns per thread, with the next chunk's tcgen05.ld in flight during the current
+            // chunk's ex2 work.  The two groups run half a period apart.
+            for (int j = 0; j < npair; ++j, ++g) {
+                if ((int)(g & 1) != grp) continue;
+                const bool two = PT_TWO(ptab[j]);
+                const int s = (int)(g % NSLOT2);
+                mbar_wait(s_full(s), (uint32_t)(g / NSLOT2) & 1u);
+                tc_fence_after();
+                if ((ew & 7) == 0 && lane == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
+                if (!skip_math && (sub == 0 || two)) {
+                    const uint32_t base = tmem_base + lane_addr + (uint32_t)s * SLOTC + (uint32_t)sub * TN2;
+                    constexpr int nch = TN2 / 16;                    // chunks of 16 columns
+                    float v[2][16];
+                    tmem_ld16(base, v[0]);
+#pragma unroll
+                    for (int ch = 0; ch < nch; ++ch) {
+                        tmem_ld_wait();                              // chunk ch has arrived
+                        if (ch + 1 < nch) tmem_ld16(base + (uint32_t)(ch + 1) * 16u, v[(ch + 1) & 1]);
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float p0 = fmaf(ex2f(v[ch & 1][2 * i]), sc, nsc), p1 = fmaf(ex2f(v[ch & 1][2 * i + 1]), sc, nsc);   // P - 2^s
+                            hi[i] = pack_f16x2_sat(p0, p1);
+                            const float2 hf = __half22float2(*(const __half2*)&hi[i]);
+                            lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
+                        }
+                        // P over S in place: 16 FP32 columns -> [8 columns of hi pairs | 8 columns of lo pairs] (the A operand of stage 2)
+                        const uint32_t cb = base + (uint32_t)ch * 16u;
+                        tmem_st8(cb, hi);
+                        tmem_st8(cb + 8u, lo);
                     }
                     tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(stage_free); }
                 }
-                if (it == 1 && tid == 0) TC_STAMP(2);
+                tc_fence_before();
+                __syncwarp();
+                if ((ew & 7) == 0 && lane == 0 && stamp && j < 60) TC_STAMP(7 + 4 * j);
+                if (lane == 0) mbar_arrive(p_ready(s));
             }
-            if (it == 1 && tid == 0) TC_STAMP(245);
-            if (it < nit) {
-                // --- main loop: S -> P in place.  The 16 epilogue warps form two groups of 8; group g owns S/P slot g, i.e. every other pair,
-                // and a thread converts 32 centres of BOTH sub-items of its pair (4 chunks of 16 columns).  The fixed cost of a round trip
-                // (barrier wake-up, first tcgen05.ld, tcgen05.wait::st, fence, arrive: ~500 cycles, measured with one-sub-item slots) is paid
-                // once per 64 columns per thread instead of once per 32, and the next chunk's tcgen05.ld is in flight during the current
-                // chunk's ex2 work.  The two groups run half a period apart.
-                static_assert(NSLOT == 2, "one epilogue group per S/P slot");
-                const bool stamp = (it == 1);
-                const float sc = rsc[(it & 1) * TM + r], nsc = -sc;  // 2^s of this thread's point row (written before stage_full of the tile)
-                const int grp = warp >> 3;                           // slot owned by this warp
-                const uint32_t chalf = (uint32_t)((warp >> 2) & 1) * 32u;   // which 32 of a sub-item's 64 centres
-                for (int j = 0; j < npair; ++j, ++g) {
-                    const int s = (int)(g % NSLOT);
-                    if (s != grp) continue;
-                    const bool two = 2 * j + 1 < nitem;
-                    if (dflags & 16) mbar_spin(s_full(s), (uint32_t)(g / NSLOT) & 1u); else mbar_wait(s_full(s), (uint32_t)(g / NSLOT) & 1u);
-                    tc_fence_after();
-                    if ((tid & 255) == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
-                    const uint32_t base = tmem_base + lane_addr + (uint32_t)s * 128u + chalf;
-                    if (!skip_math) {
-                        const int nch = two ? 4 : 2;                 // chunk c: sub-item c >> 1, columns 16 (c & 1) .. + 16 of this thread's 32
-                        float v[2][16];
-                        tmem_ld16(base, v[0]);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (c < nch) {
-                                tmem_ld_wait();                      // chunk c has arrived
-                                if (c + 1 < nch) tmem_ld16(base + (uint32_t)((c + 1) >> 1) * 64u + (uint32_t)((c + 1) & 1) * 16u, v[(c + 1) & 1]);
-                                uint32_t hi[8], lo[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float p0 = fmaf(ex2f(v[c & 1][2 * i]), sc, nsc), p1 = fmaf(ex2f(v[c & 1][2 * i + 1]), sc, nsc);   // P - 2^s
-                                    hi[i] = pack_f16x2_sat(p0, p1);
-                                    const float2 hf = __half22float2(*(const __half2*)&hi[i]);
-                                    lo[i] = pack_f16x2_sat(p0 - hf.x, p1 - hf.y);
-                                }
-                                // P over S in place: 16 FP32 columns -> [8 columns of hi pairs | 8 columns of lo pairs] (the A operand of stage 2)
-                                const uint32_t cb = base + (uint32_t)(c >> 1) * 64u + (uint32_t)(c & 1) * 16u;
-                                tmem_st8(cb, hi);
-                                tmem_st8(cb + 8u, lo);
-                            }
-                        }
-                        tmem_st_wait();
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if ((tid & 255) == 0 && stamp && j < 60) TC_STAMP(7 + 4 * j);
-                    if (lane == 0) mbar_arrive(p_ready(s));
-                }
-                // the A images of the next tile overwrite this tile's: every stage-1 MMA of the tile must have completed, also the last pair's,
-                // which may belong to the other group -- the copying warps wait for the final pair's accumulators explicitly
-                if (warp < 8) {                                      // the warps that copy the A images (group 0)
-                    const long gl = g - 1;                           // the tile's last pair (g was advanced past it)
-                    mbar_wait(s_full((int)(gl % NSLOT)), (uint32_t)(gl / NSLOT) & 1u);
-                    tc_fence_after();
-                }
+            // the A images of the next tile overwrite this tile's: every stage-1 MMA of the tile must have completed, also the last pair's,
+            // which may belong to the other group -- the copying warps wait for the final pair's accumulators explicitly
+            // (two stage-1 issuers: the last pair of each of them)
+            if (ew < 8) {
+                for (long gl = (g >= 2 ? g - 2 : 0); gl < g; ++gl)   // the tile's last two pairs (g was advanced past them)
+                    mbar_wait(s_full((int)(gl % NSLOT2)), (uint32_t)(gl / NSLOT2) & 1u);
+                tc_fence_after();
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (tid == 0) TC_STAMP(3);
-    if (warp == NEPI + 1) tmem_dealloc(tmem_base, 512);
+    if (warp == W_S1A) tmem_dealloc(tmem_base, 512);
 #undef TC_STAMP
+#undef PT_KERN
+#undef PT_TWO
+#undef PT_FIRST
+#undef PT_LAST
+#undef PT_TILE
 }
 
 template <int CLASS, int NSTEP, bool GEN>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    return ((CLASS == TC_PDE && GEN) ? 2 : 3) * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK) + NSLOT * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * A_PITCH
-           + (size_t)TM * TF_COUNT * 4 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t)) + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8
-           + 2 * TM * sizeof(float) + TC_MAXCOL * sizeof(float2) + NBAR * 8 + 16;
+    return Ring<CLASS, NSTEP, GEN>::NB1 * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK2) + Ring<CLASS, NSTEP, GEN>::NB3 * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * Stage<NSTEP>::PITCH
+           + (size_t)TM * TF_COUNT * 4 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t) + sizeof(float2)) + (size_t)TM * 4 * 8
+           + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + 2 * TM * sizeof(float) + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
 }
 
 template <int CLASS, int NSTEP, bool GEN>
@@ -1006,6 +1073,7 @@ static int launch(const GpView& gp, const TcDev& st, const double* X, long R, in
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SC_REQUIRE(3 * ((st.ntile_all + 1) / 2) <= MAX_PAIRS, "tcgen05 route: too many collocation points for the pair table (use the FP64 route)");
     const long ntiles = cdiv(R, TM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);   // persistent: one CTA per SM
     eval_tc_kernel<CLASS, NSTEP, GEN><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
@@ -1480,19 +1548,30 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
     st->nstep = (gp.D + 1 + 15) / 16;
     if (st->nstep <= 8) st->nstep = st->nstep <= 2 ? 2 : (st->nstep <= 4 ? 4 : (st->nstep <= 7 ? 7 : 8));   // instantiated k-step counts (small-d kernel)
     st->KB = (st->nstep + 3) / 4;
-    st->ntile_dom = gp.NdPad / tc::TN;
-    st->ntile_bdy = gp.NbPad / tc::TN;
+    st->compact = st->nstep <= 8 ? 1 : 0;            // resident-operand kernel: 48-centre tiles over the compact centre list
+    st->tn = st->compact ? tc::TN2 : tc::TN;
+    if (st->compact) {
+        st->ntile_all = (int)cdiv(gp.Nd + gp.Nb, tc::TN2);
+        st->ntile_dom = (int)cdiv(gp.Nd, tc::TN2);
+        st->ntile_bdy = 0;
+    } else {
+        st->ntile_dom = gp.NdPad / tc::TN;
+        st->ntile_bdy = gp.NbPad / tc::TN;
+        st->ntile_all = st->ntile_dom + st->ntile_bdy;
+    }
     build_columns(st);
-    const int ntile = st->ntile_dom + st->ntile_bdy;
-    const size_t ncentres = (size_t)ntile * tc::TN;
+    const int ntile = st->ntile_all;
+    const size_t ncentres = (size_t)gp.NdPad + gp.NbPad;      // coefficient matrix rows: GpView's padded centre list
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
-    st->b1_tile_bytes = (size_t)st->KB * 3 * tc::TN * 128;
-    st->b1_off = take((size_t)ntile * st->b1_tile_bytes);
+    st->npair_all = (ntile + 1) / 2;
+    const int ntile_img = st->compact ? 2 * st->npair_all : ntile;   // compact format: whole pairs (an odd last tile is padded with a zero tile)
+    st->b1_tile_bytes = (size_t)st->KB * 3 * st->tn * 128;
+    st->b1_off = take((size_t)ntile_img * st->b1_tile_bytes);
     for (int cls = 0; cls < 3; ++cls) {
         const int nt = st->ncol[cls][0] + st->ncol[cls][1] + st->ncol[cls][2];
         st->b3_tile_bytes[cls] = (size_t)2 * nt * 128;
-        st->b3_off[cls] = take((size_t)ntile * st->b3_tile_bytes[cls]);
+        st->b3_off[cls] = take((size_t)ntile_img * st->b3_tile_bytes[cls]);
     }
     for (int cls = 0; cls < 3; ++cls) st->desc_off[cls] = take(TC_MAXCOL * sizeof(TcColDesc));
     st->spec_off = take(3 * TC_MAXCOL * sizeof(TcColSpec));
@@ -1506,8 +1585,8 @@ size_t tc_image_bytes(const GpView& gp, TcState* st) {
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
     SC_REQUIRE(tc_supported(gp), "tcgen05 route supports d <= 1022 (larger d: FP64 route)");
     SC_REQUIRE(st.images != nullptr, "tc: image buffer is null");
-    const int ntile = st.ntile_dom + st.ntile_bdy;
-    const int ncentres = ntile * tc::TN;
+    const int ntile = st.ntile_all;
+    const int ncentres = gp.NdPad + gp.NbPad;
     TcColSpec* spec_dev = (TcColSpec*)(st.images + st.spec_off);
     double* coef = (double*)(st.images + st.scratch_off);
     unsigned long long* colmax = (unsigned long long*)(coef + 3 * (size_t)ncentres * TC_MAXCOL);
@@ -1518,12 +1597,12 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
     SC_CUDA(cudaMemsetAsync(st.images + st.ymax_off, 0, sizeof(double), stream));
     tc::ymax_kernel<<<(unsigned)cdiv(ncentres, 256), 256, 0, stream>>>(gp, ncentres, (unsigned long long*)(st.images + st.ymax_off));
     SC_LAUNCH_CHECK();
-    tc::b1_image_kernel<<<ntile, 256, 0, stream>>>(gp, st.images + st.b1_off, st.b1_tile_bytes, st.KB);
+    tc::b1_image_kernel<<<ntile, 256, 0, stream>>>(gp, st.images + st.b1_off, st.b1_tile_bytes, st.KB, st.tn, st.compact, st.npair_all);
     SC_LAUNCH_CHECK();
     for (int cls = 0; cls < 3; ++cls) {
         tc::b3_image_kernel<<<ntile, 256, 0, stream>>>(gp, spec_dev, cls, ncentres, coef, colmax, st.images + st.b3_off[cls],
                                                         st.b3_tile_bytes[cls], st.ncol[cls][TK_K], st.ncol[cls][TK_KX], st.ncol[cls][TK_KY],
-                                                        (TcColDesc*)(st.images + st.desc_off[cls]));
+                                                        (TcColDesc*)(st.images + st.desc_off[cls]), st.tn, st.compact, st.npair_all);
         SC_LAUNCH_CHECK();
     }
     tc::csum_kernel<<<dim3(TC_MAXCOL, 3), 256, 0, stream>>>(ncentres, coef, colmax, (double*)(st.images + st.csum_off));
@@ -1533,7 +1612,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
 
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const LevelDev* gen_level_dev, long long gen_off, const TcDebug* dbg) {
+                   const LevelDev* gen_level_dev, long long gen_off, const TcDebug* dbg, const double* pstat) {
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
@@ -1548,7 +1627,8 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.desc = (const TcColDesc*)(st->images + st->desc_off[cls]);
     dv.b1_tile_bytes = st->b1_tile_bytes;
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
-    dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy;
+    dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy; dv.ntile_all = st->ntile_all; dv.npair_all = st->npair_all;
+    dv.pstat = pstat;
     dv.ymax2 = (const double*)(st->images + st->ymax_off);
     dv.csum = (const double*)(st->images + st->csum_off) + cls * TC_MAXCOL;
     dv.gen = gen_level_dev; dv.gen_off = gen_off;

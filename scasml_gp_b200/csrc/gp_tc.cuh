@@ -35,7 +35,8 @@ struct TcState {
     size_t total_bytes = 0;
     int KB = 0;                      // 64-wide K blocks of the contraction axis
     int nstep = 0;                   // k-steps of 16 actually used: ceil((D + 1) / 16) (column D carries the exponent shift)
-    int ntile_dom = 0, ntile_bdy = 0;
+    int tn = 64, compact = 0;        // centres per tile; 1: tiles run over the compact centre list [domain | boundary] (resident-operand kernel)
+    int ntile_dom = 0, ntile_bdy = 0, ntile_all = 0, npair_all = 0;
     size_t b1_off = 0, b1_tile_bytes = 0;            // per tile, per K block: rows [C | Crollinv | Croll] x 128 B
     int ncol[3][3] = {};                             // padded column count per (evaluation class, kernel class)
     size_t b3_off[3] = {}, b3_tile_bytes[3] = {};    // per tile: [k hi | k lo | ky hi | ky lo | kx hi | kx lo], ncol x 128 B each
@@ -59,7 +60,8 @@ struct LevelDev;
 // (device copy of its LevelDev) into X instead of reading them
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const LevelDev* gen_level_dev = nullptr, long long gen_off = 0, const TcDebug* dbg = nullptr);
+                   const LevelDev* gen_level_dev = nullptr, long long gen_off = 0, const TcDebug* dbg = nullptr,
+                   const double* pstat = nullptr);   // pstat: [R][2] (|x|^2, sum_i x_i) per point when the caller has them (the samplers do)
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);

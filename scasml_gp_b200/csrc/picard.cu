@@ -155,6 +155,7 @@ int PicardPlan::build(const PicardParams& p, long B) {
         executed += pt;
         lv.off_P = take((size_t)pt * D * sizeof(double));
         lv.off_gid = take((size_t)pt * sizeof(long long));
+        lv.off_pstat = take(0);
         lv.off_rows = take((size_t)lv.NR * sizeof(RowRec));
         lv.off_ev0 = take((size_t)pt * sizeof(double));
         lv.off_ev1 = take((size_t)pt * sizeof(double));
@@ -846,6 +847,10 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         }
         lv.P = (double*)(ws + lr.off_P);
         lv.gid = (long long*)(ws + lr.off_gid);
+        // per-point (|X|^2, sum X) for the tcgen05 route's loader warps: not produced by the samplers -- measured at C3 they pay more for the two
+        // FP64 warp reductions per point (2.9 -> 4.7 ms per step) than the evaluation kernel saves (19.4 -> 18.2 ms); launch_eval_tc still takes
+        // such statistics from a caller that has them
+        lv.pstat = nullptr;
         lv.npoints = lr.npoints;
         lv.rows = (RowRec*)(ws + lr.off_rows);
         lv.ev0 = (double*)(ws + lr.off_ev0);
@@ -962,7 +967,8 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
                 begin_span(1);
                 if (route == 1)
                     rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
-                                        nullptr, nullptr, stream, fused ? (const LevelDev*)(ws + lr.off_lvdev) : nullptr, s.off);
+                                        nullptr, nullptr, stream, fused ? (const LevelDev*)(ws + lr.off_lvdev) : nullptr, s.off, nullptr,
+                                        lv.pstat ? lv.pstat + 2 * s.off : nullptr);
                 else
                     rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                          nullptr, nullptr, stream);

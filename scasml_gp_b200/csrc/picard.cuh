@@ -80,6 +80,7 @@ struct LevelDev {
     double cnode[MAXLK], wnode[MAXLK];  // c[k][q-1], w[k][q-1]
     double* P;                          // point buffer [npoints][D]
     long long* gid;                     // [npoints]
+    double* pstat;                      // [npoints][2] (|X|^2, sum_i X_i) of every sample point, written by the samplers for the tcgen05 route (else null)
     RowRec* rows;                       // [NR]
     double* ev0; double* ev1;           // evaluation outputs per point
     double* us[MAX_LEVEL + 1];          // finalized (u, zsum) per row, per level
@@ -112,7 +113,7 @@ public:
         long long NP[MAX_LEVEL] = {0};
         long long set_off[MAXLK] = {0};
         long long term_off = 0, ug_off = 0, pde_off = 0;
-        size_t off_P = 0, off_gid = 0, off_rows = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
+        size_t off_P = 0, off_gid = 0, off_pstat = 0, off_rows = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
     };
     const std::vector<CallRec>& calls() const { return calls_; }
     const std::vector<LevelRec>& levels() const { return levels_; }

@@ -12,6 +12,8 @@
 //   mode 9  mode 3 (epilogue chunk loop) with the MMA warp issuing TS-mode MMAs concurrently
 //   mode 10 MMA warp alone: TS-mode, one N = 128 MMA followed by two N = 16 MMAs into another accumulator (shape switching)
 //   mode 11 like 10, batched: 14 x N = 128 then 24 x N = 16
+//   mode 12 / 13  the 16 warps run a DFMA loop (8 chains) with / without the MMA warp issuing TS-mode N = `N` MMAs concurrently
+//   mode 14 / 15  the same with FFMA     (is the FP64 SIMT pipe slowed down while the tensor pipe is busy?)
 #include "common.cuh"
 #include "gp_tc.cuh"
 #include "tc_ptx.cuh"
@@ -296,15 +298,36 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
                 if ((it & 63) == 63) { tmem_st16(col, z); tmem_st_wait(); }
             }
         }
+        if (mode == 12 || mode == 13) {
+            double a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = 1.0 + i + tid;
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = fma(a[i], 1.0000001, 0.5);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sink += (float)a[i];
+        } else if (mode == 14 || mode == 15) {
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = 1.0f + i + tid;
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], 1.0000001f, 0.5f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sink += a[i];
+        }
         const long long t1 = clock64();
         if (sink == 12345.678f) out[7] = 1;
         if (blockIdx.x == 0 && tid == 0) out[0] = t1 - t0;
     } else {
         const uint32_t el = elect_one();
-        if (mode >= 4) {
+        if (mode >= 4 && mode != 13 && mode != 15) {
             const uint32_t idesc = make_idesc(128, N);
             const uint64_t ad = make_desc(smem_u32(sA), 1, 64, 2), bd = make_desc(smem_u32(sB), 1, 64, 2);
-            const int nmma = (mode == 4 || mode == 9) ? iters * 2 : (mode >= 10 ? 38 * 32 : iters);
+            const int nmma = (mode == 4 || mode == 9) ? iters * 2 : (mode >= 12 ? iters : (mode >= 10 ? 38 * 32 : iters));
             uint64_t& bar2 = *(uint64_t*)(smem + 128 * 128 + 256 * 128 + 16);
             uint64_t& bar3 = *(uint64_t*)(smem + 128 * 128 + 256 * 128 + 24);
             if (el) { mbar_init(smem_u32(&bar2), 1); mbar_init(smem_u32(&bar3), 1); mbar_arrive(smem_u32(&bar3)); fence_barrier_init(); }
@@ -346,7 +369,7 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
             } else
             for (int it = 0; it < nmma; it += 4) {
                 if (el) {
-                    if (mode == 6 || mode == 9) {
+                    if (mode == 6 || mode == 9 || mode == 12 || mode == 14) {
                         umma_f16_ts(acc, tmem_base + 480u, bd, idesc, 1u);
                         umma_f16_ts(acc, tmem_base + 488u, bd + 2ull, idesc, 1u);
                         umma_f16_ts(acc, tmem_base + 480u, bd + 4ull, idesc, 1u);
@@ -375,7 +398,7 @@ pipe_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
 }  // namespace tc
 
 int tc_pipe_bench(int mode, int N, int iters, long long* out_dev, cudaStream_t stream) {
-    SC_REQUIRE(mode >= 0 && mode <= 11 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && iters % 448 == 0, "pipe_bench: arguments");
+    SC_REQUIRE(mode >= 0 && mode <= 15 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && iters % 448 == 0, "pipe_bench: arguments");
     const size_t smem = 128 * 128 + 256 * 128 + 64;
     SC_CUDA(cudaFuncSetAttribute(tc::pipe_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SC_CUDA(cudaMemsetAsync(out_dev, 0, 8 * sizeof(long long), stream));

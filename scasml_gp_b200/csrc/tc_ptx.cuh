@@ -34,9 +34,10 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU box.  try_wait suspends the warp in hardware while the phase
-// is pending, so waiting warps do not take issue slots from the (latency-bound) MMA-issuing warp on the same scheduler;
-// mbar_test_wait is the non-blocking probe.
+// bounded wait: a protocol bug traps instead of hanging the GPU box.  mbarrier.try_wait parks the thread for a short hardware window per
+// probe; the loop around it still costs issue slots (ncu on the evaluation kernel: 360 M of its 746 M warp instructions were such probes),
+// but sleeping between probes (nanosleep 32) measured no faster -- the waiting warps were not what the busy warps lacked -- and adds
+// wake-up latency to every hand-off.  mbar_test_wait is the non-blocking probe.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {

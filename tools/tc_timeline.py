@@ -19,7 +19,7 @@ R = xd.shape[0]
 lib = _lib.load_debug()          # stamps / experiment flags exist only in the debug build
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0     # 1 skip stage-2 MMAs, 2 skip epilogue arithmetic, 4 skip low-half pass
 for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PDE")):
-    stamps = torch.zeros(256, dtype=torch.int64, device="cuda")
+    stamps = torch.zeros(1024, dtype=torch.int64, device="cuda")
     scratch = torch.empty(4 * R, dtype=torch.float64, device="cuda")
     for rep in range(2):
         _lib.check(lib.scasml_debug_tc_timeline(gp._handle, _lib.ptr(xd), R, mode, 100 | (flags << 24), _lib.ptr(stamps), _lib.ptr(scratch), _lib.stream_ptr()))
@@ -34,6 +34,13 @@ for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PD
     f = [int(x - t0) for x in t[244:249]]
     print(f"   tile boundary (stamps of the CTA's SECOND point tile): tile-0 t_full committed {f[4]}, MMA warp enters tile 1 {f[0]}, epilogue enters "
           f"tile-1 iteration {f[1]}, A images copied {t[2]-t0}, loader warp 0 saw t_full(0) {f[2]}, tile-0 outputs written {f[3]}, loader staged tile 1 at {t[1]-t0}")
+    ld = [int(x - t0) if x > 0 else 0 for x in t[800:830]]
+    print(f"   loader warp 0, staging of the CTA's THIRD tile: pass starts {ld[0:8]}, done {ld[8]}; class contractions of the SECOND tile (start, end): {ld[20:26]}")
+    lp = [int(x - t0) if x > 0 else 0 for x in t[840:848]]
+    print(f"   loader warp 0, third tile, passes 0-3 (loads landed, pass done): {lp}")
+    print(f"   pass 1 detail (row pair 0: converted+stored, reduced, shift written; row pair 1: same): {[int(x - t0) for x in t[850:856]]}")
     for w in range(min(nitem, 44)):
         a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
-        print(f"  item {w:2d}: mma issue {a:7d}..{b:7d} ({b-a:5d})   epilogue {c:7d}..{e:7d} ({e-c:5d})")
+        f = [int(t[256 + 8 * w + i] - t0) for i in range(7)]
+        print(f"  pair {w:2d}: S1 issuer reaches {a:7d} | slot free {f[0]:7d} rows landed {f[1]:7d} issued {f[2]:7d} committed {f[3]:7d} | epilogue {c:7d}..{e:7d} ({e-c:5d}) | "
+              f"S2 issuer: P ready {f[4]:7d} images landed {f[5]:7d} issued {f[6]:7d} committed {b:7d}")
