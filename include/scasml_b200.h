@@ -71,7 +71,7 @@ typedef struct scasml_picard_params {
     int rank, world;                 /* top-level sample sharding (unit u owned iff u % world == rank) */
     long long gid0;                  /* global index of the first row of x_t (RNG addressing) */
     int timing;                      /* 1: bracket kernel groups with CUDA events (adds a stream sync at the end) */
-    int reserved;                    /* flags; bit 0: tcgen05 route draws the points inside the evaluation kernel (fused sampler, opt-in) */
+    int reserved;                    /* must be 0 */
 } scasml_picard_params;
 
 typedef struct scasml_picard_stats {

@@ -60,8 +60,6 @@ struct TcDev {
     const double* csum;              // [TC_MAXCOL] per column: sum over the centres of the scaled, split coefficients (baseline term of the coefficient GEMM)
     const double* pstat;             // [R][2] (|x|^2, sum_i x_i) per point, or null: the loader warps compute them (public evaluation API, fused sampler)
     const double* ymax2;             // device scalar: max_j |y_j|^2 over the centres (per-row exponent shift, row_shift())
-    const LevelDev* gen;             // non-null: the loader warps GENERATE the points (fused sampler) instead of reading X
-    long long gen_off;               // index of the launch's first point in the level's point buffer
     long long* dbg;
     int dbg_block;
     int dbg_flags;                   // timeline experiments: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 8 no operand copies (garbage operands), 16 epilogue spins on s_full, 64 MMA issuers spin
@@ -324,9 +322,9 @@ constexpr int NB1_MAX = 6;                                           // centre-r
 // coefficient-image ring depth (pairs).  A slot is refilled only after stage 2 of its previous pair COMPLETED, and a bulk copy out of
 // L2 takes ~1 000 cycles to land: with two slots the coefficient GEMM of pair p waited for its images whenever the pair period fell
 // below ~1 600 cycles (tools/tc_timeline.py: the stage-2 issuer never waited for P, yet needed 1 300 - 1 600 cycles per pair)
-template <int CLASS, int NSTEP, bool GEN> struct Ring {
-    static constexpr int NB3 = (CLASS == TC_PDE) ? ((GEN || NSTEP == 8) ? 2 : 3) : (CLASS == TC_UG ? 2 : 4);
-    static constexpr int NB1 = (CLASS == TC_PDE || GEN) ? 3 : 4;
+template <int CLASS, int NSTEP> struct Ring {
+    static constexpr int NB3 = (CLASS == TC_PDE) ? (NSTEP == 8 ? 2 : 3) : (CLASS == TC_UG ? 2 : 4);
+    static constexpr int NB1 = (CLASS == TC_PDE) ? 3 : 4;
 };
 // staging row pitch (bytes): the row's f16 image + 16, an odd multiple of 16, so that 16-byte reads of 8 rows hit 8 bank groups
 template <int NSTEP> struct Stage { static constexpr int PITCH = NSTEP * 32 + 16; };
@@ -337,7 +335,7 @@ constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 3) * 32;             // loaders |
 // (0..15) = warp W_EPI0 + e; W_EPI0 is a multiple of 4, so warp % 4 is still the tensor-memory lane quadrant of every loader / epilogue warp.
 constexpr int W_LOAD0 = 0, W_EPI0 = NLOAD, W_PROD = W_EPI0 + NEPI, W_S1A = W_PROD + 1, W_S2A = W_PROD + 2, W_S1B = W_PROD + 3, W_S2B = W_PROD + 4;
 static_assert(W_EPI0 % 4 == 0, "lane quadrant = warp % 4");
-constexpr int MAX_PAIRS = 1024;                                      // pair table entries (16 bits each): kernel class | two | first | last | centre tile
+constexpr int MAX_PAIRS = 512;                                       // pair table entries (16 bits each): kernel class | two | first | last | centre tile
 // barriers: b1_full b1_empty (NB1 each) | b3_full b3_empty (NB3 <= 4 each) | s_full p_ready slot_free (NSLOT2 each) | t_full[2] t_free[2] | a_ready stage_full stage_free | ord[2]
 constexpr int NB3_MAX = 4;
 constexpr int NBAR = 2 * NB1_MAX + 2 * NB3_MAX + 3 * NSLOT2 + 4 + 3 + 2;   // + ord[2]: stage-2 issue order hand-off between the two stage-2 issuers
@@ -371,132 +369,7 @@ template <int CLASS> struct ClsList {
 };
 
 
-// ---- fused sampler -----------------------------------------------------------------------------------------------------------
-// Same arithmetic, operation order and Philox addressing as picard.cu::sample_terminal_kernel / sample_paths_kernel (the
-// solvers give bit-identical results with the fusion switched off): terminal points X_T = (x + mu (T-t)) + sigma sqrt(T-t) N
-// (solvers/ScaSML.py:190-198), path points X_k = X_{k-1} + (mu d_k + sigma sqrt(d_k) N_k) accumulated from the level row for
-// k' = 0..k (:220-238), full-history points x + (mu tau (T-t) + sigma sqrt(tau (T-t)) N) (ScaSML_full_history.py:142-154).
-// Two phases per point tile so that the long dependent-load chain (owner row -> call record -> parent row pointer -> global id)
-// runs for 32 points per warp at once: (1) lane <-> point: resolve the point into a GenRec in shared memory;
-// (2) 16 lanes <-> point: lane hl owns coordinates [8 hl, 8 hl + 8); flat normal index of coordinate j is f0 + j, so the lane
-// needs the tail of Philox block B0 + hl and the head of block B0 + hl + 1: it generates one block and takes the next from its
-// neighbour lane.
-struct GenRec {
-    const double* x;                 // parent (level) row
-    const CallDev* call;
-    unsigned long long f0;           // flat index of the point's first normal
-    long long pgid;                  // global sample id
-    double t;                        // time of the level row
-    int l, k;                        // step set (l, k); l = -1: terminal point
-};
-
-__device__ __forceinline__ void gen_setup(const LevelDev& lv, long long pt, bool valid, GenRec* __restrict__ rec) {
-    GenRec g;
-    g.x = nullptr; g.call = nullptr; g.f0 = 0ull; g.pgid = 0; g.t = 0.0; g.l = -1; g.k = 0;
-    if (valid) {
-        int MC = lv.MCg;
-        long long s = pt - lv.term_off;
-        if (!(pt >= lv.term_off && pt < lv.term_off + lv.NT)) {
-            for (int ll = 0; ll < lv.L; ++ll) {
-                const long long o0 = lv.set_off[ll * MAX_Q];
-                const long long np = lv.NP[ll];
-                if (np > 0 && pt >= o0 && pt < o0 + np * lv.q[ll]) { g.l = ll; g.k = (int)((pt - o0) / np); s = pt - o0 - (long long)g.k * np; MC = lv.MCf[ll]; }
-            }
-        }
-        const long long u = lv.rank + (long long)lv.world * s;
-        const long long R = u / MC;
-        const int m = (int)(u - R * MC);
-        int lo = 0, hi = lv.ncalls - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(lv.rowbase + mid) <= R) lo = mid; else hi = mid - 1;
-        }
-        const CallDev* c = lv.calls + lo;
-        const long long i = R - __ldg(lv.rowbase + lo);
-        g.call = c;
-        g.x = c->xsrc + i * lv.D;
-        const long long gidrow = c->gidsrc ? c->gidsrc[i] : lv.gid0 + i;
-        g.pgid = gidrow * MC + m;
-        g.f0 = (unsigned long long)g.pgid * (unsigned long long)lv.d;
-        g.t = __ldg(g.x + lv.d);
-    }
-    *rec = g;
-}
-
-__device__ __forceinline__ void gen_point(const LevelDev& lv, const GenRec& g, long long pt, int hl, int lane, double* __restrict__ v, bool valid) {
-    const int d = lv.d, D = lv.D;
-    const int c0 = hl * 8;
-    const int l = g.l, k = g.k;
-    const double t = g.t;
-    const double* x = g.x;
-    double X[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { v[e] = 0.0; X[e] = (valid && c0 + e < d) ? __ldg(x + c0 + e) : 0.0; }
-    const unsigned long long B0 = g.f0 >> 3;
-    const int sh = (int)(g.f0 & 7ull);
-    const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
-    const bool mine = c0 < d;                                       // this lane owns real coordinates
-    const bool last_owner = mine && (c0 + 8 >= d || hl == 15);      // its right neighbour generates no block (or is another point's lane)
-    auto normals = [&](PhiloxKey key, double* N) {
-        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = make_uint4(0u, 0u, 0u, 0u);
-        if (mine) w0 = philox4x32_10(B0 + (unsigned long long)hl, key);
-        // the two half-warps work on different points (different step counts): shuffle inside the 16-lane group only
-        w1.x = __shfl_down_sync(hmask, w0.x, 1); w1.y = __shfl_down_sync(hmask, w0.y, 1);
-        w1.z = __shfl_down_sync(hmask, w0.z, 1); w1.w = __shfl_down_sync(hmask, w0.w, 1);
-        if (last_owner && sh != 0) w1 = philox4x32_10(B0 + (unsigned long long)hl + 1ull, key);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int idx = sh + e;
-            const uint32_t ch = (idx < 8) ? chunk_of(w0, idx) : chunk_of(w1, idx - 8);
-            N[e] = chunk_to_normal(lv.ntab, ch);
-        }
-    };
-    double tcol = lv.T;
-    if (l < 0) {
-        const double Tt = lv.T - t, sq = sqrt(Tt), drift = lv.mu * Tt;
-        double N[8];
-        normals(make_key(0u, 0u, lv.seed), N);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) X[e] = __dadd_rn(__dadd_rn(X[e], drift), __dmul_rn(lv.sigma, __dmul_rn(sq, N[e])));   // explicit roundings, as picard.cu
-    } else if (lv.variant == 0) {
-        double tprev = t;
-        for (int kk = 0; kk <= k; ++kk) {
-            const int lk = l * MAX_Q + kk;
-            const double tk = cloc_of(lv.T, t, lv.cnode[lk]);
-            const double dk = __dsub_rn(tk, tprev);
-            const double sq = sqrt(dk), drift = lv.mu * dk;
-            double N[8];
-            normals(make_key(valid ? g.call->key[lk] : 0u, 1u, lv.seed), N);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) X[e] = __dadd_rn(X[e], __dadd_rn(drift, __dmul_rn(lv.sigma, __dmul_rn(sq, N[e]))));
-            tprev = tk;
-        }
-        tcol = tprev;
-    } else {
-        const PhiloxKey kT = make_key(0u, 0u, lv.seed);
-        const double tau = chunk_to_uniform(chunk16((unsigned long long)g.pgid, kT));
-        const double steps = tau * (lv.T - t);
-        const double sq = sqrt(steps), drift = lv.mu * steps;
-        double N[8];
-        normals(kT, N);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) X[e] = __dadd_rn(X[e], __dadd_rn(drift, __dmul_rn(lv.sigma, __dmul_rn(sq, N[e]))));
-        tcol = t + steps;
-    }
-    if (valid) {
-        double* dst = lv.P + pt * D;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int cc = c0 + e;
-            if (cc < d) { v[e] = X[e]; dst[cc] = X[e]; }
-            else if (cc == d) { v[e] = tcol; dst[cc] = tcol; }
-        }
-        if (hl == 0 && l >= 0) lv.gid[pt] = g.pgid;
-    }
-}
-
-
-template <int CLASS, int NSTEP, bool GEN>
+template <int CLASS, int NSTEP>
 __global__ void __launch_bounds__(NTHREADS_P, 1)
 eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mode,
                double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ out2, double* __restrict__ out3) {
@@ -509,7 +382,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     constexpr uint32_t B3_SUB = 2 * NMAX * 128;                      // one sub-item's coefficient images (hi | lo)
     constexpr uint32_t B3_SLOT = 2 * B3_SUB;                         // a pair
     constexpr uint32_t B1_SLOT = KB * 2 * B1_BLK2;                   // a pair's centre rows: per K block [sub-item a rows | sub-item b rows]
-    constexpr int NB3 = Ring<CLASS, NSTEP, GEN>::NB3, NB1 = Ring<CLASS, NSTEP, GEN>::NB1;
+    constexpr int NB3 = Ring<CLASS, NSTEP>::NB3, NB1 = Ring<CLASS, NSTEP>::NB1;
     constexpr int A_PITCH = Stage<NSTEP>::PITCH;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
@@ -526,11 +399,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint32_t* soff = (uint32_t*)(smask + TC_MAXCOL);                 // [TC_MAXCOL]
     float2* scs = (float2*)(soff + TC_MAXCOL);                       // [TC_MAXCOL]
     double* acc4 = (double*)(scs + TC_MAXCOL);                       // [128][4] output sums (u, div, lap, dt) of the tile being contracted, across its classes
-    GenRec* grec = (GenRec*)(acc4 + TM * 4);                         // [128] fused sampler: resolved points of the tile being staged
-    double* Ki = (double*)(grec + (GEN ? TM : 0));                   // [128] |x|^2 of the staged tile
-    double* sxs = Ki + TM;                                           // [128] sum_{i<d} x_i of the staged tile
-    float* rsc = (float*)(sxs + TM);                                 // [2][128] 2^s of the point rows, by tile parity (epilogue: P - 2^s = 2^s ex2(S) - 2^s)
-    uint64_t* bars = (uint64_t*)(rsc + 2 * TM);
+    double* Ki = acc4 + TM * 4;                                      // [2][128] |x|^2 of the staged tiles, by tile parity
+    double* sxs = Ki + 2 * TM;                                       // [2][128] sum_{i<d} x_i
+    uint64_t* bars = (uint64_t*)(sxs + 2 * TM);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
     uint16_t* ptab = (uint16_t*)(tmem_slot + 4);                     // [npair] pairs of the class-major stream of one point tile
 
@@ -562,7 +433,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int i = 0; i < NB3; ++i) { mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); }
         for (int i = 0; i < NSLOT2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(slot_free(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, NLOAD); }
-        mbar_init(a_ready, 8); mbar_init(stage_full, NLOAD); mbar_init(stage_free, 8);
+        mbar_init(a_ready, 8); mbar_init(stage_full, NEPI); mbar_init(stage_free, NLOAD);
         mbar_init(ord0, 1); mbar_init(ord0 + 8u, 1);
         fence_barrier_init();
     }
@@ -763,37 +634,32 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             if (el && it == 0 && w == 0) TC_STAMP(248);
         }
     } else if (warp >= W_LOAD0 && warp < W_LOAD0 + NLOAD) {
-        // ===== loader warps.  (1) Stage the NEXT point tile while the current one is in the main loop: a' x = hi + lo (f16) into
-        // the staging buffer, |x|^2, row sums and the exponent shift, two rows per warp pass (16 lanes x 8 columns).  (2) Contract
-        // each finished class of the CURRENT tile (class epochs arrive roughly every third of the main loop): out_o += K_i sum_col
-        // F[f1] F[f2] (T[col] + 2^s csum[col]) inv_scale[col].  A loader warp stages exactly the 32 rows it later contracts (its
-        // tensor-memory lane quadrant, warp % 4), so the features need no cross-warp synchronisation.  The class contractions are
-        // polled between the staging passes; what is left is waited for after the last pass. =====
+        // ===== contraction warps (one per tensor-memory lane quadrant, thread <-> point row).  Per point tile: the row's scalars (K_i with the
+        // exponent shift divided out, row sum) from the |x|^2 / sum x the epilogue warps left in shared memory when they staged the tile, then one
+        // contraction per finished class:  out_o += K_i sum_col F[f1] F[f2] (T[col] + 2^s csum[col]) inv_scale[col].
+        // The staging itself used to run on these four warps in the background; a warp issues ~0.25 instructions per cycle whatever it does, and their
+        // ~10 k instructions per tile took longer than the main loop (65 k vs 55 k cycles in the PDE class, 50 k vs 36 k in the u class:
+        // tools/tc_timeline.py), so the tile period was theirs.  Sixteen warps do it at the tile boundary in ~3 k cycles. =====
         const int qd = warp & 3;                                     // tensor-memory lane quadrant = row group of this warp
-        const double ascale = gp.a * 1.4426950408889634;             // a log2(e): S = log2 of exp(a x.y)
-        const int hl = lane & 15, sub = lane >> 4;
-        const int c0 = hl * 8;
         const double ymax2 = __ldg(st.ymax2);
-        const float ascale_f = (float)ascale;
-        const bool has_stats = !GEN && st.pstat != nullptr;         // the samplers already reduced |x|^2 and sum x of every point (opt-in)
-        const bool active = c0 < NSTEP * 16;
-        constexpr int RPW = TM / NLOAD;                              // rows per loader warp
-        static_assert(RPW == 32, "a loader warp owns one tensor-memory lane quadrant");
-        const int rq = qd * RPW + lane;                              // this thread's row in the contraction
-        double ki_prev = 0.0, sx_prev = 0.0;
-        float sc_prev = 0.0f;
-        for (int it = 0; it <= nit; ++it) {
-            double ki_new = 0.0, sx_new = 0.0;
-            float sc_new = 0.0f;
-            // --- class contractions of tile it - 1 (tp): epochs tp * NCLS .. + NCLS - 1
-            const int tp = it - 1;
-            int ce = 0;                                              // classes of tile tp contracted so far
-            const int nce = (it > 0) ? NCLS : 0;
-            auto class_ends = [&](bool block) {
-                while (ce < nce) {
-                    const int e = tp * NCLS + ce;
-                    if (block) mbar_wait(t_full(e), (uint32_t)(e >> 1) & 1u);
-                    else if (!mbar_test_wait(t_full(e), (uint32_t)(e >> 1) & 1u)) break;
+        const int rq = qd * 32 + lane;                               // this thread's row
+        for (int tp = 0; tp < nit; ++tp) {
+            mbar_wait(stage_full, (uint32_t)tp & 1u);                // tile tp is staged: its |x|^2 and row sums are in shared memory
+            double ki_prev, sx_prev;
+            float sc_prev;
+            {
+                const double nxr = Ki[(tp & 1) * TM + rq], sxr = sxs[(tp & 1) * TM + rq];
+                const int sh = row_shift(gp.a, nxr, ymax2);
+                sc_prev = exp2f((float)sh);
+                ki_prev = ldexp(exp(-0.5 * gp.a * nxr), TC_P_SHIFT - sh); sx_prev = sxr;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stage_free);                  // the scalars of tile tp have been read (their slot is re-used by tile tp + 2)
+            if (tp == 1 && qd == 0 && lane == 0) TC_STAMP(1);
+            for (int ce = 0; ce < NCLS; ++ce) {
+                const int e = tp * NCLS + ce;
+                mbar_wait(t_full(e), (uint32_t)(e >> 1) & 1u);
+                {
                     tc_fence_after();
                     const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
                     const bool ok = row < R;
@@ -866,50 +732,59 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         }
                         if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(247);
                     }
-                    ++ce;
                 }
-            };
-            if (it < nit) {
-            const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TM;
-            if (!GEN) {
-                // pull this warp's 32 rows of the tile AFTER this one into L2, a whole tile period ahead; the very first tile of a CTA also pulls its own rows
-                for (int ahead = (it == 0 ? 0 : 1); ahead <= 1; ++ahead) {
-                    const long rn = ((long)blockIdx.x + (long)(it + ahead) * gridDim.x) * TM + qd * RPW;
-                    if (it + ahead < nit && rn < R) {
-                        const long nrow = (R - rn < RPW) ? (R - rn) : RPW;
+            }
+        }
+    } else {
+        // ===== epilogue warps: group = pair parity; warp <-> (lane quadrant, sub-item of the pair); thread <-> point row x 48 centres =====
+        const int ew = warp - W_EPI0;                                // epilogue warp index 0..15
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const bool skip_math = (dflags & 2) != 0;
+        const double ymax2 = __ldg(st.ymax2);
+        const float ascale_f = (float)(gp.a * 1.4426950408889634);   // a log2(e): S = log2 of exp(a x.y)
+        const int grp = ew >> 3;
+        const int sub = (ew >> 2) & 1;
+        // --- staging of point tile ts: all 16 epilogue warps, 8 rows each (a' x = hi + lo in f16 into the staging buffer, |x|^2 and row sums into shared
+        // memory for the contraction warps; 16 lanes x 8 columns per row, one row per half-warp and step)
+        auto stage_tile = [&](int ts) {
+            {
+                const long row0 = ((long)blockIdx.x + (long)ts * gridDim.x) * TM;
+                constexpr int RPE = TM / NEPI;                       // rows per epilogue warp
+                const int hl = lane & 15, sub2 = lane >> 4;
+                const int c0 = hl * 8;
+                const bool active = c0 < NSTEP * 16;
+                if (ts + 1 < nit) {                                  // pull this warp's rows of the tile after it into L2, a whole tile period ahead
+                    const long rn = ((long)blockIdx.x + (long)(ts + 1) * gridDim.x) * TM + ew * RPE;
+                    if (rn < R) {
+                        const long nrow = (R - rn < RPE) ? (R - rn) : RPE;
                         const char* p0 = (const char*)(X + rn * (long)D);
                         const long nbytes = nrow * (long)D * 8;
                         for (long o = (long)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
                     }
                 }
-            }
-            if (it > 0) mbar_wait(stage_free, (uint32_t)(it - 1) & 1u);     // the previous tile's images are in tensor memory
-            if (GEN) {                                               // phase 1: lane <-> point (32 dependent-load chains in flight per warp)
-                const int rr = qd * RPW + lane;
-                gen_setup(*st.gen, st.gen_off + row0 + rr, row0 + rr < R, grec + rr);
-                __syncwarp();
-            }
-#pragma unroll 1
-            for (int pass = 0; pass < RPW / 4; ++pass) {
-                class_ends(false);                                   // a finished class of the current tile goes first: stage 2 of the class after next waits for its T buffer
-                double v[2][8];
+                // the contraction warps have read the scalars of tile ts - 2 (same slot).  Waited for as "they have started on tile ts - 1": that
+                // phase cannot be overtaken (their tile ts needs this very staging), whereas phase ts - 2 may already be two phases back, which a
+                // parity wait cannot tell from "pending"
+                if (ts >= 1) mbar_wait(stage_free, (uint32_t)(ts - 1) & 1u);
+                // four steps of one row per half-warp; the next step's row is in flight while the current one is converted (one exposed load latency per tile)
+                double vn[8];
+                auto load_row = [&](int stp) {
+                    const long row = row0 + ew * RPE + stp * 2 + sub2;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = qd * RPW + (pass * 2 + i) * 2 + sub;
-                    const long row = row0 + r;
-                    if (GEN) {
-                        gen_point(*st.gen, grec[r], st.gen_off + row, hl, lane, v[i], row < R);   // fused sampler: draw, write to HBM, stage
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int c = c0 + e;
-                            v[i][e] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
-                        }
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c0 + e;
+                        vn[e] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
                     }
-                }
+                };
+                load_row(0);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = qd * RPW + (pass * 2 + i) * 2 + sub;
+                for (int stp = 0; stp < RPE / 2; ++stp) {
+                    const int rr = ew * RPE + stp * 2 + sub2;
+                    double v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = vn[e];
+                    if (stp + 1 < RPE / 2) load_row(stp + 1);
                     double nx = 0.0, sx = 0.0;
                     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -918,9 +793,10 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const int c = c0 + e + q;
-                            const double val = v[i][e + q];
-                            if (!has_stats) { nx = fma(val, val, nx); if (c < d) sx += val; }
-                            sv[q] = (float)val * ascale_f;                 // columns >= D are zero (FP32 product: one FP64-pipe instruction less per element)
+                            const double val = v[e + q];
+                            nx = fma(val, val, nx);
+                            if (c < d) sx += val;
+                            sv[q] = (float)val * ascale_f;                 // columns >= D are zero
                         }
                         // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
                         const __half2 h = __floats2half2_rn(sv[0], sv[1]);
@@ -930,52 +806,28 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                         lo[e >> 1] = *(const uint32_t*)&l;
                     }
                     if (active) {
-                        uint8_t* p = sStage + (size_t)r * A_PITCH + (size_t)hl * 16;
+                        uint8_t* p = sStage + (size_t)rr * A_PITCH + (size_t)hl * 16;
                         *(uint4*)p = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *(uint4*)(p + (size_t)TM * A_PITCH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    if (!has_stats) {
 #pragma unroll
-                        for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
-                        if (hl == 0) { Ki[r] = nx; sxs[r] = sx; }
-                    }
+                    for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
+                    if (hl == 0) { Ki[(ts & 1) * TM + rr] = nx; sxs[(ts & 1) * TM + rr] = sx; }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stage_full);              // this warp's rows of tile ts are staged (16 arrivals complete the tile)
             }
-            if (GEN) __threadfence_block();                         // generated rows (global) are re-read by this warp's contraction
-            __syncwarp();
-            {   // lane <-> row (the row this thread contracts): |x|^2 and the row sum from this warp's reductions (or the sampler's statistics),
-                // exponent shift, K_i (one FP64 exp per lane instead of one per row pass)
-                double nxr, sxr;
-                if (has_stats) {
-                    const bool ok = row0 + rq < R;
-                    nxr = ok ? __ldg(st.pstat + 2 * (row0 + rq)) : 0.0;
-                    sxr = ok ? __ldg(st.pstat + 2 * (row0 + rq) + 1) : 0.0;
-                } else { nxr = Ki[rq]; sxr = sxs[rq]; }
-                const int sh = row_shift(gp.a, nxr, ymax2);
-                sc_new = exp2f((float)sh);
-                rsc[(it & 1) * TM + rq] = sc_new;                     // read by the epilogue warps after stage_full
-                ki_new = ldexp(exp(-0.5 * gp.a * nxr), TC_P_SHIFT - sh); sx_new = sxr;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(stage_full);                  // release: the staged tile is visible to the epilogue warps
-            if (it == 1 && qd == 0 && lane == 0) TC_STAMP(1);
-            }
-            class_ends(true);                                        // whatever is left of the current tile's classes
-            ki_prev = ki_new; sx_prev = sx_new; sc_prev = sc_new;
-        }
-    } else {
-        // ===== epilogue warps: group = pair parity; warp <-> (lane quadrant, sub-item of the pair); thread <-> point row x 48 centres =====
-        const int ew = warp - W_EPI0;                                // epilogue warp index 0..15
-        const int r = (warp & 3) * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const bool skip_math = (dflags & 2) != 0;
-        const int grp = ew >> 3;
-        const int sub = (ew >> 2) & 1;
+        };
+        // (Staging the next tile inside the main loop instead -- each epilogue group in turn, while the other group converts every pair of a
+        // six-pair window -- was tried: no shorter, tools/tc_timeline.py, and timing-sensitive in the product build.  The boundary costs ~10 k cycles
+        // per tile: the groups finish 1.5 k apart, staging ~5 k, image copy ~1 k, pipeline refill ~2 k.)
         long g = 0;                                                  // global pair counter
         for (int it = 0; it < nit; ++it) {
-            // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile
-            // have completed (the copying warps saw s_full of its last pair), so the images can be overwritten.
-            mbar_wait(stage_full, (uint32_t)it & 1u);
+            // --- tile `it` is staged at the tile boundary by all 16 epilogue warps
+            stage_tile(it);
+            mbar_wait(stage_full, (uint32_t)it & 1u);                // all 16 warps' rows
+            // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile have completed (the
+            // copying warps saw s_full of its last pairs at the end of their loop), so the images can be overwritten.
             if (ew < 8) {                                            // image = ew >> 2; 32-bit column c = K elements 2c, 2c + 1
                 const int img = ew >> 2;
                 const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
@@ -989,16 +841,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(stage_free); }
+                if (lane == 0) mbar_arrive(a_ready);
             }
             if (it == 1 && ew == 0 && lane == 0) TC_STAMP(2);
-            const float sc = rsc[(it & 1) * TM + r], nsc = -sc;      // 2^s of this thread's point row (written before stage_full of the tile)
+            // 2^s of this thread's point row: P - 2^s = 2^s ex2(S) - 2^s
+            const float sc = exp2f((float)row_shift(gp.a, Ki[(it & 1) * TM + r], ymax2)), nsc = -sc;
             const bool stamp = (it == 1);
             // --- main loop: S -> P - 2^s in place.  The fixed cost of a round trip (barrier wake-up, first tcgen05.ld, tcgen05.wait::st,
             // fence, arrive) is paid once per 48 columns per thread, with the next chunk's tcgen05.ld in flight during the current
             // chunk's ex2 work.  The two groups run half a period apart.
             for (int j = 0; j < npair; ++j, ++g) {
-                if ((int)(g & 1) != grp) continue;
+                if ((int)(g & 1) != grp) continue;                   // pair ownership alternates between the two groups
                 const bool two = PT_TWO(ptab[j]);
                 const int s = (int)(g % NSLOT2);
                 mbar_wait(s_full(s), (uint32_t)(g / NSLOT2) & 1u);
@@ -1055,28 +908,28 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #undef PT_TILE
 }
 
-template <int CLASS, int NSTEP, bool GEN>
+template <int CLASS, int NSTEP>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    return Ring<CLASS, NSTEP, GEN>::NB1 * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK2) + Ring<CLASS, NSTEP, GEN>::NB3 * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * Stage<NSTEP>::PITCH
+    return Ring<CLASS, NSTEP>::NB1 * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK2) + Ring<CLASS, NSTEP>::NB3 * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * Stage<NSTEP>::PITCH
            + (size_t)TM * TF_COUNT * 4 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t) + sizeof(float2)) + (size_t)TM * 4 * 8
-           + (GEN ? TM * sizeof(GenRec) : 0) + 2 * TM * 8 + 2 * TM * sizeof(float) + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
+           + 4 * TM * 8 + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
 }
 
-template <int CLASS, int NSTEP, bool GEN>
+template <int CLASS, int NSTEP>
 static int launch(const GpView& gp, const TcDev& st, const double* X, long R, int mode,
                   double* o0, double* o1, double* o2, double* o3, cudaStream_t stream) {
     // per-device attributes: set / queried on every launch (microseconds) so that a process may use several devices
-    const size_t smem = smem_bytes<CLASS, NSTEP, GEN>();
+    const size_t smem = smem_bytes<CLASS, NSTEP>();
     int dev = 0, nsm = 0;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SC_CUDA(cudaFuncSetAttribute(eval_tc_kernel<CLASS, NSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SC_REQUIRE(3 * ((st.ntile_all + 1) / 2) <= MAX_PAIRS, "tcgen05 route: too many collocation points for the pair table (use the FP64 route)");
     const long ntiles = cdiv(R, TM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);   // persistent: one CTA per SM
-    eval_tc_kernel<CLASS, NSTEP, GEN><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
+    eval_tc_kernel<CLASS, NSTEP><<<grid, NTHREADS_P, smem, stream>>>(gp, st, X, R, mode, o0, o1, o2, o3);
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -1612,7 +1465,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
 
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const LevelDev* gen_level_dev, long long gen_off, const TcDebug* dbg, const double* pstat) {
+                   const TcDebug* dbg, const double* pstat) {
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
@@ -1631,12 +1484,10 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.pstat = pstat;
     dv.ymax2 = (const double*)(st->images + st->ymax_off);
     dv.csum = (const double*)(st->images + st->csum_off) + cls * TC_MAXCOL;
-    dv.gen = gen_level_dev; dv.gen_off = gen_off;
     dv.dbg = dbg ? dbg->stamps : nullptr; dv.dbg_block = dbg ? (dbg->block & 0xFFFFFF) : 0; dv.dbg_flags = dbg ? (dbg->block >> 24) : 0;
     if (st->nstep > 8) {
         // K-streamed kernel: point images in a stream-ordered scratch buffer of this call (cudaMallocAsync: concurrent evaluations of
         // one handle on different streams never share it), processed in chunks
-        SC_REQUIRE(gen_level_dev == nullptr, "the fused sampler is not available on the K-streamed kernel");
         const int KB = (st->nstep + 3) / 4;
         const long chunk_pts = 148L * tc::TM * 4;                     // four point tiles per SM per launch
         const size_t per_tile = (size_t)KB * 2 * tc::A_BLK + 2 * tc::TM * sizeof(double) + tc::TM * sizeof(float);
@@ -1665,14 +1516,9 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     }
 #define SC_TC_DISPATCH(NS)                                                                                                  \
     do {                                                                                                                    \
-        if (dv.gen != nullptr) {                                                                                            \
-            if (cls == TC_U) return tc::launch<TC_U, NS, true>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);          \
-            if (cls == TC_UG) return tc::launch<TC_UG, NS, true>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);        \
-            return tc::launch<TC_PDE, NS, true>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                         \
-        }                                                                                                                   \
-        if (cls == TC_U) return tc::launch<TC_U, NS, false>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);             \
-        if (cls == TC_UG) return tc::launch<TC_UG, NS, false>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);           \
-        return tc::launch<TC_PDE, NS, false>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                            \
+        if (cls == TC_U) return tc::launch<TC_U, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                    \
+        if (cls == TC_UG) return tc::launch<TC_UG, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                  \
+        return tc::launch<TC_PDE, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                                   \
     } while (0)
     // the k-step count is a template parameter (lean single-thread MMA issue): images are zero-padded up to it
     if (st->nstep <= 2) SC_TC_DISPATCH(2);
@@ -1690,7 +1536,7 @@ int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, in
     TcDebug dbg;
     dbg.stamps = stamps_dev;
     dbg.block = block;
-    return launch_eval_tc(gp, &st, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream, nullptr, 0, &dbg);
+    return launch_eval_tc(gp, &st, X, R, mode, scratch_out, scratch_out + R, scratch_out + 2 * R, scratch_out + 3 * R, stream, &dbg);
 }
 #endif
 

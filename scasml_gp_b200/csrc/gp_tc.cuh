@@ -55,13 +55,10 @@ struct TcDebug {                     // debug build only: clock64 stamps of CTA 
 int tc_supported(const GpView& gp);
 size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills the layout fields and the column table
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
-struct LevelDev;
-// gen_level_dev != nullptr: fused sampler -- the kernel's loader warps generate points [gen_off, gen_off + R) of that level
-// (device copy of its LevelDev) into X instead of reading them
+// pstat: reserved (per-point (|x|^2, sum_i x_i) from a caller that has them); the kernel reduces them while staging
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const LevelDev* gen_level_dev = nullptr, long long gen_off = 0, const TcDebug* dbg = nullptr,
-                   const double* pstat = nullptr);   // pstat: [R][2] (|x|^2, sum_i x_i) per point when the caller has them (the samplers do)
+                   const TcDebug* dbg = nullptr, const double* pstat = nullptr);
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);

@@ -894,11 +894,6 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         for (size_t i = 0; i < hc.size(); ++i) rb[i] = hc[i].rowbase;
         SC_CUDA(cudaMemcpyAsync(ws + lr.off_rowbase, rb.data(), rb.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
     }
-    // fused sampler (tcgen05 route, ScaSML): the evaluation kernel's loader warps draw the points; needs the level records on the device
-    const bool fused = (route == 1) && p_.scasml && (p_.reserved & 1) && gp->D + 1 <= 128;
-    if (fused)
-        for (int L = 1; L <= n; ++L)
-            SC_CUDA(cudaMemcpyAsync(ws + levels_[L].off_lvdev, &lvs[L], sizeof(LevelDev), cudaMemcpyHostToDevice, stream));
     // sampler launch shape: persistent CTAs (two per SM when shared memory allows), 64 KB table + per-warp Philox / step buffers
     const int nslot = (d + 14) / 8;                    // Philox blocks covering d consecutive flat indices from any offset
     SC_REQUIRE(D <= 2048, "picard: d > 2047 is not supported by the sampler");
@@ -941,14 +936,14 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
             row_setup_kernel<<<(unsigned)cdiv(lv.NR, 256), 256, 0, stream>>>(lv);
             SC_LAUNCH_CHECK(); ++launches;
         }
-        if (!fused && lv.NT > 0) {
+        if (lv.NT > 0) {
             int nwarp, cpts; size_t smem; unsigned grid;
             sampler_shape(0, lv.NT, &nwarp, &smem, &grid, &cpts);
             const int rc = launch_sample_terminal(lv, nslot, cpts, grid, nwarp, smem, stream);
             if (rc != OK) return rc;
             ++launches;
         }
-        for (int l = 0; l < L && !fused; ++l) {
+        for (int l = 0; l < L; ++l) {
             if (lv.NP[l] == 0) continue;
             int nwarp, cpts; size_t smem; unsigned grid;
             sampler_shape(p_.variant == 0 ? lv.q[l] : 1, lv.NP[l], &nwarp, &smem, &grid, &cpts);
@@ -967,8 +962,7 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
                 begin_span(1);
                 if (route == 1)
                     rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
-                                        nullptr, nullptr, stream, fused ? (const LevelDev*)(ws + lr.off_lvdev) : nullptr, s.off, nullptr,
-                                        lv.pstat ? lv.pstat + 2 * s.off : nullptr);
+                                        nullptr, nullptr, stream);
                 else
                     rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                          nullptr, nullptr, stream);

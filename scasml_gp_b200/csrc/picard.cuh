@@ -30,7 +30,7 @@ struct PicardParams {
     int rank, world;          // top-level sample sharding: unit u owned iff u % world == rank
     long long gid0;           // global index of the first test point of this batch
     int timing;               // 1: CUDA-event timing of kernel groups (adds a stream sync)
-    int reserved;             // flags; bit 0: fused sampler on the tcgen05 route (the evaluation kernel's loader warps draw the points)
+    int reserved;             // must be 0
 };
 
 struct PicardStats {
@@ -80,7 +80,8 @@ struct LevelDev {
     double cnode[MAXLK], wnode[MAXLK];  // c[k][q-1], w[k][q-1]
     double* P;                          // point buffer [npoints][D]
     long long* gid;                     // [npoints]
-    double* pstat;                      // [npoints][2] (|X|^2, sum_i X_i) of every sample point, written by the samplers for the tcgen05 route (else null)
+    double* pstat;                      // reserved, null: per-point (|X|^2, sum_i X_i) from the samplers were measured -- at C3 the two FP64 warp reductions per
+                                        // point cost the samplers more (2.9 -> 4.7 ms per step) than the evaluation kernel saved (19.4 -> 18.2 ms)
     RowRec* rows;                       // [NR]
     double* ev0; double* ev1;           // evaluation outputs per point
     double* us[MAX_LEVEL + 1];          // finalized (u, zsum) per row, per level

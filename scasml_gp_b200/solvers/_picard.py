@@ -86,9 +86,6 @@ class PicardSolverBase(object):
     variant = 0                 # 0 quadrature, 1 full history
     scasml = False              # defect form with the surrogate
     stale_delta = False         # solvers/MLP.py:201,249,270
-    fused_sampler = False       # tcgen05 route: True = the evaluation kernel's loader warps draw the Brownian increments themselves
-                                # (bit-identical; measured slower at C3: 55 ms vs 29 ms per step, the four loader warps cannot
-                                # sustain the Philox + inverse-CDF gather work)
     route = None                # None: tcgen05 route for the sampled points when the GP supports it (d <= 1022 and float16-valued
                                 # collocation points: resident-operand kernel up to d = 126, K-streamed kernel above), else FP64
     quadrature = "reference"    # "reference" (bug-compatible lgwt) or "gauss_legendre" (flagged deviation)
@@ -158,7 +155,7 @@ class PicardSolverBase(object):
         p.seed, p.key_counter = int(self.seed), int(self.key) & 0xFFFFFFFF
         p.rank, p.world, p.gid0 = int(rank), int(world), 0
         p.timing = int(self.timing)
-        p.reserved = 1 if self.fused_sampler else 0
+        p.reserved = 0
         return p
 
     def plan(self, n, rho, B, M=None, rank=0, world=1):

@@ -119,29 +119,6 @@ def test_tc_solver_meets_north_star_criterion(mid):
         assert prod.evaluation_counter == orac.evaluation_counter
 
 
-def test_fused_sampler_matches_the_sampler_kernels(mid):
-    """On the tcgen05 route the evaluation kernel's loader warps draw the Brownian increments themselves (fused sampler).
-    Same Philox addressing, same operation order: switching the fusion off (stand-alone sampler kernels) must not change a bit."""
-    F, P = mid, mid.P
-    lib = P["lib"]
-    F.gp.set_right_vector(F.gp_o.right_vector)
-    X = F.test_points(150, 31)                              # 181 points: partial tiles, several CTAs
-    X[::7, -1] = F.eq_o.T                                   # degenerate steps included
-    for cls, args in ((P["ScaSML"], (3, 3, X)), (P["ScaSMLfh"], (3, None, X, 3))):
-        outs = []
-        for fused in (True, False):
-            s = cls(F.eq, F.gp)
-            s.route = lib.ROUTE_TC
-            s.quadrature = "gauss_legendre"
-            s.fused_sampler = fused
-            s.uz_solve(*args)
-            outs.append(s.last_raw.copy())
-        # same Philox addressing and operation order for the points themselves; the per-point |x|^2 / row sums are reduced in a different
-        # order (sampler kernels: lane <-> column; fused: 16 lanes x 8 columns), so K_i may differ in the last bit
-        assert np.array_equal(np.isnan(outs[0]), np.isnan(outs[1]))
-        np.testing.assert_allclose(outs[0], outs[1], rtol=1e-9, atol=1e-14)
-
-
 def test_k_streamed_kernel_in_the_solver(huge):
     """d = 300: the solver's sampled points go through the K-streamed tcgen05 kernel (point images streamed per 64-wide K block)."""
     F, P = huge, huge.P
