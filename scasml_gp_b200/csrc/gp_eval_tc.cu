@@ -58,11 +58,11 @@ struct TcDev {
     int npair_all;                   // resident-operand kernel: pairs of 48-centre tiles in the images (compact format)
     int ntile_all;                   // resident-operand kernel: 48-centre tiles of the compact centre list (k, kx classes); ntile_dom = those of the ky class
     const double* csum;              // [TC_MAXCOL] per column: sum over the centres of the scaled, split coefficients (baseline term of the coefficient GEMM)
-    const double* pstat;             // [R][2] (|x|^2, sum_i x_i) per point, or null: the loader warps compute them (public evaluation API, fused sampler)
+    const uint8_t* rec;              // resident-operand kernel: the points' operand records [R][tc_rec_bytes(NSTEP)] (gp_tc.cuh)
     const double* ymax2;             // device scalar: max_j |y_j|^2 over the centres (per-row exponent shift, row_shift())
     long long* dbg;
     int dbg_block;
-    int dbg_flags;                   // timeline experiments: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 8 no operand copies (garbage operands), 16 epilogue spins on s_full, 64 MMA issuers spin
+    int dbg_flags;                   // debug build: 1 skip stage-2 MMAs, 2 skip the epilogue arithmetic, 4 watchdog (a wait that runs out of probes names itself in the stamp buffer), 8 stage-2 hand-off by arrive instead of commit, 32 hh products only, 128 hl / lh products into the other T buffer
 };
 
 // ---- per-centre coefficient of one column (NumPy statement: tests/tc_expansion_ref.py::centre_coefficient) --------------
@@ -326,8 +326,9 @@ template <int CLASS, int NSTEP> struct Ring {
     static constexpr int NB3 = (CLASS == TC_PDE) ? (NSTEP == 8 ? 2 : 3) : (CLASS == TC_UG ? 2 : 4);
     static constexpr int NB1 = (CLASS == TC_PDE) ? 3 : 4;
 };
-// staging row pitch (bytes): the row's f16 image + 16, an odd multiple of 16, so that 16-byte reads of 8 rows hit 8 bank groups
-template <int NSTEP> struct Stage { static constexpr int PITCH = NSTEP * 32 + 16; };
+// staging buffer = the 128 operand records of a point tile as they lie in global memory (gp_tc.cuh): hi image | lo image | |x|^2 | sum x; the
+// record size, an odd multiple of 16, makes the 16-byte reads of 8 consecutive rows hit 8 bank groups
+template <int NSTEP> struct Stage { static constexpr int REC = NSTEP * 64 + 16; };
 constexpr int NLOAD = 4;                                             // loader warps
 constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 3) * 32;             // loaders | epilogue | producer | stage-1 issuer 0 | stage-2 issuer 0 | stage-1 issuer 1 | stage-2 issuer 1
 // The loader warps take the LOWEST warp ids: the warp scheduler favours them, and their background work (staging the next point tile,
@@ -336,10 +337,30 @@ constexpr int NTHREADS_P = (NEPI + 2 + NLOAD + 3) * 32;             // loaders |
 constexpr int W_LOAD0 = 0, W_EPI0 = NLOAD, W_PROD = W_EPI0 + NEPI, W_S1A = W_PROD + 1, W_S2A = W_PROD + 2, W_S1B = W_PROD + 3, W_S2B = W_PROD + 4;
 static_assert(W_EPI0 % 4 == 0, "lane quadrant = warp % 4");
 constexpr int MAX_PAIRS = 512;                                       // pair table entries (16 bits each): kernel class | two | first | last | centre tile
-// barriers: b1_full b1_empty (NB1 each) | b3_full b3_empty (NB3 <= 4 each) | s_full p_ready slot_free (NSLOT2 each) | t_full[2] t_free[2] | a_ready stage_full stage_free | ord[2]
+// barriers: b1_full b1_empty (NB1 each) | b3_full b3_empty (NB3 <= 4 each) | s_full (2 NSLOT2) p_ready slot_free (NSLOT2 each) | t_full[2] t_free[2] | a_ready stage_full (unused) | ord[2]
 constexpr int NB3_MAX = 4;
-constexpr int NBAR = 2 * NB1_MAX + 2 * NB3_MAX + 3 * NSLOT2 + 4 + 3 + 2;   // + ord[2]: stage-2 issue order hand-off between the two stage-2 issuers
+// s_full: one barrier per (slot, group) = pair index mod 6.  With one barrier per slot (pair mod 3) the waiters of consecutive phases alternated
+// between the two epilogue groups: a group waiting for pair g had never observed the phase of pair g - 3 (the other group's, issued by the other
+// stage-1 issuer), and a parity wait cannot tell "phase k pending" from "phase k - 1 still pending" -- whenever that issuer ran ~1.5 pairs late the
+// wait returned at once and the group converted a stale slot (rare, timing-dependent NaN rows; a delay in an issuer deadlocked: tools/stress_eval.py).
+// Barrier g mod 6 is only ever waited on by the group of parity g mod 2, phase after phase.
+constexpr int NSF = 2 * NSLOT2;
+constexpr int NBAR = 2 * NB1_MAX + 2 * NB3_MAX + NSF + 2 * NSLOT2 + 4 + 3 + 2;   // + ord[2]: stage-2 issue order hand-off between the two stage-2 issuers
 static_assert(COL_T2 + 2 * NTMAX == COL_A && COL_A + 2 * A_IMG_COLS == 512, "tensor-memory map");
+
+// debug build only (tools/stress_eval.py): bounded wait that names the waiter before it traps
+__device__ __noinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, long long* dbg, int line) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 21)) {
+            if (atomicCAS((unsigned long long*)(dbg + 960), 0ull, (unsigned long long)line) == 0ull) {
+                dbg[961] = blockIdx.x; dbg[962] = threadIdx.x >> 5; dbg[963] = parity; dbg[964] = bar;
+                __threadfence_system();
+            }
+            asm volatile("trap;");
+        }
+    }
+}
 
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
     uint32_t r;
@@ -383,15 +404,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     constexpr uint32_t B3_SLOT = 2 * B3_SUB;                         // a pair
     constexpr uint32_t B1_SLOT = KB * 2 * B1_BLK2;                   // a pair's centre rows: per K block [sub-item a rows | sub-item b rows]
     constexpr int NB3 = Ring<CLASS, NSTEP>::NB3, NB1 = Ring<CLASS, NSTEP>::NB1;
-    constexpr int A_PITCH = Stage<NSTEP>::PITCH;
+    constexpr int RECB = Stage<NSTEP>::REC;                          // bytes of a point's operand record
+    constexpr int REC_STAT = NSTEP * 64;                             // offset of (|x|^2, sum x) inside a record, behind its 16 NSTEP words (hi | lo << 16)
+    static_assert(RECB == NSTEP * 64 + 16, "record layout (gp_tc.cuh::tc_rec_bytes)");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];            // no static smem in this kernel: window offset 0
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) { asm volatile("trap;"); }
     uint8_t* sB1 = smem;                                             // NB1 pair slots
     uint8_t* sB3 = sB1 + NB1 * (size_t)B1_SLOT;                      // NB3 pair slots
-    uint8_t* sStage = sB3 + NB3 * (size_t)B3_SLOT;                   // A staging [hi | lo][128 rows][A_PITCH] (loader -> tensor memory)
-    float* feat = (float*)(sStage + 2 * (size_t)TM * A_PITCH);       // [128][TF_COUNT] features (floats) of the tile being contracted
+    uint8_t* sStage = sB3 + NB3 * (size_t)B3_SLOT;                   // the operand records of the next / current point tile (bulk copy -> tensor memory)
+    float* feat = (float*)(sStage + (size_t)TM * RECB);              // [128][TF_COUNT] features (floats) of the tile being contracted
     // column table of the contraction, in the form its inner loop wants: per column the byte offsets of its two features in a
     // row's float feature vector (f1 | f2 << 16), its scale 1 / (2^s 2^TC_P_SHIFT) spread over the four outputs as a one-hot float4
     // (the contraction is issue-bound) and the column sum of its coefficients as (hi, lo) floats (baseline term)
@@ -399,9 +422,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint32_t* soff = (uint32_t*)(smask + TC_MAXCOL);                 // [TC_MAXCOL]
     float2* scs = (float2*)(soff + TC_MAXCOL);                       // [TC_MAXCOL]
     double* acc4 = (double*)(scs + TC_MAXCOL);                       // [128][4] output sums (u, div, lap, dt) of the tile being contracted, across its classes
-    double* Ki = acc4 + TM * 4;                                      // [2][128] |x|^2 of the staged tiles, by tile parity
-    double* sxs = Ki + 2 * TM;                                       // [2][128] sum_{i<d} x_i
-    uint64_t* bars = (uint64_t*)(sxs + 2 * TM);
+    uint64_t* bars = (uint64_t*)(acc4 + TM * 4);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
     uint16_t* ptab = (uint16_t*)(tmem_slot + 4);                     // [npair] pairs of the class-major stream of one point tile
 
@@ -413,16 +434,18 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     const int dflags = DBG ? st.dbg_flags : 0;                        // experiment switches (debug build only): 1 no stage-2 MMAs, 2 no epilogue arithmetic
 #define TC_STAMP(slot) do { if (DBG && dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
+    // debug build: a wait that runs out of probes reports (source line, CTA, warp, parity) through the stamp buffer (pinned host memory survives the trap)
+#define MBW(bar, par) do { if (DBG && (dflags & 4)) mbar_wait_tag((bar), (par), st.dbg, __LINE__); else mbar_wait((bar), (par)); } while (0)
     const uint32_t bar0 = smem_u32(bars);
     auto b1_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     auto b1_empty = [&](int i) { return bar0 + 8u * (uint32_t)(NB1_MAX + i); };
     auto b3_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + i); };
     auto b3_empty = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + NB3_MAX + i); };
     auto s_full = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + i); };
-    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSLOT2 + i); };
-    auto slot_free = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + 2 * NSLOT2 + i); };
-    const uint32_t t_full0 = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + 3 * NSLOT2), t_free0 = t_full0 + 16u, a_ready = t_full0 + 32u,
-                   stage_full = t_full0 + 40u, stage_free = t_full0 + 48u, ord0 = t_full0 + 56u;
+    auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSF + i); };
+    auto slot_free = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSF + NSLOT2 + i); };
+    const uint32_t t_full0 = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSF + 2 * NSLOT2), t_free0 = t_full0 + 16u, a_ready = t_full0 + 32u,
+                   stage_full = t_full0 + 40u, ord0 = t_full0 + 56u;
     // T accumulators: one per class epoch e = tile * NCLS + class, double-buffered by epoch parity.  One barrier pair per buffer: a
     // waiter is never more than one phase behind.
     auto t_full = [&](int e) { return t_full0 + 8u * (uint32_t)(e & 1); };
@@ -431,9 +454,10 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     if (tid == 0) {
         for (int i = 0; i < NB1; ++i) { mbar_init(b1_full(i), 1); mbar_init(b1_empty(i), 1); }
         for (int i = 0; i < NB3; ++i) { mbar_init(b3_full(i), 1); mbar_init(b3_empty(i), 1); }
-        for (int i = 0; i < NSLOT2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_ready(i), NEPI / 2); mbar_init(slot_free(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 1); mbar_init(t_free0 + 8u * i, NLOAD); }
-        mbar_init(a_ready, 8); mbar_init(stage_full, NEPI); mbar_init(stage_free, NLOAD);
+        for (int i = 0; i < NSF; ++i) mbar_init(s_full(i), 1);
+        for (int i = 0; i < NSLOT2; ++i) { mbar_init(p_ready(i), NEPI / 2); mbar_init(slot_free(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 2); mbar_init(t_free0 + 8u * i, NLOAD); }
+        mbar_init(a_ready, NEPI + NLOAD); mbar_init(stage_full, 1);
         mbar_init(ord0, 1); mbar_init(ord0 + 8u, 1);
         fence_barrier_init();
     }
@@ -482,7 +506,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             int p1 = 0, j1 = 0, j3 = 0;
             auto load_b1 = [&]() {
                 const int s = p1 % NB1;
-                if (p1 >= NB1) mbar_wait(b1_empty(s), (uint32_t)((p1 / NB1) - 1) & 1u);
+                if (p1 >= NB1) MBW(b1_empty(s), (uint32_t)((p1 / NB1) - 1) & 1u);
                 const uint32_t e = ptab[j1];
                 const int kc = PT_KERN(e), t0 = PT_TILE(e);
                 const bool two = PT_TWO(e);
@@ -497,7 +521,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             for (int p = 0; p < ptotal; ++p) {
                 while (p1 < ptotal && p1 < p + NB1) load_b1();               // centre rows run NB1 - 1 pairs ahead of the coefficient images
                 const int q = p % NB3;
-                if (p >= NB3) mbar_wait(b3_empty(q), (uint32_t)((p / NB3) - 1) & 1u);
+                if (p >= NB3) MBW(b3_empty(q), (uint32_t)((p / NB3) - 1) & 1u);
                 const uint32_t e = ptab[j3];
                 const int kc = PT_KERN(e), t0 = PT_TILE(e);
                 const bool two = PT_TWO(e);
@@ -523,11 +547,23 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const uint32_t idS2 = make_idesc(TM, 2 * TN2), idS1 = make_idesc(TM, TN2);
         const uint32_t aBase = tmem_base + COL_A;
         int p = 0;                                                   // global pair counter
+        // The operand records of a point tile are one contiguous piece of global memory: issuer 0 moves them into the staging buffer with ONE bulk
+        // copy per tile -- tile 0 at once, tile it + 1 as soon as tile `it` has left the buffer (a_ready: its images are in tensor memory and every
+        // warp has read its rows' scalars), i.e. a whole main loop before it is needed.  (Staging used to be computed here from the FP64 rows, at the
+        // tile boundary: ~11 k cycles of load latency and FP64 conversions per tile with the tensor pipe idle, tools/tc_timeline.py.)
+        auto copy_records = [&](int ts) {
+            const long row0 = ((long)blockIdx.x + (long)ts * gridDim.x) * TM;
+            const uint32_t nrow = (uint32_t)((R - row0 < TM) ? (R - row0) : TM);    // a partial tile leaves stale rows behind: they only reach their own (unwritten) outputs
+            mbar_expect_tx(stage_full, nrow * (uint32_t)RECB);
+            bulk_g2s(smem_u32(sStage), st.rec + (size_t)row0 * RECB, nrow * (uint32_t)RECB, stage_full);
+        };
+        if (w == 0 && el) copy_records(0);
         for (int it = 0; it < nit; ++it) {
             const bool stamp = (it == 1);
             if (el && it == 1 && w == 0) TC_STAMP(244);
-            mbar_wait(a_ready, (uint32_t)it & 1u);                   // A images of this point tile are in tensor memory
+            MBW(a_ready, (uint32_t)it & 1u);                   // A images of this point tile are in tensor memory
             tc_fence_after();
+            if (w == 0 && el && it + 1 < nit) copy_records(it + 1);
             for (int j = 0; j < npair; ++j, ++p) {
                 if ((p & 1) != w) continue;
                 const int s = p % NSLOT2, s1 = p % NB1;
@@ -535,9 +571,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 const uint32_t idesc = PT_TWO(ptab[j]) ? idS2 : idS1;
                 if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
                 // the slot's previous P has been consumed: stage 2 of pair p - NSLOT2 has COMPLETED
-                if (p >= NSLOT2) { mbar_wait(slot_free(s), (uint32_t)((p / NSLOT2) - 1) & 1u); tc_fence_after(); }
+                if (p >= NSLOT2) { MBW(slot_free(s), (uint32_t)((p / NSLOT2) - 1) & 1u); tc_fence_after(); }
                 if (el && stamp && j < 60) TC_STAMP(256 + 8 * j);
-                mbar_wait(b1_full(s1), (uint32_t)(p / NB1) & 1u);    // bulk-copy bytes landed (async proxy)
+                MBW(b1_full(s1), (uint32_t)(p / NB1) & 1u);    // bulk-copy bytes landed (async proxy)
                 if (el && stamp && j < 60) TC_STAMP(257 + 8 * j);
                 const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
                 if (el) {
@@ -558,7 +594,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
                 }
                 if (el && stamp && j < 60) TC_STAMP(258 + 8 * j);
-                if (el) { umma_commit(b1_empty(s1)); umma_commit(s_full(s)); }   // centre-row slot reusable; accumulators ready
+                if (el) { umma_commit(b1_empty(s1)); umma_commit(s_full(p % NSF)); }   // centre-row slot reusable; accumulators ready
                 if (el && stamp && j < 60) TC_STAMP(259 + 8 * j);
                 __syncwarp();
             }
@@ -582,14 +618,14 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const int kc = PT_KERN(e);
                     const bool two = PT_TWO(e), first = PT_FIRST(e);
                     // P written over S by the pair's epilogue group + coefficient images landed
-                    mbar_wait(p_ready(s), (uint32_t)(p / NSLOT2) & 1u);
+                    MBW(p_ready(s), (uint32_t)(p / NSLOT2) & 1u);
                     if (el && stamp && j < 60) TC_STAMP(260 + 8 * j);
-                    mbar_wait(b3_full(q), (uint32_t)(p / NB3) & 1u);
+                    MBW(b3_full(q), (uint32_t)(p / NB3) & 1u);
                     if (el && stamp && j < 60) TC_STAMP(261 + 8 * j);
                     // first pair of a class: its T buffer has been contracted by the loader warps (class epoch - 2)
-                    if (first && epoch >= 2) mbar_wait(t_free(epoch), (uint32_t)((epoch >> 1) - 1) & 1u);
+                    if (first && epoch >= 2) MBW(t_free(epoch), (uint32_t)((epoch >> 1) - 1) & 1u);
                     // the other issuer has issued pair p - 1
-                    if (p >= 1) mbar_wait(ord_mine, (uint32_t)(w == 1 ? (p >> 1) : ((p >> 1) - 1)) & 1u);
+                    if (p >= 1) MBW(ord_mine, (uint32_t)(w == 1 ? (p >> 1) : ((p >> 1) - 1)) & 1u);
                     tc_fence_after();
                     const uint32_t ncol = (uint32_t)CL::ncol(kc);
                     const uint32_t idesc = make_idesc(TM, (int)ncol);
@@ -621,10 +657,22 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     }
                     if (el && stamp && j < 60) TC_STAMP(262 + 8 * j);
                     if (el) {
-                        mbar_arrive(ord_other);                       // the other issuer may issue pair p + 1
+                        // the other issuer may issue pair p + 1.  The fence orders this thread's MMAs before the hand-off: without it the other
+                        // issuer's first MMAs could overtake this pair's last ones on their way to the tensor pipe (results then differed from run
+                        // to run in the last bit of a few rows -- a different accumulation order: tools/stress_eval.py)
+                        if (dflags & 8) { tc_fence_before(); mbar_arrive(ord_other); } else umma_commit(ord_other);
                         umma_commit(b3_empty(q));                     // coefficient slot reusable (producer)
                         umma_commit(slot_free(s));                    // P consumed (stage-1 issuers)
-                        if (PT_LAST(e)) umma_commit(t_full(epoch));   // the class's T is complete (loader warps)
+                        // The class's T is complete (contraction warps) when the MMAs of BOTH issuers have completed: a commit only covers the
+                        // MMAs of the committing thread, so t_full takes two -- from the issuer of the class's last pair and from the other one
+                        // after ITS last pair of the class (the one before).  With the last pair's commit alone the contraction now and then read a
+                        // T that still lacked the other issuer's final products in some rows (last-bit differences from run to run).
+                        if (PT_LAST(e)) {
+                            umma_commit(t_full(epoch));
+                            if (PT_FIRST(e)) umma_commit(t_full(epoch));          // a class of one pair
+                        } else if (j + 1 < npair && PT_LAST(ptab[j + 1]) && !PT_FIRST(ptab[j + 1])) {
+                            umma_commit(t_full(epoch));
+                        }
                         if (stamp && j < 60) TC_STAMP(5 + 4 * j);
                     }
                     __syncwarp();
@@ -644,21 +692,21 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const double ymax2 = __ldg(st.ymax2);
         const int rq = qd * 32 + lane;                               // this thread's row
         for (int tp = 0; tp < nit; ++tp) {
-            mbar_wait(stage_full, (uint32_t)tp & 1u);                // tile tp is staged: its |x|^2 and row sums are in shared memory
+            MBW(stage_full, (uint32_t)tp & 1u);                // the records of tile tp have landed: |x|^2 and the row sum of this thread's row
             double ki_prev, sx_prev;
             float sc_prev;
             {
-                const double nxr = Ki[(tp & 1) * TM + rq], sxr = sxs[(tp & 1) * TM + rq];
-                const int sh = row_shift(gp.a, nxr, ymax2);
+                const double2 stat = *(const double2*)(sStage + (size_t)rq * RECB + REC_STAT);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);                 // this warp is done with the staging buffer (the next tile's records may land)
+                const int sh = row_shift(gp.a, stat.x, ymax2);
                 sc_prev = exp2f((float)sh);
-                ki_prev = ldexp(exp(-0.5 * gp.a * nxr), TC_P_SHIFT - sh); sx_prev = sxr;
+                ki_prev = ldexp(exp(-0.5 * gp.a * stat.x), TC_P_SHIFT - sh); sx_prev = stat.y;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(stage_free);                  // the scalars of tile tp have been read (their slot is re-used by tile tp + 2)
             if (tp == 1 && qd == 0 && lane == 0) TC_STAMP(1);
             for (int ce = 0; ce < NCLS; ++ce) {
                 const int e = tp * NCLS + ce;
-                mbar_wait(t_full(e), (uint32_t)(e >> 1) & 1u);
+                MBW(t_full(e), (uint32_t)(e >> 1) & 1u);
                 {
                     tc_fence_after();
                     const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
@@ -742,110 +790,40 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const bool skip_math = (dflags & 2) != 0;
         const double ymax2 = __ldg(st.ymax2);
-        const float ascale_f = (float)(gp.a * 1.4426950408889634);   // a log2(e): S = log2 of exp(a x.y)
         const int grp = ew >> 3;
         const int sub = (ew >> 2) & 1;
-        // --- staging of point tile ts: all 16 epilogue warps, 8 rows each (a' x = hi + lo in f16 into the staging buffer, |x|^2 and row sums into shared
-        // memory for the contraction warps; 16 lanes x 8 columns per row, one row per half-warp and step)
-        auto stage_tile = [&](int ts) {
-            {
-                const long row0 = ((long)blockIdx.x + (long)ts * gridDim.x) * TM;
-                constexpr int RPE = TM / NEPI;                       // rows per epilogue warp
-                const int hl = lane & 15, sub2 = lane >> 4;
-                const int c0 = hl * 8;
-                const bool active = c0 < NSTEP * 16;
-                if (ts + 1 < nit) {                                  // pull this warp's rows of the tile after it into L2, a whole tile period ahead
-                    const long rn = ((long)blockIdx.x + (long)(ts + 1) * gridDim.x) * TM + ew * RPE;
-                    if (rn < R) {
-                        const long nrow = (R - rn < RPE) ? (R - rn) : RPE;
-                        const char* p0 = (const char*)(X + rn * (long)D);
-                        const long nbytes = nrow * (long)D * 8;
-                        for (long o = (long)lane * 128; o < nbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
-                    }
-                }
-                // the contraction warps have read the scalars of tile ts - 2 (same slot).  Waited for as "they have started on tile ts - 1": that
-                // phase cannot be overtaken (their tile ts needs this very staging), whereas phase ts - 2 may already be two phases back, which a
-                // parity wait cannot tell from "pending"
-                if (ts >= 1) mbar_wait(stage_free, (uint32_t)(ts - 1) & 1u);
-                // four steps of one row per half-warp; the next step's row is in flight while the current one is converted (one exposed load latency per tile)
-                double vn[8];
-                auto load_row = [&](int stp) {
-                    const long row = row0 + ew * RPE + stp * 2 + sub2;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = c0 + e;
-                        vn[e] = (row < R && c < D) ? __ldg(X + row * (long)D + c) : 0.0;
-                    }
-                };
-                load_row(0);
-#pragma unroll
-                for (int stp = 0; stp < RPE / 2; ++stp) {
-                    const int rr = ew * RPE + stp * 2 + sub2;
-                    double v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = vn[e];
-                    if (stp + 1 < RPE / 2) load_row(stp + 1);
-                    double nx = 0.0, sx = 0.0;
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
-                        float sv[2];
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int c = c0 + e + q;
-                            const double val = v[e + q];
-                            nx = fma(val, val, nx);
-                            if (c < d) sx += val;
-                            sv[q] = (float)val * ascale_f;                 // columns >= D are zero
-                        }
-                        // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
-                        const __half2 h = __floats2half2_rn(sv[0], sv[1]);
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn(sv[0] - hf.x, sv[1] - hf.y);
-                        hi[e >> 1] = *(const uint32_t*)&h;
-                        lo[e >> 1] = *(const uint32_t*)&l;
-                    }
-                    if (active) {
-                        uint8_t* p = sStage + (size_t)rr * A_PITCH + (size_t)hl * 16;
-                        *(uint4*)p = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *(uint4*)(p + (size_t)TM * A_PITCH) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-#pragma unroll
-                    for (int o = 8; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
-                    if (hl == 0) { Ki[(ts & 1) * TM + rr] = nx; sxs[(ts & 1) * TM + rr] = sx; }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(stage_full);              // this warp's rows of tile ts are staged (16 arrivals complete the tile)
-            }
-        };
-        // (Staging the next tile inside the main loop instead -- each epilogue group in turn, while the other group converts every pair of a
-        // six-pair window -- was tried: no shorter, tools/tc_timeline.py, and timing-sensitive in the product build.  The boundary costs ~10 k cycles
-        // per tile: the groups finish 1.5 k apart, staging ~5 k, image copy ~1 k, pipeline refill ~2 k.)
         long g = 0;                                                  // global pair counter
         for (int it = 0; it < nit; ++it) {
-            // --- tile `it` is staged at the tile boundary by all 16 epilogue warps
-            stage_tile(it);
-            mbar_wait(stage_full, (uint32_t)it & 1u);                // all 16 warps' rows
+            // --- the operand records of tile `it` were bulk-copied into the staging buffer during the previous main loop
+            MBW(stage_full, (uint32_t)it & 1u);
+            if (it == 1 && ew == 0 && lane == 0) TC_STAMP(1);
+            const uint8_t* rowp = sStage + (size_t)r * RECB;
+            const double nx_r = *(const double*)(rowp + REC_STAT);   // |x|^2 of this thread's point row
             // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile have completed (the
             // copying warps saw s_full of its last pairs at the end of their loop), so the images can be overwritten.
-            if (ew < 8) {                                            // image = ew >> 2; 32-bit column c = K elements 2c, 2c + 1
+            if (ew < 8) {                                            // image = ew >> 2 (hi | lo); 32-bit column c = K elements 2c, 2c + 1
                 const int img = ew >> 2;
-                const uint8_t* rowp = sStage + (size_t)img * TM * A_PITCH + (size_t)r * A_PITCH;
+                const uint32_t sel = img ? 0x7632u : 0x5410u;        // a record word is (hi | lo << 16) of one K element: pick this image's halves
                 const uint32_t taddr = tmem_base + COL_A + (uint32_t)img * A_IMG_COLS + lane_addr;
 #pragma unroll
                 for (int ks = 0; ks < NSTEP; ++ks) {
-                    const uint4 q0 = *(const uint4*)(rowp + ks * 32), q1 = *(const uint4*)(rowp + ks * 32 + 16);
-                    const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    uint32_t wv[8];
+#pragma unroll
+                    for (int h4 = 0; h4 < 4; ++h4) {
+                        const uint4 q = *(const uint4*)(rowp + ks * 64 + h4 * 16);
+                        wv[2 * h4] = __byte_perm(q.x, q.y, sel);
+                        wv[2 * h4 + 1] = __byte_perm(q.z, q.w, sel);
+                    }
                     tmem_st8(taddr + (uint32_t)ks * 8u, wv);
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_ready);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);                     // images in tensor memory / this warp is done with the staging buffer
             if (it == 1 && ew == 0 && lane == 0) TC_STAMP(2);
             // 2^s of this thread's point row: P - 2^s = 2^s ex2(S) - 2^s
-            const float sc = exp2f((float)row_shift(gp.a, Ki[(it & 1) * TM + r], ymax2)), nsc = -sc;
+            const float sc = exp2f((float)row_shift(gp.a, nx_r, ymax2)), nsc = -sc;
             const bool stamp = (it == 1);
             // --- main loop: S -> P - 2^s in place.  The fixed cost of a round trip (barrier wake-up, first tcgen05.ld, tcgen05.wait::st,
             // fence, arrive) is paid once per 48 columns per thread, with the next chunk's tcgen05.ld in flight during the current
@@ -854,7 +832,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 if ((int)(g & 1) != grp) continue;                   // pair ownership alternates between the two groups
                 const bool two = PT_TWO(ptab[j]);
                 const int s = (int)(g % NSLOT2);
-                mbar_wait(s_full(s), (uint32_t)(g / NSLOT2) & 1u);
+                MBW(s_full((int)(g % NSF)), (uint32_t)(g / NSF) & 1u);
                 tc_fence_after();
                 if ((ew & 7) == 0 && lane == 0 && stamp && j < 60) TC_STAMP(6 + 4 * j);
                 if (!skip_math && (sub == 0 || two)) {
@@ -891,7 +869,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             // (two stage-1 issuers: the last pair of each of them)
             if (ew < 8) {
                 for (long gl = (g >= 2 ? g - 2 : 0); gl < g; ++gl)   // the tile's last two pairs (g was advanced past them)
-                    mbar_wait(s_full((int)(gl % NSLOT2)), (uint32_t)(gl / NSLOT2) & 1u);
+                    MBW(s_full((int)(gl % NSF)), (uint32_t)(gl / NSF) & 1u);
                 tc_fence_after();
             }
         }
@@ -901,6 +879,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     if (tid == 0) TC_STAMP(3);
     if (warp == W_S1A) tmem_dealloc(tmem_base, 512);
 #undef TC_STAMP
+#undef MBW
 #undef PT_KERN
 #undef PT_TWO
 #undef PT_FIRST
@@ -908,13 +887,41 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #undef PT_TILE
 }
 
+// Operand records of a caller's points (public evaluation API, tools): one warp per row, lane <-> column (coalesced 256-byte row segments).
+// The very same arithmetic and summation tree as the Picard samplers' emission (picard.cu::rec_emit / rec_reduce2), so a point's record does
+// not depend on who wrote it: per-lane FMA / add chains over c = lane, lane + 32, ..., then the xor-16-8-4-2-1 butterfly.
+__global__ void __launch_bounds__(256) rec_image_kernel(const double* __restrict__ X, long R, int D, int d, int nstep, float ascale_f,
+                                                        uint8_t* __restrict__ rec) {
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= R) return;
+    const int NC = nstep * 16, recb = nstep * 64 + 16;
+    uint32_t* rw = (uint32_t*)(rec + (size_t)row * recb);
+    const double* xr = X + row * (long)D;
+    double nx = 0.0, sx = 0.0;
+    for (int c = lane; c < ((NC + 31) & ~31); c += 32) {
+        const double val = (c < D) ? __ldg(xr + c) : 0.0;
+        nx = fma(val, val, nx);
+        sx += val;                                                   // all D columns; the time column is taken out below
+        const float sv = (float)val * ascale_f;
+        // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
+        const float hf = __half2float(__float2half_rn(sv));
+        uint32_t w;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(sv - hf), "f"(hf));      // upper half: lo, lower half: hi
+        if (c < NC) rw[c] = w;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
+    if (lane == 0) { double* stp = (double*)(rw + NC); stp[0] = nx; stp[1] = sx - __ldg(xr + d); }
+}
+
 template <int CLASS, int NSTEP>
 static size_t smem_bytes() {
     using C = Cfg<CLASS>;
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
-    return Ring<CLASS, NSTEP>::NB1 * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK2) + Ring<CLASS, NSTEP>::NB3 * (2 * 2 * NMAX * 128) + 2 * (size_t)TM * Stage<NSTEP>::PITCH
+    return Ring<CLASS, NSTEP>::NB1 * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK2) + Ring<CLASS, NSTEP>::NB3 * (2 * 2 * NMAX * 128) + (size_t)TM * Stage<NSTEP>::REC
            + (size_t)TM * TF_COUNT * 4 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t) + sizeof(float2)) + (size_t)TM * 4 * 8
-           + 4 * TM * 8 + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
+           + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
 }
 
 template <int CLASS, int NSTEP>
@@ -1465,7 +1472,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
 
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const TcDebug* dbg, const double* pstat) {
+                   const TcDebug* dbg, const uint8_t* rec) {
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
@@ -1481,7 +1488,7 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.b1_tile_bytes = st->b1_tile_bytes;
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy; dv.ntile_all = st->ntile_all; dv.npair_all = st->npair_all;
-    dv.pstat = pstat;
+    dv.rec = rec;
     dv.ymax2 = (const double*)(st->images + st->ymax_off);
     dv.csum = (const double*)(st->images + st->csum_off) + cls * TC_MAXCOL;
     dv.dbg = dbg ? dbg->stamps : nullptr; dv.dbg_block = dbg ? (dbg->block & 0xFFFFFF) : 0; dv.dbg_flags = dbg ? (dbg->block >> 24) : 0;
@@ -1514,18 +1521,40 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
         cudaFreeAsync(scratch, stream);
         return rcode;
     }
+    // resident-operand kernel.  The k-step count is a template parameter (lean single-thread MMA issue): images are zero-padded up to it
+    auto run = [&](const double* Xc, long rc, const uint8_t* recs, double* p0, double* p1, double* p2, double* p3) -> int {
+        tc::TcDev d2 = dv;
+        d2.rec = recs;
 #define SC_TC_DISPATCH(NS)                                                                                                  \
     do {                                                                                                                    \
-        if (cls == TC_U) return tc::launch<TC_U, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                    \
-        if (cls == TC_UG) return tc::launch<TC_UG, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                  \
-        return tc::launch<TC_PDE, NS>(gp, dv, X, R, mode, out0, out1, out2, out3, stream);                                   \
+        if (cls == TC_U) return tc::launch<TC_U, NS>(gp, d2, Xc, rc, mode, p0, p1, p2, p3, stream);                          \
+        if (cls == TC_UG) return tc::launch<TC_UG, NS>(gp, d2, Xc, rc, mode, p0, p1, p2, p3, stream);                        \
+        return tc::launch<TC_PDE, NS>(gp, d2, Xc, rc, mode, p0, p1, p2, p3, stream);                                         \
     } while (0)
-    // the k-step count is a template parameter (lean single-thread MMA issue): images are zero-padded up to it
-    if (st->nstep <= 2) SC_TC_DISPATCH(2);
-    if (st->nstep <= 4) SC_TC_DISPATCH(4);
-    if (st->nstep <= 7) SC_TC_DISPATCH(7);
-    SC_TC_DISPATCH(8);
+        if (st->nstep <= 2) SC_TC_DISPATCH(2);
+        if (st->nstep <= 4) SC_TC_DISPATCH(4);
+        if (st->nstep <= 7) SC_TC_DISPATCH(7);
+        SC_TC_DISPATCH(8);
 #undef SC_TC_DISPATCH
+    };
+    SC_REQUIRE(st->nstep == tc_rec_nstep(gp.D), "tc: k-step count of the images and of the operand records differ");
+    if (rec != nullptr) return run(X, R, rec, out0, out1, out2, out3);
+    // a caller without records (public evaluation API, tools): a pre-pass writes them into a stream-ordered scratch buffer of this call, in
+    // chunks of eight point tiles per SM (the scratch stays L2-sized: 70 MB at d = 100)
+    const size_t recb = (size_t)tc_rec_bytes(st->nstep);
+    const long chunk_pts = 148L * tc::TM * 8;
+    uint8_t* scratch = nullptr;
+    SC_CUDA(cudaMallocAsync((void**)&scratch, (size_t)(R < chunk_pts ? R : chunk_pts) * recb, stream));
+    int rcode = OK;
+    for (long r0 = 0; r0 < R && rcode == OK; r0 += chunk_pts) {
+        const long rc = (R - r0 < chunk_pts) ? (R - r0) : chunk_pts;
+        const double* Xc = X + r0 * (long)gp.D;
+        tc::rec_image_kernel<<<(unsigned)cdiv(rc * 32, 256), 256, 0, stream>>>(Xc, rc, gp.D, gp.d, st->nstep, tc_rec_ascale(gp.a), scratch);
+        if (cudaGetLastError() != cudaSuccess) { rcode = ERR_CUDA; set_error("rec_image_kernel launch failed"); break; }
+        rcode = run(Xc, rc, scratch, out0 + r0, out1 ? out1 + r0 : nullptr, out2 ? out2 + r0 : nullptr, out3 ? out3 + r0 : nullptr);
+    }
+    cudaFreeAsync(scratch, stream);
+    return rcode;
 }
 
 #ifdef SCASML_DEBUG_HOOKS

@@ -52,13 +52,26 @@ struct TcDebug {                     // debug build only: clock64 stamps of CTA 
     int block = 0;
 };
 
+// Per-point operand record of the resident-operand kernel (d + 2 <= 128): what its A operand needs of a point, written by whoever
+// produces the point (the Picard samplers, while the coordinates are in registers) or by a pre-pass over a caller's X:
+//   [ 16 nstep words (hi | lo << 16), f16 | |x|^2 f64 | sum_{i<d} x_i f64 ],   a log2(e) x_j = hi_j + lo_j   (columns >= D are zero)
+// The record size is an odd multiple of 16 bytes: a 128-point tile is ONE contiguous bulk copy into shared memory, and the
+// row-per-thread 16-byte reads that move it on into tensor memory are bank-conflict free.
+__host__ __device__ inline int tc_rec_nstep(int D) {               // instantiated k-step counts; 0: K-streamed kernel (no records)
+    const int n = (D + 1 + 15) / 16;
+    return n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 7 ? 7 : (n <= 8 ? 8 : 0)));
+}
+__host__ __device__ inline int tc_rec_bytes(int nstep) { return nstep * 64 + 16; }
+__host__ __device__ inline float tc_rec_ascale(double a) { return (float)(a * 1.4426950408889634); }   // S = log2 of exp(a x.y)
+
 int tc_supported(const GpView& gp);
 size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills the layout fields and the column table
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
-// pstat: reserved (per-point (|x|^2, sum_i x_i) from a caller that has them); the kernel reduces them while staging
+// rec: the points' operand records [R][tc_rec_bytes] (resident-operand kernel) from a caller that has them (the Picard samplers); null: a
+// pre-pass over X writes them into a stream-ordered scratch buffer of this call
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const TcDebug* dbg = nullptr, const double* pstat = nullptr);
+                   const TcDebug* dbg = nullptr, const uint8_t* rec = nullptr);
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);

@@ -155,7 +155,8 @@ int PicardPlan::build(const PicardParams& p, long B) {
         executed += pt;
         lv.off_P = take((size_t)pt * D * sizeof(double));
         lv.off_gid = take((size_t)pt * sizeof(long long));
-        lv.off_pstat = take(0);
+        // operand records of the tcgen05 evaluation kernel (written by the samplers; unused on the FP64 route)
+        lv.off_rec = take((p.scasml && tc_rec_nstep(D) > 0) ? (size_t)pt * tc_rec_bytes(tc_rec_nstep(D)) : 0);
         lv.off_rows = take((size_t)lv.NR * sizeof(RowRec));
         lv.off_ev0 = take((size_t)pt * sizeof(double));
         lv.off_ev1 = take((size_t)pt * sizeof(double));
@@ -250,8 +251,44 @@ struct PtRec {
 };
 constexpr int SMP_WARP_FIXED = 32 * (int)sizeof(PtRec);     // bytes per warp besides the Philox buffer / step scalars
 
+// ---- operand records of the tcgen05 evaluation kernel (gp_tc.cuh), written while a point's coordinates are in registers ----
+// Column j of a point (lane <-> column): one 32-bit word (hi | lo << 16), the f16 split of a log2(e) x_j (columns past the row are zero), and
+// this lane's share of |x|^2 and of sum x over ALL D columns (the writer takes the time column out of the sum again).  EDGE: the pass may reach
+// past the row (only a point's last pass of 32 columns does).  The same arithmetic as gp_eval_tc.cu::rec_image_kernel.
+template <bool EDGE>
+__device__ __forceinline__ void rec_emit(uint32_t* rw, int j, int NC, double v, bool inrow, float asc, double& nx, double& sx) {
+    const double vv = (!EDGE || inrow) ? v : 0.0;
+    nx = fma(vv, vv, nx);
+    sx += vv;
+    const float sv = (float)vv * asc;
+    // hi + lo split in FP32 (sv rounded to 24 bits; sv - hi is exact in FP32): |error| <= 2^-22 |sv|
+    const float hf = __half2float(__float2half_rn(sv));
+    uint32_t w;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(sv - hf), "f"(hf));      // upper half: lo, lower half: hi (hf is exact in f16)
+    if (!EDGE || j < NC) rw[j] = w;
+}
+// columns the sampler's passes do not reach (the k-step count is rounded up to an instantiated one)
+__device__ __forceinline__ void rec_zero_tail(uint32_t* rw, int jfirst, int NC) {
+    for (int j = jfirst; j < NC; j += 32) rw[j] = 0u;
+}
+// (|x|^2, sum_{i<d} x_i) of TWO points from the lanes' shares: the xor-16-8-4-2-1 butterfly of each of the four sums, packed -- after the first
+// level the lower half-warp carries point 0 and the upper one point 1, after the second the 8-lane groups carry (point, quantity): 7 FP64 adds
+// and 14 shuffles for two points instead of 20 and 40 (the FP64 warp reductions were what made sampler-side statistics a loss before).
+// tm0 / tm1: the points' time columns, which the lanes' sums include.
+__device__ __forceinline__ void rec_reduce2(uint32_t* r0, uint32_t* r1, int NC, int lane, double nx0, double sx0, double nx1, double sx1,
+                                            double tm0, double tm1) {
+    const bool up = lane >= 16, b3 = (lane & 8) != 0;
+    double an = (up ? nx1 : nx0) + __shfl_xor_sync(0xffffffffu, up ? nx0 : nx1, 16);
+    double as = (up ? sx1 : sx0) + __shfl_xor_sync(0xffffffffu, up ? sx0 : sx1, 16);
+    double v = (b3 ? as : an) + __shfl_xor_sync(0xffffffffu, b3 ? an : as, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if ((lane & 7) == 0) ((double*)((up ? r1 : r0) + NC))[b3 ? 1 : 0] = b3 ? v - (up ? tm1 : tm0) : v;
+}
+
 // terminal points X_T = (x + mu (T-t)) + sigma (sqrt(T-t) N)   (solvers/ScaSML.py:190-198)
-template <int JP>
+template <int JP, bool REC>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(LevelDev lv, int nslot, int cpts) {
     extern __shared__ __align__(16) uint8_t smp_smem[];
     __half* stab = (__half*)smp_smem;
@@ -284,9 +321,14 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
         __syncwarp();
         const int npt = (int)((NT - ch * cpts < cpts) ? (NT - ch * cpts) : cpts);
         double* const outl = lv.P + (lv.term_off + ch * cpts) * D + lane;      // this lane's column of the chunk's first point
+        const int NC = REC ? lv.rec_nstep * 16 : 0, recb = REC ? NC * 4 + 16 : 0;
+        uint32_t* const recl = REC ? (uint32_t*)(lv.rec + (size_t)(lv.term_off + ch * cpts) * recb) : nullptr;   // 32-bit words: recb / 4 per point
+        const int recw = recb >> 2;
+        const float asc = lv.rec_ascale;
         // two points per iteration; an odd tail repeats its last point (same values written twice) so nothing below is conditional
         for (int pp = 0; pp < npt; pp += 2) {
             const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
+            double rnx[2] = {0.0, 0.0}, rsx[2] = {0.0, 0.0};
             const PtRec ra = rec[pi[0]], rb = rec[pi[1]];
             const double* xs[2] = {(const double*)ra.xp, (const double*)rb.xp};
             double xv[2][REG ? JP : 1];
@@ -318,16 +360,22 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
                         const double N = chunk_to_normal_s(stab, cp[(JP <= 4 || j < d) ? j : 0]);
                         const double val = __dadd_rn(__dadd_rn(xin[qq], drp), __dmul_rn(sigma, __dmul_rn(sqp, N)));
                         store_pred(dst + 32 * (q0 + qq), (j == d) ? T : val, j <= d);
+                        if (REC) {
+                            if (q0 + qq == JP - 1) rec_emit<true>(recl + pi[hh] * recw, j, NC, (j == d) ? T : val, j <= d, asc, rnx[hh], rsx[hh]);
+                            else rec_emit<false>(recl + pi[hh] * recw, j, NC, val, true, asc, rnx[hh], rsx[hh]);
+                        }
                     }
                 }
+                if (REC) rec_zero_tail(recl + pi[hh] * recw, JP * 32 + lane, NC);
             }
+            if (REC) rec_reduce2(recl + pi[0] * recw, recl + pi[1] * recw, NC, lane, rnx[0], rsx[0], rnx[1], rsx[1], T, T);
             __syncwarp();
         }
     }
 }
 
 // interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
-template <int JP>
+template <int JP, bool REC>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(LevelDev lv, int l, int nslot, int cpts) {
     extern __shared__ __align__(16) uint8_t smp_smem[];
     __half* stab = (__half*)smp_smem;
@@ -383,6 +431,8 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
         }
         __syncwarp();
         const int npt = (int)((NP - ch * cpts < cpts) ? (NP - ch * cpts) : cpts);
+        const int NC = REC ? lv.rec_nstep * 16 : 0, recb = REC ? NC * 4 + 16 : 0, recw = recb >> 2;
+        const float asc = lv.rec_ascale;
         for (int pp = 0; pp < npt; pp += 2) {                        // an odd tail repeats its last point: nothing below is conditional
             const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
             const PtRec ra = rec[pi[0]], rb = rec[pi[1]];
@@ -403,11 +453,15 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
                 philox_blocks(pbuf + h * nslot, f0h, d, key, hl);
                 __syncwarp();
                 double* const outl = lv.P + (lv.set_off[lk] + ch * cpts) * D + lane;
+                uint32_t* const recl = REC ? (uint32_t*)(lv.rec + (size_t)(lv.set_off[lk] + ch * cpts) * recb) : nullptr;
+                double rnx[2] = {0.0, 0.0}, rsx[2] = {0.0, 0.0}, rtm[2] = {0.0, 0.0};
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int p = pi[hh];
                     const unsigned long long f0p = hh ? rb.f0 : ra.f0;
-                    const double tk = scal[(k * 3 + 0) * 32 + p], sqp = scal[(k * 3 + 1) * 32 + p], drp = scal[(k * 3 + 2) * 32 + p];
+                    const double tk = scal[(k * 3 + 0) * 32 + p];
+                    if (REC) rtm[hh] = tk;
+                    const double sqp = scal[(k * 3 + 1) * 32 + p], drp = scal[(k * 3 + 2) * 32 + p];
                     const unsigned short* cp = pch + (size_t)hh * nslot * 8 + (int)(f0p & 7ull);
                     double* const dst = outl + p * D;
                     const double* prev = (k == 0) ? xs[hh] : lv.P + (lv.set_off[lk - 1] + ch * cpts + p) * D;
@@ -428,9 +482,15 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(Lev
                             const double xn = step_add(xin[qq], drp, sigma, sqp, N);
                             if (REG) xv[hh][q0 + qq] = xn;
                             store_pred(dst + 32 * (q0 + qq), (j == d) ? tk : xn, j <= d);
+                            if (REC) {
+                                if (q0 + qq == JP - 1) rec_emit<true>(recl + p * recw, j, NC, (j == d) ? tk : xn, j <= d, asc, rnx[hh], rsx[hh]);
+                                else rec_emit<false>(recl + p * recw, j, NC, xn, true, asc, rnx[hh], rsx[hh]);
+                            }
                         }
                     }
+                    if (REC) rec_zero_tail(recl + p * recw, JP * 32 + lane, NC);
                 }
+                if (REC) rec_reduce2(recl + pi[0] * recw, recl + pi[1] * recw, NC, lane, rnx[0], rsx[0], rnx[1], rsx[1], rtm[0], rtm[1]);
                 __syncwarp();
             }
         }
@@ -768,17 +828,32 @@ int launch_reduce(const LevelDev& lv, cudaStream_t stream) {
     return OK;
 }
 
+// records (REC) exist only where the resident-operand tcgen05 kernel does: D + 1 <= 128, i.e. JP <= 4
 template <int JP>
 int launch_sample_terminal_jp(const LevelDev& lv, int nslot, int cpts, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
-    SC_CUDA(cudaFuncSetAttribute(sample_terminal_kernel<JP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_terminal_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, nslot, cpts);
+    if (JP <= 4 && lv.rec != nullptr) {
+        constexpr int J = JP <= 4 ? JP : 4;
+        SC_CUDA(cudaFuncSetAttribute(sample_terminal_kernel<J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sample_terminal_kernel<J, true><<<grid, nwarp * 32, smem, stream>>>(lv, nslot, cpts);
+    } else {
+        SC_REQUIRE(lv.rec == nullptr, "sampler: operand records need d + 2 <= 128");
+        SC_CUDA(cudaFuncSetAttribute(sample_terminal_kernel<JP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sample_terminal_kernel<JP, false><<<grid, nwarp * 32, smem, stream>>>(lv, nslot, cpts);
+    }
     SC_LAUNCH_CHECK();
     return OK;
 }
 template <int JP>
 int launch_sample_paths_jp(const LevelDev& lv, int l, int nslot, int cpts, unsigned grid, int nwarp, size_t smem, cudaStream_t stream) {
-    SC_CUDA(cudaFuncSetAttribute(sample_paths_kernel<JP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_paths_kernel<JP><<<grid, nwarp * 32, smem, stream>>>(lv, l, nslot, cpts);
+    if (JP <= 4 && lv.rec != nullptr) {
+        constexpr int J = JP <= 4 ? JP : 4;
+        SC_CUDA(cudaFuncSetAttribute(sample_paths_kernel<J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sample_paths_kernel<J, true><<<grid, nwarp * 32, smem, stream>>>(lv, l, nslot, cpts);
+    } else {
+        SC_REQUIRE(lv.rec == nullptr, "sampler: operand records need d + 2 <= 128");
+        SC_CUDA(cudaFuncSetAttribute(sample_paths_kernel<JP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sample_paths_kernel<JP, false><<<grid, nwarp * 32, smem, stream>>>(lv, l, nslot, cpts);
+    }
     SC_LAUNCH_CHECK();
     return OK;
 }
@@ -847,10 +922,12 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         }
         lv.P = (double*)(ws + lr.off_P);
         lv.gid = (long long*)(ws + lr.off_gid);
-        // per-point (|X|^2, sum X) for the tcgen05 route's loader warps: not produced by the samplers -- measured at C3 they pay more for the two
-        // FP64 warp reductions per point (2.9 -> 4.7 ms per step) than the evaluation kernel saves (19.4 -> 18.2 ms); launch_eval_tc still takes
-        // such statistics from a caller that has them
-        lv.pstat = nullptr;
+        // tcgen05 route, d + 2 <= 128: the samplers also write each point's operand record (f16 hi / lo images of a log2(e) x, |x|^2, sum x), so
+        // the evaluation kernel stages a point tile with one bulk copy instead of converting FP64 rows at its tile boundary
+        const bool recs = p_.scasml && route == 1 && gp != nullptr && tc_rec_nstep(D) > 0;
+        lv.rec = recs ? (uint8_t*)(ws + lr.off_rec) : nullptr;
+        lv.rec_nstep = recs ? tc_rec_nstep(D) : 0;
+        lv.rec_ascale = recs ? tc_rec_ascale(gp->a) : 0.0f;
         lv.npoints = lr.npoints;
         lv.rows = (RowRec*)(ws + lr.off_rows);
         lv.ev0 = (double*)(ws + lr.off_ev0);
@@ -962,7 +1039,8 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
                 begin_span(1);
                 if (route == 1)
                     rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
-                                        nullptr, nullptr, stream);
+                                        nullptr, nullptr, stream, nullptr,
+                                        lv.rec ? lv.rec + (size_t)s.off * tc_rec_bytes(lv.rec_nstep) : nullptr);
                 else
                     rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                          nullptr, nullptr, stream);

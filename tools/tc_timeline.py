@@ -33,12 +33,7 @@ for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PD
     print(f"== {name}: entry 0, scatter {t[1]-t0}, prologue {t[2]-t0}, exit {t[3]-t0} cycles; items {nitem}")
     f = [int(x - t0) for x in t[244:249]]
     print(f"   tile boundary (stamps of the CTA's SECOND point tile): tile-0 t_full committed {f[4]}, MMA warp enters tile 1 {f[0]}, epilogue enters "
-          f"tile-1 iteration {f[1]}, A images copied {t[2]-t0}, loader warp 0 saw t_full(0) {f[2]}, tile-0 outputs written {f[3]}, loader staged tile 1 at {t[1]-t0}")
-    ld = [int(x - t0) if x > 0 else 0 for x in t[800:830]]
-    print(f"   loader warp 0, staging of the CTA's THIRD tile: pass starts {ld[0:8]}, done {ld[8]}; class contractions of the SECOND tile (start, end): {ld[20:26]}")
-    lp = [int(x - t0) if x > 0 else 0 for x in t[840:848]]
-    print(f"   loader warp 0, third tile, passes 0-3 (loads landed, pass done): {lp}")
-    print(f"   pass 1 detail (row pair 0: converted+stored, reduced, shift written; row pair 1: same): {[int(x - t0) for x in t[850:856]]}")
+          f"tile-1 iteration {f[1]}, tile-1 records seen in shared memory {t[1]-t0}, A images copied {t[2]-t0}, contraction warp 0 saw t_full(0) {f[2]}, tile-0 outputs written {f[3]}")
     for w in range(min(nitem, 44)):
         a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
         f = [int(t[256 + 8 * w + i] - t0) for i in range(7)]
