@@ -422,7 +422,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     uint32_t* soff = (uint32_t*)(smask + TC_MAXCOL);                 // [TC_MAXCOL]
     float2* scs = (float2*)(soff + TC_MAXCOL);                       // [TC_MAXCOL]
     double* acc4 = (double*)(scs + TC_MAXCOL);                       // [128][4] output sums (u, div, lap, dt) of the tile being contracted, across its classes
-    uint64_t* bars = (uint64_t*)(acc4 + TM * 4);
+    double2* stat2 = (double2*)(acc4 + TM * 4);                      // [2][128] (|x|^2, sum x) of the rows of the current / next point tile, by tile parity
+    uint64_t* bars = (uint64_t*)(stat2 + 2 * TM);
     uint32_t* tmem_slot = (uint32_t*)(bars + NBAR);
     uint16_t* ptab = (uint16_t*)(tmem_slot + 4);                     // [npair] pairs of the class-major stream of one point tile
 
@@ -457,7 +458,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int i = 0; i < NSF; ++i) mbar_init(s_full(i), 1);
         for (int i = 0; i < NSLOT2; ++i) { mbar_init(p_ready(i), NEPI / 2); mbar_init(slot_free(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 2); mbar_init(t_free0 + 8u * i, NLOAD); }
-        mbar_init(a_ready, NEPI + NLOAD); mbar_init(stage_full, 1);
+        mbar_init(a_ready, NEPI); mbar_init(stage_full, 1);
         mbar_init(ord0, 1); mbar_init(ord0 + 8u, 1);
         fence_barrier_init();
     }
@@ -692,13 +693,15 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         const double ymax2 = __ldg(st.ymax2);
         const int rq = qd * 32 + lane;                               // this thread's row
         for (int tp = 0; tp < nit; ++tp) {
-            MBW(stage_full, (uint32_t)tp & 1u);                // the records of tile tp have landed: |x|^2 and the row sum of this thread's row
+            // |x|^2 and the row sum of this thread's row: the epilogue warps left them in stat2 before they released the staging buffer.  (These
+            // warps do not take part in a_ready themselves: the stage-1 issuers would wait for the previous tile's last contraction, ~2 k cycles.)
+            // stat2 is double-buffered by tile parity; tile tp + 2 is written only after every class of tile tp + 1 has been multiplied out, which
+            // needs the T buffers of tile tp back (t_free), i.e. long after this read.
+            MBW(a_ready, (uint32_t)tp & 1u);
             double ki_prev, sx_prev;
             float sc_prev;
             {
-                const double2 stat = *(const double2*)(sStage + (size_t)rq * RECB + REC_STAT);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_ready);                 // this warp is done with the staging buffer (the next tile's records may land)
+                const double2 stat = stat2[(tp & 1) * TM + rq];
                 const int sh = row_shift(gp.a, stat.x, ymax2);
                 sc_prev = exp2f((float)sh);
                 ki_prev = ldexp(exp(-0.5 * gp.a * stat.x), TC_P_SHIFT - sh); sx_prev = stat.y;
@@ -798,7 +801,9 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             MBW(stage_full, (uint32_t)it & 1u);
             if (it == 1 && ew == 0 && lane == 0) TC_STAMP(1);
             const uint8_t* rowp = sStage + (size_t)r * RECB;
-            const double nx_r = *(const double*)(rowp + REC_STAT);   // |x|^2 of this thread's point row
+            const double2 stat_r = *(const double2*)(rowp + REC_STAT);   // (|x|^2, sum x) of this thread's point row
+            const double nx_r = stat_r.x;
+            if (ew < 4) stat2[(it & 1) * TM + r] = stat_r;           // for the contraction warps (one epilogue warp per lane quadrant)
             // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile have completed (the
             // copying warps saw s_full of its last pairs at the end of their loop), so the images can be overwritten.
             if (ew < 8) {                                            // image = ew >> 2 (hi | lo); 32-bit column c = K elements 2c, 2c + 1
@@ -921,7 +926,7 @@ static size_t smem_bytes() {
     constexpr size_t NMAX = C::NK > C::NKY ? C::NK : C::NKY;
     return Ring<CLASS, NSTEP>::NB1 * (size_t)(((NSTEP + 3) / 4) * 2 * B1_BLK2) + Ring<CLASS, NSTEP>::NB3 * (2 * 2 * NMAX * 128) + (size_t)TM * Stage<NSTEP>::REC
            + (size_t)TM * TF_COUNT * 4 + TC_MAXCOL * (sizeof(float4) + sizeof(uint32_t) + sizeof(float2)) + (size_t)TM * 4 * 8
-           + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
+           + 2 * TM * sizeof(double2) + NBAR * 8 + 16 + MAX_PAIRS * sizeof(uint16_t);
 }
 
 template <int CLASS, int NSTEP>

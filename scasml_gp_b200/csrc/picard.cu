@@ -289,7 +289,7 @@ __device__ __forceinline__ void rec_reduce2(uint32_t* r0, uint32_t* r1, int NC, 
 
 // terminal points X_T = (x + mu (T-t)) + sigma (sqrt(T-t) N)   (solvers/ScaSML.py:190-198)
 template <int JP, bool REC>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(LevelDev lv, int nslot, int cpts) {
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_terminal_kernel(LevelDev lv, int nslot, int cpts) {
     extern __shared__ __align__(16) uint8_t smp_smem[];
     __half* stab = (__half*)smp_smem;
     load_normal_table(stab, lv.ntab);
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_terminal_kernel(
 
 // interior path points of step set l (all k), solvers/ScaSML.py:220-238 / ScaSML_full_history.py:142-154
 template <int JP, bool REC>
-__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, 2) sample_paths_kernel(LevelDev lv, int l, int nslot, int cpts) {
+__global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_paths_kernel(LevelDev lv, int l, int nslot, int cpts) {
     extern __shared__ __align__(16) uint8_t smp_smem[];
     __half* stab = (__half*)smp_smem;
     load_normal_table(stab, lv.ntab);
