@@ -254,10 +254,13 @@ def main():
                                                                   # stays on GP.route = FP64, the public API's default
     gp.GPsolver(dom, bdy)                                    # first fit: allocations, module load
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    gp.GPsolver(dom, bdy)
-    torch.cuda.synchronize()
-    fit_ms = 1e3 * (time.perf_counter() - t0)
+    fit_times = []
+    for _ in range(1 if d > 300 else 3):                     # median of three fits (a single wall-clock sample now and then caught a 10x host hiccup)
+        t0 = time.perf_counter()
+        gp.GPsolver(dom, bdy)
+        torch.cuda.synchronize()
+        fit_times.append(1e3 * (time.perf_counter() - t0))
+    fit_ms = sorted(fit_times)[len(fit_times) // 2]
 
     Solver = ScaSML_full_history if fh else ScaSML
 

@@ -345,20 +345,22 @@ constexpr int NB3_MAX = 4;
 // wait returned at once and the group converted a stale slot (rare, timing-dependent NaN rows; a delay in an issuer deadlocked: tools/stress_eval.py).
 // Barrier g mod 6 is only ever waited on by the group of parity g mod 2, phase after phase.
 constexpr int NSF = 2 * NSLOT2;
-constexpr int NBAR = 2 * NB1_MAX + 2 * NB3_MAX + NSF + 2 * NSLOT2 + 4 + 3 + 2;   // + ord[2]: stage-2 issue order hand-off between the two stage-2 issuers
+constexpr int NBAR = 2 * NB1_MAX + 2 * NB3_MAX + NSF + 2 * NSLOT2 + 4 + 3 + 2 + 4;   // + ord[2]: stage-2 issue order hand-off between the two stage-2 issuers; + stat_ready[2] stat_free[2]
 static_assert(COL_T2 + 2 * NTMAX == COL_A && COL_A + 2 * A_IMG_COLS == 512, "tensor-memory map");
 
 // debug build only (tools/stress_eval.py): bounded wait that names the waiter before it traps
 __device__ __noinline__ void mbar_wait_tag(uint32_t bar, uint32_t parity, long long* dbg, int line) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 21)) {
+        ++spins;
+        if (spins == (1u << 21)) {                                   // every stuck warp names its wait (stamps 900 + warp: line | parity << 16 | CTA << 32) ...
+            if ((threadIdx.x & 31) == 0) dbg[900 + (threadIdx.x >> 5)] = (long long)line | ((long long)parity << 16) | ((long long)blockIdx.x << 32);
             if (atomicCAS((unsigned long long*)(dbg + 960), 0ull, (unsigned long long)line) == 0ull) {
                 dbg[961] = blockIdx.x; dbg[962] = threadIdx.x >> 5; dbg[963] = parity; dbg[964] = bar;
-                __threadfence_system();
             }
-            asm volatile("trap;");
+            __threadfence_system();
         }
+        if (spins > (1u << 24)) { asm volatile("trap;"); }           // ... and the kernel traps once the others have had time to do the same
     }
 }
 
@@ -436,6 +438,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 #define TC_STAMP(slot) do { if (DBG && dbg) dbg[(slot)] = clock64(); } while (0)
     if (tid == 0) TC_STAMP(0);
     // debug build: a wait that runs out of probes reports (source line, CTA, warp, parity) through the stamp buffer (pinned host memory survives the trap)
+    // watchdog runs (flag 4): every role leaves its progress per CTA behind the stamps (dbg[1024 + 16 CTA + role] = tile << 16 | pair)
+#define TC_PROG(role, a, b) do { if (DBG && (dflags & 4)) st.dbg[1024 + 16 * blockIdx.x + (role)] = ((long long)(a) << 16) | (long long)(b); } while (0)
 #define MBW(bar, par) do { if (DBG && (dflags & 4)) mbar_wait_tag((bar), (par), st.dbg, __LINE__); else mbar_wait((bar), (par)); } while (0)
     const uint32_t bar0 = smem_u32(bars);
     auto b1_full = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -446,7 +450,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     auto p_ready = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSF + i); };
     auto slot_free = [&](int i) { return bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSF + NSLOT2 + i); };
     const uint32_t t_full0 = bar0 + 8u * (uint32_t)(2 * NB1_MAX + 2 * NB3_MAX + NSF + 2 * NSLOT2), t_free0 = t_full0 + 16u, a_ready = t_full0 + 32u,
-                   stage_full = t_full0 + 40u, ord0 = t_full0 + 56u;
+                   stage_full = t_full0 + 40u, ord0 = t_full0 + 56u, stat_ready0 = t_full0 + 72u, stat_free0 = t_full0 + 88u;
     // T accumulators: one per class epoch e = tile * NCLS + class, double-buffered by epoch parity.  One barrier pair per buffer: a
     // waiter is never more than one phase behind.
     auto t_full = [&](int e) { return t_full0 + 8u * (uint32_t)(e & 1); };
@@ -460,6 +464,8 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int i = 0; i < 2; ++i) { mbar_init(t_full0 + 8u * i, 2); mbar_init(t_free0 + 8u * i, NLOAD); }
         mbar_init(a_ready, NEPI); mbar_init(stage_full, 1);
         mbar_init(ord0, 1); mbar_init(ord0 + 8u, 1);
+        mbar_init(stat_ready0, 4); mbar_init(stat_ready0 + 8u, 4);
+        mbar_init(stat_free0, NLOAD); mbar_init(stat_free0 + 8u, NLOAD);
         fence_barrier_init();
     }
     if (warp == W_S1A) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -520,6 +526,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 ++p1;
             };
             for (int p = 0; p < ptotal; ++p) {
+                TC_PROG(0, p1, p);
                 while (p1 < ptotal && p1 < p + NB1) load_b1();               // centre rows run NB1 - 1 pairs ahead of the coefficient images
                 const int q = p % NB3;
                 if (p >= NB3) MBW(b3_empty(q), (uint32_t)((p / NB3) - 1) & 1u);
@@ -567,6 +574,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             if (w == 0 && el && it + 1 < nit) copy_records(it + 1);
             for (int j = 0; j < npair; ++j, ++p) {
                 if ((p & 1) != w) continue;
+                if (el) TC_PROG(2 + w, it, j);
                 const int s = p % NSLOT2, s1 = p % NB1;
                 const uint32_t accS = tmem_base + (uint32_t)s * SLOTC;
                 const uint32_t idesc = PT_TWO(ptab[j]) ? idS2 : idS1;
@@ -615,6 +623,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             for (int j = 0; j < npair; ++j, ++p) {
                 const uint32_t e = ptab[j];
                 if ((p & 1) == w) {
+                    if (el) TC_PROG(4 + w, it, j);
                     const int s = p % NSLOT2, q = p % NB3;
                     const int kc = PT_KERN(e);
                     const bool two = PT_TWO(e), first = PT_FIRST(e);
@@ -695,13 +704,17 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
         for (int tp = 0; tp < nit; ++tp) {
             // |x|^2 and the row sum of this thread's row: the epilogue warps left them in stat2 before they released the staging buffer.  (These
             // warps do not take part in a_ready themselves: the stage-1 issuers would wait for the previous tile's last contraction, ~2 k cycles.)
-            // stat2 is double-buffered by tile parity; tile tp + 2 is written only after every class of tile tp + 1 has been multiplied out, which
-            // needs the T buffers of tile tp back (t_free), i.e. long after this read.
-            MBW(a_ready, (uint32_t)tp & 1u);
+            // stat2 is double-buffered by tile parity, with a full / free barrier pair per buffer: the epilogue warps run up to three pairs ahead of
+            // stage 2 -- with one pair per class (a GP of < 49 collocation points) that is two point tiles ahead of these warps -- so they wait for
+            // stat_free before they overwrite a buffer, and nobody is ever two phases behind on a parity wait.  (Waiting on a_ready here, and a
+            // first version without stat_free, deadlocked exactly those small GPs: tests/test_gpu_tc.py::test_pipeline_protocol_under_many_tiles.)
+            MBW(stat_ready0 + 8u * (uint32_t)(tp & 1), (uint32_t)(tp >> 1) & 1u);
             double ki_prev, sx_prev;
             float sc_prev;
             {
                 const double2 stat = stat2[(tp & 1) * TM + rq];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stat_free0 + 8u * (uint32_t)(tp & 1));
                 const int sh = row_shift(gp.a, stat.x, ymax2);
                 sc_prev = exp2f((float)sh);
                 ki_prev = ldexp(exp(-0.5 * gp.a * stat.x), TC_P_SHIFT - sh); sx_prev = stat.y;
@@ -709,6 +722,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             if (tp == 1 && qd == 0 && lane == 0) TC_STAMP(1);
             for (int ce = 0; ce < NCLS; ++ce) {
                 const int e = tp * NCLS + ce;
+                if (qd == 0 && lane == 0) TC_PROG(6, tp, ce);
                 MBW(t_full(e), (uint32_t)(e >> 1) & 1u);
                 {
                     tc_fence_after();
@@ -803,7 +817,12 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             const uint8_t* rowp = sStage + (size_t)r * RECB;
             const double2 stat_r = *(const double2*)(rowp + REC_STAT);   // (|x|^2, sum x) of this thread's point row
             const double nx_r = stat_r.x;
-            if (ew < 4) stat2[(it & 1) * TM + r] = stat_r;           // for the contraction warps (one epilogue warp per lane quadrant)
+            if (ew < 4) {                                            // for the contraction warps (one epilogue warp per lane quadrant)
+                if (it >= 2) MBW(stat_free0 + 8u * (uint32_t)(it & 1), (uint32_t)((it >> 1) - 1) & 1u);   // they have read tile it - 2
+                stat2[(it & 1) * TM + r] = stat_r;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stat_ready0 + 8u * (uint32_t)(it & 1));
+            }
             // --- A images of tile `it`: staging buffer -> tensor memory (lane = row).  All stage-1 MMAs of the previous tile have completed (the
             // copying warps saw s_full of its last pairs at the end of their loop), so the images can be overwritten.
             if (ew < 8) {                                            // image = ew >> 2 (hi | lo); 32-bit column c = K elements 2c, 2c + 1
@@ -835,6 +854,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
             // chunk's ex2 work.  The two groups run half a period apart.
             for (int j = 0; j < npair; ++j, ++g) {
                 if ((int)(g & 1) != grp) continue;                   // pair ownership alternates between the two groups
+                if ((ew & 7) == 0 && lane == 0) TC_PROG(7 + grp, it, j);
                 const bool two = PT_TWO(ptab[j]);
                 const int s = (int)(g % NSLOT2);
                 MBW(s_full((int)(g % NSF)), (uint32_t)(g / NSF) & 1u);
@@ -885,6 +905,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
     if (warp == W_S1A) tmem_dealloc(tmem_base, 512);
 #undef TC_STAMP
 #undef MBW
+#undef TC_PROG
 #undef PT_KERN
 #undef PT_TWO
 #undef PT_FIRST

@@ -214,3 +214,35 @@ def test_guard_bands_around_every_buffer_stay_intact(mid, wide):
                 torch.cuda.synchronize()
                 assert intact(wbuf, nws) and intact(obuf, B * D) and intact(xbuf, B * D), (F.d, cls.__name__, route)
                 assert bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("d,nd,nb", [(20, 20, 6), (20, 90, 30), (100, 40, 8), (100, 300, 60)])
+def test_pipeline_protocol_under_many_tiles(d, nd, nb):
+    """The resident-operand kernel's mbarrier protocol under load: every CTA runs a dozen point tiles (plus a ragged last one), with one
+    pair per class (26 centres: the tile boundary is then as long as the main loop), odd pair counts, and 360 centres.  The kernel is
+    deterministic, so repeated launches must agree bit for bit (a parity wait that returns early converts a stale slot; a late one hangs
+    until the watchdog traps), and both must agree with the FP64 route."""
+    F = Fitted(d=d, nd=nd, nb=nb)
+    P, lib, torch = F.P, F.P["lib"], F.P["torch"]
+    gp = F.gp
+    gp.set_right_vector(F.gp_o.right_vector)
+    R = 148 * 128 * 12 + 77
+    rng = np.random.default_rng(5)
+    X = np.concatenate([rng.uniform(-0.5, 0.5, (R, d)), rng.uniform(0.0, 0.5, (R, 1))], axis=1)
+    xd = lib.to_device(X)
+    nout = {lib.EVAL_U: 1, lib.EVAL_UG: 2, lib.EVAL_PDE: 4}
+    for mode in (lib.EVAL_U, lib.EVAL_UG, lib.EVAL_PDE):
+        gp.route = lib.ROUTE_TC
+        first = [o.clone() for o in gp._eval(xd, mode, nout=nout[mode])]
+        for _ in range(3):
+            again = gp._eval(xd, mode, nout=nout[mode])
+            torch.cuda.synchronize()
+            for a, b in zip(first, again):
+                assert not bool(torch.isnan(b).any())
+                assert bool((a == b).all()), (d, nd, mode, int((a != b).sum()))
+        gp.route = lib.ROUTE_F64
+        ref = gp._eval(xd[:4096], mode, nout=nout[mode])
+        for a, b in zip(first, ref):
+            scale = float(b.abs().max()) + 1e-300
+            assert float((a[:4096] - b).abs().max()) < 2e-5 * scale, (d, nd, mode)
+    gp.route = lib.ROUTE_F64
