@@ -91,6 +91,21 @@ static int gp_alloc(scasml_gp* g) {
     return OK;
 }
 
+namespace scasml {
+int ensure_scratch_pool() {
+    static bool done[64] = {};
+    int dev = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[dev]) return OK;
+    cudaMemPool_t pool;
+    SC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    SC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done[dev] = true;
+    return OK;
+}
+}  // namespace scasml
+
 extern "C" {
 
 const char* scasml_last_error(void) { return last_error_cstr(); }
@@ -246,7 +261,7 @@ int scasml_gp_eval(const scasml_gp* g, const double* X_dev, long long R, int mod
     if (route == SCASML_ROUTE_TC)
         return launch_eval_tc(g->v, nullptr, X_dev, (long)R, mode, out0_dev, out1_dev, out2_dev, out3_dev, (cudaStream_t)stream);
     SC_REQUIRE(route == SCASML_ROUTE_F64, "gp_eval: unknown route");
-    return launch_eval_f64(g->v, X_dev, (long)R, mode, out0_dev, out1_dev, out2_dev, out3_dev, (cudaStream_t)stream);
+    return launch_eval_f64(g->v, X_dev, (long)R, mode, out0_dev, out1_dev, out2_dev, out3_dev, (cudaStream_t)stream, true);
 }
 
 size_t scasml_gp_gradient_workspace_bytes(const scasml_gp* g, long long R) {

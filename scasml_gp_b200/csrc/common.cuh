@@ -12,6 +12,10 @@ namespace scasml {
 enum : int { OK = 0, ERR_INVALID = 1, ERR_CUDA = 2, ERR_NUMERIC = 3, ERR_NOMEM = 4 };
 
 void set_error(const std::string& msg);          // abi.cu
+// Stream-ordered scratch (cudaMallocAsync): keeps freed blocks in the device's default memory pool across synchronisations.  With the default
+// release threshold (0) every stream synchronisation hands the pool's memory back to the driver and the next cudaMallocAsync pays for a fresh
+// allocation (tens of ms per u_solve through the public API, which synchronises for its device -> host copy).  abi.cu; once per device.
+int ensure_scratch_pool();
 const char* last_error_cstr();
 
 #define SC_CUDA(expr)                                                                      \

@@ -45,8 +45,11 @@ enum EvalMode : int {
 };
 
 // FP64 SIMT route (gp_eval.cu).  X: [R][D] float64 device.  Null outputs are skipped.
+// split_small: deal the centre tiles of a small batch out over several CTAs per point tile (public evaluation API: the top-level u_hat of a
+// u_solve).  The partial sums are added in a fixed order, but the split depends on R -- the Picard plan keeps it off so that its results do
+// not depend on how a batch is cut into workspace chunks.
 int launch_eval_f64(const GpView& gp, const double* X, long R, int mode,
-                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream);
+                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream, bool split_small = false);
 
 // full gradient vector for the public compute_gradient API (models/GP.py:673-687)
 int launch_gradient_f64(const GpView& gp, const double* X, long R, double* grad /*[R][D]*/,

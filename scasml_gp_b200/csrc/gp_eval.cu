@@ -6,6 +6,7 @@
 // products  x.y, x.roll(y), roll(x).y  as a register-tiled FP64 contraction and applies the closed-form
 // functionals and the GP weights alpha in the epilogue.
 // This is the parity anchor (errors ~1e-13 vs the oracle); the tcgen05 route lives in gp_eval_tc.cu.
+#include <algorithm>
 #include "gp.cuh"
 
 namespace scasml {
@@ -24,7 +25,10 @@ template <int CLASS, int TN>
 __global__ void __launch_bounds__(NT, 1)
 eval_f64_kernel(GpView gp, const double* __restrict__ X, long R, int mode,
                 double* __restrict__ out0, double* __restrict__ out1,
-                double* __restrict__ out2, double* __restrict__ out3) {
+                double* __restrict__ out2, double* __restrict__ out3, double* __restrict__ part) {
+    // part != null (small batches: the top-level u_hat of a u_solve is 1 200 points = 19 CTAs): the centre tiles are dealt out over
+    // gridDim.y CTAs per point tile, each leaves its partial sums in part[(y * 4 + quantity) * R + row], eval_f64_finish_kernel adds them
+    // in a fixed order
     constexpr int BN = 16 * TN;
     constexpr bool PDE = (CLASS == 2);
     __shared__ double Xs[BK][BM + 2];
@@ -74,7 +78,7 @@ eval_f64_kernel(GpView gp, const double* __restrict__ X, long R, int mode,
     for (int i = 0; i < TM; ++i) { accU[i] = 0.0; accG[i] = 0.0; accL[i] = 0.0; accT[i] = 0.0; }
 
     const int ntile_dom = gp.NdPad / BN, ntile = (gp.NdPad + gp.NbPad) / BN;
-    for (int t = 0; t < ntile; ++t) {
+    for (int t = (int)blockIdx.y; t < ntile; t += (int)gridDim.y) {
         const bool is_dom = t < ntile_dom;
         const int c0 = t * BN;
         __syncthreads();                                   // previous tile's epilogue done with cf / tiles
@@ -211,6 +215,13 @@ eval_f64_kernel(GpView gp, const double* __restrict__ X, long R, int mode,
             const long row = row0 + r;
             if (row >= R) continue;
             const double u = accU[i];
+            if (part != nullptr) {
+                double* pp = part + (size_t)blockIdx.y * 4 * R + row;
+                pp[0] = u;
+                if (CLASS >= 1) pp[R] = accG[i];
+                if (PDE) { pp[2 * R] = accL[i]; pp[3 * R] = accT[i]; }
+                continue;
+            }
             if (CLASS == 0) {
                 if (mode == EVAL_TERMINAL) {
                     const double gx = 1.0 - 1.0 / (1.0 + exp(xf[r][XF_XT] + xf[r][XF_SX]));   // equations.py:259
@@ -415,31 +426,81 @@ __global__ void grad_contract_kernel(GpView gp, const double* __restrict__ X, lo
     }
 }
 
+// sums the per-centre-range partial sums of eval_f64_kernel (fixed order) and applies the output formulas
+__global__ void __launch_bounds__(128) eval_f64_finish_kernel(GpView gp, const double* __restrict__ X, long R, int mode,
+                                                              const double* __restrict__ part, int nsplit,
+                                                              double* __restrict__ out0, double* __restrict__ out1,
+                                                              double* __restrict__ out2, double* __restrict__ out3) {
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    double u = 0.0, g = 0.0, l = 0.0, t = 0.0;
+    for (int y = 0; y < nsplit; ++y) {
+        const double* pp = part + (size_t)y * 4 * R + row;
+        u += pp[0];
+        if (mode == EVAL_UG || mode == EVAL_PDE) g += pp[R];
+        if (mode == EVAL_PDE) { l += pp[2 * R]; t += pp[3 * R]; }
+    }
+    if (mode == EVAL_U) {
+        out0[row] = u;
+    } else if (mode == EVAL_TERMINAL) {
+        const double* xr = X + row * (long)gp.D;
+        double sx = 0.0;
+        for (int i = 0; i < gp.d; ++i) sx += xr[i];
+        out0[row] = (1.0 - 1.0 / (1.0 + exp(xr[gp.d] + sx))) - u;                       // equations.py:259
+    } else if (mode == EVAL_UG) {
+        out0[row] = u; out1[row] = g;
+    } else {
+        const double s2 = gp.sig2;
+        out0[row] = t + (s2 * u - 1.0 / (double)gp.d - 0.5 * s2) * g + 0.5 * s2 * l;    // GP.py:767-768
+        if (out1) out1[row] = g;
+        if (out2) out2[row] = l;
+        if (out3) out3[row] = t;
+    }
+}
+
 }  // namespace
 
 int launch_eval_f64(const GpView& gp, const double* X, long R, int mode,
-                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream) {
+                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream, bool split_small) {
     if (R <= 0) return OK;
     SC_REQUIRE(X && out0, "eval: null pointer");
     SC_REQUIRE(gp.NdPad % CENTRE_PAD == 0 && gp.NbPad % CENTRE_PAD == 0, "eval: centre padding");
-    const dim3 grid((unsigned)cdiv(R, BM));
+    SC_REQUIRE(mode == EVAL_U || mode == EVAL_TERMINAL || mode == EVAL_UG || mode == EVAL_PDE, "eval: unknown mode");
+    if (mode == EVAL_UG) SC_REQUIRE(out1, "eval UG: out1 is null");
+    // small batches: deal the centre tiles out over several CTAs per point tile so that the launch covers the machine
+    int dev = 0, nsm = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const long gx = cdiv(R, BM);
+    const int ntile = (gp.NdPad + gp.NbPad) / (16 * (mode == EVAL_PDE ? 2 : 4));
+    int nsplit = split_small ? (int)std::min<long>(ntile, (2L * nsm) / gx) : 1;
+    if (nsplit < 2) nsplit = 1;
+    double* part = nullptr;
+    { const int prc = ensure_scratch_pool(); if (prc != OK) return prc; }
+    if (nsplit > 1) SC_CUDA(cudaMallocAsync((void**)&part, (size_t)nsplit * 4 * R * sizeof(double), stream));
+    const dim3 grid((unsigned)gx, (unsigned)nsplit);
     switch (mode) {
         case EVAL_U:
         case EVAL_TERMINAL:
-            eval_f64_kernel<0, 4><<<grid, NT, 0, stream>>>(gp, X, R, mode, out0, out1, out2, out3);
+            eval_f64_kernel<0, 4><<<grid, NT, 0, stream>>>(gp, X, R, mode, out0, out1, out2, out3, part);
             break;
         case EVAL_UG:
-            SC_REQUIRE(out1, "eval UG: out1 is null");
-            eval_f64_kernel<1, 4><<<grid, NT, 0, stream>>>(gp, X, R, mode, out0, out1, out2, out3);
-            break;
-        case EVAL_PDE:
-            eval_f64_kernel<2, 2><<<grid, NT, 0, stream>>>(gp, X, R, mode, out0, out1, out2, out3);
+            eval_f64_kernel<1, 4><<<grid, NT, 0, stream>>>(gp, X, R, mode, out0, out1, out2, out3, part);
             break;
         default:
-            SC_REQUIRE(false, "eval: unknown mode");
+            eval_f64_kernel<2, 2><<<grid, NT, 0, stream>>>(gp, X, R, mode, out0, out1, out2, out3, part);
+            break;
     }
-    SC_LAUNCH_CHECK();
-    return OK;
+    int rc = OK;
+    if (cudaGetLastError() != cudaSuccess) { rc = ERR_CUDA; set_error("eval_f64_kernel launch failed"); }
+    if (part != nullptr) {
+        if (rc == OK) {
+            eval_f64_finish_kernel<<<(unsigned)cdiv(R, 128), 128, 0, stream>>>(gp, X, R, mode, part, nsplit, out0, out1, out2, out3);
+            if (cudaGetLastError() != cudaSuccess) { rc = ERR_CUDA; set_error("eval_f64_finish_kernel launch failed"); }
+        }
+        cudaFreeAsync(part, stream);
+    }
+    return rc;
 }
 
 size_t gradient_scratch_bytes(const GpView& gp, long R) {

@@ -1526,6 +1526,7 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
         const size_t per_tile = (size_t)KB * 2 * tc::A_BLK + 2 * tc::TM * sizeof(double) + tc::TM * sizeof(float);
         const size_t need = (size_t)cdiv(R < chunk_pts ? R : chunk_pts, tc::TM) * per_tile;
         uint8_t* scratch = nullptr;
+        { const int prc = ensure_scratch_pool(); if (prc != OK) return prc; }
         SC_CUDA(cudaMallocAsync((void**)&scratch, need, stream));
         int rcode = OK;
         for (long r0 = 0; r0 < R; r0 += chunk_pts) {
@@ -1570,6 +1571,7 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     const size_t recb = (size_t)tc_rec_bytes(st->nstep);
     const long chunk_pts = 148L * tc::TM * 8;
     uint8_t* scratch = nullptr;
+    { const int prc = ensure_scratch_pool(); if (prc != OK) return prc; }
     SC_CUDA(cudaMallocAsync((void**)&scratch, (size_t)(R < chunk_pts ? R : chunk_pts) * recb, stream));
     int rcode = OK;
     for (long r0 = 0; r0 < R && rcode == OK; r0 += chunk_pts) {

@@ -761,6 +761,7 @@ int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X,
 int lu_solve_inplace(double* H, long n, double* rhs, int* d_fail, cudaStream_t st) {
     double* W = nullptr;                                    // column-major panel copy + pivots
     int* piv = nullptr;
+    { const int prc = ensure_scratch_pool(); if (prc != OK) return prc; }
     SC_CUDA(cudaMallocAsync((void**)&W, (size_t)n * LB * sizeof(double), st));
     SC_CUDA(cudaMallocAsync((void**)&piv, LB * sizeof(int), st));
     int rc = OK;
