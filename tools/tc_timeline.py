@@ -32,8 +32,8 @@ for mode, name in ((_lib.EVAL_U, "U"), (_lib.EVAL_UG, "UG"), (_lib.EVAL_PDE, "PD
     print(f"== {name} flags={flags}: steady-state period {period:.0f} cycles/item")
     print(f"== {name}: entry 0, scatter {t[1]-t0}, prologue {t[2]-t0}, exit {t[3]-t0} cycles; items {nitem}")
     f = [int(x - t0) for x in t[244:249]]
-    print(f"   tile boundary (stamps of the CTA's SECOND point tile): tile-0 t_full committed {f[4]}, MMA warp enters tile 1 {f[0]}, epilogue enters "
-          f"tile-1 iteration {f[1]}, tile-1 records seen in shared memory {t[1]-t0}, A images copied {t[2]-t0}, contraction warp 0 saw t_full(0) {f[2]}, tile-0 outputs written {f[3]}")
+    print(f"   tile boundary (stamps of the CTA's SECOND point tile): tile-0 t_full committed {f[4]}, stage-1 issuer enters tile 1 {f[0]}, "
+          f"A images copied {t[2]-t0}, contraction warp 0 saw t_full(0) {f[2]}, tile-0 outputs written {f[3]}")
     for w in range(min(nitem, 44)):
         a, b, c, e = (t[4 + 4 * w + i] - t0 for i in range(4))
         f = [int(t[256 + 8 * w + i] - t0) for i in range(7)]
