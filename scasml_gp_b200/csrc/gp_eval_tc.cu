@@ -579,11 +579,13 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 const uint32_t accS = tmem_base + (uint32_t)s * SLOTC;
                 const uint32_t idesc = PT_TWO(ptab[j]) ? idS2 : idS1;
                 if (el && stamp && j < 60) TC_STAMP(4 + 4 * j);
+                // the centre rows first: they landed long ago (the ring runs pairs ahead), and every barrier operation of this lone thread costs
+                // 100-200 cycles -- taken before the wait that IS on the pair's critical path instead of after it
+                MBW(b1_full(s1), (uint32_t)(p / NB1) & 1u);    // bulk-copy bytes landed (async proxy)
+                if (el && stamp && j < 60) TC_STAMP(257 + 8 * j);
                 // the slot's previous P has been consumed: stage 2 of pair p - NSLOT2 has COMPLETED
                 if (p >= NSLOT2) { MBW(slot_free(s), (uint32_t)((p / NSLOT2) - 1) & 1u); tc_fence_after(); }
                 if (el && stamp && j < 60) TC_STAMP(256 + 8 * j);
-                MBW(b1_full(s1), (uint32_t)(p / NB1) & 1u);    // bulk-copy bytes landed (async proxy)
-                if (el && stamp && j < 60) TC_STAMP(257 + 8 * j);
                 const uint64_t bb = b1desc0 + (uint64_t)(((uint32_t)s1 * B1_SLOT) >> 4);
                 if (el) {
 #pragma unroll
@@ -627,13 +629,13 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const int s = p % NSLOT2, q = p % NB3;
                     const int kc = PT_KERN(e);
                     const bool two = PT_TWO(e), first = PT_FIRST(e);
-                    // P written over S by the pair's epilogue group + coefficient images landed
-                    MBW(p_ready(s), (uint32_t)(p / NSLOT2) & 1u);
-                    if (el && stamp && j < 60) TC_STAMP(260 + 8 * j);
+                    // coefficient images landed (long ago) and, for the first pair of a class, its T buffer contracted (class epoch - 2): both
+                    // before the wait on the critical path -- P written over S by the pair's epilogue group
                     MBW(b3_full(q), (uint32_t)(p / NB3) & 1u);
                     if (el && stamp && j < 60) TC_STAMP(261 + 8 * j);
-                    // first pair of a class: its T buffer has been contracted by the loader warps (class epoch - 2)
                     if (first && epoch >= 2) MBW(t_free(epoch), (uint32_t)((epoch >> 1) - 1) & 1u);
+                    MBW(p_ready(s), (uint32_t)(p / NSLOT2) & 1u);
+                    if (el && stamp && j < 60) TC_STAMP(260 + 8 * j);
                     // the other issuer has issued pair p - 1
                     if (p >= 1) MBW(ord_mine, (uint32_t)(w == 1 ? (p >> 1) : ((p >> 1) - 1)) & 1u);
                     tc_fence_after();
