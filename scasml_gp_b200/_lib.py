@@ -165,8 +165,8 @@ def to_device(a, pinned=True):
     """NumPy (any float dtype) -> contiguous float64 CUDA tensor, staged through a cached pinned buffer (page-locking a fresh
     buffer per call costs more than the copy for the [B, d+1] inputs of a solve)."""
     torch = torch_cuda()
-    if isinstance(a, torch.Tensor):
-        return a.to(device="cuda", dtype=torch.float64).contiguous()
+    if isinstance(a, torch.Tensor):                        # a pinned float64 host tensor goes to the device without a staging copy
+        return a.to(device="cuda", dtype=torch.float64, non_blocking=bool(a.device.type == "cpu" and a.is_pinned())).contiguous()
     a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
     if not (pinned and a.size) or a.size > (1 << 26):      # empty, or too large to page-lock a staging copy (> 512 MB)
         return torch.from_numpy(a).to("cuda")
@@ -199,6 +199,28 @@ def to_host(t):
     stage.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return stage.numpy().copy()
+
+
+def to_device_sharded(a, rank, world, dist):
+    """Host -> device copy of an input every rank holds: each rank stages only its slice of the rows and the slices travel over NVLink
+    (one all-gather) instead of `world` full copies through one host's staging buffers (sharded solves take the WHOLE batch on every rank)."""
+    torch = torch_cuda()
+    if isinstance(a, torch.Tensor) or world <= 1:
+        return to_device(a)
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    B = a.shape[0]
+    per = -(-B // world)
+    if a.ndim != 2 or B < 8 * world:
+        return to_device(a)
+    full = torch.empty((per * world, a.shape[1]), dtype=torch.float64, device="cuda")
+    mine = a[rank * per:min(B, (rank + 1) * per)]
+    part = full[rank * per:(rank + 1) * per]
+    if mine.shape[0]:
+        part[:mine.shape[0]].copy_(to_device(mine))
+    if mine.shape[0] < per:
+        part[mine.shape[0]:].zero_()
+    dist.all_gather_into_tensor(full, part.clone())
+    return full[:B]
 
 
 def ptr(t):

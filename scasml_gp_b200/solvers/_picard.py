@@ -250,7 +250,9 @@ class PicardSolverBase(object):
         return raw
 
     def _u_solve(self, n, rho, x_t, M=None):
-        x_dev = _lib.to_device(x_t)                               # one host -> device copy serves the correction and u_hat
+        rank, world, dist = self._dist()
+        # one host -> device copy serves the correction and u_hat; sharded runs stage a row slice per rank and all-gather it
+        x_dev = _lib.to_device_sharded(x_t, rank, world, dist) if world > 1 else _lib.to_device(x_t)
         if self.scasml:
             out, uh = self._uz_device(n, rho, x_dev, M, with_u_hat=True)   # top-level u_hat(x): GP.route (FP64 by default)
         else:
