@@ -462,7 +462,7 @@ __global__ void axpy_kernel(long n, double alpha, const double* __restrict__ x, 
 }
 
 // ------------------------------------------------------------------ LU (partial pivoting) -----------------
-constexpr int LB = 32;
+constexpr int LB = 64;
 
 
 // ---- pivoted LU, panel on a column-major copy --------------------------------------------------------------------------------
@@ -528,6 +528,114 @@ __global__ void __launch_bounds__(1024) lu_panel_factor_kernel(double* __restric
         __syncthreads();
     }
 }
+// ---- multi-CTA panel factorisation (cooperative launch) ----
+// The single-CTA panel above was 62 % of a 12 000^2 solve (1.1 ms per 32-column panel: one SM doing the read-modify-write of a 3 MB panel out of
+// L2).  Here up to 128 CTAs each keep a slab of the panel's rows (a row = 32 contiguous doubles of the row-major matrix: no gather / scatter
+// passes) in shared memory; per column: local pivot candidates -> grid barrier -> every CTA picks the global pivot (largest |.|, lowest index
+// on ties: the rule of the single-CTA kernel, so the factors are bit-identical), the owners publish the pivot row and row j -> grid barrier ->
+// interchange and rank-1 update in shared memory.  Two grid barriers per column.
+struct LuPanelScratch { double cand_val[128]; long long cand_idx[128]; double row_p[LB]; double row_j[LB]; unsigned barrier; unsigned pad; };
+
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned nblocks, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*(volatile unsigned*)ctr < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+constexpr int LUP_THREADS = 256;
+__global__ void __launch_bounds__(LUP_THREADS) lu_panel_factor_mc_kernel(double* __restrict__ A, long n, long j0, int nb, long rows, int rpc,
+                                                                          LuPanelScratch* __restrict__ sc, int* __restrict__ piv, int* __restrict__ fail) {
+    extern __shared__ double lup_smem[];
+    double* slab = lup_smem;                                   // [rpc][LB + 1]
+    __shared__ double s_val[LUP_THREADS / 32];
+    __shared__ long long s_idx[LUP_THREADS / 32];
+    __shared__ double s_rowj[LB];
+    __shared__ long long s_piv;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const long r0 = (long)cta * rpc;                           // first panel-relative row of this CTA
+    const int nloc = (int)((rows - r0 < rpc) ? ((rows - r0 > 0) ? rows - r0 : 0) : rpc);
+    for (int idx = tid; idx < nloc * LB; idx += LUP_THREADS) {
+        const int r = idx / LB, c = idx % LB;
+        slab[r * (LB + 1) + c] = (c < nb) ? A[(j0 + r0 + r) * n + j0 + c] : 0.0;
+    }
+    unsigned target = 0;
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        // local pivot candidate among the rows i >= j of this slab
+        double best = -1.0; long long bi = -1;
+        for (int r = tid; r < nloc; r += LUP_THREADS) {
+            const long i = r0 + r;
+            if (i < j) continue;
+            const double v = fabs(slab[r * (LB + 1) + j]);
+            if (v > best) { best = v; bi = i; }
+        }
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (ov > best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = best; s_idx[wid] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double b = s_val[0]; long long ix = s_idx[0];
+            for (int w = 1; w < LUP_THREADS / 32; ++w)
+                if (s_idx[w] >= 0 && (s_val[w] > b || (s_val[w] == b && (ix < 0 || s_idx[w] < ix)))) { b = s_val[w]; ix = s_idx[w]; }
+            sc->cand_val[cta] = b; sc->cand_idx[cta] = ix;
+        }
+        grid_barrier(&sc->barrier, (unsigned)G, target);
+        if (wid == 0) {                                        // every CTA picks the global pivot from the candidates
+            double b = -1.0; long long ix = -1;
+            for (int g = lane; g < G; g += 32) {
+                const double v = ((volatile double*)sc->cand_val)[g]; const long long gi = ((volatile long long*)sc->cand_idx)[g];
+                if (gi >= 0 && (v > b || (v == b && (ix < 0 || gi < ix)))) { b = v; ix = gi; }
+            }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, b, o);
+                const long long oi = __shfl_xor_sync(0xffffffffu, ix, o);
+                if (oi >= 0 && (ov > b || (ov == b && (ix < 0 || oi < ix)))) { b = ov; ix = oi; }
+            }
+            if (!(b > 0.0)) { if (cta == 0 && lane == 0) *fail = 1; ix = j; }
+            if (lane == 0) { s_piv = ix; if (cta == 0) piv[j] = (int)ix; }
+        }
+        __syncthreads();
+        const long long p = s_piv;
+        // the owners publish the pivot row and row j
+        if (p >= r0 && p < r0 + nloc && tid < LB) sc->row_p[tid] = slab[(int)(p - r0) * (LB + 1) + tid];
+        if (j >= r0 && j < r0 + nloc && tid < LB) sc->row_j[tid] = slab[(int)(j - r0) * (LB + 1) + tid];
+        grid_barrier(&sc->barrier, (unsigned)G, target);
+        if (tid < LB) {
+            const double vp = ((volatile double*)sc->row_p)[tid];
+            s_rowj[tid] = vp;                                  // row j after the interchange
+            if (p != j) {
+                const double vj = ((volatile double*)sc->row_j)[tid];
+                if (p >= r0 && p < r0 + nloc) slab[(int)(p - r0) * (LB + 1) + tid] = vj;
+            }
+            if (j >= r0 && j < r0 + nloc) slab[(int)(j - r0) * (LB + 1) + tid] = vp;
+        }
+        __syncthreads();
+        const double pivv = s_rowj[j];
+        for (int r = tid; r < nloc; r += LUP_THREADS) {
+            if (r0 + r <= j) continue;
+            double* row = slab + r * (LB + 1);
+            const double lij = row[j] / pivv;
+            row[j] = lij;
+            for (int c = j + 1; c < nb; ++c) row[c] = fma(-lij, s_rowj[c], row[c]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nloc * LB; idx += LUP_THREADS) {
+        const int r = idx / LB, c = idx % LB;
+        if (c < nb) A[(j0 + r0 + r) * n + j0 + c] = slab[r * (LB + 1) + c];
+    }
+}
+
 // apply the panel's row interchanges to the columns outside the panel (one thread per column: coalesced along the rows) and to rhs
 __global__ void __launch_bounds__(256) lu_apply_swaps_kernel(double* __restrict__ A, long n, long j0, int nb, const int* __restrict__ piv, double* __restrict__ rhs) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -759,19 +867,38 @@ int tri_inverse_lower(const double* L, long n, const double* invdiag, double* X,
 }
 
 int lu_solve_inplace(double* H, long n, double* rhs, int* d_fail, cudaStream_t st) {
-    double* W = nullptr;                                    // column-major panel copy + pivots
+    double* W = nullptr;                                    // column-major panel copy (single-CTA fallback) + pivots
     int* piv = nullptr;
+    LuPanelScratch* psc = nullptr;
     { const int prc = ensure_scratch_pool(); if (prc != OK) return prc; }
     SC_CUDA(cudaMallocAsync((void**)&W, (size_t)n * LB * sizeof(double), st));
     SC_CUDA(cudaMallocAsync((void**)&piv, LB * sizeof(int), st));
+    SC_CUDA(cudaMallocAsync((void**)&psc, sizeof(LuPanelScratch), st));
+    int dev = 0, nsm = 0, coop = 0;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     int rc = OK;
     for (long j0 = 0; j0 < n && rc == OK; j0 += LB) {
-        const int nb = (int)std::min<long>(LB, n - j0);
-        const long rows = n - j0;
-        const unsigned g = (unsigned)cdiv(rows * nb, 256);
-        lu_panel_gather_kernel<<<g, 256, 0, st>>>(H, n, j0, nb, rows, W);
-        lu_panel_factor_kernel<<<1, 1024, 0, st>>>(W, rows, nb, piv, d_fail);
-        lu_panel_scatter_kernel<<<g, 256, 0, st>>>(H, n, j0, nb, rows, W);
+        int nb = (int)std::min<long>(LB, n - j0);
+        long rows = n - j0;
+        // multi-CTA panel: up to min(128, SMs) CTAs, at least 32 rows each; one CTA per SM is co-resident by construction (cooperative launch checks it)
+        int G = (int)std::min<long>(std::min(128, nsm), cdiv(rows, 32));
+        int rpc = (int)cdiv(rows, G);
+        G = (int)cdiv(rows, rpc);
+        const size_t slab = (size_t)rpc * (LB + 1) * sizeof(double);
+        if (coop && G > 1 && slab <= 160 * 1024) {
+            SC_CUDA(cudaMemsetAsync(&psc->barrier, 0, sizeof(unsigned), st));
+            SC_CUDA(cudaFuncSetAttribute(lu_panel_factor_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
+            double* Hp = H; long nn = n, jj = j0;
+            void* args[] = {&Hp, &nn, &jj, &nb, &rows, &rpc, &psc, &piv, &d_fail};
+            SC_CUDA(cudaLaunchCooperativeKernel((const void*)lu_panel_factor_mc_kernel, dim3((unsigned)G), dim3(LUP_THREADS), args, slab, st));
+        } else {
+            const unsigned g = (unsigned)cdiv(rows * nb, 256);
+            lu_panel_gather_kernel<<<g, 256, 0, st>>>(H, n, j0, nb, rows, W);
+            lu_panel_factor_kernel<<<1, 1024, 0, st>>>(W, rows, nb, piv, d_fail);
+            lu_panel_scatter_kernel<<<g, 256, 0, st>>>(H, n, j0, nb, rows, W);
+        }
         lu_apply_swaps_kernel<<<(unsigned)cdiv(n + 1, 256), 256, 0, st>>>(H, n, j0, nb, piv, rhs);
         const long rest = n - j0 - nb;
         if (rest <= 0) break;
@@ -782,6 +909,7 @@ int lu_solve_inplace(double* H, long n, double* rhs, int* d_fail, cudaStream_t s
     if (rc == OK) lu_solve_kernel<<<1, 1024, 0, st>>>(H, n, rhs);
     cudaFreeAsync(W, st);
     cudaFreeAsync(piv, st);
+    cudaFreeAsync(psc, st);
     if (rc != OK) return rc;
     SC_LAUNCH_CHECK();
     return OK;
