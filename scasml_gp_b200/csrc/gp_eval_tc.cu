@@ -59,6 +59,7 @@ struct TcDev {
     int ntile_all;                   // resident-operand kernel: 48-centre tiles of the compact centre list (k, kx classes); ntile_dom = those of the ky class
     const double* csum;              // [TC_MAXCOL] per column: sum over the centres of the scaled, split coefficients (baseline term of the coefficient GEMM)
     const uint8_t* rec;              // resident-operand kernel: the points' operand records [R][tc_rec_bytes(NSTEP)] (gp_tc.cuh)
+    const double* recf;              // ... and their feature blocks [R][TC_REC_NFEAT]: x_0, t, x_I[0..4], x_{I+1}[0..4]
     const double* ymax2;             // device scalar: max_j |y_j|^2 over the centres (per-row exponent shift, row_shift())
     long long* dbg;
     int dbg_block;
@@ -722,6 +723,31 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                 ki_prev = ldexp(exp(-0.5 * gp.a * stat.x), TC_P_SHIFT - sh); sx_prev = stat.y;
             }
             if (tp == 1 && qd == 0 && lane == 0) TC_STAMP(1);
+            {   // features of the row, once per tile, BEFORE the wait for the first class's T: the loads' latency used to sit between t_full and
+                // t_free of that class, i.e. on the path of the coefficient GEMMs two class epochs later (with the 12 scattered loads from the FP64
+                // row that was worth 2 ms per C3 step).  Floats: FP64 conversions run at 1/8 rate here.  The previous tile's contraction is done.
+                const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
+                const bool ok = row < R;
+                float* F = feat + rq * TF_COUNT;                     // private to this thread
+                // the row's 12 feature coordinates: one contiguous 96-byte block, written with the operand record
+                double fb[TC_REC_NFEAT];
+                {
+                    const double2* fp = (const double2*)(st.recf + (ok ? row : 0) * TC_REC_NFEAT);
+#pragma unroll
+                    for (int k = 0; k < TC_REC_NFEAT / 2; ++k) { const double2 v = __ldg(fp + k); fb[2 * k] = ok ? v.x : 0.0; fb[2 * k + 1] = ok ? v.y : 0.0; }
+                }
+                const double x0 = fb[0], xt = fb[1];
+                double P2 = 0.0, R2 = 0.0;
+#pragma unroll
+                for (int m = 0; m < MC_IDX; ++m) {
+                    const double xi = fb[2 + m], xir = fb[2 + MC_IDX + m];
+                    F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
+                    P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
+                }
+                F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
+                F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
+                acc4[rq * 4 + 0] = 0.0; acc4[rq * 4 + 1] = 0.0; acc4[rq * 4 + 2] = 0.0; acc4[rq * 4 + 3] = 0.0;
+            }
             for (int ce = 0; ce < NCLS; ++ce) {
                 const int e = tp * NCLS + ce;
                 if (qd == 0 && lane == 0) TC_PROG(6, tp, ce);
@@ -731,20 +757,6 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
                     const long row = ((long)blockIdx.x + (long)tp * gridDim.x) * TM + rq;
                     const bool ok = row < R;
                     float* F = feat + rq * TF_COUNT;                 // private to this thread
-                    if (ce == 0) {                                   // features of the row, once per tile (floats; FP64 runs at 1/8 rate here)
-                        const double* xr = X + row * (long)D;
-                        const double xt = ok ? __ldg(xr + d) : 0.0, x0 = ok ? __ldg(xr) : 0.0;
-                        double P2 = 0.0, R2 = 0.0;
-#pragma unroll
-                        for (int m = 0; m < MC_IDX; ++m) {
-                            const double xi = ok ? __ldg(xr + gp.I[m]) : 0.0, xir = ok ? __ldg(xr + gp.I[m] + 1) : 0.0;
-                            F[TF_XI + m] = (float)xi; F[TF_XR + m] = (float)xir;
-                            P2 = fma(xi, xi, P2); R2 = fma(xir, xir, R2);
-                        }
-                        F[TF_ONE] = 1.0f; F[TF_SX] = (float)sx_prev; F[TF_XT] = (float)xt; F[TF_X0] = (float)x0; F[TF_SXR] = (float)(sx_prev - x0 + xt);
-                        F[TF_P2] = (float)P2; F[TF_R2] = (float)R2;
-                        acc4[rq * 4 + 0] = 0.0; acc4[rq * 4 + 1] = 0.0; acc4[rq * 4 + 2] = 0.0; acc4[rq * 4 + 3] = 0.0;
-                    }
                     if (tp == 0 && qd == 0 && lane == 0) TC_STAMP(246);
                     const int kc = CL::kern(ce);
                     const int ncol = CL::ncol(kc), coff = CL::coloff(kc);
@@ -919,7 +931,7 @@ eval_tc_kernel(GpView gp, TcDev st, const double* __restrict__ X, long R, int mo
 // The very same arithmetic and summation tree as the Picard samplers' emission (picard.cu::rec_emit / rec_reduce2), so a point's record does
 // not depend on who wrote it: per-lane FMA / add chains over c = lane, lane + 32, ..., then the xor-16-8-4-2-1 butterfly.
 __global__ void __launch_bounds__(256) rec_image_kernel(const double* __restrict__ X, long R, int D, int d, int nstep, float ascale_f,
-                                                        uint8_t* __restrict__ rec) {
+                                                        TcRecIdx fi, uint8_t* __restrict__ rec, double* __restrict__ recf) {
     const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= R) return;
@@ -941,6 +953,7 @@ __global__ void __launch_bounds__(256) rec_image_kernel(const double* __restrict
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) { nx += __shfl_xor_sync(0xffffffffu, nx, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); }
     if (lane == 0) { double* stp = (double*)(rw + NC); stp[0] = nx; stp[1] = sx - __ldg(xr + d); }
+    if (lane < TC_REC_NFEAT) recf[row * TC_REC_NFEAT + lane] = __ldg(xr + fi.col[lane]);
 }
 
 template <int CLASS, int NSTEP>
@@ -1500,7 +1513,7 @@ int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream) {
 
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const TcDebug* dbg, const uint8_t* rec) {
+                   const TcDebug* dbg, const uint8_t* rec, const double* recf) {
     if (R <= 0) return OK;
     const TcState* st = (const TcState*)tc_state;
     if (st == nullptr) st = (const TcState*)gp.tc;
@@ -1516,7 +1529,7 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
     dv.b1_tile_bytes = st->b1_tile_bytes;
     dv.b3_tile_bytes = st->b3_tile_bytes[cls];
     dv.nstep = st->nstep; dv.ntile_dom = st->ntile_dom; dv.ntile_bdy = st->ntile_bdy; dv.ntile_all = st->ntile_all; dv.npair_all = st->npair_all;
-    dv.rec = rec;
+    dv.rec = rec; dv.recf = recf;
     dv.ymax2 = (const double*)(st->images + st->ymax_off);
     dv.csum = (const double*)(st->images + st->csum_off) + cls * TC_MAXCOL;
     dv.dbg = dbg ? dbg->stamps : nullptr; dv.dbg_block = dbg ? (dbg->block & 0xFFFFFF) : 0; dv.dbg_flags = dbg ? (dbg->block >> 24) : 0;
@@ -1551,9 +1564,9 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
         return rcode;
     }
     // resident-operand kernel.  The k-step count is a template parameter (lean single-thread MMA issue): images are zero-padded up to it
-    auto run = [&](const double* Xc, long rc, const uint8_t* recs, double* p0, double* p1, double* p2, double* p3) -> int {
+    auto run = [&](const double* Xc, long rc, const uint8_t* recs, const double* recfs, double* p0, double* p1, double* p2, double* p3) -> int {
         tc::TcDev d2 = dv;
-        d2.rec = recs;
+        d2.rec = recs; d2.recf = recfs;
 #define SC_TC_DISPATCH(NS)                                                                                                  \
     do {                                                                                                                    \
         if (cls == TC_U) return tc::launch<TC_U, NS>(gp, d2, Xc, rc, mode, p0, p1, p2, p3, stream);                          \
@@ -1567,21 +1580,25 @@ int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long
 #undef SC_TC_DISPATCH
     };
     SC_REQUIRE(st->nstep == tc_rec_nstep(gp.D), "tc: k-step count of the images and of the operand records differ");
-    if (rec != nullptr) return run(X, R, rec, out0, out1, out2, out3);
+    SC_REQUIRE((rec == nullptr) == (recf == nullptr), "tc: operand records and feature blocks come together");
+    if (rec != nullptr) return run(X, R, rec, recf, out0, out1, out2, out3);
     // a caller without records (public evaluation API, tools): a pre-pass writes them into a stream-ordered scratch buffer of this call, in
     // chunks of eight point tiles per SM (the scratch stays L2-sized: 70 MB at d = 100)
     const size_t recb = (size_t)tc_rec_bytes(st->nstep);
     const long chunk_pts = 148L * tc::TM * 8;
     uint8_t* scratch = nullptr;
     { const int prc = ensure_scratch_pool(); if (prc != OK) return prc; }
-    SC_CUDA(cudaMallocAsync((void**)&scratch, (size_t)(R < chunk_pts ? R : chunk_pts) * recb, stream));
+    const size_t npts = (size_t)(R < chunk_pts ? R : chunk_pts);
+    const size_t recs_bytes = (npts * recb + 255) & ~(size_t)255;
+    SC_CUDA(cudaMallocAsync((void**)&scratch, recs_bytes + npts * TC_REC_NFEAT * sizeof(double), stream));
+    double* scratchf = (double*)(scratch + recs_bytes);
     int rcode = OK;
     for (long r0 = 0; r0 < R && rcode == OK; r0 += chunk_pts) {
         const long rc = (R - r0 < chunk_pts) ? (R - r0) : chunk_pts;
         const double* Xc = X + r0 * (long)gp.D;
-        tc::rec_image_kernel<<<(unsigned)cdiv(rc * 32, 256), 256, 0, stream>>>(Xc, rc, gp.D, gp.d, st->nstep, tc_rec_ascale(gp.a), scratch);
+        tc::rec_image_kernel<<<(unsigned)cdiv(rc * 32, 256), 256, 0, stream>>>(Xc, rc, gp.D, gp.d, st->nstep, tc_rec_ascale(gp.a), tc_rec_idx(gp), scratch, scratchf);
         if (cudaGetLastError() != cudaSuccess) { rcode = ERR_CUDA; set_error("rec_image_kernel launch failed"); break; }
-        rcode = run(Xc, rc, scratch, out0 + r0, out1 ? out1 + r0 : nullptr, out2 ? out2 + r0 : nullptr, out3 ? out3 + r0 : nullptr);
+        rcode = run(Xc, rc, scratch, scratchf, out0 + r0, out1 ? out1 + r0 : nullptr, out2 ? out2 + r0 : nullptr, out3 ? out3 + r0 : nullptr);
     }
     cudaFreeAsync(scratch, stream);
     return rcode;

@@ -62,16 +62,26 @@ __host__ __device__ inline int tc_rec_nstep(int D) {               // instantiat
     return n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 7 ? 7 : (n <= 8 ? 8 : 0)));
 }
 __host__ __device__ inline int tc_rec_bytes(int nstep) { return nstep * 64 + 16; }
+// ... and, in a second array, the 12 coordinates the final contraction's monomials are made of, one contiguous 96-byte block per point:
+// x_0, t, x_{I[m]} (m < 5), x_{I[m] + 1} (m < 5)   (I = the Hutchinson index set; models/GP.py:91-93, 139-180)
+constexpr int TC_REC_NFEAT = 12;
+struct TcRecIdx { int col[TC_REC_NFEAT]; };          // column of the FP64 row each feature is
+inline TcRecIdx tc_rec_idx(const GpView& gp) {
+    TcRecIdx r;
+    r.col[0] = 0; r.col[1] = gp.d;
+    for (int m = 0; m < MC_IDX; ++m) { r.col[2 + m] = gp.I[m]; r.col[2 + MC_IDX + m] = gp.I[m] + 1; }
+    return r;
+}
 __host__ __device__ inline float tc_rec_ascale(double a) { return (float)(a * 1.4426950408889634); }   // S = log2 of exp(a x.y)
 
 int tc_supported(const GpView& gp);
 size_t tc_image_bytes(const GpView& gp, TcState* st);              // fills the layout fields and the column table
 int tc_build_images(const GpView& gp, const TcState& st, cudaStream_t stream);
-// rec: the points' operand records [R][tc_rec_bytes] (resident-operand kernel) from a caller that has them (the Picard samplers); null: a
-// pre-pass over X writes them into a stream-ordered scratch buffer of this call
+// rec / recf: the points' operand records [R][tc_rec_bytes] and feature blocks [R][TC_REC_NFEAT] (resident-operand kernel) from a caller that
+// has them (the Picard samplers); null: a pre-pass over X writes them into a stream-ordered scratch buffer of this call
 int launch_eval_tc(const GpView& gp, const void* tc_state, const double* X, long R, int mode,
                    double* out0, double* out1, double* out2, double* out3, cudaStream_t stream,
-                   const TcDebug* dbg = nullptr, const uint8_t* rec = nullptr);
+                   const TcDebug* dbg = nullptr, const uint8_t* rec = nullptr, const double* recf = nullptr);
 int tc_timeline(const GpView& gp, const TcState& st, const double* X, long R, int mode, int block, long long* stamps_dev,
                 double* scratch_out, cudaStream_t stream);
 int tc_mma_bench(int N, int nchains, int ts_mode, int iters, long long* cycles_dev, cudaStream_t stream);

@@ -157,6 +157,7 @@ int PicardPlan::build(const PicardParams& p, long B) {
         lv.off_gid = take((size_t)pt * sizeof(long long));
         // operand records of the tcgen05 evaluation kernel (written by the samplers; unused on the FP64 route)
         lv.off_rec = take((p.scasml && tc_rec_nstep(D) > 0) ? (size_t)pt * tc_rec_bytes(tc_rec_nstep(D)) : 0);
+        lv.off_recf = take((p.scasml && tc_rec_nstep(D) > 0) ? (size_t)pt * TC_REC_NFEAT * sizeof(double) : 0);
         lv.off_rows = take((size_t)lv.NR * sizeof(RowRec));
         lv.off_ev0 = take((size_t)pt * sizeof(double));
         lv.off_ev1 = take((size_t)pt * sizeof(double));
@@ -287,6 +288,30 @@ __device__ __forceinline__ void rec_reduce2(uint32_t* r0, uint32_t* r1, int NC, 
     if ((lane & 7) == 0) ((double*)((up ? r1 : r0) + NC))[b3 ? 1 : 0] = b3 ? v - (up ? tm1 : tm0) : v;
 }
 
+// Feature blocks of the TWO points a warp has just produced (12 coordinates each: x_0, t, x_I, x_{I+1}).  Lane k < 12 writes feature k of point
+// a, lane 16 + k of point b: one coalesced 96-byte store per point.  The coordinate sits in lane (c mod 32), pass (c / 32) of the lane <-> column
+// registers va / vb: two shuffles per pass and a select -- no divergence in the column loop, no read-back of the row (both were tried: +1.5 ms).
+struct RecFeatLane { int src_lane, src_q; bool is_time; };
+__device__ __forceinline__ RecFeatLane rec_feature_lane(const LevelDev& lv, int lane) {
+    const int k = lane & 15;
+    const int c = lv.rec_col[k < 12 ? k : 0];
+    RecFeatLane f; f.src_lane = c & 31; f.src_q = c >> 5; f.is_time = (c == lv.d);
+    return f;
+}
+template <int JP>
+__device__ __forceinline__ void rec_features2(double* recfl, int pa, int pb, int lane, const RecFeatLane& f, const double (&va)[JP], const double (&vb)[JP],
+                                              double ta, double tb) {
+    const bool up = lane >= 16;
+    double val = up ? tb : ta;
+#pragma unroll
+    for (int q = 0; q < JP; ++q) {
+        const double a = __shfl_sync(0xffffffffu, va[q], f.src_lane);
+        const double b = __shfl_sync(0xffffffffu, vb[q], f.src_lane);
+        if (!f.is_time && f.src_q == q) val = up ? b : a;
+    }
+    if ((lane & 15) < 12) recfl[(up ? pb : pa) * 12 + (lane & 15)] = val;
+}
+
 // terminal points X_T = (x + mu (T-t)) + sigma (sqrt(T-t) N)   (solvers/ScaSML.py:190-198)
 template <int JP, bool REC>
 __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_terminal_kernel(LevelDev lv, int nslot, int cpts) {
@@ -302,6 +327,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_termin
     const int d = lv.d, D = lv.D, MCg = lv.MCg;
     const double sigma = lv.sigma, T = lv.T, mu = lv.mu;
     const PhiloxKey key = make_key(0u, 0u, lv.seed);
+    const RecFeatLane flane = rec_feature_lane(lv, lane);
     const long long NT = lv.NT, nchunk = (NT + cpts - 1) / cpts;     // cpts <= 32 points per chunk (smaller for small launches)
     for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
         const long long s = ch * cpts + lane;
@@ -325,10 +351,12 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_termin
         uint32_t* const recl = REC ? (uint32_t*)(lv.rec + (size_t)(lv.term_off + ch * cpts) * recb) : nullptr;   // 32-bit words: recb / 4 per point
         const int recw = recb >> 2;
         const float asc = lv.rec_ascale;
+        double* const recfl = REC ? lv.recf + (size_t)(lv.term_off + ch * cpts) * 12 : nullptr;
         // two points per iteration; an odd tail repeats its last point (same values written twice) so nothing below is conditional
         for (int pp = 0; pp < npt; pp += 2) {
             const int pi[2] = {pp, (pp + 1 < npt) ? pp + 1 : pp};
             double rnx[2] = {0.0, 0.0}, rsx[2] = {0.0, 0.0};
+            double tval[2][REG ? JP : 1];                    // the points' coordinates (lane <-> column), for their feature blocks
             const PtRec ra = rec[pi[0]], rb = rec[pi[1]];
             const double* xs[2] = {(const double*)ra.xp, (const double*)rb.xp};
             double xv[2][REG ? JP : 1];
@@ -361,6 +389,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_termin
                         const double val = __dadd_rn(__dadd_rn(xin[qq], drp), __dmul_rn(sigma, __dmul_rn(sqp, N)));
                         store_pred(dst + 32 * (q0 + qq), (j == d) ? T : val, j <= d);
                         if (REC) {
+                            if (REG) tval[hh][q0 + qq] = val;
                             if (q0 + qq == JP - 1) rec_emit<true>(recl + pi[hh] * recw, j, NC, (j == d) ? T : val, j <= d, asc, rnx[hh], rsx[hh]);
                             else rec_emit<false>(recl + pi[hh] * recw, j, NC, val, true, asc, rnx[hh], rsx[hh]);
                         }
@@ -368,7 +397,10 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_termin
                 }
                 if (REC) rec_zero_tail(recl + pi[hh] * recw, JP * 32 + lane, NC);
             }
-            if (REC) rec_reduce2(recl + pi[0] * recw, recl + pi[1] * recw, NC, lane, rnx[0], rsx[0], rnx[1], rsx[1], T, T);
+            if (REC) {
+                rec_reduce2(recl + pi[0] * recw, recl + pi[1] * recw, NC, lane, rnx[0], rsx[0], rnx[1], rsx[1], T, T);
+                rec_features2<REG ? JP : 1>(recfl, pi[0], pi[1], lane, flane, tval[0], tval[1], T, T);
+            }
             __syncwarp();
         }
     }
@@ -392,6 +424,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_paths_
     const double sigma = lv.sigma, T = lv.T, mu = lv.mu;
     const long long NP = lv.NP[l];
     const PhiloxKey kT = make_key(0u, 0u, lv.seed);
+    const RecFeatLane flane = rec_feature_lane(lv, lane);
     const bool quad = lv.variant == 0;
     const long long nchunk = (NP + cpts - 1) / cpts;
     for (long long ch = (long long)blockIdx.x * nwarp + warp; ch < nchunk; ch += (long long)gridDim.x * nwarp) {
@@ -454,6 +487,7 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_paths_
                 __syncwarp();
                 double* const outl = lv.P + (lv.set_off[lk] + ch * cpts) * D + lane;
                 uint32_t* const recl = REC ? (uint32_t*)(lv.rec + (size_t)(lv.set_off[lk] + ch * cpts) * recb) : nullptr;
+                double* const recfl = REC ? lv.recf + (size_t)(lv.set_off[lk] + ch * cpts) * 12 : nullptr;
                 double rnx[2] = {0.0, 0.0}, rsx[2] = {0.0, 0.0}, rtm[2] = {0.0, 0.0};
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -490,7 +524,10 @@ __global__ void __launch_bounds__(SMP_MAX_WARPS * 32, REC ? 1 : 2) sample_paths_
                     }
                     if (REC) rec_zero_tail(recl + p * recw, JP * 32 + lane, NC);
                 }
-                if (REC) rec_reduce2(recl + pi[0] * recw, recl + pi[1] * recw, NC, lane, rnx[0], rsx[0], rnx[1], rsx[1], rtm[0], rtm[1]);
+                if (REC) {
+                    rec_reduce2(recl + pi[0] * recw, recl + pi[1] * recw, NC, lane, rnx[0], rsx[0], rnx[1], rsx[1], rtm[0], rtm[1]);
+                    rec_features2<REG ? JP : 1>(recfl, pi[0], pi[1], lane, flane, xv[0], xv[1], rtm[0], rtm[1]);
+                }
                 __syncwarp();
             }
         }
@@ -928,6 +965,8 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
         lv.rec = recs ? (uint8_t*)(ws + lr.off_rec) : nullptr;
         lv.rec_nstep = recs ? tc_rec_nstep(D) : 0;
         lv.rec_ascale = recs ? tc_rec_ascale(gp->a) : 0.0f;
+        lv.recf = recs ? (double*)(ws + lr.off_recf) : nullptr;
+        if (recs) { const TcRecIdx fi = tc_rec_idx(*gp); for (int k = 0; k < TC_REC_NFEAT; ++k) lv.rec_col[k] = fi.col[k]; }
         lv.npoints = lr.npoints;
         lv.rows = (RowRec*)(ws + lr.off_rows);
         lv.ev0 = (double*)(ws + lr.off_ev0);
@@ -1040,7 +1079,8 @@ int PicardPlan::run(const GpView* gp, int route, const double* x_t, double* out_
                 if (route == 1)
                     rc = launch_eval_tc(*gp, nullptr, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                         nullptr, nullptr, stream, nullptr,
-                                        lv.rec ? lv.rec + (size_t)s.off * tc_rec_bytes(lv.rec_nstep) : nullptr);
+                                        lv.rec ? lv.rec + (size_t)s.off * tc_rec_bytes(lv.rec_nstep) : nullptr,
+                                        lv.rec ? lv.recf + (size_t)s.off * TC_REC_NFEAT : nullptr);
                 else
                     rc = launch_eval_f64(*gp, lv.P + s.off * D, s.cnt, s.mode, lv.ev0 + s.off, lv.ev1 + s.off,
                                          nullptr, nullptr, stream);

@@ -83,6 +83,8 @@ struct LevelDev {
     uint8_t* rec;                       // [npoints][tc_rec_bytes(rec_nstep)] operand records of the tcgen05 evaluation kernel (gp_tc.cuh), written by the
                                         // samplers while a point's coordinates are in registers; null: FP64 route, plain MLP, d + 2 > 128
     int rec_nstep; float rec_ascale;    // k-steps of the records; a log2(e)
+    double* recf;                       // [npoints][12] feature blocks (x_0, t, x_I, x_{I+1}: gp_tc.cuh::TcRecIdx), written with the records
+    int rec_col[12];                    // their columns in the FP64 row
     RowRec* rows;                       // [NR]
     double* ev0; double* ev1;           // evaluation outputs per point
     double* us[MAX_LEVEL + 1];          // finalized (u, zsum) per row, per level
@@ -115,7 +117,7 @@ public:
         long long NP[MAX_LEVEL] = {0};
         long long set_off[MAXLK] = {0};
         long long term_off = 0, ug_off = 0, pde_off = 0;
-        size_t off_P = 0, off_gid = 0, off_rec = 0, off_rows = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
+        size_t off_P = 0, off_gid = 0, off_rec = 0, off_recf = 0, off_rows = 0, off_ev0 = 0, off_ev1 = 0, off_us = 0, off_calls = 0, off_rowbase = 0, off_lvdev = 0;
     };
     const std::vector<CallRec>& calls() const { return calls_; }
     const std::vector<LevelRec>& levels() const { return levels_; }
