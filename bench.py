@@ -277,8 +277,9 @@ def main():
     torch.cuda.synchronize()
 
     def step_device(s=solver, xd=x_dev):
-        uz = s._uz_device(n, rho, xd, M)
-        (uh,) = gp._eval(xd, _lib.EVAL_U)
+        # the product path of u_solve on device-resident inputs: correction + top-level u_hat(x); sharded runs evaluate u_hat on the rows
+        # r = rank (mod world) only and it travels in the same all-reduce (every rank used to evaluate all N x 1 200 rows here)
+        uz, uh = s._uz_device(n, rho, xd, M, with_u_hat=True)
         return uz[:, 0] + uh
 
     def step_e2e(s=solver, Xh=X):
@@ -467,7 +468,7 @@ def main():
             "reference_equivalent_value": ref_equiv, "fit_ms": fit_ms, "newton_steps": gp.newton_steps,
             "finite_fraction": finite,
             "e2e": {"value": e2e_value, "unit": "sample-points/s", "h2d_bytes_per_step": B_total * D * 8,
-                    "d2h_bytes_per_step": B_total * D * 8 + B_total * 8, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": 2 * B_total * 8, "ms_per_step": e2e_ms / args.steps},
             "e2e_with_fit": {"value": e2e_fit_value, "unit": "sample-points/s",
                              "note": "one GP fit + one end-to-end correction pass over the batch"},
             "gpu_launches": int((stats["launches"] + 1) * args.steps),

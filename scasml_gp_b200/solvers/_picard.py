@@ -108,7 +108,8 @@ class PicardSolverBase(object):
         self.key = 0                     # running random.split count (reference: self.key = PRNGKey(0), :27)
         self._tables = {}
         self.last_stats = None
-        self.last_raw = None
+        self._last_raw = None
+        self._last_raw_dev = None
 
     # reference-named table helpers (solvers/ScaSML.py:65-147)
     def inverse_gamma(self, gamma_input):
@@ -157,6 +158,18 @@ class PicardSolverBase(object):
         p.timing = int(self.timing)
         p.reserved = 0
         return p
+
+    @property
+    def last_raw(self):
+        """Un-rounded (u, z) [B, 1 + d] of the last solve (diagnostics / tests); fetched from the device on first access."""
+        if self._last_raw is None and self._last_raw_dev is not None:
+            self._last_raw = _lib.to_host(self._last_raw_dev)
+            self._last_raw_dev = None
+        return self._last_raw
+
+    @last_raw.setter
+    def last_raw(self, value):
+        self._last_raw, self._last_raw_dev = value, None
 
     def plan(self, n, rho, B, M=None, rank=0, world=1):
         """Host-only tree enumeration: (workspace bytes, stats) for a batch of B rows."""
@@ -263,9 +276,11 @@ class PicardSolverBase(object):
             self.last_raw_u = raw[:, :1]
             return raw[:, 0][:, np.newaxis].astype(np.float16)
         torch = _lib.torch_cuda()
-        both = _lib.to_host(torch.cat((out, uh[:, None]), dim=1))  # one device -> host copy (pinned staging)
-        raw, u_hat_raw = both[:, :-1], both[:, -1:]
-        self.last_raw = raw
-        u_breve = raw[:, 0][:, np.newaxis].astype(np.float16)
-        self.last_raw_u = u_hat_raw + raw[:, :1]
+        # one device -> host copy (pinned staging) of what u_solve returns: the two columns (u_breve, u_hat).  The un-rounded (u, z) block
+        # [B, 1 + d] of the correction stays on the device and comes to the host only if `last_raw` is read (it was 98 % of the D2H bytes).
+        both = _lib.to_host(torch.stack((out[:, 0], uh), dim=1))
+        u_breve_raw, u_hat_raw = both[:, :1], both[:, 1:]
+        self._last_raw, self._last_raw_dev = None, out
+        u_breve = u_breve_raw.astype(np.float16)
+        self.last_raw_u = u_hat_raw + u_breve_raw
         return u_hat_raw.astype(np.float16) + u_breve             # solvers/ScaSML.py:300-305 (float16 + float16)
