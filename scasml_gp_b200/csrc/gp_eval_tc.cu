@@ -1,4 +1,4 @@
-// tcgen05 route of the fused surrogate evaluation (sm_100a): two chained GEMMs per (128 points x 64 centres) tile.
+// tcgen05 route of the fused surrogate evaluation (sm_100a): two chained GEMMs per (128 points x 2 x 48 centres) pair of sub-items.
 //
 // Same contract as gp_eval.cu (reference models/GP.py:630-687, 326-411, 746-769), different arithmetic.  Every functional the
 // ScaSML correction needs of the surrogate is  sum_j kernel_c(x, y_j) polynomial(x, y_j)  with kernel_c one of
@@ -23,9 +23,11 @@
 //     TMEM columns over all centre tiles (relative error ~2e-7 rms, tests/test_tc_expansion.py emulates it);
 //   * one N = 96 MMA per k-step serves a PAIR of sub-items (48-centre tile x kernel class): the centre image rows are
 //     [C | rollinv(C) | roll(C)], because roll(x) . y = x . rollinv(y) needs no second A operand;
-//   * warp roles (23 warps, NTHREADS_P): 16 epilogue warps in two groups of 8 (group = pair parity), 1 producer warp
-//     (cp.async.bulk rings), 2 MMA-issuing warps (distance GEMMs / coefficient GEMMs; converged, one elected lane issues),
-//     4 loader warps (stage the next point tile, contract the finished classes of the current one); three S/P slots.
+//   * warp roles (23 warps, NTHREADS_P): 4 contraction warps (final contraction of each finished class), 16 epilogue warps in two
+//     groups of 8 (group = pair parity), 1 producer warp (cp.async.bulk operand rings), 2 + 2 MMA-issuing warps (distance / coefficient
+//     GEMMs of the even / odd pairs; converged, one elected lane issues); three S/P slots;
+//   * a point tile arrives as ONE bulk copy of its 128 operand records (gp_tc.cuh: f16 hi/lo words, |x|^2, sum x -- written by the Picard
+//     samplers or by rec_image_kernel below), the 12 feature coordinates of a row as one 96-byte block: the kernel never reads the FP64 rows.
 // Accuracy: ~2e-7 relative rms on every output; parity with the FP64 route is tested under the "nocast" policy.
 // Timeline stamps and experiment flags exist only in the debug build (-DSCASML_DEBUG_HOOKS, libscasml_b200_dbg.so).
 #include <cmath>
@@ -299,9 +301,10 @@ __global__ void __launch_bounds__(256) csum_kernel(int ncentres, const double* _
 // the third slot keeps stage-1 / stage-2 work of other pairs available while a pair is in its epilogue.
 // Warp roles (23 warps): 16 epilogue warps in two groups of 8 (group = pair parity; a warp converts one sub-item of its pair for one
 // lane quadrant: three 16-column chunks, the next chunk's tcgen05.ld in flight), 1 producer warp (cp.async.bulk rings: centre rows
-// three pairs deep, coefficient images two pairs deep), 2 MMA-issuing warps (distance GEMMs / coefficient GEMMs; converged, one
-// elected lane issues), 4 loader warps: stage the NEXT point tile (a' x = hi + lo in f16, K_i, row sums, exponent shift) in slices
-// and, between the slices, contract each finished class of the CURRENT tile (FP32 column products, FP64 sums).
+// three to four pairs deep, coefficient images two to four pairs deep), 2 + 2 MMA-issuing warps (distance / coefficient GEMMs of the
+// even / odd pairs; converged, one elected lane issues), 4 contraction warps (one per lane quadrant): the row's features and K_i at the
+// start of a tile, then the final contraction of each finished class (FP32 column products, FP64 sums).  The NEXT point tile's operand
+// records are bulk-copied into the staging buffer by stage-1 issuer 0 during the current tile's main loop.
 // Tensor memory (512 columns): S/P slots at 0 / 96 / 192; T buffers at 288 / 336; A images (hi | lo, 64 columns apart) at 384.
 template <int CLASS> struct Cfg;
 template <> struct Cfg<TC_U>   { static constexpr int NK = 16, NKX = 0,  NKY = 16; };
