@@ -96,6 +96,13 @@ SCASML_API int scasml_abi_version(void);
  * Replaces jax.random.normal(..., dtype=float16) (solvers/ScaSML.py:190,229). Per current device. */
 SCASML_API int scasml_set_normal_table(const uint16_t* half_bits_host);
 
+/* equations/equations.py:387-417 (generate_data / generate_test_data -> DeepXDE GeometryXTime.random_points /
+ * random_boundary_points on Hypercube x TimeDomain): n float16-valued points [n][d + 1] written on the device.  Philox stream
+ * (stream_id, domain 2, seed) replaces NumPy's global generator (DeepXDE draws on the host); boundary != 0 puts one random coordinate of
+ * every point on a face of the box. */
+SCASML_API int scasml_geometry_points(unsigned seed, unsigned stream_id, long long n, int d, double xmin, double xmax, double t0, double t1,
+                           int boundary, double* out_dev, void* stream);
+
 /* equations/equations.py:248-261 (terminal g / exact solution) and :290-304 (generator f) */
 SCASML_API int scasml_equation_g(const double* x_t_dev, long long R, int d, double* out_dev, void* stream);
 SCASML_API int scasml_equation_f(const double* u_dev, const double* z_dev, long long R, int d, double sigma, double* out_dev,

@@ -62,3 +62,20 @@ class EquationOracle:
 
     def generate_test_data(self, num_domain=100, num_boundary=20, seed=42):
         return self.generate_data(num_domain, num_boundary, seed)
+
+    # ---- the product's device-side sampler (scasml_geometry_points), restated: same Philox stream, same flat indices ----
+    def _points_philox(self, n, boundary, seed, stream_id):
+        from . import rng as orng
+        d = self.d
+        key = orng.make_key(stream_id, 2, seed)
+        u = orng.uniforms(key, 0, n * (d + 2)).reshape(n, d + 2)
+        x = u[:, :d].copy()
+        if boundary:
+            face = np.minimum((u[:, d] * d).astype(np.int64), d - 1)
+            x[np.arange(n), face] = np.round(x[np.arange(n), face])          # half to even, like rint on the device
+        x = (2 * self.radius) * x + (-self.radius)
+        t = u[:, d + 1:d + 2] * (self.T - self.t0) + self.t0
+        return r16(np.hstack([x, t]))
+
+    def generate_data_philox(self, num_domain=100, num_boundary=20, seed=1234):
+        return self._points_philox(num_domain, False, seed, 0), self._points_philox(num_boundary, True, seed, 1)

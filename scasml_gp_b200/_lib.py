@@ -39,6 +39,8 @@ _SIGNATURES = {
     "scasml_last_error": (C.c_char_p, []),
     "scasml_abi_version": (C.c_int, []),
     "scasml_set_normal_table": (C.c_int, [C.c_void_p]),
+    "scasml_geometry_points": (C.c_int, [C.c_uint, C.c_uint, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
     "scasml_equation_g": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "scasml_equation_f": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "scasml_gp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double, C.POINTER(C.c_void_p)]),

@@ -28,6 +28,31 @@ const __half* normal_table_for_current_device() {
 
 namespace {
 
+// Collocation / test points on the device: DeepXDE's GeometryXTime(Hypercube, TimeDomain) samplers (the reference's
+// equations/equations.py:387-417 calls random_points / random_boundary_points) with Philox uniforms instead of NumPy's global generator.
+// Point i draws the flat indices i (d + 2) + j of stream (stream_id, domain 2, seed): j < d the coordinates, j = d the face dimension of a
+// boundary point (that coordinate is rounded to a face: np.round, half to even), j = d + 1 the time.  float16-valued (DeepXDE float16).
+// One warp per point, lane <-> coordinate.  NumPy statement: oracle/equation.py::EquationOracle.generate_data_philox.
+__global__ void geometry_points_kernel(PhiloxKey key, long long n, int d, double xmin, double xmax, double t0, double t1, int boundary,
+                                       double* __restrict__ out) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const unsigned long long base = (unsigned long long)i * (unsigned long long)(d + 2);
+    int face = -1;
+    if (boundary) {
+        face = (int)(chunk_to_uniform(chunk16(base + (unsigned long long)d, key)) * (double)d);
+        if (face > d - 1) face = d - 1;
+    }
+    double* row = out + i * (long long)(d + 1);
+    for (int j = lane; j < d; j += 32) {
+        double u = chunk_to_uniform(chunk16(base + (unsigned long long)j, key));
+        if (j == face) u = rint(u);
+        row[j] = round_f16(__dadd_rn(__dmul_rn(xmax - xmin, u), xmin));      // NumPy's two roundings, no FMA contraction
+    }
+    if (lane == 0) row[d] = round_f16(__dadd_rn(__dmul_rn(chunk_to_uniform(chunk16(base + (unsigned long long)d + 1ull, key)), t1 - t0), t0));
+}
+
 __global__ void equation_g_kernel(const double* __restrict__ x, long long R, int d, double* __restrict__ out) {
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -118,6 +143,16 @@ int scasml_set_normal_table(const uint16_t* half_bits_host) {
     SC_REQUIRE(dev >= 0 && dev < 64, "device index");
     if (!g_ntab[dev]) SC_CUDA(cudaMalloc(&g_ntab[dev], 32768 * sizeof(__half)));
     SC_CUDA(cudaMemcpy(g_ntab[dev], half_bits_host, 32768 * sizeof(__half), cudaMemcpyHostToDevice));
+    return OK;
+}
+
+int scasml_geometry_points(unsigned seed, unsigned stream_id, long long n, int d, double xmin, double xmax, double t0, double t1,
+                           int boundary, double* out_dev, void* stream) {
+    SC_REQUIRE(d >= 1 && out_dev != nullptr, "geometry_points: invalid argument");
+    if (n <= 0) return OK;
+    geometry_points_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(make_key(stream_id, 2u, seed), n, d, xmin, xmax, t0, t1,
+                                                                                        boundary, out_dev);
+    SC_LAUNCH_CHECK();
     return OK;
 }
 

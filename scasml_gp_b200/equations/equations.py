@@ -152,3 +152,24 @@ class Grad_Dependent_Nonlinear(Equation):
     def generate_test_data(self, num_domain=100, num_boundary=20):
         geom = self.test_geometry()
         return geom.random_points(num_domain), geom.random_boundary_points(num_boundary)
+
+    # ---- the same two samplers on the device (no counterpart in the reference: DeepXDE draws on the host with NumPy's global generator) ----
+    def _points_device(self, n, boundary, seed, stream_id, radius, t0, T):
+        torch = _lib.torch_cuda()
+        d = self.n_input - 1
+        out = torch.empty((int(n), d + 1), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().scasml_geometry_points(int(seed), int(stream_id), int(n), d, -float(radius), float(radius), float(t0), float(T),
+                                                      int(bool(boundary)), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def generate_data_device(self, num_domain=100, num_boundary=20, seed=1234):
+        '''generate_data with the points drawn ON the device (Philox; float16-valued float64 CUDA tensors [n, d + 1]).  GP.GPsolver,
+        GP.predict and the solvers' u_solve take them as they are; `.cpu().numpy().astype(np.float16)` gives the reference's host arrays.'''
+        self.geometry()
+        return (self._points_device(num_domain, False, seed, 0, self.radius, self.t0, self.T),
+                self._points_device(num_boundary, True, seed, 1, self.radius, self.t0, self.T))
+
+    def generate_test_data_device(self, num_domain=100, num_boundary=20, seed=42):
+        self.test_geometry()
+        return (self._points_device(num_domain, False, seed, 0, self.test_radius, self.t0, self.test_T),
+                self._points_device(num_boundary, True, seed, 1, self.test_radius, self.t0, self.test_T))

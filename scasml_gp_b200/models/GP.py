@@ -98,6 +98,11 @@ class GP(object):
         return K.cpu().numpy().astype(np.float16)
 
     def _bind(self, x_t_domain, x_t_boundary):
+        xd_in, xb_in = x_t_domain, x_t_boundary                # device-generated points (CUDA tensors) stay on the device for the centres
+        if hasattr(x_t_domain, "detach"):
+            x_t_domain = x_t_domain.detach().cpu().numpy()
+        if hasattr(x_t_boundary, "detach"):
+            x_t_boundary = x_t_boundary.detach().cpu().numpy()
         x_t_domain = np.asarray(x_t_domain)
         x_t_boundary = np.asarray(x_t_boundary)
         self.N_domain = x_t_domain.shape[0]
@@ -106,8 +111,8 @@ class GP(object):
         self.x_t_domain = x_t_domain
         self.x_t_boundary = x_t_boundary
         self._make_handle(self.N_domain, self.N_boundary)
-        xd = _lib.to_device(x_t_domain)
-        xb = _lib.to_device(x_t_boundary)
+        xd = _lib.to_device(xd_in if hasattr(xd_in, "detach") else x_t_domain)
+        xb = _lib.to_device(xb_in if hasattr(xb_in, "detach") else x_t_boundary)
         _lib.check(_lib.load().scasml_gp_set_centres(self._handle, _lib.ptr(xd), _lib.ptr(xb), _lib.stream_ptr()))
         return xd, xb
 
