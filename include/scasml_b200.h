@@ -144,6 +144,17 @@ SCASML_API int scasml_uz_solve(const scasml_gp* gp, const scasml_picard_params* 
 /* jnp.clip(output_uz, -c, c) of solvers/ScaSML.py:284 (NaN preserved), in place */
 SCASML_API int scasml_clip(double* x_dev, long long count, double c, void* stream);
 
+/* The one collective of the path (the reference has no multi-GPU path -- north star: "correction samples are sharded across
+ * the GPUs of one box, and a single NCCL allreduce over NVLink combines the per-level sums"): sum the per-rank partial (u, z) blocks that
+ * scasml_uz_solve leaves with world > 1, in place, then scasml_clip.  One process per GPU; rank 0 creates the 128-byte id and the host
+ * side hands it to the other ranks (file, pipe, MPI ...); scasml_comm_init binds the CURRENT CUDA device.  NCCL is loaded at run time
+ * (libnccl.so.2).  The Python classes use torch.distributed for the same all-reduce; these entry points are for hosts without it. */
+typedef struct scasml_comm scasml_comm;
+SCASML_API int scasml_comm_unique_id(unsigned char* id128_host);
+SCASML_API int scasml_comm_init(const unsigned char* id128_host, int rank, int world, scasml_comm** out);
+SCASML_API int scasml_allreduce_partial(scasml_comm* comm, double* buf_dev, long long count, void* stream);
+SCASML_API int scasml_comm_destroy(scasml_comm* comm);
+
 /* 1 if this handle can use SCASML_ROUTE_TC (d <= 1022: resident-operand kernel up to d = 126, K-streamed kernel above) */
 SCASML_API int scasml_gp_tc_supported(const scasml_gp* gp);
 

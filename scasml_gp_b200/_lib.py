@@ -39,6 +39,10 @@ _SIGNATURES = {
     "scasml_last_error": (C.c_char_p, []),
     "scasml_abi_version": (C.c_int, []),
     "scasml_set_normal_table": (C.c_int, [C.c_void_p]),
+    "scasml_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "scasml_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "scasml_allreduce_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "scasml_comm_destroy": (C.c_int, [C.c_void_p]),
     "scasml_geometry_points": (C.c_int, [C.c_uint, C.c_uint, C.c_longlong, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "scasml_equation_g": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
@@ -223,6 +227,44 @@ def to_device_sharded(a, rank, world, dist):
         part[mine.shape[0]:].zero_()
     dist.all_gather_into_tensor(full, part.clone())
     return full[:B]
+
+
+class AbiComm(object):
+    """The path's all-reduce through the C ABI (scasml_comm_*: NCCL loaded by the library) instead of torch.distributed -- what a host without
+    PyTorch's process groups would do.  One process per GPU; rank 0 calls AbiComm.unique_id() and hands the 128 bytes to the other ranks.
+    Assign to `solver.comm`; the solver then shards its sample units over `world` ranks and sums the partial blocks with all_reduce()."""
+
+    class ReduceOp(object):
+        SUM = "sum"
+
+    def __init__(self, id_bytes, rank, world):
+        self.rank, self.world = int(rank), int(world)
+        torch_cuda()
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id_bytes))
+        h = C.c_void_p()
+        check(load().scasml_comm_init(buf, self.rank, self.world, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        check(load().scasml_comm_unique_id(buf))
+        return bytes(buf)
+
+    def all_reduce(self, t, op=None):
+        assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.float64"
+        check(load().scasml_allreduce_partial(self._h, ptr(t), t.numel(), stream_ptr()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().scasml_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ptr(t):

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscasml_b200.so")
 LIB_DBG = os.path.join(HERE, "libscasml_b200_dbg.so")
-SOURCES = ["abi.cu", "gp_eval.cu", "gp_eval_tc.cu", "gp_fit.cu", "picard.cu"]
+SOURCES = ["abi.cu", "comm.cu", "gp_eval.cu", "gp_eval_tc.cu", "gp_fit.cu", "picard.cu"]
 # debug library: objects shared with the product except the files that look at SCASML_DEBUG_HOOKS
 DBG_ONLY = ["abi_debug.cu", "tc_bench.cu"]
 DBG_REBUILT = ["gp_eval_tc.cu"]
@@ -58,8 +58,8 @@ def build(force=False, verbose=False):
     obj = {(src, bool(extra)): o for src, extra, o in jobs}
     prod = [obj[(s, False)] for s in SOURCES]
     dbg = [obj[(s, True)] if s in DBG_REBUILT else obj[(s, False)] for s in SOURCES] + [obj[(s, True)] for s in DBG_ONLY]
-    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *prod, "-lcudart"], check=True)
-    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB_DBG, *dbg, "-lcudart"], check=True)
+    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *prod, "-lcudart", "-ldl"], check=True)
+    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB_DBG, *dbg, "-lcudart", "-ldl"], check=True)
     return LIB
 
 

@@ -180,6 +180,9 @@ class PicardSolverBase(object):
         return ws.value, st
 
     def _dist(self):
+        comm = getattr(self, "comm", None)
+        if comm is not None:                                  # _lib.AbiComm: the all-reduce through the C ABI
+            return comm.rank, comm.world, comm
         if not self.distributed:
             return 0, 1, None
         import torch.distributed as dist
@@ -265,7 +268,7 @@ class PicardSolverBase(object):
     def _u_solve(self, n, rho, x_t, M=None):
         rank, world, dist = self._dist()
         # one host -> device copy serves the correction and u_hat; sharded runs stage a row slice per rank and all-gather it
-        x_dev = _lib.to_device_sharded(x_t, rank, world, dist) if world > 1 else _lib.to_device(x_t)
+        x_dev = _lib.to_device_sharded(x_t, rank, world, dist) if (world > 1 and hasattr(dist, "all_gather_into_tensor")) else _lib.to_device(x_t)
         if self.scasml:
             out, uh = self._uz_device(n, rho, x_dev, M, with_u_hat=True)   # top-level u_hat(x): GP.route (FP64 by default)
         else:

@@ -389,3 +389,51 @@ def test_sampler_column_pass_variants_through_the_mlp_solvers(d):
     _check_solver(prod, orac, (2, 2, X), (2, 2, X), X, exact)
     prod, orac = P["MLPfh"](eq), MLPFullHistoryOracle(eq_o, cast=False)
     _check_solver(prod, orac, (2, None, X, 3), (2, None, X, 3), X, exact)
+
+
+def _abi_comm_worker(rank, world, idfile, q):
+    import os, time
+    import torch
+    torch.cuda.set_device(rank)
+    P = _product()
+    lib = P["lib"]
+    if rank == 0:
+        with open(idfile + ".tmp", "wb") as f:
+            f.write(lib.AbiComm.unique_id())
+        os.replace(idfile + ".tmp", idfile)
+    while not os.path.exists(idfile):
+        time.sleep(0.01)
+    comm = lib.AbiComm(open(idfile, "rb").read(), rank, world)
+    F = Fitted(d=6, nd=40, nb=12)
+    F.gp.set_right_vector(F.gp_o.right_vector)
+    X = F.test_points(9, 3)
+    one = P["ScaSML"](F.eq, F.gp)
+    one.u_solve(2, 2, X)
+    many = P["ScaSML"](F.eq, F.gp)
+    many.comm = comm
+    many.u_solve(2, 2, X)
+    diff = float(np.nanmax(np.abs(many.last_raw - one.last_raw)))
+    same = bool(np.array_equal(np.isnan(many.last_raw), np.isnan(one.last_raw))) and many.evaluation_counter == one.evaluation_counter
+    torch.cuda.synchronize()
+    comm.close()
+    q.put((rank, diff, same))
+
+
+def test_allreduce_through_the_c_abi_reproduces_the_single_gpu_solve(tmp_path):
+    """scasml_comm_* (NCCL loaded by the library): two processes, one GPU each, the sample units of a level-2 solve sharded over them and
+    the partial (u, z) blocks summed by scasml_allreduce_partial -- no torch.distributed."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    idfile = str(tmp_path / "nccl_id")
+    procs = [ctx.Process(target=_abi_comm_worker, args=(r, 2, idfile, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, diff, same in res:
+        assert same and diff < 1e-12, (rank, diff, same)
