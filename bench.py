@@ -430,8 +430,13 @@ def main():
     # HBM-bound kernels of the step (samplers write, reduction reads the level point buffers: (d+1) * 8 B per sample point)
     hbm_peak = peaks.get("hbm_gbs", 6554.0) if peaks else 6554.0
     pt_bytes = (d + 1) * 8.0 * float(stats["executed_points"])
-    hbm = {"unit": "GB/s", "peak": hbm_peak, "bytes_per_point": (d + 1) * 8,
-           "sampler": {"achieved": pt_bytes / max(tstats["sample_time_ns"], 1), "frac": pt_bytes / max(tstats["sample_time_ns"], 1) / hbm_peak},
+    # what the samplers write per point: the FP64 row + its global id, and on the resident-operand tcgen05 route (d + 2 <= 128) the operand record
+    # (16 nstep words + 16 B) and the 96-byte feature block of the evaluation kernel (csrc/gp_tc.cuh)
+    nstep = next((k for k in (2, 4, 7, 8) if k >= -(-(d + 2) // 16)), 0)
+    samp_bpp = (d + 1) * 8 + 8 + ((nstep * 64 + 16 + 96) if (route == "tc" and nstep) else 0)
+    samp_bytes = float(samp_bpp) * float(stats["executed_points"])
+    hbm = {"unit": "GB/s", "peak": hbm_peak, "bytes_per_point": (d + 1) * 8, "sampler_bytes_per_point": samp_bpp,
+           "sampler": {"achieved": samp_bytes / max(tstats["sample_time_ns"], 1), "frac": samp_bytes / max(tstats["sample_time_ns"], 1) / hbm_peak},
            "reduction": {"achieved": pt_bytes / max(tstats["reduce_time_ns"], 1), "frac": pt_bytes / max(tstats["reduce_time_ns"], 1) / hbm_peak}}
     roofline["hbm_kernels"] = hbm
 
